@@ -1,0 +1,128 @@
+"""ctypes binding of oracle/liboracle.so (gravity_oracle.c, our CPU restatement of the reference algorithm).
+TEST INFRASTRUCTURE ONLY -- see the header of gravity_oracle.c for who may import this."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liboracle.so")
+
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "gravity_oracle.c")
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "oracle"])
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build())
+        L.orc_create.restype = C.c_void_p
+        L.orc_create.argtypes = [C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_void_p, _dp]
+        L.orc_destroy.argtypes = [C.c_void_p]
+        L.orc_build_tree.restype = C.c_double
+        L.orc_build_tree.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int]
+        L.orc_num_nodes.argtypes = [C.c_void_p]
+        L.orc_root.argtypes = [C.c_void_p]
+        L.orc_export_nodes.argtypes = [C.c_void_p] + [_dp] * 7 + [_ip] * 5
+        L.orc_export_particles.argtypes = [C.c_void_p, _ip, _dp, _dp, _dp, _dp, _dp, _ip]
+        L.orc_export_root.argtypes = [C.c_void_p, _dp]
+        L.orc_import_tree.argtypes = [C.c_void_p, C.c_int, C.c_int] + [_dp] * 6 + [_ip] * 4 + [_dp]
+        L.orc_ewald_table.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_int]
+        L.orc_gravity.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+                                  _dp, _dp, _dp, _dp, _ip, _dp, C.c_int, C.c_int]
+        L.orc_bucket_lists.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _ip, C.c_void_p, C.c_int,
+                                       C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        _lib = L
+    return _lib
+
+
+class OracleGravity:
+    """Same surface as oracle.reflib.RefGravity, backed by our restatement."""
+
+    def __init__(self, p, active=None, tree=None):
+        """p: Particles (input order) -- or, with `tree` (dict as returned by .tree()), the particles are taken from
+        the tree (already in tree order) and the tree is imported instead of built."""
+        L = lib()
+        self.period = np.array(p.period if tree is None else tree["period"], dtype=np.float64)
+        act = None
+        if tree is not None:
+            self.n = len(tree["x"])
+            self._act = np.ascontiguousarray(tree["active"], dtype=np.int32)
+            act = self._act.ctypes.data_as(C.c_void_p)
+            cols = [np.ascontiguousarray(tree[k], dtype=np.float64) for k in ("x", "y", "z", "m", "h")]
+        else:
+            self.n = p.n
+            if active is not None:
+                self._act = np.ascontiguousarray(active, dtype=np.int32)
+                act = self._act.ctypes.data_as(C.c_void_p)
+            cols = [np.ascontiguousarray(a, dtype=np.float64) for a in (p.x, p.y, p.z, p.m, p.h)]
+        self.h = L.orc_create(self.n, *cols, act, self.period)
+        if tree is not None:
+            c = lambda k, dt: np.ascontiguousarray(tree[k], dtype=dt)
+            L.orc_import_tree(self.h, int(tree["nNodes"]), int(tree["iRoot"]), c("bnd", np.float64),
+                              c("r", np.float64), c("fMass", np.float64), c("fSoft", np.float64),
+                              c("fOpen2", np.float64), c("mom", np.float64), c("pLower", np.int32),
+                              c("pUpper", np.int32), c("iLower", np.int32), c("iUpper", np.int32),
+                              c("root", np.float64))
+
+    def close(self):
+        if self.h:
+            lib().orc_destroy(self.h)
+            self.h = None
+
+    def build_tree(self, nBucket=8, theta=0.7, iOrder=4):
+        self.t_build = lib().orc_build_tree(self.h, nBucket, theta, iOrder)
+        return self.t_build
+
+    def tree(self):
+        L = lib()
+        nn = L.orc_num_nodes(self.h)
+        t = dict(nNodes=nn, iRoot=L.orc_root(self.h), period=self.period.copy(),
+                 bnd=np.zeros((nn, 6)), r=np.zeros((nn, 3)), fMass=np.zeros(nn), fSoft=np.zeros(nn),
+                 fOpen2=np.zeros(nn), mom=np.zeros((nn, 31)), bmax=np.zeros(nn),
+                 pLower=np.zeros(nn, np.int32), pUpper=np.zeros(nn, np.int32),
+                 iLower=np.zeros(nn, np.int32), iUpper=np.zeros(nn, np.int32), iDim=np.zeros(nn, np.int32))
+        L.orc_export_nodes(self.h, t["bnd"], t["r"], t["fMass"], t["fSoft"], t["fOpen2"], t["mom"], t["bmax"],
+                           t["pLower"], t["pUpper"], t["iLower"], t["iUpper"], t["iDim"])
+        n = self.n
+        t.update(iOrder=np.zeros(n, np.int32), x=np.zeros(n), y=np.zeros(n), z=np.zeros(n), m=np.zeros(n),
+                 h=np.zeros(n), active=np.zeros(n, np.int32))
+        L.orc_export_particles(self.h, t["iOrder"], t["x"], t["y"], t["z"], t["m"], t["h"], t["active"])
+        t["root"] = np.zeros(35)
+        L.orc_export_root(self.h, t["root"])
+        return t
+
+    def ewald_table(self, fhCut=2.8, iOrder=4):
+        buf = np.zeros((4096, 5))
+        n = lib().orc_ewald_table(self.h, fhCut, iOrder, buf.ctypes.data, 4096)
+        return buf[:n].copy()
+
+    def gravity(self, nReps, bPeriodic, iOrder=4, bEwald=1, iEwOrder=4, dEwCut=2.6, dEwhCut=2.8, walk_only=False,
+                threads=0):
+        L = lib()
+        n, nn = self.n, L.orc_num_nodes(self.h)
+        acc = np.zeros((n, 3)); pot = np.zeros(n); dt = np.zeros(n); w = np.zeros(n)
+        counts = np.zeros((nn, 3), np.int32); stats = np.zeros(8)
+        L.orc_gravity(self.h, nReps, bPeriodic, iOrder, bEwald, iEwOrder, dEwCut, dEwhCut, acc, pot, dt, w, counts,
+                      stats, int(walk_only), threads)
+        return dict(acc=acc, pot=pot, dtGrav=dt, fWeight=w, counts=counts, nActive=int(stats[0]),
+                    dPartSum=float(stats[1]), dCellSum=float(stats[2]), dSoftSum=float(stats[3]),
+                    dFlop=float(stats[4]), seconds=float(stats[5]))
+
+    def bucket_lists(self, iBucket, nReps, iOrder=4, nmax=20000):
+        n3 = np.zeros(3, np.int32)
+        ilp = np.zeros((nmax, 5)); ilcs = np.zeros((nmax, 11)); ilcn = np.zeros((nmax, 35))
+        lib().orc_bucket_lists(self.h, iBucket, nReps, iOrder, n3, ilp.ctypes.data, nmax, ilcs.ctypes.data, nmax,
+                               ilcn.ctypes.data, nmax)
+        return ilp[:n3[0]].copy(), ilcs[:n3[1]].copy(), ilcn[:n3[2]].copy()

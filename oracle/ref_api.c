@@ -1,0 +1,291 @@
+/*
+ * ref_api.c -- ctypes-friendly driver around the UNMODIFIED reference objects (oracle/_ref/libgasref.so).
+ *
+ * TEST INFRASTRUCTURE ONLY (oracle): compiled by oracle/Makefile against the headers in /root/reference,
+ * never linked or loaded by the product path.  It calls the reference's own pstBuildTree / pstColCells /
+ * pstDistribCells / pstCalcRoot / pstDistribRoot / pstGravity on a single-rank PST, i.e. exactly the
+ * sequence msrBuildTree (master.c:4249-4310) + msrGravity (master.c:5869) run, and exports
+ *   - the reference's tree, field by field (never assuming raw KDN layout),
+ *   - per-bucket interaction-list counts, captured with a linker --wrap around pkdBucketWalk
+ *     (the reference itself only reports sums, pkd.c:2945-2949),
+ *   - per-particle a, fPot, dtGrav, fWeight after pkdGravAll (pkd.c:2868).
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <sys/time.h>
+#include "pst.h"
+#include "pkd.h"
+#include "walk.h"
+#include "grav.h"
+#include "ewald.h"
+#include "opentype.h"
+
+typedef struct {
+    MDL mdl;
+    PST pst;
+    LCL lcl;
+    PKD pkd;
+    int n;
+} REF;
+
+/* ---- per-bucket counts: --wrap=pkdBucketWalk -------------------------------------------------- */
+static int *g_counts = NULL; /* 3 ints per node, indexed by iBucket */
+static int g_nCounts = 0;
+static FILE *g_fpCounts = NULL; /* multi-rank binary: REF_DUMP_COUNTS=prefix */
+void __real_pkdBucketWalk(PKD pkd, int iBucket, int nReps, int iOrder);
+void __wrap_pkdBucketWalk(PKD pkd, int iBucket, int nReps, int iOrder) {
+    __real_pkdBucketWalk(pkd, iBucket, nReps, iOrder);
+    if (g_counts && iBucket < g_nCounts) {
+        g_counts[3 * iBucket + 0] = pkd->nPart;
+        g_counts[3 * iBucket + 1] = pkd->nCellSoft;
+        g_counts[3 * iBucket + 2] = pkd->nCellNewt;
+    }
+}
+
+static double wallclock(void) {
+    struct timeval tv;
+    gettimeofday(&tv, NULL);
+    return tv.tv_sec + 1e-6 * tv.tv_usec;
+}
+
+REF *ref_create(int n, const double *x, const double *y, const double *z, const double *m, const double *h,
+                const int *active, const double *fPeriod) {
+    REF *r = calloc(1, sizeof(REF));
+    FLOAT per[3];
+    int i;
+    char *argv[2] = {"ref", NULL};
+    mdlInitialize(&r->mdl, argv, NULL);
+    assert(mdlThreads(r->mdl) == 1);
+    r->lcl.pszDataPath = NULL;
+    r->lcl.pkd = NULL;
+    pstInitialize(&r->pst, r->mdl, &r->lcl);
+    for (i = 0; i < 3; ++i) per[i] = fPeriod[i];
+    pkdInitialize(&r->pkd, r->mdl, 4, n, 1, per, -FLOAT_MAXVAL, FLOAT_MAXVAL, n, 0, 0);
+    r->lcl.pkd = r->pkd;
+    r->n = n;
+    memset(r->pkd->pStore, 0, (size_t)(n + 1) * sizeof(PARTICLE));
+    for (i = 0; i < n; ++i) {
+        PARTICLE *p = &r->pkd->pStore[i];
+        p->iOrder = i;
+        p->iActive = TYPE_DARK | TYPE_TREEACTIVE | ((!active || active[i]) ? TYPE_ACTIVE : 0);
+        p->fMass = m[i];
+        p->fSoft = h[i];
+        p->fSoft0 = h[i];
+        p->r[0] = x[i];
+        p->r[1] = y[i];
+        p->r[2] = z[i];
+        p->fWeight = 1.0;
+    }
+    r->pkd->nLocal = n;
+    r->pkd->nActive = n;
+    r->pkd->nTreeActive = n;
+    return r;
+}
+
+void ref_destroy(REF *r) {
+    pstFinish(r->pst);
+    free(r);
+}
+
+/* msrBuildTree (master.c:4249) for one rank; iOpenType = OPEN_JOSH, dCrit = theta (master.c:1897-1934). */
+double ref_build_tree(REF *r, int nBucket, double dTheta, int iOrder) {
+    struct inBuildTree in;
+    struct outBuildTree out;
+    struct inColCells inc;
+    struct ioCalcRoot root;
+    KDN *pkdn;
+    int iDum, nCell;
+    double t0 = wallclock();
+
+    pkdActiveTypeOrder(r->pkd, TYPE_ACTIVE | TYPE_TREEACTIVE); /* msrActiveTypeOrder, master.c:4263 */
+    in.nBucket = nBucket;
+    in.iOpenType = OPEN_JOSH;
+    in.iOrder = iOrder;
+    in.dCrit = dTheta;
+    in.bActiveOnly = 0;
+    in.bTreeActiveOnly = 0;
+    in.bBinary = 1;
+    in.bGravity = 1;
+    pstBuildTree(r->pst, &in, sizeof(in), &out, &iDum);
+    nCell = 1 << (1 + (int)ceil(log((double)1) / log(2.0)));
+    pkdn = malloc(nCell * sizeof(KDN));
+    inc.iCell = ROOT;
+    inc.nCell = nCell;
+    pstColCells(r->pst, &inc, sizeof(inc), pkdn, NULL);
+    pstDistribCells(r->pst, pkdn, nCell * sizeof(KDN), NULL, NULL);
+    free(pkdn);
+    pstCalcRoot(r->pst, NULL, 0, &root, &iDum);
+    pstDistribRoot(r->pst, &root, sizeof(struct ioCalcRoot), NULL, NULL);
+    return wallclock() - t0;
+}
+
+int ref_num_nodes(REF *r) { return r->pkd->nNodes; }
+int ref_root(REF *r) { return r->pkd->iRoot; }
+
+/* Field-wise export of kdNodes[0..nNodes) into SoA arrays (mom: 31 doubles Q6,O10,H15; bmom: Bmax,B2..B6). */
+void ref_export_nodes(REF *r, double *bnd, double *rc, double *fMass, double *fSoft, double *fOpen2,
+                      double *mom, double *bmom, int *pLower, int *pUpper, int *iLower, int *iUpper,
+                      int *iDim) {
+    int i, j, nn = r->pkd->nNodes;
+    for (i = 0; i < nn; ++i) {
+        KDN *c = &r->pkd->kdNodes[i];
+        double *q = &mom[31 * (size_t)i];
+        for (j = 0; j < 3; ++j) {
+            bnd[6 * (size_t)i + j] = c->bnd.fMin[j];
+            bnd[6 * (size_t)i + 3 + j] = c->bnd.fMax[j];
+            rc[3 * (size_t)i + j] = c->r[j];
+        }
+        fMass[i] = c->fMass;
+        fSoft[i] = c->fSoft;
+        fOpen2[i] = c->fOpen2;
+        q[0] = c->mom.Qxx; q[1] = c->mom.Qyy; q[2] = c->mom.Qzz;
+        q[3] = c->mom.Qxy; q[4] = c->mom.Qxz; q[5] = c->mom.Qyz;
+        q[6] = c->mom.Oxxx; q[7] = c->mom.Oxyy; q[8] = c->mom.Oxxy; q[9] = c->mom.Oyyy;
+        q[10] = c->mom.Oxxz; q[11] = c->mom.Oyyz; q[12] = c->mom.Oxyz; q[13] = c->mom.Oxzz;
+        q[14] = c->mom.Oyzz; q[15] = c->mom.Ozzz;
+        q[16] = c->mom.Hxxxx; q[17] = c->mom.Hxyyy; q[18] = c->mom.Hxxxy; q[19] = c->mom.Hyyyy;
+        q[20] = c->mom.Hxxxz; q[21] = c->mom.Hyyyz; q[22] = c->mom.Hxxyy; q[23] = c->mom.Hxxyz;
+        q[24] = c->mom.Hxyyz; q[25] = c->mom.Hxxzz; q[26] = c->mom.Hxyzz; q[27] = c->mom.Hxzzz;
+        q[28] = c->mom.Hyyzz; q[29] = c->mom.Hyzzz; q[30] = c->mom.Hzzzz;
+        if (bmom) {
+            double *b = &bmom[6 * (size_t)i];
+            b[0] = c->mom.Bmax; b[1] = c->mom.B2; b[2] = c->mom.B3;
+            b[3] = c->mom.B4; b[4] = c->mom.B5; b[5] = c->mom.B6;
+        }
+        pLower[i] = c->pLower;
+        pUpper[i] = c->pUpper;
+        iLower[i] = c->iLower;
+        iUpper[i] = c->iUpper;
+        if (iDim) iDim[i] = c->iDim;
+    }
+}
+
+/* Particles in the reference's tree order. */
+void ref_export_particles(REF *r, int *iOrder, double *x, double *y, double *z, double *m, double *h,
+                          int *active) {
+    int i;
+    for (i = 0; i < r->n; ++i) {
+        PARTICLE *p = &r->pkd->pStore[i];
+        iOrder[i] = p->iOrder;
+        x[i] = p->r[0];
+        y[i] = p->r[1];
+        z[i] = p->r[2];
+        m[i] = p->fMass;
+        h[i] = p->fSoft;
+        if (active) active[i] = TYPEQueryACTIVE(p) ? 1 : 0;
+    }
+}
+
+/* pkd->ilcnRoot in ILCN field order (pkd.h:481-494): m,x,y,z,xx,yy,xy,xz,yz,zz, 10 octopole, 15 hexadecapole */
+void ref_export_root(REF *r, double *out35) { memcpy(out35, &r->pkd->ilcnRoot, 35 * sizeof(double)); }
+
+int ref_ewald_table(REF *r, double fhCut, int iOrder, double *ewt5, int nMax) {
+    int i;
+    pkdEwaldInit(r->pkd, fhCut, iOrder);
+    for (i = 0; i < r->pkd->nEwhLoop && i < nMax; ++i) {
+        ewt5[5 * i + 0] = r->pkd->ewt[i].hx;
+        ewt5[5 * i + 1] = r->pkd->ewt[i].hy;
+        ewt5[5 * i + 2] = r->pkd->ewt[i].hz;
+        ewt5[5 * i + 3] = r->pkd->ewt[i].hCfac;
+        ewt5[5 * i + 4] = r->pkd->ewt[i].hSfac;
+    }
+    return r->pkd->nEwhLoop;
+}
+
+/*
+ * pkdInitAccel (pkd.c:5443) + pstGravity -> pkdGravAll (pst.c:3248, pkd.c:2868).
+ * counts: 3 ints per node (nPart,nCellSoft,nCellNewt), filled for buckets with an active sink, else -1.
+ * stats[0..7] = nActive, dPartSum, dCellSum, dSoftSum, dFlop, wallclock seconds of pstGravity, 0, 0.
+ * Outputs are in the reference's tree order (see ref_export_particles).
+ */
+void ref_gravity(REF *r, int nReps, int bPeriodic, int iOrder, int bEwald, int iEwOrder, double dEwCut,
+                 double dEwhCut, double *acc3, double *pot, double *dtGrav, double *fWeight, int *counts,
+                 double *stats) {
+    struct inGravity in;
+    struct outGravity out;
+    int i, iDum;
+    double t0;
+    memset(&in, 0, sizeof(in));
+    in.nReps = nReps;
+    in.bPeriodic = bPeriodic;
+    in.iOrder = iOrder;
+    in.bEwald = bEwald;
+    in.iEwOrder = iEwOrder;
+    in.bComove = 0;
+    in.bDoSun = 0;
+    in.dSunSoft = 0.0;
+    in.dEwCut = dEwCut;
+    in.dEwhCut = dEwhCut;
+    in.dRhoFac = 0.0;
+    pkdInitAccel(r->pkd);
+    g_counts = counts;
+    g_nCounts = r->pkd->nNodes;
+    if (counts)
+        for (i = 0; i < 3 * g_nCounts; ++i) counts[i] = -1;
+    t0 = wallclock();
+    pstGravity(r->pst, &in, sizeof(in), &out, &iDum);
+    stats[5] = wallclock() - t0;
+    g_counts = NULL;
+    stats[0] = out.nActive;
+    stats[1] = out.dPartSum;
+    stats[2] = out.dCellSum;
+    stats[3] = out.dSoftSum;
+    stats[4] = out.dFlop;
+    stats[6] = stats[7] = 0.0;
+    for (i = 0; i < r->n; ++i) {
+        PARTICLE *p = &r->pkd->pStore[i];
+        acc3[3 * (size_t)i + 0] = p->a[0];
+        acc3[3 * (size_t)i + 1] = p->a[1];
+        acc3[3 * (size_t)i + 2] = p->a[2];
+        pot[i] = p->fPot;
+        dtGrav[i] = p->dtGrav;
+        fWeight[i] = p->fWeight;
+    }
+}
+
+/*
+ * One bucket's lists, straight from pkdBucketWalk (walk.c:306) with the active-bbox swap pkdGravAll
+ * performs around it (pkd.c:2916-2944).  ilp: 5 doubles (m,h,x,y,z); ilcs: 11; ilcn: 35.
+ */
+void ref_bucket_lists(REF *r, int iBucket, int nReps, int iOrder, int *n3, double *ilp, int nMaxP,
+                      double *ilcs, int nMaxS, double *ilcn, int nMaxN) {
+    PKD pkd = r->pkd;
+    KDN *c = pkd->kdNodes;
+    BND bndActive, bndTmp;
+    int i, j;
+    for (j = 0; j < 3; ++j) {
+        bndActive.fMin[j] = FLOAT_MAXVAL;
+        bndActive.fMax[j] = -FLOAT_MAXVAL;
+    }
+    for (i = c[iBucket].pLower; i <= c[iBucket].pUpper; ++i) {
+        if (!TYPEQueryACTIVE(&pkd->pStore[i])) continue;
+        for (j = 0; j < 3; ++j) {
+            if (pkd->pStore[i].r[j] < bndActive.fMin[j]) bndActive.fMin[j] = pkd->pStore[i].r[j];
+            if (pkd->pStore[i].r[j] > bndActive.fMax[j]) bndActive.fMax[j] = pkd->pStore[i].r[j];
+        }
+    }
+    bndTmp = c[iBucket].bnd;
+    c[iBucket].bnd = bndActive;
+    __real_pkdBucketWalk(pkd, iBucket, nReps, iOrder);
+    c[iBucket].bnd = bndTmp;
+    n3[0] = pkd->nPart;
+    n3[1] = pkd->nCellSoft;
+    n3[2] = pkd->nCellNewt;
+    if (ilp) memcpy(ilp, pkd->ilp, sizeof(ILP) * (size_t)(pkd->nPart < nMaxP ? pkd->nPart : nMaxP));
+    if (ilcs) memcpy(ilcs, pkd->ilcs, sizeof(ILCS) * (size_t)(pkd->nCellSoft < nMaxS ? pkd->nCellSoft : nMaxS));
+    if (ilcn) memcpy(ilcn, pkd->ilcn, sizeof(ILCN) * (size_t)(pkd->nCellNewt < nMaxN ? pkd->nCellNewt : nMaxN));
+}
+
+int ref_sizeof(int which) {
+    switch (which) {
+    case 0: return (int)sizeof(PARTICLE);
+    case 1: return (int)sizeof(KDN);
+    case 2: return (int)sizeof(ILP);
+    case 3: return (int)sizeof(ILCS);
+    case 4: return (int)sizeof(ILCN);
+    case 5: return (int)sizeof(EWT);
+    }
+    return -1;
+}
