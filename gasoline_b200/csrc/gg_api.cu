@@ -1,0 +1,744 @@
+// gg_api.cu -- the C ABI (include/gasoline_b200.h): context, ingestion of the host's tree/particles into the
+// device layout, and the orchestration of one force evaluation (= pkdGravAll, pkd.c:2868-3060).
+#include <cub/device/device_scan.cuh>
+#include <float.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "gg_internal.h"
+
+void gg_ewald_table_host(const double *root, double L, double fhCut, int iOrder, std::vector<double> &ewt);
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    fprintf(stderr, "gasoline_b200: %s\n", g_err);
+    return code;
+}
+
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(GG_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct Domain {
+    int id, nNodes, nPart, iRoot, nodeBase, partBase;
+};
+
+} // namespace
+
+struct gg_context {
+    int device = 0, nSM = 0;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[6];
+    // layout
+    int idSelf = 0;
+    std::vector<Domain> dom; // dom[0] = local
+    int nNodesAll = 0, nPartAll = 0, maxBucket = 1;
+    bool haveRoot = false;
+    double root[GG_NROOT];
+    // top tree (host copy, packed at gravity time)
+    int nTop = 0;
+    std::vector<int> topLower, topUsed;
+    std::vector<double> topR, topMass, topSoft, topOpen2, topMom;
+    std::vector<int> hActive; // host copy of the local ACTIVE flags (empty = all active)
+    // device buffers
+    DevBuf nodes, momf, momq, parts, active, hsoft, tasks, ngroups, goffs, counts, acc, pot, dtg, fweight, nloop, sums,
+        misc, imgoff, ewt, raw, rawi, cubtmp;
+    void *pinned = nullptr;
+    size_t pinnedCap = 0;
+    int nTasks = 0;
+    int nLaunches = 0;
+};
+
+namespace {
+
+int ensure(gg_context *c, DevBuf &b, size_t bytes, size_t preserve = 0) {
+    if (bytes <= b.cap) return GG_OK;
+    size_t cap = bytes + bytes / 4 + 256;
+    void *np = nullptr;
+    CK(cudaMalloc(&np, cap));
+    if (preserve && b.p) CK(cudaMemcpyAsync(np, b.p, preserve, cudaMemcpyDeviceToDevice, c->st));
+    if (b.p) {
+        CK(cudaStreamSynchronize(c->st));
+        CK(cudaFree(b.p));
+    }
+    b.p = np;
+    b.cap = cap;
+    return GG_OK;
+}
+
+int ensure_pinned(gg_context *c, size_t bytes) {
+    if (bytes <= c->pinnedCap) return GG_OK;
+    if (c->pinned) CK(cudaFreeHost(c->pinned));
+    c->pinned = nullptr;
+    c->pinnedCap = 0;
+    CK(cudaMallocHost(&c->pinned, bytes + bytes / 4));
+    c->pinnedCap = bytes + bytes / 4;
+    return GG_OK;
+}
+
+// raw staging layout for one domain (doubles): r[3n] fMass[n] fSoft[n] fOpen2[n] mom[31n]; ints: pLower pUpper
+// iLower iUpper [n each]
+__global__ void k_pack_nodes(int n, const double *r, const double *fMass, const double *fSoft, const double *fOpen2,
+                             const double *mom, const int *pLower, const int *pUpper, const int *iLower,
+                             const int *iUpper, int nodeBase, int partBase, NodeW *nodes, float4 *momf, double *momq) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    NodeW w;
+    w.rx = r[3 * (size_t)i]; w.ry = r[3 * (size_t)i + 1]; w.rz = r[3 * (size_t)i + 2];
+    w.fOpen2 = fOpen2[i]; w.fSoft = fSoft[i]; w.fMass = fMass[i];
+    int c0 = iLower[i], c1 = -1;
+    if (c0 >= 0) { // second child = the first child's "next", unless that is already this cell's own next
+        int cand = iUpper[c0];
+        if (cand >= 0 && cand != iUpper[i]) c1 = cand;
+    }
+    w.c0 = c0 >= 0 ? c0 + nodeBase : -1;
+    w.c1 = c1 >= 0 ? c1 + nodeBase : -1;
+    w.pLower = pLower[i] + partBase;
+    w.nP = pUpper[i] - pLower[i] + 1;
+    if (w.nP < 0) w.nP = 0;
+    nodes[nodeBase + i] = w;
+    const double *q = &mom[(size_t)GG_NMOM * i];
+    double tr = q[0] + q[1] + q[2]; // traceless at list-build time, walk.c:41-48
+    float f[32];
+    f[0] = (float)(q[0] - tr / 3.0); f[1] = (float)(q[1] - tr / 3.0); f[2] = (float)(q[2] - tr / 3.0);
+    f[3] = (float)q[3]; f[4] = (float)q[4]; f[5] = (float)q[5];
+#pragma unroll
+    for (int k = 6; k < GG_NMOM; ++k) f[k] = (float)q[k];
+    f[31] = 0.f;
+    float4 *o = &momf[(size_t)(nodeBase + i) * 8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
+    double *oq = &momq[(size_t)(nodeBase + i) * 6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) oq[k] = q[k];
+}
+
+__global__ void k_pack_parts(int n, const double *x, const double *y, const double *z, const double *m,
+                             const double *h, int partBase, PartS *parts, double *hsoft) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PartS p;
+    p.x = x[i]; p.y = y[i]; p.z = z[i];
+    p.m = (float)m[i]; p.h = (float)h[i];
+    parts[partBase + i] = p;
+    if (hsoft) hsoft[i] = h[i];
+}
+
+// number of 8-sink passes each local bucket needs (0 for cells and for buckets without an active sink)
+__global__ void k_count_groups(int nNodes, const NodeW *nodes, const int *active, int *ngroups) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nNodes) return;
+    NodeW w = nodes[i];
+    int g = 0;
+    if (w.c0 < 0) {
+        int n = 0;
+        if (active) {
+            for (int j = 0; j < w.nP; ++j) n += active[w.pLower + j] != 0;
+        } else n = w.nP;
+        g = (n + GG_MAX_SINKS - 1) / GG_MAX_SINKS;
+    }
+    ngroups[i] = g;
+}
+
+__global__ void k_fill_tasks(int nNodes, const int *ngroups, const int *offs, Task *tasks) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nNodes) return;
+    for (int g = 0; g < ngroups[i]; ++g) tasks[offs[i] + g] = Task{i, g};
+}
+
+// Uniform background for comoving, non-periodic runs (pkd.c:2967-2991).
+__global__ void k_comove(int n, const PartS *parts, const int *active, double dRhoFac, double *acc, double *pot) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || (active && !active[i])) return;
+    PartS p = parts[i];
+    double r2 = p.x * p.x + p.y * p.y + p.z * p.z;
+    acc[3 * (size_t)i] += dRhoFac * p.x;
+    acc[3 * (size_t)i + 1] += dRhoFac * p.y;
+    acc[3 * (size_t)i + 2] += dRhoFac * p.z;
+    pot[i] -= 0.5 * dRhoFac * r2;
+}
+
+int upload_domain(gg_context *c, const gg_tree *t, const gg_particles *pp, int nodeBase, int partBase, bool local,
+                  bool onDevice) {
+    const int nn = t->nNodes, np = pp->n;
+    const cudaMemcpyKind kind = onDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    size_t nd = (size_t)nn * (3 + 3 + GG_NMOM) + (size_t)np * 5;
+    int rc;
+    if ((rc = ensure(c, c->raw, nd * sizeof(double)))) return rc;
+    if ((rc = ensure(c, c->rawi, (size_t)nn * 4 * sizeof(int)))) return rc;
+    double *d = (double *)c->raw.p;
+    double *dr = d, *dM = dr + 3 * (size_t)nn, *dS = dM + nn, *dO = dS + nn, *dmom = dO + nn;
+    double *dx = dmom + (size_t)GG_NMOM * nn, *dy = dx + np, *dz = dy + np, *dm = dz + np, *dh = dm + np;
+    int *di = (int *)c->rawi.p;
+    if (nn > 0) {
+        CK(cudaMemcpyAsync(dr, t->r, sizeof(double) * 3 * nn, kind, c->st));
+        CK(cudaMemcpyAsync(dM, t->fMass, sizeof(double) * nn, kind, c->st));
+        CK(cudaMemcpyAsync(dS, t->fSoft, sizeof(double) * nn, kind, c->st));
+        CK(cudaMemcpyAsync(dO, t->fOpen2, sizeof(double) * nn, kind, c->st));
+        CK(cudaMemcpyAsync(dmom, t->mom, sizeof(double) * GG_NMOM * nn, kind, c->st));
+        CK(cudaMemcpyAsync(di, t->pLower, sizeof(int) * nn, kind, c->st));
+        CK(cudaMemcpyAsync(di + nn, t->pUpper, sizeof(int) * nn, kind, c->st));
+        CK(cudaMemcpyAsync(di + 2 * (size_t)nn, t->iLower, sizeof(int) * nn, kind, c->st));
+        CK(cudaMemcpyAsync(di + 3 * (size_t)nn, t->iUpper, sizeof(int) * nn, kind, c->st));
+    }
+    if (np > 0) {
+        CK(cudaMemcpyAsync(dx, pp->x, sizeof(double) * np, kind, c->st));
+        CK(cudaMemcpyAsync(dy, pp->y, sizeof(double) * np, kind, c->st));
+        CK(cudaMemcpyAsync(dz, pp->z, sizeof(double) * np, kind, c->st));
+        CK(cudaMemcpyAsync(dm, pp->fMass, sizeof(double) * np, kind, c->st));
+        CK(cudaMemcpyAsync(dh, pp->fSoft, sizeof(double) * np, kind, c->st));
+    }
+    const size_t keepN = (size_t)nodeBase, keepP = (size_t)partBase;
+    if ((rc = ensure(c, c->nodes, (keepN + nn + GG_MAX_IMAGES) * sizeof(NodeW), keepN * sizeof(NodeW)))) return rc;
+    if ((rc = ensure(c, c->momf, (keepN + nn + GG_MAX_IMAGES) * 128, keepN * 128))) return rc;
+    if ((rc = ensure(c, c->momq, (keepN + nn + GG_MAX_IMAGES) * 48, keepN * 48))) return rc;
+    if ((rc = ensure(c, c->parts, (keepP + np + 1) * sizeof(PartS), keepP * sizeof(PartS)))) return rc;
+    if (local && (rc = ensure(c, c->hsoft, (size_t)(np + 1) * sizeof(double)))) return rc;
+    if (nn > 0) {
+        k_pack_nodes<<<(nn + 127) / 128, 128, 0, c->st>>>(nn, dr, dM, dS, dO, dmom, di, di + nn, di + 2 * (size_t)nn,
+                                                          di + 3 * (size_t)nn, nodeBase, partBase, (NodeW *)c->nodes.p,
+                                                          (float4 *)c->momf.p, (double *)c->momq.p);
+        CK(cudaGetLastError());
+        ++c->nLaunches;
+    }
+    if (np > 0) {
+        k_pack_parts<<<(np + 255) / 256, 256, 0, c->st>>>(np, dx, dy, dz, dm, dh, partBase, (PartS *)c->parts.p,
+                                                          local ? (double *)c->hsoft.p : nullptr);
+        CK(cudaGetLastError());
+        ++c->nLaunches;
+    }
+    // the staging buffer is reused by the next upload: finish the packing first
+    CK(cudaStreamSynchronize(c->st));
+    return GG_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *gg_last_error(void) { return g_err; }
+int gg_version(void) { return 100; }
+
+int gg_create(gg_context **pctx, int device) {
+    if (!pctx) return fail(GG_ERR_ARG, "gg_create: null out pointer");
+    int nDev = 0;
+    cudaError_t e = cudaGetDeviceCount(&nDev);
+    if (e != cudaSuccess || nDev == 0)
+        return fail(GG_ERR_CUDA, "gg_create: no usable CUDA device (%s); this library has no CPU path",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0) CK(cudaGetDevice(&device));
+    if (device >= nDev) return fail(GG_ERR_ARG, "gg_create: device %d of %d", device, nDev);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(GG_ERR_UNSUPPORTED, "gg_create: device %s is sm_%d%d; this build targets sm_100a only", prop.name,
+                    prop.major, prop.minor);
+    gg_context *c = new gg_context();
+    c->device = device;
+    c->nSM = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    for (auto &ev : c->ev) CK(cudaEventCreate(&ev));
+    *pctx = c;
+    return GG_OK;
+}
+
+void gg_destroy(gg_context *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->st);
+    DevBuf *all[] = {&c->nodes, &c->momf, &c->momq, &c->parts, &c->active, &c->hsoft, &c->tasks, &c->ngroups,
+                     &c->goffs, &c->counts, &c->acc, &c->pot, &c->dtg, &c->fweight, &c->nloop, &c->sums, &c->misc,
+                     &c->imgoff, &c->ewt, &c->raw, &c->rawi, &c->cubtmp};
+    for (DevBuf *b : all)
+        if (b->p) cudaFree(b->p);
+    if (c->pinned) cudaFreeHost(c->pinned);
+    for (auto &ev : c->ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(c->st);
+    delete c;
+}
+
+int gg_host_alloc(void **p, size_t bytes) {
+    if (!p) return fail(GG_ERR_ARG, "gg_host_alloc: null");
+    CK(cudaMallocHost(p, bytes ? bytes : 1));
+    return GG_OK;
+}
+int gg_host_free(void *p) {
+    if (p) CK(cudaFreeHost(p));
+    return GG_OK;
+}
+
+int gg_set_local(gg_context *c, int idSelf, const gg_tree *t, const gg_particles *pp) {
+    if (!c || !t || !pp) return fail(GG_ERR_ARG, "gg_set_local: null argument");
+    if (t->nNodes < 1 || pp->n < 0 || t->iRoot < 0 || t->iRoot >= t->nNodes)
+        return fail(GG_ERR_ARG, "gg_set_local: nNodes=%d n=%d iRoot=%d", t->nNodes, pp->n, t->iRoot);
+    CK(cudaSetDevice(c->device));
+    int maxB = 1;
+    for (int i = 0; i < t->nNodes; ++i)
+        if (t->iLower[i] == -1) {
+            int np = t->pUpper[i] - t->pLower[i] + 1;
+            if (np > maxB) maxB = np;
+            if (t->pLower[i] < 0 || t->pUpper[i] >= pp->n)
+                return fail(GG_ERR_ARG, "gg_set_local: bucket %d spans particles [%d,%d] outside [0,%d)", i, t->pLower[i],
+                            t->pUpper[i], pp->n);
+        }
+    if (maxB > GG_MAX_BUCKET)
+        return fail(GG_ERR_UNSUPPORTED, "gg_set_local: a bucket holds %d particles (limit GG_MAX_BUCKET=%d)", maxB,
+                    GG_MAX_BUCKET);
+    c->dom.clear();
+    c->nTop = 0;
+    c->idSelf = idSelf;
+    c->maxBucket = maxB;
+    int rc = upload_domain(c, t, pp, 0, 0, true, false);
+    if (rc) return rc;
+    c->dom.push_back(Domain{idSelf, t->nNodes, pp->n, t->iRoot, 0, 0});
+    c->nNodesAll = t->nNodes;
+    c->nPartAll = pp->n;
+    if (pp->active) {
+        c->hActive.assign(pp->active, pp->active + pp->n);
+        if ((rc = ensure(c, c->active, (size_t)(pp->n + 1) * sizeof(int)))) return rc;
+        CK(cudaMemcpyAsync(c->active.p, pp->active, sizeof(int) * pp->n, cudaMemcpyHostToDevice, c->st));
+        CK(cudaStreamSynchronize(c->st));
+    } else c->hActive.clear();
+    return GG_OK;
+}
+
+int gg_set_remote(gg_context *c, int id, const gg_tree *t, const gg_particles *pp, int bDevice) {
+    if (!c || !t || !pp) return fail(GG_ERR_ARG, "gg_set_remote: null argument");
+    if (c->dom.empty()) return fail(GG_ERR_ARG, "gg_set_remote: call gg_set_local first");
+    if (id == c->idSelf) return fail(GG_ERR_ARG, "gg_set_remote: id %d is the local domain", id);
+    CK(cudaSetDevice(c->device));
+    if (!bDevice) {
+        for (int i = 0; i < t->nNodes; ++i)
+            if (t->iLower[i] == -1) {
+                int np = t->pUpper[i] - t->pLower[i] + 1;
+                if (np > GG_MAX_BUCKET)
+                    return fail(GG_ERR_UNSUPPORTED, "gg_set_remote: a bucket holds %d particles (limit %d)", np,
+                                GG_MAX_BUCKET);
+                if (np > c->maxBucket) c->maxBucket = np;
+            }
+    } else if (c->maxBucket < GG_MAX_BUCKET) {
+        c->maxBucket = GG_MAX_BUCKET; // cannot inspect device-resident links cheaply: size for the limit
+    }
+    int rc = upload_domain(c, t, pp, c->nNodesAll, c->nPartAll, false, bDevice != 0);
+    if (rc) return rc;
+    c->dom.push_back(Domain{id, t->nNodes, pp->n, t->iRoot, c->nNodesAll, c->nPartAll});
+    c->nNodesAll += t->nNodes;
+    c->nPartAll += pp->n;
+    return GG_OK;
+}
+
+int gg_clear_remote(gg_context *c) {
+    if (!c || c->dom.empty()) return fail(GG_ERR_ARG, "gg_clear_remote: no local domain");
+    c->dom.resize(1);
+    c->nNodesAll = c->dom[0].nNodes;
+    c->nPartAll = c->dom[0].nPart;
+    c->nTop = 0;
+    return GG_OK;
+}
+
+int gg_set_top(gg_context *c, int nCell, const int *pLower, const int *bUsed, const double *r, const double *fMass,
+               const double *fSoft, const double *fOpen2, const double *mom) {
+    if (!c || nCell < 2 || !pLower || !bUsed || !r || !fMass || !fSoft || !fOpen2 || !mom)
+        return fail(GG_ERR_ARG, "gg_set_top: bad argument");
+    if (nCell > GG_MAX_IMAGES) return fail(GG_ERR_UNSUPPORTED, "gg_set_top: nCell=%d > %d", nCell, GG_MAX_IMAGES);
+    c->nTop = nCell;
+    c->topLower.assign(pLower, pLower + nCell);
+    c->topUsed.assign(bUsed, bUsed + nCell);
+    c->topR.assign(r, r + 3 * (size_t)nCell);
+    c->topMass.assign(fMass, fMass + nCell);
+    c->topSoft.assign(fSoft, fSoft + nCell);
+    c->topOpen2.assign(fOpen2, fOpen2 + nCell);
+    c->topMom.assign(mom, mom + (size_t)GG_NMOM * nCell);
+    return GG_OK;
+}
+
+int gg_set_root_moments(gg_context *c, const double root[GG_NROOT]) {
+    if (!c || !root) return fail(GG_ERR_ARG, "gg_set_root_moments: null");
+    memcpy(c->root, root, sizeof(c->root));
+    c->haveRoot = true;
+    return GG_OK;
+}
+
+} // extern "C"
+
+namespace {
+
+// Resolve a heap cell of the top tree to a global node index; interior cells live at topBase + i.
+int map_top(const gg_context *c, int i, int topBase) {
+    if (c->topLower[i] >= 0) {
+        for (const Domain &d : c->dom)
+            if (d.id == c->topLower[i]) return d.nodeBase + d.iRoot;
+        return -2;
+    }
+    return topBase + i;
+}
+
+int pack_top(gg_context *c, int *pRoot) {
+    const int topBase = c->nNodesAll;
+    const int n = c->nTop;
+    std::vector<NodeW> w(n);
+    std::vector<float> mf((size_t)n * 32, 0.f);
+    std::vector<double> mq((size_t)n * 6, 0.0);
+    for (int i = 1; i < n; ++i) {
+        if (!c->topUsed[i] || c->topLower[i] >= 0) continue;
+        NodeW &o = w[i];
+        o.rx = c->topR[3 * i]; o.ry = c->topR[3 * i + 1]; o.rz = c->topR[3 * i + 2];
+        o.fOpen2 = c->topOpen2[i]; o.fSoft = c->topSoft[i]; o.fMass = c->topMass[i];
+        if (2 * i + 1 >= n) return fail(GG_ERR_ARG, "gg_set_top: interior cell %d has no children in the heap", i);
+        o.c0 = map_top(c, 2 * i, topBase);
+        o.c1 = map_top(c, 2 * i + 1, topBase);
+        if (o.c0 < -1 || o.c1 < -1)
+            return fail(GG_ERR_ARG, "gg_set_top: a top leaf names a rank whose domain was not loaded");
+        o.pLower = 0;
+        o.nP = 1 << 30; // exempt from the "< 4 particles" rule: the top walk has no such test (walk.c:363-371)
+        const double *q = &c->topMom[(size_t)GG_NMOM * i];
+        double tr = q[0] + q[1] + q[2];
+        float *f = &mf[(size_t)i * 32];
+        f[0] = (float)(q[0] - tr / 3.0); f[1] = (float)(q[1] - tr / 3.0); f[2] = (float)(q[2] - tr / 3.0);
+        f[3] = (float)q[3]; f[4] = (float)q[4]; f[5] = (float)q[5];
+        for (int k = 6; k < GG_NMOM; ++k) f[k] = (float)q[k];
+        for (int k = 0; k < 6; ++k) mq[(size_t)i * 6 + k] = q[k];
+    }
+    int rc;
+    const size_t keep = (size_t)topBase;
+    if ((rc = ensure(c, c->nodes, (keep + n) * sizeof(NodeW), keep * sizeof(NodeW)))) return rc;
+    if ((rc = ensure(c, c->momf, (keep + n) * 128, keep * 128))) return rc;
+    if ((rc = ensure(c, c->momq, (keep + n) * 48, keep * 48))) return rc;
+    CK(cudaMemcpyAsync((NodeW *)c->nodes.p + topBase, w.data(), sizeof(NodeW) * n, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync((char *)c->momf.p + keep * 128, mf.data(), 128 * (size_t)n, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync((char *)c->momq.p + keep * 48, mq.data(), 48 * (size_t)n, cudaMemcpyHostToDevice, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    *pRoot = map_top(c, 1, topBase);
+    if (*pRoot < 0) return fail(GG_ERR_ARG, "gg_set_top: root of the top tree cannot be resolved");
+    return GG_OK;
+}
+
+struct Images {
+    std::vector<double> off;
+    int n = 0, home = 0, bits = 5;
+};
+
+// Image offsets in the reference's loop order (walk.c:325-337): ix outermost, non-periodic axes not replicated.
+Images make_images(const gg_params *prm) {
+    Images im;
+    const int nR = prm->nReps;
+    for (int ix = -nR; ix <= nR; ++ix) {
+        if (ix && prm->fPeriod[0] >= DBL_MAX) continue;
+        for (int iy = -nR; iy <= nR; ++iy) {
+            if (iy && prm->fPeriod[1] >= DBL_MAX) continue;
+            for (int iz = -nR; iz <= nR; ++iz) {
+                if (iz && prm->fPeriod[2] >= DBL_MAX) continue;
+                if (!ix && !iy && !iz) im.home = im.n;
+                im.off.push_back(ix * prm->fPeriod[0]);
+                im.off.push_back(iy * prm->fPeriod[1]);
+                im.off.push_back(iz * prm->fPeriod[2]);
+                ++im.n;
+            }
+        }
+    }
+    im.bits = im.n <= 32 ? 5 : 7;
+    return im;
+}
+
+int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_stats *stats) {
+    if (c->dom.empty()) return fail(GG_ERR_ARG, "gg_gravity: gg_set_local has not been called");
+    if (prm->iOrder < 1 || prm->iOrder > 4 || prm->iEwOrder < 0 || prm->iEwOrder > 4)
+        return fail(GG_ERR_UNSUPPORTED, "gg_gravity: iOrder=%d iEwOrder=%d (supported 1..4)", prm->iOrder, prm->iEwOrder);
+    if (prm->nReps < 0 || prm->nReps > 2) return fail(GG_ERR_UNSUPPORTED, "gg_gravity: nReps=%d (supported 0..2)", prm->nReps);
+    CK(cudaSetDevice(c->device));
+    const Domain &L = c->dom[0];
+    const int n = L.nPart, nn = L.nNodes;
+    const bool doEwald = prm->bPeriodic && prm->bEwald && prm->iEwOrder > 0 && !(prm->flags & GG_FLAG_WALK_ONLY);
+    if (doEwald && !c->haveRoot) return fail(GG_ERR_ARG, "gg_gravity: Ewald needs gg_set_root_moments");
+    Images im = make_images(prm);
+    if (im.n > GG_MAX_IMAGES) return fail(GG_ERR_UNSUPPORTED, "gg_gravity: %d images", im.n);
+    int rootNode = L.iRoot;
+    int nNodesAll = c->nNodesAll;
+    int rc;
+    if (c->nTop > 0) {
+        if ((rc = pack_top(c, &rootNode))) return rc;
+        nNodesAll += c->nTop;
+    } else if (c->dom.size() > 1)
+        return fail(GG_ERR_ARG, "gg_gravity: remote domains are loaded but gg_set_top was not called");
+    const unsigned cap = (1u << (32 - im.bits)) - 2u;
+    if ((unsigned)nNodesAll > cap || (unsigned)c->nPartAll > cap)
+        return fail(GG_ERR_UNSUPPORTED, "gg_gravity: %d nodes / %d particles exceed the %u addressable with %d images",
+                    nNodesAll, c->nPartAll, cap, im.n);
+    c->nLaunches = 0;
+    const int *dActive = c->hActive.empty() ? nullptr : (const int *)c->active.p;
+
+    if ((rc = ensure(c, c->imgoff, im.off.size() * sizeof(double)))) return rc;
+    CK(cudaMemcpyAsync(c->imgoff.p, im.off.data(), im.off.size() * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    if ((rc = ensure(c, c->counts, (size_t)nn * 3 * sizeof(int)))) return rc;
+    if ((rc = ensure(c, c->acc, (size_t)(n + 1) * 3 * sizeof(double)))) return rc;
+    if ((rc = ensure(c, c->pot, (size_t)(n + 1) * sizeof(double)))) return rc;
+    if ((rc = ensure(c, c->dtg, (size_t)(n + 1) * sizeof(double)))) return rc;
+    if ((rc = ensure(c, c->fweight, (size_t)(n + 1) * sizeof(double)))) return rc;
+    if ((rc = ensure(c, c->nloop, (size_t)(n + 1) * sizeof(int)))) return rc;
+    if ((rc = ensure(c, c->sums, 16 * sizeof(unsigned long long)))) return rc;
+    if ((rc = ensure(c, c->misc, 16 * sizeof(int)))) return rc;
+    if ((rc = ensure(c, c->ngroups, (size_t)(nn + 1) * sizeof(int)))) return rc;
+    if ((rc = ensure(c, c->goffs, (size_t)(nn + 1) * sizeof(int)))) return rc;
+
+    CK(cudaEventRecord(c->ev[0], c->st));
+    CK(cudaMemsetAsync(c->counts.p, 0xff, (size_t)nn * 3 * sizeof(int), c->st));
+    CK(cudaMemsetAsync(c->acc.p, 0, (size_t)n * 3 * sizeof(double), c->st));
+    CK(cudaMemsetAsync(c->pot.p, 0, (size_t)n * sizeof(double), c->st));
+    CK(cudaMemsetAsync(c->dtg.p, 0, (size_t)n * sizeof(double), c->st));
+    CK(cudaMemsetAsync(c->fweight.p, 0, (size_t)n * sizeof(double), c->st));
+    CK(cudaMemsetAsync(c->sums.p, 0, 16 * sizeof(unsigned long long), c->st));
+    CK(cudaMemsetAsync(c->misc.p, 0, 16 * sizeof(int), c->st));
+
+    // ---- task list: local buckets with an active sink, in tree order
+    int nTasks = 0;
+    if (singleTask) {
+        if ((rc = ensure(c, c->tasks, sizeof(Task)))) return rc;
+        CK(cudaMemcpyAsync(c->tasks.p, singleTask, sizeof(Task), cudaMemcpyHostToDevice, c->st));
+        nTasks = 1;
+    } else {
+        k_count_groups<<<(nn + 255) / 256, 256, 0, c->st>>>(nn, (const NodeW *)c->nodes.p, dActive, (int *)c->ngroups.p);
+        CK(cudaGetLastError());
+        size_t tmpBytes = 0;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, (int *)c->ngroups.p, (int *)c->goffs.p, nn + 1, c->st));
+        if ((rc = ensure(c, c->cubtmp, tmpBytes))) return rc;
+        CK(cudaMemsetAsync((int *)c->ngroups.p + nn, 0, sizeof(int), c->st));
+        CK(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmpBytes, (int *)c->ngroups.p, (int *)c->goffs.p, nn + 1, c->st));
+        CK(cudaMemcpyAsync(&nTasks, (int *)c->goffs.p + nn, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        if ((rc = ensure(c, c->tasks, (size_t)(nTasks + 1) * sizeof(Task)))) return rc;
+        k_fill_tasks<<<(nn + 255) / 256, 256, 0, c->st>>>(nn, (const int *)c->ngroups.p, (const int *)c->goffs.p,
+                                                          (Task *)c->tasks.p);
+        CK(cudaGetLastError());
+        c->nLaunches += 3;
+    }
+    c->nTasks = nTasks;
+
+    // ---- fused walk + interact
+    TreeKernelArgs ta;
+    memset(&ta, 0, sizeof(ta));
+    ta.nodes = (const NodeW *)c->nodes.p;
+    ta.momf = (const float4 *)c->momf.p;
+    ta.momq = (const double *)c->momq.p;
+    ta.parts = (const PartS *)c->parts.p;
+    ta.active = dActive;
+    ta.hsoft = (const double *)c->hsoft.p;
+    ta.tasks = (const Task *)c->tasks.p;
+    ta.nTasks = nTasks;
+    ta.taskCounter = (int *)c->misc.p;
+    ta.errFlag = (int *)c->misc.p + 1;
+    ta.rootNode = rootNode;
+    ta.nImages = im.n;
+    ta.homeImage = im.home;
+    ta.imgBits = im.bits;
+    ta.imgOff = (const double *)c->imgoff.p;
+    ta.iOrder = prm->iOrder;
+    ta.maxBucket = c->maxBucket;
+    ta.walkOnly = (prm->flags & GG_FLAG_WALK_ONLY) ? 1 : 0;
+    ta.acc = (double *)c->acc.p;
+    ta.pot = (double *)c->pot.p;
+    ta.dtg = (double *)c->dtg.p;
+    ta.counts = (int *)c->counts.p;
+    CK(cudaEventRecord(c->ev[1], c->st));
+    if (nTasks > 0) {
+        CK(gg_launch_tree_kernel(ta, c->nSM, c->st));
+        ++c->nLaunches;
+    }
+    CK(cudaEventRecord(c->ev[2], c->st));
+
+    // ---- Ewald
+    int nEwh = 0;
+    if (doEwald && !singleTask) {
+        std::vector<double> ewt;
+        const double Lbox = prm->fPeriod[0];
+        gg_ewald_table_host(c->root, Lbox, prm->fEwhCut, prm->iEwOrder, ewt);
+        nEwh = (int)(ewt.size() / 5);
+        if ((rc = ensure(c, c->ewt, (ewt.size() + 8) * sizeof(double)))) return rc;
+        CK(cudaMemcpyAsync(c->ewt.p, ewt.data(), ewt.size() * sizeof(double), cudaMemcpyHostToDevice, c->st));
+        EwaldKernelArgs ea;
+        memset(&ea, 0, sizeof(ea));
+        ea.parts = (const PartS *)c->parts.p;
+        ea.active = dActive;
+        ea.n = n;
+        memcpy(ea.root, c->root, sizeof(ea.root));
+        const double *R = c->root;
+        ea.trQ4[0] = R[20] + R[26] + R[29]; // Qxx = xxxx + xxyy + xxzz   (meval.h:36-41)
+        ea.trQ4[1] = R[22] + R[21] + R[30]; // Qxy = xxxy + xyyy + xyzz
+        ea.trQ4[2] = R[24] + R[28] + R[31]; // Qxz = xxxz + xyyz + xzzz
+        ea.trQ4[3] = R[26] + R[23] + R[32]; // Qyy = xxyy + yyyy + yyzz
+        ea.trQ4[4] = R[27] + R[25] + R[33]; // Qyz = xxyz + yyyz + yzzz
+        ea.trQ4[5] = R[29] + R[32] + R[34]; // Qzz = xxzz + yyzz + zzzz
+        ea.trQ4[6] = (1.0 / 8.0) * (ea.trQ4[0] + ea.trQ4[3] + ea.trQ4[5]);
+        ea.trQ3[0] = 0.5 * (R[10] + R[11] + R[17]); // Qx = xxx + xyy + xzz   (meval.h:55-57)
+        ea.trQ3[1] = 0.5 * (R[12] + R[13] + R[18]); // Qy = xxy + yyy + yzz
+        ea.trQ3[2] = 0.5 * (R[14] + R[15] + R[19]); // Qz = xxz + yyz + zzz
+        ea.trQ2 = 0.5 * (R[4] + R[5] + R[9]);
+        ea.ewt = (const double *)c->ewt.p;
+        ea.nEwh = nEwh;
+        ea.nReps = prm->nReps;
+        ea.nEwReps = (int)ceil(prm->fEwCut);
+        if (prm->nReps > ea.nEwReps) ea.nEwReps = prm->nReps;
+        ea.iOrder = prm->iEwOrder;
+        ea.L = Lbox;
+        ea.fEwCut2 = prm->fEwCut * prm->fEwCut * Lbox * Lbox;
+        ea.alpha = 2.0 / Lbox;
+        ea.alpha2 = ea.alpha * ea.alpha;
+        ea.k1 = M_PI / (ea.alpha2 * Lbox * Lbox * Lbox);
+        ea.ka = 2.0 * ea.alpha / sqrt(M_PI);
+        ea.acc = (double *)c->acc.p;
+        ea.pot = (double *)c->pot.p;
+        ea.nLoop = (int *)c->nloop.p;
+        CK(gg_launch_ewald_kernel(ea, c->st));
+        ++c->nLaunches;
+    }
+    CK(cudaEventRecord(c->ev[3], c->st));
+    if (prm->bComove && !prm->bPeriodic && !(prm->flags & GG_FLAG_WALK_ONLY) && n > 0) {
+        k_comove<<<(n + 255) / 256, 256, 0, c->st>>>(n, (const PartS *)c->parts.p, dActive, prm->dRhoFac,
+                                                     (double *)c->acc.p, (double *)c->pot.p);
+        CK(cudaGetLastError());
+        ++c->nLaunches;
+    }
+    // ---- bookkeeping
+    StatsKernelArgs sa;
+    memset(&sa, 0, sizeof(sa));
+    sa.nodes = (const NodeW *)c->nodes.p;
+    sa.tasks = (const Task *)c->tasks.p;
+    sa.nTasks = nTasks;
+    sa.active = dActive;
+    sa.counts = (const int *)c->counts.p;
+    sa.nLoop = (doEwald && !singleTask) ? (const int *)c->nloop.p : nullptr;
+    sa.nEwh = nEwh;
+    sa.iOrder = prm->iOrder;
+    sa.iEwOrder = prm->iEwOrder;
+    sa.fWeight = (double *)c->fweight.p;
+    sa.sums = (unsigned long long *)c->sums.p;
+    CK(gg_launch_stats_kernel(sa, c->st));
+    if (nTasks > 0) ++c->nLaunches;
+    CK(cudaEventRecord(c->ev[4], c->st));
+
+    unsigned long long hs[16];
+    int hm[16];
+    CK(cudaMemcpyAsync(hs, c->sums.p, sizeof(hs), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(hm, c->misc.p, sizeof(hm), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    if (hm[1]) return fail(GG_ERR_UNSUPPORTED, "gg_gravity: walk frontier overflowed %d entries (tree too deep)", GG_STACK_CAP);
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->nActive = (int)hs[0];
+        stats->dPartSum = (double)hs[1];
+        stats->dCellSum = (double)hs[2];
+        stats->dSoftSum = (double)hs[3];
+        stats->dFlop = (double)hs[4] + (double)hs[5];
+        stats->dFlopEwald = (double)hs[5];
+        stats->nMaxPart = (int)hs[6];
+        stats->nMaxCellSoft = (int)hs[7];
+        stats->nMaxCellNewt = (int)hs[8];
+        float ms;
+        CK(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2])); stats->msTree = ms;
+        CK(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3])); stats->msEwald = ms;
+        CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[4])); stats->msTotal = ms;
+        stats->nKernelLaunches = c->nLaunches;
+    }
+    return GG_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int gg_gravity(gg_context *c, const gg_params *prm, double *a, double *fPot, double *dtGrav, double *fWeight,
+               gg_stats *stats) {
+    if (!c || !prm) return fail(GG_ERR_ARG, "gg_gravity: null argument");
+    int rc = run_gravity(c, prm, nullptr, stats);
+    if (rc) return rc;
+    if (prm->flags & (GG_FLAG_NO_DOWNLOAD | GG_FLAG_WALK_ONLY)) return GG_OK;
+    if (!a || !fPot || !dtGrav || !fWeight) return fail(GG_ERR_ARG, "gg_gravity: null output array");
+    const int n = c->dom[0].nPart;
+    if (n == 0) return GG_OK;
+    if (!prm->accumulate) { // overwrite: straight into the caller's arrays
+        CK(cudaMemcpyAsync(a, c->acc.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaMemcpyAsync(fPot, c->pot.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaMemcpyAsync(dtGrav, c->dtg.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaMemcpyAsync(fWeight, c->fweight.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        return GG_OK;
+    }
+    if ((rc = ensure_pinned(c, sizeof(double) * 6 * (size_t)n))) return rc;
+    double *h = (double *)c->pinned, *ha = h, *hp = h + 3 * (size_t)n, *hd = hp + n, *hw = hd + n;
+    CK(cudaMemcpyAsync(ha, c->acc.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(hp, c->pot.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(hd, c->dtg.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(hw, c->fweight.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    const bool all = c->hActive.empty();
+    for (int i = 0; i < n; ++i) { // += / max / = on active particles only (pkd.c:2851-2861, grav.c:100,192-195)
+        if (!all && !c->hActive[i]) continue;
+        a[3 * (size_t)i] += ha[3 * (size_t)i];
+        a[3 * (size_t)i + 1] += ha[3 * (size_t)i + 1];
+        a[3 * (size_t)i + 2] += ha[3 * (size_t)i + 2];
+        fPot[i] += hp[i];
+        if (hd[i] > dtGrav[i]) dtGrav[i] = hd[i];
+        fWeight[i] = hw[i];
+    }
+    return GG_OK;
+}
+
+int gg_bucket_counts(gg_context *c, int *counts3) {
+    if (!c || !counts3 || c->dom.empty()) return fail(GG_ERR_ARG, "gg_bucket_counts: bad argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(counts3, c->counts.p, sizeof(int) * 3 * (size_t)c->dom[0].nNodes, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return GG_OK;
+}
+
+int gg_bucket_walk(gg_context *c, const gg_params *prm, int iBucket, int n3[3]) {
+    if (!c || !prm || !n3 || c->dom.empty()) return fail(GG_ERR_ARG, "gg_bucket_walk: bad argument");
+    if (iBucket < 0 || iBucket >= c->dom[0].nNodes) return fail(GG_ERR_ARG, "gg_bucket_walk: iBucket=%d", iBucket);
+    gg_params p = *prm;
+    p.flags |= GG_FLAG_WALK_ONLY;
+    Task t{iBucket, 0};
+    int rc = run_gravity(c, &p, &t, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(n3, (int *)c->counts.p + 3 * (size_t)iBucket, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return GG_OK;
+}
+
+int gg_ewald_table(gg_context *c, const gg_params *prm, double *ewt5, int nMax, int *pnEwh) {
+    if (!c || !prm || !pnEwh) return fail(GG_ERR_ARG, "gg_ewald_table: bad argument");
+    if (!c->haveRoot) return fail(GG_ERR_ARG, "gg_ewald_table: gg_set_root_moments has not been called");
+    std::vector<double> ewt;
+    gg_ewald_table_host(c->root, prm->fPeriod[0], prm->fEwhCut, prm->iEwOrder, ewt);
+    *pnEwh = (int)(ewt.size() / 5);
+    if (ewt5) memcpy(ewt5, ewt.data(), sizeof(double) * 5 * (size_t)(*pnEwh < nMax ? *pnEwh : nMax));
+    return GG_OK;
+}
+
+int gg_device_results(gg_context *c, void **a, void **fPot, void **dtGrav, void **fWeight) {
+    if (!c) return fail(GG_ERR_ARG, "gg_device_results: null");
+    if (a) *a = c->acc.p;
+    if (fPot) *fPot = c->pot.p;
+    if (dtGrav) *dtGrav = c->dtg.p;
+    if (fWeight) *fWeight = c->fweight.p;
+    return GG_OK;
+}
+
+} // extern "C"

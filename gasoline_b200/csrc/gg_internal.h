@@ -1,0 +1,101 @@
+// gg_internal.h -- device data layout and kernel launch interfaces shared by the .cu files.
+//
+// HBM layout (see DESIGN.md "Data layout"):
+//   NodeW  nodes[nNodesAll]   64 B  walk record: FP64 centre of mass, fOpen2, fSoft, fMass + 4 ints (children,
+//                                   first particle, particle count).  One record = two 32 B sectors; every
+//                                   opening decision reads exactly one.
+//   float4 momf[nNodesAll][8] 128 B evaluation record: FP32 traceless quadrupole, reduced octopole and
+//                                   hexadecapole (31 values + pad) = one cache line per accepted cell.
+//   double momq[nNodesAll][6] 48 B  raw FP64 quadrupole, read only on the (rare) softened-cell path.
+//   PartS  parts[nPartAll]    32 B  source record: FP64 position, FP32 mass and softening.
+// Indices are GLOBAL: the local domain first, then every remote domain, then the top-tree cells.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/gasoline_b200.h"
+
+#define GG_WARPS_PER_CTA 4
+#define GG_MAX_SINKS 8      // sinks evaluated per warp pass (accumulators live in registers)
+#define GG_STACK_CAP 1024   // walk frontier entries per warp
+#define GG_STACK_DFS_MARGIN 160
+#define GG_MAX_IMAGES 128
+
+struct __align__(16) NodeW {
+    double rx, ry, rz;
+    double fOpen2;
+    double fSoft;
+    double fMass;
+    int c0, c1;   // children (global node index), c0 == -1: bucket
+    int pLower;   // first particle (global particle index)
+    int nP;       // particle count; >= 2^30 for top-tree cells (exempt from the "< 4 particles" rule, walk.c:81)
+};
+static_assert(sizeof(NodeW) == 64, "NodeW must be 64 bytes");
+
+struct __align__(16) PartS {
+    double x, y, z;
+    float m, h;
+};
+static_assert(sizeof(PartS) == 32, "PartS must be 32 bytes");
+
+// One unit of work for a warp: a sink bucket (local node index) and which group of 8 active sinks to evaluate.
+struct Task {
+    int node;
+    int group;
+};
+
+struct TreeKernelArgs {
+    const NodeW *nodes;
+    const float4 *momf;
+    const double *momq;
+    const PartS *parts;
+    const int *active;       // local particles, may be null (all active)
+    const double *hsoft;     // local particles: FP64 softening (fSoftMax must be exact, walk.c:319-324)
+    const Task *tasks;
+    int nTasks;
+    int *taskCounter;
+    int rootNode;            // global index where every image's walk starts
+    int nImages, homeImage, imgBits;
+    const double *imgOff;    // [nImages][3]
+    int iOrder;
+    int maxBucket;           // largest particle count of any bucket (sizes the particle buffer)
+    int walkOnly;
+    // outputs (local particles, tree order)
+    double *acc;             // [n][3]
+    double *pot;
+    double *dtg;
+    int *counts;             // [nLocalNodes][3]
+    int *errFlag;
+};
+
+struct EwaldKernelArgs {
+    const PartS *parts;      // local particles
+    const int *active;
+    int n;
+    double root[GG_NROOT];
+    double trQ4[7];          // Qxx,Qxy,Qxz,Qyy,Qyz,Qzz, Qtr of the hexadecapole traces (meval.h:36-42)
+    double trQ3[3];          // Qx,Qy,Qz (meval.h:55-57)
+    double trQ2;             // 0.5*(xx+yy+zz) (meval.h:68)
+    const double *ewt;       // [nEwh][5]
+    int nEwh;
+    int nReps, nEwReps, iOrder;
+    double L, fEwCut2, alpha, alpha2, k1, ka;
+    double *acc, *pot;       // accumulated into
+    int *nLoop;              // per particle: real-space terms evaluated
+};
+
+struct StatsKernelArgs {
+    const NodeW *nodes;      // local nodes
+    const Task *tasks;
+    int nTasks;
+    const int *active;
+    const int *counts;
+    const int *nLoop;        // may be null (no Ewald)
+    int nEwh, iOrder, iEwOrder;
+    double *fWeight;
+    unsigned long long *sums; // [0] nActive [1] part [2] cell [3] soft [4] flopI [5] flopE [6..8] max lists
+};
+
+size_t gg_tree_kernel_smem(int maxBucket);
+cudaError_t gg_launch_tree_kernel(const TreeKernelArgs &a, int nSM, cudaStream_t st);
+cudaError_t gg_launch_ewald_kernel(const EwaldKernelArgs &a, cudaStream_t st);
+cudaError_t gg_launch_stats_kernel(const StatsKernelArgs &a, cudaStream_t st);

@@ -1,0 +1,317 @@
+"""Host-side mirror of the reference's `pkd` interface for the gravity path, over the C ABI.
+
+The reference's per-rank object is `PKD` (pkd.h:597-660): it owns pStore (particles), kdNodes (tree), kdTop and
+ilcnRoot, and the path is driven as  pkdBuildBinary -> pkdGravAll(-> pkdBucketWalk/Interact/Ewald).  This class
+keeps those names, argument meanings and result conventions; every force is computed by the CUDA library
+(gasoline_b200/lib/libgasoline_b200.so).  There is no CPU fallback: if the library or a GPU is missing, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .ics import FLOAT_MAXVAL
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libgasoline_b200.so")
+GG_NMOM, GG_NROOT = 31, 35
+GG_FLAG_WALK_ONLY, GG_FLAG_NO_DOWNLOAD = 1, 2
+
+
+class GasolineB200Error(RuntimeError):
+    pass
+
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+class gg_tree(C.Structure):
+    _fields_ = [("nNodes", C.c_int), ("iRoot", C.c_int), ("bnd", _dp), ("r", _dp), ("fMass", _dp), ("fSoft", _dp),
+                ("fOpen2", _dp), ("mom", _dp), ("pLower", _ip), ("pUpper", _ip), ("iLower", _ip), ("iUpper", _ip)]
+
+
+class gg_particles(C.Structure):
+    _fields_ = [("n", C.c_int), ("x", _dp), ("y", _dp), ("z", _dp), ("fMass", _dp), ("fSoft", _dp), ("active", _ip)]
+
+
+class gg_params(C.Structure):
+    _fields_ = [("nReps", C.c_int), ("bPeriodic", C.c_int), ("iOrder", C.c_int), ("bEwald", C.c_int),
+                ("iEwOrder", C.c_int), ("fEwCut", C.c_double), ("fEwhCut", C.c_double), ("bComove", C.c_int),
+                ("dRhoFac", C.c_double), ("fPeriod", C.c_double * 3), ("accumulate", C.c_int), ("flags", C.c_int)]
+
+
+class gg_stats(C.Structure):
+    _fields_ = [("nActive", C.c_int), ("dPartSum", C.c_double), ("dCellSum", C.c_double), ("dSoftSum", C.c_double),
+                ("dFlop", C.c_double), ("dFlopEwald", C.c_double), ("msTree", C.c_double), ("msEwald", C.c_double),
+                ("msTotal", C.c_double), ("nKernelLaunches", C.c_int), ("nMaxPart", C.c_int),
+                ("nMaxCellSoft", C.c_int), ("nMaxCellNewt", C.c_int)]
+
+
+_lib = None
+
+
+def load_library(path: str | None = None):
+    """dlopen the CUDA library. Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise GasolineB200Error(f"{path} is missing: run `python -m gasoline_b200.build` (nvcc, sm_100a). "
+                                "There is no CPU fallback for this path.")
+    L = C.CDLL(path)
+    L.gg_last_error.restype = C.c_char_p
+    L.gg_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    L.gg_destroy.argtypes = [C.c_void_p]
+    L.gg_set_local.argtypes = [C.c_void_p, C.c_int, C.POINTER(gg_tree), C.POINTER(gg_particles)]
+    L.gg_set_remote.argtypes = [C.c_void_p, C.c_int, C.POINTER(gg_tree), C.POINTER(gg_particles), C.c_int]
+    L.gg_clear_remote.argtypes = [C.c_void_p]
+    L.gg_set_top.argtypes = [C.c_void_p, C.c_int, _ip, _ip, _dp, _dp, _dp, _dp, _dp]
+    L.gg_set_root_moments.argtypes = [C.c_void_p, _dp]
+    L.gg_gravity.argtypes = [C.c_void_p, C.POINTER(gg_params), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                             C.POINTER(gg_stats)]
+    L.gg_bucket_counts.argtypes = [C.c_void_p, C.c_void_p]
+    L.gg_bucket_walk.argtypes = [C.c_void_p, C.POINTER(gg_params), C.c_int, _ip]
+    L.gg_ewald_table.argtypes = [C.c_void_p, C.POINTER(gg_params), C.c_void_p, C.c_int, _ip]
+    L.gg_device_results.argtypes = [C.c_void_p] + [C.POINTER(C.c_void_p)] * 4
+    L.gg_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+    L.gg_host_free.argtypes = [C.c_void_p]
+    L.gg_tree_build.argtypes = [C.c_int, _dp, _dp, _dp, _dp, _dp, _ip, _ip, C.c_int, C.c_double, C.c_int, C.c_int,
+                                C.POINTER(C.c_void_p)]
+    L.gg_tree_view.argtypes = [C.c_void_p, C.POINTER(gg_tree), _dp]
+    L.gg_tree_free.argtypes = [C.c_void_p]
+    _lib = L
+    return L
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        msg = load_library().gg_last_error().decode(errors="replace")
+        raise GasolineB200Error(f"{what} failed ({rc}): {msg}")
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip)
+
+
+def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
+    """numpy array backed by page-locked host memory (gg_host_alloc).  The allocation lives for the life of the
+    process (a handful of bench/host staging buffers), so the array can be passed around freely."""
+    L = load_library()
+    count = int(np.prod(shape))
+    n = max(count * np.dtype(dtype).itemsize, 1)
+    p = C.c_void_p()
+    _check(L.gg_host_alloc(C.byref(p), n), "gg_host_alloc")
+    buf = (C.c_char * n).from_address(p.value)
+    return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+
+
+@dataclass
+class GravityParams:
+    """The scalar arguments of pkdGravAll (pkd.h:797-801) with the reference's defaults (master.c:399-675)."""
+    nReps: int = 0            # nReplicas; 1 when periodic (master.c:1763-1765)
+    bPeriodic: int = 0
+    iOrder: int = 4
+    bEwald: int = 1
+    iEwOrder: int = 4
+    fEwCut: float = 2.6
+    fEwhCut: float = 2.8
+    bComove: int = 0
+    dRhoFac: float = 0.0
+    bDoSun: int = 0
+    dSunSoft: float = 0.0
+
+
+class Tree:
+    """SoA copy of a k-d tree with the reference's KDN semantics (pkd.h:454-469), arrays owned by numpy."""
+    FIELDS = ("bnd", "r", "fMass", "fSoft", "fOpen2", "mom", "pLower", "pUpper", "iLower", "iUpper")
+
+    def __init__(self, nNodes, iRoot, **arrays):
+        self.nNodes, self.iRoot = int(nNodes), int(iRoot)
+        for k in self.FIELDS:
+            dt = np.int32 if k[0] in "pi" else np.float64
+            setattr(self, k, np.ascontiguousarray(arrays[k], dtype=dt))
+
+    def view(self) -> gg_tree:
+        return gg_tree(self.nNodes, self.iRoot, _d(self.bnd), _d(self.r), _d(self.fMass), _d(self.fSoft),
+                       _d(self.fOpen2), _d(self.mom), _i(self.pLower), _i(self.pUpper), _i(self.iLower),
+                       _i(self.iUpper))
+
+    def as_dict(self):
+        d = {k: getattr(self, k) for k in self.FIELDS}
+        d.update(nNodes=self.nNodes, iRoot=self.iRoot)
+        return d
+
+
+class PKD:
+    """One rank's particle store + tree on one B200 (mirrors struct pkdContext, pkd.h:597-660)."""
+
+    def __init__(self, device: int = -1, idSelf: int = 0, fPeriod=(FLOAT_MAXVAL,) * 3):
+        self._L = load_library()
+        self._ctx = C.c_void_p()
+        _check(self._L.gg_create(C.byref(self._ctx), device), "gg_create")
+        self.idSelf = idSelf
+        self.fPeriod = tuple(float(v) for v in fPeriod)
+        self.nLocal = 0
+        self.tree: Tree | None = None
+        self.ilcnRoot = None
+        self.stats = None
+        self.iOrderMap = None  # tree position -> input index
+
+    # -- lifetime -------------------------------------------------------------------------------------------
+    def pkdFinish(self):
+        if self._ctx:
+            self._L.gg_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    close = pkdFinish
+
+    def __del__(self):
+        try:
+            self.pkdFinish()
+        except Exception:
+            pass
+
+    # -- particles + tree -----------------------------------------------------------------------------------
+    def pkdLoadParticles(self, x, y, z, fMass, fSoft, active=None):
+        """Fill pStore (what pkdReadTipsy pkd.c:297 does on the host). Arrays are copied; order = iOrder."""
+        self.x, self.y, self.z, self.fMass, self.fSoft = (np.array(a, dtype=np.float64, copy=True)
+                                                           for a in (x, y, z, fMass, fSoft))
+        self.nLocal = int(self.x.shape[0])
+        self.active = None if active is None else np.array(active, dtype=np.int32, copy=True)
+        self.iOrderMap = np.arange(self.nLocal, dtype=np.int32)
+        self.tree = None
+
+    def pkdBuildBinary(self, nBucket: int = 8, dCrit: float = 0.7, iOrder: int = 4, nThreads: int = 0):
+        """pkdBuildBinary (pkd.c:2627) + pkdCalcRoot (pkd.c:4395): spatial-bisection tree, OPEN_JOSH opening radius
+        with theta=dCrit; permutes pStore into tree order.  Host-side C++ (csrc/gg_tree_build.cpp)."""
+        if self.nLocal == 0:
+            raise GasolineB200Error("pkdBuildBinary: no particles")
+        bt = C.c_void_p()
+        order = np.zeros(self.nLocal, dtype=np.int32)
+        act = _i(self.active) if self.active is not None else None
+        _check(self._L.gg_tree_build(self.nLocal, _d(self.x), _d(self.y), _d(self.z), _d(self.fMass), _d(self.fSoft),
+                                     act, _i(order), nBucket, dCrit, iOrder, nThreads, C.byref(bt)), "gg_tree_build")
+        try:
+            v = gg_tree()
+            root = np.zeros(GG_NROOT)
+            _check(self._L.gg_tree_view(bt, C.byref(v), _d(root)), "gg_tree_view")
+            nn = v.nNodes
+            cp = lambda p, shape, dt: np.ctypeslib.as_array(p, shape=shape).astype(dt, copy=True)
+            self.tree = Tree(nn, v.iRoot, bnd=cp(v.bnd, (nn, 6), np.float64), r=cp(v.r, (nn, 3), np.float64),
+                             fMass=cp(v.fMass, (nn,), np.float64), fSoft=cp(v.fSoft, (nn,), np.float64),
+                             fOpen2=cp(v.fOpen2, (nn,), np.float64), mom=cp(v.mom, (nn, GG_NMOM), np.float64),
+                             pLower=cp(v.pLower, (nn,), np.int32), pUpper=cp(v.pUpper, (nn,), np.int32),
+                             iLower=cp(v.iLower, (nn,), np.int32), iUpper=cp(v.iUpper, (nn,), np.int32))
+            self.ilcnRoot = root
+        finally:
+            self._L.gg_tree_free(bt)
+        self.iOrderMap = self.iOrderMap[order]
+        self._uploaded = False
+        return self.tree
+
+    def pkdSetTree(self, tree: Tree, x, y, z, fMass, fSoft, active=None, ilcnRoot=None, iOrderMap=None):
+        """Adopt a tree built elsewhere (e.g. the host's own kdNodes); particles must already be in its order."""
+        self.x, self.y, self.z, self.fMass, self.fSoft = (np.array(a, dtype=np.float64, copy=True)
+                                                           for a in (x, y, z, fMass, fSoft))
+        self.nLocal = int(self.x.shape[0])
+        self.active = None if active is None else np.array(active, dtype=np.int32, copy=True)
+        self.tree = tree
+        self.ilcnRoot = None if ilcnRoot is None else np.array(ilcnRoot, dtype=np.float64, copy=True)
+        self.iOrderMap = np.arange(self.nLocal, dtype=np.int32) if iOrderMap is None else np.asarray(iOrderMap, np.int32)
+        self._uploaded = False
+
+    def upload(self):
+        """Ingest pStore + kdNodes into HBM (gg_set_local); also pkd->ilcnRoot when present."""
+        if self.tree is None:
+            raise GasolineB200Error("upload: build or set a tree first")
+        tv = self.tree.view()
+        pv = gg_particles(self.nLocal, _d(self.x), _d(self.y), _d(self.z), _d(self.fMass), _d(self.fSoft),
+                          _i(self.active) if self.active is not None else None)
+        _check(self._L.gg_set_local(self._ctx, self.idSelf, C.byref(tv), C.byref(pv)), "gg_set_local")
+        if self.ilcnRoot is not None:
+            _check(self._L.gg_set_root_moments(self._ctx, _d(self.ilcnRoot)), "gg_set_root_moments")
+        self._uploaded = True
+
+    def pkdSetRemote(self, id_: int, tree: Tree, x, y, z, fMass, fSoft):
+        """A remote domain's tree + particles (what pkdRemoteWalk reads via mdlAquire, walk.c:181)."""
+        cols = [np.ascontiguousarray(a, dtype=np.float64) for a in (x, y, z, fMass, fSoft)]
+        tv = tree.view()
+        pv = gg_particles(int(cols[0].shape[0]), *[_d(a) for a in cols], None)
+        _check(self._L.gg_set_remote(self._ctx, id_, C.byref(tv), C.byref(pv), 0), "gg_set_remote")
+
+    def pkdDistribCells(self, pLower, bUsed, r, fMass, fSoft, fOpen2, mom):
+        """pkdDistribCells (pkd.c:4376): the gathered top tree kdTop[0..nCell), heap indexed from ROOT=1."""
+        a = [np.ascontiguousarray(pLower, np.int32), np.ascontiguousarray(bUsed, np.int32)] + \
+            [np.ascontiguousarray(v, np.float64) for v in (r, fMass, fSoft, fOpen2, mom)]
+        _check(self._L.gg_set_top(self._ctx, int(a[0].shape[0]), _i(a[0]), _i(a[1]), *[_d(v) for v in a[2:]]),
+               "gg_set_top")
+
+    def pkdDistribRoot(self, ilcnRoot):
+        """pkdDistribRoot (pkd.c:4472): the Ewald root expansion for every rank."""
+        self.ilcnRoot = np.array(ilcnRoot, dtype=np.float64, copy=True)
+        _check(self._L.gg_set_root_moments(self._ctx, _d(self.ilcnRoot)), "gg_set_root_moments")
+
+    # -- the hot path ---------------------------------------------------------------------------------------
+    def _params(self, g: GravityParams, accumulate: int, flags: int) -> gg_params:
+        if g.bDoSun:
+            raise GasolineB200Error("pkdGravAll: bDoSun (solar indirect term, pkd.c:3003) is not supported on the GPU path")
+        return gg_params(g.nReps, g.bPeriodic, g.iOrder, g.bEwald, g.iEwOrder, g.fEwCut, g.fEwhCut, g.bComove,
+                         g.dRhoFac, (C.c_double * 3)(*self.fPeriod), accumulate, flags)
+
+    def pkdGravAll(self, g: GravityParams, a=None, fPot=None, dtGrav=None, fWeight=None, walk_only=False,
+                   download=True):
+        """pkdGravAll (pkd.c:2868).  With arrays given: a, fPot accumulate (+=), dtGrav is a running max, fWeight is
+        overwritten for active particles -- the reference's in-place semantics on pStore.  Without: fresh arrays.
+        Returns a dict with the arrays (tree order) and the scalars the reference returns through pointers
+        (nActive, dPartSum, dCellSum, dSoftSum, dFlop) plus device timings."""
+        if not getattr(self, "_uploaded", False):
+            self.upload()
+        n = self.nLocal
+        accumulate = 1 if a is not None else 0
+        flags = (GG_FLAG_WALK_ONLY if walk_only else 0) | (0 if download else GG_FLAG_NO_DOWNLOAD)
+        if a is None and download and not walk_only:
+            a = np.zeros((n, 3)); fPot = np.zeros(n); dtGrav = np.zeros(n); fWeight = np.zeros(n)
+        prm = self._params(g, accumulate, flags)
+        st = gg_stats()
+        ptr = lambda v: v.ctypes.data_as(C.c_void_p) if v is not None else None
+        _check(self._L.gg_gravity(self._ctx, C.byref(prm), ptr(a), ptr(fPot), ptr(dtGrav), ptr(fWeight), C.byref(st)),
+               "gg_gravity")
+        self.stats = {k: getattr(st, k) for k, _ in gg_stats._fields_}
+        out = dict(self.stats)
+        out.update(acc=a, pot=fPot, dtGrav=dtGrav, fWeight=fWeight)
+        return out
+
+    def pkdBucketCounts(self) -> np.ndarray:
+        """(nPart, nCellSoft, nCellNewt) per tree node after pkdGravAll -- what pkdBucketWalk leaves in
+        pkd->nPart/nCellSoft/nCellNewt (walk.c:175-177); -1 where no active sink bucket."""
+        counts = np.zeros((self.tree.nNodes, 3), dtype=np.int32)
+        _check(self._L.gg_bucket_counts(self._ctx, counts.ctypes.data_as(C.c_void_p)), "gg_bucket_counts")
+        return counts
+
+    def pkdBucketWalk(self, iBucket: int, g: GravityParams):
+        """pkdBucketWalk (walk.c:306) for one bucket: returns (nPart, nCellSoft, nCellNewt)."""
+        if not getattr(self, "_uploaded", False):
+            self.upload()
+        prm = self._params(g, 0, 0)
+        n3 = np.zeros(3, dtype=np.int32)
+        _check(self._L.gg_bucket_walk(self._ctx, C.byref(prm), int(iBucket), _i(n3)), "gg_bucket_walk")
+        return tuple(int(v) for v in n3)
+
+    def pkdEwaldInit(self, fhCut: float = 2.8, iOrder: int = 4) -> np.ndarray:
+        """pkdEwaldInit (ewald.c:182): rows (hx,hy,hz,hCfac,hSfac) of the k-space table."""
+        g = GravityParams(bPeriodic=1, iEwOrder=iOrder, fEwhCut=fhCut)
+        prm = self._params(g, 0, 0)
+        buf = np.zeros((4096, 5))
+        n = C.c_int()
+        _check(self._L.gg_ewald_table(self._ctx, C.byref(prm), buf.ctypes.data_as(C.c_void_p), 4096, C.byref(n)),
+               "gg_ewald_table")
+        return buf[: n.value].copy()

@@ -1,0 +1,175 @@
+/*
+ * gasoline_b200.h -- C ABI of the B200-native tree-gravity force evaluation.
+ *
+ * This is the drop-in boundary for ONE path of Gasoline: the per-rank gravity driver
+ *     pkdGravAll (pkd.c:2868, prototype pkd.h:797-801)
+ *       -> pkdBucketWalk (walk.c:306, walk.h:32) -> pkdBucketInteract (grav.c:23, grav.h:100)
+ *       -> pkdEwaldInit / pkdBucketEwald (ewald.c:182 / ewald.c:15, ewald.h:7-8)
+ * The reference has no FFI or plugin table: pstGravity (pst.c:3310-3315) calls pkdGravAll directly.  A C host is
+ * switched over by linking a replacement pkdGravAll that flattens its PKD into the plain arrays below and calls
+ * gg_gravity (the shim is gasoline_b200/csrc/pkd_gravall_shim.c; INTEGRATION.md shows the link line).
+ *
+ * Conventions: plain pointers and sizes only; every function returns GG_OK (0) or a negative GG_ERR_* code and
+ * never falls back to a CPU path -- without a usable CUDA device gg_create fails.  gg_last_error() returns a
+ * human-readable message for the calling thread.  One context per rank/GPU; a context is not re-entrant (the
+ * reference calls pkdGravAll once per rank per force evaluation from that rank's only thread).
+ * All floating-point inputs are the host's doubles, bit for bit (FLOAT is double, floattype.h:18): the opening
+ * decisions are made in FP64 with the reference's operation order so per-bucket list counts are identical.
+ */
+#ifndef GASOLINE_B200_H
+#define GASOLINE_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GG_OK 0
+#define GG_ERR_CUDA (-1)       /* a CUDA runtime call failed (message has file:line and the CUDA error) */
+#define GG_ERR_ARG (-2)        /* invalid argument / call order */
+#define GG_ERR_UNSUPPORTED (-3) /* e.g. bDoSun, iOrder outside 1..4, bucket larger than GG_MAX_BUCKET */
+#define GG_ERR_NOMEM (-4)
+
+#define GG_NMOM 31       /* Q6 O10 H15 in the order of struct pkdCalcCellStruct, pkd.h:441-451 */
+#define GG_NROOT 35      /* struct ilCellNewt, pkd.h:481-494: m,x,y,z,xx,yy,xy,xz,yz,zz, 10 octopole, 15 hexadecapole */
+#define GG_MAX_BUCKET 64 /* most particles one bucket may hold (reference default nBucket=8, master.c:480) */
+
+typedef struct gg_context gg_context;
+
+/*
+ * A k-d tree exactly as pkdBuildBinary + pkdThreadTree leave it in pkd->kdNodes (pkd.h:454-469), field by field
+ * in SoA form.  iLower = first child or -1 for a bucket; iUpper = next cell of the threaded depth-first sweep
+ * (pkd.c:2590-2620), -1 at the end.  pLower/pUpper index the particle arrays of the same domain.
+ */
+typedef struct gg_tree {
+    int nNodes;
+    int iRoot;            /* pkd->iRoot */
+    const double *bnd;    /* [nNodes][6]  bnd.fMin[3], bnd.fMax[3] */
+    const double *r;      /* [nNodes][3]  centre of mass */
+    const double *fMass;  /* [nNodes] */
+    const double *fSoft;  /* [nNodes]     mass-weighted softening */
+    const double *fOpen2; /* [nNodes]     squared opening radius (pkdCalcOpen, pkd.c:2228) */
+    const double *mom;    /* [nNodes][GG_NMOM] reduced multipoles about r (pkdCalcCell, pkd.c:2018) */
+    const int *pLower;    /* [nNodes] */
+    const int *pUpper;    /* [nNodes] */
+    const int *iLower;    /* [nNodes] */
+    const int *iUpper;    /* [nNodes] */
+} gg_tree;
+
+/* pkd->pStore[0..nLocal) in tree order, the five fields the path reads (pkd.h:90-108) + the ACTIVE bit. */
+typedef struct gg_particles {
+    int n;
+    const double *x, *y, *z; /* r[0..2] */
+    const double *fMass;
+    const double *fSoft;
+    const int *active; /* TYPEQueryACTIVE(p) != 0 (pkd.h:349); NULL = all active */
+} gg_particles;
+
+/* The scalar arguments of pkdGravAll (pkd.h:797-801) that the GPU path honours. */
+typedef struct gg_params {
+    int nReps;       /* image shells for the tree walk (nReplicas) */
+    int bPeriodic;
+    int iOrder;      /* multipole order of the tree lists, 1..4 */
+    int bEwald;
+    int iEwOrder;    /* order of the Ewald root expansion, 1..4 */
+    double fEwCut;   /* dEwCut  (master.c:669) */
+    double fEwhCut;  /* dEwhCut (master.c:672) */
+    int bComove;     /* with !bPeriodic: uniform background term, pkd.c:2967-2991 */
+    double dRhoFac;
+    double fPeriod[3]; /* pkd->fPeriod; >= DBL_MAX on an axis = not periodic (walk.c:326) */
+    int accumulate;  /* 1: a, fPot += and dtGrav = max(old,new) like the reference; 0: overwrite */
+    int flags;       /* GG_FLAG_* */
+} gg_params;
+
+#define GG_FLAG_WALK_ONLY 1 /* build lists and count them, skip all force arithmetic (parity hook) */
+#define GG_FLAG_NO_DOWNLOAD 2 /* leave results on the device (gg_device_results); host pointers may be NULL */
+
+/* What pkdGravAll returns through its pointer arguments (+ device timings in milliseconds, CUDA events). */
+typedef struct gg_stats {
+    int nActive;
+    double dPartSum, dCellSum, dSoftSum; /* pkd.c:2945-2949 */
+    double dFlop;                        /* grav.c:246-247 + ewald.c:175-176, the reference's own scoring */
+    double dFlopEwald;                   /* the Ewald share of dFlop */
+    double msTree;                       /* fused walk+interact kernel */
+    double msEwald;                      /* Ewald kernel */
+    double msTotal;                      /* everything on the device between upload and download */
+    int nKernelLaunches;                 /* kernels of this library launched by the call */
+    int nMaxPart, nMaxCellSoft, nMaxCellNewt; /* per-bucket list maxima (the reference's diag line, pkd.c:3057) */
+} gg_stats;
+
+const char *gg_last_error(void);
+int gg_version(void);
+
+/* device < 0: use the current device.  Fails (GG_ERR_CUDA) when no CUDA device is usable. */
+int gg_create(gg_context **pctx, int device);
+void gg_destroy(gg_context *ctx);
+
+/*
+ * Ingest the caller's domain: replaces pkd->kdNodes / pkd->pStore (host memory; pinned memory from gg_host_alloc
+ * copies fastest).  Must be called again whenever the host rebuilds its tree or moves particles (the reference
+ * frees and re-allocates kdNodes at every build, pkd.c:2636-2642).  idSelf is this domain's rank (pkd->idSelf).
+ */
+int gg_set_local(gg_context *ctx, int idSelf, const gg_tree *tree, const gg_particles *part);
+
+/*
+ * Multi-rank runs only.  The gathered top tree pkd->kdTop[1..nCell) (heap indexed, ROOT=1, pkd.h:77-86, filled by
+ * pkdDistribCells pkd.c:4376): for each heap cell its pLower (-1 interior, else the rank owning the leaf), the
+ * used flag (pUpper != 0), r, fMass, fSoft, fOpen2 and mom.  With one rank this call is not needed.
+ */
+int gg_set_top(gg_context *ctx, int nCell, const int *pLower, const int *bUsed, const double *r, const double *fMass,
+               const double *fSoft, const double *fOpen2, const double *mom);
+
+/*
+ * Multi-rank runs only.  A remote domain's tree and particles (what pkdRemoteWalk reads through mdlAquire,
+ * walk.c:181-304), or a pruned locally-essential subset of it with the same link semantics.  bDevice != 0: the
+ * pointers are device pointers on this context's GPU (filled by an NCCL gather), else host pointers.
+ */
+int gg_set_remote(gg_context *ctx, int id, const gg_tree *tree, const gg_particles *part, int bDevice);
+int gg_clear_remote(gg_context *ctx);
+
+/* pkd->ilcnRoot (pkdCalcRoot/pkdDistribRoot, pkd.c:4395-4493): complete l<=4 moments of the whole box for Ewald. */
+int gg_set_root_moments(gg_context *ctx, const double root[GG_NROOT]);
+
+/*
+ * One force evaluation = pkdGravAll (pkd.c:2868).  Output arrays are indexed like the local particles (tree
+ * order): a[3*i..], fPot[i], dtGrav[i] (running max of 1/dt^2, grav.c:100), fWeight[i] (flops of the particle's
+ * bucket, written for active particles only, pkd.c:2851).  Inactive particles are left untouched.
+ */
+int gg_gravity(gg_context *ctx, const gg_params *prm, double *a, double *fPot, double *dtGrav, double *fWeight,
+               gg_stats *stats);
+
+/* After gg_gravity: per-node (nPart, nCellSoft, nCellNewt) of the local tree, -1 where the node is not a bucket
+ * with an active sink -- the counters pkdBucketWalk leaves in pkd->nPart/nCellSoft/nCellNewt (walk.c:175-177). */
+int gg_bucket_counts(gg_context *ctx, int *counts3);
+
+/* Per-bucket debug seam mirroring pkdBucketWalk (walk.h:32): the lists of ONE bucket, as (global node index,
+ * image) pairs for cells and (particle index, image) pairs for particles.  Returns counts in n3. */
+int gg_bucket_walk(gg_context *ctx, const gg_params *prm, int iBucket, int n3[3]);
+
+/* pkdEwaldInit (ewald.c:182): the k-space table the device uses, 5 doubles per row (hx,hy,hz,hCfac,hSfac). */
+int gg_ewald_table(gg_context *ctx, const gg_params *prm, double *ewt5, int nMax, int *pnEwh);
+
+/* Device pointers to the last results (tree order): a (3 doubles per particle), fPot, dtGrav, fWeight. */
+int gg_device_results(gg_context *ctx, void **a, void **fPot, void **dtGrav, void **fWeight);
+
+/* Pinned host memory for the arrays handed to gg_set_local / gg_gravity. */
+int gg_host_alloc(void **p, size_t bytes);
+int gg_host_free(void *p);
+
+/*
+ * Host-side tree construction with the semantics of pkdBuildBinary (pkd.c:2627: midpoint split of the longest axis
+ * of the squeezed box, buckets of <= nBucket, pkdCalcCell moments, OPEN_JOSH opening radius, threaded links) and
+ * pkdCalcRoot.  Used by hosts that do not already own a Gasoline tree (bench.py, tests); a Gasoline host passes its
+ * own kdNodes instead.  Particles are permuted in place into tree order; iOrder receives the permutation.
+ */
+typedef struct gg_built_tree gg_built_tree;
+int gg_tree_build(int n, double *x, double *y, double *z, double *fMass, double *fSoft, int *active, int *iOrder,
+                  int nBucket, double dTheta, int iOrder_mom, int nThreads, gg_built_tree **out);
+int gg_tree_view(const gg_built_tree *bt, gg_tree *view, double root[GG_NROOT]);
+void gg_tree_free(gg_built_tree *bt);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
