@@ -16,8 +16,8 @@
 
 #define GG_WARPS_PER_CTA 4
 #define GG_MAX_SINKS 8      // sinks evaluated per warp pass (accumulators live in registers)
-#define GG_STACK_CAP 1024   // walk frontier entries per warp
-#define GG_STACK_DFS_MARGIN 160
+#define GG_STACK_CAP 512    // walk frontier entries per warp
+#define GG_STACK_DFS_MARGIN 128
 #define GG_MAX_IMAGES 128
 
 struct __align__(16) NodeW {
