@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""bench.py -- tree-gravity force evaluation (Gasoline's pkdGravAll path) on B200: interactions/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload plummer:1000000:0.7]
+
+A "step" is ONE force evaluation = one pkdGravAll (pkd.c:2868) over every sink bucket of the workload: tree walks,
+list evaluation and (periodic workloads) the Ewald correction.  The metric is the reference's own interaction
+count (pkd.c:2945-2949: particle-list + intra-bucket pairs + Newtonian-cell + softened-cell entries summed over
+active sinks; Ewald terms are not interactions) divided by time.
+
+  value     device time (CUDA events recorded by the library on the stream it launches on) with the tree and the
+            particles already resident in HBM; L2 is flushed between timed iterations.
+  e2e       the same through the public host API with HOST buffers: every step re-ingests the host's tree +
+            particles from pinned memory (gg_set_local: the reference frees and rebuilds kdNodes before every
+            gravity call, pkd.c:2636-2642), runs the kernels and reads a, fPot, dtGrav, fWeight back.
+  roofline  the fused walk+interact kernel against the FP32 FMA pipe (this is FP32 CUDA-core + SFU work, not HBM- or
+            tensor-bound -- DESIGN.md): achieved = the reference's own flop score of the lists it evaluated
+            (grav.c:246-247) / kernel time; peak = dependent-FFMA microbenchmark measured in this run on this GPU.
+            The HBM view (algorithmic bytes / time vs MEASURED_PEAKS.json hbm_gbs) is reported beside it.
+  cpu_baseline / --impl reference
+            the reference's own compiled pkdGravAll on the host cores (oracle/cpu_baseline.py).
+
+Workload at N=1 = BASELINE.json configs[1]: isolated Plummer sphere, 1M particles, theta=0.7, no Ewald.
+N>1: weak scaling -- N x 1M-particle Plummer sphere split into N ORB domains, one per GPU (gasoline_b200/domain.py).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "particle interactions/s (tree gravity, pkdGravAll)"
+UNIT = "interactions/s"
+PER_GPU_PARTICLES = 1_000_000
+THETA = 0.7
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, help="plummer:N:theta | periodic:n:theta (default: configs[1])")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_spec(a) -> str:
+    if a.workload:
+        return a.workload
+    return f"plummer:{PER_GPU_PARTICLES * max(a.gpus, 1)}:{THETA}"
+
+
+def config_of(spec: str, n_gpus: int) -> dict:
+    kind, n, theta = spec.split(":")
+    if kind == "plummer":
+        name = f"isolated Plummer sphere, {int(n)} particles, theta={theta}, no Ewald, nBucket=8, iOrder=4 (hexadecapole)"
+    else:
+        name = f"periodic box {n}^3 particles, theta={theta}, nReplicas=1, Ewald on, nBucket=8, iOrder=4"
+    return {"workload": name, "spec": spec, "particles_per_gpu": int(n) ** (1 if kind == "plummer" else 3) // n_gpus,
+            "parallelism": "1 GPU" if n_gpus == 1 else f"{n_gpus} ORB domains, one per GPU, LET exchange over NCCL",
+            "l2": "flushed between timed iterations (384 MB memset)"}
+
+
+# ---------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- reference arm
+def run_reference(a):
+    """The reference's own CPU pkdGravAll on the host cores; rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle import cpu_baseline
+    spec = workload_spec(a)
+    per_step = max(3.0, min(a.cpu_seconds, 100.0 / max(a.steps + a.warmup, 1)))
+    t0 = time.time()
+    r = cpu_baseline.run(spec, per_step, 0, "auto", repeats=max(1, a.steps + a.warmup))
+    out = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+           "ms_per_step": r["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic", "impl": "reference", "config": config_of(spec, a.gpus),
+           "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                            "sample": r["sample"]},
+           "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0, "wall_s": time.time() - t0}
+    print(json.dumps(out), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------- our arm
+def algorithmic_bytes(n_particles: int, n_nodes: int) -> float:
+    """Compulsory HBM traffic of one force evaluation: every source particle record (32 B) and every
+    tree node (64 B walk record + 128 B moment record) read once, 48 B of results written per particle."""
+    return 32.0 * n_particles + 192.0 * n_nodes + 48.0 * n_particles
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from gasoline_b200 import build as gbuild, ics
+    from gasoline_b200.pkd import PKD, GravityParams, pinned_empty
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    gbuild.build()
+    spec = workload_spec(a)
+    kind, n_s, theta_s = spec.split(":")
+    theta = float(theta_s)
+    if kind == "plummer":
+        p = ics.plummer(int(n_s))
+        g = GravityParams(nReps=0, bPeriodic=0, bEwald=0)
+    else:
+        p = ics.periodic_box(int(n_s))
+        g = GravityParams(nReps=1, bPeriodic=1, bEwald=1)
+
+    t0 = time.time()
+    if world == 1:
+        pkd = PKD(device=local, fPeriod=p.period, pinned=True)
+        pkd.pkdLoadParticles(p.x, p.y, p.z, p.m, p.h)
+        pkd.pkdBuildBinary(8, theta, 4)
+        exchange = None
+    else:
+        from gasoline_b200 import domain
+        pkd, exchange = domain.setup_rank(p, theta, rank, world, local)
+    t_tree = time.time() - t0
+    n = pkd.nLocal
+    pkd.upload()
+    if exchange is not None:
+        exchange()  # LET exchange once before the resident-input timing
+    peak_tf, _ = pkd.measure_fp32_peak()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident timing
+    for _ in range(a.warmup):
+        pkd.pkdGravAll(g, download=False)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    ms_total = ms_tree = ms_ewald = 0.0
+    launches = 0
+    wall0 = time.perf_counter()
+    for _ in range(a.steps):
+        pkd.flush_l2()
+        st = pkd.pkdGravAll(g, download=False)
+        ms_total += st["msTotal"]; ms_tree += st["msTree"]; ms_ewald += st["msEwald"]
+        launches += st["nKernelLaunches"]
+    barrier()
+    wall_resident = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    inter = st["dPartSum"] + st["dCellSum"] + st["dSoftSum"]
+
+    # ---- end to end through the host API: host buffers in, host buffers out, every step
+    out_a, out_p, out_d, out_w = (pinned_empty((n, 3)), pinned_empty(n), pinned_empty(n), pinned_empty(n))
+    for _ in range(min(a.warmup, 2)):
+        pkd.upload(); pkd.pkdGravAll(g, out_a, out_p, out_d, out_w, accumulate=False)
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(a.steps):
+        pkd.upload()
+        if exchange is not None:
+            exchange()
+        pkd.pkdGravAll(g, out_a, out_p, out_d, out_w, accumulate=False)
+    barrier()
+    e2e_s = time.perf_counter() - e0
+    h2d = pkd.upload_bytes()
+    d2h = 6 * 8 * n
+
+    # ---- reduce over ranks: time = max, work = sum
+    vals = torch.tensor([ms_total, ms_tree, e2e_s, wall_resident], dtype=torch.float64, device="cuda")
+    sums = torch.tensor([inter, st["dFlop"] - st["dFlopEwald"], float(launches), float(n), float(pkd.tree.nNodes),
+                         float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    ms_total_max, ms_tree_max, e2e_max, wall_res_max = vals.tolist()
+    inter_all, flop_tree_all, launches_all, n_all, nodes_all, h2d_all, d2h_all = sums.tolist()
+
+    if rank == 0:
+        ms_step = ms_total_max / a.steps
+        tree_ms = ms_tree_max / a.steps
+        value = inter_all / (ms_step * 1e-3)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        # roofline of the dominant kernel (fused walk+interact), per launch, per GPU
+        flop_per_launch = flop_tree_all / world
+        ach_tf = flop_per_launch / (tree_ms * 1e-3) * 1e-12
+        alg_bytes = algorithmic_bytes(int(n_all), int(nodes_all)) / world
+        roof = {"bound": "fp32", "kernel": "k_tree_gravity<4>", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": ach_tf / peak_tf if peak_tf else None, "traffic": None,
+                "peak_source": "dependent-FFMA microbenchmark measured in this run (nominal 74.4 TFLOP/s at 1965 MHz)",
+                "flops": "the reference's own score of the evaluated lists (grav.c:246-247: 38/particle, 82/soft "
+                         "cell, 312/hexadecapole cell)",
+                "hbm": {"achieved": alg_bytes / (tree_ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": alg_bytes / (tree_ms * 1e-3) * 1e-9 / hbm_peak,
+                        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"},
+                "ms_per_launch": tree_ms}
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+               "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f32 (FP64 opening tests, FP64 accumulation across lanes, FP64 Ewald)", "data": "synthetic",
+               "config": config_of(spec, world), "clocks": clocks,
+               "e2e": {"value": inter_all / (e2e_max / a.steps), "unit": UNIT, "h2d_bytes_per_step": int(h2d_all),
+                       "d2h_bytes_per_step": int(d2h_all), "ms_per_step": e2e_max / a.steps * 1e3},
+               "gpu_launches": int(launches_all), "roofline": roof,
+               "interactions_per_step": inter_all, "host_tree_build_s": t_tree,
+               "wall_ms_per_step_resident": wall_res_max / a.steps * 1e3}
+        if world == 1 and not a.no_cpu_baseline:
+            try:
+                r = subprocess.run([sys.executable, "-m", "oracle.cpu_baseline", "--workload", spec, "--seconds",
+                                    str(a.cpu_seconds)], cwd=ROOT, capture_output=True, text=True, timeout=900)
+                cb = json.loads(r.stdout.strip().splitlines()[-1])
+                out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            except Exception as e:  # the GPU line must still be printed
+                out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
+                                       "sample": f"failed: {e}"}
+        print(json.dumps(out), flush=True)
+    pkd.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

@@ -60,7 +60,7 @@ struct gg_context {
     std::vector<int> hActive; // host copy of the local ACTIVE flags (empty = all active)
     // device buffers
     DevBuf nodes, momf, momq, parts, active, hsoft, tasks, ngroups, goffs, counts, acc, pot, dtg, fweight, nloop, sums,
-        misc, imgoff, ewt, raw, rawi, cubtmp;
+        misc, imgoff, ewt, raw, rawi, cubtmp, flush;
     void *pinned = nullptr;
     size_t pinnedCap = 0;
     int nTasks = 0;
@@ -176,6 +176,23 @@ __global__ void k_comove(int n, const PartS *parts, const int *active, double dR
     pot[i] -= 0.5 * dRhoFac * r2;
 }
 
+// FP32 FMA-pipe peak: 8 independent dependent-FFMA chains per thread, all SMs, enough warps to hide the 4-cycle
+// FFMA latency.  Gives the denominator of the FP32 roofline on THIS GPU at its clocks under load.
+__global__ void __launch_bounds__(256) k_fma_peak(int iters, float *out) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f,
+          a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float m = 0.999f + blockIdx.x * 1e-9f, b = 1e-3f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fmaf(a0, m, b); a1 = fmaf(a1, m, b); a2 = fmaf(a2, m, b); a3 = fmaf(a3, m, b);
+            a4 = fmaf(a4, m, b); a5 = fmaf(a5, m, b); a6 = fmaf(a6, m, b); a7 = fmaf(a7, m, b);
+        }
+    }
+    const float r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 123.456f) out[0] = r; // never true: keeps the chains alive
+}
+
 int upload_domain(gg_context *c, const gg_tree *t, const gg_particles *pp, int nodeBase, int partBase, bool local,
                   bool onDevice) {
     const int nn = t->nNodes, np = pp->n;
@@ -267,7 +284,7 @@ void gg_destroy(gg_context *c) {
     cudaStreamSynchronize(c->st);
     DevBuf *all[] = {&c->nodes, &c->momf, &c->momq, &c->parts, &c->active, &c->hsoft, &c->tasks, &c->ngroups,
                      &c->goffs, &c->counts, &c->acc, &c->pot, &c->dtg, &c->fweight, &c->nloop, &c->sums, &c->misc,
-                     &c->imgoff, &c->ewt, &c->raw, &c->rawi, &c->cubtmp};
+                     &c->imgoff, &c->ewt, &c->raw, &c->rawi, &c->cubtmp, &c->flush};
     for (DevBuf *b : all)
         if (b->p) cudaFree(b->p);
     if (c->pinned) cudaFreeHost(c->pinned);
@@ -729,6 +746,40 @@ int gg_ewald_table(gg_context *c, const gg_params *prm, double *ewt5, int nMax, 
     gg_ewald_table_host(c->root, prm->fPeriod[0], prm->fEwhCut, prm->iEwOrder, ewt);
     *pnEwh = (int)(ewt.size() / 5);
     if (ewt5) memcpy(ewt5, ewt.data(), sizeof(double) * 5 * (size_t)(*pnEwh < nMax ? *pnEwh : nMax));
+    return GG_OK;
+}
+
+int gg_measure_fp32_peak(gg_context *c, double *pTflops, double *pMs) {
+    if (!c || !pTflops) return fail(GG_ERR_ARG, "gg_measure_fp32_peak: null");
+    CK(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = ensure(c, c->misc, 16 * sizeof(int)))) return rc;
+    const int iters = 4096, blocks = c->nSM * 8, threads = 256;
+    double best = 0.0, bestMs = 0.0;
+    for (int rep = 0; rep < 4; ++rep) { // first repetition warms the clocks up
+        CK(cudaEventRecord(c->ev[0], c->st));
+        k_fma_peak<<<blocks, threads, 0, c->st>>>(iters, (float *)c->misc.p);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(c->ev[1], c->st));
+        CK(cudaStreamSynchronize(c->st));
+        float ms;
+        CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+        const double tf = 2.0 * 64.0 * iters * (double)blocks * threads / (ms * 1e-3) * 1e-12;
+        if (rep > 0 && tf > best) { best = tf; bestMs = ms; }
+    }
+    *pTflops = best;
+    if (pMs) *pMs = bestMs;
+    return GG_OK;
+}
+
+int gg_flush_l2(gg_context *c) {
+    if (!c) return fail(GG_ERR_ARG, "gg_flush_l2: null");
+    CK(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)384 << 20; // 3x the 126 MB L2
+    int rc;
+    if ((rc = ensure(c, c->flush, bytes))) return rc;
+    CK(cudaMemsetAsync(c->flush.p, 0x5a, bytes, c->st));
+    CK(cudaStreamSynchronize(c->st));
     return GG_OK;
 }
 

@@ -63,7 +63,7 @@ def periodic_box(n: int, seed: int = 12345, mode: str = "zeldovich", rms_disp: f
         amp[0, 0, 0] = 0.0
         dk = amp * (rng.normal(size=k2.shape) + 1j * rng.normal(size=k2.shape))
         # displacement = grad(phi): psi_k = i k delta_k / k^2
-        d = np.stack([np.fft.irfftn(1j * kk * dk / k2, s=(n, n, n)) for kk in (kx, ky, kz)])
+        d = np.stack([np.fft.irfftn(1j * kk * dk / k2, s=(n, n, n), axes=(0, 1, 2)) for kk in (kx, ky, kz)])
         d *= rms_disp / n / np.sqrt(np.mean(np.sum(d * d, axis=0)) / 3.0 + 1e-300)
     pos = []
     for A, dd in zip((X, Y, Z), d):

@@ -84,6 +84,8 @@ def load_library(path: str | None = None):
                                 C.POINTER(C.c_void_p)]
     L.gg_tree_view.argtypes = [C.c_void_p, C.POINTER(gg_tree), _dp]
     L.gg_tree_free.argtypes = [C.c_void_p]
+    L.gg_measure_fp32_peak.argtypes = [C.c_void_p, _dp, _dp]
+    L.gg_flush_l2.argtypes = [C.c_void_p]
     _lib = L
     return L
 
@@ -154,8 +156,11 @@ class Tree:
 class PKD:
     """One rank's particle store + tree on one B200 (mirrors struct pkdContext, pkd.h:597-660)."""
 
-    def __init__(self, device: int = -1, idSelf: int = 0, fPeriod=(FLOAT_MAXVAL,) * 3):
+    def __init__(self, device: int = -1, idSelf: int = 0, fPeriod=(FLOAT_MAXVAL,) * 3, pinned: bool = False):
+        """pinned: keep pStore / kdNodes copies in page-locked host memory (what a host does with gg_host_alloc so
+        that the per-step upload runs at full PCIe/C2C speed)."""
         self._L = load_library()
+        self.pinned = pinned
         self._ctx = C.c_void_p()
         _check(self._L.gg_create(C.byref(self._ctx), device), "gg_create")
         self.idSelf = idSelf
@@ -183,12 +188,20 @@ class PKD:
     # -- particles + tree -----------------------------------------------------------------------------------
     def pkdLoadParticles(self, x, y, z, fMass, fSoft, active=None):
         """Fill pStore (what pkdReadTipsy pkd.c:297 does on the host). Arrays are copied; order = iOrder."""
-        self.x, self.y, self.z, self.fMass, self.fSoft = (np.array(a, dtype=np.float64, copy=True)
-                                                           for a in (x, y, z, fMass, fSoft))
+        self.x, self.y, self.z, self.fMass, self.fSoft = (self._own(a, np.float64) for a in (x, y, z, fMass, fSoft))
         self.nLocal = int(self.x.shape[0])
-        self.active = None if active is None else np.array(active, dtype=np.int32, copy=True)
+        self.active = None if active is None else self._own(active, np.int32)
         self.iOrderMap = np.arange(self.nLocal, dtype=np.int32)
         self.tree = None
+
+    def _own(self, a, dt):
+        """Private copy of a host array, in pinned memory when the PKD was created with pinned=True."""
+        a = np.asarray(a)
+        if not self.pinned:
+            return np.array(a, dtype=dt, copy=True)
+        out = pinned_empty(a.shape, dt)
+        out[...] = a
+        return out
 
     def pkdBuildBinary(self, nBucket: int = 8, dCrit: float = 0.7, iOrder: int = 4, nThreads: int = 0):
         """pkdBuildBinary (pkd.c:2627) + pkdCalcRoot (pkd.c:4395): spatial-bisection tree, OPEN_JOSH opening radius
@@ -205,7 +218,7 @@ class PKD:
             root = np.zeros(GG_NROOT)
             _check(self._L.gg_tree_view(bt, C.byref(v), _d(root)), "gg_tree_view")
             nn = v.nNodes
-            cp = lambda p, shape, dt: np.ctypeslib.as_array(p, shape=shape).astype(dt, copy=True)
+            cp = lambda p, shape, dt: self._own(np.ctypeslib.as_array(p, shape=shape), dt)
             self.tree = Tree(nn, v.iRoot, bnd=cp(v.bnd, (nn, 6), np.float64), r=cp(v.r, (nn, 3), np.float64),
                              fMass=cp(v.fMass, (nn,), np.float64), fSoft=cp(v.fSoft, (nn,), np.float64),
                              fOpen2=cp(v.fOpen2, (nn,), np.float64), mom=cp(v.mom, (nn, GG_NMOM), np.float64),
@@ -220,10 +233,9 @@ class PKD:
 
     def pkdSetTree(self, tree: Tree, x, y, z, fMass, fSoft, active=None, ilcnRoot=None, iOrderMap=None):
         """Adopt a tree built elsewhere (e.g. the host's own kdNodes); particles must already be in its order."""
-        self.x, self.y, self.z, self.fMass, self.fSoft = (np.array(a, dtype=np.float64, copy=True)
-                                                           for a in (x, y, z, fMass, fSoft))
+        self.x, self.y, self.z, self.fMass, self.fSoft = (self._own(a, np.float64) for a in (x, y, z, fMass, fSoft))
         self.nLocal = int(self.x.shape[0])
-        self.active = None if active is None else np.array(active, dtype=np.int32, copy=True)
+        self.active = None if active is None else self._own(active, np.int32)
         self.tree = tree
         self.ilcnRoot = None if ilcnRoot is None else np.array(ilcnRoot, dtype=np.float64, copy=True)
         self.iOrderMap = np.arange(self.nLocal, dtype=np.int32) if iOrderMap is None else np.asarray(iOrderMap, np.int32)
@@ -268,7 +280,7 @@ class PKD:
                          g.dRhoFac, (C.c_double * 3)(*self.fPeriod), accumulate, flags)
 
     def pkdGravAll(self, g: GravityParams, a=None, fPot=None, dtGrav=None, fWeight=None, walk_only=False,
-                   download=True):
+                   download=True, accumulate=None):
         """pkdGravAll (pkd.c:2868).  With arrays given: a, fPot accumulate (+=), dtGrav is a running max, fWeight is
         overwritten for active particles -- the reference's in-place semantics on pStore.  Without: fresh arrays.
         Returns a dict with the arrays (tree order) and the scalars the reference returns through pointers
@@ -276,7 +288,7 @@ class PKD:
         if not getattr(self, "_uploaded", False):
             self.upload()
         n = self.nLocal
-        accumulate = 1 if a is not None else 0
+        accumulate = (1 if a is not None else 0) if accumulate is None else int(bool(accumulate))
         flags = (GG_FLAG_WALK_ONLY if walk_only else 0) | (0 if download else GG_FLAG_NO_DOWNLOAD)
         if a is None and download and not walk_only:
             a = np.zeros((n, 3)); fPot = np.zeros(n); dtGrav = np.zeros(n); fWeight = np.zeros(n)
@@ -289,6 +301,24 @@ class PKD:
         out = dict(self.stats)
         out.update(acc=a, pot=fPot, dtGrav=dtGrav, fWeight=fWeight)
         return out
+
+    def upload_bytes(self) -> int:
+        """Bytes gg_set_local copies host->device for the current tree + particles."""
+        t = self.tree
+        b = sum(getattr(t, k).nbytes for k in Tree.FIELDS if k != "bnd")
+        b += sum(a.nbytes for a in (self.x, self.y, self.z, self.fMass, self.fSoft))
+        if self.active is not None:
+            b += self.active.nbytes
+        return int(b)
+
+    def measure_fp32_peak(self):
+        """(TFLOP/s, ms) of the dependent-FFMA microbenchmark on this GPU (gg_measure_fp32_peak)."""
+        tf, ms = C.c_double(), C.c_double()
+        _check(self._L.gg_measure_fp32_peak(self._ctx, C.byref(tf), C.byref(ms)), "gg_measure_fp32_peak")
+        return tf.value, ms.value
+
+    def flush_l2(self):
+        _check(self._L.gg_flush_l2(self._ctx), "gg_flush_l2")
 
     def pkdBucketCounts(self) -> np.ndarray:
         """(nPart, nCellSoft, nCellNewt) per tree node after pkdGravAll -- what pkdBucketWalk leaves in

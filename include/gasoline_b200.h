@@ -153,6 +153,12 @@ int gg_ewald_table(gg_context *ctx, const gg_params *prm, double *ewt5, int nMax
 /* Device pointers to the last results (tree order): a (3 doubles per particle), fPot, dtGrav, fWeight. */
 int gg_device_results(gg_context *ctx, void **a, void **fPot, void **dtGrav, void **fWeight);
 
+/* Measurement aids for bench.py (no reference counterpart): the FP32 FMA-pipe peak of this GPU at its clocks under
+ * load (dependent-FFMA microbenchmark on all SMs, TFLOP/s; kernel duration in ms) -- the denominator of the FP32
+ * roofline -- and an L2 flush (writes 384 MB) to put between timed iterations. */
+int gg_measure_fp32_peak(gg_context *ctx, double *pTflops, double *pMs);
+int gg_flush_l2(gg_context *ctx);
+
 /* Pinned host memory for the arrays handed to gg_set_local / gg_gravity. */
 int gg_host_alloc(void **p, size_t bytes);
 int gg_host_free(void *p);

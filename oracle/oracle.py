@@ -37,6 +37,7 @@ def lib():
         L.orc_export_nodes.argtypes = [C.c_void_p] + [_dp] * 7 + [_ip] * 5
         L.orc_export_particles.argtypes = [C.c_void_p, _ip, _dp, _dp, _dp, _dp, _dp, _ip]
         L.orc_export_root.argtypes = [C.c_void_p, _dp]
+        L.orc_set_active_tree.argtypes = [C.c_void_p, _ip]
         L.orc_import_tree.argtypes = [C.c_void_p, C.c_int, C.c_int] + [_dp] * 6 + [_ip] * 4 + [_dp]
         L.orc_ewald_table.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_int]
         L.orc_gravity.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
@@ -102,6 +103,9 @@ class OracleGravity:
         t["root"] = np.zeros(35)
         L.orc_export_root(self.h, t["root"])
         return t
+
+    def set_active_tree(self, active):
+        lib().orc_set_active_tree(self.h, np.ascontiguousarray(active, dtype=np.int32))
 
     def ewald_table(self, fhCut=2.8, iOrder=4):
         buf = np.zeros((4096, 5))

@@ -178,6 +178,24 @@ void ref_export_particles(REF *r, int *iOrder, double *x, double *y, double *z, 
     }
 }
 
+/*
+ * After ref_build_tree: set the ACTIVE bit from active[] given in TREE order (what msrActiveRung does between
+ * the build and msrGravity when only some rungs are kicked, master.c:8403-8420).  Used by bench.py's CPU legs to
+ * let P processes each evaluate a disjoint slice of the sink buckets with the reference's own pkdGravAll.
+ */
+void ref_set_active_tree(REF *r, const int *active) {
+    int i, n = 0;
+    for (i = 0; i < r->n; ++i) {
+        PARTICLE *p = &r->pkd->pStore[i];
+        if (active[i]) {
+            TYPESet(p, TYPE_ACTIVE);
+            ++n;
+        } else
+            TYPEReset(p, TYPE_ACTIVE);
+    }
+    r->pkd->nActive = n;
+}
+
 /* pkd->ilcnRoot in ILCN field order (pkd.h:481-494): m,x,y,z,xx,yy,xy,xz,yz,zz, 10 octopole, 15 hexadecapole */
 void ref_export_root(REF *r, double *out35) { memcpy(out35, &r->pkd->ilcnRoot, 35 * sizeof(double)); }
 

@@ -37,6 +37,7 @@ def lib():
         L.ref_export_nodes.argtypes = [C.c_void_p] + [_dp] * 7 + [_ip] * 5
         L.ref_export_particles.argtypes = [C.c_void_p, _ip, _dp, _dp, _dp, _dp, _dp, _ip]
         L.ref_export_root.argtypes = [C.c_void_p, _dp]
+        L.ref_set_active_tree.argtypes = [C.c_void_p, _ip]
         L.ref_ewald_table.argtypes = [C.c_void_p, C.c_double, C.c_int, _dp, C.c_int]
         L.ref_gravity.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
                                   C.c_double, _dp, _dp, _dp, _dp, _ip, _dp]
@@ -88,6 +89,10 @@ class RefGravity:
         t["root"] = np.zeros(35)
         L.ref_export_root(self.h, t["root"])
         return t
+
+    def set_active_tree(self, active):
+        """ACTIVE flags in tree order, after build_tree (ref_set_active_tree)."""
+        lib().ref_set_active_tree(self.h, np.ascontiguousarray(active, dtype=np.int32))
 
     def ewald_table(self, fhCut=2.8, iOrder=4):
         buf = np.zeros((4096, 5))

@@ -1,0 +1,40 @@
+"""CPU, build container only: the oracle against the reference's compiled objects run live (oracle/_ref/libgasref.so)
+at sizes beyond the committed fixtures.  Skipped where the reference library is not present."""
+import numpy as np
+import pytest
+
+from gasoline_b200 import ics
+from oracle import oracle, reflib
+
+pytestmark = pytest.mark.skipif(not reflib.available(), reason="oracle/_ref/libgasref.so not built (needs /root/reference)")
+
+CASES = {
+    "periodic16_ewald": (lambda: ics.periodic_box(16), 0.7, dict(nReps=1, bPeriodic=1, bEwald=1)),
+    "periodic12_theta04": (lambda: ics.periodic_box(12, seed=9), 0.4, dict(nReps=1, bPeriodic=1, bEwald=1)),
+    "plummer20k": (lambda: ics.plummer(20000), 0.7, dict(nReps=0, bPeriodic=0, bEwald=0)),
+    "plummer8k_theta03": (lambda: ics.plummer(8000, seed=2), 0.3, dict(nReps=0, bPeriodic=0, bEwald=0)),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_live_reference(name):
+    mk, theta, kw = CASES[name]
+    p = mk()
+    r = reflib.RefGravity(p); r.build_tree(8, theta, 4); tr = r.tree()
+    rr = r.gravity(kw["nReps"], kw["bPeriodic"], 4, kw["bEwald"], 4); r.close()
+    o = oracle.OracleGravity(p); o.build_tree(8, theta, 4); to = o.tree()
+    ro = o.gravity(kw["nReps"], kw["bPeriodic"], 4, kw["bEwald"], 4); o.close()
+    for k in ("bnd", "r", "fMass", "fSoft", "fOpen2", "mom", "pLower", "pUpper", "iLower", "iUpper", "iOrder", "root"):
+        assert np.array_equal(tr[k], to[k]), k
+    assert np.array_equal(rr["counts"], ro["counts"])
+    for k in ("nActive", "dPartSum", "dCellSum", "dSoftSum", "dFlop"):
+        assert rr[k] == ro[k], k
+    assert np.array_equal(rr["fWeight"], ro["fWeight"])
+    d = np.linalg.norm(ro["acc"] - rr["acc"], axis=1) / np.linalg.norm(rr["acc"], axis=1)
+    assert d.max() < 2e-7
+
+
+def test_reference_struct_sizes_match_survey():
+    """sizes the data-layout discussion in DESIGN.md relies on (NBODY build)."""
+    L = reflib.lib()
+    assert [L.ref_sizeof(i) for i in range(6)] == [184, 536, 40, 88, 280, 40]
