@@ -1,0 +1,164 @@
+/*
+ * pkd_gravall_shim.c -- the drop-in: a replacement for Gasoline's pkdGravAll (pkd.c:2868, prototype pkd.h:797-801)
+ * that runs the force evaluation on a B200 through the C ABI of include/gasoline_b200.h.
+ *
+ * How a Gasoline host adopts it (INTEGRATION.md has the link lines): compile the host's pkd.c with
+ * -DpkdGravAll=pkdGravAll_cpu, compile THIS file against the host's own pkd.h with the host's own -D flags (the
+ * PARTICLE and KDN layouts change with them, so every field is copied by name -- never by offset), and link
+ * libgasoline_b200.so.  pstGravity (pst.c:3310-3315) then calls this function unchanged.
+ *
+ * What it does, per call (= per rank per force evaluation):
+ *   1. flattens pkd->kdNodes[0..nNodes) and pkd->pStore[0..nLocal) into the SoA views gg_set_local takes (pinned
+ *      staging buffers kept between calls, grown by high-water mark; the reference frees and rebuilds kdNodes before
+ *      every gravity call, pkd.c:2636-2642, so nothing can be assumed resident);
+ *   2. hands over pkd->ilcnRoot (pkdDistribRoot, pkd.c:4472) when Ewald is on;
+ *   3. gg_gravity with the reference's in-place semantics: a, fPot += ; dtGrav = max ; fWeight = for ACTIVE
+ *      particles only, and returns nActive / dPartSum / dCellSum / dSoftSum / dFlop through the
+ *      pointer arguments exactly as pkdGravAll does (pkd.c:2945-2949, grav.c:246-247, ewald.c:175-176).
+ * Errors follow the host's convention: print and abort (the reference asserts; there is no CPU fallback here).
+ *
+ * Scope of this file: one MDL rank per process image of the tree (mdlThreads == 1).  Multi-GPU runs hand each rank
+ * the other domains' trees through gg_set_top / gg_set_remote (gasoline_b200/domain.py does it over NCCL).
+ * bDoSun (pkd.c:3003-3041, solar-system indirect term) is not supported on the GPU path.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "pkd.h"
+#include "gasoline_b200.h"
+
+typedef struct {
+    gg_context *ctx;
+    size_t capNodes, capPart;
+    /* pinned staging, SoA */
+    double *bnd, *r, *fMass, *fSoft, *fOpen2, *mom;
+    int *pLower, *pUpper, *iLower, *iUpper;
+    double *x, *y, *z, *m, *h, *a, *pot, *dt, *w;
+    int *active;
+} SHIM;
+
+static SHIM g_shim[64]; /* one per MDL rank living in this process (pthread-MDL ranks are threads) */
+
+static void die(const char *what) {
+    fprintf(stderr, "pkdGravAll (gasoline_b200): %s failed: %s\n", what, gg_last_error());
+    abort();
+}
+
+static void *pinned(size_t bytes) {
+    void *p = NULL;
+    if (gg_host_alloc(&p, bytes) != GG_OK) die("gg_host_alloc");
+    return p;
+}
+
+static void reserve(SHIM *s, size_t nNodes, size_t nPart) {
+    if (nNodes > s->capNodes) {
+        size_t c = nNodes + nNodes / 4 + 16;
+        gg_host_free(s->bnd); gg_host_free(s->r); gg_host_free(s->fMass); gg_host_free(s->fSoft);
+        gg_host_free(s->fOpen2); gg_host_free(s->mom); gg_host_free(s->pLower); gg_host_free(s->pUpper);
+        gg_host_free(s->iLower); gg_host_free(s->iUpper);
+        s->bnd = pinned(c * 6 * sizeof(double)); s->r = pinned(c * 3 * sizeof(double));
+        s->fMass = pinned(c * sizeof(double)); s->fSoft = pinned(c * sizeof(double));
+        s->fOpen2 = pinned(c * sizeof(double)); s->mom = pinned(c * GG_NMOM * sizeof(double));
+        s->pLower = pinned(c * sizeof(int)); s->pUpper = pinned(c * sizeof(int));
+        s->iLower = pinned(c * sizeof(int)); s->iUpper = pinned(c * sizeof(int));
+        s->capNodes = c;
+    }
+    if (nPart > s->capPart) {
+        size_t c = nPart + nPart / 4 + 16;
+        gg_host_free(s->x); gg_host_free(s->y); gg_host_free(s->z); gg_host_free(s->m); gg_host_free(s->h);
+        gg_host_free(s->a); gg_host_free(s->pot); gg_host_free(s->dt); gg_host_free(s->w); gg_host_free(s->active);
+        s->x = pinned(c * sizeof(double)); s->y = pinned(c * sizeof(double)); s->z = pinned(c * sizeof(double));
+        s->m = pinned(c * sizeof(double)); s->h = pinned(c * sizeof(double)); s->a = pinned(c * 3 * sizeof(double));
+        s->pot = pinned(c * sizeof(double)); s->dt = pinned(c * sizeof(double)); s->w = pinned(c * sizeof(double));
+        s->active = pinned(c * sizeof(int));
+        s->capPart = c;
+    }
+}
+
+void pkdGravAll(PKD pkd, int nReps, int bPeriodic, int iOrder, int bEwald, int iEwOrder, double fEwCut,
+                double fEwhCut, int bComove, double dRhoFac, int bDoSun, double dSunSoft, double *aSun, int *nActive,
+                double *pdPartSum, double *pdCellSum, double *pdSoftSum, CASTAT *pcs, double *pdFlop) {
+    const int nNodes = pkd->nNodes, n = pkdLocal(pkd);
+    SHIM *s;
+    gg_tree t;
+    gg_particles pp;
+    gg_params prm;
+    gg_stats st;
+    int i, j;
+
+    (void)dSunSoft;
+    mdlassert(pkd->mdl, !bDoSun); /* not supported on the GPU path */
+    mdlassert(pkd->mdl, mdlThreads(pkd->mdl) == 1);
+    mdlassert(pkd->mdl, pkd->idSelf >= 0 && pkd->idSelf < 64);
+    s = &g_shim[pkd->idSelf];
+    if (!s->ctx && gg_create(&s->ctx, -1) != GG_OK) die("gg_create");
+    reserve(s, (size_t)nNodes, (size_t)n);
+
+    /* the timers the caller reads back (pst.c:3316-3324) */
+    pkdClearTimer(pkd, 1);
+    pkdClearTimer(pkd, 2);
+    pkdClearTimer(pkd, 3);
+    pkdStartTimer(pkd, 2);
+
+    for (i = 0; i < nNodes; ++i) {
+        const KDN *c = &pkd->kdNodes[i];
+        const struct pkdCalcCellStruct *q = &c->mom;
+        double *mo = &s->mom[(size_t)GG_NMOM * i];
+        for (j = 0; j < 3; ++j) {
+            s->bnd[6 * (size_t)i + j] = c->bnd.fMin[j];
+            s->bnd[6 * (size_t)i + 3 + j] = c->bnd.fMax[j];
+            s->r[3 * (size_t)i + j] = c->r[j];
+        }
+        s->fMass[i] = c->fMass; s->fSoft[i] = c->fSoft; s->fOpen2[i] = c->fOpen2;
+        s->pLower[i] = c->pLower; s->pUpper[i] = c->pUpper; s->iLower[i] = c->iLower; s->iUpper[i] = c->iUpper;
+        mo[0] = q->Qxx; mo[1] = q->Qyy; mo[2] = q->Qzz; mo[3] = q->Qxy; mo[4] = q->Qxz; mo[5] = q->Qyz;
+        mo[6] = q->Oxxx; mo[7] = q->Oxyy; mo[8] = q->Oxxy; mo[9] = q->Oyyy; mo[10] = q->Oxxz; mo[11] = q->Oyyz;
+        mo[12] = q->Oxyz; mo[13] = q->Oxzz; mo[14] = q->Oyzz; mo[15] = q->Ozzz;
+        mo[16] = q->Hxxxx; mo[17] = q->Hxyyy; mo[18] = q->Hxxxy; mo[19] = q->Hyyyy; mo[20] = q->Hxxxz;
+        mo[21] = q->Hyyyz; mo[22] = q->Hxxyy; mo[23] = q->Hxxyz; mo[24] = q->Hxyyz; mo[25] = q->Hxxzz;
+        mo[26] = q->Hxyzz; mo[27] = q->Hxzzz; mo[28] = q->Hyyzz; mo[29] = q->Hyzzz; mo[30] = q->Hzzzz;
+    }
+    for (i = 0; i < n; ++i) {
+        const PARTICLE *p = &pkd->pStore[i];
+        s->x[i] = p->r[0]; s->y[i] = p->r[1]; s->z[i] = p->r[2];
+        s->m[i] = p->fMass; s->h[i] = p->fSoft;
+        s->active[i] = TYPEQueryACTIVE(p) ? 1 : 0;
+        s->a[3 * (size_t)i] = p->a[0]; s->a[3 * (size_t)i + 1] = p->a[1]; s->a[3 * (size_t)i + 2] = p->a[2];
+        s->pot[i] = p->fPot; s->dt[i] = p->dtGrav; s->w[i] = p->fWeight;
+    }
+    t.nNodes = nNodes; t.iRoot = pkd->iRoot;
+    t.bnd = s->bnd; t.r = s->r; t.fMass = s->fMass; t.fSoft = s->fSoft; t.fOpen2 = s->fOpen2; t.mom = s->mom;
+    t.pLower = s->pLower; t.pUpper = s->pUpper; t.iLower = s->iLower; t.iUpper = s->iUpper;
+    pp.n = n; pp.x = s->x; pp.y = s->y; pp.z = s->z; pp.fMass = s->m; pp.fSoft = s->h; pp.active = s->active;
+    if (gg_set_local(s->ctx, pkd->idSelf, &t, &pp) != GG_OK) die("gg_set_local");
+    if (bPeriodic && bEwald) {
+        double root[GG_NROOT];
+        const ILCN *R = &pkd->ilcnRoot;
+        root[0] = R->m; root[1] = R->x; root[2] = R->y; root[3] = R->z;
+        root[4] = R->xx; root[5] = R->yy; root[6] = R->xy; root[7] = R->xz; root[8] = R->yz; root[9] = R->zz;
+        root[10] = R->xxx; root[11] = R->xyy; root[12] = R->xxy; root[13] = R->yyy; root[14] = R->xxz;
+        root[15] = R->yyz; root[16] = R->xyz; root[17] = R->xzz; root[18] = R->yzz; root[19] = R->zzz;
+        root[20] = R->xxxx; root[21] = R->xyyy; root[22] = R->xxxy; root[23] = R->yyyy; root[24] = R->xxxz;
+        root[25] = R->yyyz; root[26] = R->xxyy; root[27] = R->xxyz; root[28] = R->xyyz; root[29] = R->xxzz;
+        root[30] = R->xyzz; root[31] = R->xzzz; root[32] = R->yyzz; root[33] = R->yzzz; root[34] = R->zzzz;
+        if (gg_set_root_moments(s->ctx, root) != GG_OK) die("gg_set_root_moments");
+    }
+    memset(&prm, 0, sizeof(prm));
+    prm.nReps = nReps; prm.bPeriodic = bPeriodic; prm.iOrder = iOrder; prm.bEwald = bEwald; prm.iEwOrder = iEwOrder;
+    prm.fEwCut = fEwCut; prm.fEwhCut = fEwhCut; prm.bComove = bComove; prm.dRhoFac = dRhoFac;
+    for (j = 0; j < 3; ++j) prm.fPeriod[j] = pkd->fPeriod[j];
+    prm.accumulate = 1;
+    if (gg_gravity(s->ctx, &prm, s->a, s->pot, s->dt, s->w, &st) != GG_OK) die("gg_gravity");
+    for (i = 0; i < n; ++i) {
+        PARTICLE *p = &pkd->pStore[i];
+        if (!s->active[i]) continue;
+        p->a[0] = s->a[3 * (size_t)i]; p->a[1] = s->a[3 * (size_t)i + 1]; p->a[2] = s->a[3 * (size_t)i + 2];
+        p->fPot = s->pot[i]; p->dtGrav = s->dt[i]; p->fWeight = s->w[i];
+    }
+    pkdStopTimer(pkd, 2);
+    *nActive = st.nActive;
+    *pdPartSum = st.dPartSum; *pdCellSum = st.dCellSum; *pdSoftSum = st.dSoftSum; *pdFlop = st.dFlop;
+    if (aSun) aSun[0] = aSun[1] = aSun[2] = 0.0;
+    memset(pcs, 0, sizeof(*pcs)); /* no software cache on this path */
+    pkd->nPart = st.nMaxPart; pkd->nCellSoft = st.nMaxCellSoft; pkd->nCellNewt = st.nMaxCellNewt; /* diag only */
+}

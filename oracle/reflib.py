@@ -10,6 +10,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ref", "libgasref.so")
+GPU_LIB_PATH = os.path.join(_HERE, "_ref", "libgasref_gpu.so")  # same objects, pkdGravAll = the product's shim
 BIN_PATH = os.path.join(_HERE, "_ref", "gasoline_ref")
 
 _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
@@ -20,13 +21,17 @@ def available() -> bool:
     return os.path.exists(LIB_PATH)
 
 
-_lib = None
+def gpu_host_available() -> bool:
+    return os.path.exists(GPU_LIB_PATH)
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        L = C.CDLL(LIB_PATH)
+_libs = {}
+
+
+def lib(gpu_host: bool = False):
+    """gpu_host=False: the pure reference.  gpu_host=True: the reference host with the product's pkdGravAll."""
+    if gpu_host not in _libs:
+        L = C.CDLL(GPU_LIB_PATH if gpu_host else LIB_PATH)
         L.ref_create.restype = C.c_void_p
         L.ref_create.argtypes = [C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_void_p, _dp]
         L.ref_destroy.argtypes = [C.c_void_p]
@@ -43,15 +48,15 @@ def lib():
                                   C.c_double, _dp, _dp, _dp, _dp, _ip, _dp]
         L.ref_bucket_lists.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _ip, C.c_void_p, C.c_int,
                                        C.c_void_p, C.c_int, C.c_void_p, C.c_int]
-        _lib = L
-    return _lib
+        _libs[gpu_host] = L
+    return _libs[gpu_host]
 
 
 class RefGravity:
     """One-rank reference run: tree build (msrBuildTree path) + gravity (pstGravity -> pkdGravAll)."""
 
-    def __init__(self, p, active=None):
-        L = lib()
+    def __init__(self, p, active=None, gpu_host=False):
+        self._L = L = lib(gpu_host)
         self.n = p.n
         per = np.array(p.period, dtype=np.float64)
         act = None
@@ -64,16 +69,16 @@ class RefGravity:
 
     def close(self):
         if self.h:
-            lib().ref_destroy(self.h)
+            self._L.ref_destroy(self.h)
             self.h = None
 
     def build_tree(self, nBucket=8, theta=0.7, iOrder=4):
-        self.t_build = lib().ref_build_tree(self.h, nBucket, theta, iOrder)
+        self.t_build = self._L.ref_build_tree(self.h, nBucket, theta, iOrder)
         return self.t_build
 
     def tree(self):
         """SoA copy of the reference's kdNodes + particles in tree order + ilcnRoot."""
-        L = lib()
+        L = self._L
         nn = L.ref_num_nodes(self.h)
         t = dict(nNodes=nn, iRoot=L.ref_root(self.h), period=self.period.copy(),
                  bnd=np.zeros((nn, 6)), r=np.zeros((nn, 3)), fMass=np.zeros(nn), fSoft=np.zeros(nn),
@@ -92,15 +97,15 @@ class RefGravity:
 
     def set_active_tree(self, active):
         """ACTIVE flags in tree order, after build_tree (ref_set_active_tree)."""
-        lib().ref_set_active_tree(self.h, np.ascontiguousarray(active, dtype=np.int32))
+        self._L.ref_set_active_tree(self.h, np.ascontiguousarray(active, dtype=np.int32))
 
     def ewald_table(self, fhCut=2.8, iOrder=4):
         buf = np.zeros((4096, 5))
-        n = lib().ref_ewald_table(self.h, fhCut, iOrder, buf, 4096)
+        n = self._L.ref_ewald_table(self.h, fhCut, iOrder, buf, 4096)
         return buf[:n].copy()
 
     def gravity(self, nReps, bPeriodic, iOrder=4, bEwald=1, iEwOrder=4, dEwCut=2.6, dEwhCut=2.8):
-        L = lib()
+        L = self._L
         n, nn = self.n, L.ref_num_nodes(self.h)
         acc = np.zeros((n, 3)); pot = np.zeros(n); dt = np.zeros(n); w = np.zeros(n)
         counts = np.zeros((nn, 3), np.int32); stats = np.zeros(8)
@@ -113,6 +118,6 @@ class RefGravity:
     def bucket_lists(self, iBucket, nReps, iOrder=4, nmax=20000):
         n3 = np.zeros(3, np.int32)
         ilp = np.zeros((nmax, 5)); ilcs = np.zeros((nmax, 11)); ilcn = np.zeros((nmax, 35))
-        lib().ref_bucket_lists(self.h, iBucket, nReps, iOrder, n3, ilp.ctypes.data, nmax, ilcs.ctypes.data,
+        self._L.ref_bucket_lists(self.h, iBucket, nReps, iOrder, n3, ilp.ctypes.data, nmax, ilcs.ctypes.data,
                                nmax, ilcn.ctypes.data, nmax)
         return ilp[:n3[0]].copy(), ilcs[:n3[1]].copy(), ilcn[:n3[2]].copy()
