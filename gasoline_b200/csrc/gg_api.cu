@@ -60,11 +60,12 @@ struct gg_context {
     std::vector<int> hActive; // host copy of the local ACTIVE flags (empty = all active)
     // device buffers
     DevBuf nodes, momf, momq, parts, active, hsoft, tasks, ngroups, goffs, counts, acc, pot, dtg, fweight, nloop, sums,
-        misc, imgoff, ewt, raw, rawi, cubtmp, flush;
+        misc, imgoff, ewt, raw, rawi, cubtmp, flush, pool, nextblk, lhead, lcnt;
     void *pinned = nullptr;
     size_t pinnedCap = 0;
     int nTasks = 0;
     int nLaunches = 0;
+    size_t capBlocks = 0; // list pool capacity (blocks of 32 references), kept at the high-water mark
 };
 
 namespace {
@@ -284,7 +285,8 @@ void gg_destroy(gg_context *c) {
     cudaStreamSynchronize(c->st);
     DevBuf *all[] = {&c->nodes, &c->momf, &c->momq, &c->parts, &c->active, &c->hsoft, &c->tasks, &c->ngroups,
                      &c->goffs, &c->counts, &c->acc, &c->pot, &c->dtg, &c->fweight, &c->nloop, &c->sums, &c->misc,
-                     &c->imgoff, &c->ewt, &c->raw, &c->rawi, &c->cubtmp, &c->flush};
+                     &c->imgoff, &c->ewt, &c->raw, &c->rawi, &c->cubtmp, &c->flush, &c->pool,
+                     &c->nextblk, &c->lhead, &c->lcnt};
     for (DevBuf *b : all)
         if (b->p) cudaFree(b->p);
     if (c->pinned) cudaFreeHost(c->pinned);
@@ -476,7 +478,7 @@ Images make_images(const gg_params *prm) {
     return im;
 }
 
-int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_stats *stats) {
+int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_stats *stats, int depth = 0) {
     if (c->dom.empty()) return fail(GG_ERR_ARG, "gg_gravity: gg_set_local has not been called");
     if (prm->iOrder < 1 || prm->iOrder > 4 || prm->iEwOrder < 0 || prm->iEwOrder > 4)
         return fail(GG_ERR_UNSUPPORTED, "gg_gravity: iOrder=%d iEwOrder=%d (supported 1..4)", prm->iOrder, prm->iEwOrder);
@@ -549,7 +551,13 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
     }
     c->nTasks = nTasks;
 
-    // ---- fused walk + interact
+    // ---- walk (lists -> HBM pool) + list evaluation
+    const bool walkOnly = (prm->flags & GG_FLAG_WALK_ONLY) != 0;
+    if ((rc = ensure(c, c->lhead, (size_t)nn * 3 * sizeof(int)))) return rc;
+    if ((rc = ensure(c, c->lcnt, (size_t)nn * 3 * sizeof(int)))) return rc;
+    if (!walkOnly && c->capBlocks == 0) { // first guess: ~700 list entries per bucket, plus one slab per resident warp
+        c->capBlocks = (size_t)nTasks * 24 + (size_t)c->nSM * 64 * GG_SLAB_BLOCKS + 1024;
+    }
     TreeKernelArgs ta;
     memset(&ta, 0, sizeof(ta));
     ta.nodes = (const NodeW *)c->nodes.p;
@@ -562,6 +570,7 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
     ta.nTasks = nTasks;
     ta.taskCounter = (int *)c->misc.p;
     ta.errFlag = (int *)c->misc.p + 1;
+    ta.poolCursor = (int *)c->misc.p + 3;
     ta.rootNode = rootNode;
     ta.nImages = im.n;
     ta.homeImage = im.home;
@@ -569,14 +578,30 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
     ta.imgOff = (const double *)c->imgoff.p;
     ta.iOrder = prm->iOrder;
     ta.maxBucket = c->maxBucket;
-    ta.walkOnly = (prm->flags & GG_FLAG_WALK_ONLY) ? 1 : 0;
+    ta.walkOnly = walkOnly ? 1 : 0;
     ta.acc = (double *)c->acc.p;
     ta.pot = (double *)c->pot.p;
     ta.dtg = (double *)c->dtg.p;
     ta.counts = (int *)c->counts.p;
+    ta.listHead = (int *)c->lhead.p;
+    ta.listCnt = (int *)c->lcnt.p;
     CK(cudaEventRecord(c->ev[1], c->st));
     if (nTasks > 0) {
-        CK(gg_launch_tree_kernel(ta, c->nSM, c->st));
+        if (!walkOnly) {
+            if (c->capBlocks > 0x7fffffffu / 32u)
+                return fail(GG_ERR_NOMEM, "gg_gravity: interaction lists need %zu blocks (> 2^31 references)", c->capBlocks);
+            if ((rc = ensure(c, c->pool, c->capBlocks * 32 * sizeof(unsigned)))) return rc;
+            if ((rc = ensure(c, c->nextblk, c->capBlocks * sizeof(int)))) return rc;
+        }
+        ta.pool = (unsigned *)c->pool.p;
+        ta.nextBlk = (int *)c->nextblk.p;
+        ta.capBlocks = (int)c->capBlocks;
+        CK(gg_launch_walk_kernel(ta, c->nSM, c->st));
+        ++c->nLaunches;
+    }
+    CK(cudaEventRecord(c->ev[5], c->st));
+    if (nTasks > 0 && !walkOnly) {
+        CK(gg_launch_eval_kernel(ta, c->nSM, c->st));
         ++c->nLaunches;
     }
     CK(cudaEventRecord(c->ev[2], c->st));
@@ -657,6 +682,12 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
     CK(cudaMemcpyAsync(hm, c->misc.p, sizeof(hm), cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
     if (hm[1]) return fail(GG_ERR_UNSUPPORTED, "gg_gravity: walk frontier overflowed %d entries (tree too deep)", GG_STACK_CAP);
+    if (!walkOnly && (size_t)hm[3] > c->capBlocks) {
+        // the list pool was too small: the walk kept counting, so hm[3] is what it needs -- grow and run again
+        if (depth >= 2) return fail(GG_ERR_NOMEM, "gg_gravity: list pool overflow persists (%d blocks)", hm[3]);
+        c->capBlocks = (size_t)hm[3] + (size_t)hm[3] / 8 + 1024;
+        return run_gravity(c, prm, singleTask, stats, depth + 1);
+    }
     if (stats) {
         memset(stats, 0, sizeof(*stats));
         stats->nActive = (int)hs[0];
@@ -670,6 +701,7 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
         stats->nMaxCellNewt = (int)hs[8];
         float ms;
         CK(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2])); stats->msTree = ms;
+        CK(cudaEventElapsedTime(&ms, c->ev[1], c->ev[5])); stats->msWalk = ms;
         CK(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3])); stats->msEwald = ms;
         CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[4])); stats->msTotal = ms;
         stats->nKernelLaunches = c->nLaunches;

@@ -155,40 +155,56 @@ __global__ void __launch_bounds__(128) k_ewald(const EwaldKernelArgs A) {
 
 // Per-bucket bookkeeping of pkdGravAll (pkd.c:2945-2998): interaction sums, the reference's flop score
 // (grav.c:246-247, ewald.c:175-176) and fWeight for the active particles of the bucket.
-__global__ void k_stats(const StatsKernelArgs A) {
+__global__ void __launch_bounds__(256) k_stats(const StatsKernelArgs A) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= A.nTasks) return;
-    const Task task = A.tasks[t];
-    if (task.group != 0) return;
-    const NodeW bk = A.nodes[task.node];
-    const int qflop[5] = {10, 10, 41, 120, 277}, mflop[5] = {10, 10, 48, 151, 343};
-    int n = 0;
-    long long nLoop = 0;
-    for (int j = 0; j < bk.nP; ++j) {
-        int pi = bk.pLower + j;
-        if (A.active && !A.active[pi]) continue;
-        ++n;
-        if (A.nLoop) nLoop += A.nLoop[pi];
+    // v[0..5]: sums (nActive, part, cell, soft, flopI, flopE); v[6..8]: maxima of the per-bucket list lengths
+    unsigned long long v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (t < A.nTasks && A.tasks[t].group == 0) {
+        const Task task = A.tasks[t];
+        const NodeW bk = A.nodes[task.node];
+        const int qflop[5] = {10, 10, 41, 120, 277}, mflop[5] = {10, 10, 48, 151, 343};
+        int n = 0;
+        long long nLoop = 0;
+        for (int j = 0; j < bk.nP; ++j) {
+            int pi = bk.pLower + j;
+            if (A.active && !A.active[pi]) continue;
+            ++n;
+            if (A.nLoop) nLoop += A.nLoop[pi];
+        }
+        const int nP = A.counts[3 * task.node], nS = A.counts[3 * task.node + 1], nN = A.counts[3 * task.node + 2];
+        const long long part = (long long)n * nP + (long long)(n * (2 * (bk.nP - 1) - n + 1) / 2); // pkd.c:2946-2947
+        const long long flopI = (long long)n * ((long long)(nP + bk.nP) * 38 + (long long)nS * 82 +
+                                                (long long)nN * (35 + qflop[A.iOrder]));
+        const long long flopE = A.nLoop ? nLoop * (104 + mflop[A.iEwOrder]) + (long long)n * A.nEwh * 58 : 0;
+        for (int j = 0; j < bk.nP; ++j) {
+            int pi = bk.pLower + j;
+            if (A.active && !A.active[pi]) continue;
+            A.fWeight[pi] = (double)flopI + (double)flopE;
+        }
+        v[0] = (unsigned long long)n; v[1] = (unsigned long long)part; v[2] = (unsigned long long)((long long)n * nN);
+        v[3] = (unsigned long long)((long long)n * nS); v[4] = (unsigned long long)flopI; v[5] = (unsigned long long)flopE;
+        v[6] = (unsigned long long)nP; v[7] = (unsigned long long)nS; v[8] = (unsigned long long)nN;
     }
-    const int nP = A.counts[3 * task.node], nS = A.counts[3 * task.node + 1], nN = A.counts[3 * task.node + 2];
-    const long long part = (long long)n * nP + (long long)(n * (2 * (bk.nP - 1) - n + 1) / 2); // pkd.c:2946-2947
-    const long long flopI = (long long)n * ((long long)(nP + bk.nP) * 38 + (long long)nS * 82 +
-                                            (long long)nN * (35 + qflop[A.iOrder]));
-    const long long flopE = A.nLoop ? nLoop * (104 + mflop[A.iEwOrder]) + (long long)n * A.nEwh * 58 : 0;
-    for (int j = 0; j < bk.nP; ++j) {
-        int pi = bk.pLower + j;
-        if (A.active && !A.active[pi]) continue;
-        A.fWeight[pi] = (double)flopI + (double)flopE;
+    // one atomic per CTA and quantity instead of one per bucket (the sums are integers: order does not matter)
+    __shared__ unsigned long long s_v[8][9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long u = __shfl_xor_sync(0xffffffffu, v[k], o);
+            v[k] = k < 6 ? v[k] + u : (u > v[k] ? u : v[k]);
+        }
     }
-    atomicAdd(&A.sums[0], (unsigned long long)n);
-    atomicAdd(&A.sums[1], (unsigned long long)part);
-    atomicAdd(&A.sums[2], (unsigned long long)((long long)n * nN));
-    atomicAdd(&A.sums[3], (unsigned long long)((long long)n * nS));
-    atomicAdd(&A.sums[4], (unsigned long long)flopI);
-    atomicAdd(&A.sums[5], (unsigned long long)flopE);
-    atomicMax(&A.sums[6], (unsigned long long)nP);
-    atomicMax(&A.sums[7], (unsigned long long)nS);
-    atomicMax(&A.sums[8], (unsigned long long)nN);
+    if ((threadIdx.x & 31) == 0)
+        for (int k = 0; k < 9; ++k) s_v[threadIdx.x >> 5][k] = v[k];
+    __syncthreads();
+    if (threadIdx.x < 9) {
+        const int k = threadIdx.x;
+        unsigned long long r = 0;
+        for (int w = 0; w < 8; ++w) r = k < 6 ? r + s_v[w][k] : (s_v[w][k] > r ? s_v[w][k] : r);
+        if (k < 6) atomicAdd(&A.sums[k], r);
+        else atomicMax(&A.sums[k], r);
+    }
 }
 
 } // namespace

@@ -14,7 +14,11 @@
 #include <stdint.h>
 #include "../../include/gasoline_b200.h"
 
-#define GG_WARPS_PER_CTA 4
+#define GG_WARPS_PER_CTA 4   // k_eval
+#define GG_MIN_CTAS 6        // resident CTAs per SM k_eval is compiled for (register cap 65536/(128*6) = 85)
+#define GG_WALK_WARPS 8      // k_walk
+#define GG_WALK_MIN_CTAS 5   // 40 warps per SM (register cap 51)
+#define GG_SLAB_BLOCKS 32    // list blocks a warp takes from the pool per atomic
 #define GG_MAX_SINKS 8      // sinks evaluated per warp pass (accumulators live in registers)
 #define GG_STACK_CAP 512    // walk frontier entries per warp
 #define GG_STACK_DFS_MARGIN 128
@@ -22,9 +26,9 @@
 
 struct __align__(16) NodeW {
     double rx, ry, rz;
+    double fMass;  // first 32 B (one sector) = everything k_eval needs of an accepted cell
     double fOpen2;
     double fSoft;
-    double fMass;
     int c0, c1;   // children (global node index), c0 == -1: bucket
     int pLower;   // first particle (global particle index)
     int nP;       // particle count; >= 2^30 for top-tree cells (exempt from the "< 4 particles" rule, walk.c:81)
@@ -52,7 +56,14 @@ struct TreeKernelArgs {
     const double *hsoft;     // local particles: FP64 softening (fSoftMax must be exact, walk.c:319-324)
     const Task *tasks;
     int nTasks;
-    int *taskCounter;
+    int *taskCounter;        // [0] k_walk's, [2] k_eval's ([1] is errFlag)
+    // interaction lists: 128 B blocks of 32 references chained per bucket (see gg_tree_kernel.cu)
+    unsigned *pool;          // [capBlocks][32]
+    int *nextBlk;            // [capBlocks]
+    int capBlocks;
+    int *poolCursor;         // blocks handed out (may exceed capBlocks: the host then grows the pool and reruns)
+    int *listHead;           // [nLocalNodes][3] first block of the particle / softened-cell / Newtonian-cell chain
+    int *listCnt;            // [nLocalNodes][3] entries in each chain
     int rootNode;            // global index where every image's walk starts
     int nImages, homeImage, imgBits;
     const double *imgOff;    // [nImages][3]
@@ -95,7 +106,7 @@ struct StatsKernelArgs {
     unsigned long long *sums; // [0] nActive [1] part [2] cell [3] soft [4] flopI [5] flopE [6..8] max lists
 };
 
-size_t gg_tree_kernel_smem(int maxBucket);
-cudaError_t gg_launch_tree_kernel(const TreeKernelArgs &a, int nSM, cudaStream_t st);
+cudaError_t gg_launch_walk_kernel(const TreeKernelArgs &a, int nSM, cudaStream_t st);
+cudaError_t gg_launch_eval_kernel(const TreeKernelArgs &a, int nSM, cudaStream_t st);
 cudaError_t gg_launch_ewald_kernel(const EwaldKernelArgs &a, cudaStream_t st);
 cudaError_t gg_launch_stats_kernel(const StatsKernelArgs &a, cudaStream_t st);

@@ -1,58 +1,47 @@
-// gg_tree_kernel.cu -- fused tree walk + interaction-list evaluation, one warp per sink bucket (sm_100a).
+// gg_tree_kernel.cu -- the two tree-gravity kernels (sm_100a): k_walk builds every sink bucket's interaction lists,
+// k_eval evaluates them.  Together they replace pkdBucketWalk (walk.c:306) + pkdBucketInteract (grav.c:23).
 //
-// Replaces, per sink bucket, the reference's pkdBucketWalk (walk.c:306) + pkdBucketInteract (grav.c:23):
+//  * k_walk -- one warp per sink bucket, compiled for high occupancy (the walk is L2-latency bound: every step waits
+//    for 32 scattered 64 B node records).  The warp keeps a frontier of (cell, periodic image) pairs in shared memory
+//    and tests 32 of them per step, one per lane.  The test is the reference's, operation for operation and in FP64
+//    without FMA contraction (INTERSECTNP walk.h:12-30; "< 4 particles => open" walk.c:81; softened-cell
+//    classification walk.c:118-127), so each bucket ends up with exactly the reference's three lists -- only their
+//    order differs, which the reference's results do not depend on beyond rounding.  Opened cells push their two
+//    children, opened buckets contribute their particles.  List entries are 4-byte references (index << imgBits |
+//    image) written in 128 B blocks of 32 into a pool in HBM; each bucket's blocks form a chain (nextBlk).  Blocks
+//    come from per-warp slabs, so the global cursor sees one atomic per 32 blocks.
+//  * k_eval -- one warp per (bucket, group of <= 8 active sinks).  For every block of a chain the warp stages the 32
+//    sources in shared memory -- each lane converts one source to FP32 coordinates relative to the bucket centre
+//    (the FP64 subtraction is done here, so FP32 displacements keep ~1e-7 relative accuracy) and copies its 128 B
+//    FP32 moment record -- and evaluates them with the classic N-body tiling: every lane owns ONE sink (position,
+//    mass and accumulators in registers) and loops over staged sources read with broadcast LDS.128; the 32 lanes
+//    are G = 32/nSinks sub-groups that split the block between them.  Per-lane FP32 partial sums are folded into
+//    FP64 accumulators after every block, and the G sub-groups are combined in FP64 in a fixed order at the end
+//    (deterministic).  1/r comes from MUFU.RSQ plus one Newton step.
 //
-//  * WALK.  The warp keeps a frontier of (cell, periodic image) pairs in shared memory and tests 32 of them per
-//    iteration, one per lane.  The test is the reference's, operation for operation and in FP64 without FMA
-//    contraction (INTERSECTNP walk.h:12-30; "< 4 particles => open" walk.c:81; softened-cell classification
-//    walk.c:118-127), so each bucket ends up with exactly the reference's three lists -- only their order differs,
-//    which the reference's results do not depend on beyond rounding.  Opened cells push their two children, opened
-//    buckets append their particles to a particle buffer, accepted cells go to a cell buffer.
-//  * INTERACT.  Whenever a buffer holds 32 entries the warp evaluates them: lane j loads source j (a 128 B FP32
-//    moment record, or a 32 B particle record) into registers once and loops over the bucket's <= 8 active sinks,
-//    whose positions sit in shared memory relative to the bucket centre (the FP64 subtraction source-centre is
-//    done at staging, so FP32 displacements keep ~1e-7 relative accuracy).  Per-sink accelerations, potentials
-//    and max 1/dt^2 accumulate in registers and are reduced across the warp with shuffles once per bucket.
-//    Lists never touch HBM.  1/r comes from MUFU.RSQ plus one Newton step.
-//
-// The arithmetic is FP32 CUDA-core work: ~130 FFMA-class instructions per (sink, hexadecapole cell)
-// pair against the reference's score of 312 flops (grav.c:156-162), ~22 per (sink, particle) pair against 38.
+// The arithmetic is FP32 CUDA-core work: 138 FFMA/FMUL/FADD per (sink, hexadecapole cell) pair
+// against the reference's score of 312 flops (grav.c:156-162), ~25 per (sink, particle) pair against 38.
 #include "gg_internal.h"
 
 #define FULL 0xffffffffu
+#define CSTRIDE 9 // float4 per staged cell: (x,y,z,M) + 8 x float4 moments = 36 words -> bank offset 4 per source
+#define PSTRIDE 3 // float4 per staged particle: (x,y,z,m), (h, index, -, -), pad = 12 words -> conflict-free for G <= 8
 
 namespace {
 
-struct WarpSmem {
-    float4 acc[GG_MAX_SINKS][32]; // per lane, per sink: ax, ay, az, potential
-    float dtm[GG_MAX_SINKS][32];  // per lane, per sink: max 1/dt^2
-    unsigned stack[GG_STACK_CAP];
-    unsigned cbuf[64];
-    float4 sink[GG_MAX_SINKS];    // x, y, z relative to the bucket centre, mass
-    float sh[GG_MAX_SINKS];
-    int sidx[GG_MAX_SINKS];
-    unsigned pbuf[32]; // really 32*maxBucket + 32
-};
-
-__host__ __device__ inline size_t warp_smem_bytes(int maxBucket) {
-    size_t b = sizeof(WarpSmem) + (size_t)32 * maxBucket * sizeof(unsigned);
-    return (b + 15) & ~(size_t)15;
+// INTERSECTNP (walk.h:12-30): squared distance from (x,y,z) to the box <= fBall2.  Branch-free but bit-identical:
+// with fMin <= fMax at most one of (fMin - x), (x - fMax) is positive, so max(max(.,.),0) selects the term the
+// reference's if/else-if picks, and adding the +0.0 of an axis inside the box changes nothing.  Intrinsics pin the
+// rounding of every product and sum (no FMA), matching the reference's x86-64 build.
+__device__ __forceinline__ double pos_part(double a, double b) { // max(a, b, 0) for finite inputs (no NaN fix-up code)
+    const double t = a > b ? a : b;
+    return t > 0.0 ? t : 0.0;
 }
-
-// INTERSECTNP (walk.h:12-30): squared distance from (x,y,z) to the box <= fBall2.  Intrinsics pin the rounding of
-// every product and sum (no FMA), matching the reference's x86-64 build.
 __device__ __forceinline__ bool intersect_np(const double *box, double fBall2, double x, double y, double z) {
-    double dx = box[0] - x, dx1 = x - box[3];
-    double dy = box[1] - y, dy1 = y - box[4];
-    double dz = box[2] - z, dz1 = z - box[5];
-    double d2;
-    if (dx > 0.0) d2 = __dmul_rn(dx, dx);
-    else if (dx1 > 0.0) d2 = __dmul_rn(dx1, dx1);
-    else d2 = 0.0;
-    if (dy > 0.0) d2 = __dadd_rn(d2, __dmul_rn(dy, dy));
-    else if (dy1 > 0.0) d2 = __dadd_rn(d2, __dmul_rn(dy1, dy1));
-    if (dz > 0.0) d2 = __dadd_rn(d2, __dmul_rn(dz, dz));
-    else if (dz1 > 0.0) d2 = __dadd_rn(d2, __dmul_rn(dz1, dz1));
+    const double dx = pos_part(box[0] - x, x - box[3]);
+    const double dy = pos_part(box[1] - y, y - box[4]);
+    const double dz = pos_part(box[2] - z, z - box[5]);
+    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
     return d2 <= fBall2;
 }
 
@@ -66,8 +55,26 @@ __device__ __forceinline__ NodeW load_node(const NodeW *p) {
     double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
     int4 d = __ldg(reinterpret_cast<const int4 *>(q + 3));
     NodeW n;
-    n.rx = a.x; n.ry = a.y; n.rz = b.x; n.fOpen2 = b.y; n.fSoft = c.x; n.fMass = c.y;
+    n.rx = a.x; n.ry = a.y; n.rz = b.x; n.fMass = b.y; n.fOpen2 = c.x; n.fSoft = c.y;
     n.c0 = d.x; n.c1 = d.y; n.pLower = d.z; n.nP = d.w;
+    return n;
+}
+
+// 16-byte asynchronous global->shared copy THROUGH L1 (.ca): the top of the tree is re-read by every bucket and
+// every periodic image, so the L1 hit rate matters (the .cg form cuda_pipeline.h picks for 16 B bypasses L1).
+__device__ __forceinline__ void cp_async_ca16(void *smem, const void *gmem) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__device__ __forceinline__ NodeW load_node_smem(const uint4 *q) {
+    const uint4 a = q[0], b = q[1], c = q[2], d = q[3];
+    NodeW n;
+    n.rx = __hiloint2double(a.y, a.x); n.ry = __hiloint2double(a.w, a.z);
+    n.rz = __hiloint2double(b.y, b.x); n.fMass = __hiloint2double(b.w, b.z);
+    n.fOpen2 = __hiloint2double(c.y, c.x); n.fSoft = __hiloint2double(c.w, c.z);
+    n.c0 = (int)d.x; n.c1 = (int)d.y; n.pLower = (int)d.z; n.nP = (int)d.w;
     return n;
 }
 
@@ -190,8 +197,11 @@ __device__ __forceinline__ void part_on_sink(float pm, float ph, float dx, float
 }
 
 // Softened cell (ILCS) on one sink: SPLINEQ grav.h:17-50 + grav.c:126-150, FP64 (rare path).
-__device__ __noinline__ void softcell_on_sink(double M, double hc, const double *Q, double dx, double dy, double dz,
-                                              double ms, double hs, float4 *pacc, float *pdt) {
+struct SoftTerm {
+    double ax, ay, az, pot, dt;
+};
+__device__ __noinline__ SoftTerm softcell_on_sink(double M, double hc, const double *Q, double dx, double dy, double dz,
+                                                  double ms, double hs) {
     double d2 = dx * dx + dy * dy + dz * dz;
     double dir = rsqrt(d2), twoh = hs + hc, a, b, c, d;
     if (d2 < twoh * twoh) {
@@ -220,25 +230,92 @@ __device__ __noinline__ void softcell_on_sink(double M, double hc, const double 
     double qir = 0.5 * (qirx * dx + qiry * dy + qirz * dz);
     double tr = 0.5 * (Q[0] + Q[1] + Q[2]);
     double qir3 = b * M + d * qir - c * tr;
-    float4 v = *pacc;
-    v.w -= (float)(a * M + c * qir - b * tr);
-    v.x -= (float)(qir3 * dx - c * qirx);
-    v.y -= (float)(qir3 * dy - c * qiry);
-    v.z -= (float)(qir3 * dz - c * qirz);
-    *pacc = v;
-    *pdt = fmaxf(*pdt, (float)((ms + M) * b));
+    SoftTerm t;
+    t.ax = -(qir3 * dx - c * qirx);
+    t.ay = -(qir3 * dy - c * qiry);
+    t.az = -(qir3 * dz - c * qirz);
+    t.pot = -(a * M + c * qir - b * tr);
+    t.dt = (ms + M) * b;
+    return t;
 }
 
-template <int ORDER>
-__global__ void __launch_bounds__(GG_WARPS_PER_CTA * 32) k_tree_gravity(const TreeKernelArgs A) {
+// The sink box of a bucket: bbox of its ACTIVE particles (pkd.c:2916-2932), fSoftMax over ALL of them
+// (walk.c:319-324) and the number of active ones.  Warp-collective.
+__device__ __forceinline__ void sink_box(const TreeKernelArgs &A, const NodeW &bk, int lane, double box[6],
+                                         double &fSoftMax, int &nAct) {
+    box[0] = box[1] = box[2] = 1.7976931348623157e308;
+    box[3] = box[4] = box[5] = -1.7976931348623157e308;
+    fSoftMax = 0.0;
+    nAct = 0;
+    for (int base = 0; base < bk.nP; base += 32) {
+        const int j = base + lane;
+        bool act = false;
+        if (j < bk.nP) {
+            const int pi = bk.pLower + j;
+            act = A.active ? (A.active[pi] != 0) : true;
+            fSoftMax = fmax(fSoftMax, A.hsoft[pi]);
+            if (act) {
+                const PartS p = load_part(&A.parts[pi]);
+                box[0] = fmin(box[0], p.x); box[3] = fmax(box[3], p.x);
+                box[1] = fmin(box[1], p.y); box[4] = fmax(box[4], p.y);
+                box[2] = fmin(box[2], p.z); box[5] = fmax(box[5], p.z);
+            }
+        }
+        nAct += __popc(__ballot_sync(FULL, act));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            box[k] = fmin(box[k], __shfl_xor_sync(FULL, box[k], o));
+            box[3 + k] = fmax(box[3 + k], __shfl_xor_sync(FULL, box[3 + k], o));
+        }
+        fSoftMax = fmax(fSoftMax, __shfl_xor_sync(FULL, fSoftMax, o));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ k_walk
+#define NSTRIDE 5 // uint4 per staged node record: 64 B + 16 B pad -> LDS.128 of 8 consecutive lanes is conflict-free
+struct WalkSmem {
+    uint4 nstage[32 * NSTRIDE]; // the 32 node records of the current step, fetched cooperatively (4 lanes per record)
+    unsigned stack[GG_STACK_CAP];
+    unsigned cbuf[64];
+    unsigned sbuf[64];
+    unsigned pbuf[32]; // really 32*maxBucket + 32
+};
+
+__host__ __device__ inline size_t walk_smem_bytes(int maxBucket) {
+    size_t b = sizeof(WalkSmem) + (size_t)32 * maxBucket * sizeof(unsigned);
+    return (b + 15) & ~(size_t)15;
+}
+
+// Append one block (<= 32 references) to a chain.  Blocks come from the warp's slab; a new slab costs one atomic.
+__device__ __forceinline__ void emit_block(const TreeKernelArgs &A, const unsigned *src, int cnt, int lane,
+                                           int &slabBase, int &slabUsed, int &head) {
+    if (slabUsed == GG_SLAB_BLOCKS) {
+        int b = 0;
+        if (lane == 0) b = atomicAdd(A.poolCursor, GG_SLAB_BLOCKS);
+        slabBase = __shfl_sync(FULL, b, 0);
+        slabUsed = 0;
+    }
+    const int blk = slabBase + slabUsed++;
+    if (blk < A.capBlocks) { // beyond the pool: the host sees cursor > capBlocks, grows the pool and reruns
+        if (lane < cnt) A.pool[(size_t)blk * 32 + lane] = src[lane];
+        if (lane == 0) A.nextBlk[blk] = head;
+        head = blk;
+    }
+}
+
+__global__ void __launch_bounds__(GG_WALK_WARPS * 32, GG_WALK_MIN_CTAS) k_walk(const TreeKernelArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double s_off[GG_MAX_IMAGES * 3];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
     for (int i = threadIdx.x; i < A.nImages * 3; i += blockDim.x) s_off[i] = A.imgOff[i];
     __syncthreads();
-    WarpSmem &W = *reinterpret_cast<WarpSmem *>(smem_raw + warp * warp_smem_bytes(A.maxBucket));
+    WalkSmem &W = *reinterpret_cast<WalkSmem *>(smem_raw + warp * walk_smem_bytes(A.maxBucket));
     const unsigned imgMask = (1u << A.imgBits) - 1u;
+    int slabBase = 0, slabUsed = GG_SLAB_BLOCKS;
 
     for (;;) {
         int t = 0;
@@ -246,42 +323,161 @@ __global__ void __launch_bounds__(GG_WARPS_PER_CTA * 32) k_tree_gravity(const Tr
         t = __shfl_sync(FULL, t, 0);
         if (t >= A.nTasks) break;
         const Task task = A.tasks[t];
+        if (task.group != 0) continue; // one walk per bucket; the other sink groups reuse its lists
         const NodeW bk = load_node(&A.nodes[task.node]);
+        double box[6], fSoftMax;
+        int nAct;
+        sink_box(A, bk, lane, box, fSoftMax, nAct);
 
-        // ---- stage the sinks: bbox of ACTIVE particles (pkd.c:2916-2932), fSoftMax over ALL (walk.c:319-324)
-        double box[6] = {1.7976931348623157e308,  1.7976931348623157e308,  1.7976931348623157e308,
-                         -1.7976931348623157e308, -1.7976931348623157e308, -1.7976931348623157e308};
-        double fSoftMax = 0.0;
-        int nAct = 0;
-        for (int base = 0; base < bk.nP; base += 32) {
-            const int j = base + lane;
-            bool act = false;
-            if (j < bk.nP) {
-                const int pi = bk.pLower + j;
-                act = A.active ? (A.active[pi] != 0) : true;
-                fSoftMax = fmax(fSoftMax, A.hsoft[pi]);
-                if (act) {
-                    const PartS p = load_part(&A.parts[pi]);
-                    box[0] = fmin(box[0], p.x); box[3] = fmax(box[3], p.x);
-                    box[1] = fmin(box[1], p.y); box[4] = fmax(box[4], p.y);
-                    box[2] = fmin(box[2], p.z); box[5] = fmax(box[5], p.z);
+        int nStack = A.nImages, nCell = 0, nPart = 0, nSoft = 0;
+        int cntP = 0, cntS = 0, cntN = 0, own = 0;
+        int headC = -1, headS = -1, headP = -1;
+        for (int i = lane; i < A.nImages; i += 32) W.stack[i] = ((unsigned)A.rootNode << A.imgBits) | (unsigned)i;
+        __syncwarp();
+
+        while (nStack > 0) {
+            int k = min(32, nStack);
+            if (nStack > GG_STACK_CAP - GG_STACK_DFS_MARGIN) k = 1; // near the cap: depth-first, growth <= 1 per step
+            unsigned item = 0xffffffffu;
+            if (lane < k) item = W.stack[nStack - 1 - lane];
+            nStack -= k;
+            __syncwarp();
+            // fetch the k node records COALESCED: 4 lanes per 64 B record, so a warp-wide 16 B access touches 8 cache
+            // lines instead of 32 (the walk is bound by L1 tag lookups otherwise); cp.async lands them in shared memory
+            const int node = item != 0xffffffffu ? (int)(item >> A.imgBits) : -1;
+            {
+                const int piece = lane & 3, sub = lane >> 2;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int rec = 8 * i + sub;
+                    const int rn = __shfl_sync(FULL, node, rec);
+                    if (rn >= 0)
+                        cp_async_ca16(&W.nstage[rec * NSTRIDE + piece], reinterpret_cast<const uint4 *>(&A.nodes[rn]) + piece);
                 }
+                cp_async_wait_all();
             }
-            nAct += __popc(__ballot_sync(FULL, act));
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                box[k] = fmin(box[k], __shfl_xor_sync(FULL, box[k], o));
-                box[3 + k] = fmax(box[3 + k], __shfl_xor_sync(FULL, box[3 + k], o));
+            __syncwarp();
+            // classify: 1 push children, 2 Newtonian cell, 3 source bucket, 4 own bucket, 5 softened cell
+            int action = 0, img = 0, np = 0, c0 = -1, c1 = -1, pLower = 0;
+            if (node >= 0) {
+                img = (int)(item & imgMask);
+                const NodeW nd = load_node_smem(&W.nstage[lane * NSTRIDE]);
+                const double x = nd.rx + s_off[3 * img], y = nd.ry + s_off[3 * img + 1], z = nd.rz + s_off[3 * img + 2];
+                bool open = intersect_np(box, nd.fOpen2, x, y, z);
+                if (nd.nP < 4) open = true; // walk.c:81 (pUpper - pLower < 3)
+                if (open) {
+                    if (nd.c0 >= 0) action = 1;
+                    else action = (node == task.node && img == A.homeImage) ? 4 : 3; // walk.c:93
+                } else {
+                    double twoh2 = nd.fSoft + fSoftMax;
+                    twoh2 = __dmul_rn(twoh2, twoh2);
+                    bool soft = false;
+                    if (!(twoh2 < nd.fOpen2)) soft = intersect_np(box, twoh2, x, y, z); // walk.c:122-127
+                    action = soft ? 5 : 2;
+                }
+                c0 = nd.c0; c1 = nd.c1; pLower = nd.pLower;
+                if (action == 3 || action == 4) np = nd.nP;
             }
-            fSoftMax = fmax(fSoftMax, __shfl_xor_sync(FULL, fSoftMax, o));
+            // children (a single-child cell, pkdThreadTree pkd.c:2597-2609, pushes a no-op as second item)
+            const unsigned mPush = __ballot_sync(FULL, action == 1);
+            if (action == 1) {
+                const int pos = nStack + 2 * __popc(mPush & lt);
+                if (pos + 1 < GG_STACK_CAP) {
+                    W.stack[pos] = c1 >= 0 ? (((unsigned)c1 << A.imgBits) | (unsigned)img) : 0xffffffffu;
+                    W.stack[pos + 1] = ((unsigned)c0 << A.imgBits) | (unsigned)img;
+                } else atomicExch(A.errFlag, 1);
+            }
+            nStack += 2 * __popc(mPush);
+            // Newtonian cells
+            const unsigned mCell = __ballot_sync(FULL, action == 2);
+            if (action == 2) W.cbuf[nCell + __popc(mCell & lt)] = item;
+            nCell += __popc(mCell);
+            cntN += __popc(mCell);
+            // softened cells
+            const unsigned mSoft = __ballot_sync(FULL, action == 5);
+            if (mSoft) {
+                if (action == 5) W.sbuf[nSoft + __popc(mSoft & lt)] = item;
+                nSoft += __popc(mSoft);
+                cntS += __popc(mSoft);
+            }
+            // source particles
+            const unsigned mBk = __ballot_sync(FULL, np > 0);
+            if (mBk) {
+                int incl = np;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const int total = __shfl_sync(FULL, incl, 31);
+                const int wpos = nPart + incl - np;
+                for (int j = 0; j < np; ++j) W.pbuf[wpos + j] = ((unsigned)(pLower + j) << A.imgBits) | (unsigned)img;
+                const unsigned mOwn = __ballot_sync(FULL, action == 4);
+                if (mOwn) own = __shfl_sync(FULL, np, __ffs(mOwn) - 1);
+                nPart += total;
+                cntP += total;
+            }
+            __syncwarp();
+            if (!A.walkOnly) {
+                while (nCell >= 32) { nCell -= 32; emit_block(A, &W.cbuf[nCell], 32, lane, slabBase, slabUsed, headC); }
+                while (nSoft >= 32) { nSoft -= 32; emit_block(A, &W.sbuf[nSoft], 32, lane, slabBase, slabUsed, headS); }
+                while (nPart >= 32) { nPart -= 32; emit_block(A, &W.pbuf[nPart], 32, lane, slabBase, slabUsed, headP); }
+            } else {
+                nCell = nSoft = nPart = 0;
+            }
+            __syncwarp();
         }
+        if (!A.walkOnly) {
+            if (nCell > 0) emit_block(A, W.cbuf, nCell, lane, slabBase, slabUsed, headC);
+            if (nSoft > 0) emit_block(A, W.sbuf, nSoft, lane, slabBase, slabUsed, headS);
+            if (nPart > 0) emit_block(A, W.pbuf, nPart, lane, slabBase, slabUsed, headP);
+        }
+        if (lane == 0) {
+            int *c = &A.counts[3 * task.node];
+            c[0] = cntP - own; c[1] = cntS; c[2] = cntN;         // what pkdBucketWalk reports (walk.c:175-177)
+            int *h = &A.listHead[3 * task.node], *n = &A.listCnt[3 * task.node];
+            h[0] = headP; h[1] = headS; h[2] = headC;
+            n[0] = cntP; n[1] = cntS; n[2] = cntN;               // chain lengths (particles include the own bucket)
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ k_eval
+struct EvalSmem {
+    float4 stage[32 * CSTRIDE]; // staged block; also the sink hand-out at task start and the final reduction scratch
+};
+
+template <int ORDER>
+__global__ void __launch_bounds__(GG_WARPS_PER_CTA * 32, GG_MIN_CTAS) k_eval(const TreeKernelArgs A) {
+    __shared__ EvalSmem s_w[GG_WARPS_PER_CTA];
+    __shared__ double s_off[GG_MAX_IMAGES * 3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int i = threadIdx.x; i < A.nImages * 3; i += blockDim.x) s_off[i] = A.imgOff[i];
+    __syncthreads();
+    EvalSmem &W = s_w[warp];
+    const unsigned imgMask = (1u << A.imgBits) - 1u;
+
+    for (;;) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(A.taskCounter + 2, 1);
+        t = __shfl_sync(FULL, t, 0);
+        if (t >= A.nTasks) break;
+        const Task task = A.tasks[t];
+        const NodeW bk = load_node(&A.nodes[task.node]);
+        double box[6], fSoftMax;
+        int nAct;
+        sink_box(A, bk, lane, box, fSoftMax, nAct);
         const double cenx = 0.5 * (box[0] + box[3]), ceny = 0.5 * (box[1] + box[4]), cenz = 0.5 * (box[2] + box[5]);
-        // sinks of this pass: active ranks [8*group, 8*group+8)
+
+        // ---- hand the sinks of this pass (active ranks [8*group, 8*group+8)) to their lanes: lane = q*nS + s owns
+        //      sink s; the G = 32/nS sub-groups q split every staged block between them
         const int rank0 = task.group * GG_MAX_SINKS;
         const int nS = min(GG_MAX_SINKS, nAct - rank0);
+        const int G = 32 / nS;
+        const int q = lane / nS, sI = lane - q * nS;
+        const bool worker = q < G;
         __syncwarp();
         {
             int seen = 0;
@@ -293,198 +489,153 @@ __global__ void __launch_bounds__(GG_WARPS_PER_CTA * 32) k_tree_gravity(const Tr
                 const int rank = seen + __popc(m & lt) - rank0;
                 if (act && rank >= 0 && rank < GG_MAX_SINKS) {
                     const PartS p = load_part(&A.parts[pi]);
-                    W.sink[rank] = make_float4((float)(p.x - cenx), (float)(p.y - ceny), (float)(p.z - cenz), p.m);
-                    W.sh[rank] = p.h;
-                    W.sidx[rank] = pi;
+                    W.stage[rank] = make_float4((float)(p.x - cenx), (float)(p.y - ceny), (float)(p.z - cenz), p.m);
+                    W.stage[GG_MAX_SINKS + rank] = make_float4(p.h, __int_as_float(pi), 0.f, 0.f);
                 }
                 seen += __popc(m);
             }
         }
-        for (int s = 0; s < nS; ++s) {
-            W.acc[s][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
-            W.dtm[s][lane] = 0.f;
-        }
-
-        // ---- walk + evaluate
-        int nStack = A.nImages, nCell = 0, nPart = 0;
-        int cntP = 0, cntS = 0, cntN = 0;
-        for (int i = lane; i < A.nImages; i += 32) W.stack[i] = ((unsigned)A.rootNode << A.imgBits) | (unsigned)i;
         __syncwarp();
+        const float4 sk = W.stage[sI], sk2 = W.stage[GG_MAX_SINKS + sI];
+        const float sx = sk.x, sy = sk.y, sz = sk.z, ms = sk.w, hs = sk2.x;
+        const int sidx = __float_as_int(sk2.y);
+        __syncwarp();
+        float ax = 0.f, ay = 0.f, az = 0.f, ap = 0.f, dtm = 0.f; // FP32 partial sums of the current block
+        double dax = 0.0, day = 0.0, daz = 0.0, dap = 0.0;         // FP64 running sums
+        const int *heads = &A.listHead[3 * task.node], *cnts = &A.listCnt[3 * task.node];
 
-        for (;;) {
-            if (nStack > 0) {
-                int k = min(32, nStack);
-                if (nStack > GG_STACK_CAP - GG_STACK_DFS_MARGIN) k = 1; // near the cap: depth-first, growth <= 1 per step
-                const bool has = lane < k;
-                const unsigned item = has ? W.stack[nStack - 1 - lane] : 0xffffffffu;
-                nStack -= k;
-                __syncwarp();
-                int action = 0; // 1 push children, 2 Newtonian cell, 3 source bucket, 4 own bucket, 5 softened cell
-                NodeW nd;
-                int node = 0, img = 0;
-                nd.nP = 0; nd.c0 = -1; nd.c1 = -1; nd.pLower = 0; nd.fMass = 0; nd.fSoft = 0;
-                double x = 0, y = 0, z = 0;
-                if (item != 0xffffffffu) {
-                    node = (int)(item >> A.imgBits);
-                    img = (int)(item & imgMask);
-                    nd = load_node(&A.nodes[node]);
-                    x = nd.rx + s_off[3 * img];
-                    y = nd.ry + s_off[3 * img + 1];
-                    z = nd.rz + s_off[3 * img + 2];
-                    bool open = intersect_np(box, nd.fOpen2, x, y, z);
-                    if (nd.nP < 4) open = true; // walk.c:81 (pUpper - pLower < 3)
-                    if (open) {
-                        if (nd.c0 >= 0) action = 1;
-                        else action = (node == task.node && img == A.homeImage) ? 4 : 3; // walk.c:93
-                    } else {
-                        double twoh2 = nd.fSoft + fSoftMax;
-                        twoh2 = __dmul_rn(twoh2, twoh2);
-                        bool soft = false;
-                        if (!(twoh2 < nd.fOpen2)) soft = intersect_np(box, twoh2, x, y, z); // walk.c:122-127
-                        action = soft ? 5 : 2;
-                    }
+        // ---- Newtonian cells (ILCN): QEVAL to ORDER
+        {
+            int blk = heads[2], total = cnts[2];
+            int cnt = total > 0 ? total - 32 * ((total - 1) / 32) : 0; // the head block is the partial one
+            while (blk >= 0) {
+                const int nxt = A.nextBlk[blk];
+                // stage the block: positions by their own lane (32 B = one sector each); moment records COALESCED,
+                // LPR lanes per 128 B record (a warp-wide LDG.128 touches 32/LPR lines instead of 32)
+                int cn = 0;
+                if (lane < cnt) {
+                    const unsigned it = A.pool[(size_t)blk * 32 + lane];
+                    cn = (int)(it >> A.imgBits);
+                    const int ci = (int)(it & imgMask);
+                    const double2 *nq = reinterpret_cast<const double2 *>(&A.nodes[cn]);
+                    const double2 p01 = __ldg(nq), p23 = __ldg(nq + 1);
+                    W.stage[lane * CSTRIDE] =
+                        make_float4((float)((p01.x + s_off[3 * ci]) - cenx), (float)((p01.y + s_off[3 * ci + 1]) - ceny),
+                                    (float)((p23.x + s_off[3 * ci + 2]) - cenz), (float)p23.y);
                 }
-                // children (a single-child cell, pkdThreadTree pkd.c:2597-2609, pushes a no-op as second item)
-                const unsigned mPush = __ballot_sync(FULL, action == 1);
-                if (action == 1) {
-                    const int pos = nStack + 2 * __popc(mPush & lt);
-                    if (pos + 1 < GG_STACK_CAP) {
-                        W.stack[pos] = nd.c1 >= 0 ? (((unsigned)nd.c1 << A.imgBits) | (unsigned)img) : 0xffffffffu;
-                        W.stack[pos + 1] = ((unsigned)nd.c0 << A.imgBits) | (unsigned)img;
-                    } else atomicExch(A.errFlag, 1);
-                }
-                nStack += 2 * __popc(mPush);
-                // Newtonian cells
-                const unsigned mCell = __ballot_sync(FULL, action == 2);
-                if (action == 2) W.cbuf[nCell + __popc(mCell & lt)] = item;
-                nCell += __popc(mCell);
-                cntN += __popc(mCell);
-                // source particles
-                const int np = (action == 3 || action == 4) ? nd.nP : 0;
-                const unsigned mBk = __ballot_sync(FULL, np > 0);
-                if (mBk) {
-                    int incl = np;
+                if (ORDER >= 2) {
+                    constexpr int LPR = ORDER == 2 ? 2 : (ORDER == 3 ? 4 : 8); // float4 pieces of the record in use
+                    const int piece = lane & (LPR - 1), sub = lane / LPR;
 #pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int v = __shfl_up_sync(FULL, incl, o);
-                        if (lane >= o) incl += v;
-                    }
-                    const int total = __shfl_sync(FULL, incl, 31);
-                    const int wpos = nPart + incl - np;
-                    for (int j = 0; j < np; ++j)
-                        W.pbuf[wpos + j] = ((unsigned)(nd.pLower + j) << A.imgBits) | (unsigned)img;
-                    const unsigned mOwn = __ballot_sync(FULL, action == 4);
-                    const int own = mOwn ? __shfl_sync(FULL, np, __ffs(mOwn) - 1) : 0;
-                    nPart += total;
-                    cntP += total - own;
-                }
-                // softened cells: evaluated on the spot by the lane that found them
-                const unsigned mSoft = __ballot_sync(FULL, action == 5);
-                if (mSoft) {
-                    cntS += __popc(mSoft);
-                    if (action == 5 && !A.walkOnly) {
-                        const double *Q = &A.momq[(size_t)node * 6];
-                        for (int s = 0; s < nS; ++s) {
-                            const float4 sk = W.sink[s];
-                            softcell_on_sink(nd.fMass, nd.fSoft, Q, ((double)sk.x + cenx) - x, ((double)sk.y + ceny) - y,
-                                             ((double)sk.z + cenz) - z, (double)sk.w, (double)W.sh[s], &W.acc[s][lane],
-                                             &W.dtm[s][lane]);
-                        }
+                    for (int i = 0; i < LPR; ++i) {
+                        const int rec = i * (32 / LPR) + sub;
+                        const int rn = __shfl_sync(FULL, cn, rec);
+                        if (rec < cnt) W.stage[rec * CSTRIDE + 1 + piece] = __ldg(&A.momf[(size_t)rn * 8 + piece]);
                     }
                 }
                 __syncwarp();
-            }
-            const bool done = (nStack == 0);
-            if (A.walkOnly) {
-                nCell = 0;
-                nPart = 0;
-            }
-            // ---- evaluate full chunks (from the top of each buffer: no shifting), everything once the walk is done
-            while (nCell >= 32 || (done && nCell > 0)) {
-                const int cnt = min(32, nCell);
-                nCell -= cnt;
-                if (lane < cnt) {
-                    const unsigned item = W.cbuf[nCell + lane];
-                    const int node = (int)(item >> A.imgBits), img = (int)(item & imgMask);
-                    const double2 *nq = reinterpret_cast<const double2 *>(&A.nodes[node]);
-                    const double2 p01 = __ldg(nq), p23 = __ldg(nq + 1), p45 = __ldg(nq + 2);
-                    const float cx = (float)((p01.x + s_off[3 * img]) - cenx);
-                    const float cy = (float)((p01.y + s_off[3 * img + 1]) - ceny);
-                    const float cz = (float)((p23.x + s_off[3 * img + 2]) - cenz);
-                    const float M = (float)p45.y;
-                    CellMom c;
-                    const float4 *mq = &A.momf[(size_t)node * 8];
-                    c.m0 = __ldg(mq); c.m1 = __ldg(mq + 1);
-                    if (ORDER >= 3) { c.m2 = __ldg(mq + 2); c.m3 = __ldg(mq + 3); }
-                    if (ORDER >= 4) { c.m4 = __ldg(mq + 4); c.m5 = __ldg(mq + 5); c.m6 = __ldg(mq + 6); c.m7 = __ldg(mq + 7); }
-#pragma unroll 2
-                    for (int s = 0; s < nS; ++s) {
-                        const float4 sk = W.sink[s];
+                if (worker) {
+#pragma unroll 1
+                    for (int j = q; j < cnt; j += G) {
+                        const float4 *S = &W.stage[j * CSTRIDE];
+                        const float4 pc = S[0];
+                        CellMom c;
+                        c.m0 = S[1]; c.m1 = S[2];
+                        if (ORDER >= 3) { c.m2 = S[3]; c.m3 = S[4]; }
+                        if (ORDER >= 4) { c.m4 = S[5]; c.m5 = S[6]; c.m6 = S[7]; c.m7 = S[8]; }
                         float fx, fy, fz, fp, fdt;
-                        cell_on_sink<ORDER>(c, M, sk.x - cx, sk.y - cy, sk.z - cz, sk.w, fx, fy, fz, fp, fdt);
-                        float4 v = W.acc[s][lane];
-                        v.x += fx; v.y += fy; v.z += fz; v.w -= fp;
-                        W.acc[s][lane] = v;
-                        W.dtm[s][lane] = fmaxf(W.dtm[s][lane], fdt);
+                        cell_on_sink<ORDER>(c, pc.w, sx - pc.x, sy - pc.y, sz - pc.z, ms, fx, fy, fz, fp, fdt);
+                        ax += fx; ay += fy; az += fz; ap -= fp;
+                        dtm = fmaxf(dtm, fdt);
                     }
                 }
+                dax += (double)ax; day += (double)ay; daz += (double)az; dap += (double)ap;
+                ax = ay = az = ap = 0.f;
                 __syncwarp();
+                blk = nxt;
+                cnt = 32;
             }
-            while (nPart >= 32 || (done && nPart > 0)) {
-                const int cnt = min(32, nPart);
-                nPart -= cnt;
+        }
+        // ---- particles (ILP) incl. the bucket's own (intra-bucket pairs, grav.c:211-242): SPLINE-softened monopoles
+        {
+            int blk = heads[0], total = cnts[0];
+            int cnt = total > 0 ? total - 32 * ((total - 1) / 32) : 0;
+            while (blk >= 0) {
+                const int nxt = A.nextBlk[blk];
                 if (lane < cnt) {
-                    const unsigned item = W.pbuf[nPart + lane];
-                    const int pi = (int)(item >> A.imgBits), img = (int)(item & imgMask);
+                    const unsigned it = A.pool[(size_t)blk * 32 + lane];
+                    const int pi = (int)(it >> A.imgBits), ci = (int)(it & imgMask);
                     const PartS p = load_part(&A.parts[pi]);
-                    const float px = (float)((p.x + s_off[3 * img]) - cenx);
-                    const float py = (float)((p.y + s_off[3 * img + 1]) - ceny);
-                    const float pz = (float)((p.z + s_off[3 * img + 2]) - cenz);
-                    const bool home = (img == A.homeImage);
-#pragma unroll 2
-                    for (int s = 0; s < nS; ++s) {
-                        if (home && pi == W.sidx[s]) continue; // a particle does not act on itself (grav.c:211)
-                        const float4 sk = W.sink[s];
-                        float fx, fy, fz, fp, fdt;
-                        part_on_sink(p.m, p.h, sk.x - px, sk.y - py, sk.z - pz, sk.w, W.sh[s], fx, fy, fz, fp, fdt);
-                        float4 v = W.acc[s][lane];
-                        v.x += fx; v.y += fy; v.z += fz; v.w -= fp;
-                        W.acc[s][lane] = v;
-                        W.dtm[s][lane] = fmaxf(W.dtm[s][lane], fdt);
-                    }
+                    float4 *S = &W.stage[lane * PSTRIDE];
+                    S[0] = make_float4((float)((p.x + s_off[3 * ci]) - cenx), (float)((p.y + s_off[3 * ci + 1]) - ceny),
+                                       (float)((p.z + s_off[3 * ci + 2]) - cenz), p.m);
+                    // a particle does not act on itself (grav.c:211): remember who it is, in the home image only
+                    S[1] = make_float4(p.h, __int_as_float(ci == A.homeImage ? pi : -1), 0.f, 0.f);
                 }
                 __syncwarp();
+                if (worker) {
+#pragma unroll 2
+                    for (int j = q; j < cnt; j += G) {
+                        const float4 pp = W.stage[j * PSTRIDE];
+                        const float2 ph = *reinterpret_cast<const float2 *>(&W.stage[j * PSTRIDE + 1]);
+                        if (__float_as_int(ph.y) == sidx) continue;
+                        float fx, fy, fz, fp, fdt;
+                        part_on_sink(pp.w, ph.x, sx - pp.x, sy - pp.y, sz - pp.z, ms, hs, fx, fy, fz, fp, fdt);
+                        ax += fx; ay += fy; az += fz; ap -= fp;
+                        dtm = fmaxf(dtm, fdt);
+                    }
+                }
+                dax += (double)ax; day += (double)ay; daz += (double)az; dap += (double)ap;
+                ax = ay = az = ap = 0.f;
+                __syncwarp();
+                blk = nxt;
+                cnt = 32;
             }
-            if (done) break;
+        }
+        // ---- softened cells (ILCS, rare): FP64, the first nS lanes each take their sink
+        {
+            int blk = heads[1], total = cnts[1];
+            int cnt = total > 0 ? total - 32 * ((total - 1) / 32) : 0;
+            while (blk >= 0) {
+                const int nxt = A.nextBlk[blk];
+                for (int j = 0; j < cnt; ++j) {
+                    const unsigned it = A.pool[(size_t)blk * 32 + j];
+                    const int cn = (int)(it >> A.imgBits), ci = (int)(it & imgMask);
+                    if (lane < nS) {
+                        const NodeW nd = load_node(&A.nodes[cn]);
+                        const double cx = nd.rx + s_off[3 * ci], cy = nd.ry + s_off[3 * ci + 1], cz = nd.rz + s_off[3 * ci + 2];
+                        const SoftTerm st = softcell_on_sink(nd.fMass, nd.fSoft, &A.momq[(size_t)cn * 6], ((double)sx + cenx) - cx,
+                                                             ((double)sy + ceny) - cy, ((double)sz + cenz) - cz, (double)ms,
+                                                             (double)hs);
+                        dax += st.ax; day += st.ay; daz += st.az; dap += st.pot;
+                        dtm = fmaxf(dtm, (float)st.dt);
+                    }
+                }
+                blk = nxt;
+                cnt = 32;
+            }
         }
 
-        // ---- reduce across the warp and write out
-        if (task.group == 0 && lane == 0) {
-            A.counts[3 * task.node] = cntP;
-            A.counts[3 * task.node + 1] = cntS;
-            A.counts[3 * task.node + 2] = cntN;
-        }
-        if (!A.walkOnly) {
-            for (int s = 0; s < nS; ++s) {
-                const float4 v = W.acc[s][lane];
-                double vx = v.x, vy = v.y, vz = v.z, vp = v.w;
-                float vd = W.dtm[s][lane];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    vx += __shfl_xor_sync(FULL, vx, o);
-                    vy += __shfl_xor_sync(FULL, vy, o);
-                    vz += __shfl_xor_sync(FULL, vz, o);
-                    vp += __shfl_xor_sync(FULL, vp, o);
-                    vd = fmaxf(vd, __shfl_xor_sync(FULL, vd, o));
+        // ---- combine the G sub-groups (FP64, fixed order) and write out
+        {
+            double *red = reinterpret_cast<double *>(W.stage); // [32][4] doubles, then [32] floats
+            float *redt = reinterpret_cast<float *>(red + 128);
+            red[4 * lane] = dax; red[4 * lane + 1] = day; red[4 * lane + 2] = daz; red[4 * lane + 3] = dap;
+            redt[lane] = dtm;
+            __syncwarp();
+            if (lane < nS) {
+                double vx = 0.0, vy = 0.0, vz = 0.0, vp = 0.0;
+                float vd = 0.f;
+                for (int g = 0; g < G; ++g) {
+                    const int l = g * nS + lane;
+                    vx += red[4 * l]; vy += red[4 * l + 1]; vz += red[4 * l + 2]; vp += red[4 * l + 3];
+                    vd = fmaxf(vd, redt[l]);
                 }
-                if (lane == 0) {
-                    const int pi = W.sidx[s];
-                    A.acc[3 * (size_t)pi] = vx;
-                    A.acc[3 * (size_t)pi + 1] = vy;
-                    A.acc[3 * (size_t)pi + 2] = vz;
-                    A.pot[pi] = vp;
-                    A.dtg[pi] = (double)vd;
-                }
+                A.acc[3 * (size_t)sidx] = vx;
+                A.acc[3 * (size_t)sidx + 1] = vy;
+                A.acc[3 * (size_t)sidx + 2] = vz;
+                A.pot[sidx] = vp;
+                A.dtg[sidx] = (double)vd;
             }
         }
         __syncwarp();
@@ -493,26 +644,39 @@ __global__ void __launch_bounds__(GG_WARPS_PER_CTA * 32) k_tree_gravity(const Tr
 
 } // namespace
 
-size_t gg_tree_kernel_smem(int maxBucket) { return GG_WARPS_PER_CTA * warp_smem_bytes(maxBucket); }
+size_t gg_walk_kernel_smem(int maxBucket) { return GG_WALK_WARPS * walk_smem_bytes(maxBucket); }
 
-cudaError_t gg_launch_tree_kernel(const TreeKernelArgs &a, int nSM, cudaStream_t st) {
-    void (*fn)(const TreeKernelArgs) = nullptr;
-    switch (a.iOrder) {
-    case 1: fn = k_tree_gravity<1>; break;
-    case 2: fn = k_tree_gravity<2>; break;
-    case 3: fn = k_tree_gravity<3>; break;
-    default: fn = k_tree_gravity<4>; break;
-    }
-    size_t smem = gg_tree_kernel_smem(a.maxBucket);
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+static int grid_for(const void *fn, int threads, size_t smem, int nSM, int warpsPerCta, int nTasks, cudaError_t *pe) {
     int perSM = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, fn, GG_WARPS_PER_CTA * 32, smem);
-    if (e != cudaSuccess) return e;
+    *pe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, fn, threads, smem);
     if (perSM < 1) perSM = 1;
     int grid = nSM * perSM;
-    int need = (a.nTasks + GG_WARPS_PER_CTA - 1) / GG_WARPS_PER_CTA;
+    const int need = (nTasks + warpsPerCta - 1) / warpsPerCta;
     if (grid > need) grid = need > 0 ? need : 1;
-    fn<<<grid, GG_WARPS_PER_CTA * 32, smem, st>>>(a);
+    return grid;
+}
+
+cudaError_t gg_launch_walk_kernel(const TreeKernelArgs &a, int nSM, cudaStream_t st) {
+    const size_t smem = gg_walk_kernel_smem(a.maxBucket);
+    cudaError_t e = cudaFuncSetAttribute(k_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int grid = grid_for((const void *)k_walk, GG_WALK_WARPS * 32, smem, nSM, GG_WALK_WARPS, a.nTasks, &e);
+    if (e != cudaSuccess) return e;
+    k_walk<<<grid, GG_WALK_WARPS * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t gg_launch_eval_kernel(const TreeKernelArgs &a, int nSM, cudaStream_t st) {
+    void (*fn)(const TreeKernelArgs) = nullptr;
+    switch (a.iOrder) {
+    case 1: fn = k_eval<1>; break;
+    case 2: fn = k_eval<2>; break;
+    case 3: fn = k_eval<3>; break;
+    default: fn = k_eval<4>; break;
+    }
+    cudaError_t e;
+    const int grid = grid_for((const void *)fn, GG_WARPS_PER_CTA * 32, 0, nSM, GG_WARPS_PER_CTA, a.nTasks, &e);
+    if (e != cudaSuccess) return e;
+    fn<<<grid, GG_WARPS_PER_CTA * 32, 0, st>>>(a);
     return cudaGetLastError();
 }

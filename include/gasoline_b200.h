@@ -91,11 +91,12 @@ typedef struct gg_stats {
     double dPartSum, dCellSum, dSoftSum; /* pkd.c:2945-2949 */
     double dFlop;                        /* grav.c:246-247 + ewald.c:175-176, the reference's own scoring */
     double dFlopEwald;                   /* the Ewald share of dFlop */
-    double msTree;                       /* fused walk+interact kernel */
+    double msTree;                       /* walk + list-evaluation kernels */
     double msEwald;                      /* Ewald kernel */
     double msTotal;                      /* everything on the device between upload and download */
     int nKernelLaunches;                 /* kernels of this library launched by the call */
     int nMaxPart, nMaxCellSoft, nMaxCellNewt; /* per-bucket list maxima (the reference's diag line, pkd.c:3057) */
+    double msWalk;                       /* the walk kernel's share of msTree */
 } gg_stats;
 
 const char *gg_last_error(void);
