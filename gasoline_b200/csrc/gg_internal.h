@@ -15,7 +15,12 @@
 #include "../../include/gasoline_b200.h"
 
 #define GG_WARPS_PER_CTA 4   // k_eval
+#ifndef GG_MIN_CTAS
 #define GG_MIN_CTAS 6        // resident CTAs per SM k_eval is compiled for (register cap 65536/(128*6) = 85)
+#endif
+#ifndef GG_CELL_UNROLL
+#define GG_CELL_UNROLL 1     // unroll factor of k_eval's (sink, cell) loop
+#endif
 #define GG_WALK_WARPS 8      // k_walk
 #define GG_WALK_MIN_CTAS 5   // 40 warps per SM (register cap 51)
 #define GG_SLAB_BLOCKS 32    // list blocks a warp takes from the pool per atomic

@@ -535,7 +535,8 @@ __global__ void __launch_bounds__(GG_WARPS_PER_CTA * 32, GG_MIN_CTAS) k_eval(con
                 }
                 __syncwarp();
                 if (worker) {
-#pragma unroll 1
+                    constexpr int kUnroll = GG_CELL_UNROLL;
+#pragma unroll kUnroll
                     for (int j = q; j < cnt; j += G) {
                         const float4 *S = &W.stage[j * CSTRIDE];
                         const float4 pc = S[0];

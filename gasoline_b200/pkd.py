@@ -59,7 +59,7 @@ def load_library(path: str | None = None):
     global _lib
     if _lib is not None:
         return _lib
-    path = path or LIB_PATH
+    path = path or os.environ.get("GASOLINE_B200_LIB") or LIB_PATH  # the env override is for kernel experiments
     if not os.path.exists(path):
         raise GasolineB200Error(f"{path} is missing: run `python -m gasoline_b200.build` (nvcc, sm_100a). "
                                 "There is no CPU fallback for this path.")
