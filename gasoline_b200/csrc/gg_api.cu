@@ -165,6 +165,14 @@ __global__ void k_fill_tasks(int nNodes, const int *ngroups, const int *offs, Ta
     for (int g = 0; g < ngroups[i]; ++g) tasks[offs[i] + g] = Task{i, g};
 }
 
+__global__ void k_max_bucket(int n, const int *pLower, const int *pUpper, const int *iLower, int *out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int v = (i < n && iLower[i] == -1) ? pUpper[i] - pLower[i] + 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0 && v > 0) atomicMax(out, v);
+}
+
 // Uniform background for comoving, non-periodic runs (pkd.c:2967-2991).
 __global__ void k_comove(int n, const PartS *parts, const int *active, double dRhoFac, double *acc, double *pot) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -354,8 +362,19 @@ int gg_set_remote(gg_context *c, int id, const gg_tree *t, const gg_particles *p
                                 GG_MAX_BUCKET);
                 if (np > c->maxBucket) c->maxBucket = np;
             }
-    } else if (c->maxBucket < GG_MAX_BUCKET) {
-        c->maxBucket = GG_MAX_BUCKET; // cannot inspect device-resident links cheaply: size for the limit
+    } else if (t->nNodes > 0) { // device-resident links: one small reduction kernel finds the largest bucket
+        int rc0;
+        if ((rc0 = ensure(c, c->misc, 16 * sizeof(int)))) return rc0;
+        CK(cudaMemsetAsync((int *)c->misc.p + 8, 0, sizeof(int), c->st));
+        k_max_bucket<<<(t->nNodes + 255) / 256, 256, 0, c->st>>>(t->nNodes, t->pLower, t->pUpper, t->iLower,
+                                                                 (int *)c->misc.p + 8);
+        CK(cudaGetLastError());
+        int maxB = 0;
+        CK(cudaMemcpyAsync(&maxB, (int *)c->misc.p + 8, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        if (maxB > GG_MAX_BUCKET)
+            return fail(GG_ERR_UNSUPPORTED, "gg_set_remote: a bucket holds %d particles (limit %d)", maxB, GG_MAX_BUCKET);
+        if (maxB > c->maxBucket) c->maxBucket = maxB;
     }
     int rc = upload_domain(c, t, pp, c->nNodesAll, c->nPartAll, false, bDevice != 0);
     if (rc) return rc;

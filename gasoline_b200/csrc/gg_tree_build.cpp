@@ -364,3 +364,16 @@ extern "C" int gg_tree_view(const gg_built_tree *bt, gg_tree *v, double root[GG_
 }
 
 extern "C" void gg_tree_free(gg_built_tree *bt) { delete bt; }
+
+// pkdCalcCell (pkd.c:2018) over a whole domain about a given centre: one rank's contribution to a top-tree cell.
+extern "C" int gg_cell_moments(int n, const double *x, const double *y, const double *z, const double *fMass,
+                               const double rcm[3], int iOrder, double mom[GG_NMOM], double *pBmax) {
+    if (n < 0 || !x || !y || !z || !fMass || !rcm || !mom || !pBmax || iOrder < 1 || iOrder > 4) return GG_ERR_ARG;
+    std::vector<P> p((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        p[i].r[0] = x[i]; p[i].r[1] = y[i]; p[i].r[2] = z[i];
+        p[i].m = fMass[i]; p[i].h = 0.0; p[i].active = 1; p[i].iOrder = i;
+    }
+    cell_moments(p.data(), 0, n - 1, rcm, iOrder, mom, pBmax);
+    return GG_OK;
+}

@@ -1,0 +1,406 @@
+"""Multi-GPU runs: one spatial domain per rank/GPU, the reference's top tree on every rank, remote trees over NCCL.
+
+The reference splits the particles over its ranks by ORB (pstDomainDecomp, pst.c:1854), builds one local tree per
+rank (pkdBuildBinary), hangs the local roots under a small "top tree" that mirrors the rank tree (PST) and that
+every rank holds (pstBuildTree interior branch pst.c:2918-2951, pstColCells/pkdDistribCells), and then lets every
+bucket walk top tree -> local tree or remote trees (pkdBucketWalk walk.c:342-435; remote cells and particles come
+through the MDL software cache, element by element).  Here the same structures are assembled with collectives:
+
+  1. all-gather of each rank's root cell (78 doubles)                      -> every rank knows all local roots
+  2. every rank combines them bottom-up like pkdCombine (pkd.c:1973)       -> mass, centre, softening of each top cell
+  3. every rank sums its particles' moments about the centre of each top cell above it (pkdCalcCell pkd.c:2018 via
+     gg_cell_moments), all-gather, add in the PST's lower-then-upper order (pstCalcCell pst.c:3789), pkdCalcOpen
+                                                                            -> kdTop, bit-identical to the reference's
+  4. Ewald root expansion like pkdCalcRoot/pkdDistribRoot (pkd.c:4395-4493): m, centre, quadrupole of kdTop[ROOT];
+     l = 3, 4 moments summed over the ranks' LOCAL expansions (the reference's convention)
+  5. all-gather of the trees + particles themselves (NCCL over NVLink when the ranks are GPUs) and gg_set_remote:
+     a push of whole domains instead of the reference's pull-on-demand cache.
+
+`Domain` is the per-rank state and holds only host arrays, so steps 1-4 run (and are tested) without a GPU;
+`attach()` hands the result to a PKD.  `run_in_process` drives several Domains inside one process (tests; several
+contexts on one GPU); `DistributedExchange` drives one Domain per torch.distributed rank (bench.py --gpus N).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import pkd as _pkd
+from .pkd import GG_NMOM, GG_NROOT, PKD, Tree
+
+SUMMARY_LEN = 6 + 3 + 3 + GG_NMOM + GG_NROOT  # bnd, r, (fMass, fSoft, fOpen2), mom, local root expansion
+
+
+# ---------------------------------------------------------------------------------------------- rank tree (PST)
+@dataclass
+class PstNode:
+    iCell: int                 # heap index in kdTop: ROOT = 1, LOWER(i) = 2i, UPPER(i) = 2i+1 (pkd.h:77-86)
+    ranks: list                # ranks below this node, lower subtree first
+    lower: "PstNode | None" = None
+    upper: "PstNode | None" = None
+
+    @property
+    def leaf(self) -> bool:
+        return self.lower is None
+
+
+def pst_tree(nThreads: int) -> PstNode:
+    """The rank tree msrInitialize grows by adding ranks 1..n-1 one at a time with pstSetAdd (pst.c:598-625): a new
+    rank goes to the upper side when the lower side is heavier, else to the lower side; a leaf that receives a rank
+    becomes a node with itself as the lower and the newcomer as the upper leaf."""
+    class N:
+        def __init__(self, rank):
+            self.rank, self.nLeaves, self.nLower, self.nUpper, self.lo, self.up = rank, 1, 0, 0, None, None
+
+    def add(n, rank):
+        if n.nLeaves > 1:
+            n.nLeaves += 1
+            if n.nLower > n.nUpper:
+                n.nUpper += 1
+                add(n.up, rank)
+            else:
+                n.nLower += 1
+                add(n.lo, rank)
+        else:
+            n.nLeaves, n.nLower, n.nUpper = 2, 1, 1
+            n.lo, n.up = N(n.rank), N(rank)
+
+    root = N(0)
+    for r in range(1, nThreads):
+        add(root, r)
+
+    def conv(n, iCell):
+        if n.lo is None:
+            return PstNode(iCell, [n.rank])
+        lo, up = conv(n.lo, 2 * iCell), conv(n.up, 2 * iCell + 1)
+        return PstNode(iCell, lo.ranks + up.ranks, lo, up)
+
+    return conv(root, 1)
+
+
+def top_cells(nThreads: int) -> int:
+    """nCell of kdTop: 2^(1+ceil(log2 nThreads)) (master.c:4293)."""
+    return 1 << (1 + int(np.ceil(np.log(float(nThreads)) / np.log(2.0)))) if nThreads > 1 else 2
+
+
+def interior_nodes(root: PstNode) -> list:
+    out = []
+
+    def walk(n):
+        if not n.leaf:
+            out.append(n)
+            walk(n.lower)
+            walk(n.upper)
+
+    walk(root)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- decomposition
+def orb_decompose(x, y, z, nThreads: int, weights=None) -> list:
+    """ORB over the rank tree (pstDomainDecomp pst.c:1854): at every node split the LONGEST axis of the node's
+    bounding box so that the lower side receives the share nLower/nLeaves of the weight (particle count when
+    weights is None -- the reference's bSplitWork=0 path; pass last step's fWeight for work balancing).
+    Returns one index array per rank.  (A Gasoline host does this itself; bench.py and the tests use it.)"""
+    pos = np.stack([np.asarray(x), np.asarray(y), np.asarray(z)], axis=1)
+    w = np.ones(len(pos)) if weights is None else np.asarray(weights, dtype=np.float64)
+    out = [None] * nThreads
+
+    def split(node, idx):
+        if node.leaf:
+            out[node.ranks[0]] = np.sort(idx)
+            return
+        p = pos[idx]
+        d = int(np.argmax(p.max(axis=0) - p.min(axis=0)))
+        order = np.argsort(p[:, d], kind="stable")
+        cw = np.cumsum(w[idx][order])
+        share = len(node.lower.ranks) / len(node.ranks)
+        k = int(np.searchsorted(cw, share * cw[-1], side="left")) + 1
+        k = min(max(k, 1), len(idx) - 1)
+        split(node.lower, idx[order[:k]])
+        split(node.upper, idx[order[k:]])
+
+    split(pst_tree(nThreads), np.arange(len(pos)))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- per-rank state
+class Domain:
+    """One rank: its particles (tree order) and local tree on the host; the top tree once assemble() has run."""
+
+    def __init__(self, idSelf: int, nThreads: int, x, y, z, m, h, fPeriod, theta: float, nBucket: int = 8,
+                 iOrder: int = 4, active=None, pinned: bool = False, device: int | None = None):
+        self.idSelf, self.nThreads, self.theta, self.iOrder = idSelf, nThreads, float(theta), iOrder
+        self.fPeriod = tuple(float(v) for v in fPeriod)
+        self.pst = pst_tree(nThreads)
+        self.L = _pkd.load_library()
+        # the tree builder is host code; a PKD (GPU context) is only created when a device is given
+        self.pkd = PKD(device=device, idSelf=idSelf, fPeriod=fPeriod, pinned=pinned) if device is not None else None
+        host = self.pkd if self.pkd is not None else _HostStore()
+        host.pkdLoadParticles(x, y, z, m, h, active)
+        _build(host, nBucket, theta, iOrder)
+        self.host = host
+        self.kdTop = None
+        self.ilcnRoot = None
+
+    # -- step 1
+    def summary(self) -> np.ndarray:
+        t, r = self.host.tree, self.host.tree.iRoot
+        return np.concatenate([t.bnd[r], t.r[r], [t.fMass[r], t.fSoft[r], t.fOpen2[r]], t.mom[r],
+                               self.host.ilcnRoot]).astype(np.float64)
+
+    # -- steps 2 + 3 (local part)
+    def ancestor_moments(self, summaries: np.ndarray) -> np.ndarray:
+        """[nInterior][32]: this rank's pkdCalcCell sums (31 moments + Bmax) about the centre of every top cell above
+        it, zeros for top cells that do not contain it."""
+        cells = combine_top(self.pst, summaries)
+        nodes = interior_nodes(self.pst)
+        out = np.zeros((len(nodes), GG_NMOM + 1))
+        h = self.host
+        for k, n in enumerate(nodes):
+            if self.idSelf not in n.ranks:
+                continue
+            rcm = np.ascontiguousarray(cells[n.iCell]["r"], dtype=np.float64)
+            mom, bmax = np.zeros(GG_NMOM), C.c_double()
+            rc = self.L.gg_cell_moments(h.nLocal, _pkd._d(h.x), _pkd._d(h.y), _pkd._d(h.z), _pkd._d(h.fMass),
+                                        _pkd._d(rcm), self.iOrder, _pkd._d(mom), C.byref(bmax))
+            if rc != 0:
+                raise _pkd.GasolineB200Error(f"gg_cell_moments failed ({rc})")
+            out[k, :GG_NMOM], out[k, GG_NMOM] = mom, bmax.value
+        return out
+
+    # -- steps 3 (sum) + 4
+    def assemble(self, summaries: np.ndarray, anc: np.ndarray):
+        """summaries [nThreads][SUMMARY_LEN], anc [nThreads][nInterior][32] -> self.kdTop (dict of heap arrays) and
+        self.ilcnRoot, the same on every rank."""
+        self.kdTop, self.ilcnRoot = assemble_top(self.pst, self.nThreads, summaries, anc, self.theta)
+        return self.kdTop, self.ilcnRoot
+
+    # -- step 5
+    def export_raw(self):
+        """(doubles, ints) holding this domain's tree + particles in the field order gg_set_remote reads."""
+        t, h = self.host.tree, self.host
+        dbl = np.concatenate([t.r.ravel(), t.fMass, t.fSoft, t.fOpen2, t.mom.ravel(), h.x, h.y, h.z, h.fMass, h.fSoft])
+        ints = np.concatenate([[t.nNodes, t.iRoot, h.nLocal, 0], t.pLower, t.pUpper, t.iLower, t.iUpper]).astype(np.int32)
+        return np.ascontiguousarray(dbl, dtype=np.float64), ints
+
+    def attach(self):
+        """Hand kdTop + ilcnRoot to the GPU context (gg_set_local via upload, gg_set_top, gg_set_root_moments)."""
+        if self.pkd is None:
+            raise _pkd.GasolineB200Error("Domain.attach: created without a device")
+        self.pkd.upload()
+        k = self.kdTop
+        self.pkd.pkdDistribCells(k["pLower"], k["bUsed"], k["r"], k["fMass"], k["fSoft"], k["fOpen2"], k["mom"])
+        self.pkd.pkdDistribRoot(self.ilcnRoot)
+
+    def set_remote_raw(self, id_: int, dbl, ints, dbl_ptr: int | None = None, int_ptr: int | None = None):
+        """A remote domain from export_raw() data.  With dbl_ptr/int_ptr (device addresses of the same layout, e.g.
+        inside an NCCL all-gather buffer) nothing is staged through the host: gg_set_remote(bDevice=1)."""
+        nn, iRoot, n = int(ints[0]), int(ints[1]), int(ints[2])
+        esz_d, esz_i = 8, 4
+        base_d = dbl_ptr if dbl_ptr is not None else dbl.ctypes.data
+        base_i = (int_ptr if int_ptr is not None else ints.ctypes.data) + 4 * esz_i
+        off = 0
+
+        def dptr(count):
+            nonlocal off
+            p = C.cast(base_d + off * esz_d, _pkd._dp)
+            off += count
+            return p
+
+        tv = _pkd.gg_tree()
+        tv.nNodes, tv.iRoot = nn, iRoot
+        tv.bnd = None
+        tv.r, tv.fMass, tv.fSoft, tv.fOpen2, tv.mom = dptr(3 * nn), dptr(nn), dptr(nn), dptr(nn), dptr(GG_NMOM * nn)
+        pv = _pkd.gg_particles()
+        pv.n = n
+        pv.x, pv.y, pv.z, pv.fMass, pv.fSoft = dptr(n), dptr(n), dptr(n), dptr(n), dptr(n)
+        pv.active = None
+        ip = lambda k: C.cast(base_i + k * nn * esz_i, _pkd._ip)
+        tv.pLower, tv.pUpper, tv.iLower, tv.iUpper = ip(0), ip(1), ip(2), ip(3)
+        _pkd._check(self.L.gg_set_remote(self.pkd._ctx, id_, C.byref(tv), C.byref(pv), 1 if dbl_ptr is not None else 0),
+                    "gg_set_remote")
+
+
+class _HostStore:
+    """The particle/tree half of PKD without a GPU context (CPU-only hosts and tests)."""
+    pinned = False
+
+    def __init__(self):
+        self._L = _pkd.load_library()
+
+    _own = PKD._own
+    pkdLoadParticles = PKD.pkdLoadParticles
+    pkdBuildBinary = PKD.pkdBuildBinary
+
+
+def _build(host, nBucket, theta, iOrder):
+    host.pkdBuildBinary(nBucket, theta, iOrder)
+
+
+# ---------------------------------------------------------------------------------------------- top tree arithmetic
+def _unpack(s):
+    return dict(bnd=s[0:6], r=s[6:9], fMass=s[9], fSoft=s[10], fOpen2=s[11], mom=s[12:12 + GG_NMOM],
+                root=s[12 + GG_NMOM:12 + GG_NMOM + GG_NROOT])
+
+
+def combine_top(pst: PstNode, summaries: np.ndarray) -> dict:
+    """pkdCombine (pkd.c:1973-2015) bottom-up over the rank tree: {iCell: {bnd, r, fMass, fSoft}}; leaves carry the
+    ranks' root cells.  Plain double arithmetic in the reference's operation order (products, then one sum, then
+    the division), so every rank -- and the reference -- gets the same bits."""
+    cells = {}
+
+    def walk(n):
+        if n.leaf:
+            cells[n.iCell] = _unpack(summaries[n.ranks[0]])
+            return cells[n.iCell]
+        a, b = walk(n.lower), walk(n.upper)
+        bnd = np.concatenate([np.where(b["bnd"][:3] < a["bnd"][:3], b["bnd"][:3], a["bnd"][:3]),
+                              np.where(b["bnd"][3:] > a["bnd"][3:], b["bnd"][3:], a["bnd"][3:])])
+        m1, m2 = float(a["fMass"]), float(b["fMass"])
+        mass = m1 + m2
+        soft = m1 * float(a["fSoft"]) + m2 * float(b["fSoft"])
+        r = np.array([m1 * float(a["r"][j]) + m2 * float(b["r"][j]) for j in range(3)])
+        if mass > 0:
+            soft /= mass
+            r = np.array([float(v) / mass for v in r])
+        cells[n.iCell] = dict(bnd=bnd, r=r, fMass=mass, fSoft=soft)
+        return cells[n.iCell]
+
+    walk(pst)
+    return cells
+
+
+def calc_open(bmax: float, theta: float) -> float:
+    """pkdCalcOpen, OPEN_JOSH (pkd.c:2253-2260), squared (pst.c:2950)."""
+    d = 2 / np.sqrt(3.0) * bmax / theta
+    if d < bmax:
+        d = bmax
+    return float(d * d)
+
+
+def assemble_top(pst: PstNode, nThreads: int, summaries: np.ndarray, anc: np.ndarray, theta: float):
+    nCell = top_cells(nThreads)
+    cells = combine_top(pst, summaries)
+    nodes = interior_nodes(pst)
+    index = {n.iCell: k for k, n in enumerate(nodes)}
+    top = dict(pLower=np.full(nCell, -1, np.int32), bUsed=np.zeros(nCell, np.int32), r=np.zeros((nCell, 3)),
+               fMass=np.zeros(nCell), fSoft=np.zeros(nCell), fOpen2=np.zeros(nCell), mom=np.zeros((nCell, GG_NMOM)),
+               bnd=np.zeros((nCell, 6)))
+
+    def moment_sum(sub: PstNode, k: int):
+        """pstCalcCell (pst.c:3789-3845): lower subtree + upper subtree, element by element; Bmax is a maximum."""
+        if sub.leaf:
+            return anc[sub.ranks[0]][k].copy()
+        a, b = moment_sum(sub.lower, k), moment_sum(sub.upper, k)
+        out = a.copy()
+        out[:GG_NMOM] = a[:GG_NMOM] + b[:GG_NMOM]
+        out[GG_NMOM] = b[GG_NMOM] if b[GG_NMOM] > a[GG_NMOM] else a[GG_NMOM]
+        return out
+
+    def fill(n: PstNode):
+        c, i = cells[n.iCell], n.iCell
+        top["bUsed"][i] = 1
+        top["r"][i], top["fMass"][i], top["fSoft"][i], top["bnd"][i] = c["r"], c["fMass"], c["fSoft"], c["bnd"]
+        if n.leaf:
+            top["pLower"][i] = n.ranks[0]
+            top["fOpen2"][i], top["mom"][i] = c["fOpen2"], c["mom"]
+            return
+        s = moment_sum(n, index[i])
+        top["mom"][i] = s[:GG_NMOM]
+        top["fOpen2"][i] = calc_open(float(s[GG_NMOM]), theta)
+        fill(n.lower)
+        fill(n.upper)
+
+    fill(pst)
+
+    # pkdCalcRoot summed like pstCalcRoot (lower + upper), then pkdDistribRoot's overwrite of m, centre, quadrupole
+    def root_sum(sub: PstNode):
+        if sub.leaf:
+            return _unpack(summaries[sub.ranks[0]])["root"].copy()
+        return root_sum(sub.lower) + root_sum(sub.upper)
+
+    root = root_sum(pst)
+    q = top["mom"][1]
+    root[0] = top["fMass"][1]
+    root[1:4] = top["r"][1]
+    root[4], root[5], root[6], root[7], root[8], root[9] = q[0], q[1], q[3], q[4], q[5], q[2]  # xx yy xy xz yz zz
+    return top, root
+
+
+# ---------------------------------------------------------------------------------------------- drivers
+def run_in_process(domains: list, exchange_trees: bool = True):
+    """All ranks inside this process (tests; several contexts on one GPU): the all-gathers are list comprehensions."""
+    summaries = np.stack([d.summary() for d in domains])
+    anc = np.stack([d.ancestor_moments(summaries) for d in domains])
+    for d in domains:
+        d.assemble(summaries, anc)
+    if exchange_trees and all(d.pkd is not None for d in domains):
+        raws = [d.export_raw() for d in domains]
+        for d in domains:
+            d.attach()
+            for o, (dbl, ints) in zip(domains, raws):
+                if o.idSelf != d.idSelf:
+                    d.set_remote_raw(o.idSelf, dbl, ints)
+    return summaries, anc
+
+
+class DistributedExchange:
+    """One Domain per torch.distributed rank.  Small collectives (steps 1-4) go through host tensors on gloo or
+    device tensors on NCCL; the bulk tree exchange (step 5) is one padded all_gather_into_tensor per element type
+    on the device, and the remote domains are ingested straight from the gather buffer (no host staging)."""
+
+    def __init__(self, domain: Domain, backend_device: str):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.d, self.dev = torch, dist, domain, backend_device
+        self.world = dist.get_world_size()
+        self._bufs = None
+
+    def _all_gather_np(self, a: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(a)
+        t = self.torch.from_numpy(a.reshape(-1)).to(self.dev)
+        out = self.torch.empty(self.world * t.numel(), dtype=t.dtype, device=self.dev)
+        self.dist.all_gather_into_tensor(out, t)  # flat in, flat out: the form both gloo and NCCL accept
+        return out.cpu().numpy().reshape((self.world,) + a.shape)
+
+    def top_tree(self):
+        summaries = self._all_gather_np(self.d.summary())
+        anc = self._all_gather_np(self.d.ancestor_moments(summaries))
+        self.d.assemble(summaries, anc)
+        return summaries, anc
+
+    def exchange(self, attach: bool = True):
+        """Steps 1-5.  Returns the bytes this rank received over the interconnect."""
+        torch, dist, d = self.torch, self.dist, self.d
+        self.top_tree()
+        dbl, ints = d.export_raw()
+        sizes = self._all_gather_np(np.array([dbl.size, ints.size], dtype=np.int64))
+        nd, ni = int(sizes[:, 0].max()), int(sizes[:, 1].max())
+        if self._bufs is None or self._bufs[2].numel() != nd or self._bufs[3].numel() != ni:
+            self._bufs = (torch.empty(self.world * nd, dtype=torch.float64, device=self.dev),
+                          torch.empty(self.world * ni, dtype=torch.int32, device=self.dev),
+                          torch.zeros(nd, dtype=torch.float64, device=self.dev),
+                          torch.zeros(ni, dtype=torch.int32, device=self.dev))
+        fd, fi, sd, si = self._bufs
+        sd[:dbl.size].copy_(torch.from_numpy(dbl), non_blocking=True)
+        si[:ints.size].copy_(torch.from_numpy(ints), non_blocking=True)
+        dist.all_gather_into_tensor(fd, sd)  # every domain padded to the largest: one collective per element type
+        dist.all_gather_into_tensor(fi, si)
+        gd, gi = fd.view(self.world, nd), fi.view(self.world, ni)
+        if self.dev != "cpu":
+            torch.cuda.synchronize()
+        if attach and d.pkd is not None:
+            d.attach()
+            hosts = gi.cpu().numpy()
+            for r in range(self.world):
+                if r == d.idSelf:
+                    continue
+                if self.dev == "cpu":
+                    d.set_remote_raw(r, gd[r].numpy(), hosts[r])
+                else:
+                    d.set_remote_raw(r, None, hosts[r], gd[r].data_ptr(), gi[r].data_ptr())
+        self.gathered = (gd, gi, sizes)
+        return int((sizes[:, 0].sum() - dbl.size) * 8 + (sizes[:, 1].sum() - ints.size) * 4)

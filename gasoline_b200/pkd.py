@@ -84,6 +84,7 @@ def load_library(path: str | None = None):
                                 C.POINTER(C.c_void_p)]
     L.gg_tree_view.argtypes = [C.c_void_p, C.POINTER(gg_tree), _dp]
     L.gg_tree_free.argtypes = [C.c_void_p]
+    L.gg_cell_moments.argtypes = [C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_int, _dp, _dp]
     L.gg_measure_fp32_peak.argtypes = [C.c_void_p, _dp, _dp]
     L.gg_flush_l2.argtypes = [C.c_void_p]
     _lib = L

@@ -176,6 +176,13 @@ int gg_tree_build(int n, double *x, double *y, double *z, double *fMass, double 
 int gg_tree_view(const gg_built_tree *bt, gg_tree *view, double root[GG_NROOT]);
 void gg_tree_free(gg_built_tree *bt);
 
+
+/* pkdCalcCell (pkd.c:2018-2135) over all n particles of a domain about the centre rcm: reduced multipoles in GG_NMOM
+ * order and Bmax -- one rank's contribution to an interior cell of the top tree, which pstCalcCell (pst.c:3789) sums
+ * over the ranks below that cell.  Host code (no GPU needed); used by multi-GPU hosts that are not Gasoline. */
+int gg_cell_moments(int n, const double *x, const double *y, const double *z, const double *fMass,
+                    const double rcm[3], int iOrder, double mom[GG_NMOM], double *pBmax);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,6 +10,7 @@
  *     (the reference itself only reports sums, pkd.c:2945-2949),
  *   - per-particle a, fPot, dtGrav, fWeight after pkdGravAll (pkd.c:2868).
  */
+#include <assert.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -33,14 +34,87 @@ typedef struct {
 /* ---- per-bucket counts: --wrap=pkdBucketWalk -------------------------------------------------- */
 static int *g_counts = NULL; /* 3 ints per node, indexed by iBucket */
 static int g_nCounts = 0;
-static FILE *g_fpCounts = NULL; /* multi-rank binary: REF_DUMP_COUNTS=prefix */
 void __real_pkdBucketWalk(PKD pkd, int iBucket, int nReps, int iOrder);
+/*
+ * Multi-rank dump (gasoline_ref binary, pthread MDL ranks; env REF_DUMP=<prefix>): on a rank's first pkdBucketWalk
+ * write <prefix>.rank<id>: ints nThreads idSelf nLocal nNodes iRoot nTopCells; per particle (tree order) iOrder;
+ * kdTop[0..nTop) as records of (int pLower, int pUpper, doubles r[3] fMass fSoft fOpen2 mom[31]); ilcnRoot (35
+ * doubles); then one record (iBucket pLower pUpper nPart nCellSoft nCellNewt) per bucket walked.
+ */
+#define REF_MAX_RANKS 64
+static FILE *g_dump[REF_MAX_RANKS];
+static void dump_header(PKD pkd) {
+    const char *prefix = getenv("REF_DUMP");
+    char name[512];
+    FILE *f;
+    int i, k, hdr[6], nTop;
+    snprintf(name, sizeof(name), "%s.rank%d", prefix, pkd->idSelf);
+    f = fopen(name, "wb");
+    assert(f);
+    g_dump[pkd->idSelf] = f;
+    nTop = 1;
+    while (nTop < 2 * mdlThreads(pkd->mdl)) nTop *= 2; /* master.c:4293: 2^(1+ceil(log2 nThreads)) */
+    if (mdlThreads(pkd->mdl) == 1) nTop = 2;
+    hdr[0] = mdlThreads(pkd->mdl); hdr[1] = pkd->idSelf; hdr[2] = pkd->nLocal; hdr[3] = pkd->nNodes;
+    hdr[4] = pkd->iRoot; hdr[5] = nTop;
+    fwrite(hdr, sizeof(int), 6, f);
+    for (i = 0; i < pkd->nLocal; ++i) fwrite(&pkd->pStore[i].iOrder, sizeof(int), 1, f);
+    for (i = 0; i < nTop; ++i) {
+        const KDN *c = &pkd->kdTop[i];
+        const double *mo = (const double *)&c->mom;
+        double rec[6 + 31];
+        int ii[2];
+        ii[0] = c->pLower; ii[1] = c->pUpper;
+        rec[0] = c->r[0]; rec[1] = c->r[1]; rec[2] = c->r[2]; rec[3] = c->fMass; rec[4] = c->fSoft; rec[5] = c->fOpen2;
+        for (k = 0; k < 31; ++k) rec[6 + k] = mo[k];
+        fwrite(ii, sizeof(int), 2, f);
+        fwrite(rec, sizeof(double), 37, f);
+    }
+    fwrite(&pkd->ilcnRoot, sizeof(double), 35, f);
+    fflush(f);
+}
+
 void __wrap_pkdBucketWalk(PKD pkd, int iBucket, int nReps, int iOrder) {
     __real_pkdBucketWalk(pkd, iBucket, nReps, iOrder);
+    if (getenv("REF_DUMP") && pkd->idSelf < REF_MAX_RANKS) {
+        int rec[6];
+        if (!g_dump[pkd->idSelf]) dump_header(pkd);
+        rec[0] = iBucket; rec[1] = pkd->kdNodes[iBucket].pLower; rec[2] = pkd->kdNodes[iBucket].pUpper;
+        rec[3] = pkd->nPart; rec[4] = pkd->nCellSoft; rec[5] = pkd->nCellNewt;
+        fwrite(rec, sizeof(int), 6, g_dump[pkd->idSelf]);
+        fflush(g_dump[pkd->idSelf]);
+    }
     if (g_counts && iBucket < g_nCounts) {
         g_counts[3 * iBucket + 0] = pkd->nPart;
         g_counts[3 * iBucket + 1] = pkd->nCellSoft;
         g_counts[3 * iBucket + 2] = pkd->nCellNewt;
+    }
+}
+
+/* After the rank's pkdGravAll: marker record (iBucket = -1) + per-particle a[3], fPot, dtGrav, fWeight (tree order). */
+void __real_pkdGravAll(PKD pkd, int nReps, int bPeriodic, int iOrder, int bEwald, int iEwOrder, double fEwCut,
+                       double fEwhCut, int bComove, double dRhoFac, int bDoSun, double dSunSoft, double *aSun,
+                       int *nActive, double *pdPartSum, double *pdCellSum, double *pdSoftSum, CASTAT *pcs, double *pdFlop);
+void __wrap_pkdGravAll(PKD pkd, int nReps, int bPeriodic, int iOrder, int bEwald, int iEwOrder, double fEwCut,
+                       double fEwhCut, int bComove, double dRhoFac, int bDoSun, double dSunSoft, double *aSun,
+                       int *nActive, double *pdPartSum, double *pdCellSum, double *pdSoftSum, CASTAT *pcs, double *pdFlop) {
+    __real_pkdGravAll(pkd, nReps, bPeriodic, iOrder, bEwald, iEwOrder, fEwCut, fEwhCut, bComove, dRhoFac, bDoSun,
+                      dSunSoft, aSun, nActive, pdPartSum, pdCellSum, pdSoftSum, pcs, pdFlop);
+    if (getenv("REF_DUMP") && pkd->idSelf < REF_MAX_RANKS && g_dump[pkd->idSelf]) {
+        FILE *f = g_dump[pkd->idSelf];
+        int rec[6] = {-1, 0, 0, 0, 0, 0}, i;
+        double sums[4];
+        fwrite(rec, sizeof(int), 6, f);
+        sums[0] = *pdPartSum; sums[1] = *pdCellSum; sums[2] = *pdSoftSum; sums[3] = *pdFlop;
+        fwrite(sums, sizeof(double), 4, f);
+        for (i = 0; i < pkd->nLocal; ++i) {
+            const PARTICLE *p = &pkd->pStore[i];
+            double v[6];
+            v[0] = p->a[0]; v[1] = p->a[1]; v[2] = p->a[2]; v[3] = p->fPot; v[4] = p->dtGrav; v[5] = p->fWeight;
+            fwrite(v, sizeof(double), 6, f);
+        }
+        fclose(f);
+        g_dump[pkd->idSelf] = NULL;
     }
 }
 

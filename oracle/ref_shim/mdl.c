@@ -109,8 +109,11 @@ void mdlAddService(MDL mdl, int sid, void *p1, void (*fcn)(void *, void *, int, 
     mdl->psrv[sid].nOutBytes = nOutBytes;
 }
 
+static int g_trace = -1;
+#define TRACE(...) do { if (g_trace < 0) g_trace = getenv("MDL_TRACE") != NULL; if (g_trace) { fprintf(stderr, __VA_ARGS__); fflush(stderr);} } while (0)
 void mdlReqService(MDL mdl, int id, int sid, void *vin, int nInBytes) {
     struct mdlShared *s = mdl->shared;
+    TRACE("[%d] req -> %d sid %d\n", mdl->idSelf, id, sid);
     MDL t = mdl->pmdl[id];
     char *copy = NULL;
     if (nInBytes > 0) {
@@ -186,6 +189,7 @@ int mdlSwap(MDL mdl, int id, size_t nBufBytes, void *vBuf, size_t nOutBytes, siz
     struct mdlShared *s = mdl->shared;
     MDL o = mdl->pmdl[id];
     size_t nIn, nSnd, nRoomOther, nOtherOut, nOtherDone0;
+    TRACE("[%d] swap with %d buf %zu out %zu\n", mdl->idSelf, id, nBufBytes, nOutBytes);
     pthread_mutex_lock(&s->mux);
     mdl->pSwapBuf = vBuf;
     mdl->nSwapBuf = nBufBytes;
@@ -193,7 +197,8 @@ int mdlSwap(MDL mdl, int id, size_t nBufBytes, void *vBuf, size_t nOutBytes, siz
     mdl->idSwapWith = id;
     mdl->iSwapState = 1; /* published */
     pthread_cond_broadcast(&s->cv);
-    while (!(o->iSwapState == 1 && o->idSwapWith == mdl->idSelf)) pthread_cond_wait(&s->cv, &s->mux);
+    /* the partner may already have copied (state 2) by the time we look: >= 1, not == 1 */
+    while (!(o->iSwapState >= 1 && o->idSwapWith == mdl->idSelf)) pthread_cond_wait(&s->cv, &s->mux);
     nOtherDone0 = o->nSwapTaken; /* reused as a monotonic "swaps completed" counter */
     pthread_mutex_unlock(&s->mux);
     /* both published: pull what fits from the partner's outgoing region (its top) into my bottom */
@@ -214,6 +219,7 @@ int mdlSwap(MDL mdl, int id, size_t nBufBytes, void *vBuf, size_t nOutBytes, siz
     pthread_mutex_unlock(&s->mux);
     *pnSndBytes = nSnd;
     *pnRcvBytes = nIn;
+    TRACE("[%d] swap done snd %zu rcv %zu\n", mdl->idSelf, nSnd, nIn);
     return (nSnd == nOutBytes && nIn == nOtherOut);
 }
 

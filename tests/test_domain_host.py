@@ -1,0 +1,107 @@
+"""CPU: the multi-GPU host logic (gasoline_b200/domain.py) -- rank tree, decomposition, top tree, Ewald root
+expansion -- against fixtures from MULTI-RANK runs of the reference binary, and across real processes with
+torch.distributed (gloo, world_size 2)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from gasoline_b200 import domain, ics
+from multirank_cases import NAMES, load, make_domains
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_pst_tree_matches_setadd_order():
+    # leaves left to right for 2, 3, 4, 8 ranks: what pstSetAdd produces (pst.c:598)
+    leaves = lambda n: domain.pst_tree(n).ranks
+    assert leaves(1) == [0] and leaves(2) == [0, 1] and leaves(3) == [0, 2, 1]
+    assert leaves(4) == [0, 2, 1, 3] and leaves(8) == [0, 4, 2, 6, 1, 5, 3, 7]
+    assert [domain.top_cells(n) for n in (1, 2, 3, 4, 5, 8)] == [2, 4, 8, 8, 16, 16]
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_top_tree_and_root_match_multirank_reference(name):
+    p, theta, nThreads, z = load(name)
+    doms = make_domains(p, theta, nThreads, z)
+    for r, d in enumerate(doms):  # same local trees as the reference ranks
+        assert d.host.tree.nNodes == int(z[f"r{r}_nNodes"]) and d.host.tree.iRoot == int(z[f"r{r}_iRoot"])
+        assert np.array_equal(d.host.iOrderMap, np.arange(d.host.nLocal))
+        bk = z[f"r{r}_buckets"]
+        assert np.array_equal(d.host.tree.pLower[bk[:, 0]], bk[:, 1]) and np.array_equal(d.host.tree.pUpper[bk[:, 0]], bk[:, 2])
+    domain.run_in_process(doms, exchange_trees=False)
+    top_i, top_d = z["top_i"], z["top_d"]
+    for d in doms:
+        k = d.kdTop
+        used = top_i[:, 1] != 0
+        assert np.array_equal(k["bUsed"].astype(bool), used)
+        assert np.array_equal(k["pLower"][used], top_i[used, 0])
+        assert np.array_equal(k["r"][used], top_d[used, 0:3])           # pkdCombine: bit-exact
+        assert np.array_equal(k["fMass"][used], top_d[used, 3])
+        assert np.array_equal(k["fSoft"][used], top_d[used, 4])
+        assert np.array_equal(k["fOpen2"][used], top_d[used, 5])        # pstCalcCell + pkdCalcOpen: bit-exact
+        assert np.array_equal(k["mom"][used], top_d[used, 6:37])
+        assert np.array_equal(d.ilcnRoot, z["root"])                    # pkdCalcRoot/pkdDistribRoot: bit-exact
+
+
+def test_orb_decompose_balances_and_partitions():
+    p = ics.plummer(20000, seed=4)
+    for n in (2, 3, 8):
+        parts = domain.orb_decompose(p.x, p.y, p.z, n)
+        allidx = np.concatenate(parts)
+        assert len(allidx) == p.n and len(np.unique(allidx)) == p.n
+        assert max(len(a) for a in parts) - min(len(a) for a in parts) <= n
+        # domains are boxes that do not overlap along the first split axis
+        lo, up = domain.pst_tree(n).lower.ranks, domain.pst_tree(n).upper.ranks
+        pos = np.stack([p.x, p.y, p.z], 1)
+        d = int(np.argmax(pos.max(0) - pos.min(0)))
+        assert max(pos[parts[r], d].max() for r in lo) <= min(pos[parts[r], d].min() for r in up)
+    w = np.ones(p.n); w[p.x > 0] = 3.0
+    parts = domain.orb_decompose(p.x, p.y, p.z, 2, weights=w)
+    assert abs(w[parts[0]].sum() - w[parts[1]].sum()) <= 6.0
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import numpy as np, torch, torch.distributed as dist
+from gasoline_b200 import domain
+from multirank_cases import load
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+p, theta, nThreads, z = load("multirank_periodic10_r2")
+assert world == nThreads
+io = z[f"r{{rank}}_iOrder"]
+d = domain.Domain(rank, world, p.x[io], p.y[io], p.z[io], p.m[io], p.h[io], p.period, theta)
+ex = domain.DistributedExchange(d, "cpu")
+nbytes = ex.exchange(attach=False)
+used = z["top_i"][:, 1] != 0
+assert np.array_equal(d.kdTop["mom"][used], z["top_d"][used, 6:37])
+assert np.array_equal(d.kdTop["fOpen2"][used], z["top_d"][used, 5])
+assert np.array_equal(d.ilcnRoot, z["root"])
+# the bulk exchange delivered the other rank's tree + particles intact
+gd, gi, sizes = ex.gathered
+o = 1 - rank
+io_o = z[f"r{{o}}_iOrder"]
+nn, n = int(gi[o][0]), int(gi[o][2])
+assert nn == int(z[f"r{{o}}_nNodes"]) and n == len(io_o)
+x_o = gd[o].numpy()[(3 + 3 + 31) * nn:(3 + 3 + 31) * nn + n]  # after r[3nn] fMass fSoft fOpen2 mom[31nn]
+assert np.array_equal(x_o, p.x[io_o])
+assert nbytes == int(sizes[o, 0]) * 8 + int(sizes[o, 1]) * 4
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_distributed_top_tree_gloo_world2(tmp_path):
+    """Two real processes, gloo backend: every rank assembles the reference's kdTop / ilcnRoot and receives the
+    other domain's tree through the collective path bench.py uses on NCCL."""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29531", str(script)],
+                       capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
