@@ -91,7 +91,7 @@ x_o = gd[o].numpy()[(3 + 3 + 31) * nn:(3 + 3 + 31) * nn + n]  # after r[3nn] fMa
 assert np.array_equal(x_o, p.x[io_o])
 assert nbytes == int(sizes[o, 0]) * 8 + int(sizes[o, 1]) * 4
 dist.destroy_process_group()
-print("rank", rank, "ok")
+open(os.path.join(os.environ["GG_TEST_OUT"], f"rank{{rank}}.ok"), "w").write("ok")
 """
 
 
@@ -102,6 +102,7 @@ def test_distributed_top_tree_gloo_world2(tmp_path):
     script.write_text(_WORKER.format(root=ROOT))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                         "--master-addr", "127.0.0.1", "--master-port", "29531", str(script)],
-                       capture_output=True, text=True, timeout=300, cwd=ROOT)
+                       capture_output=True, text=True, timeout=300, cwd=ROOT,
+                       env=dict(os.environ, GG_TEST_OUT=str(tmp_path)))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
+    assert (tmp_path / "rank0.ok").exists() and (tmp_path / "rank1.ok").exists()
