@@ -60,7 +60,7 @@ struct gg_context {
     std::vector<int> hActive; // host copy of the local ACTIVE flags (empty = all active)
     // device buffers
     DevBuf nodes, momf, momq, parts, active, hsoft, tasks, ngroups, goffs, counts, acc, pot, dtg, fweight, nloop, sums,
-        misc, imgoff, ewt, raw, rawi, cubtmp, flush, pool, nextblk, lhead, lcnt;
+        misc, imgoff, ewt, raw, rawi, cubtmp, flush, pool, nextblk, poolmask, isb, boffs, bnode, ghead, gcnt;
     void *pinned = nullptr;
     size_t pinnedCap = 0;
     int nTasks = 0;
@@ -144,7 +144,7 @@ __global__ void k_pack_parts(int n, const double *x, const double *y, const doub
 }
 
 // number of 8-sink passes each local bucket needs (0 for cells and for buckets without an active sink)
-__global__ void k_count_groups(int nNodes, const NodeW *nodes, const int *active, int *ngroups) {
+__global__ void k_count_groups(int nNodes, const NodeW *nodes, const int *active, int *ngroups, int *isBucket) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nNodes) return;
     NodeW w = nodes[i];
@@ -157,12 +157,15 @@ __global__ void k_count_groups(int nNodes, const NodeW *nodes, const int *active
         g = (n + GG_MAX_SINKS - 1) / GG_MAX_SINKS;
     }
     ngroups[i] = g;
+    isBucket[i] = g > 0;
 }
 
-__global__ void k_fill_tasks(int nNodes, const int *ngroups, const int *offs, Task *tasks) {
+__global__ void k_fill_tasks(int nNodes, const int *ngroups, const int *offs, const int *ords, Task *tasks,
+                             int *bucketNode) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nNodes) return;
-    for (int g = 0; g < ngroups[i]; ++g) tasks[offs[i] + g] = Task{i, g};
+    for (int g = 0; g < ngroups[i]; ++g) tasks[offs[i] + g] = Task{i, g, ords[i], 0};
+    if (ngroups[i] > 0) bucketNode[ords[i]] = i;
 }
 
 __global__ void k_max_bucket(int n, const int *pLower, const int *pUpper, const int *iLower, int *out) {
@@ -294,7 +297,7 @@ void gg_destroy(gg_context *c) {
     DevBuf *all[] = {&c->nodes, &c->momf, &c->momq, &c->parts, &c->active, &c->hsoft, &c->tasks, &c->ngroups,
                      &c->goffs, &c->counts, &c->acc, &c->pot, &c->dtg, &c->fweight, &c->nloop, &c->sums, &c->misc,
                      &c->imgoff, &c->ewt, &c->raw, &c->rawi, &c->cubtmp, &c->flush, &c->pool,
-                     &c->nextblk, &c->lhead, &c->lcnt};
+                     &c->nextblk, &c->poolmask, &c->isb, &c->boffs, &c->bnode, &c->ghead, &c->gcnt};
     for (DevBuf *b : all)
         if (b->p) cudaFree(b->p);
     if (c->pinned) cudaFreeHost(c->pinned);
@@ -536,6 +539,9 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
     if ((rc = ensure(c, c->misc, 16 * sizeof(int)))) return rc;
     if ((rc = ensure(c, c->ngroups, (size_t)(nn + 1) * sizeof(int)))) return rc;
     if ((rc = ensure(c, c->goffs, (size_t)(nn + 1) * sizeof(int)))) return rc;
+    if ((rc = ensure(c, c->isb, (size_t)(nn + 1) * sizeof(int)))) return rc;
+    if ((rc = ensure(c, c->boffs, (size_t)(nn + 1) * sizeof(int)))) return rc;
+    if ((rc = ensure(c, c->bnode, (size_t)(nn + 1) * sizeof(int)))) return rc;
 
     CK(cudaEventRecord(c->ev[0], c->st));
     CK(cudaMemsetAsync(c->counts.p, 0xff, (size_t)nn * 3 * sizeof(int), c->st));
@@ -546,36 +552,42 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
     CK(cudaMemsetAsync(c->sums.p, 0, 16 * sizeof(unsigned long long), c->st));
     CK(cudaMemsetAsync(c->misc.p, 0, 16 * sizeof(int), c->st));
 
-    // ---- task list: local buckets with an active sink, in tree order
-    int nTasks = 0;
+    // ---- task list: local buckets with an active sink, in tree order (+ their ordinals: walk groups)
+    int nTasks = 0, nBuckets = 0;
     if (singleTask) {
         if ((rc = ensure(c, c->tasks, sizeof(Task)))) return rc;
         CK(cudaMemcpyAsync(c->tasks.p, singleTask, sizeof(Task), cudaMemcpyHostToDevice, c->st));
-        nTasks = 1;
+        CK(cudaMemcpyAsync(c->bnode.p, &singleTask->node, sizeof(int), cudaMemcpyHostToDevice, c->st));
+        nTasks = nBuckets = 1;
     } else {
-        k_count_groups<<<(nn + 255) / 256, 256, 0, c->st>>>(nn, (const NodeW *)c->nodes.p, dActive, (int *)c->ngroups.p);
+        k_count_groups<<<(nn + 255) / 256, 256, 0, c->st>>>(nn, (const NodeW *)c->nodes.p, dActive, (int *)c->ngroups.p,
+                                                            (int *)c->isb.p);
         CK(cudaGetLastError());
         size_t tmpBytes = 0;
         CK(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, (int *)c->ngroups.p, (int *)c->goffs.p, nn + 1, c->st));
         if ((rc = ensure(c, c->cubtmp, tmpBytes))) return rc;
         CK(cudaMemsetAsync((int *)c->ngroups.p + nn, 0, sizeof(int), c->st));
+        CK(cudaMemsetAsync((int *)c->isb.p + nn, 0, sizeof(int), c->st));
         CK(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmpBytes, (int *)c->ngroups.p, (int *)c->goffs.p, nn + 1, c->st));
+        CK(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmpBytes, (int *)c->isb.p, (int *)c->boffs.p, nn + 1, c->st));
         CK(cudaMemcpyAsync(&nTasks, (int *)c->goffs.p + nn, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+        CK(cudaMemcpyAsync(&nBuckets, (int *)c->boffs.p + nn, sizeof(int), cudaMemcpyDeviceToHost, c->st));
         CK(cudaStreamSynchronize(c->st));
         if ((rc = ensure(c, c->tasks, (size_t)(nTasks + 1) * sizeof(Task)))) return rc;
         k_fill_tasks<<<(nn + 255) / 256, 256, 0, c->st>>>(nn, (const int *)c->ngroups.p, (const int *)c->goffs.p,
-                                                          (Task *)c->tasks.p);
+                                                          (const int *)c->boffs.p, (Task *)c->tasks.p, (int *)c->bnode.p);
         CK(cudaGetLastError());
-        c->nLaunches += 3;
+        c->nLaunches += 5;
     }
+    const int nWalkGroups = (nBuckets + GG_WALK_GB - 1) / GG_WALK_GB;
+    if ((rc = ensure(c, c->ghead, (size_t)(nWalkGroups + 1) * 6 * sizeof(int)))) return rc;
+    if ((rc = ensure(c, c->gcnt, (size_t)(nWalkGroups + 1) * 6 * sizeof(int)))) return rc;
     c->nTasks = nTasks;
 
     // ---- walk (lists -> HBM pool) + list evaluation
     const bool walkOnly = (prm->flags & GG_FLAG_WALK_ONLY) != 0;
-    if ((rc = ensure(c, c->lhead, (size_t)nn * 3 * sizeof(int)))) return rc;
-    if ((rc = ensure(c, c->lcnt, (size_t)nn * 3 * sizeof(int)))) return rc;
     if (!walkOnly && c->capBlocks == 0) { // first guess: ~700 list entries per bucket, plus one slab per resident warp
-        c->capBlocks = (size_t)nTasks * 24 + (size_t)c->nSM * 64 * GG_SLAB_BLOCKS + 1024;
+        c->capBlocks = (size_t)nBuckets * 16 + (size_t)c->nSM * 64 * GG_SLAB_BLOCKS + 1024;
     }
     TreeKernelArgs ta;
     memset(&ta, 0, sizeof(ta));
@@ -587,6 +599,10 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
     ta.hsoft = (const double *)c->hsoft.p;
     ta.tasks = (const Task *)c->tasks.p;
     ta.nTasks = nTasks;
+    ta.bucketNode = (const int *)c->bnode.p;
+    ta.nBuckets = nBuckets;
+    ta.groupHead = (int *)c->ghead.p;
+    ta.groupCnt = (int *)c->gcnt.p;
     ta.taskCounter = (int *)c->misc.p;
     ta.errFlag = (int *)c->misc.p + 1;
     ta.poolCursor = (int *)c->misc.p + 3;
@@ -602,8 +618,6 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
     ta.pot = (double *)c->pot.p;
     ta.dtg = (double *)c->dtg.p;
     ta.counts = (int *)c->counts.p;
-    ta.listHead = (int *)c->lhead.p;
-    ta.listCnt = (int *)c->lcnt.p;
     CK(cudaEventRecord(c->ev[1], c->st));
     if (nTasks > 0) {
         if (!walkOnly) {
@@ -611,9 +625,11 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
                 return fail(GG_ERR_NOMEM, "gg_gravity: interaction lists need %zu blocks (> 2^31 references)", c->capBlocks);
             if ((rc = ensure(c, c->pool, c->capBlocks * 32 * sizeof(unsigned)))) return rc;
             if ((rc = ensure(c, c->nextblk, c->capBlocks * sizeof(int)))) return rc;
+            if ((rc = ensure(c, c->poolmask, c->capBlocks * 32))) return rc;
         }
         ta.pool = (unsigned *)c->pool.p;
         ta.nextBlk = (int *)c->nextblk.p;
+        ta.poolMask = (unsigned char *)c->poolmask.p;
         ta.capBlocks = (int)c->capBlocks;
         CK(gg_launch_walk_kernel(ta, c->nSM, c->st));
         ++c->nLaunches;
@@ -782,7 +798,7 @@ int gg_bucket_walk(gg_context *c, const gg_params *prm, int iBucket, int n3[3]) 
     if (iBucket < 0 || iBucket >= c->dom[0].nNodes) return fail(GG_ERR_ARG, "gg_bucket_walk: iBucket=%d", iBucket);
     gg_params p = *prm;
     p.flags |= GG_FLAG_WALK_ONLY;
-    Task t{iBucket, 0};
+    Task t{iBucket, 0, 0, 0};
     int rc = run_gravity(c, &p, &t, nullptr);
     if (rc) return rc;
     CK(cudaMemcpyAsync(n3, (int *)c->counts.p + 3 * (size_t)iBucket, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->st));

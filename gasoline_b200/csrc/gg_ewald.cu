@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(256) k_stats(const StatsKernelArgs A) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     // v[0..5]: sums (nActive, part, cell, soft, flopI, flopE); v[6..8]: maxima of the per-bucket list lengths
     unsigned long long v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    if (t < A.nTasks && A.tasks[t].group == 0) {
+    if (t < A.nTasks && A.tasks[t].pass == 0) {
         const Task task = A.tasks[t];
         const NodeW bk = A.nodes[task.node];
         const int qflop[5] = {10, 10, 41, 120, 277}, mflop[5] = {10, 10, 48, 151, 343};

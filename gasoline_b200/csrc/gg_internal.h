@@ -22,8 +22,11 @@
 #define GG_CELL_UNROLL 1     // unroll factor of k_eval's (sink, cell) loop
 #endif
 #define GG_WALK_WARPS 8      // k_walk
-#define GG_WALK_MIN_CTAS 5   // 40 warps per SM (register cap 51)
+#define GG_WALK_MIN_CTAS 4   // 32 warps per SM (register cap 64)
 #define GG_SLAB_BLOCKS 32    // list blocks a warp takes from the pool per atomic
+#ifndef GG_WALK_GB
+#define GG_WALK_GB 6         // sink buckets that share one tree traversal in k_walk (<= 8: one mask byte per frontier item)
+#endif
 #define GG_MAX_SINKS 8      // sinks evaluated per warp pass (accumulators live in registers)
 #define GG_STACK_CAP 512    // walk frontier entries per warp
 #define GG_STACK_DFS_MARGIN 128
@@ -46,10 +49,13 @@ struct __align__(16) PartS {
 };
 static_assert(sizeof(PartS) == 32, "PartS must be 32 bytes");
 
-// One unit of work for a warp: a sink bucket (local node index) and which group of 8 active sinks to evaluate.
+// One unit of work for a k_eval warp: a sink bucket (local node index), which pass of 8 active sinks to evaluate, and
+// the bucket's ordinal among the sink buckets (tree order); ordinal / GG_WALK_GB is its walk group.
 struct Task {
     int node;
-    int group;
+    int pass;
+    int ord;
+    int pad;
 };
 
 struct TreeKernelArgs {
@@ -62,13 +68,16 @@ struct TreeKernelArgs {
     const Task *tasks;
     int nTasks;
     int *taskCounter;        // [0] k_walk's, [2] k_eval's ([1] is errFlag)
-    // interaction lists: 128 B blocks of 32 references chained per bucket (see gg_tree_kernel.cu)
+    const int *bucketNode;   // [nBuckets] sink buckets (local node index) in tree order
+    int nBuckets;
+    // interaction lists: 128 B blocks of 32 references chained per bucket / per walk group (see gg_tree_kernel.cu)
     unsigned *pool;          // [capBlocks][32]
     int *nextBlk;            // [capBlocks]
     int capBlocks;
     int *poolCursor;         // blocks handed out (may exceed capBlocks: the host then grows the pool and reruns)
-    int *listHead;           // [nLocalNodes][3] first block of the particle / softened-cell / Newtonian-cell chain
-    int *listCnt;            // [nLocalNodes][3] entries in each chain
+    unsigned char *poolMask; // [capBlocks][32] masked chains: which buckets of the walk group the entry belongs to
+    int *groupHead;          // [nWalkGroups][3 list types][2]: chain shared by every bucket of the group, masked chain
+    int *groupCnt;           // [nWalkGroups][3][2] entries in each chain
     int rootNode;            // global index where every image's walk starts
     int nImages, homeImage, imgBits;
     const double *imgOff;    // [nImages][3]

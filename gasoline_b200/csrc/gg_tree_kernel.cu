@@ -278,34 +278,106 @@ __device__ __forceinline__ void sink_box(const TreeKernelArgs &A, const NodeW &b
 #define NSTRIDE 5 // uint4 per staged node record: 64 B + 16 B pad -> LDS.128 of 8 consecutive lanes is conflict-free
 struct WalkSmem {
     uint4 nstage[32 * NSTRIDE]; // the 32 node records of the current step, fetched cooperatively (4 lanes per record)
-    unsigned stack[GG_STACK_CAP];
-    unsigned cbuf[64];
-    unsigned sbuf[64];
-    unsigned pbuf[32]; // really 32*maxBucket + 32
+    unsigned stack[GG_STACK_CAP];     // frontier: (cell << imgBits) | image
+    unsigned char smask[GG_STACK_CAP]; // ... and the buckets of the group for which that cell is still undecided
+    double box[GG_WALK_GB][6];  // sink boxes (active particles) of the group's buckets
+    double fSoftMax[GG_WALK_GB];
+    int head[3][2], fill[3][2], cnt[3][2]; // chain state per list type (0 leaves, 1 soft, 2 Newtonian) x (shared, masked)
+    int own[GG_WALK_GB];        // particles of the bucket itself met in the home image (walk.c:93)
+    int bnode[GG_WALK_GB];
 };
 
-__host__ __device__ inline size_t walk_smem_bytes(int maxBucket) {
-    size_t b = sizeof(WalkSmem) + (size_t)32 * maxBucket * sizeof(unsigned);
-    return (b + 15) & ~(size_t)15;
+__host__ __device__ inline size_t walk_smem_bytes() { return (sizeof(WalkSmem) + 15) & ~(size_t)15; }
+
+// squared distance from a point to the FARTHEST corner of a box: an upper bound, term by term and rounding by
+// rounding, of INTERSECTNP's squared distance to any box inside it
+__device__ __forceinline__ double far_dist2(const double *box, double x, double y, double z) {
+    const double dx = fmax(x - box[0], box[3] - x), dy = fmax(y - box[1], box[4] - y), dz = fmax(z - box[2], box[5] - z);
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+__device__ __forceinline__ double near_dist2(const double *box, double x, double y, double z) {
+    const double dx = pos_part(box[0] - x, x - box[3]);
+    const double dy = pos_part(box[1] - y, y - box[4]);
+    const double dz = pos_part(box[2] - z, z - box[5]);
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
 }
 
-// Append one block (<= 32 references) to a chain.  Blocks come from the warp's slab; a new slab costs one atomic.
-__device__ __forceinline__ void emit_block(const TreeKernelArgs &A, const unsigned *src, int cnt, int lane,
-                                           int &slabBase, int &slabUsed, int &head) {
-    if (slabUsed == GG_SLAB_BLOCKS) {
-        int b = 0;
-        if (lane == 0) b = atomicAdd(A.poolCursor, GG_SLAB_BLOCKS);
-        slabBase = __shfl_sync(FULL, b, 0);
-        slabUsed = 0;
+struct Slab {
+    int base, used;
+};
+
+// Append <= 32 entries (one per lane with `has`) to chain (type, d); d = 1 also records the entry's bucket mask.
+// The head block of a chain is the one being filled; older blocks are full.  Blocks come from the warp's slab; a
+// new slab costs one atomic.  Warp-collective.
+__device__ __forceinline__ void append(const TreeKernelArgs &A, WalkSmem &W, int type, int d, bool has, unsigned entry,
+                                       unsigned mask, int lane, unsigned lt, Slab &slab) {
+    const unsigned m = __ballot_sync(FULL, has);
+    if (!m) return;
+    const int n = __popc(m), pos = __popc(m & lt);
+    const int head = W.head[type][d], fill = W.fill[type][d];
+    const int room = head >= 0 ? 32 - fill : 0;
+    int nb = head;
+    if (n > room) {
+        if (slab.used == GG_SLAB_BLOCKS) {
+            int b = 0;
+            if (lane == 0) b = atomicAdd(A.poolCursor, GG_SLAB_BLOCKS);
+            slab.base = __shfl_sync(FULL, b, 0);
+            slab.used = 0;
+        }
+        nb = slab.base + slab.used++;
     }
-    const int blk = slabBase + slabUsed++;
-    if (blk < A.capBlocks) { // beyond the pool: the host sees cursor > capBlocks, grows the pool and reruns
-        if (lane < cnt) A.pool[(size_t)blk * 32 + lane] = src[lane];
-        if (lane == 0) A.nextBlk[blk] = head;
-        head = blk;
+    __syncwarp();
+    const bool fits = nb < A.capBlocks; // beyond the pool: the host sees cursor > capBlocks, grows the pool and reruns
+    if (has && !A.walkOnly) {
+        size_t at = (size_t)head * 32 + fill + pos;
+        if (pos >= room) at = (size_t)nb * 32 + (pos - room);
+        if (pos < room || fits) {
+            A.pool[at] = entry;
+            if (d) A.poolMask[at] = (unsigned char)mask;
+        }
+    }
+    if (lane == 0) {
+        if (n > room) {
+            if (fits && !A.walkOnly) A.nextBlk[nb] = head;
+            W.head[type][d] = fits ? nb : head;
+            W.fill[type][d] = fits ? n - room : fill;
+        } else W.fill[type][d] = fill + n;
+        W.cnt[type][d] += n;
+    }
+    __syncwarp();
+}
+
+// One list type of one step: lanes with dm == all go to the group's shared chain, the others to its masked chain.
+// myCnt (lane b counts for bucket b of the group) gets the per-bucket number of masked entries -- of particles for
+// leaves (np > 0).
+__device__ __forceinline__ void distribute(const TreeKernelArgs &A, WalkSmem &W, int type, unsigned dm, unsigned all,
+                                           int nB, unsigned entry, int np, int lane, unsigned lt, Slab &slab,
+                                           int &myCnt, int &sharedP) {
+    const unsigned mAny = __ballot_sync(FULL, dm != 0);
+    if (!mAny) return;
+    const bool shared = dm == all;
+    const unsigned mSh = __ballot_sync(FULL, shared);
+    if (mSh) {
+        if (type == 0) sharedP += __reduce_add_sync(FULL, shared ? np : 0);
+        append(A, W, type, 0, shared, entry, 0u, lane, lt, slab);
+    }
+    if (mAny != mSh) {
+        const unsigned pm = shared ? 0u : dm;
+        for (int b = 0; b < nB; ++b) {
+            const bool has = (pm >> b) & 1u;
+            const unsigned mb = __ballot_sync(FULL, has);
+            if (!mb) continue;
+            const int c = type == 0 ? __reduce_add_sync(FULL, has ? np : 0) : __popc(mb);
+            if (lane == b) myCnt += c;
+        }
+        append(A, W, type, 1, pm != 0, entry, pm, lane, lt, slab);
     }
 }
 
+// One warp walks the tree ONCE for a group of up to GG_WALK_GB consecutive sink buckets.  Every frontier item
+// carries the set of buckets that have opened all of its ancestors; the reference's per-bucket opening test
+// (walk.c:81-127) is evaluated for exactly those buckets, short-cut by two conservative tests against the box of
+// the whole group that are monotone in floating point (so they can never disagree with the per-bucket result).
 __global__ void __launch_bounds__(GG_WALK_WARPS * 32, GG_WALK_MIN_CTAS) k_walk(const TreeKernelArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double s_off[GG_MAX_IMAGES * 3];
@@ -313,37 +385,58 @@ __global__ void __launch_bounds__(GG_WALK_WARPS * 32, GG_WALK_MIN_CTAS) k_walk(c
     const unsigned lt = (1u << lane) - 1u;
     for (int i = threadIdx.x; i < A.nImages * 3; i += blockDim.x) s_off[i] = A.imgOff[i];
     __syncthreads();
-    WalkSmem &W = *reinterpret_cast<WalkSmem *>(smem_raw + warp * walk_smem_bytes(A.maxBucket));
+    WalkSmem &W = *reinterpret_cast<WalkSmem *>(smem_raw + warp * walk_smem_bytes());
     const unsigned imgMask = (1u << A.imgBits) - 1u;
-    int slabBase = 0, slabUsed = GG_SLAB_BLOCKS;
+    Slab slab{0, GG_SLAB_BLOCKS};
+    const int nGroups = (A.nBuckets + GG_WALK_GB - 1) / GG_WALK_GB;
 
     for (;;) {
-        int t = 0;
-        if (lane == 0) t = atomicAdd(A.taskCounter, 1);
-        t = __shfl_sync(FULL, t, 0);
-        if (t >= A.nTasks) break;
-        const Task task = A.tasks[t];
-        if (task.group != 0) continue; // one walk per bucket; the other sink groups reuse its lists
-        const NodeW bk = load_node(&A.nodes[task.node]);
-        double box[6], fSoftMax;
-        int nAct;
-        sink_box(A, bk, lane, box, fSoftMax, nAct);
-
-        int nStack = A.nImages, nCell = 0, nPart = 0, nSoft = 0;
-        int cntP = 0, cntS = 0, cntN = 0, own = 0;
-        int headC = -1, headS = -1, headP = -1;
-        for (int i = lane; i < A.nImages; i += 32) W.stack[i] = ((unsigned)A.rootNode << A.imgBits) | (unsigned)i;
+        int g = 0;
+        if (lane == 0) g = atomicAdd(A.taskCounter, 1);
+        g = __shfl_sync(FULL, g, 0);
+        if (g >= nGroups) break;
+        const int b0 = g * GG_WALK_GB, nB = min(GG_WALK_GB, A.nBuckets - b0);
+        const unsigned all = (1u << nB) - 1u;
+        // ---- the group's sink boxes
+        double gbox[6] = {1.7976931348623157e308, 1.7976931348623157e308, 1.7976931348623157e308,
+                          -1.7976931348623157e308, -1.7976931348623157e308, -1.7976931348623157e308};
+        double gSoftMax = 0.0;
+        for (int b = 0; b < nB; ++b) {
+            const int node = A.bucketNode[b0 + b];
+            const NodeW bk = load_node(&A.nodes[node]);
+            double box[6], fSoftMax;
+            int nAct;
+            sink_box(A, bk, lane, box, fSoftMax, nAct);
+            {
+                const double v = lane == 0 ? box[0] : lane == 1 ? box[1] : lane == 2 ? box[2] : lane == 3 ? box[3]
+                                 : lane == 4 ? box[4] : box[5];
+                if (lane < 6) W.box[b][lane] = v;
+            }
+            if (lane == 0) { W.fSoftMax[b] = fSoftMax; W.bnode[b] = node; W.own[b] = 0; }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { gbox[k] = fmin(gbox[k], box[k]); gbox[3 + k] = fmax(gbox[3 + k], box[3 + k]); }
+            gSoftMax = fmax(gSoftMax, fSoftMax);
+        }
+        if (lane < 6) {
+            (&W.head[0][0])[lane] = -1; (&W.fill[0][0])[lane] = 0; (&W.cnt[0][0])[lane] = 0;
+        }
+        int myP = 0, myS = 0, myN = 0, sharedP = 0, unused = 0; // lane b: masked entries of bucket b
+        int nStack = A.nImages;
+        for (int i = lane; i < A.nImages; i += 32) {
+            W.stack[i] = ((unsigned)A.rootNode << A.imgBits) | (unsigned)i;
+            W.smask[i] = (unsigned char)all;
+        }
         __syncwarp();
 
         while (nStack > 0) {
             int k = min(32, nStack);
             if (nStack > GG_STACK_CAP - GG_STACK_DFS_MARGIN) k = 1; // near the cap: depth-first, growth <= 1 per step
-            unsigned item = 0xffffffffu;
-            if (lane < k) item = W.stack[nStack - 1 - lane];
+            unsigned item = 0xffffffffu, mask = 0;
+            if (lane < k) { item = W.stack[nStack - 1 - lane]; mask = W.smask[nStack - 1 - lane]; }
             nStack -= k;
             __syncwarp();
             // fetch the k node records COALESCED: 4 lanes per 64 B record, so a warp-wide 16 B access touches 8 cache
-            // lines instead of 32 (the walk is bound by L1 tag lookups otherwise); cp.async lands them in shared memory
+            // lines instead of 32; cp.async lands them in shared memory
             const int node = item != 0xffffffffu ? (int)(item >> A.imgBits) : -1;
             {
                 const int piece = lane & 3, sub = lane >> 2;
@@ -357,97 +450,236 @@ __global__ void __launch_bounds__(GG_WALK_WARPS * 32, GG_WALK_MIN_CTAS) k_walk(c
                 cp_async_wait_all();
             }
             __syncwarp();
-            // classify: 1 push children, 2 Newtonian cell, 3 source bucket, 4 own bucket, 5 softened cell
-            int action = 0, img = 0, np = 0, c0 = -1, c1 = -1, pLower = 0;
+            // ---- decide, per bucket of the item's mask: open / Newtonian cell / softened cell
+            unsigned mOpen = 0, mSoft = 0, mNewt = 0;
+            int img = 0, np = 0, c0 = -1, c1 = -1;
             if (node >= 0) {
                 img = (int)(item & imgMask);
                 const NodeW nd = load_node_smem(&W.nstage[lane * NSTRIDE]);
                 const double x = nd.rx + s_off[3 * img], y = nd.ry + s_off[3 * img + 1], z = nd.rz + s_off[3 * img + 2];
-                bool open = intersect_np(box, nd.fOpen2, x, y, z);
-                if (nd.nP < 4) open = true; // walk.c:81 (pUpper - pLower < 3)
-                if (open) {
-                    if (nd.c0 >= 0) action = 1;
-                    else action = (node == task.node && img == A.homeImage) ? 4 : 3; // walk.c:93
-                } else {
-                    double twoh2 = nd.fSoft + fSoftMax;
-                    twoh2 = __dmul_rn(twoh2, twoh2);
-                    bool soft = false;
-                    if (!(twoh2 < nd.fOpen2)) soft = intersect_np(box, twoh2, x, y, z); // walk.c:122-127
-                    action = soft ? 5 : 2;
+                if (nd.nP < 4) mOpen = mask; // walk.c:81 (pUpper - pLower < 3)
+                else if (near_dist2(gbox, x, y, z) <= nd.fOpen2) { // else: no bucket inside the group box opens it
+                    if (far_dist2(gbox, x, y, z) <= nd.fOpen2) mOpen = mask; // every bucket inside the group box does
+                    else
+                        for (unsigned mm = mask; mm; mm &= mm - 1) {
+                            const int b = __ffs(mm) - 1;
+                            if (intersect_np(W.box[b], nd.fOpen2, x, y, z)) mOpen |= 1u << b;
+                        }
                 }
-                c0 = nd.c0; c1 = nd.c1; pLower = nd.pLower;
-                if (action == 3 || action == 4) np = nd.nP;
+                const unsigned mAcc = mask & ~mOpen;
+                if (mAcc) { // walk.c:118-127
+                    double t2 = nd.fSoft + gSoftMax;
+                    t2 = __dmul_rn(t2, t2);
+                    if (!(t2 < nd.fOpen2)) // (fSoft + fSoftMax_b)^2 <= t2 for every bucket: only then can one be soft
+                        for (unsigned mm = mAcc; mm; mm &= mm - 1) {
+                            const int b = __ffs(mm) - 1;
+                            double twoh2 = nd.fSoft + W.fSoftMax[b];
+                            twoh2 = __dmul_rn(twoh2, twoh2);
+                            if (!(twoh2 < nd.fOpen2) && intersect_np(W.box[b], twoh2, x, y, z)) mSoft |= 1u << b;
+                        }
+                    mNewt = mAcc & ~mSoft;
+                }
+                c0 = nd.c0; c1 = nd.c1;
+                if (mOpen && c0 < 0) { // an opened bucket: all its particles are sources (walk.c:93-114)
+                    np = nd.nP;
+                    if (img == A.homeImage)
+                        for (unsigned mm = mOpen; mm; mm &= mm - 1) {
+                            const int b = __ffs(mm) - 1;
+                            if (W.bnode[b] == node) W.own[b] = np;
+                        }
+                }
             }
             // children (a single-child cell, pkdThreadTree pkd.c:2597-2609, pushes a no-op as second item)
-            const unsigned mPush = __ballot_sync(FULL, action == 1);
-            if (action == 1) {
+            const bool push = mOpen && c0 >= 0;
+            const unsigned mPush = __ballot_sync(FULL, push);
+            if (push) {
                 const int pos = nStack + 2 * __popc(mPush & lt);
                 if (pos + 1 < GG_STACK_CAP) {
                     W.stack[pos] = c1 >= 0 ? (((unsigned)c1 << A.imgBits) | (unsigned)img) : 0xffffffffu;
                     W.stack[pos + 1] = ((unsigned)c0 << A.imgBits) | (unsigned)img;
+                    W.smask[pos] = (unsigned char)mOpen;
+                    W.smask[pos + 1] = (unsigned char)mOpen;
                 } else atomicExch(A.errFlag, 1);
             }
             nStack += 2 * __popc(mPush);
-            // Newtonian cells
-            const unsigned mCell = __ballot_sync(FULL, action == 2);
-            if (action == 2) W.cbuf[nCell + __popc(mCell & lt)] = item;
-            nCell += __popc(mCell);
-            cntN += __popc(mCell);
-            // softened cells
-            const unsigned mSoft = __ballot_sync(FULL, action == 5);
-            if (mSoft) {
-                if (action == 5) W.sbuf[nSoft + __popc(mSoft & lt)] = item;
-                nSoft += __popc(mSoft);
-                cntS += __popc(mSoft);
-            }
-            // source particles
-            const unsigned mBk = __ballot_sync(FULL, np > 0);
-            if (mBk) {
-                int incl = np;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int v = __shfl_up_sync(FULL, incl, o);
-                    if (lane >= o) incl += v;
-                }
-                const int total = __shfl_sync(FULL, incl, 31);
-                const int wpos = nPart + incl - np;
-                for (int j = 0; j < np; ++j) W.pbuf[wpos + j] = ((unsigned)(pLower + j) << A.imgBits) | (unsigned)img;
-                const unsigned mOwn = __ballot_sync(FULL, action == 4);
-                if (mOwn) own = __shfl_sync(FULL, np, __ffs(mOwn) - 1);
-                nPart += total;
-                cntP += total;
-            }
-            __syncwarp();
-            if (!A.walkOnly) {
-                while (nCell >= 32) { nCell -= 32; emit_block(A, &W.cbuf[nCell], 32, lane, slabBase, slabUsed, headC); }
-                while (nSoft >= 32) { nSoft -= 32; emit_block(A, &W.sbuf[nSoft], 32, lane, slabBase, slabUsed, headS); }
-                while (nPart >= 32) { nPart -= 32; emit_block(A, &W.pbuf[nPart], 32, lane, slabBase, slabUsed, headP); }
-            } else {
-                nCell = nSoft = nPart = 0;
-            }
+            distribute(A, W, 2, mNewt, all, nB, item, 0, lane, lt, slab, myN, unused);
+            distribute(A, W, 1, mSoft, all, nB, item, 0, lane, lt, slab, myS, unused);
+            distribute(A, W, 0, np > 0 ? mOpen : 0u, all, nB, item, np, lane, lt, slab, myP, sharedP);
             __syncwarp();
         }
-        if (!A.walkOnly) {
-            if (nCell > 0) emit_block(A, W.cbuf, nCell, lane, slabBase, slabUsed, headC);
-            if (nSoft > 0) emit_block(A, W.sbuf, nSoft, lane, slabBase, slabUsed, headS);
-            if (nPart > 0) emit_block(A, W.pbuf, nPart, lane, slabBase, slabUsed, headP);
+        // ---- hand the chains over, and what pkdBucketWalk reports per bucket (walk.c:175-177)
+        if (lane < nB) {
+            int *c = &A.counts[3 * W.bnode[lane]];
+            c[0] = sharedP + myP - W.own[lane];
+            c[1] = W.cnt[1][0] + myS;
+            c[2] = W.cnt[2][0] + myN;
         }
-        if (lane == 0) {
-            int *c = &A.counts[3 * task.node];
-            c[0] = cntP - own; c[1] = cntS; c[2] = cntN;         // what pkdBucketWalk reports (walk.c:175-177)
-            int *h = &A.listHead[3 * task.node], *n = &A.listCnt[3 * task.node];
-            h[0] = headP; h[1] = headS; h[2] = headC;
-            n[0] = cntP; n[1] = cntS; n[2] = cntN;               // chain lengths (particles include the own bucket)
+        if (lane < 6) {
+            A.groupHead[6 * g + lane] = (&W.head[0][0])[lane];
+            A.groupCnt[6 * g + lane] = (&W.cnt[0][0])[lane];
         }
         __syncwarp();
     }
 }
 
 // ------------------------------------------------------------------------------------------------ k_eval
+#define PCAP (32 * CSTRIDE / PSTRIDE) // particles staged at once (96)
 struct EvalSmem {
     float4 stage[32 * CSTRIDE]; // staged block; also the sink hand-out at task start and the final reduction scratch
+    unsigned queue[64];         // list entries of this bucket waiting to be evaluated (filtered from the group's chains)
+    int lstart[32], lpart[32];  // leaf expansion: first staging slot and first particle of each leaf of the batch
+    unsigned char owner[PCAP];  // staging slot -> leaf of the batch
+    unsigned char limg[32];
 };
 
+// Per-lane evaluation state of one k_eval task: the lane's sink, its FP32 block sums and FP64 running sums.
+struct Sink {
+    float sx, sy, sz, ms, hs;
+    int sidx;
+    float ax, ay, az, ap, dtm;
+    double dax, day, daz, dap;
+    __device__ __forceinline__ void fold() { // FP32 partial sums of one block -> FP64
+        dax += (double)ax; day += (double)ay; daz += (double)az; dap += (double)ap;
+        ax = ay = az = ap = 0.f;
+    }
+};
+
+struct EvalCtx {
+    double cenx, ceny, cenz;
+    int nS, G, q;
+    bool worker;
+    unsigned imgMask;
+};
+
+// <= 32 Newtonian cells (ILCN), one per lane (`it`, lanes < cnt): stage + QEVAL to ORDER.
+template <int ORDER>
+__device__ __forceinline__ void eval_cells(const TreeKernelArgs &A, EvalSmem &W, const double *s_off, const EvalCtx &E,
+                                           Sink &K, unsigned it, int cnt, int lane) {
+    // stage the block: positions by their own lane (32 B = one sector each); moment records COALESCED,
+    // LPR lanes per 128 B record (a warp-wide LDG.128 touches 32/LPR lines instead of 32)
+    int cn = 0;
+    if (lane < cnt) {
+        cn = (int)(it >> A.imgBits);
+        const int ci = (int)(it & E.imgMask);
+        const double2 *nq = reinterpret_cast<const double2 *>(&A.nodes[cn]);
+        const double2 p01 = __ldg(nq), p23 = __ldg(nq + 1);
+        W.stage[lane * CSTRIDE] =
+            make_float4((float)((p01.x + s_off[3 * ci]) - E.cenx), (float)((p01.y + s_off[3 * ci + 1]) - E.ceny),
+                        (float)((p23.x + s_off[3 * ci + 2]) - E.cenz), (float)p23.y);
+    }
+    if (ORDER >= 2) {
+        constexpr int LPR = ORDER == 2 ? 2 : (ORDER == 3 ? 4 : 8); // float4 pieces of the record in use
+        const int piece = lane & (LPR - 1), sub = lane / LPR;
+#pragma unroll
+        for (int i = 0; i < LPR; ++i) {
+            const int rec = i * (32 / LPR) + sub;
+            const int rn = __shfl_sync(FULL, cn, rec);
+            if (rec < cnt) W.stage[rec * CSTRIDE + 1 + piece] = __ldg(&A.momf[(size_t)rn * 8 + piece]);
+        }
+    }
+    __syncwarp();
+    if (E.worker) {
+        constexpr int kUnroll = GG_CELL_UNROLL;
+#pragma unroll kUnroll
+        for (int j = E.q; j < cnt; j += E.G) {
+            const float4 *S = &W.stage[j * CSTRIDE];
+            const float4 pc = S[0];
+            CellMom c;
+            c.m0 = S[1]; c.m1 = S[2];
+            if (ORDER >= 3) { c.m2 = S[3]; c.m3 = S[4]; }
+            if (ORDER >= 4) { c.m4 = S[5]; c.m5 = S[6]; c.m6 = S[7]; c.m7 = S[8]; }
+            float fx, fy, fz, fp, fdt;
+            cell_on_sink<ORDER>(c, pc.w, K.sx - pc.x, K.sy - pc.y, K.sz - pc.z, K.ms, fx, fy, fz, fp, fdt);
+            K.ax += fx; K.ay += fy; K.az += fz; K.ap -= fp;
+            K.dtm = fmaxf(K.dtm, fdt);
+        }
+    }
+    K.fold();
+    __syncwarp();
+}
+
+// <= 32 opened source BUCKETS (leaves), each standing for all its particles -- incl. the sink bucket itself
+// (intra-bucket pairs, grav.c:211-242).  SPLINE-softened monopoles (ILP, grav.c:89-108).
+__device__ __forceinline__ void eval_leaves(const TreeKernelArgs &A, EvalSmem &W, const double *s_off, const EvalCtx &E,
+                                            Sink &K, unsigned it, int cnt, int lane) {
+    int np = 0, pl = 0, ci = 0;
+    if (lane < cnt) {
+        ci = (int)(it & E.imgMask);
+        const int4 d = __ldg(reinterpret_cast<const int4 *>(&A.nodes[it >> A.imgBits]) + 3);
+        pl = d.z; np = d.w;
+    }
+    int incl = np;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
+    }
+    // batches of consecutive leaves that fit the staging buffer (a leaf holds <= GG_MAX_BUCKET <= PCAP particles)
+    int r0 = 0;
+    while (r0 < cnt) {
+        const int base = __shfl_sync(FULL, incl - np, r0);
+        const unsigned mIn = __ballot_sync(FULL, lane >= r0 && lane < cnt && incl - base <= PCAP);
+        const int r1 = r0 + __popc(mIn);
+        const int nStaged = __shfl_sync(FULL, incl, r1 - 1) - base;
+        if (lane >= r0 && lane < r1) {
+            const int s0 = incl - np - base;
+            W.lstart[lane] = s0; W.lpart[lane] = pl; W.limg[lane] = (unsigned char)ci;
+            for (int j = 0; j < np; ++j) W.owner[s0 + j] = (unsigned char)lane;
+        }
+        __syncwarp();
+        for (int s = lane; s < nStaged; s += 32) {
+            const int r = W.owner[s], ri = W.limg[r];
+            const int pi = W.lpart[r] + (s - W.lstart[r]);
+            const PartS p = load_part(&A.parts[pi]);
+            float4 *S = &W.stage[s * PSTRIDE];
+            S[0] = make_float4((float)((p.x + s_off[3 * ri]) - E.cenx), (float)((p.y + s_off[3 * ri + 1]) - E.ceny),
+                               (float)((p.z + s_off[3 * ri + 2]) - E.cenz), p.m);
+            // a particle does not act on itself (grav.c:211): remember who it is, in the home image only
+            S[1] = make_float4(p.h, __int_as_float(ri == A.homeImage ? pi : -1), 0.f, 0.f);
+        }
+        __syncwarp();
+        if (E.worker) {
+#pragma unroll 2
+            for (int j = E.q; j < nStaged; j += E.G) {
+                const float4 pp = W.stage[j * PSTRIDE];
+                const float2 ph = *reinterpret_cast<const float2 *>(&W.stage[j * PSTRIDE + 1]);
+                if (__float_as_int(ph.y) == K.sidx) continue;
+                float fx, fy, fz, fp, fdt;
+                part_on_sink(pp.w, ph.x, K.sx - pp.x, K.sy - pp.y, K.sz - pp.z, K.ms, K.hs, fx, fy, fz, fp, fdt);
+                K.ax += fx; K.ay += fy; K.az += fz; K.ap -= fp;
+                K.dtm = fmaxf(K.dtm, fdt);
+            }
+        }
+        K.fold();
+        __syncwarp();
+        r0 = r1;
+    }
+}
+
+// <= 32 softened cells (ILCS, rare): FP64, the first nS lanes each take their sink.  Returns the lane's sums.
+__device__ __noinline__ SoftTerm eval_soft(const NodeW *nodes, const double *momq, int imgBits, const double *s_off,
+                                           double sx, double sy, double sz, double ms, double hs, int nS, unsigned it,
+                                           int cnt, int lane) {
+    SoftTerm sum;
+    sum.ax = sum.ay = sum.az = sum.pot = sum.dt = 0.0;
+    const unsigned imgMask = (1u << imgBits) - 1u;
+    for (int j = 0; j < cnt; ++j) {
+        const unsigned e = __shfl_sync(FULL, it, j);
+        const int cn = (int)(e >> imgBits), ci = (int)(e & imgMask);
+        if (lane < nS) {
+            const NodeW nd = load_node(&nodes[cn]);
+            const double cx = nd.rx + s_off[3 * ci], cy = nd.ry + s_off[3 * ci + 1], cz = nd.rz + s_off[3 * ci + 2];
+            const SoftTerm st = softcell_on_sink(nd.fMass, nd.fSoft, &momq[(size_t)cn * 6], sx - cx, sy - cy, sz - cz, ms, hs);
+            sum.ax += st.ax; sum.ay += st.ay; sum.az += st.az; sum.pot += st.pot;
+            sum.dt = fmax(sum.dt, st.dt);
+        }
+    }
+    return sum;
+}
+
+// One warp per (bucket, pass of <= 8 active sinks).  The lists come from the bucket's walk group: for every list
+// type a chain all buckets of the group share and a chain whose entries carry a bucket mask; the warp filters its
+// own entries into a queue and evaluates them 32 at a time.
 template <int ORDER>
 __global__ void __launch_bounds__(GG_WARPS_PER_CTA * 32, GG_MIN_CTAS) k_eval(const TreeKernelArgs A) {
     __shared__ EvalSmem s_w[GG_WARPS_PER_CTA];
@@ -457,7 +689,8 @@ __global__ void __launch_bounds__(GG_WARPS_PER_CTA * 32, GG_MIN_CTAS) k_eval(con
     for (int i = threadIdx.x; i < A.nImages * 3; i += blockDim.x) s_off[i] = A.imgOff[i];
     __syncthreads();
     EvalSmem &W = s_w[warp];
-    const unsigned imgMask = (1u << A.imgBits) - 1u;
+    EvalCtx E;
+    E.imgMask = (1u << A.imgBits) - 1u;
 
     for (;;) {
         int t = 0;
@@ -469,15 +702,16 @@ __global__ void __launch_bounds__(GG_WARPS_PER_CTA * 32, GG_MIN_CTAS) k_eval(con
         double box[6], fSoftMax;
         int nAct;
         sink_box(A, bk, lane, box, fSoftMax, nAct);
-        const double cenx = 0.5 * (box[0] + box[3]), ceny = 0.5 * (box[1] + box[4]), cenz = 0.5 * (box[2] + box[5]);
+        E.cenx = 0.5 * (box[0] + box[3]); E.ceny = 0.5 * (box[1] + box[4]); E.cenz = 0.5 * (box[2] + box[5]);
 
-        // ---- hand the sinks of this pass (active ranks [8*group, 8*group+8)) to their lanes: lane = q*nS + s owns
+        // ---- hand the sinks of this pass (active ranks [8*pass, 8*pass+8)) to their lanes: lane = q*nS + s owns
         //      sink s; the G = 32/nS sub-groups q split every staged block between them
-        const int rank0 = task.group * GG_MAX_SINKS;
-        const int nS = min(GG_MAX_SINKS, nAct - rank0);
-        const int G = 32 / nS;
-        const int q = lane / nS, sI = lane - q * nS;
-        const bool worker = q < G;
+        const int rank0 = task.pass * GG_MAX_SINKS;
+        E.nS = min(GG_MAX_SINKS, nAct - rank0);
+        E.G = 32 / E.nS;
+        E.q = lane / E.nS;
+        const int sI = lane - E.q * E.nS;
+        E.worker = E.q < E.G;
         __syncwarp();
         {
             int seen = 0;
@@ -489,131 +723,74 @@ __global__ void __launch_bounds__(GG_WARPS_PER_CTA * 32, GG_MIN_CTAS) k_eval(con
                 const int rank = seen + __popc(m & lt) - rank0;
                 if (act && rank >= 0 && rank < GG_MAX_SINKS) {
                     const PartS p = load_part(&A.parts[pi]);
-                    W.stage[rank] = make_float4((float)(p.x - cenx), (float)(p.y - ceny), (float)(p.z - cenz), p.m);
+                    W.stage[rank] = make_float4((float)(p.x - E.cenx), (float)(p.y - E.ceny), (float)(p.z - E.cenz), p.m);
                     W.stage[GG_MAX_SINKS + rank] = make_float4(p.h, __int_as_float(pi), 0.f, 0.f);
                 }
                 seen += __popc(m);
             }
         }
         __syncwarp();
-        const float4 sk = W.stage[sI], sk2 = W.stage[GG_MAX_SINKS + sI];
-        const float sx = sk.x, sy = sk.y, sz = sk.z, ms = sk.w, hs = sk2.x;
-        const int sidx = __float_as_int(sk2.y);
+        Sink K;
+        {
+            const float4 sk = W.stage[sI], sk2 = W.stage[GG_MAX_SINKS + sI];
+            K.sx = sk.x; K.sy = sk.y; K.sz = sk.z; K.ms = sk.w; K.hs = sk2.x;
+            K.sidx = __float_as_int(sk2.y);
+        }
+        K.ax = K.ay = K.az = K.ap = K.dtm = 0.f;
+        K.dax = K.day = K.daz = K.dap = 0.0;
         __syncwarp();
-        float ax = 0.f, ay = 0.f, az = 0.f, ap = 0.f, dtm = 0.f; // FP32 partial sums of the current block
-        double dax = 0.0, day = 0.0, daz = 0.0, dap = 0.0;         // FP64 running sums
-        const int *heads = &A.listHead[3 * task.node], *cnts = &A.listCnt[3 * task.node];
+        const int wg = task.ord / GG_WALK_GB;
+        const unsigned myBit = 1u << (task.ord - wg * GG_WALK_GB);
+        const int *heads = &A.groupHead[6 * wg], *cnts = &A.groupCnt[6 * wg];
 
-        // ---- Newtonian cells (ILCN): QEVAL to ORDER
-        {
-            int blk = heads[2], total = cnts[2];
-            int cnt = total > 0 ? total - 32 * ((total - 1) / 32) : 0; // the head block is the partial one
-            while (blk >= 0) {
-                const int nxt = A.nextBlk[blk];
-                // stage the block: positions by their own lane (32 B = one sector each); moment records COALESCED,
-                // LPR lanes per 128 B record (a warp-wide LDG.128 touches 32/LPR lines instead of 32)
-                int cn = 0;
-                if (lane < cnt) {
-                    const unsigned it = A.pool[(size_t)blk * 32 + lane];
-                    cn = (int)(it >> A.imgBits);
-                    const int ci = (int)(it & imgMask);
-                    const double2 *nq = reinterpret_cast<const double2 *>(&A.nodes[cn]);
-                    const double2 p01 = __ldg(nq), p23 = __ldg(nq + 1);
-                    W.stage[lane * CSTRIDE] =
-                        make_float4((float)((p01.x + s_off[3 * ci]) - cenx), (float)((p01.y + s_off[3 * ci + 1]) - ceny),
-                                    (float)((p23.x + s_off[3 * ci + 2]) - cenz), (float)p23.y);
-                }
-                if (ORDER >= 2) {
-                    constexpr int LPR = ORDER == 2 ? 2 : (ORDER == 3 ? 4 : 8); // float4 pieces of the record in use
-                    const int piece = lane & (LPR - 1), sub = lane / LPR;
-#pragma unroll
-                    for (int i = 0; i < LPR; ++i) {
-                        const int rec = i * (32 / LPR) + sub;
-                        const int rn = __shfl_sync(FULL, cn, rec);
-                        if (rec < cnt) W.stage[rec * CSTRIDE + 1 + piece] = __ldg(&A.momf[(size_t)rn * 8 + piece]);
+#pragma unroll 1
+        for (int type = 2; type >= 0; --type) { // Newtonian cells, softened cells, leaves
+            // walk the group's shared chain (src 0), then its masked chain (src 1); entries of this bucket queue up
+            int pending = 0, src = 0;
+            int blk = heads[2 * type];
+            int cnt = cnts[2 * type];
+            cnt = cnt > 0 ? cnt - 32 * ((cnt - 1) / 32) : 0; // the head block is the partial one
+            for (;;) {
+                if (pending < 32) {
+                    if (blk >= 0) {
+                        bool has = lane < cnt;
+                        unsigned it = 0;
+                        if (has) {
+                            it = A.pool[(size_t)blk * 32 + lane];
+                            if (src) has = (A.poolMask[(size_t)blk * 32 + lane] & myBit) != 0;
+                        }
+                        blk = A.nextBlk[blk];
+                        cnt = 32;
+                        const unsigned m = __ballot_sync(FULL, has);
+                        if (has) W.queue[pending + __popc(m & lt)] = it;
+                        pending += __popc(m);
+                        __syncwarp();
+                        continue;
                     }
+                    if (src == 0) {
+                        src = 1;
+                        blk = heads[2 * type + 1];
+                        cnt = cnts[2 * type + 1];
+                        cnt = cnt > 0 ? cnt - 32 * ((cnt - 1) / 32) : 0;
+                        continue;
+                    }
+                    if (pending == 0) break;
+                }
+                const int n = min(32, pending);
+                const unsigned e = W.queue[lane];
+                const unsigned rest = W.queue[32 + lane];
+                __syncwarp();
+                W.queue[lane] = rest;
+                pending -= n;
+                if (type == 2) eval_cells<ORDER>(A, W, s_off, E, K, e, n, lane);
+                else if (type == 0) eval_leaves(A, W, s_off, E, K, e, n, lane);
+                else {
+                    const SoftTerm st = eval_soft(A.nodes, A.momq, A.imgBits, s_off, (double)K.sx + E.cenx, (double)K.sy + E.ceny,
+                                                  (double)K.sz + E.cenz, (double)K.ms, (double)K.hs, E.nS, e, n, lane);
+                    K.dax += st.ax; K.day += st.ay; K.daz += st.az; K.dap += st.pot;
+                    K.dtm = fmaxf(K.dtm, (float)st.dt);
                 }
                 __syncwarp();
-                if (worker) {
-                    constexpr int kUnroll = GG_CELL_UNROLL;
-#pragma unroll kUnroll
-                    for (int j = q; j < cnt; j += G) {
-                        const float4 *S = &W.stage[j * CSTRIDE];
-                        const float4 pc = S[0];
-                        CellMom c;
-                        c.m0 = S[1]; c.m1 = S[2];
-                        if (ORDER >= 3) { c.m2 = S[3]; c.m3 = S[4]; }
-                        if (ORDER >= 4) { c.m4 = S[5]; c.m5 = S[6]; c.m6 = S[7]; c.m7 = S[8]; }
-                        float fx, fy, fz, fp, fdt;
-                        cell_on_sink<ORDER>(c, pc.w, sx - pc.x, sy - pc.y, sz - pc.z, ms, fx, fy, fz, fp, fdt);
-                        ax += fx; ay += fy; az += fz; ap -= fp;
-                        dtm = fmaxf(dtm, fdt);
-                    }
-                }
-                dax += (double)ax; day += (double)ay; daz += (double)az; dap += (double)ap;
-                ax = ay = az = ap = 0.f;
-                __syncwarp();
-                blk = nxt;
-                cnt = 32;
-            }
-        }
-        // ---- particles (ILP) incl. the bucket's own (intra-bucket pairs, grav.c:211-242): SPLINE-softened monopoles
-        {
-            int blk = heads[0], total = cnts[0];
-            int cnt = total > 0 ? total - 32 * ((total - 1) / 32) : 0;
-            while (blk >= 0) {
-                const int nxt = A.nextBlk[blk];
-                if (lane < cnt) {
-                    const unsigned it = A.pool[(size_t)blk * 32 + lane];
-                    const int pi = (int)(it >> A.imgBits), ci = (int)(it & imgMask);
-                    const PartS p = load_part(&A.parts[pi]);
-                    float4 *S = &W.stage[lane * PSTRIDE];
-                    S[0] = make_float4((float)((p.x + s_off[3 * ci]) - cenx), (float)((p.y + s_off[3 * ci + 1]) - ceny),
-                                       (float)((p.z + s_off[3 * ci + 2]) - cenz), p.m);
-                    // a particle does not act on itself (grav.c:211): remember who it is, in the home image only
-                    S[1] = make_float4(p.h, __int_as_float(ci == A.homeImage ? pi : -1), 0.f, 0.f);
-                }
-                __syncwarp();
-                if (worker) {
-#pragma unroll 2
-                    for (int j = q; j < cnt; j += G) {
-                        const float4 pp = W.stage[j * PSTRIDE];
-                        const float2 ph = *reinterpret_cast<const float2 *>(&W.stage[j * PSTRIDE + 1]);
-                        if (__float_as_int(ph.y) == sidx) continue;
-                        float fx, fy, fz, fp, fdt;
-                        part_on_sink(pp.w, ph.x, sx - pp.x, sy - pp.y, sz - pp.z, ms, hs, fx, fy, fz, fp, fdt);
-                        ax += fx; ay += fy; az += fz; ap -= fp;
-                        dtm = fmaxf(dtm, fdt);
-                    }
-                }
-                dax += (double)ax; day += (double)ay; daz += (double)az; dap += (double)ap;
-                ax = ay = az = ap = 0.f;
-                __syncwarp();
-                blk = nxt;
-                cnt = 32;
-            }
-        }
-        // ---- softened cells (ILCS, rare): FP64, the first nS lanes each take their sink
-        {
-            int blk = heads[1], total = cnts[1];
-            int cnt = total > 0 ? total - 32 * ((total - 1) / 32) : 0;
-            while (blk >= 0) {
-                const int nxt = A.nextBlk[blk];
-                for (int j = 0; j < cnt; ++j) {
-                    const unsigned it = A.pool[(size_t)blk * 32 + j];
-                    const int cn = (int)(it >> A.imgBits), ci = (int)(it & imgMask);
-                    if (lane < nS) {
-                        const NodeW nd = load_node(&A.nodes[cn]);
-                        const double cx = nd.rx + s_off[3 * ci], cy = nd.ry + s_off[3 * ci + 1], cz = nd.rz + s_off[3 * ci + 2];
-                        const SoftTerm st = softcell_on_sink(nd.fMass, nd.fSoft, &A.momq[(size_t)cn * 6], ((double)sx + cenx) - cx,
-                                                             ((double)sy + ceny) - cy, ((double)sz + cenz) - cz, (double)ms,
-                                                             (double)hs);
-                        dax += st.ax; day += st.ay; daz += st.az; dap += st.pot;
-                        dtm = fmaxf(dtm, (float)st.dt);
-                    }
-                }
-                blk = nxt;
-                cnt = 32;
             }
         }
 
@@ -621,22 +798,22 @@ __global__ void __launch_bounds__(GG_WARPS_PER_CTA * 32, GG_MIN_CTAS) k_eval(con
         {
             double *red = reinterpret_cast<double *>(W.stage); // [32][4] doubles, then [32] floats
             float *redt = reinterpret_cast<float *>(red + 128);
-            red[4 * lane] = dax; red[4 * lane + 1] = day; red[4 * lane + 2] = daz; red[4 * lane + 3] = dap;
-            redt[lane] = dtm;
+            red[4 * lane] = K.dax; red[4 * lane + 1] = K.day; red[4 * lane + 2] = K.daz; red[4 * lane + 3] = K.dap;
+            redt[lane] = K.dtm;
             __syncwarp();
-            if (lane < nS) {
+            if (lane < E.nS) {
                 double vx = 0.0, vy = 0.0, vz = 0.0, vp = 0.0;
                 float vd = 0.f;
-                for (int g = 0; g < G; ++g) {
-                    const int l = g * nS + lane;
+                for (int g = 0; g < E.G; ++g) {
+                    const int l = g * E.nS + lane;
                     vx += red[4 * l]; vy += red[4 * l + 1]; vz += red[4 * l + 2]; vp += red[4 * l + 3];
                     vd = fmaxf(vd, redt[l]);
                 }
-                A.acc[3 * (size_t)sidx] = vx;
-                A.acc[3 * (size_t)sidx + 1] = vy;
-                A.acc[3 * (size_t)sidx + 2] = vz;
-                A.pot[sidx] = vp;
-                A.dtg[sidx] = (double)vd;
+                A.acc[3 * (size_t)K.sidx] = vx;
+                A.acc[3 * (size_t)K.sidx + 1] = vy;
+                A.acc[3 * (size_t)K.sidx + 2] = vz;
+                A.pot[K.sidx] = vp;
+                A.dtg[K.sidx] = (double)vd;
             }
         }
         __syncwarp();
@@ -645,7 +822,7 @@ __global__ void __launch_bounds__(GG_WARPS_PER_CTA * 32, GG_MIN_CTAS) k_eval(con
 
 } // namespace
 
-size_t gg_walk_kernel_smem(int maxBucket) { return GG_WALK_WARPS * walk_smem_bytes(maxBucket); }
+size_t gg_walk_kernel_smem() { return GG_WALK_WARPS * walk_smem_bytes(); }
 
 static int grid_for(const void *fn, int threads, size_t smem, int nSM, int warpsPerCta, int nTasks, cudaError_t *pe) {
     int perSM = 0;
@@ -658,10 +835,11 @@ static int grid_for(const void *fn, int threads, size_t smem, int nSM, int warps
 }
 
 cudaError_t gg_launch_walk_kernel(const TreeKernelArgs &a, int nSM, cudaStream_t st) {
-    const size_t smem = gg_walk_kernel_smem(a.maxBucket);
+    const size_t smem = gg_walk_kernel_smem();
     cudaError_t e = cudaFuncSetAttribute(k_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const int grid = grid_for((const void *)k_walk, GG_WALK_WARPS * 32, smem, nSM, GG_WALK_WARPS, a.nTasks, &e);
+    const int nGroups = (a.nBuckets + GG_WALK_GB - 1) / GG_WALK_GB;
+    const int grid = grid_for((const void *)k_walk, GG_WALK_WARPS * 32, smem, nSM, GG_WALK_WARPS, nGroups, &e);
     if (e != cudaSuccess) return e;
     k_walk<<<grid, GG_WALK_WARPS * 32, smem, st>>>(a);
     return cudaGetLastError();
