@@ -60,7 +60,7 @@ struct gg_context {
     std::vector<int> hActive; // host copy of the local ACTIVE flags (empty = all active)
     // device buffers
     DevBuf nodes, momf, momq, parts, active, hsoft, tasks, ngroups, goffs, counts, acc, pot, dtg, fweight, nloop, sums,
-        misc, imgoff, ewt, raw, rawi, cubtmp, flush, pool, nextblk, poolmask, isb, boffs, bnode, ghead, gcnt;
+        misc, imgoff, ewt, raw, rawi, cubtmp, flush, pool, nextblk, poolmask, isb, boffs, bnode, ghead, gcnt, bcnt, btot, boff64, lists;
     void *pinned = nullptr;
     size_t pinnedCap = 0;
     int nTasks = 0;
@@ -297,7 +297,8 @@ void gg_destroy(gg_context *c) {
     DevBuf *all[] = {&c->nodes, &c->momf, &c->momq, &c->parts, &c->active, &c->hsoft, &c->tasks, &c->ngroups,
                      &c->goffs, &c->counts, &c->acc, &c->pot, &c->dtg, &c->fweight, &c->nloop, &c->sums, &c->misc,
                      &c->imgoff, &c->ewt, &c->raw, &c->rawi, &c->cubtmp, &c->flush, &c->pool,
-                     &c->nextblk, &c->poolmask, &c->isb, &c->boffs, &c->bnode, &c->ghead, &c->gcnt};
+                     &c->nextblk, &c->poolmask, &c->isb, &c->boffs, &c->bnode, &c->ghead, &c->gcnt, &c->bcnt, &c->btot,
+                     &c->boff64, &c->lists};
     for (DevBuf *b : all)
         if (b->p) cudaFree(b->p);
     if (c->pinned) cudaFreeHost(c->pinned);
@@ -582,6 +583,9 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
     const int nWalkGroups = (nBuckets + GG_WALK_GB - 1) / GG_WALK_GB;
     if ((rc = ensure(c, c->ghead, (size_t)(nWalkGroups + 1) * 6 * sizeof(int)))) return rc;
     if ((rc = ensure(c, c->gcnt, (size_t)(nWalkGroups + 1) * 6 * sizeof(int)))) return rc;
+    if ((rc = ensure(c, c->bcnt, (size_t)(nBuckets + 1) * 3 * sizeof(int)))) return rc;
+    if ((rc = ensure(c, c->btot, (size_t)(nBuckets + 1) * sizeof(long long)))) return rc;
+    if ((rc = ensure(c, c->boff64, (size_t)(nBuckets + 1) * sizeof(long long)))) return rc;
     c->nTasks = nTasks;
 
     // ---- walk (lists -> HBM pool) + list evaluation
@@ -603,6 +607,9 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
     ta.nBuckets = nBuckets;
     ta.groupHead = (int *)c->ghead.p;
     ta.groupCnt = (int *)c->gcnt.p;
+    ta.bucketCnt = (int *)c->bcnt.p;
+    ta.bucketTot = (long long *)c->btot.p;
+    ta.bucketOff = (const long long *)c->boff64.p;
     ta.taskCounter = (int *)c->misc.p;
     ta.errFlag = (int *)c->misc.p + 1;
     ta.poolCursor = (int *)c->misc.p + 3;
@@ -636,8 +643,29 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
     }
     CK(cudaEventRecord(c->ev[5], c->st));
     if (nTasks > 0 && !walkOnly) {
+        // per-bucket list offsets = exclusive scan of the entry counts the walk left; the total sizes the list array
+        size_t tmpBytes = 0;
+        CK(cudaMemsetAsync((long long *)c->btot.p + nBuckets, 0, sizeof(long long), c->st));
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, (long long *)c->btot.p, (long long *)c->boff64.p, nBuckets + 1, c->st));
+        if ((rc = ensure(c, c->cubtmp, tmpBytes))) return rc;
+        CK(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmpBytes, (long long *)c->btot.p, (long long *)c->boff64.p, nBuckets + 1, c->st));
+        long long nEntries = 0;
+        int hm3[4];
+        CK(cudaMemcpyAsync(&nEntries, (long long *)c->boff64.p + nBuckets, sizeof(long long), cudaMemcpyDeviceToHost, c->st));
+        CK(cudaMemcpyAsync(hm3, c->misc.p, sizeof(hm3), cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        if (hm3[1]) return fail(GG_ERR_UNSUPPORTED, "gg_gravity: walk frontier overflowed %d entries (tree too deep)", GG_STACK_CAP);
+        if ((size_t)hm3[3] > c->capBlocks) {
+            // the chain pool was too small: the walk kept counting, so hm3[3] is what it needs -- grow and run again
+            if (depth >= 2) return fail(GG_ERR_NOMEM, "gg_gravity: list pool overflow persists (%d blocks)", hm3[3]);
+            c->capBlocks = (size_t)hm3[3] + (size_t)hm3[3] / 8 + 1024;
+            return run_gravity(c, prm, singleTask, stats, depth + 1);
+        }
+        if ((rc = ensure(c, c->lists, ((size_t)nEntries + 32) * sizeof(unsigned)))) return rc;
+        ta.lists = (unsigned *)c->lists.p;
+        CK(gg_launch_scatter_kernel(ta, c->nSM, c->st));
         CK(gg_launch_eval_kernel(ta, c->nSM, c->st));
-        ++c->nLaunches;
+        c->nLaunches += 4;
     }
     CK(cudaEventRecord(c->ev[2], c->st));
 

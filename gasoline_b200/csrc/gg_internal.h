@@ -16,7 +16,7 @@
 
 #define GG_WARPS_PER_CTA 4   // k_eval
 #ifndef GG_MIN_CTAS
-#define GG_MIN_CTAS 6        // resident CTAs per SM k_eval is compiled for (register cap 65536/(128*6) = 85)
+#define GG_MIN_CTAS 5        // resident CTAs per SM k_eval is compiled for (44 KB shared memory each; register cap 102)
 #endif
 #ifndef GG_CELL_UNROLL
 #define GG_CELL_UNROLL 1     // unroll factor of k_eval's (sink, cell) loop
@@ -78,6 +78,11 @@ struct TreeKernelArgs {
     unsigned char *poolMask; // [capBlocks][32] masked chains: which buckets of the walk group the entry belongs to
     int *groupHead;          // [nWalkGroups][3 list types][2]: chain shared by every bucket of the group, masked chain
     int *groupCnt;           // [nWalkGroups][3][2] entries in each chain
+    // per-bucket contiguous lists (k_scatter output, k_eval input), indexed by bucket ordinal
+    int *bucketCnt;          // [nBuckets][3] entries of the bucket's leaf / softened-cell / Newtonian-cell list
+    long long *bucketTot;    // [nBuckets + 1] k_walk: entries of the bucket over the three lists
+    const long long *bucketOff; // [nBuckets + 1] exclusive scan of bucketTot: where the bucket's lists start
+    unsigned *lists;         // [bucketOff[nBuckets]]: per bucket its Newtonian cells, softened cells, leaves
     int rootNode;            // global index where every image's walk starts
     int nImages, homeImage, imgBits;
     const double *imgOff;    // [nImages][3]
@@ -121,6 +126,7 @@ struct StatsKernelArgs {
 };
 
 cudaError_t gg_launch_walk_kernel(const TreeKernelArgs &a, int nSM, cudaStream_t st);
+cudaError_t gg_launch_scatter_kernel(const TreeKernelArgs &a, int nSM, cudaStream_t st);
 cudaError_t gg_launch_eval_kernel(const TreeKernelArgs &a, int nSM, cudaStream_t st);
 cudaError_t gg_launch_ewald_kernel(const EwaldKernelArgs &a, cudaStream_t st);
 cudaError_t gg_launch_stats_kernel(const StatsKernelArgs &a, cudaStream_t st);

@@ -46,7 +46,8 @@ __device__ __forceinline__ bool intersect_np(const double *box, double fBall2, d
 }
 
 __device__ __forceinline__ float rsqrt_nr(float d2) {
-    float y = rsqrtf(d2);
+    float y; // the bare MUFU.RSQ: rsqrtf() wraps it in a denormal-range fix-up that no squared distance here needs
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(d2));
     return y * fmaf(-0.5f * d2, y * y, 1.5f); // one Newton step: MUFU.RSQ is good to ~2^-22
 }
 
@@ -352,7 +353,7 @@ __device__ __forceinline__ void append(const TreeKernelArgs &A, WalkSmem &W, int
 // leaves (np > 0).
 __device__ __forceinline__ void distribute(const TreeKernelArgs &A, WalkSmem &W, int type, unsigned dm, unsigned all,
                                            int nB, unsigned entry, int np, int lane, unsigned lt, Slab &slab,
-                                           int &myCnt, int &sharedP) {
+                                           int &myCnt, int &sharedP, int &myLeaves) {
     const unsigned mAny = __ballot_sync(FULL, dm != 0);
     if (!mAny) return;
     const bool shared = dm == all;
@@ -368,7 +369,7 @@ __device__ __forceinline__ void distribute(const TreeKernelArgs &A, WalkSmem &W,
             const unsigned mb = __ballot_sync(FULL, has);
             if (!mb) continue;
             const int c = type == 0 ? __reduce_add_sync(FULL, has ? np : 0) : __popc(mb);
-            if (lane == b) myCnt += c;
+            if (lane == b) { myCnt += c; myLeaves += __popc(mb); }
         }
         append(A, W, type, 1, pm != 0, entry, pm, lane, lt, slab);
     }
@@ -420,7 +421,7 @@ __global__ void __launch_bounds__(GG_WALK_WARPS * 32, GG_WALK_MIN_CTAS) k_walk(c
         if (lane < 6) {
             (&W.head[0][0])[lane] = -1; (&W.fill[0][0])[lane] = 0; (&W.cnt[0][0])[lane] = 0;
         }
-        int myP = 0, myS = 0, myN = 0, sharedP = 0, unused = 0; // lane b: masked entries of bucket b
+        int myP = 0, myS = 0, myN = 0, myL = 0, sharedP = 0, unused = 0; // lane b: masked entries of bucket b
         int nStack = A.nImages;
         for (int i = lane; i < A.nImages; i += 32) {
             W.stack[i] = ((unsigned)A.rootNode << A.imgBits) | (unsigned)i;
@@ -502,9 +503,9 @@ __global__ void __launch_bounds__(GG_WALK_WARPS * 32, GG_WALK_MIN_CTAS) k_walk(c
                 } else atomicExch(A.errFlag, 1);
             }
             nStack += 2 * __popc(mPush);
-            distribute(A, W, 2, mNewt, all, nB, item, 0, lane, lt, slab, myN, unused);
-            distribute(A, W, 1, mSoft, all, nB, item, 0, lane, lt, slab, myS, unused);
-            distribute(A, W, 0, np > 0 ? mOpen : 0u, all, nB, item, np, lane, lt, slab, myP, sharedP);
+            distribute(A, W, 2, mNewt, all, nB, item, 0, lane, lt, slab, myN, unused, unused);
+            distribute(A, W, 1, mSoft, all, nB, item, 0, lane, lt, slab, myS, unused, unused);
+            distribute(A, W, 0, np > 0 ? mOpen : 0u, all, nB, item, np, lane, lt, slab, myP, sharedP, myL);
             __syncwarp();
         }
         // ---- hand the chains over, and what pkdBucketWalk reports per bucket (walk.c:175-177)
@@ -513,6 +514,9 @@ __global__ void __launch_bounds__(GG_WALK_WARPS * 32, GG_WALK_MIN_CTAS) k_walk(c
             c[0] = sharedP + myP - W.own[lane];
             c[1] = W.cnt[1][0] + myS;
             c[2] = W.cnt[2][0] + myN;
+            int *e = &A.bucketCnt[3 * (b0 + lane)]; // list ENTRIES (a leaf entry stands for all particles of a bucket)
+            e[0] = W.cnt[0][0] + myL; e[1] = c[1]; e[2] = c[2];
+            A.bucketTot[b0 + lane] = (long long)e[0] + e[1] + e[2];
         }
         if (lane < 6) {
             A.groupHead[6 * g + lane] = (&W.head[0][0])[lane];
@@ -523,14 +527,70 @@ __global__ void __launch_bounds__(GG_WALK_WARPS * 32, GG_WALK_MIN_CTAS) k_walk(c
 }
 
 // ------------------------------------------------------------------------------------------------ k_eval
+// ------------------------------------------------------------------------------------------------ k_scatter
+// One warp per walk group: copy the group's chains into the contiguous per-bucket lists k_eval streams through
+// (shared entries to every bucket of the group, masked entries to the buckets of their mask).  Bucket b's lists
+// start at bucketOff[b]: Newtonian cells, then softened cells, then leaves.
+__global__ void __launch_bounds__(256) k_scatter(const TreeKernelArgs A) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int nGroups = (A.nBuckets + GG_WALK_GB - 1) / GG_WALK_GB;
+    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= nGroups) return;
+    const int b0 = g * GG_WALK_GB, nB = min(GG_WALK_GB, A.nBuckets - b0);
+    const unsigned all = (1u << nB) - 1u;
+    // lane b < nB: write cursor of bucket b, advanced type by type (2 Newtonian, 1 softened, 0 leaves)
+    long long cursor = lane < nB ? A.bucketOff[b0 + lane] : 0;
+    int c0 = 0, c1 = 0, c2 = 0;
+    if (lane < nB) { c0 = A.bucketCnt[3 * (b0 + lane)]; c1 = A.bucketCnt[3 * (b0 + lane) + 1]; c2 = A.bucketCnt[3 * (b0 + lane) + 2]; }
+#pragma unroll 1
+    for (int type = 2; type >= 0; --type) {
+        long long cur = cursor;
+#pragma unroll 1
+        for (int src = 0; src < 2; ++src) {
+            int blk = A.groupHead[6 * g + 2 * type + src];
+            const int total = A.groupCnt[6 * g + 2 * type + src];
+            int cnt = total > 0 ? total - 32 * ((total - 1) / 32) : 0; // the head block is the partial one
+            while (blk >= 0) {
+                unsigned it = 0, mk = 0;
+                if (lane < cnt) {
+                    it = A.pool[(size_t)blk * 32 + lane];
+                    mk = src ? A.poolMask[(size_t)blk * 32 + lane] : all;
+                }
+                blk = A.nextBlk[blk];
+                cnt = 32;
+                for (int b = 0; b < nB; ++b) {
+                    const bool has = (mk >> b) & 1u;
+                    const unsigned m = __ballot_sync(FULL, has);
+                    if (!m) continue;
+                    const long long base = __shfl_sync(FULL, cur, b);
+                    if (has) A.lists[base + __popc(m & lt)] = it;
+                    if (lane == b) cur += __popc(m);
+                }
+            }
+        }
+        cursor += type == 2 ? c2 : (type == 1 ? c1 : c0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ k_eval
 #define PCAP (32 * CSTRIDE / PSTRIDE) // particles staged at once (96)
 struct EvalSmem {
-    float4 stage[32 * CSTRIDE]; // staged block; also the sink hand-out at task start and the final reduction scratch
-    unsigned queue[64];         // list entries of this bucket waiting to be evaluated (filtered from the group's chains)
-    int lstart[32], lpart[32];  // leaf expansion: first staging slot and first particle of each leaf of the batch
-    unsigned char owner[PCAP];  // staging slot -> leaf of the batch
-    unsigned char limg[32];
+    float4 stage[2][32 * CSTRIDE]; // double-buffered staged block; [0] also the sink hand-out / final reduction scratch
+    union {
+        double raw[32 * 4];        // cells: FP64 (x, y, z, M) of the block in flight, converted to sink-centred FP32 on arrival
+        struct {                   // leaves (never in flight together with cells)
+            int lstart[32], lpart[32]; // first staging slot and first particle of each leaf of the batch
+            unsigned char owner[PCAP]; // staging slot -> leaf of the batch
+            unsigned char limg[32];
+        };
+    };
 };
+
+__device__ __forceinline__ void cp_async_cg16(void *smem, const void *gmem) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem) : "memory");
+}
 
 // Per-lane evaluation state of one k_eval task: the lane's sink, its FP32 block sums and FP64 running sums.
 struct Sink {
@@ -551,21 +611,17 @@ struct EvalCtx {
     unsigned imgMask;
 };
 
-// <= 32 Newtonian cells (ILCN), one per lane (`it`, lanes < cnt): stage + QEVAL to ORDER.
+// Start the asynchronous gather of one block of <= 32 Newtonian cells (entry `it` per lane, lanes < cnt) into stage
+// buffer `buf`: the FP64 (x,y,z,M) half of the walk record by its own lane, the 128 B FP32 moment record
+// COALESCED, LPR lanes per record (a warp-wide 16 B access touches 32/LPR lines instead of 32).
 template <int ORDER>
-__device__ __forceinline__ void eval_cells(const TreeKernelArgs &A, EvalSmem &W, const double *s_off, const EvalCtx &E,
-                                           Sink &K, unsigned it, int cnt, int lane) {
-    // stage the block: positions by their own lane (32 B = one sector each); moment records COALESCED,
-    // LPR lanes per 128 B record (a warp-wide LDG.128 touches 32/LPR lines instead of 32)
+__device__ __forceinline__ void gather_cells(const TreeKernelArgs &A, EvalSmem &W, int buf, unsigned it, int cnt, int lane) {
     int cn = 0;
     if (lane < cnt) {
         cn = (int)(it >> A.imgBits);
-        const int ci = (int)(it & E.imgMask);
-        const double2 *nq = reinterpret_cast<const double2 *>(&A.nodes[cn]);
-        const double2 p01 = __ldg(nq), p23 = __ldg(nq + 1);
-        W.stage[lane * CSTRIDE] =
-            make_float4((float)((p01.x + s_off[3 * ci]) - E.cenx), (float)((p01.y + s_off[3 * ci + 1]) - E.ceny),
-                        (float)((p23.x + s_off[3 * ci + 2]) - E.cenz), (float)p23.y);
+        const char *src = reinterpret_cast<const char *>(&A.nodes[cn]);
+        cp_async_cg16(&W.raw[4 * lane], src);
+        cp_async_cg16(&W.raw[4 * lane + 2], src + 16);
     }
     if (ORDER >= 2) {
         constexpr int LPR = ORDER == 2 ? 2 : (ORDER == 3 ? 4 : 8); // float4 pieces of the record in use
@@ -574,28 +630,80 @@ __device__ __forceinline__ void eval_cells(const TreeKernelArgs &A, EvalSmem &W,
         for (int i = 0; i < LPR; ++i) {
             const int rec = i * (32 / LPR) + sub;
             const int rn = __shfl_sync(FULL, cn, rec);
-            if (rec < cnt) W.stage[rec * CSTRIDE + 1 + piece] = __ldg(&A.momf[(size_t)rn * 8 + piece]);
+            if (rec < cnt) cp_async_cg16(&W.stage[buf][rec * CSTRIDE + 1 + piece], &A.momf[(size_t)rn * 8 + piece]);
         }
     }
-    __syncwarp();
-    if (E.worker) {
-        constexpr int kUnroll = GG_CELL_UNROLL;
-#pragma unroll kUnroll
-        for (int j = E.q; j < cnt; j += E.G) {
-            const float4 *S = &W.stage[j * CSTRIDE];
-            const float4 pc = S[0];
-            CellMom c;
-            c.m0 = S[1]; c.m1 = S[2];
-            if (ORDER >= 3) { c.m2 = S[3]; c.m3 = S[4]; }
-            if (ORDER >= 4) { c.m4 = S[5]; c.m5 = S[6]; c.m6 = S[7]; c.m7 = S[8]; }
-            float fx, fy, fz, fp, fdt;
-            cell_on_sink<ORDER>(c, pc.w, K.sx - pc.x, K.sy - pc.y, K.sz - pc.z, K.ms, fx, fy, fz, fp, fdt);
-            K.ax += fx; K.ay += fy; K.az += fz; K.ap -= fp;
-            K.dtm = fmaxf(K.dtm, fdt);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// The Newtonian-cell list (ILCN) of the bucket: n entries at L.  Software pipeline: while block i is evaluated
+// (QEVAL to ORDER), block i+1 is being gathered into the other stage buffer and the entries of block i+2 are
+// being loaded.
+template <int ORDER>
+__device__ __forceinline__ void eval_cells(const TreeKernelArgs &A, EvalSmem &W, const double *s_off, const EvalCtx &E,
+                                           Sink &K, const unsigned *L, int n, int lane) {
+    if (n <= 0) return;
+    const int nBlk = (n + 31) >> 5;
+    unsigned itCur = lane < n ? L[lane] : 0u;
+    gather_cells<ORDER>(A, W, 0, itCur, min(32, n), lane);
+    unsigned itNext = 32 + lane < n ? L[32 + lane] : 0u;
+#pragma unroll 1
+    for (int i = 0; i < nBlk; ++i) {
+        const int buf = i & 1, cnt = min(32, n - 32 * i);
+        cp_async_wait_all();
+        __syncwarp();
+        if (lane < cnt) { // FP64 subtraction of the sink-bucket centre, then FP32
+            const int ci = (int)(itCur & E.imgMask);
+            const double2 p01 = *reinterpret_cast<const double2 *>(&W.raw[4 * lane]);
+            const double2 p23 = *reinterpret_cast<const double2 *>(&W.raw[4 * lane + 2]);
+            W.stage[buf][lane * CSTRIDE] =
+                make_float4((float)((p01.x + s_off[3 * ci]) - E.cenx), (float)((p01.y + s_off[3 * ci + 1]) - E.ceny),
+                            (float)((p23.x + s_off[3 * ci + 2]) - E.cenz), (float)p23.y);
         }
+        __syncwarp();
+        if (i + 1 < nBlk) {
+            gather_cells<ORDER>(A, W, buf ^ 1, itNext, min(32, n - 32 * (i + 1)), lane);
+            itCur = itNext;
+            const int k = 32 * (i + 2) + lane;
+            itNext = k < n ? L[k] : 0u;
+        }
+        if (E.worker) {
+            auto load_cell = [&](int j, float4 &pc, CellMom &c) {
+                const float4 *S = &W.stage[buf][j * CSTRIDE];
+                pc = S[0];
+                c.m0 = S[1]; c.m1 = S[2];
+                if (ORDER >= 3) { c.m2 = S[3]; c.m3 = S[4]; }
+                if (ORDER >= 4) { c.m4 = S[5]; c.m5 = S[6]; c.m6 = S[7]; c.m7 = S[8]; }
+            };
+            int j = E.q;
+#if GG_CELL_UNROLL >= 2
+            // two cells per trip in ONE basic block: the second cell's independent work fills the issue slots the
+            // first one's serial 1/r chain (MUFU.RSQ -> Newton step -> g0..g5) leaves empty, and vice versa
+            for (; j + E.G < cnt; j += 2 * E.G) {
+                float4 pa, pb;
+                CellMom ca, cb;
+                load_cell(j, pa, ca);
+                load_cell(j + E.G, pb, cb);
+                float fx, fy, fz, fp, fdt, gx, gy, gz, gp, gdt;
+                cell_on_sink<ORDER>(ca, pa.w, K.sx - pa.x, K.sy - pa.y, K.sz - pa.z, K.ms, fx, fy, fz, fp, fdt);
+                cell_on_sink<ORDER>(cb, pb.w, K.sx - pb.x, K.sy - pb.y, K.sz - pb.z, K.ms, gx, gy, gz, gp, gdt);
+                K.ax += fx + gx; K.ay += fy + gy; K.az += fz + gz; K.ap -= fp + gp;
+                K.dtm = fmaxf(K.dtm, fmaxf(fdt, gdt));
+            }
+#endif
+            for (; j < cnt; j += E.G) {
+                float4 pc;
+                CellMom c;
+                load_cell(j, pc, c);
+                float fx, fy, fz, fp, fdt;
+                cell_on_sink<ORDER>(c, pc.w, K.sx - pc.x, K.sy - pc.y, K.sz - pc.z, K.ms, fx, fy, fz, fp, fdt);
+                K.ax += fx; K.ay += fy; K.az += fz; K.ap -= fp;
+                K.dtm = fmaxf(K.dtm, fdt);
+            }
+        }
+        K.fold();
+        __syncwarp();
     }
-    K.fold();
-    __syncwarp();
 }
 
 // <= 32 opened source BUCKETS (leaves), each standing for all its particles -- incl. the sink bucket itself
@@ -631,7 +739,7 @@ __device__ __forceinline__ void eval_leaves(const TreeKernelArgs &A, EvalSmem &W
             const int r = W.owner[s], ri = W.limg[r];
             const int pi = W.lpart[r] + (s - W.lstart[r]);
             const PartS p = load_part(&A.parts[pi]);
-            float4 *S = &W.stage[s * PSTRIDE];
+            float4 *S = &W.stage[0][s * PSTRIDE];
             S[0] = make_float4((float)((p.x + s_off[3 * ri]) - E.cenx), (float)((p.y + s_off[3 * ri + 1]) - E.ceny),
                                (float)((p.z + s_off[3 * ri + 2]) - E.cenz), p.m);
             // a particle does not act on itself (grav.c:211): remember who it is, in the home image only
@@ -641,8 +749,8 @@ __device__ __forceinline__ void eval_leaves(const TreeKernelArgs &A, EvalSmem &W
         if (E.worker) {
 #pragma unroll 2
             for (int j = E.q; j < nStaged; j += E.G) {
-                const float4 pp = W.stage[j * PSTRIDE];
-                const float2 ph = *reinterpret_cast<const float2 *>(&W.stage[j * PSTRIDE + 1]);
+                const float4 pp = W.stage[0][j * PSTRIDE];
+                const float2 ph = *reinterpret_cast<const float2 *>(&W.stage[0][j * PSTRIDE + 1]);
                 if (__float_as_int(ph.y) == K.sidx) continue;
                 float fx, fy, fz, fp, fdt;
                 part_on_sink(pp.w, ph.x, K.sx - pp.x, K.sy - pp.y, K.sz - pp.z, K.ms, K.hs, fx, fy, fz, fp, fdt);
@@ -677,13 +785,12 @@ __device__ __noinline__ SoftTerm eval_soft(const NodeW *nodes, const double *mom
     return sum;
 }
 
-// One warp per (bucket, pass of <= 8 active sinks).  The lists come from the bucket's walk group: for every list
-// type a chain all buckets of the group share and a chain whose entries carry a bucket mask; the warp filters its
-// own entries into a queue and evaluates them 32 at a time.
+// One warp per (bucket, pass of <= 8 active sinks), streaming through the bucket's three contiguous lists.
 template <int ORDER>
 __global__ void __launch_bounds__(GG_WARPS_PER_CTA * 32, GG_MIN_CTAS) k_eval(const TreeKernelArgs A) {
-    __shared__ EvalSmem s_w[GG_WARPS_PER_CTA];
-    __shared__ double s_off[GG_MAX_IMAGES * 3];
+    extern __shared__ __align__(16) unsigned char eval_smem_raw[];
+    EvalSmem *s_w = reinterpret_cast<EvalSmem *>(eval_smem_raw);
+    double *s_off = reinterpret_cast<double *>(s_w + GG_WARPS_PER_CTA);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
     for (int i = threadIdx.x; i < A.nImages * 3; i += blockDim.x) s_off[i] = A.imgOff[i];
@@ -723,8 +830,8 @@ __global__ void __launch_bounds__(GG_WARPS_PER_CTA * 32, GG_MIN_CTAS) k_eval(con
                 const int rank = seen + __popc(m & lt) - rank0;
                 if (act && rank >= 0 && rank < GG_MAX_SINKS) {
                     const PartS p = load_part(&A.parts[pi]);
-                    W.stage[rank] = make_float4((float)(p.x - E.cenx), (float)(p.y - E.ceny), (float)(p.z - E.cenz), p.m);
-                    W.stage[GG_MAX_SINKS + rank] = make_float4(p.h, __int_as_float(pi), 0.f, 0.f);
+                    W.stage[0][rank] = make_float4((float)(p.x - E.cenx), (float)(p.y - E.ceny), (float)(p.z - E.cenz), p.m);
+                    W.stage[0][GG_MAX_SINKS + rank] = make_float4(p.h, __int_as_float(pi), 0.f, 0.f);
                 }
                 seen += __popc(m);
             }
@@ -732,71 +839,36 @@ __global__ void __launch_bounds__(GG_WARPS_PER_CTA * 32, GG_MIN_CTAS) k_eval(con
         __syncwarp();
         Sink K;
         {
-            const float4 sk = W.stage[sI], sk2 = W.stage[GG_MAX_SINKS + sI];
+            const float4 sk = W.stage[0][sI], sk2 = W.stage[0][GG_MAX_SINKS + sI];
             K.sx = sk.x; K.sy = sk.y; K.sz = sk.z; K.ms = sk.w; K.hs = sk2.x;
             K.sidx = __float_as_int(sk2.y);
         }
         K.ax = K.ay = K.az = K.ap = K.dtm = 0.f;
         K.dax = K.day = K.daz = K.dap = 0.0;
         __syncwarp();
-        const int wg = task.ord / GG_WALK_GB;
-        const unsigned myBit = 1u << (task.ord - wg * GG_WALK_GB);
-        const int *heads = &A.groupHead[6 * wg], *cnts = &A.groupCnt[6 * wg];
+        const int nLeaf = A.bucketCnt[3 * task.ord], nSoft = A.bucketCnt[3 * task.ord + 1], nNewt = A.bucketCnt[3 * task.ord + 2];
+        const unsigned *L = A.lists + A.bucketOff[task.ord];
 
-#pragma unroll 1
-        for (int type = 2; type >= 0; --type) { // Newtonian cells, softened cells, leaves
-            // walk the group's shared chain (src 0), then its masked chain (src 1); entries of this bucket queue up
-            int pending = 0, src = 0;
-            int blk = heads[2 * type];
-            int cnt = cnts[2 * type];
-            cnt = cnt > 0 ? cnt - 32 * ((cnt - 1) / 32) : 0; // the head block is the partial one
-            for (;;) {
-                if (pending < 32) {
-                    if (blk >= 0) {
-                        bool has = lane < cnt;
-                        unsigned it = 0;
-                        if (has) {
-                            it = A.pool[(size_t)blk * 32 + lane];
-                            if (src) has = (A.poolMask[(size_t)blk * 32 + lane] & myBit) != 0;
-                        }
-                        blk = A.nextBlk[blk];
-                        cnt = 32;
-                        const unsigned m = __ballot_sync(FULL, has);
-                        if (has) W.queue[pending + __popc(m & lt)] = it;
-                        pending += __popc(m);
-                        __syncwarp();
-                        continue;
-                    }
-                    if (src == 0) {
-                        src = 1;
-                        blk = heads[2 * type + 1];
-                        cnt = cnts[2 * type + 1];
-                        cnt = cnt > 0 ? cnt - 32 * ((cnt - 1) / 32) : 0;
-                        continue;
-                    }
-                    if (pending == 0) break;
-                }
-                const int n = min(32, pending);
-                const unsigned e = W.queue[lane];
-                const unsigned rest = W.queue[32 + lane];
-                __syncwarp();
-                W.queue[lane] = rest;
-                pending -= n;
-                if (type == 2) eval_cells<ORDER>(A, W, s_off, E, K, e, n, lane);
-                else if (type == 0) eval_leaves(A, W, s_off, E, K, e, n, lane);
-                else {
-                    const SoftTerm st = eval_soft(A.nodes, A.momq, A.imgBits, s_off, (double)K.sx + E.cenx, (double)K.sy + E.ceny,
-                                                  (double)K.sz + E.cenz, (double)K.ms, (double)K.hs, E.nS, e, n, lane);
-                    K.dax += st.ax; K.day += st.ay; K.daz += st.az; K.dap += st.pot;
-                    K.dtm = fmaxf(K.dtm, (float)st.dt);
-                }
-                __syncwarp();
-            }
+        eval_cells<ORDER>(A, W, s_off, E, K, L, nNewt, lane);
+        L += nNewt;
+        for (int i = 0; i < nSoft; i += 32) {
+            const int cnt = min(32, nSoft - i);
+            const unsigned e = lane < cnt ? L[i + lane] : 0u;
+            const SoftTerm st = eval_soft(A.nodes, A.momq, A.imgBits, s_off, (double)K.sx + E.cenx, (double)K.sy + E.ceny,
+                                          (double)K.sz + E.cenz, (double)K.ms, (double)K.hs, E.nS, e, cnt, lane);
+            K.dax += st.ax; K.day += st.ay; K.daz += st.az; K.dap += st.pot;
+            K.dtm = fmaxf(K.dtm, (float)st.dt);
+        }
+        L += nSoft;
+        for (int i = 0; i < nLeaf; i += 32) {
+            const int cnt = min(32, nLeaf - i);
+            const unsigned e = lane < cnt ? L[i + lane] : 0u;
+            eval_leaves(A, W, s_off, E, K, e, cnt, lane);
         }
 
         // ---- combine the G sub-groups (FP64, fixed order) and write out
         {
-            double *red = reinterpret_cast<double *>(W.stage); // [32][4] doubles, then [32] floats
+            double *red = reinterpret_cast<double *>(W.stage[0]); // [32][4] doubles, then [32] floats
             float *redt = reinterpret_cast<float *>(red + 128);
             red[4 * lane] = K.dax; red[4 * lane + 1] = K.day; red[4 * lane + 2] = K.daz; red[4 * lane + 3] = K.dap;
             redt[lane] = K.dtm;
@@ -845,6 +917,16 @@ cudaError_t gg_launch_walk_kernel(const TreeKernelArgs &a, int nSM, cudaStream_t
     return cudaGetLastError();
 }
 
+cudaError_t gg_launch_scatter_kernel(const TreeKernelArgs &a, int nSM, cudaStream_t st) {
+    (void)nSM;
+    const int nGroups = (a.nBuckets + GG_WALK_GB - 1) / GG_WALK_GB;
+    if (nGroups <= 0) return cudaSuccess;
+    k_scatter<<<(nGroups + 7) / 8, 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+size_t gg_eval_kernel_smem() { return GG_WARPS_PER_CTA * sizeof(EvalSmem) + GG_MAX_IMAGES * 3 * sizeof(double); }
+
 cudaError_t gg_launch_eval_kernel(const TreeKernelArgs &a, int nSM, cudaStream_t st) {
     void (*fn)(const TreeKernelArgs) = nullptr;
     switch (a.iOrder) {
@@ -853,9 +935,11 @@ cudaError_t gg_launch_eval_kernel(const TreeKernelArgs &a, int nSM, cudaStream_t
     case 3: fn = k_eval<3>; break;
     default: fn = k_eval<4>; break;
     }
-    cudaError_t e;
-    const int grid = grid_for((const void *)fn, GG_WARPS_PER_CTA * 32, 0, nSM, GG_WARPS_PER_CTA, a.nTasks, &e);
+    const size_t smem = gg_eval_kernel_smem();
+    cudaError_t e = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    fn<<<grid, GG_WARPS_PER_CTA * 32, 0, st>>>(a);
+    const int grid = grid_for((const void *)fn, GG_WARPS_PER_CTA * 32, smem, nSM, GG_WARPS_PER_CTA, a.nTasks, &e);
+    if (e != cudaSuccess) return e;
+    fn<<<grid, GG_WARPS_PER_CTA * 32, smem, st>>>(a);
     return cudaGetLastError();
 }

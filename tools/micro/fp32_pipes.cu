@@ -12,13 +12,15 @@ __global__ void __launch_bounds__(256) k(float *out, int *iout) {
     __syncthreads();
     float2 a0 = make_float2(threadIdx.x * 1e-3f, 1.f), a1 = make_float2(2.f, 3.f), a2 = make_float2(4.f, 5.f),
            a3 = make_float2(6.f, 7.f);
-    const float2 m = make_float2(0.999f + blockIdx.x * 1e-9f, 0.998f), b = make_float2(1e-3f, 2e-3f);
+    const float2 m = make_float2(0.999f + blockIdx.x * 1e-9f, 0.998f);
+    // MODE >= 6: the addend is a run-time register too (3-register FFMA, no immediate form)
+    const float2 b = MODE >= 6 ? make_float2(1e-3f + blockIdx.x * 1e-9f, 2e-3f + threadIdx.x * 1e-9f) : make_float2(1e-3f, 2e-3f);
     int i0 = threadIdx.x, i1 = blockIdx.x, i2 = 3, i3 = 7;
     float l0 = 0.f;
     for (int it = 0; it < ITERS; ++it) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            if (MODE == 0 || MODE == 2 || MODE == 4) { // scalar: 8 FFMA
+            if (MODE == 0 || MODE == 2 || MODE == 4 || MODE == 6) { // scalar: 8 FFMA
                 a0.x = fmaf(a0.x, m.x, b.x); a0.y = fmaf(a0.y, m.y, b.y); a1.x = fmaf(a1.x, m.x, b.x); a1.y = fmaf(a1.y, m.y, b.y);
                 a2.x = fmaf(a2.x, m.x, b.x); a2.y = fmaf(a2.y, m.y, b.y); a3.x = fmaf(a3.x, m.x, b.x); a3.y = fmaf(a3.y, m.y, b.y);
             } else { // packed: 4 FFMA2 = the same 8 FMAs
@@ -64,5 +66,7 @@ int main() {
     run<3>("FFMA2 + 4 int ALU / 8 FMA", p.multiProcessorCount, d, di);
     run<4>("FFMA  + 2 LDS / 8 FMA", p.multiProcessorCount, d, di);
     run<5>("FFMA2 + 2 LDS / 8 FMA", p.multiProcessorCount, d, di);
+    run<6>("FFMA 3-register", p.multiProcessorCount, d, di);
+    run<7>("FFMA2 3-register", p.multiProcessorCount, d, di);
     return 0;
 }
