@@ -13,10 +13,12 @@ active sinks; Ewald terms are not interactions) divided by time.
   e2e       the same through the public host API with HOST buffers: every step re-ingests the host's tree +
             particles from pinned memory (gg_set_local: the reference frees and rebuilds kdNodes before every
             gravity call, pkd.c:2636-2642), runs the kernels and reads a, fPot, dtGrav, fWeight back.
-  roofline  the fused walk+interact kernel against the FP32 FMA pipe (this is FP32 CUDA-core + SFU work, not HBM- or
-            tensor-bound -- DESIGN.md): achieved = the reference's own flop score of the lists it evaluated
-            (grav.c:246-247) / kernel time; peak = dependent-FFMA microbenchmark measured in this run on this GPU.
-            The HBM view (algorithmic bytes / time vs MEASURED_PEAKS.json hbm_gbs) is reported beside it.
+  roofline  the dominant kernel, k_eval<4> (list evaluation), against the FP32 FMA pipe (this is FP32 CUDA-core + SFU
+            work, not HBM- or tensor-bound -- DESIGN.md 5): achieved = the reference's own flop score of the lists it
+            evaluated (grav.c:246-247) / the kernel's duration (CUDA events recorded around the launch on the
+            library's stream); peak = dependent-FFMA microbenchmark measured in this run on this GPU.  The HBM view
+            (algorithmic bytes / time vs MEASURED_PEAKS.json hbm_gbs) is reported beside it; traffic = DRAM bytes of
+            one k_eval launch from the committed ncu capture (profiles/).
   cpu_baseline / --impl reference
             the reference's own compiled pkdGravAll on the host cores (oracle/cpu_baseline.py).
 
@@ -137,10 +139,20 @@ def run_reference(a):
 
 
 # ---------------------------------------------------------------------------------------------- our arm
-def algorithmic_bytes(n_particles: int, n_nodes: int) -> float:
-    """Compulsory HBM traffic of one force evaluation: every source particle record (32 B) and every
-    tree node (64 B walk record + 128 B moment record) read once, 48 B of results written per particle."""
-    return 32.0 * n_particles + 192.0 * n_nodes + 48.0 * n_particles
+def algorithmic_bytes(n_particles: int, n_nodes: int, n_list_entries: float) -> float:
+    """Compulsory HBM traffic of one k_eval launch: every source particle record (32 B) and every tree
+    node (64 B walk record + 128 B moment record) read once, the per-bucket interaction lists streamed once (4 B per
+    entry), 40 B of results written per particle."""
+    return 32.0 * n_particles + 192.0 * n_nodes + 4.0 * n_list_entries + 40.0 * n_particles
+
+
+def ncu_traffic(spec: str):
+    """DRAM bytes of one k_eval launch from the committed ncu capture of this workload (None if absent)."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "k_eval_summary.json")))
+        return d["dram_bytes_per_launch"] if d.get("workload") == spec else None
+    except (OSError, KeyError, ValueError):
+        return None
 
 
 def run_ours(a):
@@ -196,13 +208,14 @@ def run_ours(a):
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
-    ms_total = ms_tree = ms_ewald = 0.0
+    ms_total = ms_tree = ms_ewald = ms_eval = ms_walk = 0.0
     launches = 0
     wall0 = time.perf_counter()
     for _ in range(a.steps):
         pkd.flush_l2()
         st = pkd.pkdGravAll(g, download=False)
         ms_total += st["msTotal"]; ms_tree += st["msTree"]; ms_ewald += st["msEwald"]
+        ms_eval += st["msEval"]; ms_walk += st["msWalk"]
         launches += st["nKernelLaunches"]
     barrier()
     wall_resident = time.perf_counter() - wall0
@@ -226,14 +239,15 @@ def run_ours(a):
     d2h = 6 * 8 * n
 
     # ---- reduce over ranks: time = max, work = sum
-    vals = torch.tensor([ms_total, ms_tree, e2e_s, wall_resident], dtype=torch.float64, device="cuda")
+    vals = torch.tensor([ms_total, ms_tree, e2e_s, wall_resident, ms_eval, ms_walk, ms_ewald], dtype=torch.float64,
+                        device="cuda")
     sums = torch.tensor([inter, st["dFlop"] - st["dFlopEwald"], float(launches), float(n), float(pkd.tree.nNodes),
-                         float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
+                         float(h2d), float(d2h), st["nListEntries"]], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    ms_total_max, ms_tree_max, e2e_max, wall_res_max = vals.tolist()
-    inter_all, flop_tree_all, launches_all, n_all, nodes_all, h2d_all, d2h_all = sums.tolist()
+    ms_total_max, ms_tree_max, e2e_max, wall_res_max, ms_eval_max, ms_walk_max, ms_ewald_max = vals.tolist()
+    inter_all, flop_tree_all, launches_all, n_all, nodes_all, h2d_all, d2h_all, entries_all = sums.tolist()
 
     if rank == 0:
         ms_step = ms_total_max / a.steps
@@ -245,19 +259,23 @@ def run_ours(a):
         except OSError:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        # roofline of the dominant kernel (fused walk+interact), per launch, per GPU
+        # roofline of the dominant kernel (k_eval), per launch, per GPU
+        eval_ms = ms_eval_max / a.steps
         flop_per_launch = flop_tree_all / world
-        ach_tf = flop_per_launch / (tree_ms * 1e-3) * 1e-12
-        alg_bytes = algorithmic_bytes(int(n_all), int(nodes_all)) / world
-        roof = {"bound": "fp32", "kernel": "k_tree_gravity<4>", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": ach_tf / peak_tf if peak_tf else None, "traffic": None,
+        ach_tf = flop_per_launch / (eval_ms * 1e-3) * 1e-12
+        alg_bytes = algorithmic_bytes(int(n_all / world), int(nodes_all / world), entries_all / world)
+        roof = {"bound": "fp32", "kernel": f"k_eval<{g.iOrder}>", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": ach_tf / peak_tf if peak_tf else None, "traffic": ncu_traffic(spec),
                 "peak_source": "dependent-FFMA microbenchmark measured in this run (nominal 74.4 TFLOP/s at 1965 MHz)",
                 "flops": "the reference's own score of the evaluated lists (grav.c:246-247: 38/particle, 82/soft "
                          "cell, 312/hexadecapole cell)",
-                "hbm": {"achieved": alg_bytes / (tree_ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": alg_bytes / (tree_ms * 1e-3) * 1e-9 / hbm_peak,
-                        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"},
-                "ms_per_launch": tree_ms}
+                "hbm": {"achieved": alg_bytes / (eval_ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": alg_bytes / (eval_ms * 1e-3) * 1e-9 / hbm_peak, "algorithmic_bytes": alg_bytes,
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback (B200_PROFILING.md)"},
+                "ms_per_launch": eval_ms,
+                "step_breakdown_ms": {"k_walk": ms_walk_max / a.steps, "scan+k_scatter": tree_ms - eval_ms - ms_walk_max / a.steps,
+                                      "k_eval": eval_ms, "k_ewald": ms_ewald_max / a.steps,
+                                      "other (task list, memsets, k_stats)": ms_step - tree_ms - ms_ewald_max / a.steps}}
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f32 (FP64 opening tests, FP64 accumulation across lanes, FP64 Ewald)", "data": "synthetic",

@@ -46,7 +46,7 @@ struct Domain {
 struct gg_context {
     int device = 0, nSM = 0;
     cudaStream_t st = nullptr;
-    cudaEvent_t ev[6];
+    cudaEvent_t ev[8];
     // layout
     int idSelf = 0;
     std::vector<Domain> dom; // dom[0] = local
@@ -642,6 +642,8 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
         ++c->nLaunches;
     }
     CK(cudaEventRecord(c->ev[5], c->st));
+    bool evalTimed = false;
+    long long nListEntries = 0;
     if (nTasks > 0 && !walkOnly) {
         // per-bucket list offsets = exclusive scan of the entry counts the walk left; the total sizes the list array
         size_t tmpBytes = 0;
@@ -661,10 +663,13 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
             c->capBlocks = (size_t)hm3[3] + (size_t)hm3[3] / 8 + 1024;
             return run_gravity(c, prm, singleTask, stats, depth + 1);
         }
+        nListEntries = nEntries;
         if ((rc = ensure(c, c->lists, ((size_t)nEntries + 32) * sizeof(unsigned)))) return rc;
         ta.lists = (unsigned *)c->lists.p;
         CK(gg_launch_scatter_kernel(ta, c->nSM, c->st));
+        CK(cudaEventRecord(c->ev[6], c->st));
         CK(gg_launch_eval_kernel(ta, c->nSM, c->st));
+        evalTimed = true;
         c->nLaunches += 4;
     }
     CK(cudaEventRecord(c->ev[2], c->st));
@@ -765,6 +770,8 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
         float ms;
         CK(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2])); stats->msTree = ms;
         CK(cudaEventElapsedTime(&ms, c->ev[1], c->ev[5])); stats->msWalk = ms;
+        if (evalTimed) { CK(cudaEventElapsedTime(&ms, c->ev[6], c->ev[2])); stats->msEval = ms; }
+        stats->nListEntries = (double)nListEntries;
         CK(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3])); stats->msEwald = ms;
         CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[4])); stats->msTotal = ms;
         stats->nKernelLaunches = c->nLaunches;

@@ -48,7 +48,8 @@ class gg_stats(C.Structure):
     _fields_ = [("nActive", C.c_int), ("dPartSum", C.c_double), ("dCellSum", C.c_double), ("dSoftSum", C.c_double),
                 ("dFlop", C.c_double), ("dFlopEwald", C.c_double), ("msTree", C.c_double), ("msEwald", C.c_double),
                 ("msTotal", C.c_double), ("nKernelLaunches", C.c_int), ("nMaxPart", C.c_int),
-                ("nMaxCellSoft", C.c_int), ("nMaxCellNewt", C.c_int), ("msWalk", C.c_double)]
+                ("nMaxCellSoft", C.c_int), ("nMaxCellNewt", C.c_int), ("msWalk", C.c_double), ("msEval", C.c_double),
+                ("nListEntries", C.c_double)]
 
 
 _lib = None

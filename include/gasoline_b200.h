@@ -97,6 +97,8 @@ typedef struct gg_stats {
     int nKernelLaunches;                 /* kernels of this library launched by the call */
     int nMaxPart, nMaxCellSoft, nMaxCellNewt; /* per-bucket list maxima (the reference's diag line, pkd.c:3057) */
     double msWalk;                       /* the walk kernel's share of msTree */
+    double msEval;                       /* the list-evaluation kernel's share of msTree (the dominant kernel) */
+    double nListEntries;                 /* entries of the per-bucket interaction lists k_eval streamed (4 B each) */
 } gg_stats;
 
 const char *gg_last_error(void);

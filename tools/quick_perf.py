@@ -31,6 +31,6 @@ for i in range(a.reps):
     out = pkd.pkdGravAll(g, download=False)
     dt = time.time() - t
     inter = out["dPartSum"] + out["dCellSum"] + out["dSoftSum"]
-    print(f"  rep {i}: walk {out["msWalk"]:.3f} tree {out["msTree"]:.3f} ms ewald {out['msEwald']:.3f} ms total {out['msTotal']:.3f} ms wall {dt*1e3:.2f} ms | "
+    print(f"  rep {i}: walk {out["msWalk"]:.3f} eval {out["msEval"]:.3f} tree {out["msTree"]:.3f} ms ewald {out['msEwald']:.3f} ms total {out['msTotal']:.3f} ms wall {dt*1e3:.2f} ms | "
           f"inter {inter:.4g} -> {inter/out['msTotal']*1e3:.4g} int/s, flop {out['dFlop']:.4g} -> {out['dFlop']/out['msTotal']*1e-9:.1f} TFLOP/s(ref-scored), "
           f"maxlists {out['nMaxPart']}/{out['nMaxCellSoft']}/{out['nMaxCellNewt']}")
