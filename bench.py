@@ -168,6 +168,8 @@ def run_ours(a):
         raise SystemExit("bench.py: no CUDA device -- this path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     gbuild.build()
     spec = workload_spec(a)
@@ -225,13 +227,20 @@ def run_ours(a):
     # ---- end to end through the host API: host buffers in, host buffers out, every step
     out_a, out_p, out_d, out_w = (pinned_empty((n, 3)), pinned_empty(n), pinned_empty(n), pinned_empty(n))
     for _ in range(min(a.warmup, 2)):
-        pkd.upload(); pkd.pkdGravAll(g, out_a, out_p, out_d, out_w, accumulate=False)
+        if exchange is not None:
+            exchange()
+        else:
+            pkd.upload()
+        pkd.pkdGravAll(g, out_a, out_p, out_d, out_w, accumulate=False)
     barrier()
     e0 = time.perf_counter()
     for _ in range(a.steps):
-        pkd.upload()
         if exchange is not None:
-            exchange()
+            # this rank's own upload (gg_set_local) + the NCCL tree exchange; the top tree belongs to the host's tree
+            # build (pstBuildTree's interior branch), which is outside the timed region like pkdBuildBinary
+            exchange(top=False)
+        else:
+            pkd.upload()
         pkd.pkdGravAll(g, out_a, out_p, out_d, out_w, accumulate=False)
     barrier()
     e2e_s = time.perf_counter() - e0
@@ -285,6 +294,8 @@ def run_ours(a):
                "gpu_launches": int(launches_all), "roofline": roof,
                "interactions_per_step": inter_all, "host_tree_build_s": t_tree,
                "wall_ms_per_step_resident": wall_res_max / a.steps * 1e3}
+        if exchange is not None:
+            out["exchange_phases_ms_rank0"] = {k: v * 1e3 for k, v in exchange.driver.timing.items()}
         if world == 1 and not a.no_cpu_baseline:
             try:
                 r = subprocess.run([sys.executable, "-m", "oracle.cpu_baseline", "--workload", spec, "--seconds",
@@ -300,8 +311,17 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+def _json_only_stdout():
+    """Libraries below us (NCCL's version banner, ...) write to file descriptor 1; the contract is ONE JSON line on
+    stdout.  Point fd 1 at stderr for the whole run and give Python's sys.stdout a private copy of the real one."""
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
+
+
 if __name__ == "__main__":
     args = parse_args()
+    _json_only_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -143,6 +143,18 @@ __global__ void k_pack_parts(int n, const double *x, const double *y, const doub
     if (hsoft) hsoft[i] = h[i];
 }
 
+// A remote domain arriving in device record layout: copy the walk records with links / particle indices rebased
+// from the owner's numbering (base 0) to this rank's global numbering.
+__global__ void k_rebase_nodes(int n, const NodeW *src, int nodeBase, int partBase, NodeW *dst) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    NodeW w = src[i];
+    if (w.c0 >= 0) w.c0 += nodeBase;
+    if (w.c1 >= 0) w.c1 += nodeBase;
+    w.pLower += partBase;
+    dst[nodeBase + i] = w;
+}
+
 // number of 8-sink passes each local bucket needs (0 for cells and for buckets without an active sink)
 __global__ void k_count_groups(int nNodes, const NodeW *nodes, const int *active, int *ngroups, int *isBucket) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -385,6 +397,56 @@ int gg_set_remote(gg_context *c, int id, const gg_tree *t, const gg_particles *p
     c->dom.push_back(Domain{id, t->nNodes, pp->n, t->iRoot, c->nNodesAll, c->nPartAll});
     c->nNodesAll += t->nNodes;
     c->nPartAll += pp->n;
+    return GG_OK;
+}
+
+int gg_export_size(gg_context *c, size_t *bytes, int hdr[3]) {
+    if (!c || !bytes || !hdr || c->dom.empty()) return fail(GG_ERR_ARG, "gg_export_size: no local domain");
+    const Domain &L = c->dom[0];
+    hdr[0] = L.nNodes; hdr[1] = L.nPart; hdr[2] = L.iRoot;
+    *bytes = (size_t)L.nNodes * (sizeof(NodeW) + 128 + 48) + (size_t)L.nPart * sizeof(PartS);
+    return GG_OK;
+}
+
+int gg_export_local(gg_context *c, void *dst) {
+    if (!c || !dst || c->dom.empty()) return fail(GG_ERR_ARG, "gg_export_local: no local domain");
+    CK(cudaSetDevice(c->device));
+    const Domain &L = c->dom[0];
+    char *o = (char *)dst;
+    const size_t nn = (size_t)L.nNodes, np = (size_t)L.nPart;
+    CK(cudaMemcpyAsync(o, c->nodes.p, nn * sizeof(NodeW), cudaMemcpyDeviceToDevice, c->st)); o += nn * sizeof(NodeW);
+    CK(cudaMemcpyAsync(o, c->momf.p, nn * 128, cudaMemcpyDeviceToDevice, c->st)); o += nn * 128;
+    CK(cudaMemcpyAsync(o, c->momq.p, nn * 48, cudaMemcpyDeviceToDevice, c->st)); o += nn * 48;
+    CK(cudaMemcpyAsync(o, c->parts.p, np * sizeof(PartS), cudaMemcpyDeviceToDevice, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return GG_OK;
+}
+
+int gg_set_remote_packed(gg_context *c, int id, const int hdr[3], const void *src) {
+    if (!c || !hdr || !src) return fail(GG_ERR_ARG, "gg_set_remote_packed: null argument");
+    if (c->dom.empty()) return fail(GG_ERR_ARG, "gg_set_remote_packed: call gg_set_local first");
+    if (id == c->idSelf) return fail(GG_ERR_ARG, "gg_set_remote_packed: id %d is the local domain", id);
+    const int nn = hdr[0], np = hdr[1], iRoot = hdr[2];
+    if (nn < 1 || np < 0 || iRoot < 0 || iRoot >= nn) return fail(GG_ERR_ARG, "gg_set_remote_packed: nNodes=%d n=%d iRoot=%d", nn, np, iRoot);
+    CK(cudaSetDevice(c->device));
+    const size_t keepN = (size_t)c->nNodesAll, keepP = (size_t)c->nPartAll;
+    int rc;
+    if ((rc = ensure(c, c->nodes, (keepN + nn + GG_MAX_IMAGES) * sizeof(NodeW), keepN * sizeof(NodeW)))) return rc;
+    if ((rc = ensure(c, c->momf, (keepN + nn + GG_MAX_IMAGES) * 128, keepN * 128))) return rc;
+    if ((rc = ensure(c, c->momq, (keepN + nn + GG_MAX_IMAGES) * 48, keepN * 48))) return rc;
+    if ((rc = ensure(c, c->parts, (keepP + np + 1) * sizeof(PartS), keepP * sizeof(PartS)))) return rc;
+    const char *i0 = (const char *)src;
+    const char *i1 = i0 + (size_t)nn * sizeof(NodeW), *i2 = i1 + (size_t)nn * 128, *i3 = i2 + (size_t)nn * 48;
+    k_rebase_nodes<<<(nn + 255) / 256, 256, 0, c->st>>>(nn, (const NodeW *)i0, (int)keepN, (int)keepP, (NodeW *)c->nodes.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync((char *)c->momf.p + keepN * 128, i1, (size_t)nn * 128, cudaMemcpyDeviceToDevice, c->st));
+    CK(cudaMemcpyAsync((char *)c->momq.p + keepN * 48, i2, (size_t)nn * 48, cudaMemcpyDeviceToDevice, c->st));
+    CK(cudaMemcpyAsync((PartS *)c->parts.p + keepP, i3, (size_t)np * sizeof(PartS), cudaMemcpyDeviceToDevice, c->st));
+    CK(cudaStreamSynchronize(c->st)); // the source buffer belongs to the caller (next all-gather may overwrite it)
+    c->dom.push_back(Domain{id, nn, np, iRoot, (int)keepN, (int)keepP});
+    c->nNodesAll += nn;
+    c->nPartAll += np;
+    // the device records do not say how large the owner's buckets are; GG_MAX_BUCKET bounds them on every rank
     return GG_OK;
 }
 

@@ -727,8 +727,8 @@ __device__ __forceinline__ void eval_leaves(const TreeKernelArgs &A, EvalSmem &W
     while (r0 < cnt) {
         const int base = __shfl_sync(FULL, incl - np, r0);
         const unsigned mIn = __ballot_sync(FULL, lane >= r0 && lane < cnt && incl - base <= PCAP);
-        const int r1 = r0 + __popc(mIn);
-        const int nStaged = __shfl_sync(FULL, incl, r1 - 1) - base;
+        const int r1 = r0 + max(1, __popc(mIn)); // (a leaf beyond PCAP cannot exist: GG_MAX_BUCKET <= PCAP; never spin)
+        const int nStaged = min(__shfl_sync(FULL, incl, r1 - 1) - base, PCAP);
         if (lane >= r0 && lane < r1) {
             const int s0 = incl - np - base;
             W.lstart[lane] = s0; W.lpart[lane] = pl; W.limg[lane] = (unsigned char)ci;

@@ -331,12 +331,30 @@ def assemble_top(pst: PstNode, nThreads: int, summaries: np.ndarray, anc: np.nda
 
 
 # ---------------------------------------------------------------------------------------------- drivers
-def run_in_process(domains: list, exchange_trees: bool = True):
-    """All ranks inside this process (tests; several contexts on one GPU): the all-gathers are list comprehensions."""
+def run_in_process(domains: list, exchange_trees: bool = True, packed: bool = False):
+    """All ranks inside this process (tests; several contexts on one GPU): the all-gathers are list comprehensions.
+    packed=True moves the trees device to device in record layout (gg_export_local -> gg_set_remote_packed), the form
+    DistributedExchange.exchange_packed sends through NCCL."""
     summaries = np.stack([d.summary() for d in domains])
     anc = np.stack([d.ancestor_moments(summaries) for d in domains])
     for d in domains:
         d.assemble(summaries, anc)
+    if exchange_trees and packed:
+        import torch
+        for d in domains:
+            d.attach()
+        bufs = []
+        for d in domains:
+            nbytes, hdr = d.pkd.export_size()
+            b = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+            d.pkd.export_local(b.data_ptr())
+            bufs.append((b, hdr))
+        torch.cuda.synchronize()
+        for d in domains:
+            for o, (b, hdr) in zip(domains, bufs):
+                if o.idSelf != d.idSelf:
+                    d.pkd.pkdSetRemotePacked(o.idSelf, hdr, b.data_ptr())
+        return summaries, anc
     if exchange_trees and all(d.pkd is not None for d in domains):
         raws = [d.export_raw() for d in domains]
         for d in domains:
@@ -358,6 +376,7 @@ class DistributedExchange:
         self.torch, self.dist, self.d, self.dev = torch, dist, domain, backend_device
         self.world = dist.get_world_size()
         self._bufs = None
+        self._pbufs = None
 
     def _all_gather_np(self, a: np.ndarray) -> np.ndarray:
         a = np.ascontiguousarray(a)
@@ -373,10 +392,25 @@ class DistributedExchange:
         return summaries, anc
 
     def exchange(self, attach: bool = True):
-        """Steps 1-5.  Returns the bytes this rank received over the interconnect."""
+        """Steps 1-5.  Returns the bytes this rank received over the interconnect.  self.timing holds the seconds of
+        each phase of the last call (host wall clock, device work synchronised at the phase boundaries)."""
+        import time
         torch, dist, d = self.torch, self.dist, self.d
+        tm = {}
+        t0 = time.perf_counter()
+
+        def lap(name):
+            nonlocal t0
+            if self.dev != "cpu":
+                torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            tm[name] = tm.get(name, 0.0) + (t1 - t0)
+            t0 = t1
+
         self.top_tree()
+        lap("top_tree")
         dbl, ints = d.export_raw()
+        lap("export_raw")
         sizes = self._all_gather_np(np.array([dbl.size, ints.size], dtype=np.int64))
         nd, ni = int(sizes[:, 0].max()), int(sizes[:, 1].max())
         if self._bufs is None or self._bufs[2].numel() != nd or self._bufs[3].numel() != ni:
@@ -387,20 +421,92 @@ class DistributedExchange:
         fd, fi, sd, si = self._bufs
         sd[:dbl.size].copy_(torch.from_numpy(dbl), non_blocking=True)
         si[:ints.size].copy_(torch.from_numpy(ints), non_blocking=True)
+        lap("h2d")
         dist.all_gather_into_tensor(fd, sd)  # every domain padded to the largest: one collective per element type
         dist.all_gather_into_tensor(fi, si)
         gd, gi = fd.view(self.world, nd), fi.view(self.world, ni)
-        if self.dev != "cpu":
-            torch.cuda.synchronize()
+        lap("all_gather")
         if attach and d.pkd is not None:
             d.attach()
-            hosts = gi.cpu().numpy()
+            lap("attach_local")
+            hosts = gi[:, :4].cpu().numpy()
             for r in range(self.world):
                 if r == d.idSelf:
                     continue
                 if self.dev == "cpu":
-                    d.set_remote_raw(r, gd[r].numpy(), hosts[r])
+                    d.set_remote_raw(r, gd[r].numpy(), gi[r].numpy())
                 else:
                     d.set_remote_raw(r, None, hosts[r], gd[r].data_ptr(), gi[r].data_ptr())
+            lap("set_remote")
         self.gathered = (gd, gi, sizes)
+        self.timing = tm
         return int((sizes[:, 0].sum() - dbl.size) * 8 + (sizes[:, 1].sum() - ints.size) * 4)
+
+
+    def exchange_packed(self, top: bool = True):
+        """The per-step exchange on GPUs, device to device: this rank's upload (gg_set_local), then ONE padded NCCL
+        all-gather of every domain's device records (64 B walk + 128 B moment + 48 B quadrupole record per node, 32 B
+        per particle) and ingestion straight from the receive buffer (gg_set_remote_packed).  top=False reuses the
+        top tree / Ewald root of the last top_tree() call (they belong to the tree build, like pkdBuildBinary).
+        Returns the bytes this rank received over NVLink."""
+        import time
+        torch, dist, d = self.torch, self.dist, self.d
+        tm = {}
+        t0 = time.perf_counter()
+
+        def lap(name):
+            nonlocal t0
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            tm[name] = t1 - t0
+            t0 = t1
+
+        if top or d.kdTop is None:
+            self.top_tree()
+            lap("top_tree")
+        d.attach()
+        lap("attach_local")
+        nbytes, hdr = d.pkd.export_size()
+        meta = self._all_gather_np(np.array([nbytes, hdr[0], hdr[1], hdr[2]], dtype=np.int64))
+        cap = int(meta[:, 0].max())
+        cap = (cap + 255) // 256 * 256
+        if self._pbufs is None or self._pbufs[0].numel() < cap:
+            self._pbufs = (torch.empty(cap, dtype=torch.uint8, device=self.dev),
+                           torch.empty(self.world * cap, dtype=torch.uint8, device=self.dev))
+        send, recv = self._pbufs
+        cap = send.numel()
+        d.pkd.export_local(send.data_ptr())
+        lap("export")
+        dist.all_gather_into_tensor(recv, send)
+        lap("all_gather")
+        for r in range(self.world):
+            if r != d.idSelf:
+                d.pkd.pkdSetRemotePacked(r, meta[r, 1:4], recv.data_ptr() + r * cap)
+        lap("set_remote")
+        self.timing = tm
+        return int(meta[:, 0].sum() - nbytes)
+
+
+def setup_rank(p, theta: float, rank: int, world: int, device: int | None, nBucket: int = 8, iOrder: int = 4,
+               weights=None, backend_device: str | None = None):
+    """What one torch.distributed rank does before its first force evaluation (bench.py --gpus N, tests): every rank
+    holds the same particle set `p`, takes ITS share of the ORB decomposition (the host's job in a Gasoline run,
+    pstDomainDecomp pst.c:1854), builds its local tree and creates its GPU context.  Returns (pkd, exchange) where
+    exchange() runs the top-tree assembly + the tree exchange (steps 1-5 of this module) and returns the bytes this
+    rank received; with device=None no GPU context exists (host-only checks) and pkd is the host store."""
+    parts = orb_decompose(p.x, p.y, p.z, world, weights=weights)
+    idx = parts[rank]
+    d = Domain(rank, world, p.x[idx], p.y[idx], p.z[idx], p.m[idx], p.h[idx], p.period, theta, nBucket=nBucket,
+               iOrder=iOrder, pinned=device is not None, device=device)
+    d.global_index = idx[d.host.iOrderMap]  # tree position -> index in p
+    ex = DistributedExchange(d, backend_device or ("cpu" if device is None else "cuda"))
+    attach = device is not None
+
+    def exchange(top: bool = True):
+        if attach and ex.dev != "cpu":
+            return ex.exchange_packed(top=top)
+        return ex.exchange(attach=attach)
+
+    exchange.domain = d
+    exchange.driver = ex
+    return (d.pkd if d.pkd is not None else d.host), exchange

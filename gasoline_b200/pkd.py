@@ -71,6 +71,9 @@ def load_library(path: str | None = None):
     L.gg_set_local.argtypes = [C.c_void_p, C.c_int, C.POINTER(gg_tree), C.POINTER(gg_particles)]
     L.gg_set_remote.argtypes = [C.c_void_p, C.c_int, C.POINTER(gg_tree), C.POINTER(gg_particles), C.c_int]
     L.gg_clear_remote.argtypes = [C.c_void_p]
+    L.gg_export_size.argtypes = [C.c_void_p, C.POINTER(C.c_size_t), _ip]
+    L.gg_export_local.argtypes = [C.c_void_p, C.c_void_p]
+    L.gg_set_remote_packed.argtypes = [C.c_void_p, C.c_int, _ip, C.c_void_p]
     L.gg_set_top.argtypes = [C.c_void_p, C.c_int, _ip, _ip, _dp, _dp, _dp, _dp, _dp]
     L.gg_set_root_moments.argtypes = [C.c_void_p, _dp]
     L.gg_gravity.argtypes = [C.c_void_p, C.POINTER(gg_params), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -261,6 +264,21 @@ class PKD:
         tv = tree.view()
         pv = gg_particles(int(cols[0].shape[0]), *[_d(a) for a in cols], None)
         _check(self._L.gg_set_remote(self._ctx, id_, C.byref(tv), C.byref(pv), 0), "gg_set_remote")
+
+    def export_size(self):
+        """(bytes, [nNodes, nPart, iRoot]) of this domain in device record layout (gg_export_size)."""
+        nbytes, hdr = C.c_size_t(), np.zeros(3, dtype=np.int32)
+        _check(self._L.gg_export_size(self._ctx, C.byref(nbytes), _i(hdr)), "gg_export_size")
+        return int(nbytes.value), hdr
+
+    def export_local(self, device_ptr: int):
+        """Write the local domain's device records to a device buffer (the send side of an NCCL all-gather)."""
+        _check(self._L.gg_export_local(self._ctx, C.c_void_p(device_ptr)), "gg_export_local")
+
+    def pkdSetRemotePacked(self, id_: int, hdr, device_ptr: int):
+        """A remote domain from device records at device_ptr (a slice of an NCCL receive buffer)."""
+        h = np.ascontiguousarray(hdr, dtype=np.int32)
+        _check(self._L.gg_set_remote_packed(self._ctx, int(id_), _i(h), C.c_void_p(device_ptr)), "gg_set_remote_packed")
 
     def pkdDistribCells(self, pLower, bUsed, r, fMass, fSoft, fOpen2, mom):
         """pkdDistribCells (pkd.c:4376): the gathered top tree kdTop[0..nCell), heap indexed from ROOT=1."""

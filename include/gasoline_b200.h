@@ -131,6 +131,18 @@ int gg_set_top(gg_context *ctx, int nCell, const int *pLower, const int *bUsed, 
 int gg_set_remote(gg_context *ctx, int id, const gg_tree *tree, const gg_particles *part, int bDevice);
 int gg_clear_remote(gg_context *ctx);
 
+/*
+ * Multi-rank runs, device-to-device form of the same exchange (what a host with NCCL uses; no host staging).
+ * gg_export_size: bytes of this rank's domain in the DEVICE record layout (per node a 64 B walk record, a 128 B FP32
+ * moment record and a 48 B raw quadrupole; per particle a 32 B source record).  gg_export_local: write those records,
+ * section after section, to the device buffer dst (e.g. the send half of an NCCL all-gather) and wait for the copy.
+ * gg_set_remote_packed: ingest a remote domain from such a buffer (device pointer, e.g. a slice of the all-gather's
+ * receive buffer); links and particle indices are rebased on the fly.  hdr receives / supplies {nNodes, nPart, iRoot}.
+ */
+int gg_export_size(gg_context *ctx, size_t *bytes, int hdr[3]);
+int gg_export_local(gg_context *ctx, void *dst);
+int gg_set_remote_packed(gg_context *ctx, int id, const int hdr[3], const void *src);
+
 /* pkd->ilcnRoot (pkdCalcRoot/pkdDistribRoot, pkd.c:4395-4493): complete l<=4 moments of the whole box for Ewald. */
 int gg_set_root_moments(gg_context *ctx, const double root[GG_NROOT]);
 

@@ -90,6 +90,15 @@ assert nn == int(z[f"r{{o}}_nNodes"]) and n == len(io_o)
 x_o = gd[o].numpy()[(3 + 3 + 31) * nn:(3 + 3 + 31) * nn + n]  # after r[3nn] fMass fSoft fOpen2 mom[31nn]
 assert np.array_equal(x_o, p.x[io_o])
 assert nbytes == int(sizes[o, 0]) * 8 + int(sizes[o, 1]) * 4
+# bench.py's per-rank setup on the same backend: shares of the ORB decomposition are disjoint and complete
+from gasoline_b200 import ics
+q = ics.plummer(4000, seed=5)
+host, exchange = domain.setup_rank(q, 0.7, rank, world, None)
+exchange()
+cnt = torch.zeros(q.n, dtype=torch.int32); cnt[torch.from_numpy(exchange.domain.global_index.astype(np.int64))] = 1
+dist.all_reduce(cnt)
+assert int(cnt.min()) == 1 and int(cnt.max()) == 1
+assert exchange.domain.kdTop is not None and exchange.domain.ilcnRoot is not None
 dist.destroy_process_group()
 open(os.path.join(os.environ["GG_TEST_OUT"], f"rank{{rank}}.ok"), "w").write("ok")
 """

@@ -12,11 +12,12 @@ from parity import MAX_TOL, RMS_TOL
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("packed", [False, True], ids=["host-arrays", "device-records"])
 @pytest.mark.parametrize("name", NAMES)
-def test_multidomain_matches_multirank_reference(name, gpu_lib):
+def test_multidomain_matches_multirank_reference(name, packed, gpu_lib):
     p, theta, nThreads, z = load(name)
     doms = make_domains(p, theta, nThreads, z, device=0)
-    domain.run_in_process(doms)
+    domain.run_in_process(doms, packed=packed)
     g = GravityParams(nReps=1, bPeriodic=1, bEwald=1) if p.periodic else GravityParams(nReps=0, bPeriodic=0, bEwald=0)
     for r, d in enumerate(doms):
         out = d.pkd.pkdGravAll(g)
