@@ -282,6 +282,7 @@ struct WalkSmem {
     unsigned stack[GG_STACK_CAP];     // frontier: (cell << imgBits) | image
     unsigned char smask[GG_STACK_CAP]; // ... and the buckets of the group for which that cell is still undecided
     double box[GG_WALK_GB][6];  // sink boxes (active particles) of the group's buckets
+    double gbox[6];             // ... and the box around all of them
     double fSoftMax[GG_WALK_GB];
     int head[3][2], fill[3][2], cnt[3][2]; // chain state per list type (0 leaves, 1 soft, 2 Newtonian) x (shared, masked)
     int own[GG_WALK_GB];        // particles of the bucket itself met in the home image (walk.c:93)
@@ -364,14 +365,45 @@ __device__ __forceinline__ void distribute(const TreeKernelArgs &A, WalkSmem &W,
     }
     if (mAny != mSh) {
         const unsigned pm = shared ? 0u : dm;
-        for (int b = 0; b < nB; ++b) {
+#pragma unroll
+        for (int b = 0; b < GG_WALK_GB; ++b) { // (bits >= nB are never set)
             const bool has = (pm >> b) & 1u;
             const unsigned mb = __ballot_sync(FULL, has);
-            if (!mb) continue;
-            const int c = type == 0 ? __reduce_add_sync(FULL, has ? np : 0) : __popc(mb);
-            if (lane == b) { myCnt += c; myLeaves += __popc(mb); }
+            if (type == 0) {
+                if (mb) {
+                    const int c = __reduce_add_sync(FULL, has ? np : 0);
+                    if (lane == b) { myCnt += c; myLeaves += __popc(mb); }
+                }
+            } else if (lane == b) myCnt += __popc(mb);
         }
         append(A, W, type, 1, pm != 0, entry, pm, lane, lt, slab);
+    }
+}
+
+// The sink boxes of up to four buckets of <= 8 particles at once: lane = 8 * (bucket within the pass) + particle.
+// Same results as sink_box (min / max / max are exact and order-independent).
+__device__ __forceinline__ void sink_box4(const TreeKernelArgs &A, int pLower, int nP, int lane, double box[6],
+                                          double &fSoftMax) {
+    box[0] = box[1] = box[2] = 1.7976931348623157e308;
+    box[3] = box[4] = box[5] = -1.7976931348623157e308;
+    fSoftMax = 0.0;
+    const int j = lane & 7;
+    if (j < nP) {
+        const int pi = pLower + j;
+        fSoftMax = A.hsoft[pi];
+        if (A.active ? (A.active[pi] != 0) : true) {
+            const PartS p = load_part(&A.parts[pi]);
+            box[0] = box[3] = p.x; box[1] = box[4] = p.y; box[2] = box[5] = p.z;
+        }
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            box[k] = fmin(box[k], __shfl_xor_sync(FULL, box[k], o));
+            box[3 + k] = fmax(box[3 + k], __shfl_xor_sync(FULL, box[3 + k], o));
+        }
+        fSoftMax = fmax(fSoftMax, __shfl_xor_sync(FULL, fSoftMax, o));
     }
 }
 
@@ -402,21 +434,53 @@ __global__ void __launch_bounds__(GG_WALK_WARPS * 32, GG_WALK_MIN_CTAS) k_walk(c
         double gbox[6] = {1.7976931348623157e308, 1.7976931348623157e308, 1.7976931348623157e308,
                           -1.7976931348623157e308, -1.7976931348623157e308, -1.7976931348623157e308};
         double gSoftMax = 0.0;
-        for (int b = 0; b < nB; ++b) {
-            const int node = A.bucketNode[b0 + b];
-            const NodeW bk = load_node(&A.nodes[node]);
-            double box[6], fSoftMax;
-            int nAct;
-            sink_box(A, bk, lane, box, fSoftMax, nAct);
-            {
-                const double v = lane == 0 ? box[0] : lane == 1 ? box[1] : lane == 2 ? box[2] : lane == 3 ? box[3]
-                                 : lane == 4 ? box[4] : box[5];
-                if (lane < 6) W.box[b][lane] = v;
+        {
+            // lane b < nB: bucket b's node
+            int myNode = 0, myLower = 0, myNP = 0;
+            if (lane < nB) {
+                myNode = A.bucketNode[b0 + lane];
+                const int4 d = __ldg(reinterpret_cast<const int4 *>(&A.nodes[myNode]) + 3);
+                myLower = d.z; myNP = d.w;
+                W.bnode[lane] = myNode; W.own[lane] = 0;
             }
-            if (lane == 0) { W.fSoftMax[b] = fSoftMax; W.bnode[b] = node; W.own[b] = 0; }
+            const bool small = __all_sync(FULL, myNP <= 8);
+            for (int bb = 0; bb < nB; bb += 4) {
+                double box[6], fSoftMax;
+                if (small) { // four buckets per pass, eight lanes each
+                    const int b = min(bb + (lane >> 3), nB - 1);
+                    const int pl = __shfl_sync(FULL, myLower, b), np = __shfl_sync(FULL, myNP, b);
+                    sink_box4(A, pl, np, lane, box, fSoftMax);
+                    if (bb + (lane >> 3) < nB) {
+                        const int k = lane & 7;
+                        const double v = k == 0 ? box[0] : k == 1 ? box[1] : k == 2 ? box[2] : k == 3 ? box[3]
+                                         : k == 4 ? box[4] : k == 5 ? box[5] : fSoftMax;
+                        if (k < 6) W.box[b][k] = v;
+                        else if (k == 6) W.fSoftMax[b] = v;
+                    }
+                } else {
+                    for (int b = bb; b < min(bb + 4, nB); ++b) {
+                        NodeW bk;
+                        bk.pLower = __shfl_sync(FULL, myLower, b); bk.nP = __shfl_sync(FULL, myNP, b);
+                        int nAct;
+                        sink_box(A, bk, lane, box, fSoftMax, nAct);
+                        const double v = lane == 0 ? box[0] : lane == 1 ? box[1] : lane == 2 ? box[2] : lane == 3 ? box[3]
+                                         : lane == 4 ? box[4] : lane == 5 ? box[5] : fSoftMax;
+                        if (lane < 6) W.box[b][lane] = v;
+                        else if (lane == 6) W.fSoftMax[b] = v;
+                    }
+                }
+            }
+            __syncwarp();
+            for (int b = 0; b < nB; ++b) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) { gbox[k] = fmin(gbox[k], box[k]); gbox[3 + k] = fmax(gbox[3 + k], box[3 + k]); }
-            gSoftMax = fmax(gSoftMax, fSoftMax);
+                for (int k = 0; k < 3; ++k) { gbox[k] = fmin(gbox[k], W.box[b][k]); gbox[3 + k] = fmax(gbox[3 + k], W.box[b][3 + k]); }
+                gSoftMax = fmax(gSoftMax, W.fSoftMax[b]);
+            }
+            {
+                const double v = lane == 0 ? gbox[0] : lane == 1 ? gbox[1] : lane == 2 ? gbox[2] : lane == 3 ? gbox[3]
+                                 : lane == 4 ? gbox[4] : gbox[5];
+                if (lane < 6) W.gbox[lane] = v;
+            }
         }
         if (lane < 6) {
             (&W.head[0][0])[lane] = -1; (&W.fill[0][0])[lane] = 0; (&W.cnt[0][0])[lane] = 0;
@@ -452,37 +516,68 @@ __global__ void __launch_bounds__(GG_WALK_WARPS * 32, GG_WALK_MIN_CTAS) k_walk(c
             }
             __syncwarp();
             // ---- decide, per bucket of the item's mask: open / Newtonian cell / softened cell
-            unsigned mOpen = 0, mSoft = 0, mNewt = 0;
-            int img = 0, np = 0, c0 = -1, c1 = -1;
+            unsigned mOpen = 0, mSoft = 0, mNewt = 0, amb = 0;
+            int img = 0, np = 0, c0 = -1, c1 = -1, nPnode = 0;
+            double x = 0.0, y = 0.0, z = 0.0, fOpen2 = 0.0, fSoftC = 0.0;
             if (node >= 0) {
                 img = (int)(item & imgMask);
                 const NodeW nd = load_node_smem(&W.nstage[lane * NSTRIDE]);
-                const double x = nd.rx + s_off[3 * img], y = nd.ry + s_off[3 * img + 1], z = nd.rz + s_off[3 * img + 2];
+                x = nd.rx + s_off[3 * img]; y = nd.ry + s_off[3 * img + 1]; z = nd.rz + s_off[3 * img + 2];
+                fOpen2 = nd.fOpen2; fSoftC = nd.fSoft; c0 = nd.c0; c1 = nd.c1; nPnode = nd.nP;
                 if (nd.nP < 4) mOpen = mask; // walk.c:81 (pUpper - pLower < 3)
-                else if (near_dist2(gbox, x, y, z) <= nd.fOpen2) { // else: no bucket inside the group box opens it
-                    if (far_dist2(gbox, x, y, z) <= nd.fOpen2) mOpen = mask; // every bucket inside the group box does
-                    else
-                        for (unsigned mm = mask; mm; mm &= mm - 1) {
-                            const int b = __ffs(mm) - 1;
-                            if (intersect_np(W.box[b], nd.fOpen2, x, y, z)) mOpen |= 1u << b;
-                        }
+                else if (near_dist2(W.gbox, x, y, z) <= fOpen2) { // else: no bucket inside the group box opens it
+                    if (far_dist2(W.gbox, x, y, z) <= fOpen2) mOpen = mask; // every bucket inside the group box does
+                    else amb = mask;                                      // the buckets have to be asked one by one
                 }
+            }
+            // the per-bucket tests of all lanes, spread over the warp: one (item, bucket) pair per lane and round
+            {
+                const int na = __popc(amb);
+                int incl = na;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const int nPairs = __shfl_sync(FULL, incl, 31);
+                if (nPairs > 0) {
+                    __syncwarp(); // every lane has its record out of nstage: reuse it as scratch
+                    double *tq = reinterpret_cast<double *>(W.nstage);                 // [32][4] x, y, z, fOpen2
+                    unsigned char *pairs = reinterpret_cast<unsigned char *>(tq + 128); // [<= 32 * 8]
+                    unsigned *mres = reinterpret_cast<unsigned *>(pairs + 256);        // [32]
+                    mres[lane] = 0u;
+                    if (amb) {
+                        tq[4 * lane] = x; tq[4 * lane + 1] = y; tq[4 * lane + 2] = z; tq[4 * lane + 3] = fOpen2;
+                        int o = incl - na;
+                        for (unsigned mm = amb; mm; mm &= mm - 1) pairs[o++] = (unsigned char)((lane << 3) | (__ffs(mm) - 1));
+                    }
+                    __syncwarp();
+                    for (int p = lane; p < nPairs; p += 32) {
+                        const int pr = pairs[p], o = pr >> 3, b = pr & 7;
+                        if (intersect_np(W.box[b], tq[4 * o + 3], tq[4 * o], tq[4 * o + 1], tq[4 * o + 2]))
+                            atomicOr(&mres[o], 1u << b);
+                    }
+                    __syncwarp();
+                    if (amb) mOpen = mres[lane];
+                    __syncwarp();
+                }
+            }
+            if (node >= 0) {
                 const unsigned mAcc = mask & ~mOpen;
                 if (mAcc) { // walk.c:118-127
-                    double t2 = nd.fSoft + gSoftMax;
+                    double t2 = fSoftC + gSoftMax;
                     t2 = __dmul_rn(t2, t2);
-                    if (!(t2 < nd.fOpen2)) // (fSoft + fSoftMax_b)^2 <= t2 for every bucket: only then can one be soft
+                    if (!(t2 < fOpen2)) // (fSoft + fSoftMax_b)^2 <= t2 for every bucket: only then can one be soft
                         for (unsigned mm = mAcc; mm; mm &= mm - 1) {
                             const int b = __ffs(mm) - 1;
-                            double twoh2 = nd.fSoft + W.fSoftMax[b];
+                            double twoh2 = fSoftC + W.fSoftMax[b];
                             twoh2 = __dmul_rn(twoh2, twoh2);
-                            if (!(twoh2 < nd.fOpen2) && intersect_np(W.box[b], twoh2, x, y, z)) mSoft |= 1u << b;
+                            if (!(twoh2 < fOpen2) && intersect_np(W.box[b], twoh2, x, y, z)) mSoft |= 1u << b;
                         }
                     mNewt = mAcc & ~mSoft;
                 }
-                c0 = nd.c0; c1 = nd.c1;
                 if (mOpen && c0 < 0) { // an opened bucket: all its particles are sources (walk.c:93-114)
-                    np = nd.nP;
+                    np = nPnode;
                     if (img == A.homeImage)
                         for (unsigned mm = mOpen; mm; mm &= mm - 1) {
                             const int b = __ffs(mm) - 1;
