@@ -694,11 +694,11 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
                 return fail(GG_ERR_NOMEM, "gg_gravity: interaction lists need %zu blocks (> 2^31 references)", c->capBlocks);
             if ((rc = ensure(c, c->pool, c->capBlocks * 32 * sizeof(unsigned)))) return rc;
             if ((rc = ensure(c, c->nextblk, c->capBlocks * sizeof(int)))) return rc;
-            if ((rc = ensure(c, c->poolmask, c->capBlocks * 32))) return rc;
+            if ((rc = ensure(c, c->poolmask, c->capBlocks * 32 * sizeof(gg_mask_t)))) return rc;
         }
         ta.pool = (unsigned *)c->pool.p;
         ta.nextBlk = (int *)c->nextblk.p;
-        ta.poolMask = (unsigned char *)c->poolmask.p;
+        ta.poolMask = (gg_mask_t *)c->poolmask.p;
         ta.capBlocks = (int)c->capBlocks;
         CK(gg_launch_walk_kernel(ta, c->nSM, c->st));
         ++c->nLaunches;

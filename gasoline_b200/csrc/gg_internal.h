@@ -25,7 +25,12 @@
 #define GG_WALK_MIN_CTAS 4   // 32 warps per SM (register cap 64)
 #define GG_SLAB_BLOCKS 32    // list blocks a warp takes from the pool per atomic
 #ifndef GG_WALK_GB
-#define GG_WALK_GB 6         // sink buckets that share one tree traversal in k_walk (<= 8: one mask byte per frontier item)
+#define GG_WALK_GB 10        // sink buckets that share one tree traversal in k_walk (<= 16: one mask bit per bucket)
+#endif
+#if GG_WALK_GB <= 8
+typedef unsigned char gg_mask_t;  // bucket mask of a frontier item / of a masked list entry
+#else
+typedef unsigned short gg_mask_t;
 #endif
 #define GG_MAX_SINKS 8      // sinks evaluated per warp pass (accumulators live in registers)
 #define GG_STACK_CAP 512    // walk frontier entries per warp
@@ -75,7 +80,7 @@ struct TreeKernelArgs {
     int *nextBlk;            // [capBlocks]
     int capBlocks;
     int *poolCursor;         // blocks handed out (may exceed capBlocks: the host then grows the pool and reruns)
-    unsigned char *poolMask; // [capBlocks][32] masked chains: which buckets of the walk group the entry belongs to
+    gg_mask_t *poolMask;     // [capBlocks][32] masked chains: which buckets of the walk group the entry belongs to
     int *groupHead;          // [nWalkGroups][3 list types][2]: chain shared by every bucket of the group, masked chain
     int *groupCnt;           // [nWalkGroups][3][2] entries in each chain
     // per-bucket contiguous lists (k_scatter output, k_eval input), indexed by bucket ordinal

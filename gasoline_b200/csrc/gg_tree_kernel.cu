@@ -280,7 +280,7 @@ __device__ __forceinline__ void sink_box(const TreeKernelArgs &A, const NodeW &b
 struct WalkSmem {
     uint4 nstage[32 * NSTRIDE]; // the 32 node records of the current step, fetched cooperatively (4 lanes per record)
     unsigned stack[GG_STACK_CAP];     // frontier: (cell << imgBits) | image
-    unsigned char smask[GG_STACK_CAP]; // ... and the buckets of the group for which that cell is still undecided
+    gg_mask_t smask[GG_STACK_CAP];     // ... and the buckets of the group for which that cell is still undecided
     double box[GG_WALK_GB][6];  // sink boxes (active particles) of the group's buckets
     double gbox[6];             // ... and the box around all of them
     double fSoftMax[GG_WALK_GB];
@@ -335,7 +335,7 @@ __device__ __forceinline__ void append(const TreeKernelArgs &A, WalkSmem &W, int
         if (pos >= room) at = (size_t)nb * 32 + (pos - room);
         if (pos < room || fits) {
             A.pool[at] = entry;
-            if (d) A.poolMask[at] = (unsigned char)mask;
+            if (d) A.poolMask[at] = (gg_mask_t)mask;
         }
     }
     if (lane == 0) {
@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(GG_WALK_WARPS * 32, GG_WALK_MIN_CTAS) k_walk(c
         int nStack = A.nImages;
         for (int i = lane; i < A.nImages; i += 32) {
             W.stack[i] = ((unsigned)A.rootNode << A.imgBits) | (unsigned)i;
-            W.smask[i] = (unsigned char)all;
+            W.smask[i] = (gg_mask_t)all;
         }
         __syncwarp();
 
@@ -543,17 +543,18 @@ __global__ void __launch_bounds__(GG_WALK_WARPS * 32, GG_WALK_MIN_CTAS) k_walk(c
                 if (nPairs > 0) {
                     __syncwarp(); // every lane has its record out of nstage: reuse it as scratch
                     double *tq = reinterpret_cast<double *>(W.nstage);                 // [32][4] x, y, z, fOpen2
-                    unsigned char *pairs = reinterpret_cast<unsigned char *>(tq + 128); // [<= 32 * 8]
-                    unsigned *mres = reinterpret_cast<unsigned *>(pairs + 256);        // [32]
+                    unsigned short *pairs = reinterpret_cast<unsigned short *>(tq + 128); // [<= 32 * GG_WALK_GB]
+                    unsigned *mres = reinterpret_cast<unsigned *>(pairs + 32 * GG_WALK_GB); // [32]
+                    static_assert(1024 + 64 * GG_WALK_GB + 128 <= sizeof(W.nstage), "pair scratch must fit the node stage");
                     mres[lane] = 0u;
                     if (amb) {
                         tq[4 * lane] = x; tq[4 * lane + 1] = y; tq[4 * lane + 2] = z; tq[4 * lane + 3] = fOpen2;
                         int o = incl - na;
-                        for (unsigned mm = amb; mm; mm &= mm - 1) pairs[o++] = (unsigned char)((lane << 3) | (__ffs(mm) - 1));
+                        for (unsigned mm = amb; mm; mm &= mm - 1) pairs[o++] = (unsigned short)((lane << 4) | (__ffs(mm) - 1));
                     }
                     __syncwarp();
                     for (int p = lane; p < nPairs; p += 32) {
-                        const int pr = pairs[p], o = pr >> 3, b = pr & 7;
+                        const int pr = pairs[p], o = pr >> 4, b = pr & 15;
                         if (intersect_np(W.box[b], tq[4 * o + 3], tq[4 * o], tq[4 * o + 1], tq[4 * o + 2]))
                             atomicOr(&mres[o], 1u << b);
                     }
@@ -593,8 +594,8 @@ __global__ void __launch_bounds__(GG_WALK_WARPS * 32, GG_WALK_MIN_CTAS) k_walk(c
                 if (pos + 1 < GG_STACK_CAP) {
                     W.stack[pos] = c1 >= 0 ? (((unsigned)c1 << A.imgBits) | (unsigned)img) : 0xffffffffu;
                     W.stack[pos + 1] = ((unsigned)c0 << A.imgBits) | (unsigned)img;
-                    W.smask[pos] = (unsigned char)mOpen;
-                    W.smask[pos + 1] = (unsigned char)mOpen;
+                    W.smask[pos] = (gg_mask_t)mOpen;
+                    W.smask[pos + 1] = (gg_mask_t)mOpen;
                 } else atomicExch(A.errFlag, 1);
             }
             nStack += 2 * __popc(mPush);
@@ -621,50 +622,48 @@ __global__ void __launch_bounds__(GG_WALK_WARPS * 32, GG_WALK_MIN_CTAS) k_walk(c
     }
 }
 
-// ------------------------------------------------------------------------------------------------ k_eval
 // ------------------------------------------------------------------------------------------------ k_scatter
-// One warp per walk group: copy the group's chains into the contiguous per-bucket lists k_eval streams through
-// (shared entries to every bucket of the group, masked entries to the buckets of their mask).  Bucket b's lists
-// start at bucketOff[b]: Newtonian cells, then softened cells, then leaves.
+// One warp per (walk group, list type, chain): copy the chain into the contiguous per-bucket lists k_eval streams
+// through (shared entries to every bucket of the group, masked entries to the buckets of their mask).  Bucket b's
+// lists start at bucketOff[b]: Newtonian cells, then softened cells, then leaves; within a type the group's shared
+// entries come first, so all six warps of a group know where to write without talking to each other.
 __global__ void __launch_bounds__(256) k_scatter(const TreeKernelArgs A) {
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const int nGroups = (A.nBuckets + GG_WALK_GB - 1) / GG_WALK_GB;
-    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int g = w / 6, sub = w - 6 * g, type = sub >> 1, src = sub & 1;
     if (g >= nGroups) return;
+    int blk = A.groupHead[6 * g + 2 * type + src];
+    if (blk < 0) return;
+    const int total = A.groupCnt[6 * g + 2 * type + src];
     const int b0 = g * GG_WALK_GB, nB = min(GG_WALK_GB, A.nBuckets - b0);
     const unsigned all = (1u << nB) - 1u;
-    // lane b < nB: write cursor of bucket b, advanced type by type (2 Newtonian, 1 softened, 0 leaves)
-    long long cursor = lane < nB ? A.bucketOff[b0 + lane] : 0;
-    int c0 = 0, c1 = 0, c2 = 0;
-    if (lane < nB) { c0 = A.bucketCnt[3 * (b0 + lane)]; c1 = A.bucketCnt[3 * (b0 + lane) + 1]; c2 = A.bucketCnt[3 * (b0 + lane) + 2]; }
-#pragma unroll 1
-    for (int type = 2; type >= 0; --type) {
-        long long cur = cursor;
-#pragma unroll 1
-        for (int src = 0; src < 2; ++src) {
-            int blk = A.groupHead[6 * g + 2 * type + src];
-            const int total = A.groupCnt[6 * g + 2 * type + src];
-            int cnt = total > 0 ? total - 32 * ((total - 1) / 32) : 0; // the head block is the partial one
-            while (blk >= 0) {
-                unsigned it = 0, mk = 0;
-                if (lane < cnt) {
-                    it = A.pool[(size_t)blk * 32 + lane];
-                    mk = src ? A.poolMask[(size_t)blk * 32 + lane] : all;
-                }
-                blk = A.nextBlk[blk];
-                cnt = 32;
-                for (int b = 0; b < nB; ++b) {
-                    const bool has = (mk >> b) & 1u;
-                    const unsigned m = __ballot_sync(FULL, has);
-                    if (!m) continue;
-                    const long long base = __shfl_sync(FULL, cur, b);
-                    if (has) A.lists[base + __popc(m & lt)] = it;
-                    if (lane == b) cur += __popc(m);
-                }
-            }
+    // lane b < nB: write cursor of bucket b
+    long long cur = 0;
+    if (lane < nB) {
+        const int *e = &A.bucketCnt[3 * (b0 + lane)];
+        cur = A.bucketOff[b0 + lane] + (type <= 1 ? e[2] : 0) + (type == 0 ? e[1] : 0) +
+              (src ? A.groupCnt[6 * g + 2 * type] : 0);
+    }
+    int cnt = total - 32 * ((total - 1) / 32); // the head block is the partial one
+    while (blk >= 0) {
+        unsigned it = 0, mk = 0;
+        if (lane < cnt) {
+            it = A.pool[(size_t)blk * 32 + lane];
+            mk = src ? (unsigned)A.poolMask[(size_t)blk * 32 + lane] : all;
         }
-        cursor += type == 2 ? c2 : (type == 1 ? c1 : c0);
+        blk = A.nextBlk[blk];
+        cnt = 32;
+#pragma unroll 2
+        for (int b = 0; b < nB; ++b) {
+            const bool has = (mk >> b) & 1u;
+            const unsigned m = __ballot_sync(FULL, has);
+            if (!m) continue;
+            const long long base = __shfl_sync(FULL, cur, b);
+            if (has) A.lists[base + __popc(m & lt)] = it;
+            if (lane == b) cur += __popc(m);
+        }
     }
 }
 
@@ -1016,7 +1015,7 @@ cudaError_t gg_launch_scatter_kernel(const TreeKernelArgs &a, int nSM, cudaStrea
     (void)nSM;
     const int nGroups = (a.nBuckets + GG_WALK_GB - 1) / GG_WALK_GB;
     if (nGroups <= 0) return cudaSuccess;
-    k_scatter<<<(nGroups + 7) / 8, 256, 0, st>>>(a);
+    k_scatter<<<(6 * nGroups + 7) / 8, 256, 0, st>>>(a);
     return cudaGetLastError();
 }
 
