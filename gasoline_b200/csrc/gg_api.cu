@@ -683,6 +683,7 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
     ta.iOrder = prm->iOrder;
     ta.maxBucket = c->maxBucket;
     ta.walkOnly = walkOnly ? 1 : 0;
+    ta.mono64 = prm->bPeriodic ? 1 : 0;
     ta.acc = (double *)c->acc.p;
     ta.pot = (double *)c->pot.p;
     ta.dtg = (double *)c->dtg.p;

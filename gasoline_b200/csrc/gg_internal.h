@@ -94,6 +94,7 @@ struct TreeKernelArgs {
     int iOrder;
     int maxBucket;           // largest particle count of any bucket (sizes the particle buffer)
     int walkOnly;
+    int mono64;              // k_eval: cell monopoles in FP64 (periodic boxes, see eval_cells)
     // outputs (local particles, tree order)
     double *acc;             // [n][3]
     double *pot;

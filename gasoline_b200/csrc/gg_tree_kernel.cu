@@ -101,15 +101,17 @@ struct CellMom {
 // Reduced-multipole evaluation of one Newtonian cell on one sink (QEVAL qeval.h:21-64 + gam[] grav.c:172-191),
 // restructured around scaled monomials so every moment is used in exactly one FMA per force component.
 // Returns the contribution (fx,fy,fz) to the acceleration, fp to -potential and 1/dt^2.
-template <int ORDER>
+// MONO64: leave the monopole term out (the caller adds it in FP64, see eval_cells) and hand back the FP32 1/r.
+template <int ORDER, bool MONO64 = false>
 __device__ __forceinline__ void cell_on_sink(const CellMom &c, float M, float dx, float dy, float dz, float ms,
-                                             float &ox_, float &oy_, float &oz_, float &op_, float &odt) {
+                                             float &ox_, float &oy_, float &oz_, float &op_, float &odt, float *pg0 = nullptr) {
     const float xx = dx * dx, yy = dy * dy, zz = dz * dz;
     const float d2 = xx + yy + zz;
     const float g0 = rsqrt_nr(d2);
     const float dir2 = g0 * g0;
     const float g1 = g0 * dir2;
-    float fx = 0.f, fy = 0.f, fz = 0.f, ta = g1 * M, fp = g0 * M;
+    float fx = 0.f, fy = 0.f, fz = 0.f, ta = MONO64 ? 0.f : g1 * M, fp = MONO64 ? 0.f : g0 * M;
+    if (MONO64) *pg0 = g0;
     if (ORDER >= 2) {
         const float g2 = 3.f * g1 * dir2, g3 = 5.f * g2 * dir2;
         const float Qxx = c.m0.x, Qyy = c.m0.y, Qzz = c.m0.z, Qxy = c.m0.w, Qxz = c.m1.x, Qyz = c.m1.y;
@@ -669,10 +671,13 @@ __global__ void __launch_bounds__(256) k_scatter(const TreeKernelArgs A) {
 
 // ------------------------------------------------------------------------------------------------ k_eval
 #define PCAP (32 * CSTRIDE / PSTRIDE) // particles staged at once (96)
-struct EvalSmem {
+template <int NRAW>
+struct EvalSmemT {
     float4 stage[2][32 * CSTRIDE]; // double-buffered staged block; [0] also the sink hand-out / final reduction scratch
     union {
-        double raw[32 * 4];        // cells: FP64 (x, y, z, M) of the block in flight, converted to sink-centred FP32 on arrival
+        // cells: FP64 (x, y, z, M) of the block in flight, converted to sink-centred FP32 on arrival.  NRAW = 2 (MONO64):
+        // double-buffered like `stage`, and the conversion leaves the FP64 sink-centred position behind for the hot loop
+        double raw[NRAW][32 * 4];
         struct {                   // leaves (never in flight together with cells)
             int lstart[32], lpart[32]; // first staging slot and first particle of each leaf of the batch
             unsigned char owner[PCAP]; // staging slot -> leaf of the batch
@@ -692,6 +697,7 @@ struct Sink {
     int sidx;
     float ax, ay, az, ap, dtm;
     double dax, day, daz, dap;
+    double sxd, syd, szd; // MONO64 only: the sink's position relative to the bucket centre in FP64
     __device__ __forceinline__ void fold() { // FP32 partial sums of one block -> FP64
         dax += (double)ax; day += (double)ay; daz += (double)az; dap += (double)ap;
         ax = ay = az = ap = 0.f;
@@ -708,14 +714,14 @@ struct EvalCtx {
 // Start the asynchronous gather of one block of <= 32 Newtonian cells (entry `it` per lane, lanes < cnt) into stage
 // buffer `buf`: the FP64 (x,y,z,M) half of the walk record by its own lane, the 128 B FP32 moment record
 // COALESCED, LPR lanes per record (a warp-wide 16 B access touches 32/LPR lines instead of 32).
-template <int ORDER>
-__device__ __forceinline__ void gather_cells(const TreeKernelArgs &A, EvalSmem &W, int buf, unsigned it, int cnt, int lane) {
+template <int ORDER, class SM>
+__device__ __forceinline__ void gather_cells(const TreeKernelArgs &A, SM &W, int buf, int rbuf, unsigned it, int cnt, int lane) {
     int cn = 0;
     if (lane < cnt) {
         cn = (int)(it >> A.imgBits);
         const char *src = reinterpret_cast<const char *>(&A.nodes[cn]);
-        cp_async_cg16(&W.raw[4 * lane], src);
-        cp_async_cg16(&W.raw[4 * lane + 2], src + 16);
+        cp_async_cg16(&W.raw[rbuf][4 * lane], src);
+        cp_async_cg16(&W.raw[rbuf][4 * lane + 2], src + 16);
     }
     if (ORDER >= 2) {
         constexpr int LPR = ORDER == 2 ? 2 : (ORDER == 3 ? 4 : 8); // float4 pieces of the record in use
@@ -733,66 +739,70 @@ __device__ __forceinline__ void gather_cells(const TreeKernelArgs &A, EvalSmem &
 // The Newtonian-cell list (ILCN) of the bucket: n entries at L.  Software pipeline: while block i is evaluated
 // (QEVAL to ORDER), block i+1 is being gathered into the other stage buffer and the entries of block i+2 are
 // being loaded.
-template <int ORDER>
-__device__ __forceinline__ void eval_cells(const TreeKernelArgs &A, EvalSmem &W, const double *s_off, const EvalCtx &E,
+//
+// MONO64 (periodic boxes): the monopole term of every cell is evaluated in FP64.  In a nearly uniform periodic box the
+// 27 image sums cancel to a small net force and potential (|a_net| << sum |a_term|, |phi| ~ 1e-3 of the tree sum), so
+// the FP32 rounding of the big far-image monopoles (1e-7 each) is what limits the result, and the smaller the
+// perturbations (the larger the box in particles, at fixed displacement in grid units) the worse.  One FP64 Newton
+// step on the FP32 1/r against the FP64 displacement (19 DFMA-pipe instructions per pair) removes that error; the
+// quadrupole and higher terms (<= ~10 % of the monopole, FP32) stay as they are.
+template <int ORDER, bool MONO64, class SM>
+__device__ __forceinline__ void eval_cells(const TreeKernelArgs &A, SM &W, const double *s_off, const EvalCtx &E,
                                            Sink &K, const unsigned *L, int n, int lane) {
     if (n <= 0) return;
     const int nBlk = (n + 31) >> 5;
     unsigned itCur = lane < n ? L[lane] : 0u;
-    gather_cells<ORDER>(A, W, 0, itCur, min(32, n), lane);
+    gather_cells<ORDER>(A, W, 0, 0, itCur, min(32, n), lane);
     unsigned itNext = 32 + lane < n ? L[32 + lane] : 0u;
 #pragma unroll 1
     for (int i = 0; i < nBlk; ++i) {
-        const int buf = i & 1, cnt = min(32, n - 32 * i);
+        const int buf = i & 1, rbuf = MONO64 ? buf : 0, cnt = min(32, n - 32 * i);
         cp_async_wait_all();
         __syncwarp();
         if (lane < cnt) { // FP64 subtraction of the sink-bucket centre, then FP32
             const int ci = (int)(itCur & E.imgMask);
-            const double2 p01 = *reinterpret_cast<const double2 *>(&W.raw[4 * lane]);
-            const double2 p23 = *reinterpret_cast<const double2 *>(&W.raw[4 * lane + 2]);
-            W.stage[buf][lane * CSTRIDE] =
-                make_float4((float)((p01.x + s_off[3 * ci]) - E.cenx), (float)((p01.y + s_off[3 * ci + 1]) - E.ceny),
-                            (float)((p23.x + s_off[3 * ci + 2]) - E.cenz), (float)p23.y);
+            const double2 p01 = *reinterpret_cast<const double2 *>(&W.raw[rbuf][4 * lane]);
+            const double2 p23 = *reinterpret_cast<const double2 *>(&W.raw[rbuf][4 * lane + 2]);
+            const double rx = (p01.x + s_off[3 * ci]) - E.cenx, ry = (p01.y + s_off[3 * ci + 1]) - E.ceny,
+                         rz = (p23.x + s_off[3 * ci + 2]) - E.cenz;
+            W.stage[buf][lane * CSTRIDE] = make_float4((float)rx, (float)ry, (float)rz, (float)p23.y);
+            if (MONO64) {
+                *reinterpret_cast<double2 *>(&W.raw[rbuf][4 * lane]) = make_double2(rx, ry);
+                W.raw[rbuf][4 * lane + 2] = rz;
+            }
         }
         __syncwarp();
         if (i + 1 < nBlk) {
-            gather_cells<ORDER>(A, W, buf ^ 1, itNext, min(32, n - 32 * (i + 1)), lane);
+            gather_cells<ORDER>(A, W, buf ^ 1, MONO64 ? buf ^ 1 : 0, itNext, min(32, n - 32 * (i + 1)), lane);
             itCur = itNext;
             const int k = 32 * (i + 2) + lane;
             itNext = k < n ? L[k] : 0u;
         }
         if (E.worker) {
-            auto load_cell = [&](int j, float4 &pc, CellMom &c) {
+            for (int j = E.q; j < cnt; j += E.G) {
                 const float4 *S = &W.stage[buf][j * CSTRIDE];
-                pc = S[0];
+                const float4 pc = S[0];
+                CellMom c;
                 c.m0 = S[1]; c.m1 = S[2];
                 if (ORDER >= 3) { c.m2 = S[3]; c.m3 = S[4]; }
                 if (ORDER >= 4) { c.m4 = S[5]; c.m5 = S[6]; c.m6 = S[7]; c.m7 = S[8]; }
-            };
-            int j = E.q;
-#if GG_CELL_UNROLL >= 2
-            // two cells per trip in ONE basic block: the second cell's independent work fills the issue slots the
-            // first one's serial 1/r chain (MUFU.RSQ -> Newton step -> g0..g5) leaves empty, and vice versa
-            for (; j + E.G < cnt; j += 2 * E.G) {
-                float4 pa, pb;
-                CellMom ca, cb;
-                load_cell(j, pa, ca);
-                load_cell(j + E.G, pb, cb);
-                float fx, fy, fz, fp, fdt, gx, gy, gz, gp, gdt;
-                cell_on_sink<ORDER>(ca, pa.w, K.sx - pa.x, K.sy - pa.y, K.sz - pa.z, K.ms, fx, fy, fz, fp, fdt);
-                cell_on_sink<ORDER>(cb, pb.w, K.sx - pb.x, K.sy - pb.y, K.sz - pb.z, K.ms, gx, gy, gz, gp, gdt);
-                K.ax += fx + gx; K.ay += fy + gy; K.az += fz + gz; K.ap -= fp + gp;
-                K.dtm = fmaxf(K.dtm, fmaxf(fdt, gdt));
-            }
-#endif
-            for (; j < cnt; j += E.G) {
-                float4 pc;
-                CellMom c;
-                load_cell(j, pc, c);
-                float fx, fy, fz, fp, fdt;
-                cell_on_sink<ORDER>(c, pc.w, K.sx - pc.x, K.sy - pc.y, K.sz - pc.z, K.ms, fx, fy, fz, fp, fdt);
+                float fx, fy, fz, fp, fdt, g0;
+                cell_on_sink<ORDER, MONO64>(c, pc.w, K.sx - pc.x, K.sy - pc.y, K.sz - pc.z, K.ms, fx, fy, fz, fp, fdt, &g0);
                 K.ax += fx; K.ay += fy; K.az += fz; K.ap -= fp;
                 K.dtm = fmaxf(K.dtm, fdt);
+                if (MONO64) {
+                    const double2 q01 = *reinterpret_cast<const double2 *>(&W.raw[rbuf][4 * j]);
+                    const double2 q23 = *reinterpret_cast<const double2 *>(&W.raw[rbuf][4 * j + 2]);
+                    const double ddx = K.sxd - q01.x, ddy = K.syd - q01.y, ddz = K.szd - q23.x;
+                    const double d2 = ddx * ddx + ddy * ddy + ddz * ddz;
+                    const double y = (double)g0;
+                    const double e = fma(-(d2 * y), y, 1.0); // 1 - d2 y^2: what the FP32 1/r (and FP32 dx) got wrong
+                    const double w = fma(0.5 * y, e, y);     // one Newton step: 1/r to ~1e-14
+                    const double Mw = q23.y * w;
+                    const double Mw3 = Mw * (w * w);
+                    K.dap -= Mw;
+                    K.dax -= ddx * Mw3; K.day -= ddy * Mw3; K.daz -= ddz * Mw3;
+                }
             }
         }
         K.fold();
@@ -802,7 +812,8 @@ __device__ __forceinline__ void eval_cells(const TreeKernelArgs &A, EvalSmem &W,
 
 // <= 32 opened source BUCKETS (leaves), each standing for all its particles -- incl. the sink bucket itself
 // (intra-bucket pairs, grav.c:211-242).  SPLINE-softened monopoles (ILP, grav.c:89-108).
-__device__ __forceinline__ void eval_leaves(const TreeKernelArgs &A, EvalSmem &W, const double *s_off, const EvalCtx &E,
+template <class SM>
+__device__ __forceinline__ void eval_leaves(const TreeKernelArgs &A, SM &W, const double *s_off, const EvalCtx &E,
                                             Sink &K, unsigned it, int cnt, int lane) {
     int np = 0, pl = 0, ci = 0;
     if (lane < cnt) {
@@ -880,8 +891,9 @@ __device__ __noinline__ SoftTerm eval_soft(const NodeW *nodes, const double *mom
 }
 
 // One warp per (bucket, pass of <= 8 active sinks), streaming through the bucket's three contiguous lists.
-template <int ORDER>
-__global__ void __launch_bounds__(GG_WARPS_PER_CTA * 32, GG_MIN_CTAS) k_eval(const TreeKernelArgs A) {
+template <int ORDER, bool MONO64>
+__global__ void __launch_bounds__(GG_WARPS_PER_CTA * 32, MONO64 ? GG_MIN_CTAS - 1 : GG_MIN_CTAS) k_eval(const TreeKernelArgs A) {
+    typedef EvalSmemT<MONO64 ? 2 : 1> EvalSmem;
     extern __shared__ __align__(16) unsigned char eval_smem_raw[];
     EvalSmem *s_w = reinterpret_cast<EvalSmem *>(eval_smem_raw);
     double *s_off = reinterpret_cast<double *>(s_w + GG_WARPS_PER_CTA);
@@ -926,6 +938,7 @@ __global__ void __launch_bounds__(GG_WARPS_PER_CTA * 32, GG_MIN_CTAS) k_eval(con
                     const PartS p = load_part(&A.parts[pi]);
                     W.stage[0][rank] = make_float4((float)(p.x - E.cenx), (float)(p.y - E.ceny), (float)(p.z - E.cenz), p.m);
                     W.stage[0][GG_MAX_SINKS + rank] = make_float4(p.h, __int_as_float(pi), 0.f, 0.f);
+                    if (MONO64) { W.raw[0][4 * rank] = p.x - E.cenx; W.raw[0][4 * rank + 1] = p.y - E.ceny; W.raw[0][4 * rank + 2] = p.z - E.cenz; }
                 }
                 seen += __popc(m);
             }
@@ -936,6 +949,8 @@ __global__ void __launch_bounds__(GG_WARPS_PER_CTA * 32, GG_MIN_CTAS) k_eval(con
             const float4 sk = W.stage[0][sI], sk2 = W.stage[0][GG_MAX_SINKS + sI];
             K.sx = sk.x; K.sy = sk.y; K.sz = sk.z; K.ms = sk.w; K.hs = sk2.x;
             K.sidx = __float_as_int(sk2.y);
+            K.sxd = K.syd = K.szd = 0.0;
+            if (MONO64) { K.sxd = W.raw[0][4 * sI]; K.syd = W.raw[0][4 * sI + 1]; K.szd = W.raw[0][4 * sI + 2]; }
         }
         K.ax = K.ay = K.az = K.ap = K.dtm = 0.f;
         K.dax = K.day = K.daz = K.dap = 0.0;
@@ -943,7 +958,7 @@ __global__ void __launch_bounds__(GG_WARPS_PER_CTA * 32, GG_MIN_CTAS) k_eval(con
         const int nLeaf = A.bucketCnt[3 * task.ord], nSoft = A.bucketCnt[3 * task.ord + 1], nNewt = A.bucketCnt[3 * task.ord + 2];
         const unsigned *L = A.lists + A.bucketOff[task.ord];
 
-        eval_cells<ORDER>(A, W, s_off, E, K, L, nNewt, lane);
+        eval_cells<ORDER, MONO64>(A, W, s_off, E, K, L, nNewt, lane);
         L += nNewt;
         for (int i = 0; i < nSoft; i += 32) {
             const int cnt = min(32, nSoft - i);
@@ -1019,17 +1034,28 @@ cudaError_t gg_launch_scatter_kernel(const TreeKernelArgs &a, int nSM, cudaStrea
     return cudaGetLastError();
 }
 
-size_t gg_eval_kernel_smem() { return GG_WARPS_PER_CTA * sizeof(EvalSmem) + GG_MAX_IMAGES * 3 * sizeof(double); }
+size_t gg_eval_kernel_smem(int mono64) {
+    return GG_WARPS_PER_CTA * (mono64 ? sizeof(EvalSmemT<2>) : sizeof(EvalSmemT<1>)) + GG_MAX_IMAGES * 3 * sizeof(double);
+}
 
 cudaError_t gg_launch_eval_kernel(const TreeKernelArgs &a, int nSM, cudaStream_t st) {
     void (*fn)(const TreeKernelArgs) = nullptr;
-    switch (a.iOrder) {
-    case 1: fn = k_eval<1>; break;
-    case 2: fn = k_eval<2>; break;
-    case 3: fn = k_eval<3>; break;
-    default: fn = k_eval<4>; break;
+    if (a.mono64) {
+        switch (a.iOrder) {
+        case 1: fn = k_eval<1, true>; break;
+        case 2: fn = k_eval<2, true>; break;
+        case 3: fn = k_eval<3, true>; break;
+        default: fn = k_eval<4, true>; break;
+        }
+    } else {
+        switch (a.iOrder) {
+        case 1: fn = k_eval<1, false>; break;
+        case 2: fn = k_eval<2, false>; break;
+        case 3: fn = k_eval<3, false>; break;
+        default: fn = k_eval<4, false>; break;
+        }
     }
-    const size_t smem = gg_eval_kernel_smem();
+    const size_t smem = gg_eval_kernel_smem(a.mono64);
     cudaError_t e = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int grid = grid_for((const void *)fn, GG_WARPS_PER_CTA * 32, smem, nSM, GG_WARPS_PER_CTA, a.nTasks, &e);
