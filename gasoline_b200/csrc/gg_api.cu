@@ -46,6 +46,9 @@ struct Domain {
 struct gg_context {
     int device = 0, nSM = 0;
     cudaStream_t st = nullptr;
+    cudaStream_t st2 = nullptr; // the local domain's moments travel here while the walk already runs on st
+    cudaEvent_t evMom = nullptr;
+    bool momPending = false;    // st2 work (moment upload + k_pack_mom) not yet known to be complete
     cudaEvent_t ev[8];
     // layout
     int idSelf = 0;
@@ -95,11 +98,20 @@ int ensure_pinned(gg_context *c, size_t bytes) {
     return GG_OK;
 }
 
+// Wait for the asynchronous half of the last gg_set_local (moments) before touching what it reads or writes.
+int finish_mom(gg_context *c) {
+    if (c->momPending) {
+        CK(cudaStreamSynchronize(c->st2));
+        c->momPending = false;
+    }
+    return GG_OK;
+}
+
 // raw staging layout for one domain (doubles): r[3n] fMass[n] fSoft[n] fOpen2[n] mom[31n]; ints: pLower pUpper
 // iLower iUpper [n each]
 __global__ void k_pack_nodes(int n, const double *r, const double *fMass, const double *fSoft, const double *fOpen2,
-                             const double *mom, const int *pLower, const int *pUpper, const int *iLower,
-                             const int *iUpper, int nodeBase, int partBase, NodeW *nodes, float4 *momf, double *momq) {
+                             const int *pLower, const int *pUpper, const int *iLower, const int *iUpper, int nodeBase,
+                             int partBase, NodeW *nodes) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     NodeW w;
@@ -116,8 +128,15 @@ __global__ void k_pack_nodes(int n, const double *r, const double *fMass, const 
     w.nP = pUpper[i] - pLower[i] + 1;
     if (w.nP < 0) w.nP = 0;
     nodes[nodeBase + i] = w;
+}
+
+// The evaluation records: FP32 moments (quadrupole made traceless like SETILIST, walk.c:41-48) and the raw FP64
+// quadrupole of the softened-cell path.
+__global__ void k_pack_mom(int n, const double *mom, int nodeBase, float4 *momf, double *momq) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
     const double *q = &mom[(size_t)GG_NMOM * i];
-    double tr = q[0] + q[1] + q[2]; // traceless at list-build time, walk.c:41-48
+    double tr = q[0] + q[1] + q[2];
     float f[32];
     f[0] = (float)(q[0] - tr / 3.0); f[1] = (float)(q[1] - tr / 3.0); f[2] = (float)(q[2] - tr / 3.0);
     f[3] = (float)q[3]; f[4] = (float)q[4]; f[5] = (float)q[5];
@@ -223,18 +242,25 @@ int upload_domain(gg_context *c, const gg_tree *t, const gg_particles *pp, int n
     const cudaMemcpyKind kind = onDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     size_t nd = (size_t)nn * (3 + 3 + GG_NMOM) + (size_t)np * 5;
     int rc;
+    if ((rc = finish_mom(c))) return rc;
     if ((rc = ensure(c, c->raw, nd * sizeof(double)))) return rc;
     if ((rc = ensure(c, c->rawi, (size_t)nn * 4 * sizeof(int)))) return rc;
     double *d = (double *)c->raw.p;
     double *dr = d, *dM = dr + 3 * (size_t)nn, *dS = dM + nn, *dO = dS + nn, *dmom = dO + nn;
     double *dx = dmom + (size_t)GG_NMOM * nn, *dy = dx + np, *dz = dy + np, *dm = dz + np, *dh = dm + np;
     int *di = (int *)c->rawi.p;
+    const size_t keepN = (size_t)nodeBase, keepP = (size_t)partBase;
+    if ((rc = ensure(c, c->nodes, (keepN + nn + GG_MAX_IMAGES) * sizeof(NodeW), keepN * sizeof(NodeW)))) return rc;
+    if ((rc = ensure(c, c->momf, (keepN + nn + GG_MAX_IMAGES) * 128, keepN * 128))) return rc;
+    if ((rc = ensure(c, c->momq, (keepN + nn + GG_MAX_IMAGES) * 48, keepN * 48))) return rc;
+    if ((rc = ensure(c, c->parts, (keepP + np + 1) * sizeof(PartS), keepP * sizeof(PartS)))) return rc;
+    if (local && (rc = ensure(c, c->hsoft, (size_t)(np + 1) * sizeof(double)))) return rc;
+    // ---- what the walk needs, on the main stream (issued first: the copy engine serves it first)
     if (nn > 0) {
         CK(cudaMemcpyAsync(dr, t->r, sizeof(double) * 3 * nn, kind, c->st));
         CK(cudaMemcpyAsync(dM, t->fMass, sizeof(double) * nn, kind, c->st));
         CK(cudaMemcpyAsync(dS, t->fSoft, sizeof(double) * nn, kind, c->st));
         CK(cudaMemcpyAsync(dO, t->fOpen2, sizeof(double) * nn, kind, c->st));
-        CK(cudaMemcpyAsync(dmom, t->mom, sizeof(double) * GG_NMOM * nn, kind, c->st));
         CK(cudaMemcpyAsync(di, t->pLower, sizeof(int) * nn, kind, c->st));
         CK(cudaMemcpyAsync(di + nn, t->pUpper, sizeof(int) * nn, kind, c->st));
         CK(cudaMemcpyAsync(di + 2 * (size_t)nn, t->iLower, sizeof(int) * nn, kind, c->st));
@@ -247,16 +273,20 @@ int upload_domain(gg_context *c, const gg_tree *t, const gg_particles *pp, int n
         CK(cudaMemcpyAsync(dm, pp->fMass, sizeof(double) * np, kind, c->st));
         CK(cudaMemcpyAsync(dh, pp->fSoft, sizeof(double) * np, kind, c->st));
     }
-    const size_t keepN = (size_t)nodeBase, keepP = (size_t)partBase;
-    if ((rc = ensure(c, c->nodes, (keepN + nn + GG_MAX_IMAGES) * sizeof(NodeW), keepN * sizeof(NodeW)))) return rc;
-    if ((rc = ensure(c, c->momf, (keepN + nn + GG_MAX_IMAGES) * 128, keepN * 128))) return rc;
-    if ((rc = ensure(c, c->momq, (keepN + nn + GG_MAX_IMAGES) * 48, keepN * 48))) return rc;
-    if ((rc = ensure(c, c->parts, (keepP + np + 1) * sizeof(PartS), keepP * sizeof(PartS)))) return rc;
-    if (local && (rc = ensure(c, c->hsoft, (size_t)(np + 1) * sizeof(double)))) return rc;
+    // ---- the moments (60 % of the bytes; only k_eval reads them): the LOCAL domain's go on a second stream and are
+    //      not waited for here, so that the walk of the following gg_gravity overlaps their transfer
+    cudaStream_t ms = local ? c->st2 : c->st;
     if (nn > 0) {
-        k_pack_nodes<<<(nn + 127) / 128, 128, 0, c->st>>>(nn, dr, dM, dS, dO, dmom, di, di + nn, di + 2 * (size_t)nn,
-                                                          di + 3 * (size_t)nn, nodeBase, partBase, (NodeW *)c->nodes.p,
-                                                          (float4 *)c->momf.p, (double *)c->momq.p);
+        CK(cudaMemcpyAsync(dmom, t->mom, sizeof(double) * GG_NMOM * nn, kind, ms));
+        k_pack_mom<<<(nn + 127) / 128, 128, 0, ms>>>(nn, dmom, nodeBase, (float4 *)c->momf.p, (double *)c->momq.p);
+        CK(cudaGetLastError());
+        ++c->nLaunches;
+        if (local) {
+            CK(cudaEventRecord(c->evMom, c->st2));
+            c->momPending = true;
+        }
+        k_pack_nodes<<<(nn + 127) / 128, 128, 0, c->st>>>(nn, dr, dM, dS, dO, di, di + nn, di + 2 * (size_t)nn,
+                                                          di + 3 * (size_t)nn, nodeBase, partBase, (NodeW *)c->nodes.p);
         CK(cudaGetLastError());
         ++c->nLaunches;
     }
@@ -266,7 +296,7 @@ int upload_domain(gg_context *c, const gg_tree *t, const gg_particles *pp, int n
         CK(cudaGetLastError());
         ++c->nLaunches;
     }
-    // the staging buffer is reused by the next upload: finish the packing first
+    // the staging buffer is reused by the next upload: finish the packing first (the moment half: finish_mom)
     CK(cudaStreamSynchronize(c->st));
     return GG_OK;
 }
@@ -297,6 +327,8 @@ int gg_create(gg_context **pctx, int device) {
     c->device = device;
     c->nSM = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->evMom, cudaEventDisableTiming));
     for (auto &ev : c->ev) CK(cudaEventCreate(&ev));
     *pctx = c;
     return GG_OK;
@@ -306,6 +338,7 @@ void gg_destroy(gg_context *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
+    cudaStreamSynchronize(c->st2);
     DevBuf *all[] = {&c->nodes, &c->momf, &c->momq, &c->parts, &c->active, &c->hsoft, &c->tasks, &c->ngroups,
                      &c->goffs, &c->counts, &c->acc, &c->pot, &c->dtg, &c->fweight, &c->nloop, &c->sums, &c->misc,
                      &c->imgoff, &c->ewt, &c->raw, &c->rawi, &c->cubtmp, &c->flush, &c->pool,
@@ -316,6 +349,8 @@ void gg_destroy(gg_context *c) {
     if (c->pinned) cudaFreeHost(c->pinned);
     for (auto &ev : c->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->st);
+    cudaStreamDestroy(c->st2);
+    cudaEventDestroy(c->evMom);
     delete c;
 }
 
@@ -411,6 +446,7 @@ int gg_export_size(gg_context *c, size_t *bytes, int hdr[3]) {
 int gg_export_local(gg_context *c, void *dst) {
     if (!c || !dst || c->dom.empty()) return fail(GG_ERR_ARG, "gg_export_local: no local domain");
     CK(cudaSetDevice(c->device));
+    { int rc0 = finish_mom(c); if (rc0) return rc0; }
     const Domain &L = c->dom[0];
     char *o = (char *)dst;
     const size_t nn = (size_t)L.nNodes, np = (size_t)L.nPart;
@@ -431,6 +467,7 @@ int gg_set_remote_packed(gg_context *c, int id, const int hdr[3], const void *sr
     CK(cudaSetDevice(c->device));
     const size_t keepN = (size_t)c->nNodesAll, keepP = (size_t)c->nPartAll;
     int rc;
+    if ((rc = finish_mom(c))) return rc;
     if ((rc = ensure(c, c->nodes, (keepN + nn + GG_MAX_IMAGES) * sizeof(NodeW), keepN * sizeof(NodeW)))) return rc;
     if ((rc = ensure(c, c->momf, (keepN + nn + GG_MAX_IMAGES) * 128, keepN * 128))) return rc;
     if ((rc = ensure(c, c->momq, (keepN + nn + GG_MAX_IMAGES) * 48, keepN * 48))) return rc;
@@ -578,6 +615,9 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
     int rootNode = L.iRoot;
     int nNodesAll = c->nNodesAll;
     int rc;
+    if (c->nTop > 0 || c->dom.size() > 1) { // several domains: buffers may be re-allocated below -- no overlap
+        if ((rc = finish_mom(c))) return rc;
+    }
     if (c->nTop > 0) {
         if ((rc = pack_top(c, &rootNode))) return rc;
         nNodesAll += c->nTop;
@@ -705,7 +745,7 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
         ++c->nLaunches;
     }
     CK(cudaEventRecord(c->ev[5], c->st));
-    bool evalTimed = false;
+    bool evalTimed = false, evalQueued = false;
     long long nListEntries = 0;
     if (nTasks > 0 && !walkOnly) {
         // per-bucket list offsets = exclusive scan of the entry counts the walk left; the total sizes the list array
@@ -730,8 +770,10 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
         if ((rc = ensure(c, c->lists, ((size_t)nEntries + 32) * sizeof(unsigned)))) return rc;
         ta.lists = (unsigned *)c->lists.p;
         CK(gg_launch_scatter_kernel(ta, c->nSM, c->st));
+        if (c->momPending) CK(cudaStreamWaitEvent(c->st, c->evMom, 0)); // the moments arrive on the second stream
         CK(cudaEventRecord(c->ev[6], c->st));
         CK(gg_launch_eval_kernel(ta, c->nSM, c->st));
+        evalQueued = true;
         evalTimed = true;
         c->nLaunches += 4;
     }
@@ -812,6 +854,7 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
     CK(cudaMemcpyAsync(hs, c->sums.p, sizeof(hs), cudaMemcpyDeviceToHost, c->st));
     CK(cudaMemcpyAsync(hm, c->misc.p, sizeof(hm), cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
+    if (evalQueued) c->momPending = false; // k_eval waited for the moments and has finished
     if (hm[1]) return fail(GG_ERR_UNSUPPORTED, "gg_gravity: walk frontier overflowed %d entries (tree too deep)", GG_STACK_CAP);
     if (!walkOnly && (size_t)hm[3] > c->capBlocks) {
         // the list pool was too small: the walk kept counting, so hm[3] is what it needs -- grow and run again

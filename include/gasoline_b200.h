@@ -112,6 +112,9 @@ void gg_destroy(gg_context *ctx);
  * Ingest the caller's domain: replaces pkd->kdNodes / pkd->pStore (host memory; pinned memory from gg_host_alloc
  * copies fastest).  Must be called again whenever the host rebuilds its tree or moves particles (the reference
  * frees and re-allocates kdNodes at every build, pkd.c:2636-2642).  idSelf is this domain's rank (pkd->idSelf).
+ * On return everything the tree walk needs is on the device; the transfer of tree->mom (60 % of the bytes, read only
+ * by the list evaluation) may still be in flight on a second stream so that it overlaps the walk of the following
+ * gg_gravity: tree->mom must stay valid and unmodified until the next call into this library returns.
  */
 int gg_set_local(gg_context *ctx, int idSelf, const gg_tree *tree, const gg_particles *part);
 

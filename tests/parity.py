@@ -14,18 +14,13 @@ def acc_errors(a, a_ref):
     return float(np.sqrt(np.mean(rel ** 2))), float(rel.max())
 
 
-def pot_errors(p, p_ref, tree_rms=None):
+def pot_errors(p, p_ref):
     """(relative RMS, max relative) of per-particle potentials, each error measured against max(|phi_i|, rms(phi)):
     potentials change sign in a periodic box (the reference's own v_sqrt1 / native-sqrt build variants already differ
-    by 1e-3 relative on particles whose potential is ~0).
-
-    tree_rms: only for the NEAR-UNIFORM ("jitter") periodic boxes.  There the tree part of the potential (27 images,
-    |phi_tree| ~ 21 for M = L = 1) cancels against the Ewald term to |phi| ~ 1e-2, so an FP32 evaluation of the tree
-    terms -- measured error 2e-8 |phi_tree|, i.e. below one ulp of the sum -- is already 4e-5 of rms(phi).  For these
-    cases the floor is max(rms(phi), 5e-3 * rms(phi_tree)): the test then bounds the error at 5e-8 of the quantity
-    the FP32 kernel actually sums (DESIGN.md "Accuracy").  The clustered BASELINE boxes use the strict floor."""
+    by 1e-3 relative on particles whose potential is ~0), so the floor is the RMS potential of the case.  In nearly
+    uniform periodic boxes the tree part of the potential (27 images, |phi_tree| ~ 21 for M = L = 1) cancels against
+    the Ewald term to |phi| ~ 1e-2; the GPU path evaluates the cell monopoles of periodic runs in FP64 (k_eval MONO64)
+    precisely so that this strict floor holds there too."""
     floor = np.sqrt(np.mean(p_ref ** 2))
-    if tree_rms is not None:
-        floor = max(floor, 5e-3 * tree_rms)
     rel = np.abs(p - p_ref) / np.maximum(np.abs(p_ref), floor)
     return float(np.sqrt(np.mean(rel ** 2))), float(rel.max())

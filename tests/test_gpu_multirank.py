@@ -32,8 +32,6 @@ def test_multidomain_matches_multirank_reference(name, packed, gpu_lib):
         rel = np.linalg.norm(out["acc"] - res[:, 0:3], axis=1) / np.linalg.norm(res[:, 0:3], axis=1)
         rms, mx = float(np.sqrt(np.mean(rel ** 2))), float(rel.max())
         floor = np.sqrt(np.mean(res[:, 3] ** 2))
-        if "jitter" in name:  # near-uniform periodic box, see parity.pot_errors
-            floor = max(floor, 5e-3 * 21.0)
         dp = np.abs(out["pot"] - res[:, 3]) / np.maximum(np.abs(res[:, 3]), floor)
         print(f"{name} rank {r}: acc rms {rms:.2e} max {mx:.2e}; pot max {dp.max():.2e}")
         assert rms <= RMS_TOL and mx <= MAX_TOL
