@@ -195,7 +195,7 @@ def run_ours(a):
     n = pkd.nLocal
     pkd.upload()
     if exchange is not None:
-        exchange()  # LET exchange once before the resident-input timing
+        exchange(let=g)  # top tree + pruned locally-essential trees (NCCL all-to-all), once before the resident timing
     peak_tf, _ = pkd.measure_fp32_peak()
 
     def barrier():
@@ -228,7 +228,7 @@ def run_ours(a):
     out_a, out_p, out_d, out_w = (pinned_empty((n, 3)), pinned_empty(n), pinned_empty(n), pinned_empty(n))
     for _ in range(min(a.warmup, 2)):
         if exchange is not None:
-            exchange()
+            exchange(top=False, let=g)
         else:
             pkd.upload()
         pkd.pkdGravAll(g, out_a, out_p, out_d, out_w, accumulate=False)
@@ -238,7 +238,7 @@ def run_ours(a):
         if exchange is not None:
             # this rank's own upload (gg_set_local) + the NCCL tree exchange; the top tree belongs to the host's tree
             # build (pstBuildTree's interior branch), which is outside the timed region like pkdBuildBinary
-            exchange(top=False)
+            exchange(top=False, let=g)
         else:
             pkd.upload()
         pkd.pkdGravAll(g, out_a, out_p, out_d, out_w, accumulate=False)
@@ -296,6 +296,8 @@ def run_ours(a):
                "wall_ms_per_step_resident": wall_res_max / a.steps * 1e3}
         if exchange is not None:
             out["exchange_phases_ms_rank0"] = {k: v * 1e3 for k, v in exchange.driver.timing.items()}
+            out["let_bytes_rank0"] = {"sent": exchange.driver.let_bytes[0], "received": exchange.driver.let_bytes[1],
+                                      "whole_domain": pkd.export_size()[0]}
         if world == 1 and not a.no_cpu_baseline:
             try:
                 r = subprocess.run([sys.executable, "-m", "oracle.cpu_baseline", "--workload", spec, "--seconds",

@@ -63,7 +63,7 @@ struct gg_context {
     std::vector<int> hActive; // host copy of the local ACTIVE flags (empty = all active)
     // device buffers
     DevBuf nodes, momf, momq, parts, active, hsoft, tasks, ngroups, goffs, counts, acc, pot, dtg, fweight, nloop, sums,
-        misc, imgoff, ewt, raw, rawi, cubtmp, flush, pool, nextblk, poolmask, isb, boffs, bnode, ghead, gcnt, bcnt, btot, boff64, lists;
+        misc, imgoff, ewt, raw, rawi, cubtmp, flush, pool, nextblk, poolmask, isb, boffs, bnode, ghead, gcnt, bcnt, btot, boff64, lists, letflag, letfront, letidx, letout, letmisc;
     void *pinned = nullptr;
     size_t pinnedCap = 0;
     int nTasks = 0;
@@ -96,6 +96,33 @@ int ensure_pinned(gg_context *c, size_t bytes) {
     CK(cudaMallocHost(&c->pinned, bytes + bytes / 4));
     c->pinnedCap = bytes + bytes / 4;
     return GG_OK;
+}
+
+struct Images {
+    std::vector<double> off;
+    int n = 0, home = 0, bits = 5;
+};
+
+// Image offsets in the reference's loop order (walk.c:325-337): ix outermost, non-periodic axes not replicated.
+Images make_images(const gg_params *prm) {
+    Images im;
+    const int nR = prm->nReps;
+    for (int ix = -nR; ix <= nR; ++ix) {
+        if (ix && prm->fPeriod[0] >= DBL_MAX) continue;
+        for (int iy = -nR; iy <= nR; ++iy) {
+            if (iy && prm->fPeriod[1] >= DBL_MAX) continue;
+            for (int iz = -nR; iz <= nR; ++iz) {
+                if (iz && prm->fPeriod[2] >= DBL_MAX) continue;
+                if (!ix && !iy && !iz) im.home = im.n;
+                im.off.push_back(ix * prm->fPeriod[0]);
+                im.off.push_back(iy * prm->fPeriod[1]);
+                im.off.push_back(iz * prm->fPeriod[2]);
+                ++im.n;
+            }
+        }
+    }
+    im.bits = im.n <= 32 ? 5 : 7;
+    return im;
 }
 
 // Wait for the asynchronous half of the last gg_set_local (moments) before touching what it reads or writes.
@@ -172,6 +199,94 @@ __global__ void k_rebase_nodes(int n, const NodeW *src, int nodeBase, int partBa
     if (w.c1 >= 0) w.c1 += nodeBase;
     w.pLower += partBase;
     dst[nodeBase + i] = w;
+}
+
+// ---------------------------------------------------------------------------------------------- LET export
+// flags per (remote, node): bit 0 = the remote rank's walks can reach the cell, bit 1 = ... and may open it
+struct LetArgs {
+    const NodeW *nodes;
+    int nNodes, nRemote, nImages;
+    const double *imgOff;  // [nImages][3]
+    const double *bnd;     // [nRemote][6]
+    unsigned char *flag;   // [nRemote][nNodes]
+    const unsigned *front; // this level: (remote << 28) | node
+    unsigned *next;
+    int *count;            // [0] this level, [1] next level
+};
+
+// One level of the marking walk: every frontier item tests its cell against the remote box under all image offsets
+// (opened under ANY offset = opened in the pruned tree, which all images share) and pushes the children.
+__global__ void k_let_level(const LetArgs A, int level) {
+    const int n = A.count[level & 1];
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const unsigned it = A.front[t];
+        const int r = (int)(it >> 28), i = (int)(it & 0x0fffffffu);
+        const NodeW w = A.nodes[i];
+        bool open = w.nP < 4; // walk.c:81
+        if (!open) {
+            const double *b = &A.bnd[6 * r];
+            for (int k = 0; k < A.nImages && !open; ++k) {
+                const double x = w.rx + A.imgOff[3 * k], y = w.ry + A.imgOff[3 * k + 1], z = w.rz + A.imgOff[3 * k + 2];
+                double dx = b[0] - x, dy = b[1] - y, dz = b[2] - z;
+                const double ex = x - b[3], ey = y - b[4], ez = z - b[5];
+                dx = dx > ex ? dx : ex; dy = dy > ey ? dy : ey; dz = dz > ez ? dz : ez;
+                dx = dx > 0.0 ? dx : 0.0; dy = dy > 0.0 ? dy : 0.0; dz = dz > 0.0 ? dz : 0.0;
+                const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                open = d2 <= w.fOpen2;
+            }
+        }
+        A.flag[(size_t)r * A.nNodes + i] = open ? 3 : 1;
+        if (open && w.c0 >= 0) {
+            const int nc = w.c1 >= 0 ? 2 : 1;
+            const int pos = atomicAdd(&A.count[(level + 1) & 1], nc);
+            A.next[pos] = ((unsigned)r << 28) | (unsigned)w.c0;
+            if (nc == 2) A.next[pos + 1] = ((unsigned)r << 28) | (unsigned)w.c1;
+        }
+    }
+}
+
+__global__ void k_let_seed(unsigned *front, int *count, int nRemote, int iRoot) {
+    const int r = threadIdx.x;
+    if (r < nRemote) front[r] = ((unsigned)r << 28) | (unsigned)iRoot;
+    if (r == 0) { count[0] = nRemote; count[1] = 0; }
+}
+
+__global__ void k_let_reset(int *count, int level) { count[(level + 1) & 1] = 0; }
+
+// per node of one remote: 1 if kept / the particles it contributes (opened buckets only)
+__global__ void k_let_counts(int n, const NodeW *nodes, const unsigned char *flag, int *keep, int *npart) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned char f = flag[i];
+    keep[i] = f & 1;
+    npart[i] = (f == 3 && nodes[i].c0 < 0) ? nodes[i].nP : 0;
+}
+
+__global__ void k_let_pack(int n, const NodeW *nodes, const float4 *momf, const double *momq, const PartS *parts,
+                           const unsigned char *flag, const int *newIdx, const int *newPart, NodeW *oNodes, float4 *oMomf,
+                           double *oMomq, PartS *oParts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !(flag[i] & 1)) return;
+    const bool open = flag[i] == 3;
+    NodeW w = nodes[i];
+    const int o = newIdx[i];
+    if (open && w.c0 >= 0) {
+        w.c0 = newIdx[w.c0];
+        w.c1 = w.c1 >= 0 ? newIdx[w.c1] : -1;
+        w.pLower = 0;
+    } else if (open) { // opened bucket: its particles travel
+        const int p0 = newPart[i];
+        for (int j = 0; j < w.nP; ++j) oParts[p0 + j] = parts[w.pLower + j];
+        w.pLower = p0;
+    } else { // never opened over there: a childless cell (nP >= 4 keeps it clear of the "< 4 particles" rule)
+        w.c0 = w.c1 = -1;
+        w.pLower = 0;
+    }
+    oNodes[o] = w;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) oMomf[(size_t)o * 8 + k] = momf[(size_t)i * 8 + k];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) oMomq[(size_t)o * 6 + k] = momq[(size_t)i * 6 + k];
 }
 
 // number of 8-sink passes each local bucket needs (0 for cells and for buckets without an active sink)
@@ -343,7 +458,7 @@ void gg_destroy(gg_context *c) {
                      &c->goffs, &c->counts, &c->acc, &c->pot, &c->dtg, &c->fweight, &c->nloop, &c->sums, &c->misc,
                      &c->imgoff, &c->ewt, &c->raw, &c->rawi, &c->cubtmp, &c->flush, &c->pool,
                      &c->nextblk, &c->poolmask, &c->isb, &c->boffs, &c->bnode, &c->ghead, &c->gcnt, &c->bcnt, &c->btot,
-                     &c->boff64, &c->lists};
+                     &c->boff64, &c->lists, &c->letflag, &c->letfront, &c->letidx, &c->letout, &c->letmisc};
     for (DevBuf *b : all)
         if (b->p) cudaFree(b->p);
     if (c->pinned) cudaFreeHost(c->pinned);
@@ -432,6 +547,99 @@ int gg_set_remote(gg_context *c, int id, const gg_tree *t, const gg_particles *p
     c->dom.push_back(Domain{id, t->nNodes, pp->n, t->iRoot, c->nNodesAll, c->nPartAll});
     c->nNodesAll += t->nNodes;
     c->nPartAll += pp->n;
+    return GG_OK;
+}
+
+int gg_let_export(gg_context *c, int nRemote, const double *bnd, const gg_params *prm, void **pDev, size_t *offsets,
+                  int *hdr) {
+    if (!c || !bnd || !prm || !pDev || !offsets || !hdr || c->dom.empty())
+        return fail(GG_ERR_ARG, "gg_let_export: bad argument / no local domain");
+    if (nRemote < 1 || nRemote > 15) return fail(GG_ERR_UNSUPPORTED, "gg_let_export: nRemote=%d (1..15)", nRemote);
+    CK(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = finish_mom(c))) return rc;
+    const Domain &L = c->dom[0];
+    const int nn = L.nNodes;
+    if (nn >= (1 << 28)) return fail(GG_ERR_UNSUPPORTED, "gg_let_export: %d nodes", nn);
+    Images im = make_images(prm);
+    if (im.n > GG_MAX_IMAGES) return fail(GG_ERR_UNSUPPORTED, "gg_let_export: %d images", im.n);
+    if ((rc = ensure(c, c->imgoff, im.off.size() * sizeof(double)))) return rc;
+    if ((rc = ensure(c, c->letflag, (size_t)nRemote * nn))) return rc;
+    if ((rc = ensure(c, c->letfront, (size_t)2 * nRemote * nn * sizeof(unsigned)))) return rc;
+    if ((rc = ensure(c, c->letidx, (size_t)4 * (nn + 1) * sizeof(int)))) return rc;
+    if ((rc = ensure(c, c->letmisc, 64 * sizeof(double) * 2 + 64))) return rc;
+    double *dBnd = (double *)c->letmisc.p;
+    int *dCount = (int *)(dBnd + 6 * 16);
+    CK(cudaMemcpyAsync(c->imgoff.p, im.off.data(), im.off.size() * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(dBnd, bnd, sizeof(double) * 6 * nRemote, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemsetAsync(c->letflag.p, 0, (size_t)nRemote * nn, c->st));
+    unsigned *f0 = (unsigned *)c->letfront.p, *f1 = f0 + (size_t)nRemote * nn;
+    k_let_seed<<<1, 32, 0, c->st>>>(f0, dCount, nRemote, L.iRoot);
+    CK(cudaGetLastError());
+    LetArgs la;
+    la.nodes = (const NodeW *)c->nodes.p; la.nNodes = nn; la.nRemote = nRemote; la.nImages = im.n;
+    la.imgOff = (const double *)c->imgoff.p; la.bnd = dBnd; la.flag = (unsigned char *)c->letflag.p; la.count = dCount;
+    const int grid = c->nSM * 8;
+    for (int level = 0;; ++level) { // one launch per tree level; the frontier size is read back every 8 levels
+        la.front = (level & 1) ? f1 : f0;
+        la.next = (level & 1) ? f0 : f1;
+        k_let_level<<<grid, 256, 0, c->st>>>(la, level);
+        CK(cudaGetLastError());
+        k_let_reset<<<1, 1, 0, c->st>>>(dCount, level + 1);
+        if ((level & 7) == 7) {
+            int cnt[2];
+            CK(cudaMemcpyAsync(cnt, dCount, sizeof(cnt), cudaMemcpyDeviceToHost, c->st));
+            CK(cudaStreamSynchronize(c->st));
+            if (cnt[(level + 1) & 1] == 0) break;
+        }
+        if (level > 4096) return fail(GG_ERR_UNSUPPORTED, "gg_let_export: tree deeper than 4096 levels");
+    }
+    // ---- compaction per remote: new node numbers, new particle offsets, sizes
+    int *keep = (int *)c->letidx.p, *npart = keep + (nn + 1), *newIdx = npart + (nn + 1), *newPart = newIdx + (nn + 1);
+    size_t tmpBytes = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, keep, newIdx, nn + 1, c->st));
+    if ((rc = ensure(c, c->cubtmp, tmpBytes))) return rc;
+    std::vector<int> nOut(nRemote), nOutP(nRemote);
+    // sizes first (one pass per remote), then one output buffer, then the packing pass
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1) {
+            size_t off = 0;
+            for (int r = 0; r < nRemote; ++r) {
+                offsets[r] = off;
+                off += (size_t)nOut[r] * (sizeof(NodeW) + 128 + 48) + (size_t)nOutP[r] * sizeof(PartS);
+                off = (off + 255) & ~(size_t)255;
+            }
+            offsets[nRemote] = off;
+            if ((rc = ensure(c, c->letout, off + 256))) return rc;
+        }
+        for (int r = 0; r < nRemote; ++r) {
+            const unsigned char *fl = (const unsigned char *)c->letflag.p + (size_t)r * nn;
+            k_let_counts<<<(nn + 255) / 256, 256, 0, c->st>>>(nn, (const NodeW *)c->nodes.p, fl, keep, npart);
+            CK(cudaGetLastError());
+            CK(cudaMemsetAsync(keep + nn, 0, sizeof(int), c->st));
+            CK(cudaMemsetAsync(npart + nn, 0, sizeof(int), c->st));
+            CK(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmpBytes, keep, newIdx, nn + 1, c->st));
+            CK(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmpBytes, npart, newPart, nn + 1, c->st));
+            if (pass == 0) {
+                CK(cudaMemcpyAsync(&nOut[r], newIdx + nn, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+                CK(cudaMemcpyAsync(&nOutP[r], newPart + nn, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+                CK(cudaStreamSynchronize(c->st));
+            } else {
+                char *o = (char *)c->letout.p + offsets[r];
+                NodeW *oN = (NodeW *)o;
+                float4 *oF = (float4 *)(o + (size_t)nOut[r] * sizeof(NodeW));
+                double *oQ = (double *)((char *)oF + (size_t)nOut[r] * 128);
+                PartS *oP = (PartS *)((char *)oQ + (size_t)nOut[r] * 48);
+                k_let_pack<<<(nn + 127) / 128, 128, 0, c->st>>>(nn, (const NodeW *)c->nodes.p, (const float4 *)c->momf.p,
+                                                                (const double *)c->momq.p, (const PartS *)c->parts.p, fl,
+                                                                newIdx, newPart, oN, oF, oQ, oP);
+                CK(cudaGetLastError());
+                hdr[3 * r] = nOut[r]; hdr[3 * r + 1] = nOutP[r]; hdr[3 * r + 2] = 0; // pre-order: the root stays first
+            }
+        }
+    }
+    CK(cudaStreamSynchronize(c->st));
+    *pDev = c->letout.p;
     return GG_OK;
 }
 
@@ -571,33 +779,6 @@ int pack_top(gg_context *c, int *pRoot) {
     *pRoot = map_top(c, 1, topBase);
     if (*pRoot < 0) return fail(GG_ERR_ARG, "gg_set_top: root of the top tree cannot be resolved");
     return GG_OK;
-}
-
-struct Images {
-    std::vector<double> off;
-    int n = 0, home = 0, bits = 5;
-};
-
-// Image offsets in the reference's loop order (walk.c:325-337): ix outermost, non-periodic axes not replicated.
-Images make_images(const gg_params *prm) {
-    Images im;
-    const int nR = prm->nReps;
-    for (int ix = -nR; ix <= nR; ++ix) {
-        if (ix && prm->fPeriod[0] >= DBL_MAX) continue;
-        for (int iy = -nR; iy <= nR; ++iy) {
-            if (iy && prm->fPeriod[1] >= DBL_MAX) continue;
-            for (int iz = -nR; iz <= nR; ++iz) {
-                if (iz && prm->fPeriod[2] >= DBL_MAX) continue;
-                if (!ix && !iy && !iz) im.home = im.n;
-                im.off.push_back(ix * prm->fPeriod[0]);
-                im.off.push_back(iy * prm->fPeriod[1]);
-                im.off.push_back(iz * prm->fPeriod[2]);
-                ++im.n;
-            }
-        }
-    }
-    im.bits = im.n <= 32 ? 5 : 7;
-    return im;
 }
 
 int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_stats *stats, int depth = 0) {

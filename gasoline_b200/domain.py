@@ -331,7 +331,7 @@ def assemble_top(pst: PstNode, nThreads: int, summaries: np.ndarray, anc: np.nda
 
 
 # ---------------------------------------------------------------------------------------------- drivers
-def run_in_process(domains: list, exchange_trees: bool = True, packed: bool = False):
+def run_in_process(domains: list, exchange_trees: bool = True, packed: bool = False, let=None):
     """All ranks inside this process (tests; several contexts on one GPU): the all-gathers are list comprehensions.
     packed=True moves the trees device to device in record layout (gg_export_local -> gg_set_remote_packed), the form
     DistributedExchange.exchange_packed sends through NCCL."""
@@ -339,6 +339,23 @@ def run_in_process(domains: list, exchange_trees: bool = True, packed: bool = Fa
     anc = np.stack([d.ancestor_moments(summaries) for d in domains])
     for d in domains:
         d.assemble(summaries, anc)
+    if exchange_trees and let is not None:
+        # pruned locally-essential trees (gg_let_export), `let` = the GravityParams of the coming force evaluation
+        import torch
+        for d in domains:
+            d.attach()
+        bnds = {d.idSelf: summaries[d.idSelf][0:6] for d in domains}
+        stats = {}
+        for o in domains:
+            others = [d for d in domains if d.idSelf != o.idSelf]
+            ptr, offs, hdr = o.pkd.let_export(np.stack([bnds[d.idSelf] for d in others]), let)
+            full, _ = o.pkd.export_size()
+            for k, d in enumerate(others):
+                d.pkd.pkdSetRemotePacked(o.idSelf, hdr[k], ptr + int(offs[k]))  # (copied before o's next export)
+                stats[(o.idSelf, d.idSelf)] = (int(offs[k + 1] - offs[k]), full)
+        torch.cuda.synchronize()
+        run_in_process.let_stats = stats
+        return summaries, anc
     if exchange_trees and packed:
         import torch
         for d in domains:
@@ -377,6 +394,8 @@ class DistributedExchange:
         self.world = dist.get_world_size()
         self._bufs = None
         self._pbufs = None
+        self._lbufs = None
+        self._summaries = None
 
     def _all_gather_np(self, a: np.ndarray) -> np.ndarray:
         a = np.ascontiguousarray(a)
@@ -389,6 +408,7 @@ class DistributedExchange:
         summaries = self._all_gather_np(self.d.summary())
         anc = self._all_gather_np(self.d.ancestor_moments(summaries))
         self.d.assemble(summaries, anc)
+        self._summaries = summaries
         return summaries, anc
 
     def exchange(self, attach: bool = True):
@@ -487,6 +507,73 @@ class DistributedExchange:
         return int(meta[:, 0].sum() - nbytes)
 
 
+    def exchange_let(self, g, top: bool = True):
+        """The per-step exchange with PRUNED trees: this rank's upload, gg_let_export against every other domain's root
+        bounds (known from the top-tree summaries), sizes by a small all-gather, ONE NCCL all-to-all of the pruned
+        domains in device record layout, gg_set_remote_packed from the receive buffer.  Returns bytes received."""
+        import time
+        torch, dist, d = self.torch, self.dist, self.d
+        tm = {}
+        t0 = time.perf_counter()
+
+        def lap(name):
+            nonlocal t0
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            tm[name] = t1 - t0
+            t0 = t1
+
+        if top or d.kdTop is None:
+            self._summaries, _ = self.top_tree()
+            lap("top_tree")
+        d.attach()
+        lap("attach_local")
+        others = [r for r in range(self.world) if r != d.idSelf]
+        ptr, offs, hdr = d.pkd.let_export(np.stack([self._summaries[r][0:6] for r in others]), g)
+        lap("let_export")
+        # meta[r] = what THIS rank sends to rank r: bytes, nNodes, nPart, iRoot
+        meta = np.zeros((self.world, 4), dtype=np.int64)
+        for k, r in enumerate(others):
+            meta[r] = (offs[k + 1] - offs[k], hdr[k][0], hdr[k][1], hdr[k][2])
+        allmeta = self._all_gather_np(meta)  # [sender][receiver][4]
+        send_sizes = [int(meta[r, 0]) for r in range(self.world)]
+        recv_sizes = [int(allmeta[r, d.idSelf, 0]) for r in range(self.world)]
+        nsend, nrecv = sum(send_sizes), sum(recv_sizes)
+        if self._lbufs is None or self._lbufs[0].numel() < nsend or self._lbufs[1].numel() < nrecv:
+            self._lbufs = (torch.empty(int(nsend * 1.25) + 256, dtype=torch.uint8, device=self.dev),
+                           torch.empty(int(nrecv * 1.25) + 256, dtype=torch.uint8, device=self.dev))
+        send, recv = self._lbufs[0][:nsend], self._lbufs[1][:nrecv]
+        # the export buffer already holds the domains back to back in rank order (with alignment gaps): compact it
+        pos = 0
+        src = _DevView(ptr, int(offs[-1]), self.dev, torch)
+        for k, r in enumerate(others):
+            n = send_sizes[r]
+            send[pos:pos + n].copy_(src.t[int(offs[k]):int(offs[k]) + n])
+            pos += n
+        dist.all_to_all_single(recv, send, output_split_sizes=recv_sizes, input_split_sizes=send_sizes)
+        lap("all_to_all")
+        pos = 0
+        for r in range(self.world):
+            if r != d.idSelf:
+                d.pkd.pkdSetRemotePacked(r, allmeta[r, d.idSelf, 1:4], recv.data_ptr() + pos)
+            pos += recv_sizes[r]
+        lap("set_remote")
+        self.timing = tm
+        self.let_bytes = (nsend, nrecv)
+        return nrecv
+
+
+class _DevView:
+    """A torch uint8 view of a raw device allocation owned by the library (no copy, no ownership)."""
+
+    def __init__(self, ptr: int, nbytes: int, dev: str, torch):
+        class _Arr:
+            pass
+        a = _Arr()
+        a.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+        self.t = torch.as_tensor(a, device=dev)
+
+
 def setup_rank(p, theta: float, rank: int, world: int, device: int | None, nBucket: int = 8, iOrder: int = 4,
                weights=None, backend_device: str | None = None):
     """What one torch.distributed rank does before its first force evaluation (bench.py --gpus N, tests): every rank
@@ -502,9 +589,10 @@ def setup_rank(p, theta: float, rank: int, world: int, device: int | None, nBuck
     ex = DistributedExchange(d, backend_device or ("cpu" if device is None else "cuda"))
     attach = device is not None
 
-    def exchange(top: bool = True):
+    def exchange(top: bool = True, let=None):
+        """let = GravityParams: send pruned locally-essential trees (gg_let_export) instead of whole domains."""
         if attach and ex.dev != "cpu":
-            return ex.exchange_packed(top=top)
+            return ex.exchange_let(let, top=top) if let is not None else ex.exchange_packed(top=top)
         return ex.exchange(attach=attach)
 
     exchange.domain = d

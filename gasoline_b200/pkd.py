@@ -71,6 +71,8 @@ def load_library(path: str | None = None):
     L.gg_set_local.argtypes = [C.c_void_p, C.c_int, C.POINTER(gg_tree), C.POINTER(gg_particles)]
     L.gg_set_remote.argtypes = [C.c_void_p, C.c_int, C.POINTER(gg_tree), C.POINTER(gg_particles), C.c_int]
     L.gg_clear_remote.argtypes = [C.c_void_p]
+    L.gg_let_export.argtypes = [C.c_void_p, C.c_int, _dp, C.POINTER(gg_params), C.POINTER(C.c_void_p),
+                                C.POINTER(C.c_size_t), _ip]
     L.gg_export_size.argtypes = [C.c_void_p, C.POINTER(C.c_size_t), _ip]
     L.gg_export_local.argtypes = [C.c_void_p, C.c_void_p]
     L.gg_set_remote_packed.argtypes = [C.c_void_p, C.c_int, _ip, C.c_void_p]
@@ -264,6 +266,19 @@ class PKD:
         tv = tree.view()
         pv = gg_particles(int(cols[0].shape[0]), *[_d(a) for a in cols], None)
         _check(self._L.gg_set_remote(self._ctx, id_, C.byref(tv), C.byref(pv), 0), "gg_set_remote")
+
+    def let_export(self, bnds, g: "GravityParams"):
+        """Locally essential (pruned) copies of this domain for the remote domains whose root bounds are bnds[r]
+        (fMin[3], fMax[3]): gg_let_export.  Returns (device pointer, offsets[nRemote+1], hdr[nRemote][3]); the buffer
+        belongs to the context and is valid until the next call."""
+        b = np.ascontiguousarray(bnds, dtype=np.float64).reshape(-1, 6)
+        nR = b.shape[0]
+        prm = self._params(g, 0, 0)
+        dev = C.c_void_p()
+        offs = (C.c_size_t * (nR + 1))()
+        hdr = np.zeros((nR, 3), dtype=np.int32)
+        _check(self._L.gg_let_export(self._ctx, nR, _d(b), C.byref(prm), C.byref(dev), offs, _i(hdr)), "gg_let_export")
+        return int(dev.value), np.array(list(offs), dtype=np.int64), hdr
 
     def export_size(self):
         """(bytes, [nNodes, nPart, iRoot]) of this domain in device record layout (gg_export_size)."""

@@ -142,6 +142,19 @@ int gg_clear_remote(gg_context *ctx);
  * gg_set_remote_packed: ingest a remote domain from such a buffer (device pointer, e.g. a slice of the all-gather's
  * receive buffer); links and particle indices are rebased on the fly.  hdr receives / supplies {nNodes, nPart, iRoot}.
  */
+/*
+ * The pruned form of the same export: the LOCALLY ESSENTIAL part of this rank's tree for each of nRemote other domains
+ * whose particles lie inside bnd[r] = (fMin[3], fMax[3]) -- the root bounds every rank knows from the top tree.
+ * This rank walks its own tree against each remote box, for every periodic image offset of prm, with the reference's
+ * opening test (INTERSECTNP walk.h:12-30 against c.fOpen2, cells of < 4 particles always opened, walk.c:81): a cell
+ * the box does not open can never be opened by a bucket inside the box (the point-to-box distance only grows, in
+ * floating point too), so the remote rank's walks see exactly what they would see in the full tree.  Kept: every
+ * visited cell with its moments; the particles of opened buckets; links re-indexed.  Output: one device buffer
+ * (owned by the context, valid until the next call) holding nRemote domains in the gg_export_local layout; domain r
+ * occupies [offsets[r], offsets[r+1]) and hdr[3r..] = {nNodes, nPart, iRoot} for gg_set_remote_packed.
+ */
+int gg_let_export(gg_context *ctx, int nRemote, const double *bnd, const gg_params *prm, void **pDev, size_t *offsets,
+                  int *hdr);
 int gg_export_size(gg_context *ctx, size_t *bytes, int hdr[3]);
 int gg_export_local(gg_context *ctx, void *dst);
 int gg_set_remote_packed(gg_context *ctx, int id, const int hdr[3], const void *src);

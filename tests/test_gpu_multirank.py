@@ -12,13 +12,18 @@ from parity import MAX_TOL, RMS_TOL
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("packed", [False, True], ids=["host-arrays", "device-records"])
+@pytest.mark.parametrize("mode", ["host-arrays", "device-records", "pruned-let"])
 @pytest.mark.parametrize("name", NAMES)
-def test_multidomain_matches_multirank_reference(name, packed, gpu_lib):
+def test_multidomain_matches_multirank_reference(name, mode, gpu_lib):
     p, theta, nThreads, z = load(name)
     doms = make_domains(p, theta, nThreads, z, device=0)
-    domain.run_in_process(doms, packed=packed)
     g = GravityParams(nReps=1, bPeriodic=1, bEwald=1) if p.periodic else GravityParams(nReps=0, bPeriodic=0, bEwald=0)
+    domain.run_in_process(doms, packed=mode == "device-records", let=g if mode == "pruned-let" else None)
+    if mode == "pruned-let":
+        sent = sum(v[0] for v in domain.run_in_process.let_stats.values())
+        full = sum(v[1] for v in domain.run_in_process.let_stats.values())
+        print(f"{name}: pruned trees are {100.0 * sent / full:.1f} % of the whole domains")
+        assert sent <= full
     for r, d in enumerate(doms):
         out = d.pkd.pkdGravAll(g)
         counts = d.pkd.pkdBucketCounts()
@@ -40,3 +45,34 @@ def test_multidomain_matches_multirank_reference(name, packed, gpu_lib):
         assert np.array_equal(out["fWeight"], res[:, 5])
     for d in doms:
         d.pkd.close()
+
+
+@pytest.mark.parametrize("case", ["plummer200k_r4", "periodic32_r3"])
+def test_pruned_let_equals_whole_domains(case, gpu_lib):
+    """The locally essential trees (gg_let_export) must give every bucket exactly the lists the whole remote domains
+    give -- same entries in the same order, hence bit-identical forces -- while shipping a fraction of the bytes."""
+    from gasoline_b200 import ics
+    if case == "plummer200k_r4":
+        p, world, g = ics.plummer(200_000, seed=9), 4, GravityParams(nReps=0, bPeriodic=0, bEwald=0)
+    else:
+        p, world, g = ics.periodic_box(32), 3, GravityParams(nReps=1, bPeriodic=1, bEwald=1)
+    parts = domain.orb_decompose(p.x, p.y, p.z, world)
+    results = {}
+    for mode in ("whole", "let"):
+        doms = [domain.Domain(r, world, p.x[ix], p.y[ix], p.z[ix], p.m[ix], p.h[ix], p.period, 0.7, device=0)
+                for r, ix in enumerate(parts)]
+        domain.run_in_process(doms, packed=mode == "whole", let=g if mode == "let" else None)
+        results[mode] = [(d.pkd.pkdGravAll(g), d.pkd.pkdBucketCounts()) for d in doms]
+        if mode == "let":
+            st = domain.run_in_process.let_stats
+            sent, full = sum(v[0] for v in st.values()), sum(v[1] for v in st.values())
+            print(f"{case}: pruned trees are {100.0 * sent / full:.1f} % of the whole domains ({sent / 1e6:.1f} of {full / 1e6:.1f} MB)")
+            assert sent < 0.7 * full
+        for d in doms:
+            d.pkd.close()
+    for (a, ca), (b, cb) in zip(results["whole"], results["let"]):
+        assert np.array_equal(ca, cb)
+        for k in ("dPartSum", "dCellSum", "dSoftSum", "dFlop"):
+            assert a[k] == b[k]
+        assert np.array_equal(a["acc"], b["acc"]) and np.array_equal(a["pot"], b["pot"])
+        assert np.array_equal(a["fWeight"], b["fWeight"])
