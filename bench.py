@@ -12,7 +12,9 @@ active sinks; Ewald terms are not interactions) divided by time.
             particles already resident in HBM; L2 is flushed between timed iterations.
   e2e       the same through the public host API with HOST buffers: every step re-ingests the host's tree +
             particles from pinned memory (gg_set_local: the reference frees and rebuilds kdNodes before every
-            gravity call, pkd.c:2636-2642), runs the kernels and reads a, fPot, dtGrav, fWeight back.
+            gravity call, pkd.c:2636-2642; the cells' moments are formed on the device instead of transferred),
+            runs the kernels and delivers a, fPot, dtGrav, fWeight into pinned host arrays (stored by the kernels
+            as each sink bucket finishes; d2h_bytes_per_step counts them).
   roofline  the dominant kernel, k_eval<4> (list evaluation), against the FP32 FMA pipe (this is FP32 CUDA-core + SFU
             work, not HBM- or tensor-bound -- DESIGN.md 5): achieved = the reference's own flop score of the lists it
             evaluated (grav.c:246-247) / the kernel's duration (CUDA events recorded around the launch on the
@@ -193,6 +195,9 @@ def run_ours(a):
         pkd, exchange = domain.setup_rank(p, theta, rank, world, local)
     t_tree = time.time() - t0
     n = pkd.nLocal
+    # gg_tree.mom = NULL: the cells' multipole moments (58 % of the tree bytes) are not transferred; the device forms
+    # them from the particles while the walk runs (gg_moments.cu; forces identical, tests/test_gpu_device_moments.py)
+    pkd.device_moments = True
     pkd.upload()
     if exchange is not None:
         exchange(let=g)  # top tree + pruned locally-essential trees (NCCL all-to-all), once before the resident timing

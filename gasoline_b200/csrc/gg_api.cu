@@ -6,7 +6,10 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
+#include <time.h>
 #include <string>
+#include <thread>
 #include <vector>
 #include "gg_internal.h"
 
@@ -48,6 +51,10 @@ struct gg_context {
     cudaStream_t st = nullptr;
     cudaStream_t st2 = nullptr; // the local domain's moments travel here while the walk already runs on st
     cudaEvent_t evMom = nullptr;
+    cudaStream_t st3 = nullptr; // k_stats (bookkeeping + fWeight) runs here, beside the list scatter / evaluation
+    cudaEvent_t evWalk = nullptr, evStats = nullptr, evPacked = nullptr;
+    double *zc[4] = {nullptr, nullptr, nullptr, nullptr}; // device aliases of the caller's mapped a, fPot, dtGrav, fWeight
+    double *zcHost[4] = {nullptr, nullptr, nullptr, nullptr};
     bool momPending = false;    // st2 work (moment upload + k_pack_mom) not yet known to be complete
     cudaEvent_t ev[8];
     // layout
@@ -63,15 +70,30 @@ struct gg_context {
     std::vector<int> hActive; // host copy of the local ACTIVE flags (empty = all active)
     // device buffers
     DevBuf nodes, momf, momq, parts, active, hsoft, tasks, ngroups, goffs, counts, acc, pot, dtg, fweight, nloop, sums,
-        misc, imgoff, ewt, raw, rawi, cubtmp, flush, pool, nextblk, poolmask, isb, boffs, bnode, ghead, gcnt, bcnt, btot, boff64, lists, letflag, letfront, letidx, letout, letmisc;
+        misc, imgoff, ewt, raw, rawi, cubtmp, flush, pool, nextblk, poolmask, isb, boffs, bnode, ghead, gcnt, bcnt, btot, boff64, lists, letflag, letfront, letidx, letout, letmisc, momraw, mparent, dbgtask;
     void *pinned = nullptr;
     size_t pinnedCap = 0;
     int nTasks = 0;
+    int nTasksLocal = 0, nBucketsLocal = 0, nPartUpload = 0; // the task list gg_set_local built
     int nLaunches = 0;
     size_t capBlocks = 0; // list pool capacity (blocks of 32 references), kept at the high-water mark
 };
 
 namespace {
+
+// GG_TRACE=1: host-side phase timings on stderr (development aid)
+struct Trace {
+    bool on;
+    double t0;
+    static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+    Trace() : on(getenv("GG_TRACE") != nullptr), t0(now()) {}
+    void mark(const char *what) {
+        if (!on) return;
+        const double t = now();
+        fprintf(stderr, "[gg trace] %-28s %8.3f ms\n", what, t - t0);
+        t0 = t;
+    }
+};
 
 int ensure(gg_context *c, DevBuf &b, size_t bytes, size_t preserve = 0) {
     if (bytes <= b.cap) return GG_OK;
@@ -138,8 +160,21 @@ int finish_mom(gg_context *c) {
 // iLower iUpper [n each]
 __global__ void k_pack_nodes(int n, const double *r, const double *fMass, const double *fSoft, const double *fOpen2,
                              const int *pLower, const int *pUpper, const int *iLower, const int *iUpper, int nodeBase,
-                             int partBase, NodeW *nodes) {
+                             int partBase, NodeW *nodes, int nPartDomain, int *chk) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    // validation the host used to do in a serial loop (0.8 ms per 357 k cells): chk[0] = largest bucket,
+    // chk[1] = buckets whose particle range leaves [0, nPartDomain)
+    int nb = 0, bad = 0;
+    if (i < n && iLower[i] == -1) {
+        nb = pUpper[i] - pLower[i] + 1;
+        bad = pLower[i] < 0 || pUpper[i] >= nPartDomain;
+    }
+    nb = __reduce_max_sync(0xffffffffu, nb);
+    bad = __reduce_add_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0) {
+        if (nb > 0) atomicMax(&chk[0], nb);
+        if (bad) atomicAdd(&chk[1], bad);
+    }
     if (i >= n) return;
     NodeW w;
     w.rx = r[3 * (size_t)i]; w.ry = r[3 * (size_t)i + 1]; w.rz = r[3 * (size_t)i + 2];
@@ -351,18 +386,53 @@ __global__ void __launch_bounds__(256) k_fma_peak(int iters, float *out) {
     if (r == 123.456f) out[0] = r; // never true: keeps the chains alive
 }
 
+// The local domain's task list: sink buckets with >= 1 ACTIVE particle in tree order, one task per pass of 8 sinks.
+// Depends only on the tree and the ACTIVE flags, so it is built at upload time; hCounts receives {nTasks, nBuckets}
+// after the caller's next synchronisation of c->st.
+int build_task_list(gg_context *c, int nn, const int *dActive, int *hCounts) {
+    int rc;
+    if ((rc = ensure(c, c->ngroups, (size_t)(nn + 1) * sizeof(int)))) return rc;
+    if ((rc = ensure(c, c->goffs, (size_t)(nn + 1) * sizeof(int)))) return rc;
+    if ((rc = ensure(c, c->isb, (size_t)(nn + 1) * sizeof(int)))) return rc;
+    if ((rc = ensure(c, c->boffs, (size_t)(nn + 1) * sizeof(int)))) return rc;
+    if ((rc = ensure(c, c->bnode, (size_t)(nn + 1) * sizeof(int)))) return rc;
+    // every bucket has >= 1 particle, a bucket of nP particles has <= ceil(nP/8) passes: nn + nPart/8 bounds the tasks
+    if ((rc = ensure(c, c->tasks, ((size_t)nn + (size_t)c->nPartUpload / GG_MAX_SINKS + 2) * sizeof(Task)))) return rc;
+    k_count_groups<<<(nn + 255) / 256, 256, 0, c->st>>>(nn, (const NodeW *)c->nodes.p, dActive, (int *)c->ngroups.p,
+                                                        (int *)c->isb.p);
+    CK(cudaGetLastError());
+    size_t tmpBytes = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, (int *)c->ngroups.p, (int *)c->goffs.p, nn + 1, c->st));
+    if ((rc = ensure(c, c->cubtmp, tmpBytes))) return rc;
+    CK(cudaMemsetAsync((int *)c->ngroups.p + nn, 0, sizeof(int), c->st));
+    CK(cudaMemsetAsync((int *)c->isb.p + nn, 0, sizeof(int), c->st));
+    CK(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmpBytes, (int *)c->ngroups.p, (int *)c->goffs.p, nn + 1, c->st));
+    CK(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmpBytes, (int *)c->isb.p, (int *)c->boffs.p, nn + 1, c->st));
+    k_fill_tasks<<<(nn + 255) / 256, 256, 0, c->st>>>(nn, (const int *)c->ngroups.p, (const int *)c->goffs.p,
+                                                      (const int *)c->boffs.p, (Task *)c->tasks.p, (int *)c->bnode.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&hCounts[0], (int *)c->goffs.p + nn, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(&hCounts[1], (int *)c->boffs.p + nn, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    c->nLaunches += 5;
+    return GG_OK;
+}
+
 int upload_domain(gg_context *c, const gg_tree *t, const gg_particles *pp, int nodeBase, int partBase, bool local,
                   bool onDevice) {
     const int nn = t->nNodes, np = pp->n;
     const cudaMemcpyKind kind = onDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    size_t nd = (size_t)nn * (3 + 3 + GG_NMOM) + (size_t)np * 5;
+    const bool devMom = t->mom == nullptr; // the cells' moments are formed on the device from the particles (gg_moments.cu)
+    const size_t nMomD = devMom ? 0 : (size_t)GG_NMOM * nn;
+    size_t nd = (size_t)nn * (3 + 3) + nMomD + (size_t)np * 5;
     int rc;
+    Trace tr;
     if ((rc = finish_mom(c))) return rc;
+    tr.mark("  upload: finish_mom");
     if ((rc = ensure(c, c->raw, nd * sizeof(double)))) return rc;
     if ((rc = ensure(c, c->rawi, (size_t)nn * 4 * sizeof(int)))) return rc;
     double *d = (double *)c->raw.p;
     double *dr = d, *dM = dr + 3 * (size_t)nn, *dS = dM + nn, *dO = dS + nn, *dmom = dO + nn;
-    double *dx = dmom + (size_t)GG_NMOM * nn, *dy = dx + np, *dz = dy + np, *dm = dz + np, *dh = dm + np;
+    double *dx = dmom + nMomD, *dy = dx + np, *dz = dy + np, *dm = dz + np, *dh = dm + np;
     int *di = (int *)c->rawi.p;
     const size_t keepN = (size_t)nodeBase, keepP = (size_t)partBase;
     if ((rc = ensure(c, c->nodes, (keepN + nn + GG_MAX_IMAGES) * sizeof(NodeW), keepN * sizeof(NodeW)))) return rc;
@@ -392,16 +462,21 @@ int upload_domain(gg_context *c, const gg_tree *t, const gg_particles *pp, int n
     //      not waited for here, so that the walk of the following gg_gravity overlaps their transfer
     cudaStream_t ms = local ? c->st2 : c->st;
     if (nn > 0) {
-        CK(cudaMemcpyAsync(dmom, t->mom, sizeof(double) * GG_NMOM * nn, kind, ms));
-        k_pack_mom<<<(nn + 127) / 128, 128, 0, ms>>>(nn, dmom, nodeBase, (float4 *)c->momf.p, (double *)c->momq.p);
-        CK(cudaGetLastError());
-        ++c->nLaunches;
-        if (local) {
-            CK(cudaEventRecord(c->evMom, c->st2));
-            c->momPending = true;
+        if (!devMom) {
+            CK(cudaMemcpyAsync(dmom, t->mom, sizeof(double) * GG_NMOM * nn, kind, ms));
+            k_pack_mom<<<(nn + 127) / 128, 128, 0, ms>>>(nn, dmom, nodeBase, (float4 *)c->momf.p, (double *)c->momq.p);
+            CK(cudaGetLastError());
+            ++c->nLaunches;
+            if (local) {
+                CK(cudaEventRecord(c->evMom, c->st2));
+                c->momPending = true;
+            }
         }
+        if ((rc = ensure(c, c->misc, 16 * sizeof(int)))) return rc;
+        CK(cudaMemsetAsync((int *)c->misc.p + 8, 0, 2 * sizeof(int), c->st));
         k_pack_nodes<<<(nn + 127) / 128, 128, 0, c->st>>>(nn, dr, dM, dS, dO, di, di + nn, di + 2 * (size_t)nn,
-                                                          di + 3 * (size_t)nn, nodeBase, partBase, (NodeW *)c->nodes.p);
+                                                          di + 3 * (size_t)nn, nodeBase, partBase, (NodeW *)c->nodes.p,
+                                                          np, (int *)c->misc.p + 8);
         CK(cudaGetLastError());
         ++c->nLaunches;
     }
@@ -411,8 +486,52 @@ int upload_domain(gg_context *c, const gg_tree *t, const gg_particles *pp, int n
         CK(cudaGetLastError());
         ++c->nLaunches;
     }
+    if (devMom && nn > 0) {
+        // moments from the packed walk records + the FP64 particle columns still in the staging buffer; for the local
+        // domain on the second stream, beside the walk of the following gg_gravity (k_eval waits for evMom)
+        if ((rc = ensure(c, c->momraw, (size_t)nn * 32 * sizeof(double)))) return rc;
+        if ((rc = ensure(c, c->mparent, (size_t)nn * 2 * sizeof(int)))) return rc;
+        if (local) {
+            CK(cudaEventRecord(c->evPacked, c->st));
+            CK(cudaStreamWaitEvent(c->st2, c->evPacked, 0));
+        }
+        CK(gg_launch_device_moments(nn, (const NodeW *)c->nodes.p, nodeBase, partBase, t->iRoot, dx, dy, dz, dm,
+                                    (int *)c->mparent.p, (int *)c->mparent.p + nn, (double *)c->momraw.p,
+                                    (float4 *)c->momf.p, (double *)c->momq.p, ms));
+        c->nLaunches += 2;
+        if (local) {
+            CK(cudaEventRecord(c->evMom, c->st2));
+            c->momPending = true;
+        }
+    }
+    // the local domain's sink-bucket task list depends only on the tree and the ACTIVE flags: built here, so that
+    // gg_gravity starts its walk without a host round trip
+    int hChk[2] = {0, 0}, hCounts[2] = {0, 0};
+    if (local) {
+        const int *dActive = nullptr;
+        if (pp->active) {
+            if ((rc = ensure(c, c->active, (size_t)(np + 1) * sizeof(int)))) return rc;
+            CK(cudaMemcpyAsync(c->active.p, pp->active, sizeof(int) * np, cudaMemcpyHostToDevice, c->st));
+            dActive = (const int *)c->active.p;
+        }
+        c->nPartUpload = np;
+        if ((rc = build_task_list(c, nn, dActive, hCounts))) return rc;
+    }
+    if (nn > 0) CK(cudaMemcpyAsync(hChk, (int *)c->misc.p + 8, sizeof(hChk), cudaMemcpyDeviceToHost, c->st));
+    tr.mark("  upload: enqueue");
     // the staging buffer is reused by the next upload: finish the packing first (the moment half: finish_mom)
     CK(cudaStreamSynchronize(c->st));
+    tr.mark("  upload: sync");
+    if (hChk[1])
+        return fail(GG_ERR_ARG, "gg_set_%s: %d bucket(s) span particles outside [0,%d)", local ? "local" : "remote", hChk[1], np);
+    if (hChk[0] > GG_MAX_BUCKET)
+        return fail(GG_ERR_UNSUPPORTED, "gg_set_%s: a bucket holds %d particles (limit GG_MAX_BUCKET=%d)",
+                    local ? "local" : "remote", hChk[0], GG_MAX_BUCKET);
+    if (local) {
+        c->maxBucket = hChk[0] > 1 ? hChk[0] : 1;
+        c->nTasksLocal = hCounts[0];
+        c->nBucketsLocal = hCounts[1];
+    } else if (hChk[0] > c->maxBucket) c->maxBucket = hChk[0];
     return GG_OK;
 }
 
@@ -444,6 +563,10 @@ int gg_create(gg_context **pctx, int device) {
     CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->evMom, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&c->st3, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->evWalk, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->evStats, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->evPacked, cudaEventDisableTiming));
     for (auto &ev : c->ev) CK(cudaEventCreate(&ev));
     *pctx = c;
     return GG_OK;
@@ -454,17 +577,23 @@ void gg_destroy(gg_context *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
     cudaStreamSynchronize(c->st2);
+    if (c->st3) cudaStreamSynchronize(c->st3);
     DevBuf *all[] = {&c->nodes, &c->momf, &c->momq, &c->parts, &c->active, &c->hsoft, &c->tasks, &c->ngroups,
                      &c->goffs, &c->counts, &c->acc, &c->pot, &c->dtg, &c->fweight, &c->nloop, &c->sums, &c->misc,
                      &c->imgoff, &c->ewt, &c->raw, &c->rawi, &c->cubtmp, &c->flush, &c->pool,
                      &c->nextblk, &c->poolmask, &c->isb, &c->boffs, &c->bnode, &c->ghead, &c->gcnt, &c->bcnt, &c->btot,
-                     &c->boff64, &c->lists, &c->letflag, &c->letfront, &c->letidx, &c->letout, &c->letmisc};
+                     &c->boff64, &c->lists, &c->letflag, &c->letfront, &c->letidx, &c->letout, &c->letmisc, &c->momraw,
+                     &c->mparent, &c->dbgtask};
     for (DevBuf *b : all)
         if (b->p) cudaFree(b->p);
     if (c->pinned) cudaFreeHost(c->pinned);
     for (auto &ev : c->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->st);
     cudaStreamDestroy(c->st2);
+    if (c->st3) cudaStreamDestroy(c->st3);
+    if (c->evWalk) cudaEventDestroy(c->evWalk);
+    if (c->evStats) cudaEventDestroy(c->evStats);
+    if (c->evPacked) cudaEventDestroy(c->evPacked);
     cudaEventDestroy(c->evMom);
     delete c;
 }
@@ -484,33 +613,18 @@ int gg_set_local(gg_context *c, int idSelf, const gg_tree *t, const gg_particles
     if (t->nNodes < 1 || pp->n < 0 || t->iRoot < 0 || t->iRoot >= t->nNodes)
         return fail(GG_ERR_ARG, "gg_set_local: nNodes=%d n=%d iRoot=%d", t->nNodes, pp->n, t->iRoot);
     CK(cudaSetDevice(c->device));
-    int maxB = 1;
-    for (int i = 0; i < t->nNodes; ++i)
-        if (t->iLower[i] == -1) {
-            int np = t->pUpper[i] - t->pLower[i] + 1;
-            if (np > maxB) maxB = np;
-            if (t->pLower[i] < 0 || t->pUpper[i] >= pp->n)
-                return fail(GG_ERR_ARG, "gg_set_local: bucket %d spans particles [%d,%d] outside [0,%d)", i, t->pLower[i],
-                            t->pUpper[i], pp->n);
-        }
-    if (maxB > GG_MAX_BUCKET)
-        return fail(GG_ERR_UNSUPPORTED, "gg_set_local: a bucket holds %d particles (limit GG_MAX_BUCKET=%d)", maxB,
-                    GG_MAX_BUCKET);
+    Trace tr;
     c->dom.clear();
     c->nTop = 0;
     c->idSelf = idSelf;
-    c->maxBucket = maxB;
     int rc = upload_domain(c, t, pp, 0, 0, true, false);
     if (rc) return rc;
+    tr.mark("set_local: upload_domain");
     c->dom.push_back(Domain{idSelf, t->nNodes, pp->n, t->iRoot, 0, 0});
     c->nNodesAll = t->nNodes;
     c->nPartAll = pp->n;
-    if (pp->active) {
-        c->hActive.assign(pp->active, pp->active + pp->n);
-        if ((rc = ensure(c, c->active, (size_t)(pp->n + 1) * sizeof(int)))) return rc;
-        CK(cudaMemcpyAsync(c->active.p, pp->active, sizeof(int) * pp->n, cudaMemcpyHostToDevice, c->st));
-        CK(cudaStreamSynchronize(c->st));
-    } else c->hActive.clear();
+    if (pp->active) c->hActive.assign(pp->active, pp->active + pp->n); // (the device copy went up with the domain)
+    else c->hActive.clear();
     return GG_OK;
 }
 
@@ -519,29 +633,7 @@ int gg_set_remote(gg_context *c, int id, const gg_tree *t, const gg_particles *p
     if (c->dom.empty()) return fail(GG_ERR_ARG, "gg_set_remote: call gg_set_local first");
     if (id == c->idSelf) return fail(GG_ERR_ARG, "gg_set_remote: id %d is the local domain", id);
     CK(cudaSetDevice(c->device));
-    if (!bDevice) {
-        for (int i = 0; i < t->nNodes; ++i)
-            if (t->iLower[i] == -1) {
-                int np = t->pUpper[i] - t->pLower[i] + 1;
-                if (np > GG_MAX_BUCKET)
-                    return fail(GG_ERR_UNSUPPORTED, "gg_set_remote: a bucket holds %d particles (limit %d)", np,
-                                GG_MAX_BUCKET);
-                if (np > c->maxBucket) c->maxBucket = np;
-            }
-    } else if (t->nNodes > 0) { // device-resident links: one small reduction kernel finds the largest bucket
-        int rc0;
-        if ((rc0 = ensure(c, c->misc, 16 * sizeof(int)))) return rc0;
-        CK(cudaMemsetAsync((int *)c->misc.p + 8, 0, sizeof(int), c->st));
-        k_max_bucket<<<(t->nNodes + 255) / 256, 256, 0, c->st>>>(t->nNodes, t->pLower, t->pUpper, t->iLower,
-                                                                 (int *)c->misc.p + 8);
-        CK(cudaGetLastError());
-        int maxB = 0;
-        CK(cudaMemcpyAsync(&maxB, (int *)c->misc.p + 8, sizeof(int), cudaMemcpyDeviceToHost, c->st));
-        CK(cudaStreamSynchronize(c->st));
-        if (maxB > GG_MAX_BUCKET)
-            return fail(GG_ERR_UNSUPPORTED, "gg_set_remote: a bucket holds %d particles (limit %d)", maxB, GG_MAX_BUCKET);
-        if (maxB > c->maxBucket) c->maxBucket = maxB;
-    }
+    // (bucket sizes and particle ranges are validated on the device while the records are packed)
     int rc = upload_domain(c, t, pp, c->nNodesAll, c->nPartAll, false, bDevice != 0);
     if (rc) return rc;
     c->dom.push_back(Domain{id, t->nNodes, pp->n, t->iRoot, c->nNodesAll, c->nPartAll});
@@ -561,6 +653,7 @@ int gg_let_export(gg_context *c, int nRemote, const double *bnd, const gg_params
     const Domain &L = c->dom[0];
     const int nn = L.nNodes;
     if (nn >= (1 << 28)) return fail(GG_ERR_UNSUPPORTED, "gg_let_export: %d nodes", nn);
+    Trace tr;
     Images im = make_images(prm);
     if (im.n > GG_MAX_IMAGES) return fail(GG_ERR_UNSUPPORTED, "gg_let_export: %d images", im.n);
     if ((rc = ensure(c, c->imgoff, im.off.size() * sizeof(double)))) return rc;
@@ -787,10 +880,12 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
         return fail(GG_ERR_UNSUPPORTED, "gg_gravity: iOrder=%d iEwOrder=%d (supported 1..4)", prm->iOrder, prm->iEwOrder);
     if (prm->nReps < 0 || prm->nReps > 2) return fail(GG_ERR_UNSUPPORTED, "gg_gravity: nReps=%d (supported 0..2)", prm->nReps);
     CK(cudaSetDevice(c->device));
+    if (depth > 0) CK(cudaStreamSynchronize(c->st3)); // a re-run: the previous attempt's k_stats may still be in flight
     const Domain &L = c->dom[0];
     const int n = L.nPart, nn = L.nNodes;
     const bool doEwald = prm->bPeriodic && prm->bEwald && prm->iEwOrder > 0 && !(prm->flags & GG_FLAG_WALK_ONLY);
     if (doEwald && !c->haveRoot) return fail(GG_ERR_ARG, "gg_gravity: Ewald needs gg_set_root_moments");
+    Trace tr;
     Images im = make_images(prm);
     if (im.n > GG_MAX_IMAGES) return fail(GG_ERR_UNSUPPORTED, "gg_gravity: %d images", im.n);
     int rootNode = L.iRoot;
@@ -836,131 +931,9 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
     CK(cudaMemsetAsync(c->sums.p, 0, 16 * sizeof(unsigned long long), c->st));
     CK(cudaMemsetAsync(c->misc.p, 0, 16 * sizeof(int), c->st));
 
-    // ---- task list: local buckets with an active sink, in tree order (+ their ordinals: walk groups)
-    int nTasks = 0, nBuckets = 0;
-    if (singleTask) {
-        if ((rc = ensure(c, c->tasks, sizeof(Task)))) return rc;
-        CK(cudaMemcpyAsync(c->tasks.p, singleTask, sizeof(Task), cudaMemcpyHostToDevice, c->st));
-        CK(cudaMemcpyAsync(c->bnode.p, &singleTask->node, sizeof(int), cudaMemcpyHostToDevice, c->st));
-        nTasks = nBuckets = 1;
-    } else {
-        k_count_groups<<<(nn + 255) / 256, 256, 0, c->st>>>(nn, (const NodeW *)c->nodes.p, dActive, (int *)c->ngroups.p,
-                                                            (int *)c->isb.p);
-        CK(cudaGetLastError());
-        size_t tmpBytes = 0;
-        CK(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, (int *)c->ngroups.p, (int *)c->goffs.p, nn + 1, c->st));
-        if ((rc = ensure(c, c->cubtmp, tmpBytes))) return rc;
-        CK(cudaMemsetAsync((int *)c->ngroups.p + nn, 0, sizeof(int), c->st));
-        CK(cudaMemsetAsync((int *)c->isb.p + nn, 0, sizeof(int), c->st));
-        CK(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmpBytes, (int *)c->ngroups.p, (int *)c->goffs.p, nn + 1, c->st));
-        CK(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmpBytes, (int *)c->isb.p, (int *)c->boffs.p, nn + 1, c->st));
-        CK(cudaMemcpyAsync(&nTasks, (int *)c->goffs.p + nn, sizeof(int), cudaMemcpyDeviceToHost, c->st));
-        CK(cudaMemcpyAsync(&nBuckets, (int *)c->boffs.p + nn, sizeof(int), cudaMemcpyDeviceToHost, c->st));
-        CK(cudaStreamSynchronize(c->st));
-        if ((rc = ensure(c, c->tasks, (size_t)(nTasks + 1) * sizeof(Task)))) return rc;
-        k_fill_tasks<<<(nn + 255) / 256, 256, 0, c->st>>>(nn, (const int *)c->ngroups.p, (const int *)c->goffs.p,
-                                                          (const int *)c->boffs.p, (Task *)c->tasks.p, (int *)c->bnode.p);
-        CK(cudaGetLastError());
-        c->nLaunches += 5;
-    }
-    const int nWalkGroups = (nBuckets + GG_WALK_GB - 1) / GG_WALK_GB;
-    if ((rc = ensure(c, c->ghead, (size_t)(nWalkGroups + 1) * 6 * sizeof(int)))) return rc;
-    if ((rc = ensure(c, c->gcnt, (size_t)(nWalkGroups + 1) * 6 * sizeof(int)))) return rc;
-    if ((rc = ensure(c, c->bcnt, (size_t)(nBuckets + 1) * 3 * sizeof(int)))) return rc;
-    if ((rc = ensure(c, c->btot, (size_t)(nBuckets + 1) * sizeof(long long)))) return rc;
-    if ((rc = ensure(c, c->boff64, (size_t)(nBuckets + 1) * sizeof(long long)))) return rc;
-    c->nTasks = nTasks;
-
-    // ---- walk (lists -> HBM pool) + list evaluation
-    const bool walkOnly = (prm->flags & GG_FLAG_WALK_ONLY) != 0;
-    if (!walkOnly && c->capBlocks == 0) { // first guess: ~700 list entries per bucket, plus one slab per resident warp
-        c->capBlocks = (size_t)nBuckets * 16 + (size_t)c->nSM * 64 * GG_SLAB_BLOCKS + 1024;
-    }
-    TreeKernelArgs ta;
-    memset(&ta, 0, sizeof(ta));
-    ta.nodes = (const NodeW *)c->nodes.p;
-    ta.momf = (const float4 *)c->momf.p;
-    ta.momq = (const double *)c->momq.p;
-    ta.parts = (const PartS *)c->parts.p;
-    ta.active = dActive;
-    ta.hsoft = (const double *)c->hsoft.p;
-    ta.tasks = (const Task *)c->tasks.p;
-    ta.nTasks = nTasks;
-    ta.bucketNode = (const int *)c->bnode.p;
-    ta.nBuckets = nBuckets;
-    ta.groupHead = (int *)c->ghead.p;
-    ta.groupCnt = (int *)c->gcnt.p;
-    ta.bucketCnt = (int *)c->bcnt.p;
-    ta.bucketTot = (long long *)c->btot.p;
-    ta.bucketOff = (const long long *)c->boff64.p;
-    ta.taskCounter = (int *)c->misc.p;
-    ta.errFlag = (int *)c->misc.p + 1;
-    ta.poolCursor = (int *)c->misc.p + 3;
-    ta.rootNode = rootNode;
-    ta.nImages = im.n;
-    ta.homeImage = im.home;
-    ta.imgBits = im.bits;
-    ta.imgOff = (const double *)c->imgoff.p;
-    ta.iOrder = prm->iOrder;
-    ta.maxBucket = c->maxBucket;
-    ta.walkOnly = walkOnly ? 1 : 0;
-    ta.mono64 = prm->bPeriodic ? 1 : 0;
-    ta.acc = (double *)c->acc.p;
-    ta.pot = (double *)c->pot.p;
-    ta.dtg = (double *)c->dtg.p;
-    ta.counts = (int *)c->counts.p;
-    CK(cudaEventRecord(c->ev[1], c->st));
-    if (nTasks > 0) {
-        if (!walkOnly) {
-            if (c->capBlocks > 0x7fffffffu / 32u)
-                return fail(GG_ERR_NOMEM, "gg_gravity: interaction lists need %zu blocks (> 2^31 references)", c->capBlocks);
-            if ((rc = ensure(c, c->pool, c->capBlocks * 32 * sizeof(unsigned)))) return rc;
-            if ((rc = ensure(c, c->nextblk, c->capBlocks * sizeof(int)))) return rc;
-            if ((rc = ensure(c, c->poolmask, c->capBlocks * 32 * sizeof(gg_mask_t)))) return rc;
-        }
-        ta.pool = (unsigned *)c->pool.p;
-        ta.nextBlk = (int *)c->nextblk.p;
-        ta.poolMask = (gg_mask_t *)c->poolmask.p;
-        ta.capBlocks = (int)c->capBlocks;
-        CK(gg_launch_walk_kernel(ta, c->nSM, c->st));
-        ++c->nLaunches;
-    }
-    CK(cudaEventRecord(c->ev[5], c->st));
-    bool evalTimed = false, evalQueued = false;
-    long long nListEntries = 0;
-    if (nTasks > 0 && !walkOnly) {
-        // per-bucket list offsets = exclusive scan of the entry counts the walk left; the total sizes the list array
-        size_t tmpBytes = 0;
-        CK(cudaMemsetAsync((long long *)c->btot.p + nBuckets, 0, sizeof(long long), c->st));
-        CK(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, (long long *)c->btot.p, (long long *)c->boff64.p, nBuckets + 1, c->st));
-        if ((rc = ensure(c, c->cubtmp, tmpBytes))) return rc;
-        CK(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmpBytes, (long long *)c->btot.p, (long long *)c->boff64.p, nBuckets + 1, c->st));
-        long long nEntries = 0;
-        int hm3[4];
-        CK(cudaMemcpyAsync(&nEntries, (long long *)c->boff64.p + nBuckets, sizeof(long long), cudaMemcpyDeviceToHost, c->st));
-        CK(cudaMemcpyAsync(hm3, c->misc.p, sizeof(hm3), cudaMemcpyDeviceToHost, c->st));
-        CK(cudaStreamSynchronize(c->st));
-        if (hm3[1]) return fail(GG_ERR_UNSUPPORTED, "gg_gravity: walk frontier overflowed %d entries (tree too deep)", GG_STACK_CAP);
-        if ((size_t)hm3[3] > c->capBlocks) {
-            // the chain pool was too small: the walk kept counting, so hm3[3] is what it needs -- grow and run again
-            if (depth >= 2) return fail(GG_ERR_NOMEM, "gg_gravity: list pool overflow persists (%d blocks)", hm3[3]);
-            c->capBlocks = (size_t)hm3[3] + (size_t)hm3[3] / 8 + 1024;
-            return run_gravity(c, prm, singleTask, stats, depth + 1);
-        }
-        nListEntries = nEntries;
-        if ((rc = ensure(c, c->lists, ((size_t)nEntries + 32) * sizeof(unsigned)))) return rc;
-        ta.lists = (unsigned *)c->lists.p;
-        CK(gg_launch_scatter_kernel(ta, c->nSM, c->st));
-        if (c->momPending) CK(cudaStreamWaitEvent(c->st, c->evMom, 0)); // the moments arrive on the second stream
-        CK(cudaEventRecord(c->ev[6], c->st));
-        CK(gg_launch_eval_kernel(ta, c->nSM, c->st));
-        evalQueued = true;
-        evalTimed = true;
-        c->nLaunches += 4;
-    }
-    CK(cudaEventRecord(c->ev[2], c->st));
-
-    // ---- Ewald
+    // ---- Ewald correction and comoving background FIRST: they need only the particles and the root moments, and
+    //      with them already in acc/pot the list evaluation's store is the final one (zero-copy delivery below)
+    CK(cudaEventRecord(c->ev[7], c->st));
     int nEwh = 0;
     if (doEwald && !singleTask) {
         std::vector<double> ewt;
@@ -1012,11 +985,90 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
         CK(cudaGetLastError());
         ++c->nLaunches;
     }
-    // ---- bookkeeping
+    // ---- task list: local buckets with an active sink, in tree order (+ their ordinals: walk groups)
+    int nTasks = 0, nBuckets = 0;
+    if (singleTask) {
+        // (its own small buffer: the task list of gg_set_local stays intact for the next gg_gravity)
+        if ((rc = ensure(c, c->dbgtask, sizeof(Task) + sizeof(int)))) return rc;
+        CK(cudaMemcpyAsync(c->dbgtask.p, singleTask, sizeof(Task), cudaMemcpyHostToDevice, c->st));
+        CK(cudaMemcpyAsync((char *)c->dbgtask.p + sizeof(Task), &singleTask->node, sizeof(int), cudaMemcpyHostToDevice, c->st));
+        nTasks = nBuckets = 1;
+    } else {
+        nTasks = c->nTasksLocal;   // built by gg_set_local (build_task_list)
+        nBuckets = c->nBucketsLocal;
+    }
+    const int nWalkGroups = (nBuckets + GG_WALK_GB - 1) / GG_WALK_GB;
+    if ((rc = ensure(c, c->ghead, (size_t)(nWalkGroups + 1) * 6 * sizeof(int)))) return rc;
+    if ((rc = ensure(c, c->gcnt, (size_t)(nWalkGroups + 1) * 6 * sizeof(int)))) return rc;
+    if ((rc = ensure(c, c->bcnt, (size_t)(nBuckets + 1) * 3 * sizeof(int)))) return rc;
+    if ((rc = ensure(c, c->btot, (size_t)(nBuckets + 1) * sizeof(long long)))) return rc;
+    if ((rc = ensure(c, c->boff64, (size_t)(nBuckets + 1) * sizeof(long long)))) return rc;
+    c->nTasks = nTasks;
+
+    // ---- walk (lists -> HBM pool) + list evaluation
+    const bool walkOnly = (prm->flags & GG_FLAG_WALK_ONLY) != 0;
+    if (!walkOnly && c->capBlocks == 0) { // first guess: ~700 list entries per bucket, plus one slab per resident warp
+        c->capBlocks = (size_t)nBuckets * 16 + (size_t)c->nSM * 64 * GG_SLAB_BLOCKS + 1024;
+    }
+    TreeKernelArgs ta;
+    memset(&ta, 0, sizeof(ta));
+    ta.nodes = (const NodeW *)c->nodes.p;
+    ta.momf = (const float4 *)c->momf.p;
+    ta.momq = (const double *)c->momq.p;
+    ta.parts = (const PartS *)c->parts.p;
+    ta.active = dActive;
+    ta.hsoft = (const double *)c->hsoft.p;
+    ta.tasks = singleTask ? (const Task *)c->dbgtask.p : (const Task *)c->tasks.p;
+    ta.nTasks = nTasks;
+    ta.bucketNode = singleTask ? (const int *)((const char *)c->dbgtask.p + sizeof(Task)) : (const int *)c->bnode.p;
+    ta.nBuckets = nBuckets;
+    ta.groupHead = (int *)c->ghead.p;
+    ta.groupCnt = (int *)c->gcnt.p;
+    ta.bucketCnt = (int *)c->bcnt.p;
+    ta.bucketTot = (long long *)c->btot.p;
+    ta.bucketOff = (const long long *)c->boff64.p;
+    ta.taskCounter = (int *)c->misc.p;
+    ta.errFlag = (int *)c->misc.p + 1;
+    ta.poolCursor = (int *)c->misc.p + 3;
+    ta.rootNode = rootNode;
+    ta.nImages = im.n;
+    ta.homeImage = im.home;
+    ta.imgBits = im.bits;
+    ta.imgOff = (const double *)c->imgoff.p;
+    ta.iOrder = prm->iOrder;
+    ta.maxBucket = c->maxBucket;
+    ta.walkOnly = walkOnly ? 1 : 0;
+    ta.mono64 = prm->bPeriodic ? 1 : 0;
+    ta.acc = (double *)c->acc.p;
+    ta.pot = (double *)c->pot.p;
+    ta.dtg = (double *)c->dtg.p;
+    ta.counts = (int *)c->counts.p;
+    ta.hacc = c->zc[0]; ta.hpot = c->zc[1]; ta.hdtg = c->zc[2];
+    CK(cudaEventRecord(c->ev[1], c->st));
+    if (nTasks > 0) {
+        if (!walkOnly) {
+            if (c->capBlocks > 0x7fffffffu / 32u)
+                return fail(GG_ERR_NOMEM, "gg_gravity: interaction lists need %zu blocks (> 2^31 references)", c->capBlocks);
+            if ((rc = ensure(c, c->pool, c->capBlocks * 32 * sizeof(unsigned)))) return rc;
+            if ((rc = ensure(c, c->nextblk, c->capBlocks * sizeof(int)))) return rc;
+            if ((rc = ensure(c, c->poolmask, c->capBlocks * 32 * sizeof(gg_mask_t)))) return rc;
+        }
+        ta.pool = (unsigned *)c->pool.p;
+        ta.nextBlk = (int *)c->nextblk.p;
+        ta.poolMask = (gg_mask_t *)c->poolmask.p;
+        ta.capBlocks = (int)c->capBlocks;
+        CK(gg_launch_walk_kernel(ta, c->nSM, c->st));
+        ++c->nLaunches;
+    }
+    CK(cudaEventRecord(c->ev[5], c->st));
+    // ---- bookkeeping (pkd.c:2945-2998): needs only the walk's counts (and Ewald's loop counts), so it runs on its own
+    //      stream beside the list scatter and evaluation; fWeight goes straight to the caller's mapped array if any
+    CK(cudaEventRecord(c->evWalk, c->st));
+    CK(cudaStreamWaitEvent(c->st3, c->evWalk, 0));
     StatsKernelArgs sa;
     memset(&sa, 0, sizeof(sa));
     sa.nodes = (const NodeW *)c->nodes.p;
-    sa.tasks = (const Task *)c->tasks.p;
+    sa.tasks = ta.tasks;
     sa.nTasks = nTasks;
     sa.active = dActive;
     sa.counts = (const int *)c->counts.p;
@@ -1025,9 +1077,49 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
     sa.iOrder = prm->iOrder;
     sa.iEwOrder = prm->iEwOrder;
     sa.fWeight = (double *)c->fweight.p;
+    sa.hfWeight = (!walkOnly && dActive) ? c->zc[3] : nullptr; // partially active: only active entries may be written
     sa.sums = (unsigned long long *)c->sums.p;
-    CK(gg_launch_stats_kernel(sa, c->st));
+    CK(gg_launch_stats_kernel(sa, c->st3));
+    if (!walkOnly && c->zc[3] && !dActive && n > 0) // one coalesced copy (per-bucket 8-byte stores over PCIe cost ~1 ms per 1 M particles)
+        CK(cudaMemcpyAsync(c->zcHost[3], c->fweight.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->st3));
+    CK(cudaEventRecord(c->evStats, c->st3));
     if (nTasks > 0) ++c->nLaunches;
+    bool evalTimed = false, evalQueued = false;
+    long long nListEntries = 0;
+    if (nTasks > 0 && !walkOnly) {
+        // per-bucket list offsets = exclusive scan of the entry counts the walk left; the total sizes the list array
+        size_t tmpBytes = 0;
+        CK(cudaMemsetAsync((long long *)c->btot.p + nBuckets, 0, sizeof(long long), c->st));
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, (long long *)c->btot.p, (long long *)c->boff64.p, nBuckets + 1, c->st));
+        if ((rc = ensure(c, c->cubtmp, tmpBytes))) return rc;
+        CK(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmpBytes, (long long *)c->btot.p, (long long *)c->boff64.p, nBuckets + 1, c->st));
+        long long nEntries = 0;
+        int hm3[4];
+        CK(cudaMemcpyAsync(&nEntries, (long long *)c->boff64.p + nBuckets, sizeof(long long), cudaMemcpyDeviceToHost, c->st));
+        CK(cudaMemcpyAsync(hm3, c->misc.p, sizeof(hm3), cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        tr.mark("gravity: walk sync");
+        if (hm3[1]) return fail(GG_ERR_UNSUPPORTED, "gg_gravity: walk frontier overflowed %d entries (tree too deep)", GG_STACK_CAP);
+        if ((size_t)hm3[3] > c->capBlocks) {
+            // the chain pool was too small: the walk kept counting, so hm3[3] is what it needs -- grow and run again
+            if (depth >= 2) return fail(GG_ERR_NOMEM, "gg_gravity: list pool overflow persists (%d blocks)", hm3[3]);
+            c->capBlocks = (size_t)hm3[3] + (size_t)hm3[3] / 8 + 1024;
+            return run_gravity(c, prm, singleTask, stats, depth + 1);
+        }
+        nListEntries = nEntries;
+        if ((rc = ensure(c, c->lists, ((size_t)nEntries + 32) * sizeof(unsigned)))) return rc;
+        ta.lists = (unsigned *)c->lists.p;
+        CK(gg_launch_scatter_kernel(ta, c->nSM, c->st));
+        if (c->momPending) CK(cudaStreamWaitEvent(c->st, c->evMom, 0)); // the moments arrive on the second stream
+        CK(cudaEventRecord(c->ev[6], c->st));
+        CK(gg_launch_eval_kernel(ta, c->nSM, c->st));
+        evalQueued = true;
+        evalTimed = true;
+        c->nLaunches += 4;
+    }
+    CK(cudaEventRecord(c->ev[2], c->st));
+
+    CK(cudaStreamWaitEvent(c->st, c->evStats, 0));
     CK(cudaEventRecord(c->ev[4], c->st));
 
     unsigned long long hs[16];
@@ -1035,6 +1127,7 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
     CK(cudaMemcpyAsync(hs, c->sums.p, sizeof(hs), cudaMemcpyDeviceToHost, c->st));
     CK(cudaMemcpyAsync(hm, c->misc.p, sizeof(hm), cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
+    tr.mark("gravity: final sync");
     if (evalQueued) c->momPending = false; // k_eval waited for the moments and has finished
     if (hm[1]) return fail(GG_ERR_UNSUPPORTED, "gg_gravity: walk frontier overflowed %d entries (tree too deep)", GG_STACK_CAP);
     if (!walkOnly && (size_t)hm[3] > c->capBlocks) {
@@ -1059,7 +1152,7 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
         CK(cudaEventElapsedTime(&ms, c->ev[1], c->ev[5])); stats->msWalk = ms;
         if (evalTimed) { CK(cudaEventElapsedTime(&ms, c->ev[6], c->ev[2])); stats->msEval = ms; }
         stats->nListEntries = (double)nListEntries;
-        CK(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3])); stats->msEwald = ms;
+        CK(cudaEventElapsedTime(&ms, c->ev[7], c->ev[3])); stats->msEwald = ms;
         CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[4])); stats->msTotal = ms;
         stats->nKernelLaunches = c->nLaunches;
     }
@@ -1073,13 +1166,34 @@ extern "C" {
 int gg_gravity(gg_context *c, const gg_params *prm, double *a, double *fPot, double *dtGrav, double *fWeight,
                gg_stats *stats) {
     if (!c || !prm) return fail(GG_ERR_ARG, "gg_gravity: null argument");
+    const bool wantOut = !(prm->flags & (GG_FLAG_NO_DOWNLOAD | GG_FLAG_WALK_ONLY));
+    if (wantOut && (!a || !fPot || !dtGrav || !fWeight)) return fail(GG_ERR_ARG, "gg_gravity: null output array");
+    // Zero-copy delivery: in overwrite mode, output arrays that are mapped pinned host memory (gg_host_alloc,
+    // cudaHostAlloc, cudaHostRegister) are written by the kernels themselves as each sink bucket finishes, so the
+    // device->host transfer overlaps the evaluation instead of following it.  Only ACTIVE particles are written
+    // (the reference's contract, pkd.c:2851-2861).  Anything else takes the staged copy below.
+    bool zeroCopy = false;
+    c->zc[0] = c->zc[1] = c->zc[2] = c->zc[3] = nullptr;
+    if (wantOut && !prm->accumulate && !c->dom.empty() && c->dom[0].nPart > 0) {
+        double *hp[4] = {a, fPot, dtGrav, fWeight}, *dp[4] = {nullptr, nullptr, nullptr, nullptr};
+        zeroCopy = true;
+        CK(cudaSetDevice(c->device));
+        for (int k = 0; k < 4 && zeroCopy; ++k) {
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, hp[k]) != cudaSuccess) { cudaGetLastError(); zeroCopy = false; break; }
+            if (at.type != cudaMemoryTypeHost || !at.devicePointer) zeroCopy = false;
+            else dp[k] = (double *)at.devicePointer;
+        }
+        if (zeroCopy) for (int k = 0; k < 4; ++k) { c->zc[k] = dp[k]; c->zcHost[k] = hp[k]; }
+    }
     int rc = run_gravity(c, prm, nullptr, stats);
+    c->zc[0] = c->zc[1] = c->zc[2] = c->zc[3] = nullptr;
     if (rc) return rc;
-    if (prm->flags & (GG_FLAG_NO_DOWNLOAD | GG_FLAG_WALK_ONLY)) return GG_OK;
-    if (!a || !fPot || !dtGrav || !fWeight) return fail(GG_ERR_ARG, "gg_gravity: null output array");
+    if (!wantOut || zeroCopy) return GG_OK;
     const int n = c->dom[0].nPart;
     if (n == 0) return GG_OK;
-    if (!prm->accumulate) { // overwrite: straight into the caller's arrays
+    const bool all = c->hActive.empty();
+    if (!prm->accumulate && all) { // overwrite, every particle active: straight into the caller's arrays
         CK(cudaMemcpyAsync(a, c->acc.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->st));
         CK(cudaMemcpyAsync(fPot, c->pot.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->st));
         CK(cudaMemcpyAsync(dtGrav, c->dtg.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->st));
@@ -1087,6 +1201,8 @@ int gg_gravity(gg_context *c, const gg_params *prm, double *a, double *fPot, dou
         CK(cudaStreamSynchronize(c->st));
         return GG_OK;
     }
+    // staged: pinned bounce buffer, then += / max / = (accumulate, the reference's in-place semantics: pkd.c:2851-2861,
+    // grav.c:100,192-195) or plain assignment (overwrite) on ACTIVE particles only -- inactive ones are never touched
     if ((rc = ensure_pinned(c, sizeof(double) * 6 * (size_t)n))) return rc;
     double *h = (double *)c->pinned, *ha = h, *hp = h + 3 * (size_t)n, *hd = hp + n, *hw = hd + n;
     CK(cudaMemcpyAsync(ha, c->acc.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->st));
@@ -1094,15 +1210,35 @@ int gg_gravity(gg_context *c, const gg_params *prm, double *a, double *fPot, dou
     CK(cudaMemcpyAsync(hd, c->dtg.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->st));
     CK(cudaMemcpyAsync(hw, c->fweight.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
-    const bool all = c->hActive.empty();
-    for (int i = 0; i < n; ++i) { // += / max / = on active particles only (pkd.c:2851-2861, grav.c:100,192-195)
-        if (!all && !c->hActive[i]) continue;
-        a[3 * (size_t)i] += ha[3 * (size_t)i];
-        a[3 * (size_t)i + 1] += ha[3 * (size_t)i + 1];
-        a[3 * (size_t)i + 2] += ha[3 * (size_t)i + 2];
-        fPot[i] += hp[i];
-        if (hd[i] > dtGrav[i]) dtGrav[i] = hd[i];
-        fWeight[i] = hw[i];
+    const int *act = all ? nullptr : c->hActive.data();
+    const bool acc = prm->accumulate != 0;
+    auto merge = [=](int i0, int i1) {
+        for (int i = i0; i < i1; ++i) {
+            if (act && !act[i]) continue;
+            if (acc) {
+                a[3 * (size_t)i] += ha[3 * (size_t)i];
+                a[3 * (size_t)i + 1] += ha[3 * (size_t)i + 1];
+                a[3 * (size_t)i + 2] += ha[3 * (size_t)i + 2];
+                fPot[i] += hp[i];
+                if (hd[i] > dtGrav[i]) dtGrav[i] = hd[i];
+            } else {
+                a[3 * (size_t)i] = ha[3 * (size_t)i];
+                a[3 * (size_t)i + 1] = ha[3 * (size_t)i + 1];
+                a[3 * (size_t)i + 2] = ha[3 * (size_t)i + 2];
+                fPot[i] = hp[i];
+                dtGrav[i] = hd[i];
+            }
+            fWeight[i] = hw[i];
+        }
+    };
+    const int nT = n >= (1 << 17) ? 4 : 1; // the merge is memory-bound: a few threads saturate it
+    if (nT == 1) merge(0, n);
+    else {
+        std::vector<std::thread> th;
+        const int chunk = (n + nT - 1) / nT;
+        for (int t = 1; t < nT; ++t) th.emplace_back(merge, t * chunk, std::min(n, (t + 1) * chunk));
+        merge(0, std::min(n, chunk));
+        for (auto &t : th) t.join();
     }
     return GG_OK;
 }

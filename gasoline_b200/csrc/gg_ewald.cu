@@ -180,6 +180,7 @@ __global__ void __launch_bounds__(256) k_stats(const StatsKernelArgs A) {
             int pi = bk.pLower + j;
             if (A.active && !A.active[pi]) continue;
             A.fWeight[pi] = (double)flopI + (double)flopE;
+            if (A.hfWeight) A.hfWeight[pi] = (double)flopI + (double)flopE;
         }
         v[0] = (unsigned long long)n; v[1] = (unsigned long long)part; v[2] = (unsigned long long)((long long)n * nN);
         v[3] = (unsigned long long)((long long)n * nS); v[4] = (unsigned long long)flopI; v[5] = (unsigned long long)flopE;

@@ -101,6 +101,9 @@ struct TreeKernelArgs {
     double *dtg;
     int *counts;             // [nLocalNodes][3]
     int *errFlag;
+    // zero-copy result delivery: the caller's a / fPot / dtGrav arrays when they are mapped pinned host memory (device
+    // aliases, else null) -- k_eval stores every finished sink there as well, so the download overlaps the evaluation
+    double *hacc, *hpot, *hdtg;
 };
 
 struct EwaldKernelArgs {
@@ -128,6 +131,7 @@ struct StatsKernelArgs {
     const int *nLoop;        // may be null (no Ewald)
     int nEwh, iOrder, iEwOrder;
     double *fWeight;
+    double *hfWeight;        // the caller's fWeight array (mapped pinned host memory) or null
     unsigned long long *sums; // [0] nActive [1] part [2] cell [3] soft [4] flopI [5] flopE [6..8] max lists
 };
 
@@ -136,3 +140,7 @@ cudaError_t gg_launch_scatter_kernel(const TreeKernelArgs &a, int nSM, cudaStrea
 cudaError_t gg_launch_eval_kernel(const TreeKernelArgs &a, int nSM, cudaStream_t st);
 cudaError_t gg_launch_ewald_kernel(const EwaldKernelArgs &a, cudaStream_t st);
 cudaError_t gg_launch_stats_kernel(const StatsKernelArgs &a, cudaStream_t st);
+// gg_moments.cu: multipole moments of a domain's cells from its particles, on the device (two kernels on st)
+cudaError_t gg_launch_device_moments(int nn, const NodeW *nodes, int nodeBase, int partBase, int iRootLocal,
+                                     const double *x, const double *y, const double *z, const double *m, int *parent,
+                                     int *arrive, double *raw, float4 *momf, double *momq, cudaStream_t st);

@@ -377,3 +377,42 @@ extern "C" int gg_cell_moments(int n, const double *x, const double *y, const do
     cell_moments(p.data(), 0, n - 1, rcm, iOrder, mom, pBmax);
     return GG_OK;
 }
+
+// The moments of every cell by the DEVICE's algorithm (gg_moments.cu: raw moments of the buckets, children translated
+// and summed in (lower, upper) order, gg_raw_reduce), run on the host: lets the CPU test suite check the translation
+// and reduction formulas of gg_m2m.h against the particle-by-particle sums of pkdCalcCell without a GPU.
+#include "gg_m2m.h"
+extern "C" int gg_tree_moments_m2m(const gg_tree *t, const gg_particles *pp, double *mom) {
+    if (!t || !pp || !mom || t->nNodes < 1) return GG_ERR_ARG;
+    const int nn = t->nNodes;
+    std::vector<GGRawMom> raw((size_t)nn);
+    std::vector<char> done((size_t)nn, 0);
+    std::vector<int> st{t->iRoot};
+    while (!st.empty()) {
+        const int g = st.back();
+        const int c0 = t->iLower[g];
+        if (c0 < 0) {
+            GGRawMom a;
+            gg_raw_zero(a);
+            for (int i = t->pLower[g]; i <= t->pUpper[g]; ++i)
+                gg_raw_add_particle(a, pp->fMass[i], pp->x[i] - t->r[3 * (size_t)g], pp->y[i] - t->r[3 * (size_t)g + 1],
+                                    pp->z[i] - t->r[3 * (size_t)g + 2]);
+            raw[g] = a;
+        } else {
+            const int c1 = t->iUpper[c0];
+            if (!done[c0]) { st.push_back(c1); st.push_back(c0); continue; }
+            GGRawMom a;
+            gg_raw_zero(a);
+            const int kids[2] = {c0, c1};
+            for (int k = 0; k < 2; ++k)
+                gg_raw_shift_add(a, raw[kids[k]], t->r[3 * (size_t)kids[k]] - t->r[3 * (size_t)g],
+                                 t->r[3 * (size_t)kids[k] + 1] - t->r[3 * (size_t)g + 1],
+                                 t->r[3 * (size_t)kids[k] + 2] - t->r[3 * (size_t)g + 2]);
+            raw[g] = a;
+        }
+        gg_raw_reduce(raw[g], &mom[(size_t)GG_NMOM * g]);
+        done[g] = 1;
+        st.pop_back();
+    }
+    return GG_OK;
+}

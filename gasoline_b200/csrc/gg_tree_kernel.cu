@@ -990,11 +990,19 @@ __global__ void __launch_bounds__(GG_WARPS_PER_CTA * 32, MONO64 ? GG_MIN_CTAS - 
                     vx += red[4 * l]; vy += red[4 * l + 1]; vz += red[4 * l + 2]; vp += red[4 * l + 3];
                     vd = fmaxf(vd, redt[l]);
                 }
-                A.acc[3 * (size_t)K.sidx] = vx;
-                A.acc[3 * (size_t)K.sidx + 1] = vy;
-                A.acc[3 * (size_t)K.sidx + 2] = vz;
-                A.pot[K.sidx] = vp;
-                A.dtg[K.sidx] = (double)vd;
+                // the Ewald correction and the comoving background term (pkd.c:2962-2991) were accumulated before this
+                // kernel; the tree sum is added to them here (a + b == b + a bit for bit), so this store is final and
+                // can go straight to the caller's mapped host arrays as well
+                const size_t si = (size_t)K.sidx;
+                vx += A.acc[3 * si]; vy += A.acc[3 * si + 1]; vz += A.acc[3 * si + 2]; vp += A.pot[si];
+                A.acc[3 * si] = vx; A.acc[3 * si + 1] = vy; A.acc[3 * si + 2] = vz;
+                A.pot[si] = vp;
+                A.dtg[si] = (double)vd;
+                if (A.hacc) {
+                    A.hacc[3 * si] = vx; A.hacc[3 * si + 1] = vy; A.hacc[3 * si + 2] = vz;
+                    A.hpot[si] = vp;
+                    A.hdtg[si] = (double)vd;
+                }
             }
         }
         __syncwarp();

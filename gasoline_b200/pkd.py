@@ -91,6 +91,7 @@ def load_library(path: str | None = None):
     L.gg_tree_view.argtypes = [C.c_void_p, C.POINTER(gg_tree), _dp]
     L.gg_tree_free.argtypes = [C.c_void_p]
     L.gg_cell_moments.argtypes = [C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_int, _dp, _dp]
+    L.gg_tree_moments_m2m.argtypes = [C.POINTER(gg_tree), C.POINTER(gg_particles), _dp]
     L.gg_measure_fp32_peak.argtypes = [C.c_void_p, _dp, _dp]
     L.gg_flush_l2.argtypes = [C.c_void_p]
     _lib = L
@@ -149,10 +150,11 @@ class Tree:
             dt = np.int32 if k[0] in "pi" else np.float64
             setattr(self, k, np.ascontiguousarray(arrays[k], dtype=dt))
 
-    def view(self) -> gg_tree:
+    def view(self, with_mom: bool = True) -> gg_tree:
+        """with_mom=False leaves gg_tree.mom NULL: the device forms the cells' moments itself (gg_moments.cu)."""
         return gg_tree(self.nNodes, self.iRoot, _d(self.bnd), _d(self.r), _d(self.fMass), _d(self.fSoft),
-                       _d(self.fOpen2), _d(self.mom), _i(self.pLower), _i(self.pUpper), _i(self.iLower),
-                       _i(self.iUpper))
+                       _d(self.fOpen2), _d(self.mom) if with_mom else None, _i(self.pLower), _i(self.pUpper),
+                       _i(self.iLower), _i(self.iUpper))
 
     def as_dict(self):
         d = {k: getattr(self, k) for k in self.FIELDS}
@@ -163,11 +165,14 @@ class Tree:
 class PKD:
     """One rank's particle store + tree on one B200 (mirrors struct pkdContext, pkd.h:597-660)."""
 
-    def __init__(self, device: int = -1, idSelf: int = 0, fPeriod=(FLOAT_MAXVAL,) * 3, pinned: bool = False):
+    def __init__(self, device: int = -1, idSelf: int = 0, fPeriod=(FLOAT_MAXVAL,) * 3, pinned: bool = False,
+                 device_moments: bool = False):
         """pinned: keep pStore / kdNodes copies in page-locked host memory (what a host does with gg_host_alloc so
-        that the per-step upload runs at full PCIe/C2C speed)."""
+        that the per-step upload runs at full PCIe/C2C speed).  device_moments: do not transfer kdNodes[].mom (58 % of
+        the upload); the device forms the multipole moments from the particles (gg_tree.mom = NULL)."""
         self._L = load_library()
         self.pinned = pinned
+        self.device_moments = bool(device_moments)
         self._ctx = C.c_void_p()
         _check(self._L.gg_create(C.byref(self._ctx), device), "gg_create")
         self.idSelf = idSelf
@@ -252,7 +257,7 @@ class PKD:
         """Ingest pStore + kdNodes into HBM (gg_set_local); also pkd->ilcnRoot when present."""
         if self.tree is None:
             raise GasolineB200Error("upload: build or set a tree first")
-        tv = self.tree.view()
+        tv = self.tree.view(with_mom=not self.device_moments)
         pv = gg_particles(self.nLocal, _d(self.x), _d(self.y), _d(self.z), _d(self.fMass), _d(self.fSoft),
                           _i(self.active) if self.active is not None else None)
         _check(self._L.gg_set_local(self._ctx, self.idSelf, C.byref(tv), C.byref(pv)), "gg_set_local")
@@ -340,11 +345,20 @@ class PKD:
     def upload_bytes(self) -> int:
         """Bytes gg_set_local copies host->device for the current tree + particles."""
         t = self.tree
-        b = sum(getattr(t, k).nbytes for k in Tree.FIELDS if k != "bnd")
+        b = sum(getattr(t, k).nbytes for k in Tree.FIELDS if k != "bnd" and not (k == "mom" and self.device_moments))
         b += sum(a.nbytes for a in (self.x, self.y, self.z, self.fMass, self.fSoft))
         if self.active is not None:
             b += self.active.nbytes
         return int(b)
+
+    def tree_moments_m2m(self) -> np.ndarray:
+        """The cells' reduced multipoles by the device's bottom-up algorithm, executed on the host
+        (gg_tree_moments_m2m): [nNodes][GG_NMOM]."""
+        out = np.zeros((self.tree.nNodes, GG_NMOM))
+        tv = self.tree.view()
+        pv = gg_particles(self.nLocal, _d(self.x), _d(self.y), _d(self.z), _d(self.fMass), _d(self.fSoft), None)
+        _check(self._L.gg_tree_moments_m2m(C.byref(tv), C.byref(pv), _d(out)), "gg_tree_moments_m2m")
+        return out
 
     def measure_fp32_peak(self):
         """(TFLOP/s, ms) of the dependent-FFMA microbenchmark on this GPU (gg_measure_fp32_peak)."""

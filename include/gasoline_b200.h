@@ -50,7 +50,9 @@ typedef struct gg_tree {
     const double *fMass;  /* [nNodes] */
     const double *fSoft;  /* [nNodes]     mass-weighted softening */
     const double *fOpen2; /* [nNodes]     squared opening radius (pkdCalcOpen, pkd.c:2228) */
-    const double *mom;    /* [nNodes][GG_NMOM] reduced multipoles about r (pkdCalcCell, pkd.c:2018) */
+    const double *mom;    /* [nNodes][GG_NMOM] reduced multipoles about r (pkdCalcCell, pkd.c:2018); NULL: the device
+                             forms them itself from the particles (same definition, summed bottom-up in FP64) and the
+                             248 B per cell are not transferred -- r, fMass, fSoft, fOpen2 stay the host's */
     const int *pLower;    /* [nNodes] */
     const int *pUpper;    /* [nNodes] */
     const int *iLower;    /* [nNodes] */
@@ -206,6 +208,11 @@ int gg_tree_build(int n, double *x, double *y, double *z, double *fMass, double 
 int gg_tree_view(const gg_built_tree *bt, gg_tree *view, double root[GG_NROOT]);
 void gg_tree_free(gg_built_tree *bt);
 
+
+/* Every cell's reduced multipoles by the algorithm the DEVICE uses when gg_tree.mom is NULL (raw moments of the
+ * buckets, children translated to the parent's centre and summed, then reduced as pkdCalcCell defines them), executed
+ * on the host: mom[nNodes][GG_NMOM].  A checking aid for hosts and tests; no GPU needed. */
+int gg_tree_moments_m2m(const gg_tree *tree, const gg_particles *part, double *mom);
 
 /* pkdCalcCell (pkd.c:2018-2135) over all n particles of a domain about the centre rcm: reduced multipoles in GG_NMOM
  * order and Bmax -- one rank's contribution to an interior cell of the top tree, which pstCalcCell (pst.c:3789) sums

@@ -86,3 +86,35 @@ def test_host_tree_builder_matches_reference_tree(lib, name):
         assert np.array_equal(order, z["tree_iOrder"])
         assert np.array_equal(root, z["tree_root"])
         lib.gg_tree_free(bt)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_bottom_up_moments_match_particle_sums(lib, name):
+    """gg_tree_moments_m2m = the device's moment algorithm (gg_moments.cu / gg_m2m.h: raw bucket moments, children
+    translated and summed, reduced as pkd.c:2056-2131) run on the host, against the REFERENCE's particle-by-particle
+    pkdCalcCell sums stored in the golden fixture.  Same quantity, different summation order: agreement to FP64
+    rounding of the largest term, M * Bmax^l."""
+    from gasoline_b200 import pkd as pk
+    p, active, theta, kw, z = load(name)
+    nn = int(z["nNodes"])
+    order = z["tree_iOrder"]
+    cols = [np.ascontiguousarray(np.asarray(a, dtype=np.float64)[order]) for a in (p.x, p.y, p.z, p.m, p.h)]
+    ints = {k: np.ascontiguousarray(z["tree_" + k], dtype=np.int32) for k in ("pLower", "pUpper", "iLower", "iUpper")}
+    dbl = {k: np.ascontiguousarray(z["tree_" + k], dtype=np.float64) for k in ("bnd", "r", "fMass", "fSoft", "fOpen2", "mom")}
+    tv = pk.gg_tree(nn, int(z["iRoot"]), pk._d(dbl["bnd"]), pk._d(dbl["r"]), pk._d(dbl["fMass"]), pk._d(dbl["fSoft"]),
+                    pk._d(dbl["fOpen2"]), None, pk._i(ints["pLower"]), pk._i(ints["pUpper"]), pk._i(ints["iLower"]),
+                    pk._i(ints["iUpper"]))
+    pv = pk.gg_particles(p.n, *[pk._d(c) for c in cols], None)
+    out = np.zeros((nn, 31))
+    assert lib.gg_tree_moments_m2m(C.byref(tv), C.byref(pv), pk._d(out)) == 0
+    ref = dbl["mom"]
+    # scale of order l: M * Bmax^l, with Bmax recovered from fOpen2 = max(Bmax, 2/sqrt(3) Bmax/theta)^2
+    bmax = np.sqrt(dbl["fOpen2"]) / max(1.0, 2.0 / np.sqrt(3.0) / theta)
+    M = dbl["fMass"]
+    for lo, hi, l in ((0, 6, 2), (6, 16, 3), (16, 31, 4)):
+        scale = (M * bmax ** l)[:, None]
+        ok = scale[:, 0] > 0
+        err = np.abs(out[ok, lo:hi] - ref[ok, lo:hi]) / scale[ok]
+        assert err.max() < 2e-13, (l, err.max())
+    # single-particle / zero-extent cells: both are exactly zero
+    assert np.all(out[bmax == 0] == 0)

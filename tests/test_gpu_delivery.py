@@ -1,0 +1,54 @@
+"""Result delivery of gg_gravity (pkd.c:2851-2861 semantics): zero-copy stores into mapped pinned host arrays must be
+bit-identical to the staged device->host copy, for open and periodic (Ewald-first ordering) runs, and must leave
+inactive particles untouched."""
+import numpy as np
+import pytest
+
+from gasoline_b200 import ics
+from gasoline_b200.pkd import PKD, GravityParams, pinned_empty
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "plummer20k": (lambda: ics.plummer(20000), GravityParams(nReps=0, bPeriodic=0, bEwald=0)),
+    "periodic16_ewald": (lambda: ics.periodic_box(16), GravityParams(nReps=1, bPeriodic=1, bEwald=1)),
+    "plummer_comove": (lambda: ics.plummer(5000), GravityParams(nReps=0, bPeriodic=0, bEwald=0, bComove=1, dRhoFac=0.37)),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_zero_copy_equals_staged(name, gpu_lib):
+    mk, g = CASES[name]
+    p = mk()
+    pkd = PKD(fPeriod=p.period, pinned=True)
+    pkd.pkdLoadParticles(p.x, p.y, p.z, p.m, p.h)
+    pkd.pkdBuildBinary(8, 0.7, 4)
+    n = pkd.nLocal
+    staged = pkd.pkdGravAll(g)  # fresh pageable arrays -> staged copy
+    pin = [pinned_empty((n, 3)), pinned_empty(n), pinned_empty(n), pinned_empty(n)]
+    for v in pin:
+        v[...] = np.nan
+    pkd.pkdGravAll(g, *pin, accumulate=False)  # mapped pinned arrays -> stored by the kernels
+    for nm, u in zip(("acc", "pot", "dtGrav", "fWeight"), pin):
+        assert np.array_equal(u, staged[nm]), nm
+    pkd.close()
+
+
+def test_zero_copy_leaves_inactive_untouched(gpu_lib):
+    p = ics.plummer(8000, seed=11)
+    active = (np.random.default_rng(5).random(p.n) < 0.4).astype(np.int32)
+    g = GravityParams(nReps=0, bPeriodic=0, bEwald=0)
+    pkd = PKD(fPeriod=p.period, pinned=True)
+    pkd.pkdLoadParticles(p.x, p.y, p.z, p.m, p.h, active)
+    pkd.pkdBuildBinary(8, 0.7, 4)
+    n = pkd.nLocal
+    act = pkd.active.astype(bool)
+    staged = pkd.pkdGravAll(g)
+    pin = [pinned_empty((n, 3)), pinned_empty(n), pinned_empty(n), pinned_empty(n)]
+    for v in pin:
+        v[...] = -7.0
+    pkd.pkdGravAll(g, *pin, accumulate=False)
+    for nm, u in zip(("acc", "pot", "dtGrav", "fWeight"), pin):
+        assert np.array_equal(u[act], staged[nm][act]), nm
+        assert np.all(u[~act] == -7.0), nm
+    pkd.close()
