@@ -198,13 +198,8 @@ __global__ void k_pack_mom(int n, const double *mom, int nodeBase, float4 *momf,
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double *q = &mom[(size_t)GG_NMOM * i];
-    double tr = q[0] + q[1] + q[2];
     float f[32];
-    f[0] = (float)(q[0] - tr / 3.0); f[1] = (float)(q[1] - tr / 3.0); f[2] = (float)(q[2] - tr / 3.0);
-    f[3] = (float)q[3]; f[4] = (float)q[4]; f[5] = (float)q[5];
-#pragma unroll
-    for (int k = 6; k < GG_NMOM; ++k) f[k] = (float)q[k];
-    f[31] = 0.f;
+    gg_pack_momf(q, f);
     float4 *o = &momf[(size_t)(nodeBase + i) * 8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) o[k] = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
@@ -853,11 +848,7 @@ int pack_top(gg_context *c, int *pRoot) {
         o.pLower = 0;
         o.nP = 1 << 30; // exempt from the "< 4 particles" rule: the top walk has no such test (walk.c:363-371)
         const double *q = &c->topMom[(size_t)GG_NMOM * i];
-        double tr = q[0] + q[1] + q[2];
-        float *f = &mf[(size_t)i * 32];
-        f[0] = (float)(q[0] - tr / 3.0); f[1] = (float)(q[1] - tr / 3.0); f[2] = (float)(q[2] - tr / 3.0);
-        f[3] = (float)q[3]; f[4] = (float)q[4]; f[5] = (float)q[5];
-        for (int k = 6; k < GG_NMOM; ++k) f[k] = (float)q[k];
+        gg_pack_momf(q, &mf[(size_t)i * 32]);
         for (int k = 0; k < 6; ++k) mq[(size_t)i * 6 + k] = q[k];
     }
     int rc;

@@ -14,12 +14,17 @@
 #include <stdint.h>
 #include "../../include/gasoline_b200.h"
 
+#ifndef GG_WARPS_PER_CTA
 #define GG_WARPS_PER_CTA 4   // k_eval
+#endif
 #ifndef GG_MIN_CTAS
 #define GG_MIN_CTAS 5        // resident CTAs per SM k_eval is compiled for (44 KB shared memory each; register cap 102)
 #endif
 #ifndef GG_CELL_UNROLL
 #define GG_CELL_UNROLL 1     // unroll factor of k_eval's (sink, cell) loop
+#endif
+#ifndef GG_EVAL_BSG
+#define GG_EVAL_BSG 1       // k_eval stages blocks of the largest multiple of G cells (<= 32) instead of always 32
 #endif
 #define GG_WALK_WARPS 8      // k_walk
 #define GG_WALK_MIN_CTAS 4   // 32 warps per SM (register cap 64)
@@ -36,6 +41,21 @@ typedef unsigned short gg_mask_t;
 #define GG_STACK_CAP 512    // walk frontier entries per warp
 #define GG_STACK_DFS_MARGIN 128
 #define GG_MAX_IMAGES 128
+
+// The FP32 evaluation record of one cell from the reference's reduced multipoles q[GG_NMOM] (pkdCalcCell order): the
+// quadrupole made traceless like SETILIST (walk.c:41-48), and each order pre-multiplied by (2l-1)!! -- 3, 15, 105 -- so
+// that k_eval needs only the bare powers 1/r^(2l+1) instead of gam[l] = (2l-1)!!/r^(2l+1) (grav.c:172-191).
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline void gg_pack_momf(const double *q, float *f) {
+    const double tr = (q[0] + q[1] + q[2]) / 3.0;
+    f[0] = (float)(3.0 * (q[0] - tr)); f[1] = (float)(3.0 * (q[1] - tr)); f[2] = (float)(3.0 * (q[2] - tr));
+    f[3] = (float)(3.0 * q[3]); f[4] = (float)(3.0 * q[4]); f[5] = (float)(3.0 * q[5]);
+    for (int k = 6; k < 16; ++k) f[k] = (float)(15.0 * q[k]);
+    for (int k = 16; k < 31; ++k) f[k] = (float)(105.0 * q[k]);
+    f[31] = 0.f;
+}
 
 struct __align__(16) NodeW {
     double rx, ry, rz;

@@ -46,13 +46,8 @@ __device__ __forceinline__ void load_raw(const double *raw, GGRawMom &r) { // L2
 __device__ __forceinline__ void finish_cell(const GGRawMom &r, float4 *momf, double *momq) {
     double q[31];
     gg_raw_reduce(r, q);
-    const double tr = q[0] + q[1] + q[2];
     float f[32];
-    f[0] = (float)(q[0] - tr / 3.0); f[1] = (float)(q[1] - tr / 3.0); f[2] = (float)(q[2] - tr / 3.0);
-    f[3] = (float)q[3]; f[4] = (float)q[4]; f[5] = (float)q[5];
-#pragma unroll
-    for (int k = 6; k < 31; ++k) f[k] = (float)q[k];
-    f[31] = 0.f;
+    gg_pack_momf(q, f);
 #pragma unroll
     for (int k = 0; k < 8; ++k) momf[k] = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
 #pragma unroll

@@ -99,31 +99,40 @@ struct CellMom {
 };
 
 // Reduced-multipole evaluation of one Newtonian cell on one sink (QEVAL qeval.h:21-64 + gam[] grav.c:172-191),
-// restructured around scaled monomials so every moment is used in exactly one FMA per force component.
-// Returns the contribution (fx,fy,fz) to the acceleration, fp to -potential and 1/dt^2.
-// MONO64: leave the monopole term out (the caller adds it in FP64, see eval_cells) and hand back the FP32 1/r.
+// restructured so that every moment is used in exactly one FMA per force component and the per-order constants
+// disappear: the record holds (2l-1)!! x the moments (gg_pack_momf), so the kernel needs only e_l = 1/r^(2l+1)
+// (one FMUL each).  With A = e2 (Q'r).r, B = e3 (O'rr).r, C = e4 (H'rrr).r:
+//     -phi  = M/r + A/2 + B/3 + C/4
+//     a     = e2 Q'r + e3 O'rr/2 + e4 H'rrr/6 - r [ M e1 + (5A/2 + 7B/3 + 9C/4)/r^2 ]
+// The three force components chain straight onto the lane's running sums (ax, ay, az); ap accumulates -phi and dtm
+// the running maximum of 1/dt^2 = (m_sink + M)/r^3 (grav.c:189-190).  ~126 FP32 instructions at hexadecapole order
+// (the reference scores 312 flops).  MONO64: the monopole term is left to the caller (FP64, see eval_cells), which
+// gets the FP32 1/r back through pg0.
 template <int ORDER, bool MONO64 = false>
 __device__ __forceinline__ void cell_on_sink(const CellMom &c, float M, float dx, float dy, float dz, float ms,
-                                             float &ox_, float &oy_, float &oz_, float &op_, float &odt, float *pg0 = nullptr) {
+                                             float &ax, float &ay, float &az, float &ap, float &dtm, float *pg0 = nullptr) {
     const float xx = dx * dx, yy = dy * dy, zz = dz * dz;
     const float d2 = xx + yy + zz;
     const float g0 = rsqrt_nr(d2);
-    const float dir2 = g0 * g0;
-    const float g1 = g0 * dir2;
-    float fx = 0.f, fy = 0.f, fz = 0.f, ta = MONO64 ? 0.f : g1 * M, fp = MONO64 ? 0.f : g0 * M;
+    const float u = g0 * g0;
+    const float e1 = g0 * u;
     if (MONO64) *pg0 = g0;
+    dtm = fmaxf(dtm, (ms + M) * e1);
+    float fp = MONO64 ? 0.f : g0 * M;
+    float ts = 0.f;
+    float fx = ax, fy = ay, fz = az;
     if (ORDER >= 2) {
-        const float g2 = 3.f * g1 * dir2, g3 = 5.f * g2 * dir2;
+        const float e2 = e1 * u;
         const float Qxx = c.m0.x, Qyy = c.m0.y, Qzz = c.m0.z, Qxy = c.m0.w, Qxz = c.m1.x, Qyz = c.m1.y;
         const float qx = fmaf(Qxz, dz, fmaf(Qxy, dy, Qxx * dx));
         const float qy = fmaf(Qyz, dz, fmaf(Qxy, dx, Qyy * dy));
         const float qz = fmaf(Qyz, dy, fmaf(Qxz, dx, Qzz * dz));
-        const float qr = 0.5f * fmaf(qz, dz, fmaf(qy, dy, qx * dx));
-        fp = fmaf(g2, qr, fp);
-        ta = fmaf(g3, qr, ta);
-        fx = g2 * qx; fy = g2 * qy; fz = g2 * qz;
+        const float A = e2 * fmaf(qz, dz, fmaf(qy, dy, qx * dx));
+        fp = fmaf(0.5f, A, fp);
+        ts = 2.5f * A;
+        fx = fmaf(e2, qx, fx); fy = fmaf(e2, qy, fy); fz = fmaf(e2, qz, fz);
         if (ORDER >= 3) {
-            const float g4 = 7.f * g3 * dir2;
+            const float e3 = e2 * u;
             const float hxx = 0.5f * xx, hyy = 0.5f * yy, hzz = 0.5f * zz;
             const float xy = dx * dy, xz = dx * dz, yz = dy * dz;
             const float Oxxx = c.m1.z, Oxyy = c.m1.w, Oxxy = c.m2.x, Oyyy = c.m2.y, Oxxz = c.m2.z, Oyyz = c.m2.w,
@@ -131,12 +140,12 @@ __device__ __forceinline__ void cell_on_sink(const CellMom &c, float M, float dx
             const float ox = fmaf(Oxzz, hzz, fmaf(Oxyz, yz, fmaf(Oxyy, hyy, fmaf(Oxxz, xz, fmaf(Oxxy, xy, Oxxx * hxx)))));
             const float oy = fmaf(Oyzz, hzz, fmaf(Oyyz, yz, fmaf(Oyyy, hyy, fmaf(Oxyz, xz, fmaf(Oxyy, xy, Oxxy * hxx)))));
             const float oz = fmaf(Ozzz, hzz, fmaf(Oyzz, yz, fmaf(Oyyz, hyy, fmaf(Oxzz, xz, fmaf(Oxyz, xy, Oxxz * hxx)))));
-            const float orr = (1.f / 3.f) * fmaf(oz, dz, fmaf(oy, dy, ox * dx));
-            fp = fmaf(g3, orr, fp);
-            ta = fmaf(g4, orr, ta);
-            fx = fmaf(g3, ox, fx); fy = fmaf(g3, oy, fy); fz = fmaf(g3, oz, fz);
+            const float B = e3 * fmaf(oz, dz, fmaf(oy, dy, ox * dx));
+            fp = fmaf(1.f / 3.f, B, fp);
+            ts = fmaf(7.f / 3.f, B, ts);
+            fx = fmaf(e3, ox, fx); fy = fmaf(e3, oy, fy); fz = fmaf(e3, oz, fz);
             if (ORDER >= 4) {
-                const float g5 = 9.f * g4 * dir2;
+                const float e4 = e3 * u;
                 // cubic monomials with multiplicity/6: x^3/6, x^2 y/2, xyz, ...
                 const float cxxx = (1.f / 3.f) * hxx * dx, cyyy = (1.f / 3.f) * hyy * dy, czzz = (1.f / 3.f) * hzz * dz;
                 const float cxxy = hxx * dy, cxxz = hxx * dz, cxyy = hyy * dx, cyyz = hyy * dz, cxzz = hzz * dx,
@@ -153,18 +162,18 @@ __device__ __forceinline__ void cell_on_sink(const CellMom &c, float M, float dx
                 const float hz = fmaf(Hzzzz, czzz, fmaf(Hyzzz, cyzz, fmaf(Hyyzz, cyyz, fmaf(Hyyyz, cyyy,
                                  fmaf(Hxzzz, cxzz, fmaf(Hxyzz, cxyz, fmaf(Hxyyz, cxyy, fmaf(Hxxzz, cxxz,
                                  fmaf(Hxxyz, cxxy, Hxxxz * cxxx)))))))));
-                const float hr = 0.25f * fmaf(hz, dz, fmaf(hy, dy, hx * dx));
-                fp = fmaf(g4, hr, fp);
-                ta = fmaf(g5, hr, ta);
-                fx = fmaf(g4, hx, fx); fy = fmaf(g4, hy, fy); fz = fmaf(g4, hz, fz);
+                const float C = e4 * fmaf(hz, dz, fmaf(hy, dy, hx * dx));
+                fp = fmaf(0.25f, C, fp);
+                ts = fmaf(2.25f, C, ts);
+                fx = fmaf(e4, hx, fx); fy = fmaf(e4, hy, fy); fz = fmaf(e4, hz, fz);
             }
         }
     }
-    op_ = fp;
-    ox_ = fmaf(-dx, ta, fx);
-    oy_ = fmaf(-dy, ta, fy);
-    oz_ = fmaf(-dz, ta, fz);
-    odt = (ms + M) * g1; // grav.c:189-190
+    const float ta = MONO64 ? u * ts : fmaf(u, ts, e1 * M);
+    ax = fmaf(-dx, ta, fx);
+    ay = fmaf(-dy, ta, fy);
+    az = fmaf(-dz, ta, fz);
+    ap += fp;
 }
 
 // Particle-particle kernel with Hernquist-Katz K3 spline softening (SPLINEM grav.h:53-69, grav.c:89-108).
@@ -699,7 +708,7 @@ struct Sink {
     double dax, day, daz, dap;
     double sxd, syd, szd; // MONO64 only: the sink's position relative to the bucket centre in FP64
     __device__ __forceinline__ void fold() { // FP32 partial sums of one block -> FP64
-        dax += (double)ax; day += (double)ay; daz += (double)az; dap += (double)ap;
+        dax += (double)ax; day += (double)ay; daz += (double)az; dap -= (double)ap; // ap accumulates -phi
         ax = ay = az = ap = 0.f;
     }
 };
@@ -726,11 +735,19 @@ __device__ __forceinline__ void gather_cells(const TreeKernelArgs &A, SM &W, int
     if (ORDER >= 2) {
         constexpr int LPR = ORDER == 2 ? 2 : (ORDER == 3 ? 4 : 8); // float4 pieces of the record in use
         const int piece = lane & (LPR - 1), sub = lane / LPR;
+        // one shuffle, one 64-bit multiply-add and the copy per record: the lane's piece offset is folded into both
+        // bases once, and the shared-memory address of trip i is the base plus a compile-time constant
+        const unsigned sdst = (unsigned)__cvta_generic_to_shared(&W.stage[buf][sub * CSTRIDE + 1 + piece]);
+        const char *gsrc = reinterpret_cast<const char *>(A.momf) + piece * 16;
 #pragma unroll
         for (int i = 0; i < LPR; ++i) {
             const int rec = i * (32 / LPR) + sub;
-            const int rn = __shfl_sync(FULL, cn, rec);
-            if (rec < cnt) cp_async_cg16(&W.stage[buf][rec * CSTRIDE + 1 + piece], &A.momf[(size_t)rn * 8 + piece]);
+            const unsigned rn = (unsigned)__shfl_sync(FULL, cn, rec);
+            unsigned long long src;
+            asm("mad.wide.u32 %0, %1, 128, %2;" : "=l"(src) : "r"(rn), "l"(gsrc));
+            if (rec < cnt)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + i * (32 / LPR) * CSTRIDE * 16), "l"(src)
+                             : "memory");
         }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -750,13 +767,16 @@ template <int ORDER, bool MONO64, class SM>
 __device__ __forceinline__ void eval_cells(const TreeKernelArgs &A, SM &W, const double *s_off, const EvalCtx &E,
                                            Sink &K, const unsigned *L, int n, int lane) {
     if (n <= 0) return;
-    const int nBlk = (n + 31) >> 5;
-    unsigned itCur = lane < n ? L[lane] : 0u;
-    gather_cells<ORDER>(A, W, 0, 0, itCur, min(32, n), lane);
-    unsigned itNext = 32 + lane < n ? L[32 + lane] : 0u;
+    // block size = the largest multiple of G that fits the 32 staging slots: the G sub-groups then make the same number
+    // of trips through a full block (with 32 cells and G = 6 two sub-groups would run a 6th trip alone: 11 % idle)
+    const int BS = GG_EVAL_BSG ? 32 - (32 % E.G) : 32;
+    const int nBlk = (n + BS - 1) / BS;
+    unsigned itCur = lane < min(BS, n) ? L[lane] : 0u;
+    gather_cells<ORDER>(A, W, 0, 0, itCur, min(BS, n), lane);
+    unsigned itNext = (lane < BS && BS + lane < n) ? L[BS + lane] : 0u;
 #pragma unroll 1
     for (int i = 0; i < nBlk; ++i) {
-        const int buf = i & 1, rbuf = MONO64 ? buf : 0, cnt = min(32, n - 32 * i);
+        const int buf = i & 1, rbuf = MONO64 ? buf : 0, cnt = min(BS, n - BS * i);
         cp_async_wait_all();
         __syncwarp();
         if (lane < cnt) { // FP64 subtraction of the sink-bucket centre, then FP32
@@ -773,10 +793,10 @@ __device__ __forceinline__ void eval_cells(const TreeKernelArgs &A, SM &W, const
         }
         __syncwarp();
         if (i + 1 < nBlk) {
-            gather_cells<ORDER>(A, W, buf ^ 1, MONO64 ? buf ^ 1 : 0, itNext, min(32, n - 32 * (i + 1)), lane);
+            gather_cells<ORDER>(A, W, buf ^ 1, MONO64 ? buf ^ 1 : 0, itNext, min(BS, n - BS * (i + 1)), lane);
             itCur = itNext;
-            const int k = 32 * (i + 2) + lane;
-            itNext = k < n ? L[k] : 0u;
+            const int k = BS * (i + 2) + lane;
+            itNext = (lane < BS && k < n) ? L[k] : 0u;
         }
         if (E.worker) {
             for (int j = E.q; j < cnt; j += E.G) {
@@ -786,10 +806,9 @@ __device__ __forceinline__ void eval_cells(const TreeKernelArgs &A, SM &W, const
                 c.m0 = S[1]; c.m1 = S[2];
                 if (ORDER >= 3) { c.m2 = S[3]; c.m3 = S[4]; }
                 if (ORDER >= 4) { c.m4 = S[5]; c.m5 = S[6]; c.m6 = S[7]; c.m7 = S[8]; }
-                float fx, fy, fz, fp, fdt, g0;
-                cell_on_sink<ORDER, MONO64>(c, pc.w, K.sx - pc.x, K.sy - pc.y, K.sz - pc.z, K.ms, fx, fy, fz, fp, fdt, &g0);
-                K.ax += fx; K.ay += fy; K.az += fz; K.ap -= fp;
-                K.dtm = fmaxf(K.dtm, fdt);
+                float g0;
+                cell_on_sink<ORDER, MONO64>(c, pc.w, K.sx - pc.x, K.sy - pc.y, K.sz - pc.z, K.ms, K.ax, K.ay, K.az, K.ap,
+                                            K.dtm, &g0);
                 if (MONO64) {
                     const double2 q01 = *reinterpret_cast<const double2 *>(&W.raw[rbuf][4 * j]);
                     const double2 q23 = *reinterpret_cast<const double2 *>(&W.raw[rbuf][4 * j + 2]);
@@ -859,7 +878,7 @@ __device__ __forceinline__ void eval_leaves(const TreeKernelArgs &A, SM &W, cons
                 if (__float_as_int(ph.y) == K.sidx) continue;
                 float fx, fy, fz, fp, fdt;
                 part_on_sink(pp.w, ph.x, K.sx - pp.x, K.sy - pp.y, K.sz - pp.z, K.ms, K.hs, fx, fy, fz, fp, fdt);
-                K.ax += fx; K.ay += fy; K.az += fz; K.ap -= fp;
+                K.ax += fx; K.ay += fy; K.az += fz; K.ap += fp;
                 K.dtm = fmaxf(K.dtm, fdt);
             }
         }
@@ -892,7 +911,11 @@ __device__ __noinline__ SoftTerm eval_soft(const NodeW *nodes, const double *mom
 
 // One warp per (bucket, pass of <= 8 active sinks), streaming through the bucket's three contiguous lists.
 template <int ORDER, bool MONO64>
+#ifdef GG_EVAL_MAXREG
+__global__ void __launch_bounds__(GG_WARPS_PER_CTA * 32) __maxnreg__(MONO64 ? 128 : GG_EVAL_MAXREG) k_eval(const TreeKernelArgs A) {
+#else
 __global__ void __launch_bounds__(GG_WARPS_PER_CTA * 32, MONO64 ? GG_MIN_CTAS - 1 : GG_MIN_CTAS) k_eval(const TreeKernelArgs A) {
+#endif
     typedef EvalSmemT<MONO64 ? 2 : 1> EvalSmem;
     extern __shared__ __align__(16) unsigned char eval_smem_raw[];
     EvalSmem *s_w = reinterpret_cast<EvalSmem *>(eval_smem_raw);
