@@ -12,6 +12,7 @@
 #include <thread>
 #include <vector>
 #include "gg_internal.h"
+#include "gg_m2m.h"
 
 void gg_ewald_table_host(const double *root, double L, double fhCut, int iOrder, std::vector<double> &ewt);
 
@@ -77,6 +78,10 @@ struct gg_context {
     int nTasksLocal = 0, nBucketsLocal = 0, nPartUpload = 0; // the task list gg_set_local built
     int nLaunches = 0;
     size_t capBlocks = 0; // list pool capacity (blocks of 32 references), kept at the high-water mark
+    void *builder = nullptr; // gg_tree_gpu.cu workspace (gg_build_local)
+    GGBuiltDev built{};      // the last device-built tree (all zero: none)
+    bool rootLazy = false;   // the Ewald root expansion is to be read from the device-formed moments when first needed
+    double msBuild = 0.0;
 };
 
 namespace {
@@ -506,7 +511,7 @@ int upload_domain(gg_context *c, const gg_tree *t, const gg_particles *pp, int n
         const int *dActive = nullptr;
         if (pp->active) {
             if ((rc = ensure(c, c->active, (size_t)(np + 1) * sizeof(int)))) return rc;
-            CK(cudaMemcpyAsync(c->active.p, pp->active, sizeof(int) * np, cudaMemcpyHostToDevice, c->st));
+            CK(cudaMemcpyAsync(c->active.p, pp->active, sizeof(int) * np, cudaMemcpyDefault, c->st));
             dActive = (const int *)c->active.p;
         }
         c->nPartUpload = np;
@@ -582,6 +587,7 @@ void gg_destroy(gg_context *c) {
     for (DevBuf *b : all)
         if (b->p) cudaFree(b->p);
     if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->builder) gg_builder_free(c->builder);
     for (auto &ev : c->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->st);
     cudaStreamDestroy(c->st2);
@@ -612,6 +618,8 @@ int gg_set_local(gg_context *c, int idSelf, const gg_tree *t, const gg_particles
     c->dom.clear();
     c->nTop = 0;
     c->idSelf = idSelf;
+    c->built = GGBuiltDev{};
+    c->rootLazy = false;
     int rc = upload_domain(c, t, pp, 0, 0, true, false);
     if (rc) return rc;
     tr.mark("set_local: upload_domain");
@@ -620,6 +628,116 @@ int gg_set_local(gg_context *c, int idSelf, const gg_tree *t, const gg_particles
     c->nPartAll = pp->n;
     if (pp->active) c->hActive.assign(pp->active, pp->active + pp->n); // (the device copy went up with the domain)
     else c->hActive.clear();
+    return GG_OK;
+}
+
+// The Ewald root expansion (pkdCalcRoot, pkd.c:4395-4470: complete l <= 4 moments about the root's centre of mass) of a
+// device-built tree: exactly the RAW moment record gg_moments.cu leaves for the root cell.
+static int fetch_root_lazy(gg_context *c) {
+    if (!c->rootLazy) return GG_OK;
+    int rc = finish_mom(c);
+    if (rc) return rc;
+    const int iRoot = c->dom[0].iRoot;
+    double raw[32];
+    NodeW w;
+    CK(cudaMemcpyAsync(raw, (const double *)c->momraw.p + (size_t)iRoot * 32, sizeof(raw), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(&w, (const NodeW *)c->nodes.p + iRoot, sizeof(w), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    double *R = c->root;
+    const double *q = raw + 1;
+    R[0] = w.fMass; R[1] = w.rx; R[2] = w.ry; R[3] = w.rz;
+    R[4] = q[0]; R[5] = q[1]; R[6] = q[3]; R[7] = q[4]; R[8] = q[5]; R[9] = q[2];
+    for (int k = 6; k < 31; ++k) R[10 + (k - 6)] = q[k];
+    c->haveRoot = true;
+    c->rootLazy = false;
+    return GG_OK;
+}
+
+int gg_build_local(gg_context *c, int idSelf, const gg_particles *pp, int nBucket, double dTheta, int *iOrder,
+                   int *pnNodes, double *root) {
+    if (!c || !pp) return fail(GG_ERR_ARG, "gg_build_local: null argument");
+    if (pp->n < 1 || !pp->x || !pp->y || !pp->z || !pp->fMass || !pp->fSoft || nBucket < 1 || nBucket > GG_MAX_BUCKET ||
+        !(dTheta > 0))
+        return fail(GG_ERR_ARG, "gg_build_local: n=%d nBucket=%d dTheta=%g", pp->n, nBucket, dTheta);
+    CK(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = finish_mom(c))) return rc;
+    char msg[400];
+    int nl = 0;
+    GGBuiltDev b{};
+    CK(cudaEventRecord(c->ev[6], c->st));
+    rc = gg_builder_run(&c->builder, pp, nBucket, dTheta, c->st, &b, &nl, msg, sizeof(msg));
+    if (rc) return fail(rc, "%s", msg);
+    CK(cudaEventRecord(c->ev[7], c->st));
+    c->nLaunches += nl;
+    c->dom.clear();
+    c->nTop = 0;
+    c->idSelf = idSelf;
+    gg_tree t{};
+    t.nNodes = b.nNodes; t.iRoot = 0;
+    t.bnd = b.bnd; t.r = b.r; t.fMass = b.fMass; t.fSoft = b.fSoft; t.fOpen2 = b.fOpen2; t.mom = nullptr;
+    t.pLower = b.pLower; t.pUpper = b.pUpper; t.iLower = b.iLower; t.iUpper = b.iUpper;
+    gg_particles dp{};
+    dp.n = b.nPart; dp.x = b.x; dp.y = b.y; dp.z = b.z; dp.fMass = b.m; dp.fSoft = b.h; dp.active = b.active;
+    if ((rc = upload_domain(c, &t, &dp, 0, 0, true, true))) return rc;
+    c->dom.push_back(Domain{idSelf, t.nNodes, dp.n, 0, 0, 0});
+    c->nNodesAll = t.nNodes;
+    c->nPartAll = dp.n;
+    c->built = b;
+    if (b.active) {
+        c->hActive.resize((size_t)dp.n);
+        CK(cudaMemcpyAsync(c->hActive.data(), b.active, sizeof(int) * dp.n, cudaMemcpyDeviceToHost, c->st));
+    } else c->hActive.clear();
+    if (iOrder) CK(cudaMemcpyAsync(iOrder, b.iorder, sizeof(int) * dp.n, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]));
+    c->msBuild = ms;
+    c->rootLazy = true;
+    c->haveRoot = false;
+    if (root) {
+        if ((rc = fetch_root_lazy(c))) return rc;
+        memcpy(root, c->root, sizeof(c->root));
+    }
+    if (pnNodes) *pnNodes = t.nNodes;
+    return GG_OK;
+}
+
+int gg_build_info(gg_context *c, int *pnNodes, int *pnLevels, double *pmsBuild) {
+    if (!c || !c->built.nNodes) return fail(GG_ERR_ARG, "gg_build_info: no device-built tree");
+    if (pnNodes) *pnNodes = c->built.nNodes;
+    if (pnLevels) *pnLevels = c->built.nLevels;
+    if (pmsBuild) *pmsBuild = c->msBuild;
+    return GG_OK;
+}
+
+int gg_tree_fetch(gg_context *c, double *bnd, double *r, double *fMass, double *fSoft, double *fOpen2, double *mom,
+                  int *pLower, int *pUpper, int *iLower, int *iUpper, double *x, double *y, double *z, double *m,
+                  double *h, int *active) {
+    if (!c || !c->built.nNodes) return fail(GG_ERR_ARG, "gg_tree_fetch: no device-built tree (gg_build_local)");
+    CK(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = finish_mom(c))) return rc;
+    const GGBuiltDev &b = c->built;
+    const size_t nn = (size_t)b.nNodes, np = (size_t)b.nPart;
+    struct { void *dst; const void *src; size_t bytes; } cp[] = {
+        {bnd, b.bnd, 48 * nn}, {r, b.r, 24 * nn}, {fMass, b.fMass, 8 * nn}, {fSoft, b.fSoft, 8 * nn},
+        {fOpen2, b.fOpen2, 8 * nn}, {pLower, b.pLower, 4 * nn}, {pUpper, b.pUpper, 4 * nn}, {iLower, b.iLower, 4 * nn},
+        {iUpper, b.iUpper, 4 * nn}, {x, b.x, 8 * np}, {y, b.y, 8 * np}, {z, b.z, 8 * np}, {m, b.m, 8 * np}, {h, b.h, 8 * np},
+        {active, b.active, 4 * np}};
+    for (auto &e : cp)
+        if (e.dst && e.src) CK(cudaMemcpyAsync(e.dst, e.src, e.bytes, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    if (mom) { // the reduced multipoles the device formed: reduce the raw records on the host (gg_m2m.h)
+        std::vector<double> raw(nn * 32);
+        CK(cudaMemcpy(raw.data(), c->momraw.p, sizeof(double) * 32 * nn, cudaMemcpyDeviceToHost));
+        for (size_t g = 0; g < nn; ++g) {
+            GGRawMom a;
+            a.M = raw[g * 32];
+            for (int k = 0; k < 31; ++k) a.q[k] = raw[g * 32 + 1 + k];
+            gg_raw_reduce(a, mom + g * GG_NMOM);
+        }
+    }
     return GG_OK;
 }
 
@@ -812,6 +930,7 @@ int gg_set_root_moments(gg_context *c, const double root[GG_NROOT]) {
     if (!c || !root) return fail(GG_ERR_ARG, "gg_set_root_moments: null");
     memcpy(c->root, root, sizeof(c->root));
     c->haveRoot = true;
+    c->rootLazy = false;
     return GG_OK;
 }
 
@@ -875,6 +994,10 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
     const Domain &L = c->dom[0];
     const int n = L.nPart, nn = L.nNodes;
     const bool doEwald = prm->bPeriodic && prm->bEwald && prm->iEwOrder > 0 && !(prm->flags & GG_FLAG_WALK_ONLY);
+    if (doEwald && c->rootLazy) {
+        int rcr = fetch_root_lazy(c);
+        if (rcr) return rcr;
+    }
     if (doEwald && !c->haveRoot) return fail(GG_ERR_ARG, "gg_gravity: Ewald needs gg_set_root_moments");
     Trace tr;
     Images im = make_images(prm);
@@ -1257,6 +1380,10 @@ int gg_bucket_walk(gg_context *c, const gg_params *prm, int iBucket, int n3[3]) 
 
 int gg_ewald_table(gg_context *c, const gg_params *prm, double *ewt5, int nMax, int *pnEwh) {
     if (!c || !prm || !pnEwh) return fail(GG_ERR_ARG, "gg_ewald_table: bad argument");
+    if (c->rootLazy) {
+        int rcr = fetch_root_lazy(c);
+        if (rcr) return rcr;
+    }
     if (!c->haveRoot) return fail(GG_ERR_ARG, "gg_ewald_table: gg_set_root_moments has not been called");
     std::vector<double> ewt;
     gg_ewald_table_host(c->root, prm->fPeriod[0], prm->fEwhCut, prm->iEwOrder, ewt);

@@ -164,3 +164,18 @@ cudaError_t gg_launch_stats_kernel(const StatsKernelArgs &a, cudaStream_t st);
 cudaError_t gg_launch_device_moments(int nn, const NodeW *nodes, int nodeBase, int partBase, int iRootLocal,
                                      const double *x, const double *y, const double *z, const double *m, int *parent,
                                      int *arrive, double *raw, float4 *momf, double *momq, cudaStream_t st);
+
+// gg_tree_gpu.cu: the gravity tree built on the device.  The arrays are device pointers into the builder's workspace
+// (valid until the next build): the tree in the reference's pre-order numbering, SoA like gg_tree, and the particles
+// permuted into tree order; iorder[i] = input index of the particle now at position i.
+struct GGBuiltDev {
+    int nNodes, nPart, nLevels;
+    const double *bnd, *r, *fMass, *fSoft, *fOpen2;
+    const int *pLower, *pUpper, *iLower, *iUpper;
+    const double *x, *y, *z, *m, *h;
+    const int *active; // null: all active
+    const int *iorder;
+};
+int gg_builder_run(void **pBuilder, const gg_particles *pp, int nBucket, double dTheta, cudaStream_t st, GGBuiltDev *out,
+                   int *pnLaunches, char *err, size_t errLen);
+void gg_builder_free(void *builder);

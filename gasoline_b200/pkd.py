@@ -92,6 +92,9 @@ def load_library(path: str | None = None):
     L.gg_tree_free.argtypes = [C.c_void_p]
     L.gg_cell_moments.argtypes = [C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_int, _dp, _dp]
     L.gg_tree_moments_m2m.argtypes = [C.POINTER(gg_tree), C.POINTER(gg_particles), _dp]
+    L.gg_build_local.argtypes = [C.c_void_p, C.c_int, C.POINTER(gg_particles), C.c_int, C.c_double, _ip, _ip, _dp]
+    L.gg_build_info.argtypes = [C.c_void_p, _ip, _ip, _dp]
+    L.gg_tree_fetch.argtypes = [C.c_void_p] + [_dp] * 6 + [_ip] * 4 + [_dp] * 5 + [_ip]
     L.gg_measure_fp32_peak.argtypes = [C.c_void_p, _dp, _dp]
     L.gg_flush_l2.argtypes = [C.c_void_p]
     _lib = L
@@ -243,6 +246,50 @@ class PKD:
         self._uploaded = False
         return self.tree
 
+    def pkdBuildBinaryDevice(self, nBucket: int = 8, dCrit: float = 0.7, want_root: bool = False):
+        """pkdBuildBinary (pkd.c:2627) ON THE DEVICE (gg_build_local, csrc/gg_tree_gpu.cu): the particles go up in their
+        current order, the tree -- bit-identical to pkdBuildBinary's -- is built and left loaded on the GPU, moments
+        formed there; pkdGravAll follows without any tree transfer.  Results come back in tree order; iOrderMap maps
+        tree position -> original index.  self.tree stays None (pkdFetchTree downloads it when a host wants it)."""
+        if self.nLocal == 0:
+            raise GasolineB200Error("pkdBuildBinaryDevice: no particles")
+        pv = gg_particles(self.nLocal, _d(self.x), _d(self.y), _d(self.z), _d(self.fMass), _d(self.fSoft),
+                          _i(self.active) if self.active is not None else None)
+        if getattr(self, "_devOrder", None) is None or self._devOrder.shape[0] != self.nLocal:
+            self._devOrder = pinned_empty((self.nLocal,), np.int32) if self.pinned else np.zeros(self.nLocal, np.int32)
+        nn = C.c_int()
+        root = np.zeros(GG_NROOT) if want_root else None
+        _check(self._L.gg_build_local(self._ctx, self.idSelf, C.byref(pv), int(nBucket), float(dCrit),
+                                      _i(self._devOrder), C.byref(nn), _d(root) if want_root else None), "gg_build_local")
+        self.nNodesDevice = int(nn.value)
+        self.treeOrder = self._devOrder  # tree position -> index into the arrays given to pkdLoadParticles
+        self.tree = None
+        if want_root:
+            self.ilcnRoot = root
+        self._uploaded = True
+        return self.nNodesDevice
+
+    def pkdBuildInfo(self):
+        """(nNodes, tree levels, device milliseconds) of the last pkdBuildBinaryDevice."""
+        nn, nl, ms = C.c_int(), C.c_int(), C.c_double()
+        _check(self._L.gg_build_info(self._ctx, C.byref(nn), C.byref(nl), C.byref(ms)), "gg_build_info")
+        return nn.value, nl.value, ms.value
+
+    def pkdFetchTree(self, with_mom: bool = True):
+        """Download the device-built tree (gg_tree_fetch): returns (Tree, dict of the particles in tree order)."""
+        nn, n = self.nNodesDevice, self.nLocal
+        a = dict(bnd=np.zeros((nn, 6)), r=np.zeros((nn, 3)), fMass=np.zeros(nn), fSoft=np.zeros(nn), fOpen2=np.zeros(nn),
+                 mom=np.zeros((nn, GG_NMOM)), pLower=np.zeros(nn, np.int32), pUpper=np.zeros(nn, np.int32),
+                 iLower=np.zeros(nn, np.int32), iUpper=np.zeros(nn, np.int32))
+        p = dict(x=np.zeros(n), y=np.zeros(n), z=np.zeros(n), fMass=np.zeros(n), fSoft=np.zeros(n),
+                 active=np.zeros(n, np.int32) if self.active is not None else None)
+        _check(self._L.gg_tree_fetch(self._ctx, _d(a["bnd"]), _d(a["r"]), _d(a["fMass"]), _d(a["fSoft"]), _d(a["fOpen2"]),
+                                     _d(a["mom"]) if with_mom else None, _i(a["pLower"]), _i(a["pUpper"]),
+                                     _i(a["iLower"]), _i(a["iUpper"]), _d(p["x"]), _d(p["y"]), _d(p["z"]),
+                                     _d(p["fMass"]), _d(p["fSoft"]),
+                                     _i(p["active"]) if p["active"] is not None else None), "gg_tree_fetch")
+        return Tree(nn, 0, **a), p
+
     def pkdSetTree(self, tree: Tree, x, y, z, fMass, fSoft, active=None, ilcnRoot=None, iOrderMap=None):
         """Adopt a tree built elsewhere (e.g. the host's own kdNodes); particles must already be in its order."""
         self.x, self.y, self.z, self.fMass, self.fSoft = (self._own(a, np.float64) for a in (x, y, z, fMass, fSoft))
@@ -372,7 +419,8 @@ class PKD:
     def pkdBucketCounts(self) -> np.ndarray:
         """(nPart, nCellSoft, nCellNewt) per tree node after pkdGravAll -- what pkdBucketWalk leaves in
         pkd->nPart/nCellSoft/nCellNewt (walk.c:175-177); -1 where no active sink bucket."""
-        counts = np.zeros((self.tree.nNodes, 3), dtype=np.int32)
+        nn = self.tree.nNodes if self.tree is not None else self.nNodesDevice
+        counts = np.zeros((nn, 3), dtype=np.int32)
         _check(self._L.gg_bucket_counts(self._ctx, counts.ctypes.data_as(C.c_void_p)), "gg_bucket_counts")
         return counts
 

@@ -209,6 +209,28 @@ int gg_tree_view(const gg_built_tree *bt, gg_tree *view, double root[GG_NROOT]);
 void gg_tree_free(gg_built_tree *bt);
 
 
+/*
+ * pkdBuildBinary ON THE DEVICE (reference: BuildBinary pkd.c:2437-2587, pkdUpperPart pkd.c:1106-1133,
+ * pkdCombine pkd.c:1973, pkdCalcCell pkd.c:2018, pkdCalcOpen pkd.c:2228, pkdThreadTree pkd.c:2590).  Takes the rank's
+ * particles in ANY order (host pointers; pinned copies fastest), builds the gravity tree on the GPU -- the same cells,
+ * the same particle order inside every bucket and bit-identical r, fMass, fSoft, fOpen2, bnd as gg_tree_build / the
+ * reference's host build -- forms the moments there (as with gg_tree.mom = NULL) and leaves the domain loaded exactly
+ * as gg_set_local would: gg_gravity follows.  Results of gg_gravity are in TREE order; iOrder[i] (host, may be NULL)
+ * receives the input index of the particle at tree position i.  root (may be NULL) receives pkd->ilcnRoot
+ * (pkdCalcRoot); it is kept for Ewald either way.  Replaces gg_tree_build + gg_set_local for hosts that hand over
+ * particles instead of a tree.
+ */
+int gg_build_local(gg_context *ctx, int idSelf, const gg_particles *part, int nBucket, double dTheta, int *iOrder,
+                   int *pnNodes, double root[GG_NROOT]);
+/* nodes, tree levels and device time (ms, CUDA events) of the last gg_build_local */
+int gg_build_info(gg_context *ctx, int *pnNodes, int *pnLevels, double *pmsBuild);
+/* Copy the device-built tree (pre-order numbering, the layout of gg_tree; mom = the device-formed reduced multipoles)
+ * and the particles in tree order to host arrays; any pointer may be NULL.  Checking aid and the way a host gets
+ * kdNodes back. */
+int gg_tree_fetch(gg_context *ctx, double *bnd, double *r, double *fMass, double *fSoft, double *fOpen2, double *mom,
+                  int *pLower, int *pUpper, int *iLower, int *iUpper, double *x, double *y, double *z, double *fMass_p,
+                  double *fSoft_p, int *active);
+
 /* Every cell's reduced multipoles by the algorithm the DEVICE uses when gg_tree.mom is NULL (raw moments of the
  * buckets, children translated to the parent's centre and summed, then reduced as pkdCalcCell defines them), executed
  * on the host: mom[nNodes][GG_NMOM].  A checking aid for hosts and tests; no GPU needed. */
