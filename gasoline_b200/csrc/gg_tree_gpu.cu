@@ -18,11 +18,11 @@
 //   * cells are numbered in depth-first pre-order, as pkd->iFreeCell++ numbers them during the recursion.
 // The multipole moments come from gg_moments.cu (bottom-up M2M, FP64), exactly as for gg_set_local with mom = NULL.
 //
-// Level-synchronous construction, five launches per tree level over all n particles (cellOf[i] = the deepest cell
-// holding position i):  k_bounds (min/max by ordered-integer atomics, block/warp pre-reduced) -> k_flag (split decision
-// recomputed per particle from the cell's bounds; flag = r[dim] < split) -> cub exclusive scan -> k_split (ranks ->
-// exchange table; the first particle of a cell allocates the two children) -> k_swap (exchange pair k, re-home
-// position i).  Then one bottom-up kernel (arrival counters, like gg_moments.cu), one numbering kernel (pre-order index
+// Level-synchronous construction, three kernels + one scan per tree level over all n particles (cellOf[i] = the deepest
+// cell holding position i):  k_flag (split decision recomputed per particle from the cell's bounds; flag = r[dim] < split;
+// the first particle of a cell allocates the two children) -> cub exclusive scan -> k_split (ranks -> exchange table;
+// children's ranges; children's squeezed bounds by ordered-integer atomic min/max, block/warp pre-reduced -- a particle's
+// side is its flag, wherever the exchange will put it) -> k_swap (exchange pair k, re-home position i).  Then one bottom-up kernel (arrival counters, like gg_moments.cu), one numbering kernel (pre-order index
 // and threaded "next" from subtree sizes), Bmax by warp-aggregated atomic max while climbing, and the emit kernel.
 #include <cub/cub.cuh>
 #include <math.h>
@@ -52,6 +52,23 @@ __device__ __forceinline__ double dec(unsigned long long k) {
     return __longlong_as_double((k & 0x8000000000000000ull) ? (long long)(k & 0x7fffffffffffffffull) : (long long)~k);
 }
 
+// min/max of six ordered-integer keys over the lanes of a warp: two 32-bit REDUX per 64-bit key (high halves, then the
+// low halves of the lanes that hold the winning high half) instead of ten shuffles
+__device__ __forceinline__ unsigned long long warp_min64(unsigned long long v) {
+    const unsigned h = (unsigned)(v >> 32), mh = __reduce_min_sync(0xffffffffu, h);
+    const unsigned ml = __reduce_min_sync(0xffffffffu, h == mh ? (unsigned)v : 0xffffffffu);
+    return ((unsigned long long)mh << 32) | ml;
+}
+__device__ __forceinline__ unsigned long long warp_max64(unsigned long long v) {
+    const unsigned h = (unsigned)(v >> 32), mh = __reduce_max_sync(0xffffffffu, h);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, h == mh ? (unsigned)v : 0u);
+    return ((unsigned long long)mh << 32) | ml;
+}
+__device__ __forceinline__ void warp_minmax(unsigned long long *lo, unsigned long long *hi) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { lo[k] = warp_min64(lo[k]); hi[k] = warp_max64(hi[k]); }
+}
+
 __global__ void k_b_init(int n, int *iord, int *cellOf, BNode *nodes, int *ctr, int *levelStart) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { iord[i] = i; cellOf[i] = 0; }
@@ -61,11 +78,12 @@ __global__ void k_b_init(int n, int *iord, int *cellOf, BNode *nodes, int *ctr, 
         for (int k = 0; k < 3; ++k) { r.b[k] = ~0ull; r.b[3 + k] = 0ull; }
         nodes[0] = r;
         ctr[0] = 1;
-        levelStart[0] = 0;
+        levelStart[0] = 0; // the root is fresh at level 0
+        levelStart[1] = 1; // cells allocated by level 0 start here
     }
 }
 
-// squeezed bounds of the cells created by the previous level
+// squeezed bounds of the root (level 0); the children's bounds are accumulated by k_split of the level that makes them
 __global__ void __launch_bounds__(256) k_bounds(int n, const double *x, const double *y, const double *z, const int *cellOf,
                                                 const int *levelStart, int level, BNode *nodes) {
     const int i = blockIdx.x * 256 + threadIdx.x;
@@ -88,16 +106,7 @@ __global__ void __launch_bounds__(256) k_bounds(int n, const double *x, const do
     if (blockUniform && cb < 0) return;
     const int c0 = __shfl_sync(0xffffffffu, c, 0);
     const bool warpUniform = __all_sync(0xffffffffu, c == c0);
-    if (warpUniform) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-#pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                const unsigned long long a = __shfl_xor_sync(0xffffffffu, lo[k], o), b = __shfl_xor_sync(0xffffffffu, hi[k], o);
-                lo[k] = a < lo[k] ? a : lo[k];
-                hi[k] = b > hi[k] ? b : hi[k];
-            }
-    }
+    if (warpUniform) warp_minmax(lo, hi);
     if (blockUniform) {
         const int w = threadIdx.x >> 5;
         if ((threadIdx.x & 31) == 0)
@@ -126,23 +135,23 @@ __global__ void __launch_bounds__(256) k_bounds(int n, const double *x, const do
 // BuildBinary's decision for a fresh cell (pkd.c:2437-2587): split the longest axis of the squeezed box at its midpoint
 // when the cell holds more than nBucket particles and has extent; first axis wins ties.
 __device__ __forceinline__ int decide(const BNode &nd, int nBucket, double *pSplit) {
-    double mn[3], mx[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { mn[k] = dec(nd.b[k]); mx[k] = dec(nd.b[3 + k]); }
-    const bool good = (mx[0] > mn[0]) || (mx[1] > mn[1]) || (mx[2] > mn[2]);
+    const double mn0 = dec(nd.b[0]), mn1 = dec(nd.b[1]), mn2 = dec(nd.b[2]);
+    const double mx0 = dec(nd.b[3]), mx1 = dec(nd.b[4]), mx2 = dec(nd.b[5]);
+    const bool good = (mx0 > mn0) || (mx1 > mn1) || (mx2 > mn2);
     if (!(nd.hi - nd.lo + 1 > nBucket && good)) return -1;
     int d = 0;
-    if (__dsub_rn(mx[1], mn[1]) > __dsub_rn(mx[d], mn[d])) d = 1;
-    if (__dsub_rn(mx[2], mn[2]) > __dsub_rn(mx[d], mn[d])) d = 2;
-    *pSplit = __dmul_rn(0.5, __dadd_rn(mn[d], mx[d]));
+    double e = __dsub_rn(mx0, mn0), lo = mn0, hi = mx0;
+    const double e1 = __dsub_rn(mx1, mn1), e2 = __dsub_rn(mx2, mn2);
+    if (e1 > e) { d = 1; e = e1; lo = mn1; hi = mx1; }
+    if (e2 > e) { d = 2; lo = mn2; hi = mx2; }
+    *pSplit = __dmul_rn(0.5, __dadd_rn(lo, hi));
     return d;
 }
 
 __global__ void __launch_bounds__(256) k_flag(int n, const double *x, const double *y, const double *z, const int *cellOf,
-                                              int *levelStart, int level, BNode *nodes, int nBucket, int *flag,
-                                              const int *ctr) {
+                                              const int *levelStart, int level, BNode *nodes, int nBucket, int *flag,
+                                              int *ctr) {
     const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i == 0) levelStart[level + 1] = ctr[0]; // cells allocated by this level's k_split are fresh at the next level
     if (i > n) return;
     int f = 0;
     if (i < n) {
@@ -155,37 +164,108 @@ __global__ void __launch_bounds__(256) k_flag(int n, const double *x, const doub
                 const double v = d == 0 ? x[i] : (d == 1 ? y[i] : z[i]);
                 f = v < split;
             }
-            if (i == nd.lo) { nodes[c].dim = d; nodes[c].split = d >= 0 ? split : 0.0; }
+            if (i == nd.lo) { // one thread per cell records the decision and, for a split, allocates the two children
+                nodes[c].dim = d;
+                nodes[c].split = d >= 0 ? split : 0.0;
+                if (d >= 0) {
+                    const int id = atomicAdd(&ctr[0], 2);
+                    BNode ch;
+                    ch.lo = ch.hi = 0; // filled by k_split once the scan has placed the boundary
+                    ch.left = ch.right = -1; ch.parent = c; ch.dim = -1; ch.mid = 0; ch.nMis = 0; ch.split = 0.0;
+                    for (int k = 0; k < 3; ++k) { ch.b[k] = ~0ull; ch.b[3 + k] = 0ull; }
+                    nodes[id] = ch;
+                    nodes[id + 1] = ch;
+                    nodes[c].left = id;
+                    nodes[c].right = id + 1;
+                }
+            }
         }
     }
     flag[i] = f; // flag[n] = 0 closes the exclusive scan
 }
 
-__global__ void __launch_bounds__(256) k_split(int n, const int *cellOf, const int *levelStart, int level, BNode *nodes,
-                                               const int *flag, const int *S, int *tabL, int *tabR, int *ctr) {
+// Ranks of the misplaced particles -> exchange table; the squeezed bounds of the two children (a particle goes below
+// iff its flag is set, wherever the exchange puts it); the first particle of the cell fills in the children's ranges.
+__global__ void __launch_bounds__(256) k_split(int n, const double *x, const double *y, const double *z, const int *cellOf,
+                                               int *levelStart, int level, BNode *nodes, const int *flag, const int *S,
+                                               int *tabL, int *tabR, const int *ctr) {
     const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= n) return;
-    const int c = cellOf[i];
-    if (c < levelStart[level]) return;
-    const int dim = nodes[c].dim;
-    if (dim < 0) return;
-    const int lo = nodes[c].lo, hi = nodes[c].hi;
-    const int base = S[lo], nLeft = S[hi + 1] - base, mid = lo + nLeft;
-    const int less = flag[i];
-    if (i < mid) {
-        if (!less) tabL[lo + (i - lo) - (S[i] - base)] = i;
-    } else if (less) tabR[lo + (S[hi + 1] - S[i + 1])] = i;
-    if (i == lo) {
-        const int id = atomicAdd(&ctr[0], 2);
-        BNode ch;
-        ch.left = ch.right = -1; ch.parent = c; ch.dim = -1; ch.mid = 0; ch.nMis = 0; ch.split = 0.0;
-        for (int k = 0; k < 3; ++k) { ch.b[k] = ~0ull; ch.b[3 + k] = 0ull; }
-        ch.lo = lo; ch.hi = mid - 1;
-        nodes[id] = ch;
-        ch.lo = mid; ch.hi = hi;
-        nodes[id + 1] = ch;
-        nodes[c].left = id; nodes[c].right = id + 1; nodes[c].mid = mid;
-        nodes[c].nMis = (mid - lo) - (S[mid] - base);
+    if (i == 0) levelStart[level + 2] = ctr[0]; // every allocation of this level happened in k_flag
+    int c = -1, less = 0;
+    if (i < n) {
+        c = cellOf[i];
+        if (c < levelStart[level] || nodes[c].dim < 0) c = -1;
+    }
+    unsigned long long lo0[3] = {~0ull, ~0ull, ~0ull}, hi0[3] = {0ull, 0ull, 0ull}, lo1[3] = {~0ull, ~0ull, ~0ull},
+                       hi1[3] = {0ull, 0ull, 0ull}, key[3] = {0ull, 0ull, 0ull};
+    int left = -1;
+    if (c >= 0) {
+        const int clo = nodes[c].lo, chi = nodes[c].hi;
+        left = nodes[c].left;
+        const int base = S[clo], nLeft = S[chi + 1] - base, mid = clo + nLeft;
+        less = flag[i];
+        if (i < mid) {
+            if (!less) tabL[clo + (i - clo) - (S[i] - base)] = i;
+        } else if (less) tabR[clo + (S[chi + 1] - S[i + 1])] = i;
+        if (i == clo) {
+            nodes[left].lo = clo; nodes[left].hi = mid - 1;
+            nodes[left + 1].lo = mid; nodes[left + 1].hi = chi;
+            nodes[c].mid = mid;
+            nodes[c].nMis = (mid - clo) - (S[mid] - base);
+        }
+        key[0] = enc(x[i]); key[1] = enc(y[i]); key[2] = enc(z[i]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (less) lo0[k] = hi0[k] = key[k];
+            else lo1[k] = hi1[k] = key[k];
+        }
+    }
+    // children's bounds: pre-reduce over the block / the warp when all of it stands in one cell
+    __shared__ int s_c;
+    __shared__ unsigned long long s_v[8][12];
+    if (threadIdx.x == 0) s_c = c;
+    __syncthreads();
+    const int cb = s_c;
+    const bool blockUniform = __syncthreads_and(c == cb);
+    if (blockUniform && cb < 0) return;
+    const int c0 = __shfl_sync(0xffffffffu, c, 0);
+    const bool warpUniform = __all_sync(0xffffffffu, c == c0);
+    if (warpUniform && c0 >= 0) { warp_minmax(lo0, hi0); warp_minmax(lo1, hi1); }
+    if (blockUniform) {
+        const int w = threadIdx.x >> 5;
+        if ((threadIdx.x & 31) == 0)
+            for (int k = 0; k < 3; ++k) {
+                s_v[w][k] = lo0[k]; s_v[w][3 + k] = hi0[k]; s_v[w][6 + k] = lo1[k]; s_v[w][9 + k] = hi1[k];
+            }
+        __syncthreads();
+        if (threadIdx.x < 12) {
+            const int k = threadIdx.x, isMin = (k % 6) < 3;
+            unsigned long long v = s_v[0][k];
+            for (int q = 1; q < 8; ++q) {
+                const unsigned long long u = s_v[q][k];
+                v = isMin ? (u < v ? u : v) : (u > v ? u : v);
+            }
+            unsigned long long *dst = &nodes[left + k / 6].b[k % 6];
+            if (isMin) { if (v != ~0ull) atomicMin(dst, v); }
+            else if (v != 0ull) atomicMax(dst, v);
+        }
+        return;
+    }
+    if (warpUniform) {
+        if (c0 >= 0 && (threadIdx.x & 31) == 0) {
+            if (lo0[0] != ~0ull)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { atomicMin(&nodes[left].b[k], lo0[k]); atomicMax(&nodes[left].b[3 + k], hi0[k]); }
+            if (lo1[0] != ~0ull)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { atomicMin(&nodes[left + 1].b[k], lo1[k]); atomicMax(&nodes[left + 1].b[3 + k], hi1[k]); }
+        }
+        return;
+    }
+    if (c >= 0) {
+        BNode *ch = &nodes[left + (less ? 0 : 1)];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { atomicMin(&ch->b[k], key[k]); atomicMax(&ch->b[3 + k], key[k]); }
     }
 }
 
@@ -381,7 +461,7 @@ int gg_builder_run(void **pBuilder, const gg_particles *pp, int nBucket, double 
     BCK(B.cell.need(sizeof(int) * (size_t)n));
     BCK(B.scan.need(sizeof(int) * 2 * ((size_t)n + 1)));
     BCK(B.tab.need(sizeof(int) * 2 * (size_t)n));
-    BCK(B.ctr.need(sizeof(int) * (8 + GGB_MAX_LEVELS + 2)));
+    BCK(B.ctr.need(sizeof(int) * (8 + GGB_MAX_LEVELS + 4)));
     if (!B.hCtr) BCK(cudaMallocHost((void **)&B.hCtr, sizeof(int) * 4));
     double *x = (double *)B.part.p, *y = x + n, *z = y + n, *m = z + n, *h = m + n;
     int *iord = (int *)B.ipart.p, *act = pp->active ? iord + n : nullptr;
@@ -411,12 +491,12 @@ int gg_builder_run(void **pBuilder, const gg_particles *pp, int nBucket, double 
                      GGB_MAX_LEVELS, nBucket);
             return GG_ERR_UNSUPPORTED;
         }
-        k_bounds<<<gridP, 256, 0, st>>>(n, x, y, z, cellOf, levelStart, level, nodes);
+        if (level == 0) { k_bounds<<<gridP, 256, 0, st>>>(n, x, y, z, cellOf, levelStart, level, nodes); ++nl; }
         k_flag<<<gridP1, 256, 0, st>>>(n, x, y, z, cellOf, levelStart, level, nodes, nBucket, flag, ctr);
         BCK(cub::DeviceScan::ExclusiveSum(B.cub.p, cubBytes, flag, S, n + 1, st));
-        k_split<<<gridP, 256, 0, st>>>(n, cellOf, levelStart, level, nodes, flag, S, tabL, tabR, ctr);
+        k_split<<<gridP, 256, 0, st>>>(n, x, y, z, cellOf, levelStart, level, nodes, flag, S, tabL, tabR, ctr);
         k_swap<<<gridP, 256, 0, st>>>(n, cellOf, levelStart, level, nodes, tabL, tabR, x, y, z, m, h, act, iord);
-        nl += 6;
+        nl += 5;
         // a level of a balanced tree cannot be the last one before ~log2(n / nBucket); afterwards look every level
         if ((1ll << (level + 1)) * (long long)nBucket < (long long)n) continue;
         BCK(cudaMemcpyAsync(B.hCtr, ctr, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -74,3 +74,27 @@ def test_full_size_sampled_buckets_and_invariants(name, gpu_lib):
     assert prms <= RMS_TOL and pmx <= MAX_TOL
     assert np.array_equal(out["fWeight"][act], ref["fWeight"][act])
     pkd.close()
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_full_size_device_tree_build_identical(name, gpu_lib):
+    """pkdBuildBinary on the device at BASELINE.json's sizes: every tree array and the particle order equal the host
+    build's bit for bit (the host build is pinned to the reference's in the CPU suite)."""
+    mk, theta, g, _ = CASES[name]
+    p = mk()
+    host = PKD(fPeriod=p.period)
+    host.pkdLoadParticles(p.x, p.y, p.z, p.m, p.h)
+    th = host.pkdBuildBinary(8, theta, 4)
+    dev = PKD(fPeriod=p.period)
+    dev.pkdLoadParticles(p.x, p.y, p.z, p.m, p.h)
+    assert dev.pkdBuildBinaryDevice(8, theta) == th.nNodes
+    dev.pkdBuildBinaryDevice(8, theta)  # second build on warm buffers: the timing below is steady state
+    td, pd_ = dev.pkdFetchTree(with_mom=False)
+    for k in ("bnd", "r", "fMass", "fSoft", "fOpen2", "pLower", "pUpper", "iLower", "iUpper"):
+        assert np.array_equal(getattr(td, k), getattr(th, k)), f"{name}: tree field {k} differs from the host build"
+    assert np.array_equal(dev.treeOrder, host.iOrderMap)
+    assert np.array_equal(pd_["x"], host.x) and np.array_equal(pd_["z"], host.z)
+    nn, nl, ms = dev.pkdBuildInfo()
+    print(f"{name}: device tree build {nn} cells, {nl} levels, {ms:.2f} ms")
+    host.close()
+    dev.close()
