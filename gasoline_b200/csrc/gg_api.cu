@@ -82,6 +82,11 @@ struct gg_context {
     GGBuiltDev built{};      // the last device-built tree (all zero: none)
     bool rootLazy = false;   // the Ewald root expansion is to be read from the device-formed moments when first needed
     double msBuild = 0.0;
+    // device-resident particle store (gg_state_*): positions / mass / softening / ACTIVE in tree order after every
+    // gg_state_build, velocities SoA [3][n], persistent particle id, time step
+    DevBuf sx, sy, sz, sm, sh, sact, svel, sid, sdt, svel2, sid2, sdt2, sacc;
+    int stateN = 0;
+    bool stateHasActive = false, stateDirty = true, stateForces = false;
 };
 
 namespace {
@@ -583,7 +588,8 @@ void gg_destroy(gg_context *c) {
                      &c->imgoff, &c->ewt, &c->raw, &c->rawi, &c->cubtmp, &c->flush, &c->pool,
                      &c->nextblk, &c->poolmask, &c->isb, &c->boffs, &c->bnode, &c->ghead, &c->gcnt, &c->bcnt, &c->btot,
                      &c->boff64, &c->lists, &c->letflag, &c->letfront, &c->letidx, &c->letout, &c->letmisc, &c->momraw,
-                     &c->mparent, &c->dbgtask};
+                     &c->mparent, &c->dbgtask, &c->sx, &c->sy, &c->sz, &c->sm, &c->sh, &c->sact, &c->svel, &c->sid, &c->sdt,
+                     &c->svel2, &c->sid2, &c->sdt2, &c->sacc};
     for (DevBuf *b : all)
         if (b->p) cudaFree(b->p);
     if (c->pinned) cudaFreeHost(c->pinned);
@@ -620,6 +626,7 @@ int gg_set_local(gg_context *c, int idSelf, const gg_tree *t, const gg_particles
     c->idSelf = idSelf;
     c->built = GGBuiltDev{};
     c->rootLazy = false;
+    c->stateN = 0; // a host-supplied domain replaces any resident store
     int rc = upload_domain(c, t, pp, 0, 0, true, false);
     if (rc) return rc;
     tr.mark("set_local: upload_domain");
@@ -653,13 +660,9 @@ static int fetch_root_lazy(gg_context *c) {
     return GG_OK;
 }
 
-int gg_build_local(gg_context *c, int idSelf, const gg_particles *pp, int nBucket, double dTheta, int *iOrder,
-                   int *pnNodes, double *root) {
-    if (!c || !pp) return fail(GG_ERR_ARG, "gg_build_local: null argument");
-    if (pp->n < 1 || !pp->x || !pp->y || !pp->z || !pp->fMass || !pp->fSoft || nBucket < 1 || nBucket > GG_MAX_BUCKET ||
-        !(dTheta > 0))
-        return fail(GG_ERR_ARG, "gg_build_local: n=%d nBucket=%d dTheta=%g", pp->n, nBucket, dTheta);
-    CK(cudaSetDevice(c->device));
+// Build the tree of the particles pp (host or device pointers) on the device and load it as the local domain.
+static int build_and_load(gg_context *c, int idSelf, const gg_particles *pp, int nBucket, double dTheta, int *iOrder,
+                          int *pnNodes, double *root) {
     int rc;
     if ((rc = finish_mom(c))) return rc;
     char msg[400];
@@ -700,6 +703,166 @@ int gg_build_local(gg_context *c, int idSelf, const gg_particles *pp, int nBucke
         memcpy(root, c->root, sizeof(c->root));
     }
     if (pnNodes) *pnNodes = t.nNodes;
+    return GG_OK;
+}
+
+int gg_build_local(gg_context *c, int idSelf, const gg_particles *pp, int nBucket, double dTheta, int *iOrder,
+                   int *pnNodes, double *root) {
+    if (!c || !pp) return fail(GG_ERR_ARG, "gg_build_local: null argument");
+    if (pp->n < 1 || !pp->x || !pp->y || !pp->z || !pp->fMass || !pp->fSoft || nBucket < 1 || nBucket > GG_MAX_BUCKET ||
+        !(dTheta > 0))
+        return fail(GG_ERR_ARG, "gg_build_local: n=%d nBucket=%d dTheta=%g", pp->n, nBucket, dTheta);
+    CK(cudaSetDevice(c->device));
+    c->stateN = 0; // a tree built from host particles replaces any resident store
+    return build_and_load(c, idSelf, pp, nBucket, dTheta, iOrder, pnNodes, root);
+}
+
+// ---- device-resident particle store: pkd->pStore kept in HBM across force evaluations ----
+
+int gg_state_load(gg_context *c, int n, const double *x, const double *y, const double *z, const double *vx,
+                  const double *vy, const double *vz, const double *fMass, const double *fSoft, const int *active,
+                  double dt0) {
+    if (!c || n < 1 || !x || !y || !z || !vx || !vy || !vz || !fMass || !fSoft)
+        return fail(GG_ERR_ARG, "gg_state_load: bad argument (n=%d)", n);
+    CK(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = finish_mom(c))) return rc;
+    const size_t nb = sizeof(double) * (size_t)n;
+    DevBuf *d8[] = {&c->sx, &c->sy, &c->sz, &c->sm, &c->sh, &c->sdt, &c->sdt2};
+    for (DevBuf *b : d8)
+        if ((rc = ensure(c, *b, nb))) return rc;
+    if ((rc = ensure(c, c->svel, 3 * nb)) || (rc = ensure(c, c->svel2, 3 * nb))) return rc;
+    if ((rc = ensure(c, c->sid, sizeof(int) * (size_t)n)) || (rc = ensure(c, c->sid2, sizeof(int) * (size_t)n)) ||
+        (rc = ensure(c, c->sact, sizeof(int) * (size_t)n)))
+        return rc;
+    const double *src[] = {x, y, z, fMass, fSoft};
+    DevBuf *dst[] = {&c->sx, &c->sy, &c->sz, &c->sm, &c->sh};
+    for (int k = 0; k < 5; ++k) CK(cudaMemcpyAsync(dst[k]->p, src[k], nb, cudaMemcpyDefault, c->st));
+    double *v = (double *)c->svel.p;
+    CK(cudaMemcpyAsync(v, vx, nb, cudaMemcpyDefault, c->st));
+    CK(cudaMemcpyAsync(v + n, vy, nb, cudaMemcpyDefault, c->st));
+    CK(cudaMemcpyAsync(v + 2 * (size_t)n, vz, nb, cudaMemcpyDefault, c->st));
+    if (active) CK(cudaMemcpyAsync(c->sact.p, active, sizeof(int) * (size_t)n, cudaMemcpyDefault, c->st));
+    CK(gg_launch_state_init(n, (int *)c->sid.p, (double *)c->sdt.p, dt0, c->st));
+    ++c->nLaunches;
+    CK(cudaStreamSynchronize(c->st));
+    c->stateN = n;
+    c->stateHasActive = active != nullptr;
+    c->stateDirty = true;
+    c->stateForces = false;
+    return GG_OK;
+}
+
+int gg_state_build(gg_context *c, int idSelf, int nBucket, double dTheta, int *pnNodes) {
+    if (!c || c->stateN < 1) return fail(GG_ERR_ARG, "gg_state_build: no resident particles (gg_state_load)");
+    if (nBucket < 1 || nBucket > GG_MAX_BUCKET || !(dTheta > 0))
+        return fail(GG_ERR_ARG, "gg_state_build: nBucket=%d dTheta=%g", nBucket, dTheta);
+    CK(cudaSetDevice(c->device));
+    const int n = c->stateN;
+    gg_particles pp{};
+    pp.n = n;
+    pp.x = (const double *)c->sx.p; pp.y = (const double *)c->sy.p; pp.z = (const double *)c->sz.p;
+    pp.fMass = (const double *)c->sm.p; pp.fSoft = (const double *)c->sh.p;
+    pp.active = c->stateHasActive ? (const int *)c->sact.p : nullptr;
+    int rc = build_and_load(c, idSelf, &pp, nBucket, dTheta, nullptr, pnNodes, nullptr);
+    if (rc) return rc;
+    // the store follows the tree order: velocities, ids and time steps by the build's permutation, the rest as built
+    const GGBuiltDev &b = c->built;
+    CK(gg_launch_permute(n, b.iorder, (const double *)c->svel.p, (double *)c->svel2.p, (const int *)c->sid.p,
+                         (int *)c->sid2.p, (const double *)c->sdt.p, (double *)c->sdt2.p, c->st));
+    ++c->nLaunches;
+    std::swap(c->svel, c->svel2);
+    std::swap(c->sid, c->sid2);
+    std::swap(c->sdt, c->sdt2);
+    const size_t nb = sizeof(double) * (size_t)n;
+    CK(cudaMemcpyAsync(c->sx.p, b.x, nb, cudaMemcpyDeviceToDevice, c->st));
+    CK(cudaMemcpyAsync(c->sy.p, b.y, nb, cudaMemcpyDeviceToDevice, c->st));
+    CK(cudaMemcpyAsync(c->sz.p, b.z, nb, cudaMemcpyDeviceToDevice, c->st));
+    CK(cudaMemcpyAsync(c->sm.p, b.m, nb, cudaMemcpyDeviceToDevice, c->st));
+    CK(cudaMemcpyAsync(c->sh.p, b.h, nb, cudaMemcpyDeviceToDevice, c->st));
+    if (b.active) CK(cudaMemcpyAsync(c->sact.p, b.active, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, c->st));
+    c->stateDirty = false;
+    c->stateForces = false;
+    return GG_OK;
+}
+
+int gg_state_kick(gg_context *c, double dvFacOne, double dvFacTwo, const double *a) {
+    if (!c || c->stateN < 1) return fail(GG_ERR_ARG, "gg_state_kick: no resident particles (gg_state_load)");
+    CK(cudaSetDevice(c->device));
+    const int n = c->stateN;
+    const double *da = nullptr;
+    if (a) { // the caller's accelerations, [n][3] in the store's current order
+        int rc;
+        if ((rc = ensure(c, c->sacc, sizeof(double) * 3 * (size_t)n))) return rc;
+        CK(cudaMemcpyAsync(c->sacc.p, a, sizeof(double) * 3 * (size_t)n, cudaMemcpyDefault, c->st));
+        da = (const double *)c->sacc.p;
+    } else {
+        if (c->stateDirty || !c->stateForces)
+            return fail(GG_ERR_ARG, "gg_state_kick: no accelerations for the current particle order "
+                                    "(sequence: gg_state_build, gg_gravity, gg_state_kick)");
+        da = (const double *)c->acc.p;
+    }
+    CK(gg_launch_kick(n, (double *)c->svel.p, da, c->stateHasActive ? (const int *)c->sact.p : nullptr, dvFacOne,
+                      dvFacTwo, c->st));
+    ++c->nLaunches;
+    if (a) CK(cudaStreamSynchronize(c->st));
+    return GG_OK;
+}
+
+int gg_state_drift(gg_context *c, double dDelta, const double fCenter[3], int bPeriodic, const double fPeriod[3]) {
+    if (!c || c->stateN < 1) return fail(GG_ERR_ARG, "gg_state_drift: no resident particles (gg_state_load)");
+    if (bPeriodic && (!fCenter || !fPeriod)) return fail(GG_ERR_ARG, "gg_state_drift: periodic drift needs fCenter, fPeriod");
+    CK(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = finish_mom(c))) return rc; // the moment kernels of the last build read the positions
+    if ((rc = ensure(c, c->misc, 16 * sizeof(int)))) return rc;
+    int *dOut = (int *)c->misc.p + 12;
+    const double zero[3] = {0, 0, 0}, one[3] = {1, 1, 1};
+    CK(cudaMemsetAsync(dOut, 0, sizeof(int), c->st));
+    CK(gg_launch_drift(c->stateN, (double *)c->sx.p, (double *)c->sy.p, (double *)c->sz.p, (const double *)c->svel.p,
+                       dDelta, bPeriodic ? fCenter : zero, bPeriodic, bPeriodic ? fPeriod : one, dOut, c->st));
+    ++c->nLaunches;
+    c->stateDirty = true;
+    if (bPeriodic) { // the reference asserts every particle is back inside the box (pkd.c:3754-3756)
+        int nOut = 0;
+        CK(cudaMemcpyAsync(&nOut, dOut, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        if (nOut) return fail(GG_ERR_ARG, "gg_state_drift: %d particle(s) left the periodic box by more than one period", nOut);
+    }
+    return GG_OK;
+}
+
+int gg_state_gravstep(gg_context *c, double dEta, double *pdtMin) {
+    if (!c || c->stateN < 1) return fail(GG_ERR_ARG, "gg_state_gravstep: no resident particles (gg_state_load)");
+    if (c->stateDirty || !c->stateForces)
+        return fail(GG_ERR_ARG, "gg_state_gravstep: no dtGrav for the current particle order (gg_gravity first)");
+    CK(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = ensure(c, c->misc, 16 * sizeof(int)))) return rc;
+    unsigned long long *dMin = (unsigned long long *)((int *)c->misc.p + 14);
+    CK(cudaMemsetAsync(dMin, 0xff, sizeof(unsigned long long), c->st));
+    CK(gg_launch_gravstep(c->stateN, (double *)c->sdt.p, (const double *)c->dtg.p,
+                          c->stateHasActive ? (const int *)c->sact.p : nullptr, dEta, dMin, c->st));
+    ++c->nLaunches;
+    unsigned long long bits = 0;
+    CK(cudaMemcpyAsync(&bits, dMin, sizeof(bits), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    if (pdtMin) memcpy(pdtMin, &bits, sizeof(double));
+    return GG_OK;
+}
+
+int gg_state_fetch(gg_context *c, double *x, double *y, double *z, double *vx, double *vy, double *vz, int *id, double *dt) {
+    if (!c || c->stateN < 1) return fail(GG_ERR_ARG, "gg_state_fetch: no resident particles (gg_state_load)");
+    CK(cudaSetDevice(c->device));
+    const int n = c->stateN;
+    const size_t nb = sizeof(double) * (size_t)n;
+    const double *v = (const double *)c->svel.p;
+    struct { void *dst; const void *src; size_t bytes; } cp[] = {
+        {x, c->sx.p, nb}, {y, c->sy.p, nb}, {z, c->sz.p, nb}, {vx, v, nb}, {vy, v + n, nb}, {vz, v + 2 * (size_t)n, nb},
+        {id, c->sid.p, sizeof(int) * (size_t)n}, {dt, c->sdt.p, nb}};
+    for (auto &e : cp)
+        if (e.dst) CK(cudaMemcpyAsync(e.dst, e.src, e.bytes, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
     return GG_OK;
 }
 
@@ -1300,9 +1463,12 @@ int gg_gravity(gg_context *c, const gg_params *prm, double *a, double *fPot, dou
         }
         if (zeroCopy) for (int k = 0; k < 4; ++k) { c->zc[k] = dp[k]; c->zcHost[k] = hp[k]; }
     }
+    if (c->stateN > 0 && c->stateDirty)
+        return fail(GG_ERR_ARG, "gg_gravity: the resident particles moved since the last tree build (gg_state_build first)");
     int rc = run_gravity(c, prm, nullptr, stats);
     c->zc[0] = c->zc[1] = c->zc[2] = c->zc[3] = nullptr;
     if (rc) return rc;
+    if (c->stateN > 0 && !(prm->flags & GG_FLAG_WALK_ONLY)) c->stateForces = true;
     if (!wantOut || zeroCopy) return GG_OK;
     const int n = c->dom[0].nPart;
     if (n == 0) return GG_OK;

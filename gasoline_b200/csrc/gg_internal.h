@@ -179,3 +179,13 @@ struct GGBuiltDev {
 int gg_builder_run(void **pBuilder, const gg_particles *pp, int nBucket, double dTheta, cudaStream_t st, GGBuiltDev *out,
                    int *pnLaunches, char *err, size_t errLen);
 void gg_builder_free(void *builder);
+
+// gg_state.cu: kick / drift / grav-step on the device-resident particle store
+cudaError_t gg_launch_kick(int n, double *v, const double *a, const int *active, double f1, double f2, cudaStream_t st);
+cudaError_t gg_launch_drift(int n, double *x, double *y, double *z, const double *v, double dDelta, const double c[3],
+                            int bPeriodic, const double L[3], int *nOutside, cudaStream_t st);
+cudaError_t gg_launch_gravstep(int n, double *dt, const double *dtGrav, const int *active, double dEta,
+                               unsigned long long *dtMinBits, cudaStream_t st);
+cudaError_t gg_launch_permute(int n, const int *iorder, const double *vIn, double *vOut, const int *idIn, int *idOut,
+                              const double *dtIn, double *dtOut, cudaStream_t st);
+cudaError_t gg_launch_state_init(int n, int *id, double *dt, double dt0, cudaStream_t st);

@@ -1,0 +1,109 @@
+// gg_state.cu -- the particle store resident on the device across force evaluations and the two steps either side of
+// the force path: pkdKick (pkd.c:3780; -DNBODY branch pkd.c:3956-3962), pkdDrift
+// (pkd.c:3686-3777) and pkdGravStep (pkd.c:4609-4623).  Element-wise FP64, HBM-bound (kick: 24 B acceleration + 48 B
+// velocity traffic per particle; drift: 72 B), written with __dmul_rn/__dadd_rn in the reference's operation order so
+// the results are bit-identical to the reference's (which is compiled without FMA).
+#include "gg_internal.h"
+
+namespace {
+
+// v = v*dvFacOne + a*dvFacTwo on ACTIVE particles; v is SoA [3][n], a is the force kernels' AoS [n][3]
+__global__ void __launch_bounds__(256) k_kick(int n, double *v, const double *a, const int *active, double f1, double f2) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    if (active && !active[i]) return;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const size_t k = (size_t)j * n + i;
+        v[k] = __dadd_rn(__dmul_rn(v[k], f1), __dmul_rn(a[3 * (size_t)i + j], f2));
+    }
+}
+
+// r += dDelta*v for ALL particles, then the reference's two independent wrap tests per axis (pkd.c:3731-3757)
+__global__ void __launch_bounds__(256) k_drift(int n, double *x, double *y, double *z, const double *v, double dDelta,
+                                               double cx, double cy, double cz, int bPeriodic, double Lx, double Ly,
+                                               double Lz, int *nOutside) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    double *r[3] = {x + i, y + i, z + i};
+    const double c[3] = {cx, cy, cz}, L[3] = {Lx, Ly, Lz};
+    int bad = 0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        double q = __dadd_rn(*r[j], __dmul_rn(dDelta, v[(size_t)j * n + i]));
+        if (bPeriodic) {
+            const double hi = __dadd_rn(c[j], __dmul_rn(0.5, L[j])), lo = __dsub_rn(c[j], __dmul_rn(0.5, L[j]));
+            if (q >= hi) q = __dsub_rn(q, L[j]);
+            if (q < lo) q = __dadd_rn(q, L[j]);
+            bad |= !(q >= lo && q < hi);
+        }
+        *r[j] = q;
+    }
+    if (bad) atomicAdd(nOutside, 1);
+}
+
+// dt = min(dt, dEta/sqrt(dtGrav)) on ACTIVE particles; the smallest dt of all particles -> dtMinBits (ordered integer)
+__global__ void __launch_bounds__(256) k_gravstep(int n, double *dt, const double *dtGrav, const int *active, double dEta,
+                                                  unsigned long long *dtMinBits) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    double d = __longlong_as_double(0x7ff0000000000000ll);
+    if (i < n) {
+        d = dt[i];
+        if (!active || active[i]) {
+            const double g = __ddiv_rn(dEta, __dsqrt_rn(dtGrav[i]));
+            if (g < d) { d = g; dt[i] = d; }
+        }
+    }
+    // positive doubles order like their bit patterns
+    unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    const unsigned h = (unsigned)(b >> 32), mh = __reduce_min_sync(0xffffffffu, h);
+    const unsigned ml = __reduce_min_sync(0xffffffffu, h == mh ? (unsigned)b : 0xffffffffu);
+    if ((threadIdx.x & 31) == 0) atomicMin(dtMinBits, ((unsigned long long)mh << 32) | ml);
+}
+
+// the state's per-particle payload follows the tree build's permutation: out[i] = in[iorder[i]]
+__global__ void __launch_bounds__(256) k_permute(int n, const int *iorder, const double *vIn, double *vOut, const int *idIn,
+                                                 int *idOut, const double *dtIn, double *dtOut) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const int s = iorder[i];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) vOut[(size_t)j * n + i] = vIn[(size_t)j * n + s];
+    idOut[i] = idIn[s];
+    dtOut[i] = dtIn[s];
+}
+
+__global__ void __launch_bounds__(256) k_state_init(int n, int *id, double *dt, double dt0) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    id[i] = i;
+    dt[i] = dt0;
+}
+
+} // namespace
+
+cudaError_t gg_launch_kick(int n, double *v, const double *a, const int *active, double f1, double f2, cudaStream_t st) {
+    if (n > 0) k_kick<<<(n + 255) / 256, 256, 0, st>>>(n, v, a, active, f1, f2);
+    return cudaGetLastError();
+}
+cudaError_t gg_launch_drift(int n, double *x, double *y, double *z, const double *v, double dDelta, const double c[3],
+                            int bPeriodic, const double L[3], int *nOutside, cudaStream_t st) {
+    if (n > 0)
+        k_drift<<<(n + 255) / 256, 256, 0, st>>>(n, x, y, z, v, dDelta, c[0], c[1], c[2], bPeriodic, L[0], L[1], L[2],
+                                                 nOutside);
+    return cudaGetLastError();
+}
+cudaError_t gg_launch_gravstep(int n, double *dt, const double *dtGrav, const int *active, double dEta,
+                               unsigned long long *dtMinBits, cudaStream_t st) {
+    if (n > 0) k_gravstep<<<(n + 255) / 256, 256, 0, st>>>(n, dt, dtGrav, active, dEta, dtMinBits);
+    return cudaGetLastError();
+}
+cudaError_t gg_launch_permute(int n, const int *iorder, const double *vIn, double *vOut, const int *idIn, int *idOut,
+                              const double *dtIn, double *dtOut, cudaStream_t st) {
+    if (n > 0) k_permute<<<(n + 255) / 256, 256, 0, st>>>(n, iorder, vIn, vOut, idIn, idOut, dtIn, dtOut);
+    return cudaGetLastError();
+}
+cudaError_t gg_launch_state_init(int n, int *id, double *dt, double dt0, cudaStream_t st) {
+    if (n > 0) k_state_init<<<(n + 255) / 256, 256, 0, st>>>(n, id, dt, dt0);
+    return cudaGetLastError();
+}

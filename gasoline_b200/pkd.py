@@ -95,6 +95,12 @@ def load_library(path: str | None = None):
     L.gg_build_local.argtypes = [C.c_void_p, C.c_int, C.POINTER(gg_particles), C.c_int, C.c_double, _ip, _ip, _dp]
     L.gg_build_info.argtypes = [C.c_void_p, _ip, _ip, _dp]
     L.gg_tree_fetch.argtypes = [C.c_void_p] + [_dp] * 6 + [_ip] * 4 + [_dp] * 5 + [_ip]
+    L.gg_state_load.argtypes = [C.c_void_p, C.c_int] + [_dp] * 8 + [_ip, C.c_double]
+    L.gg_state_build.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, _ip]
+    L.gg_state_kick.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p]
+    L.gg_state_drift.argtypes = [C.c_void_p, C.c_double, _dp, C.c_int, _dp]
+    L.gg_state_gravstep.argtypes = [C.c_void_p, C.c_double, _dp]
+    L.gg_state_fetch.argtypes = [C.c_void_p] + [_dp] * 6 + [_ip, _dp]
     L.gg_measure_fp32_peak.argtypes = [C.c_void_p, _dp, _dp]
     L.gg_flush_l2.argtypes = [C.c_void_p]
     _lib = L
@@ -208,6 +214,7 @@ class PKD:
         self.active = None if active is None else self._own(active, np.int32)
         self.iOrderMap = np.arange(self.nLocal, dtype=np.int32)
         self.tree = None
+        self._resident = False
 
     def _own(self, a, dt):
         """Private copy of a host array, in pinned memory when the PKD was created with pinned=True."""
@@ -289,6 +296,58 @@ class PKD:
                                      _d(p["fMass"]), _d(p["fSoft"]),
                                      _i(p["active"]) if p["active"] is not None else None), "gg_tree_fetch")
         return Tree(nn, 0, **a), p
+
+    # -- device-resident particle store (gg_state_*): pStore lives in HBM, kick / drift / tree build / gravity on it --
+    def pkdLoadResident(self, x, y, z, vx, vy, vz, fMass, fSoft, active=None, dt0: float = 1e30):
+        """Upload pStore once (gg_state_load); afterwards pkdDrift / pkdKick / pkdBuildBinaryResident / pkdGravAll /
+        pkdGravStep run on the device copy with no per-step particle traffic."""
+        cols = [np.ascontiguousarray(a, dtype=np.float64) for a in (x, y, z, vx, vy, vz, fMass, fSoft)]
+        self.nLocal = int(cols[0].shape[0])
+        act = None if active is None else np.ascontiguousarray(active, dtype=np.int32)
+        self.active = act
+        _check(self._L.gg_state_load(self._ctx, self.nLocal, *[_d(a) for a in cols], _i(act) if act is not None else None,
+                                     float(dt0)), "gg_state_load")
+        self.tree = None
+        self._uploaded = False
+        self._resident = True
+
+    def pkdBuildBinaryResident(self, nBucket: int = 8, dCrit: float = 0.7):
+        """pkdBuildBinary on the resident store (gg_state_build): the store is permuted into tree order on the device."""
+        nn = C.c_int()
+        _check(self._L.gg_state_build(self._ctx, self.idSelf, int(nBucket), float(dCrit), C.byref(nn)), "gg_state_build")
+        self.nNodesDevice = int(nn.value)
+        self._uploaded = True
+        return self.nNodesDevice
+
+    def pkdKick(self, dvFacOne: float, dvFacTwo: float, a=None):
+        """pkdKick (pkd.c:3780) on the resident store; a: optional [n][3] accelerations in the store's order (default:
+        the device results of the last pkdGravAll)."""
+        ap = None
+        if a is not None:
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            ap = a.ctypes.data_as(C.c_void_p)
+        _check(self._L.gg_state_kick(self._ctx, float(dvFacOne), float(dvFacTwo), ap), "gg_state_kick")
+
+    def pkdDrift(self, dDelta: float, fCenter=(0.0, 0.0, 0.0), bPeriodic: int = 0):
+        """pkdDrift (pkd.c:3686) on the resident store, periodic wrap with this PKD's fPeriod."""
+        c = np.array(fCenter, dtype=np.float64)
+        L = np.array(self.fPeriod, dtype=np.float64)
+        _check(self._L.gg_state_drift(self._ctx, float(dDelta), _d(c), int(bPeriodic), _d(L)), "gg_state_drift")
+        self._uploaded = False
+
+    def pkdGravStep(self, dEta: float) -> float:
+        """pkdGravStep (pkd.c:4609) on the resident store; returns the smallest time step of all particles."""
+        dmin = np.zeros(1)
+        _check(self._L.gg_state_gravstep(self._ctx, float(dEta), _d(dmin)), "gg_state_gravstep")
+        return float(dmin[0])
+
+    def pkdFetchResident(self):
+        """Download the resident store (current order): dict with r [n][3], v [n][3], iOrder, dt."""
+        n = self.nLocal
+        c = [np.zeros(n) for _ in range(6)]
+        ids, dt = np.zeros(n, np.int32), np.zeros(n)
+        _check(self._L.gg_state_fetch(self._ctx, *[_d(a) for a in c], _i(ids), _d(dt)), "gg_state_fetch")
+        return dict(r=np.stack(c[:3], axis=1), v=np.stack(c[3:], axis=1), iOrder=ids, dt=dt)
 
     def pkdSetTree(self, tree: Tree, x, y, z, fMass, fSoft, active=None, ilcnRoot=None, iOrderMap=None):
         """Adopt a tree built elsewhere (e.g. the host's own kdNodes); particles must already be in its order."""
@@ -372,8 +431,8 @@ class PKD:
         overwritten for active particles -- the reference's in-place semantics on pStore.  Without: fresh arrays.
         Returns a dict with the arrays (tree order) and the scalars the reference returns through pointers
         (nActive, dPartSum, dCellSum, dSoftSum, dFlop) plus device timings."""
-        if not getattr(self, "_uploaded", False):
-            self.upload()
+        if not getattr(self, "_uploaded", False) and not getattr(self, "_resident", False):
+            self.upload()  # (a resident store that moved since its last build makes gg_gravity fail loudly instead)
         n = self.nLocal
         accumulate = (1 if a is not None else 0) if accumulate is None else int(bool(accumulate))
         flags = (GG_FLAG_WALK_ONLY if walk_only else 0) | (0 if download else GG_FLAG_NO_DOWNLOAD)

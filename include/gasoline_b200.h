@@ -231,6 +231,33 @@ int gg_tree_fetch(gg_context *ctx, double *bnd, double *r, double *fMass, double
                   int *pLower, int *pUpper, int *iLower, int *iUpper, double *x, double *y, double *z, double *fMass_p,
                   double *fSoft_p, int *active);
 
+/*
+ * pkd->pStore RESIDENT on the device across force evaluations, with the steps either side of the force path
+ * (SURVEY 8f ranks 2, 3).  A time-stepping host keeps positions, velocities, masses, softenings, ACTIVE flags and time
+ * steps in HBM and drives
+ *     gg_state_load once;  per step:  gg_state_kick, gg_state_drift, gg_state_build, gg_gravity(GG_FLAG_NO_DOWNLOAD),
+ *     gg_state_kick, [gg_state_gravstep];  gg_state_fetch when it wants output
+ * with no per-step host<->device particle traffic.  The store is kept in TREE order (gg_state_build permutes it like
+ * pkdBuildBinary permutes pStore); id[] carries the index each particle had at gg_state_load (PARTICLE.iOrder).
+ *   gg_state_kick     = pkdKick (pkd.c:3780; the -DNBODY branch pkd.c:3956-3962): ACTIVE particles
+ *                       v = v*dvFacOne + a*dvFacTwo; a = the device results of the last gg_gravity, or the caller's
+ *                       array a[n][3] (host or device pointer, the store's current order) when not NULL
+ *   gg_state_drift    = pkdDrift (pkd.c:3686-3777): ALL particles r += dDelta*v, then the reference's periodic wrap
+ *                       about fCenter; fails if a particle is still outside the box (the reference asserts)
+ *   gg_state_gravstep = pkdGravStep (pkd.c:4609-4623): ACTIVE particles dt = min(dt, dEta/sqrt(dtGrav)); *pdtMin = the
+ *                       smallest dt of all particles (what a single-rung host steps with)
+ * All three are bit-identical to the reference's functions on the same inputs (tests/test_gpu_state.py).
+ */
+int gg_state_load(gg_context *ctx, int n, const double *x, const double *y, const double *z, const double *vx,
+                  const double *vy, const double *vz, const double *fMass, const double *fSoft, const int *active,
+                  double dt0);
+int gg_state_build(gg_context *ctx, int idSelf, int nBucket, double dTheta, int *pnNodes);
+int gg_state_kick(gg_context *ctx, double dvFacOne, double dvFacTwo, const double *a);
+int gg_state_drift(gg_context *ctx, double dDelta, const double fCenter[3], int bPeriodic, const double fPeriod[3]);
+int gg_state_gravstep(gg_context *ctx, double dEta, double *pdtMin);
+int gg_state_fetch(gg_context *ctx, double *x, double *y, double *z, double *vx, double *vy, double *vz, int *id,
+                   double *dt);
+
 /* Every cell's reduced multipoles by the algorithm the DEVICE uses when gg_tree.mom is NULL (raw moments of the
  * buckets, children translated to the parent's centre and summed, then reduced as pkdCalcCell defines them), executed
  * on the host: mom[nNodes][GG_NMOM].  A checking aid for hosts and tests; no GPU needed. */

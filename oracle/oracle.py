@@ -44,8 +44,36 @@ def lib():
                                   _dp, _dp, _dp, _dp, _ip, _dp, C.c_int, C.c_int]
         L.orc_bucket_lists.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _ip, C.c_void_p, C.c_int,
                                        C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.oracle_step_ops.restype = C.c_int
+        L.oracle_step_ops.argtypes = [C.c_int, _dp, _dp, _dp, C.c_void_p, _dp, _dp, C.c_double, C.c_double, C.c_double,
+                                      _dp, C.c_int, _dp, C.c_double, C.c_int]
         _lib = L
     return _lib
+
+
+KICK, DRIFT, GRAVSTEP = 1, 2, 4
+
+
+def step_ops(fn, r, v, a, active, dtGrav, dt, dvFacOne=1.0, dvFacTwo=0.0, dDelta=0.0, fCenter=(0, 0, 0), bPeriodic=0,
+             fPeriod=(1, 1, 1), dEta=0.2, what=KICK | DRIFT):
+    """Common driver of oracle_step_ops / ref_step_ops (same C signature): returns updated copies (r, v, dt) and the
+    function's return value."""
+    r = np.array(r, dtype=np.float64, copy=True).reshape(-1, 3)
+    v = np.array(v, dtype=np.float64, copy=True).reshape(-1, 3)
+    dt = np.array(dt, dtype=np.float64, copy=True)
+    act = None
+    if active is not None:
+        act_arr = np.ascontiguousarray(active, dtype=np.int32)
+        act = act_arr.ctypes.data_as(C.c_void_p)
+    rc = fn(r.shape[0], r, v, np.ascontiguousarray(a, dtype=np.float64).reshape(-1, 3), act,
+            np.ascontiguousarray(dtGrav, dtype=np.float64), dt, float(dvFacOne), float(dvFacTwo), float(dDelta),
+            np.array(fCenter, dtype=np.float64), int(bPeriodic), np.array(fPeriod, dtype=np.float64), float(dEta), int(what))
+    return r, v, dt, rc
+
+
+def oracle_step_ops(*args, **kw):
+    """pkdKick / pkdDrift / pkdGravStep restated (gravity_oracle.c: oracle_step_ops)."""
+    return step_ops(lib().oracle_step_ops, *args, **kw)
 
 
 class OracleGravity:

@@ -381,3 +381,47 @@ int ref_sizeof(int which) {
     }
     return -1;
 }
+
+/*
+ * The steps either side of the force evaluation, run by the reference's OWN pkdKick
+ * (pkd.c:3780, -DNBODY branch :3956-3962), pkdDrift (pkd.c:3686-3777) and pkdGravStep (pkd.c:4609-4623) on a
+ * throw-away one-rank PKD filled from the given arrays.  what: bit 0 kick, bit 1 drift, bit 2 grav-step; applied in
+ * that order.  r3, v3, dt are updated in place.  Pins oracle_step_ops (oracle/gravity_oracle.c) and the golden
+ * fixture tests/golden/stepops.npz.
+ */
+void ref_step_ops(int n, double *r3, double *v3, const double *a3, const int *active, const double *dtGrav, double *dt,
+                  double dvFacOne, double dvFacTwo, double dDelta, const double *fCenter, int bPeriodic,
+                  const double *fPeriod, double dEta, int what) {
+    static const double open3[3] = {FLOAT_MAXVAL, FLOAT_MAXVAL, FLOAT_MAXVAL};
+    double *zero = calloc((size_t)n + 1, sizeof(double));
+    REF *r = ref_create(n, zero, zero, zero, zero, zero, NULL, bPeriodic ? fPeriod : open3);
+    FLOAT c[3];
+    UHC uhc;
+    int i, j;
+    free(zero);
+    memset(&uhc, 0, sizeof(uhc));
+    for (i = 0; i < n; ++i) {
+        PARTICLE *p = &r->pkd->pStore[i];
+        p->iActive = TYPE_DARK | TYPE_TREEACTIVE | ((!active || active[i]) ? TYPE_ACTIVE : 0);
+        for (j = 0; j < 3; ++j) {
+            p->r[j] = r3[3 * i + j];
+            p->v[j] = v3[3 * i + j];
+            p->a[j] = a3[3 * i + j];
+        }
+        p->dtGrav = dtGrav[i];
+        p->dt = dt[i];
+    }
+    for (j = 0; j < 3; ++j) c[j] = fCenter[j];
+    if (what & 1) pkdKick(r->pkd, dvFacOne, dvFacTwo, 0.0, 0.0, 0.0, 0.0, 0, 0.0, 0.0, 0.0, uhc);
+    if (what & 2) pkdDrift(r->pkd, dDelta, c, bPeriodic, 0, 0, 0.0, 0.0);
+    if (what & 4) pkdGravStep(r->pkd, dEta);
+    for (i = 0; i < n; ++i) {
+        PARTICLE *p = &r->pkd->pStore[i];
+        for (j = 0; j < 3; ++j) {
+            r3[3 * i + j] = p->r[j];
+            v3[3 * i + j] = p->v[j];
+        }
+        dt[i] = p->dt;
+    }
+    ref_destroy(r);
+}

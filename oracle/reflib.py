@@ -48,8 +48,17 @@ def lib(gpu_host: bool = False):
                                   C.c_double, _dp, _dp, _dp, _dp, _ip, _dp]
         L.ref_bucket_lists.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _ip, C.c_void_p, C.c_int,
                                        C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.ref_step_ops.restype = None
+        L.ref_step_ops.argtypes = [C.c_int, _dp, _dp, _dp, C.c_void_p, _dp, _dp, C.c_double, C.c_double, C.c_double,
+                                   _dp, C.c_int, _dp, C.c_double, C.c_int]
         _libs[gpu_host] = L
     return _libs[gpu_host]
+
+
+def ref_step_ops(*args, **kw):
+    """The reference's own pkdKick / pkdDrift / pkdGravStep (ref_api.c: ref_step_ops); same driver as the oracle's."""
+    from oracle.oracle import step_ops
+    return step_ops(lib().ref_step_ops, *args, **kw)
 
 
 class RefGravity:
