@@ -162,6 +162,7 @@ def run_ours(a):
     import torch.distributed as dist
     from gasoline_b200 import build as gbuild, ics
     from gasoline_b200.pkd import PKD, GravityParams, pinned_empty
+    import numpy as np
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -276,6 +277,35 @@ def run_ours(a):
                           "what": "host particles (any order) -> gg_build_local (pkdBuildBinary on the device) -> "
                                   "gg_gravity -> host arrays; the host tree build of the e2e leg is not needed"}
         pkd2.close()
+        # ---- SURVEY 8f ranks 2+3: the particle store resident in HBM; one kick-drift-kick step = kick, drift, tree
+        #      build, gravity, kick, grav-step, all on the device, no per-step particle traffic
+        pkd3 = PKD(device=local, fPeriod=p.period)
+        zero = np.zeros(n)
+        pkd3.pkdLoadResident(p.x, p.y, p.z, zero, zero, zero, p.m, p.h)
+        pkd3.pkdBuildBinaryResident(8, theta)
+        pkd3.pkdGravAll(g, download=False)
+        dstep = 1e-4  # small: the workload (list lengths) stays that of the configuration
+        inter_res = 0.0
+        for it in range(min(a.warmup, 2) + a.steps):
+            if it == min(a.warmup, 2):
+                barrier()
+                r0 = time.perf_counter()
+            pkd3.pkdKick(1.0, 0.5 * dstep)
+            pkd3.pkdDrift(dstep, (0.0, 0.0, 0.0), g.bPeriodic)
+            pkd3.pkdBuildBinaryResident(8, theta)
+            st3 = pkd3.pkdGravAll(g, download=False)
+            pkd3.pkdKick(1.0, 0.5 * dstep)
+            dt_min = pkd3.pkdGravStep(0.2)
+            if it >= min(a.warmup, 2):
+                inter_res += st3["dPartSum"] + st3["dCellSum"] + st3["dSoftSum"]
+        barrier()
+        rs_s = (time.perf_counter() - r0) / a.steps
+        from_particles["resident_kdk_step"] = {
+            "value": inter_res / a.steps / rs_s, "unit": UNIT, "ms_per_step": rs_s * 1e3, "dt_min": dt_min,
+            "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 16,
+            "what": "gg_state_kick, gg_state_drift, gg_state_build, gg_gravity(NO_DOWNLOAD), gg_state_kick, "
+                    "gg_state_gravstep on the device-resident store"}
+        pkd3.close()
 
     # ---- reduce over ranks: time = max, work = sum
     vals = torch.tensor([ms_total, ms_tree, e2e_s, wall_resident, ms_eval, ms_walk, ms_ewald], dtype=torch.float64,

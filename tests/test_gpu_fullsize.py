@@ -1,4 +1,5 @@
-"""GPU parity at BASELINE.json's full sizes (configs[1] = Plummer 1 M, configs[2] = periodic 128^3 + Ewald).
+"""GPU parity at BASELINE.json's full sizes (configs[1] = Plummer 1 M, configs[2] = periodic 128^3 + Ewald,
+configs[3] = periodic 256^3 = 16.8 M particles at theta = 0.5 on ONE GPU).
 
 The oracle cannot evaluate millions of sinks in seconds, so the full-size run is checked three ways:
   * a random sample of COMPLETE sink buckets is re-evaluated by the oracle on the same tree (the oracle marks just
@@ -21,6 +22,7 @@ pytestmark = pytest.mark.gpu
 CASES = {
     "c2_plummer_1m": (lambda: ics.plummer(1_000_000), 0.7, GravityParams(nReps=0, bPeriodic=0, bEwald=0), 300),
     "c3_periodic128_ewald": (lambda: ics.periodic_box(128), 0.7, GravityParams(nReps=1, bPeriodic=1, bEwald=1), 150),
+    "c4_periodic256_theta05_ewald": (lambda: ics.periodic_box(256), 0.5, GravityParams(nReps=1, bPeriodic=1, bEwald=1), 100),
 }
 
 

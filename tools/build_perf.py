@@ -28,5 +28,7 @@ for i in range(a.reps):
     if a.gravity:
         t = time.time()
         out = pkd.pkdGravAll(g, download=False)
-        line += f" | gravity total {out['msTotal']:.3f} ms wall {(time.time()-t)*1e3:.2f} ms"
+        inter = out["dPartSum"] + out["dCellSum"] + out["dSoftSum"]
+        line += (f" | gravity total {out['msTotal']:.3f} ms (walk {out['msWalk']:.2f} eval {out['msEval']:.2f} ewald {out['msEwald']:.2f})"
+                 f" wall {(time.time()-t)*1e3:.2f} ms, {inter:.4g} interactions -> {inter/out['msTotal']*1e3:.4g}/s")
     print(line)
