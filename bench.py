@@ -307,6 +307,33 @@ def run_ours(a):
                     "gg_state_gravstep on the device-resident store"}
         pkd3.close()
 
+    if world > 1:
+        # ---- the same per-step work with every rank's tree built on its GPU (gg_build_local) instead of handed over by
+        #      the host: particles H2D, tree build, root summaries + top tree (two small all-gathers), pruned LET
+        #      exchange, force evaluation, results to the host
+        from gasoline_b200 import domain
+        pkd4, exchange4 = domain.setup_rank(p, theta, rank, world, local, device_build=True)
+        n4 = pkd4.nLocal
+        o4 = (pinned_empty((n4, 3)), pinned_empty(n4), pinned_empty(n4), pinned_empty(n4))
+        for it in range(min(a.warmup, 2) + a.steps):
+            if it == min(a.warmup, 2):
+                barrier()
+                f0 = time.perf_counter()
+            exchange4(let=g, rebuild=True)
+            st4 = pkd4.pkdGravAll(g, *o4, accumulate=False)
+        barrier()
+        fp_s = (time.perf_counter() - f0) / a.steps
+        fp_vals = torch.tensor([fp_s], dtype=torch.float64, device="cuda")
+        fp_sums = torch.tensor([st4["dPartSum"] + st4["dCellSum"] + st4["dSoftSum"]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(fp_vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(fp_sums, op=dist.ReduceOp.SUM)
+        from_particles = {"value": fp_sums.item() / fp_vals.item(), "unit": UNIT, "ms_per_step": fp_vals.item() * 1e3,
+                          "tree_build_device_ms_rank0": pkd4.pkdBuildInfo()[2],
+                          "phases_ms_rank0": {k: v * 1e3 for k, v in exchange4.driver.timing.items()},
+                          "what": "per rank: host particles -> gg_build_local -> root summaries / top tree (all-gathers) -> "
+                                  "pruned LET exchange (NCCL all-to-all) -> gg_gravity -> host arrays"}
+        pkd4.close()
+
     # ---- reduce over ranks: time = max, work = sum
     vals = torch.tensor([ms_total, ms_tree, e2e_s, wall_resident, ms_eval, ms_walk, ms_ewald], dtype=torch.float64,
                         device="cuda")

@@ -866,6 +866,72 @@ int gg_state_fetch(gg_context *c, double *x, double *y, double *z, double *vx, d
     return GG_OK;
 }
 
+// The root cell of the local (device-built) domain: what a multi-rank host hands to pstColCells / pstCalcRoot.
+int gg_domain_summary(gg_context *c, double bnd[6], double r[3], double *fMass, double *fSoft, double *fOpen2,
+                      double mom[GG_NMOM], double root[GG_NROOT]) {
+    if (!c || !c->built.nNodes || c->dom.empty())
+        return fail(GG_ERR_ARG, "gg_domain_summary: no device-built local tree (gg_build_local)");
+    CK(cudaSetDevice(c->device));
+    int rc;
+    c->rootLazy = true; // (re)read from the device records: gg_set_root_moments may have replaced c->root meanwhile
+    double keep[GG_NROOT];
+    const bool had = c->haveRoot;
+    memcpy(keep, c->root, sizeof(keep));
+    if ((rc = fetch_root_lazy(c))) return rc;
+    if (root) memcpy(root, c->root, sizeof(c->root));
+    if (had) memcpy(c->root, keep, sizeof(keep)); // a multi-rank root set by the host stays in force
+    const int iRoot = c->dom[0].iRoot;
+    double raw[32];
+    NodeW w;
+    CK(cudaMemcpyAsync(raw, (const double *)c->momraw.p + (size_t)iRoot * 32, sizeof(raw), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(&w, (const NodeW *)c->nodes.p + iRoot, sizeof(w), cudaMemcpyDeviceToHost, c->st));
+    if (bnd) CK(cudaMemcpyAsync(bnd, c->built.bnd + 6 * (size_t)iRoot, 6 * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    if (r) { r[0] = w.rx; r[1] = w.ry; r[2] = w.rz; }
+    if (fMass) *fMass = w.fMass;
+    if (fSoft) *fSoft = w.fSoft;
+    if (fOpen2) *fOpen2 = w.fOpen2;
+    if (mom) {
+        GGRawMom a;
+        a.M = raw[0];
+        for (int k = 0; k < 31; ++k) a.q[k] = raw[1 + k];
+        gg_raw_reduce(a, mom);
+    }
+    return GG_OK;
+}
+
+// pkdCalcCell (pkd.c:2018-2135) over the whole local domain about the centre rcm -- one rank's contribution to an
+// interior cell of the top tree (pstCalcCell, pst.c:3789): the moments by translating the root's raw moment record to
+// rcm (exact binomial shift) and reducing it, Bmax by one pass over the particles.
+int gg_domain_moments_about(gg_context *c, const double rcm[3], double mom[GG_NMOM], double *pBmax) {
+    if (!c || !rcm || !mom || !pBmax || c->dom.empty() || !c->momraw.p)
+        return fail(GG_ERR_ARG, "gg_domain_moments_about: needs a local domain with device-formed moments");
+    CK(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = finish_mom(c))) return rc;
+    if ((rc = ensure(c, c->misc, 16 * sizeof(int)))) return rc;
+    unsigned long long *dMax = (unsigned long long *)((int *)c->misc.p + 14);
+    const Domain &L = c->dom[0];
+    CK(cudaMemsetAsync(dMax, 0, sizeof(unsigned long long), c->st));
+    CK(gg_launch_bmax_about(L.nPart, (const PartS *)c->parts.p + L.partBase, rcm, dMax, c->st));
+    ++c->nLaunches;
+    double raw[32];
+    NodeW w;
+    unsigned long long bits = 0;
+    CK(cudaMemcpyAsync(raw, (const double *)c->momraw.p + (size_t)L.iRoot * 32, sizeof(raw), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(&w, (const NodeW *)c->nodes.p + L.nodeBase + L.iRoot, sizeof(w), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(&bits, dMax, sizeof(bits), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    GGRawMom src, dst;
+    src.M = raw[0];
+    for (int k = 0; k < 31; ++k) src.q[k] = raw[1 + k];
+    gg_raw_zero(dst);
+    gg_raw_shift_add(dst, src, w.rx - rcm[0], w.ry - rcm[1], w.rz - rcm[2]);
+    gg_raw_reduce(dst, mom);
+    memcpy(pBmax, &bits, sizeof(double));
+    return GG_OK;
+}
+
 int gg_build_info(gg_context *c, int *pnNodes, int *pnLevels, double *pmsBuild) {
     if (!c || !c->built.nNodes) return fail(GG_ERR_ARG, "gg_build_info: no device-built tree");
     if (pnNodes) *pnNodes = c->built.nNodes;

@@ -189,3 +189,4 @@ cudaError_t gg_launch_gravstep(int n, double *dt, const double *dtGrav, const in
 cudaError_t gg_launch_permute(int n, const int *iorder, const double *vIn, double *vOut, const int *idIn, int *idOut,
                               const double *dtIn, double *dtOut, cudaStream_t st);
 cudaError_t gg_launch_state_init(int n, int *id, double *dt, double dt0, cudaStream_t st);
+cudaError_t gg_launch_bmax_about(int n, const PartS *parts, const double c[3], unsigned long long *out, cudaStream_t st);

@@ -80,7 +80,28 @@ __global__ void __launch_bounds__(256) k_state_init(int n, int *id, double *dt, 
     dt[i] = dt0;
 }
 
+// max |r_p - rcm| over the particles (Bmax of pkdCalcCell, pkd.c:2018-2135, for one domain about a given centre):
+// distances in the reference's expression, the maximum as an ordered-integer atomicMax
+__global__ void __launch_bounds__(256) k_bmax_about(int n, const PartS *parts, double cx, double cy, double cz,
+                                                    unsigned long long *out) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    unsigned long long b = 0ull;
+    if (i < n) {
+        const double dx = __dsub_rn(parts[i].x, cx), dy = __dsub_rn(parts[i].y, cy), dz = __dsub_rn(parts[i].z, cz);
+        const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+        b = (unsigned long long)__double_as_longlong(__dsqrt_rn(d2));
+    }
+    const unsigned h = (unsigned)(b >> 32), mh = __reduce_max_sync(0xffffffffu, h);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, h == mh ? (unsigned)b : 0u);
+    if ((threadIdx.x & 31) == 0) atomicMax(out, ((unsigned long long)mh << 32) | ml);
+}
+
 } // namespace
+
+cudaError_t gg_launch_bmax_about(int n, const PartS *parts, const double c[3], unsigned long long *out, cudaStream_t st) {
+    if (n > 0) k_bmax_about<<<(n + 255) / 256, 256, 0, st>>>(n, parts, c[0], c[1], c[2], out);
+    return cudaGetLastError();
+}
 
 cudaError_t gg_launch_kick(int n, double *v, const double *a, const int *active, double f1, double f2, cudaStream_t st) {
     if (n > 0) k_kick<<<(n + 255) / 256, 256, 0, st>>>(n, v, a, active, f1, f2);

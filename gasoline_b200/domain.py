@@ -131,8 +131,16 @@ class Domain:
     """One rank: its particles (tree order) and local tree on the host; the top tree once assemble() has run."""
 
     def __init__(self, idSelf: int, nThreads: int, x, y, z, m, h, fPeriod, theta: float, nBucket: int = 8,
-                 iOrder: int = 4, active=None, pinned: bool = False, device: int | None = None):
+                 iOrder: int = 4, active=None, pinned: bool = False, device: int | None = None,
+                 device_build: bool = False):
+        """device_build: the local tree is built ON THE GPU from the particles (gg_build_local) and never exists on the
+        host; the rank's root summary and its ancestor sums come from the device (gg_domain_summary,
+        gg_domain_moments_about).  Needs a device."""
         self.idSelf, self.nThreads, self.theta, self.iOrder = idSelf, nThreads, float(theta), iOrder
+        self.nBucket = nBucket
+        self.device_build = bool(device_build)
+        if self.device_build and device is None:
+            raise _pkd.GasolineB200Error("Domain: device_build needs a device")
         self.fPeriod = tuple(float(v) for v in fPeriod)
         self.pst = pst_tree(nThreads)
         self.L = _pkd.load_library()
@@ -140,13 +148,25 @@ class Domain:
         self.pkd = PKD(device=device, idSelf=idSelf, fPeriod=fPeriod, pinned=pinned) if device is not None else None
         host = self.pkd if self.pkd is not None else _HostStore()
         host.pkdLoadParticles(x, y, z, m, h, active)
-        _build(host, nBucket, theta, iOrder)
         self.host = host
+        if self.device_build:
+            self.rebuild()
+        else:
+            _build(host, nBucket, theta, iOrder)
         self.kdTop = None
         self.ilcnRoot = None
 
+    def rebuild(self):
+        """(device_build) pkdBuildBinary on the GPU from the rank's current particles; the domain is left loaded."""
+        self.pkd.pkdBuildBinaryDevice(self.nBucket, self.theta)
+        self.kdTop = None
+
     # -- step 1
     def summary(self) -> np.ndarray:
+        if self.device_build:
+            s = self.pkd.pkdDomainSummary()
+            return np.concatenate([s["bnd"], s["r"], [s["fMass"], s["fSoft"], s["fOpen2"]], s["mom"],
+                                   s["root"]]).astype(np.float64)
         t, r = self.host.tree, self.host.tree.iRoot
         return np.concatenate([t.bnd[r], t.r[r], [t.fMass[r], t.fSoft[r], t.fOpen2[r]], t.mom[r],
                                self.host.ilcnRoot]).astype(np.float64)
@@ -163,6 +183,9 @@ class Domain:
             if self.idSelf not in n.ranks:
                 continue
             rcm = np.ascontiguousarray(cells[n.iCell]["r"], dtype=np.float64)
+            if self.device_build:
+                out[k, :GG_NMOM], out[k, GG_NMOM] = self.pkd.pkdDomainMomentsAbout(rcm)
+                continue
             mom, bmax = np.zeros(GG_NMOM), C.c_double()
             rc = self.L.gg_cell_moments(h.nLocal, _pkd._d(h.x), _pkd._d(h.y), _pkd._d(h.z), _pkd._d(h.fMass),
                                         _pkd._d(rcm), self.iOrder, _pkd._d(mom), C.byref(bmax))
@@ -190,7 +213,8 @@ class Domain:
         """Hand kdTop + ilcnRoot to the GPU context (gg_set_local via upload, gg_set_top, gg_set_root_moments)."""
         if self.pkd is None:
             raise _pkd.GasolineB200Error("Domain.attach: created without a device")
-        self.pkd.upload()
+        if not self.device_build:  # (a device-built domain is already loaded)
+            self.pkd.upload()
         k = self.kdTop
         self.pkd.pkdDistribCells(k["pLower"], k["bUsed"], k["r"], k["fMass"], k["fSoft"], k["fOpen2"], k["mom"])
         self.pkd.pkdDistribRoot(self.ilcnRoot)
@@ -575,7 +599,7 @@ class _DevView:
 
 
 def setup_rank(p, theta: float, rank: int, world: int, device: int | None, nBucket: int = 8, iOrder: int = 4,
-               weights=None, backend_device: str | None = None):
+               weights=None, backend_device: str | None = None, device_build: bool = False):
     """What one torch.distributed rank does before its first force evaluation (bench.py --gpus N, tests): every rank
     holds the same particle set `p`, takes ITS share of the ORB decomposition (the host's job in a Gasoline run,
     pstDomainDecomp pst.c:1854), builds its local tree and creates its GPU context.  Returns (pkd, exchange) where
@@ -584,13 +608,17 @@ def setup_rank(p, theta: float, rank: int, world: int, device: int | None, nBuck
     parts = orb_decompose(p.x, p.y, p.z, world, weights=weights)
     idx = parts[rank]
     d = Domain(rank, world, p.x[idx], p.y[idx], p.z[idx], p.m[idx], p.h[idx], p.period, theta, nBucket=nBucket,
-               iOrder=iOrder, pinned=device is not None, device=device)
-    d.global_index = idx[d.host.iOrderMap]  # tree position -> index in p
+               iOrder=iOrder, pinned=device is not None, device=device, device_build=device_build)
+    d.global_index = idx[d.pkd.treeOrder if device_build else d.host.iOrderMap]  # tree position -> index in p
     ex = DistributedExchange(d, backend_device or ("cpu" if device is None else "cuda"))
     attach = device is not None
 
-    def exchange(top: bool = True, let=None):
-        """let = GravityParams: send pruned locally-essential trees (gg_let_export) instead of whole domains."""
+    def exchange(top: bool = True, let=None, rebuild: bool = False):
+        """let = GravityParams: send pruned locally-essential trees (gg_let_export) instead of whole domains.
+        rebuild (device_build only): build the local tree again from the rank's particles first (a new step)."""
+        if rebuild:
+            d.rebuild()
+            top = True
         if attach and ex.dev != "cpu":
             return ex.exchange_let(let, top=top) if let is not None else ex.exchange_packed(top=top)
         return ex.exchange(attach=attach)

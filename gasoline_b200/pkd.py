@@ -94,6 +94,8 @@ def load_library(path: str | None = None):
     L.gg_tree_moments_m2m.argtypes = [C.POINTER(gg_tree), C.POINTER(gg_particles), _dp]
     L.gg_build_local.argtypes = [C.c_void_p, C.c_int, C.POINTER(gg_particles), C.c_int, C.c_double, _ip, _ip, _dp]
     L.gg_build_info.argtypes = [C.c_void_p, _ip, _ip, _dp]
+    L.gg_domain_summary.argtypes = [C.c_void_p] + [_dp] * 7
+    L.gg_domain_moments_about.argtypes = [C.c_void_p, _dp, _dp, _dp]
     L.gg_tree_fetch.argtypes = [C.c_void_p] + [_dp] * 6 + [_ip] * 4 + [_dp] * 5 + [_ip]
     L.gg_state_load.argtypes = [C.c_void_p, C.c_int] + [_dp] * 8 + [_ip, C.c_double]
     L.gg_state_build.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, _ip]
@@ -281,6 +283,21 @@ class PKD:
         nn, nl, ms = C.c_int(), C.c_int(), C.c_double()
         _check(self._L.gg_build_info(self._ctx, C.byref(nn), C.byref(nl), C.byref(ms)), "gg_build_info")
         return nn.value, nl.value, ms.value
+
+    def pkdDomainSummary(self):
+        """The root cell of the device-built local tree (gg_domain_summary): dict bnd, r, fMass, fSoft, fOpen2, mom,
+        root (pkdCalcRoot's expansion of this rank) -- what pstColCells / pstCalcRoot collect from a rank."""
+        bnd, r, sc, mom, root = np.zeros(6), np.zeros(3), np.zeros(3), np.zeros(GG_NMOM), np.zeros(GG_NROOT)
+        _check(self._L.gg_domain_summary(self._ctx, _d(bnd), _d(r), _d(sc[0:1]), _d(sc[1:2]), _d(sc[2:3]), _d(mom),
+                                         _d(root)), "gg_domain_summary")
+        return dict(bnd=bnd, r=r, fMass=float(sc[0]), fSoft=float(sc[1]), fOpen2=float(sc[2]), mom=mom, root=root)
+
+    def pkdDomainMomentsAbout(self, rcm):
+        """pkdCalcCell over the whole local domain about rcm (gg_domain_moments_about): (mom[31], Bmax)."""
+        c = np.ascontiguousarray(rcm, dtype=np.float64)
+        mom, bmax = np.zeros(GG_NMOM), np.zeros(1)
+        _check(self._L.gg_domain_moments_about(self._ctx, _d(c), _d(mom), _d(bmax)), "gg_domain_moments_about")
+        return mom, float(bmax[0])
 
     def pkdFetchTree(self, with_mom: bool = True):
         """Download the device-built tree (gg_tree_fetch): returns (Tree, dict of the particles in tree order)."""

@@ -222,6 +222,16 @@ void gg_tree_free(gg_built_tree *bt);
  */
 int gg_build_local(gg_context *ctx, int idSelf, const gg_particles *part, int nBucket, double dTheta, int *iOrder,
                    int *pnNodes, double root[GG_NROOT]);
+/*
+ * Multi-rank hosts with device-built trees: the root cell of this rank's tree (what pstColCells gathers into kdTop,
+ * pkd.c:4349, and pkdCalcRoot's expansion, pkd.c:4395) and this rank's pkdCalcCell sums about the centre of an interior
+ * top-tree cell (pstCalcCell, pst.c:3789: reduced moments + Bmax over ALL local particles about rcm) -- the two things
+ * the top-tree assembly needs from a rank, without the tree ever leaving the device.  Any output pointer of
+ * gg_domain_summary may be NULL.
+ */
+int gg_domain_summary(gg_context *ctx, double bnd[6], double r[3], double *fMass, double *fSoft, double *fOpen2,
+                      double mom[GG_NMOM], double root[GG_NROOT]);
+int gg_domain_moments_about(gg_context *ctx, const double rcm[3], double mom[GG_NMOM], double *pBmax);
 /* nodes, tree levels and device time (ms, CUDA events) of the last gg_build_local */
 int gg_build_info(gg_context *ctx, int *pnNodes, int *pnLevels, double *pmsBuild);
 /* Copy the device-built tree (pre-order numbering, the layout of gg_tree; mom = the device-formed reduced multipoles)

@@ -76,3 +76,43 @@ def test_pruned_let_equals_whole_domains(case, gpu_lib):
             assert a[k] == b[k]
         assert np.array_equal(a["acc"], b["acc"]) and np.array_equal(a["pot"], b["pot"])
         assert np.array_equal(a["fWeight"], b["fWeight"])
+
+
+@pytest.mark.parametrize("case", ["plummer200k_r4", "periodic32_r3"])
+def test_device_built_domains_equal_host_built(case, gpu_lib):
+    """Multi-domain run with every rank's tree built ON THE GPU (gg_build_local; root summaries and ancestor sums from
+    gg_domain_summary / gg_domain_moments_about) against the host-built run: identical local trees and identical top-tree
+    geometry (r, fMass, fSoft, fOpen2 -- Bmax is a maximum) give identical interaction lists; the top cells' moments are
+    summed in another order (translated root record instead of particle by particle), so forces agree to FP64 rounding
+    of those few cells' moments, far inside the tolerance."""
+    from gasoline_b200 import ics
+    if case == "plummer200k_r4":
+        p, world, g = ics.plummer(200_000, seed=9), 4, GravityParams(nReps=0, bPeriodic=0, bEwald=0)
+    else:
+        p, world, g = ics.periodic_box(32), 3, GravityParams(nReps=1, bPeriodic=1, bEwald=1)
+    parts = domain.orb_decompose(p.x, p.y, p.z, world)
+    results, tops = {}, {}
+    for mode in ("host", "device"):
+        doms = [domain.Domain(r, world, p.x[ix], p.y[ix], p.z[ix], p.m[ix], p.h[ix], p.period, 0.7, device=0,
+                              device_build=mode == "device") for r, ix in enumerate(parts)]
+        domain.run_in_process(doms, let=g)
+        tops[mode] = (doms[0].kdTop, doms[0].ilcnRoot)
+        results[mode] = [(d.pkd.pkdGravAll(g), d.pkd.pkdBucketCounts(),
+                          d.pkd.treeOrder.copy() if mode == "device" else d.host.iOrderMap.copy()) for d in doms]
+        for d in doms:
+            d.pkd.close()
+    th, td = tops["host"][0], tops["device"][0]
+    for k in ("pLower", "bUsed", "r", "fMass", "fSoft", "fOpen2", "bnd"):
+        assert np.array_equal(th[k], td[k]), f"top tree field {k} differs"
+    scale = np.abs(th["mom"]).max(axis=0) + 1e-300
+    assert np.max(np.abs(th["mom"] - td["mom"]) / scale) < 1e-9
+    assert np.allclose(tops["host"][1], tops["device"][1], rtol=1e-6, atol=1e-9 * np.abs(tops["host"][1]).max())
+    for (a, ca, oa), (b, cb, ob) in zip(results["host"], results["device"]):
+        assert np.array_equal(oa, ob), "particle order differs"
+        assert np.array_equal(ca, cb), "per-bucket list counts differ"
+        for k in ("dPartSum", "dCellSum", "dSoftSum", "dFlop"):
+            assert a[k] == b[k]
+        rel = np.linalg.norm(a["acc"] - b["acc"], axis=1) / np.linalg.norm(a["acc"], axis=1)
+        print(f"{case}: device-built vs host-built domains: acc max rel diff {rel.max():.2e}")
+        assert rel.max() < 1e-6
+        assert np.array_equal(a["fWeight"], b["fWeight"])
