@@ -12,4 +12,9 @@ timeout 600 python tools/quick_perf.py --workload periodic --n 64 --theta 0.7 --
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_ncu.log 2>&1
 bash tools/gpu_prof.sh k_eval k_walk k_scatter
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_ewald -s 0 -c 1 -f -o gpurun_out/prof_k_ewald python tools/quick_perf.py --workload periodic --n 64 --reps 1 > gpurun_out/ncu_ewald.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_eval -s 1 -c 1 -f -o gpurun_out/prof_k_eval_mono64 python tools/quick_perf.py --workload periodic --n 128 --reps 2 > gpurun_out/ncu_mono.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/launches_build.csv python tools/build_perf.py --reps 1 --gravity 0 > gpurun_out/build_ncu.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_split -s 40 -c 1 -f -o gpurun_out/prof_k_split python tools/build_perf.py --reps 2 --gravity 0 > gpurun_out/ncu_split.log 2>&1
+timeout 300 python tools/build_perf.py --reps 3 > gpurun_out/build_perf.log 2>&1
+timeout 300 python tools/build_perf.py --workload periodic --n 128 --reps 3 >> gpurun_out/build_perf.log 2>&1
 ls -la gpurun_out
