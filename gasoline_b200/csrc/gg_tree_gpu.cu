@@ -22,7 +22,10 @@
 // cell holding position i):  k_flag (split decision recomputed per particle from the cell's bounds; flag = r[dim] < split;
 // the first particle of a cell allocates the two children) -> cub exclusive scan -> k_split (ranks -> exchange table;
 // children's ranges; children's squeezed bounds by ordered-integer atomic min/max, block/warp pre-reduced -- a particle's
-// side is its flag, wherever the exchange will put it) -> k_swap (exchange pair k, re-home position i).  Then one bottom-up kernel (arrival counters, like gg_moments.cu), one numbering kernel (pre-order index
+// side is its flag, wherever the exchange will put it) -> k_swap (exchange pair k, re-home position i).  A cell that
+// still splits but holds <= GGB_WCAP particles leaves this path: k_finish builds its whole sub-tree with one warp in
+// shared memory (same rules, ballots instead of the scan), which removes the deepest levels of launches (Plummer 1 M:
+// 34 -> 28 levels).  Then one bottom-up kernel (arrival counters, like gg_moments.cu), one numbering kernel (pre-order index
 // and threaded "next" from subtree sizes), Bmax by warp-aggregated atomic max while climbing, and the emit kernel.
 #include <cub/cub.cuh>
 #include <math.h>
@@ -43,6 +46,9 @@ struct __align__(8) BNode { // construction record, breadth-first numbering
 };
 
 #define GGB_MAX_LEVELS 192
+#ifndef GGB_WCAP
+#define GGB_WCAP 128 // largest cell (particles) finished by one warp in shared memory (64 / 128 / 256 measured: 3.08 / 2.94 / 2.98 ms)
+#endif
 
 __device__ __forceinline__ unsigned long long enc(double v) {
     const long long b = __double_as_longlong(v);
@@ -78,6 +84,7 @@ __global__ void k_b_init(int n, int *iord, int *cellOf, BNode *nodes, int *ctr, 
         for (int k = 0; k < 3; ++k) { r.b[k] = ~0ull; r.b[3 + k] = 0ull; }
         nodes[0] = r;
         ctr[0] = 1;
+        ctr[1] = 0; // cells handed to k_finish
         levelStart[0] = 0; // the root is fresh at level 0
         levelStart[1] = 1; // cells allocated by level 0 start here
     }
@@ -150,7 +157,7 @@ __device__ __forceinline__ int decide(const BNode &nd, int nBucket, double *pSpl
 
 __global__ void __launch_bounds__(256) k_flag(int n, const double *x, const double *y, const double *z, const int *cellOf,
                                               const int *levelStart, int level, BNode *nodes, int nBucket, int *flag,
-                                              int *ctr) {
+                                              int *ctr, int *retired) {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i > n) return;
     int f = 0;
@@ -159,7 +166,10 @@ __global__ void __launch_bounds__(256) k_flag(int n, const double *x, const doub
         if (c >= levelStart[level]) {
             const BNode nd = nodes[c];
             double split;
-            const int d = decide(nd, nBucket, &split);
+            int d = decide(nd, nBucket, &split);
+            // a cell that still splits but holds <= GGB_WCAP particles leaves the level-synchronous path here: one warp
+            // of k_finish builds its whole sub-tree in shared memory
+            if (d >= 0 && nd.hi - nd.lo + 1 <= GGB_WCAP) d = -2;
             if (d >= 0) {
                 const double v = d == 0 ? x[i] : (d == 1 ? y[i] : z[i]);
                 f = v < split;
@@ -167,6 +177,7 @@ __global__ void __launch_bounds__(256) k_flag(int n, const double *x, const doub
             if (i == nd.lo) { // one thread per cell records the decision and, for a split, allocates the two children
                 nodes[c].dim = d;
                 nodes[c].split = d >= 0 ? split : 0.0;
+                if (d == -2) retired[atomicAdd(&ctr[1], 1)] = c;
                 if (d >= 0) {
                     const int id = atomicAdd(&ctr[0], 2);
                     BNode ch;
@@ -291,6 +302,130 @@ __global__ void __launch_bounds__(256) k_swap(int n, int *cellOf, const int *lev
         if (act) { u = act[a]; act[a] = act[b]; act[b] = u; }
     }
     cellOf[j] = j < mid ? nd.left : nd.right;
+}
+
+// The sub-tree of one retired cell (<= GGB_WCAP particles), built by ONE WARP in shared memory with the same rules as the
+// level-synchronous path: squeezed bounds as ordered integers, BuildBinary's decision, the reference's exchange
+// partition reproduced from prefix counts (ballots), children allocated from the same node counter.  Depth-first with
+// an explicit stack; the final cell numbering does not depend on allocation order (k_number).  At the end the warp
+// applies its permutation to the particle payload and re-homes its positions (cellOf = the bucket holding them).
+struct FinishSmem {
+    double x[GGB_WCAP], y[GGB_WCAP], z[GGB_WCAP];
+    double pm[GGB_WCAP], ph[GGB_WCAP];
+    int pa[GGB_WCAP], po[GGB_WCAP];
+    int stack[GGB_WCAP + 2][3]; // cell, first, one past last (offsets into the retired cell's range)
+    unsigned char idx[GGB_WCAP], tabL[GGB_WCAP / 2], tabR[GGB_WCAP / 2];
+};
+#ifndef GGB_FINISH_WARPS
+#define GGB_FINISH_WARPS 4
+#endif
+
+__global__ void __launch_bounds__(GGB_FINISH_WARPS * 32) k_finish(int nRet, const int *retired, BNode *nodes, int *cellOf,
+                                                                  double *x, double *y, double *z, double *m, double *h,
+                                                                  int *act, int *iord, int nBucket, int *ctr) {
+    __shared__ FinishSmem s_all[GGB_FINISH_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int w = blockIdx.x * GGB_FINISH_WARPS + warp;
+    if (w >= nRet) return;
+    FinishSmem &S = s_all[warp];
+    const unsigned lt = (1u << lane) - 1u;
+    const int c0 = retired[w];
+    const int lo = nodes[c0].lo, n = nodes[c0].hi - lo + 1;
+    for (int i = lane; i < n; i += 32) {
+        S.x[i] = x[lo + i]; S.y[i] = y[lo + i]; S.z[i] = z[lo + i];
+        S.idx[i] = (unsigned char)i;
+    }
+    if (lane == 0) { S.stack[0][0] = c0; S.stack[0][1] = 0; S.stack[0][2] = n; }
+    int sp = 1;
+    __syncwarp();
+    while (sp > 0) {
+        --sp;
+        const int cell = S.stack[sp][0], a = S.stack[sp][1], b = S.stack[sp][2];
+        __syncwarp();
+        // squeezed bounds
+        unsigned long long mn[3] = {~0ull, ~0ull, ~0ull}, mx[3] = {0ull, 0ull, 0ull};
+        for (int i = a + lane; i < b; i += 32) {
+            const unsigned long long kx = enc(S.x[i]), ky = enc(S.y[i]), kz = enc(S.z[i]);
+            mn[0] = kx < mn[0] ? kx : mn[0]; mx[0] = kx > mx[0] ? kx : mx[0];
+            mn[1] = ky < mn[1] ? ky : mn[1]; mx[1] = ky > mx[1] ? ky : mx[1];
+            mn[2] = kz < mn[2] ? kz : mn[2]; mx[2] = kz > mx[2] ? kz : mx[2];
+        }
+        warp_minmax(mn, mx);
+        BNode nd;
+        nd.lo = lo + a; nd.hi = lo + b - 1;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { nd.b[k] = mn[k]; nd.b[3 + k] = mx[k]; }
+        if (cell != c0 && lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { nodes[cell].b[k] = mn[k]; nodes[cell].b[3 + k] = mx[k]; }
+        }
+        double split;
+        const int d = decide(nd, nBucket, &split);
+        if (d < 0) { // bucket
+            for (int i = a + lane; i < b; i += 32) cellOf[lo + i] = cell;
+            if (lane == 0) nodes[cell].dim = -1;
+            continue;
+        }
+        const double *cd = d == 0 ? S.x : (d == 1 ? S.y : S.z);
+        // exchange partition (pkdUpperPart): totals first, then every misplaced element's pair index
+        int total = 0;
+        for (int base = a; base < b; base += 32) {
+            const int i = base + lane;
+            total += __popc(__ballot_sync(0xffffffffu, i < b && cd[i] < split));
+        }
+        const int mid = a + total;
+        int before = 0, nMis = 0;
+        for (int base = a; base < b; base += 32) {
+            const int i = base + lane;
+            const bool in = i < b, less = in && cd[i] < split;
+            const unsigned bal = __ballot_sync(0xffffffffu, less);
+            const int lb = before + __popc(bal & lt); // elements < split in [a, i)
+            const bool misL = in && i < mid && !less;
+            if (misL) S.tabL[(i - a) - lb] = (unsigned char)i;
+            if (in && i >= mid && less) S.tabR[total - lb - 1] = (unsigned char)i;
+            nMis += __popc(__ballot_sync(0xffffffffu, misL));
+            before += __popc(bal);
+        }
+        __syncwarp();
+        for (int k = lane; k < nMis; k += 32) {
+            const int p = S.tabL[k], q = S.tabR[k];
+            double t;
+            t = S.x[p]; S.x[p] = S.x[q]; S.x[q] = t;
+            t = S.y[p]; S.y[p] = S.y[q]; S.y[q] = t;
+            t = S.z[p]; S.z[p] = S.z[q]; S.z[q] = t;
+            const unsigned char u = S.idx[p]; S.idx[p] = S.idx[q]; S.idx[q] = u;
+        }
+        int id = 0;
+        if (lane == 0) {
+            id = atomicAdd(&ctr[0], 2);
+            BNode ch;
+            ch.left = ch.right = -1; ch.parent = cell; ch.dim = -1; ch.mid = 0; ch.nMis = 0; ch.split = 0.0;
+            for (int k = 0; k < 3; ++k) { ch.b[k] = ~0ull; ch.b[3 + k] = 0ull; }
+            ch.lo = lo + a; ch.hi = lo + mid - 1;
+            nodes[id] = ch;
+            ch.lo = lo + mid; ch.hi = lo + b - 1;
+            nodes[id + 1] = ch;
+            nodes[cell].left = id; nodes[cell].right = id + 1; nodes[cell].dim = d; nodes[cell].split = split;
+            nodes[cell].mid = lo + mid; nodes[cell].nMis = nMis;
+            S.stack[sp][0] = id + 1; S.stack[sp][1] = mid; S.stack[sp][2] = b;
+            S.stack[sp + 1][0] = id; S.stack[sp + 1][1] = a; S.stack[sp + 1][2] = mid;
+        }
+        sp += 2;
+        __syncwarp();
+    }
+    // the payload follows the permutation: staged through shared memory so that every read of the old order has
+    // completed before the first write of the new one
+    for (int i = lane; i < n; i += 32) {
+        const int src = lo + S.idx[i];
+        S.pm[i] = m[src]; S.ph[i] = h[src]; S.po[i] = iord[src];
+        S.pa[i] = act ? act[src] : 0;
+    }
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+        x[lo + i] = S.x[i]; y[lo + i] = S.y[i]; z[lo + i] = S.z[i];
+        m[lo + i] = S.pm[i]; h[lo + i] = S.ph[i]; iord[lo + i] = S.po[i];
+        if (act) act[lo + i] = S.pa[i];
+    }
 }
 
 // mass, centre of mass, mass-weighted softening and subtree size of every cell, children before parents
@@ -433,7 +568,7 @@ struct Buf {
 };
 
 struct Builder {
-    Buf part, ipart, nodes, cell, scan, tab, cub, ctr, up, num, out, outi;
+    Buf part, ipart, nodes, cell, scan, tab, cub, ctr, up, num, out, outi, ret;
     int *hCtr = nullptr; // pinned
     ~Builder() { if (hCtr) cudaFreeHost(hCtr); }
 };
@@ -461,8 +596,10 @@ int gg_builder_run(void **pBuilder, const gg_particles *pp, int nBucket, double 
     BCK(B.cell.need(sizeof(int) * (size_t)n));
     BCK(B.scan.need(sizeof(int) * 2 * ((size_t)n + 1)));
     BCK(B.tab.need(sizeof(int) * 2 * (size_t)n));
+    BCK(B.ret.need(sizeof(int) * ((size_t)n + 1)));
     BCK(B.ctr.need(sizeof(int) * (8 + GGB_MAX_LEVELS + 4)));
     if (!B.hCtr) BCK(cudaMallocHost((void **)&B.hCtr, sizeof(int) * 4));
+    static_assert(GGB_WCAP <= 256 && GG_MAX_BUCKET <= GGB_WCAP, "k_finish indexes its particles with unsigned char");
     double *x = (double *)B.part.p, *y = x + n, *z = y + n, *m = z + n, *h = m + n;
     int *iord = (int *)B.ipart.p, *act = pp->active ? iord + n : nullptr;
     BNode *nodes = (BNode *)B.nodes.p;
@@ -492,18 +629,29 @@ int gg_builder_run(void **pBuilder, const gg_particles *pp, int nBucket, double 
             return GG_ERR_UNSUPPORTED;
         }
         if (level == 0) { k_bounds<<<gridP, 256, 0, st>>>(n, x, y, z, cellOf, levelStart, level, nodes); ++nl; }
-        k_flag<<<gridP1, 256, 0, st>>>(n, x, y, z, cellOf, levelStart, level, nodes, nBucket, flag, ctr);
+        k_flag<<<gridP1, 256, 0, st>>>(n, x, y, z, cellOf, levelStart, level, nodes, nBucket, flag, ctr, (int *)B.ret.p);
         BCK(cub::DeviceScan::ExclusiveSum(B.cub.p, cubBytes, flag, S, n + 1, st));
         k_split<<<gridP, 256, 0, st>>>(n, x, y, z, cellOf, levelStart, level, nodes, flag, S, tabL, tabR, ctr);
         k_swap<<<gridP, 256, 0, st>>>(n, cellOf, levelStart, level, nodes, tabL, tabR, x, y, z, m, h, act, iord);
         nl += 5;
-        // a level of a balanced tree cannot be the last one before ~log2(n / nBucket); afterwards look every level
-        if ((1ll << (level + 1)) * (long long)nBucket < (long long)n) continue;
-        BCK(cudaMemcpyAsync(B.hCtr, ctr, sizeof(int), cudaMemcpyDeviceToHost, st));
-        BCK(cudaMemcpyAsync(B.hCtr + 1, levelStart + level + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        // while 2^level cells of GGB_WCAP particles cannot hold all n, some cell still splits here; afterwards look every level
+        if ((1ll << (level + 1)) * (long long)GGB_WCAP < (long long)n) continue;
+        BCK(cudaMemcpyAsync(B.hCtr, ctr, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        BCK(cudaMemcpyAsync(B.hCtr + 2, levelStart + level + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
         BCK(cudaStreamSynchronize(st));
         nn = B.hCtr[0];
-        if (B.hCtr[0] == B.hCtr[1]) break; // this level split nothing
+        if (B.hCtr[0] == B.hCtr[2]) break; // this level split nothing
+    }
+    BCK(cudaGetLastError());
+    // ---- the sub-trees of the retired cells, one warp each
+    const int nRet = B.hCtr[1];
+    if (nRet > 0) {
+        k_finish<<<(nRet + GGB_FINISH_WARPS - 1) / GGB_FINISH_WARPS, GGB_FINISH_WARPS * 32, 0, st>>>(
+            nRet, (const int *)B.ret.p, nodes, cellOf, x, y, z, m, h, act, iord, nBucket, ctr);
+        ++nl;
+        BCK(cudaMemcpyAsync(B.hCtr, ctr, sizeof(int), cudaMemcpyDeviceToHost, st));
+        BCK(cudaStreamSynchronize(st));
+        nn = B.hCtr[0];
     }
     BCK(cudaGetLastError());
     // ---- per-cell quantities
