@@ -157,6 +157,26 @@ def ncu_traffic(spec: str):
         return None
 
 
+def bind_to_gpu_cpus(index: int):
+    """Pin this rank to the CPU cores NVML reports as local to its GPU (what an MPI launcher's binding does for the
+    reference): the rank's pinned host buffers are then first-touched on the GPU's NUMA node and its host<->device
+    copies do not cross sockets.  Returns the number of cores in the mask, or None when NVML cannot tell."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -170,6 +190,7 @@ def run_ours(a):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- this path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_cpus(local) if world > 1 else None
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
@@ -383,6 +404,8 @@ def run_ours(a):
                "wall_ms_per_step_resident": wall_res_max / a.steps * 1e3}
         if from_particles is not None:
             out["e2e_from_particles"] = from_particles
+        if numa is not None:
+            out["config"]["cpu_binding"] = f"rank bound to the {numa} cores local to its GPU (NVML affinity)"
         if exchange is not None:
             out["exchange_phases_ms_rank0"] = {k: v * 1e3 for k, v in exchange.driver.timing.items()}
             out["let_bytes_rank0"] = {"sent": exchange.driver.let_bytes[0], "received": exchange.driver.let_bytes[1],
