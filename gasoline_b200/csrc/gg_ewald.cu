@@ -125,8 +125,12 @@ __global__ void __launch_bounds__(128, GG_EWALD_MIN_CTAS) k_ewald(const EwaldKer
                     g[5] = alphan * (r2 / 13 - 1.0 / 11.0);
                 } else { // ewald.c:118-136
                     double r = sqrt(r2), dir = 1.0 / r, dir2 = dir * dir;
-                    double a = exp(-r2 * A.alpha2) * A.ka * dir2;
-                    g[0] = (hole ? -erf(A.alpha * r) : erfc(A.alpha * r)) * dir;
+                    // erfc(x) = exp(-x^2) erfcx(x): the exponential is needed anyway (ewald.c:121), and the scaled function
+                    // is the cheaper one; -erf(x) = erfc(x) - 1 (x > 0.1 here: the series branch took the small radii)
+                    const double ex = exp(-r2 * A.alpha2);
+                    double a = ex * A.ka * dir2;
+                    const double ec = ex * erfcx(A.alpha * r);
+                    g[0] = (hole ? ec - 1.0 : ec) * dir;
                     double alphan = 2 * A.alpha2;
                     g[1] = g[0] * dir2 + a;
                     g[2] = 3 * g[1] * dir2 + alphan * a; alphan *= 2 * A.alpha2;
