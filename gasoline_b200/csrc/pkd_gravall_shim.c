@@ -10,20 +10,26 @@
  * What it does, per call (= per rank per force evaluation):
  *   1. flattens pkd->kdNodes[0..nNodes) and pkd->pStore[0..nLocal) into the SoA views gg_set_local takes (pinned
  *      staging buffers kept between calls, grown by high-water mark; the reference frees and rebuilds kdNodes before
- *      every gravity call, pkd.c:2636-2642, so nothing can be assumed resident);
+ *      every gravity call, pkd.c:2636-2642, so nothing can be assumed resident).  The AoS records are 536 B / 184 B
+ *      wide, so this pass is memory-bound host work: it runs on GG_SHIM_THREADS threads (default min(8, cores)).
+ *      The cells' multipole moments are NOT copied unless GG_SHIM_HOST_MOMENTS=1: the device forms them from the
+ *      particles (gg_tree.mom = NULL; same definition, FP64, forces identical to rounding of the FP32 records);
  *   2. hands over pkd->ilcnRoot (pkdDistribRoot, pkd.c:4472) when Ewald is on;
- *   3. gg_gravity with the reference's in-place semantics: a, fPot += ; dtGrav = max ; fWeight = for ACTIVE
- *      particles only, and returns nActive / dPartSum / dCellSum / dSoftSum / dFlop through the
- *      pointer arguments exactly as pkdGravAll does (pkd.c:2945-2949, grav.c:246-247, ewald.c:175-176).
+ *   3. gg_gravity in overwrite mode into pinned result arrays (the kernels deliver them zero-copy while they run), then
+ *      ONE threaded pass applies the reference's in-place semantics to pStore: a, fPot += ; dtGrav = max ; fWeight =
+ *      for ACTIVE particles only; nActive / dPartSum / dCellSum / dSoftSum / dFlop go back through the
+ *      pointer arguments exactly as pkdGravAll returns them (pkd.c:2945-2949, grav.c:246-247, ewald.c:175-176).
  * Errors follow the host's convention: print and abort (the reference asserts; there is no CPU fallback here).
  *
  * Scope of this file: one MDL rank per process image of the tree (mdlThreads == 1).  Multi-GPU runs hand each rank
  * the other domains' trees through gg_set_top / gg_set_remote (gasoline_b200/domain.py does it over NCCL).
  * bDoSun (pkd.c:3003-3041, solar-system indirect term) is not supported on the GPU path.
  */
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 #include "pkd.h"
 #include "gasoline_b200.h"
 
@@ -38,6 +44,114 @@ typedef struct {
 } SHIM;
 
 static SHIM g_shim[64]; /* one per MDL rank living in this process (pthread-MDL ranks are threads) */
+
+/* ---- a minimal parallel-for over [0, n): the flatten / write-back passes are bandwidth-bound strided copies ---- */
+typedef struct {
+    void (*fn)(void *, size_t, size_t);
+    void *arg;
+    size_t lo, hi;
+} JOB;
+
+static void *job_main(void *p) {
+    JOB *j = (JOB *)p;
+    j->fn(j->arg, j->lo, j->hi);
+    return NULL;
+}
+
+static int shim_threads(void) {
+    static int nT = 0;
+    if (!nT) {
+        const char *e = getenv("GG_SHIM_THREADS");
+        long nc = sysconf(_SC_NPROCESSORS_ONLN);
+        nT = e ? atoi(e) : (int)(nc < 8 ? nc : 8);
+        if (nT < 1) nT = 1;
+        if (nT > 64) nT = 64;
+    }
+    return nT;
+}
+
+static void parallel_for(size_t n, void (*fn)(void *, size_t, size_t), void *arg) {
+    int nT = shim_threads(), t, started = 0;
+    pthread_t th[64];
+    JOB job[64];
+    size_t chunk;
+    if (n < 65536) nT = 1;
+    chunk = (n + nT - 1) / nT;
+    for (t = 1; t < nT; ++t) {
+        job[t].fn = fn; job[t].arg = arg;
+        job[t].lo = (size_t)t * chunk; job[t].hi = job[t].lo + chunk < n ? job[t].lo + chunk : n;
+        if (job[t].lo >= job[t].hi) break;
+        if (pthread_create(&th[t], NULL, job_main, &job[t]) != 0) { /* run it here instead */
+            fn(arg, job[t].lo, job[t].hi);
+            th[t] = 0;
+        }
+        started = t;
+    }
+    fn(arg, 0, chunk < n ? chunk : n);
+    for (t = 1; t <= started; ++t)
+        if (th[t]) pthread_join(th[t], NULL);
+}
+
+typedef struct {
+    PKD pkd;
+    SHIM *s;
+    int bMom;
+} PASS;
+
+static void flatten_nodes(void *arg, size_t lo, size_t hi) {
+    PASS *a = (PASS *)arg;
+    SHIM *s = a->s;
+    size_t i;
+    int j;
+    for (i = lo; i < hi; ++i) {
+        const KDN *c = &a->pkd->kdNodes[i];
+        for (j = 0; j < 3; ++j) {
+            s->bnd[6 * i + j] = c->bnd.fMin[j];
+            s->bnd[6 * i + 3 + j] = c->bnd.fMax[j];
+            s->r[3 * i + j] = c->r[j];
+        }
+        s->fMass[i] = c->fMass; s->fSoft[i] = c->fSoft; s->fOpen2[i] = c->fOpen2;
+        s->pLower[i] = c->pLower; s->pUpper[i] = c->pUpper; s->iLower[i] = c->iLower; s->iUpper[i] = c->iUpper;
+        if (a->bMom) {
+            const struct pkdCalcCellStruct *q = &c->mom;
+            double *mo = &s->mom[(size_t)GG_NMOM * i];
+            mo[0] = q->Qxx; mo[1] = q->Qyy; mo[2] = q->Qzz; mo[3] = q->Qxy; mo[4] = q->Qxz; mo[5] = q->Qyz;
+            mo[6] = q->Oxxx; mo[7] = q->Oxyy; mo[8] = q->Oxxy; mo[9] = q->Oyyy; mo[10] = q->Oxxz; mo[11] = q->Oyyz;
+            mo[12] = q->Oxyz; mo[13] = q->Oxzz; mo[14] = q->Oyzz; mo[15] = q->Ozzz;
+            mo[16] = q->Hxxxx; mo[17] = q->Hxyyy; mo[18] = q->Hxxxy; mo[19] = q->Hyyyy; mo[20] = q->Hxxxz;
+            mo[21] = q->Hyyyz; mo[22] = q->Hxxyy; mo[23] = q->Hxxyz; mo[24] = q->Hxyyz; mo[25] = q->Hxxzz;
+            mo[26] = q->Hxyzz; mo[27] = q->Hxzzz; mo[28] = q->Hyyzz; mo[29] = q->Hyzzz; mo[30] = q->Hzzzz;
+        }
+    }
+}
+
+static void flatten_particles(void *arg, size_t lo, size_t hi) {
+    PASS *a = (PASS *)arg;
+    SHIM *s = a->s;
+    size_t i;
+    for (i = lo; i < hi; ++i) {
+        const PARTICLE *p = &a->pkd->pStore[i];
+        s->x[i] = p->r[0]; s->y[i] = p->r[1]; s->z[i] = p->r[2];
+        s->m[i] = p->fMass; s->h[i] = p->fSoft;
+        s->active[i] = TYPEQueryACTIVE(p) ? 1 : 0;
+    }
+}
+
+/* a, fPot += ; dtGrav = max ; fWeight = : what pkdBucketInteract / pkdBucketEwald / pkdBucketWeight leave in pStore
+ * (grav.c:100,192-195, ewald.c:166-170, pkd.c:2851-2861), ACTIVE particles only */
+static void write_back(void *arg, size_t lo, size_t hi) {
+    PASS *a = (PASS *)arg;
+    SHIM *s = a->s;
+    size_t i;
+    for (i = lo; i < hi; ++i) {
+        PARTICLE *p = &a->pkd->pStore[i];
+        if (!s->active[i]) continue;
+        p->a[0] += s->a[3 * i]; p->a[1] += s->a[3 * i + 1]; p->a[2] += s->a[3 * i + 2];
+        p->fPot += s->pot[i];
+        if (s->dt[i] > p->dtGrav) p->dtGrav = s->dt[i];
+        p->fWeight = s->w[i];
+    }
+}
 
 static void die(const char *what) {
     fprintf(stderr, "pkdGravAll (gasoline_b200): %s failed: %s\n", what, gg_last_error());
@@ -84,7 +198,8 @@ void pkdGravAll(PKD pkd, int nReps, int bPeriodic, int iOrder, int bEwald, int i
     gg_particles pp;
     gg_params prm;
     gg_stats st;
-    int i, j;
+    PASS pass;
+    int j;
 
     (void)dSunSoft;
     mdlassert(pkd->mdl, !bDoSun); /* not supported on the GPU path */
@@ -100,34 +215,13 @@ void pkdGravAll(PKD pkd, int nReps, int bPeriodic, int iOrder, int bEwald, int i
     pkdClearTimer(pkd, 3);
     pkdStartTimer(pkd, 2);
 
-    for (i = 0; i < nNodes; ++i) {
-        const KDN *c = &pkd->kdNodes[i];
-        const struct pkdCalcCellStruct *q = &c->mom;
-        double *mo = &s->mom[(size_t)GG_NMOM * i];
-        for (j = 0; j < 3; ++j) {
-            s->bnd[6 * (size_t)i + j] = c->bnd.fMin[j];
-            s->bnd[6 * (size_t)i + 3 + j] = c->bnd.fMax[j];
-            s->r[3 * (size_t)i + j] = c->r[j];
-        }
-        s->fMass[i] = c->fMass; s->fSoft[i] = c->fSoft; s->fOpen2[i] = c->fOpen2;
-        s->pLower[i] = c->pLower; s->pUpper[i] = c->pUpper; s->iLower[i] = c->iLower; s->iUpper[i] = c->iUpper;
-        mo[0] = q->Qxx; mo[1] = q->Qyy; mo[2] = q->Qzz; mo[3] = q->Qxy; mo[4] = q->Qxz; mo[5] = q->Qyz;
-        mo[6] = q->Oxxx; mo[7] = q->Oxyy; mo[8] = q->Oxxy; mo[9] = q->Oyyy; mo[10] = q->Oxxz; mo[11] = q->Oyyz;
-        mo[12] = q->Oxyz; mo[13] = q->Oxzz; mo[14] = q->Oyzz; mo[15] = q->Ozzz;
-        mo[16] = q->Hxxxx; mo[17] = q->Hxyyy; mo[18] = q->Hxxxy; mo[19] = q->Hyyyy; mo[20] = q->Hxxxz;
-        mo[21] = q->Hyyyz; mo[22] = q->Hxxyy; mo[23] = q->Hxxyz; mo[24] = q->Hxyyz; mo[25] = q->Hxxzz;
-        mo[26] = q->Hxyzz; mo[27] = q->Hxzzz; mo[28] = q->Hyyzz; mo[29] = q->Hyzzz; mo[30] = q->Hzzzz;
-    }
-    for (i = 0; i < n; ++i) {
-        const PARTICLE *p = &pkd->pStore[i];
-        s->x[i] = p->r[0]; s->y[i] = p->r[1]; s->z[i] = p->r[2];
-        s->m[i] = p->fMass; s->h[i] = p->fSoft;
-        s->active[i] = TYPEQueryACTIVE(p) ? 1 : 0;
-        s->a[3 * (size_t)i] = p->a[0]; s->a[3 * (size_t)i + 1] = p->a[1]; s->a[3 * (size_t)i + 2] = p->a[2];
-        s->pot[i] = p->fPot; s->dt[i] = p->dtGrav; s->w[i] = p->fWeight;
-    }
+    pass.pkd = pkd; pass.s = s;
+    pass.bMom = getenv("GG_SHIM_HOST_MOMENTS") != NULL && atoi(getenv("GG_SHIM_HOST_MOMENTS")) != 0;
+    parallel_for((size_t)nNodes, flatten_nodes, &pass);
+    parallel_for((size_t)n, flatten_particles, &pass);
     t.nNodes = nNodes; t.iRoot = pkd->iRoot;
-    t.bnd = s->bnd; t.r = s->r; t.fMass = s->fMass; t.fSoft = s->fSoft; t.fOpen2 = s->fOpen2; t.mom = s->mom;
+    t.bnd = s->bnd; t.r = s->r; t.fMass = s->fMass; t.fSoft = s->fSoft; t.fOpen2 = s->fOpen2;
+    t.mom = pass.bMom ? s->mom : NULL;
     t.pLower = s->pLower; t.pUpper = s->pUpper; t.iLower = s->iLower; t.iUpper = s->iUpper;
     pp.n = n; pp.x = s->x; pp.y = s->y; pp.z = s->z; pp.fMass = s->m; pp.fSoft = s->h; pp.active = s->active;
     if (gg_set_local(s->ctx, pkd->idSelf, &t, &pp) != GG_OK) die("gg_set_local");
@@ -147,14 +241,9 @@ void pkdGravAll(PKD pkd, int nReps, int bPeriodic, int iOrder, int bEwald, int i
     prm.nReps = nReps; prm.bPeriodic = bPeriodic; prm.iOrder = iOrder; prm.bEwald = bEwald; prm.iEwOrder = iEwOrder;
     prm.fEwCut = fEwCut; prm.fEwhCut = fEwhCut; prm.bComove = bComove; prm.dRhoFac = dRhoFac;
     for (j = 0; j < 3; ++j) prm.fPeriod[j] = pkd->fPeriod[j];
-    prm.accumulate = 1;
+    prm.accumulate = 0; /* this call's contribution, delivered zero-copy into the pinned arrays; merged below */
     if (gg_gravity(s->ctx, &prm, s->a, s->pot, s->dt, s->w, &st) != GG_OK) die("gg_gravity");
-    for (i = 0; i < n; ++i) {
-        PARTICLE *p = &pkd->pStore[i];
-        if (!s->active[i]) continue;
-        p->a[0] = s->a[3 * (size_t)i]; p->a[1] = s->a[3 * (size_t)i + 1]; p->a[2] = s->a[3 * (size_t)i + 2];
-        p->fPot = s->pot[i]; p->dtGrav = s->dt[i]; p->fWeight = s->w[i];
-    }
+    parallel_for((size_t)n, write_back, &pass);
     pkdStopTimer(pkd, 2);
     *nActive = st.nActive;
     *pdPartSum = st.dPartSum; *pdCellSum = st.dCellSum; *pdSoftSum = st.dSoftSum; *pdFlop = st.dFlop;
