@@ -71,7 +71,7 @@ struct gg_context {
     std::vector<int> hActive; // host copy of the local ACTIVE flags (empty = all active)
     // device buffers
     DevBuf nodes, momf, momq, parts, active, hsoft, tasks, ngroups, goffs, counts, acc, pot, dtg, fweight, nloop, sums,
-        misc, imgoff, ewt, raw, rawi, cubtmp, flush, pool, nextblk, poolmask, isb, boffs, bnode, ghead, gcnt, bcnt, btot, boff64, lists, letflag, letfront, letidx, letout, letmisc, momraw, mparent, dbgtask;
+        misc, imgoff, ewt, raw, rawi, cubtmp, flush, pool, nextblk, poolmask, isb, boffs, bnode, ghead, gcnt, bcnt, btot, boff64, lists, letflag, letfront, letidx, letout, letmisc, momraw, mparent, dbgtask, momout;
     void *pinned = nullptr;
     size_t pinnedCap = 0;
     int nTasks = 0;
@@ -588,7 +588,7 @@ void gg_destroy(gg_context *c) {
                      &c->imgoff, &c->ewt, &c->raw, &c->rawi, &c->cubtmp, &c->flush, &c->pool,
                      &c->nextblk, &c->poolmask, &c->isb, &c->boffs, &c->bnode, &c->ghead, &c->gcnt, &c->bcnt, &c->btot,
                      &c->boff64, &c->lists, &c->letflag, &c->letfront, &c->letidx, &c->letout, &c->letmisc, &c->momraw,
-                     &c->mparent, &c->dbgtask, &c->sx, &c->sy, &c->sz, &c->sm, &c->sh, &c->sact, &c->svel, &c->sid, &c->sdt,
+                     &c->mparent, &c->dbgtask, &c->momout, &c->sx, &c->sy, &c->sz, &c->sm, &c->sh, &c->sact, &c->svel, &c->sid, &c->sdt,
                      &c->svel2, &c->sid2, &c->sdt2, &c->sacc};
     for (DevBuf *b : all)
         if (b->p) cudaFree(b->p);
@@ -957,16 +957,26 @@ int gg_tree_fetch(gg_context *c, double *bnd, double *r, double *fMass, double *
     for (auto &e : cp)
         if (e.dst && e.src) CK(cudaMemcpyAsync(e.dst, e.src, e.bytes, cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
-    if (mom) { // the reduced multipoles the device formed: reduce the raw records on the host (gg_m2m.h)
-        std::vector<double> raw(nn * 32);
-        CK(cudaMemcpy(raw.data(), c->momraw.p, sizeof(double) * 32 * nn, cudaMemcpyDeviceToHost));
-        for (size_t g = 0; g < nn; ++g) {
-            GGRawMom a;
-            a.M = raw[g * 32];
-            for (int k = 0; k < 31; ++k) a.q[k] = raw[g * 32 + 1 + k];
-            gg_raw_reduce(a, mom + g * GG_NMOM);
-        }
+    if (mom) { // the reduced multipoles the device formed: raw records reduced by a kernel, then one copy
+        int rc2;
+        if ((rc2 = ensure(c, c->momout, sizeof(double) * GG_NMOM * nn))) return rc2;
+        CK(gg_launch_mom_reduce((int)nn, (const double *)c->momraw.p, (double *)c->momout.p, c->st));
+        ++c->nLaunches;
+        CK(cudaMemcpyAsync(mom, c->momout.p, sizeof(double) * GG_NMOM * nn, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
     }
+    return GG_OK;
+}
+
+int gg_tree_fetch_build(gg_context *c, int *iDim, double *fSplit, double *fBmax) {
+    if (!c || !c->built.nNodes) return fail(GG_ERR_ARG, "gg_tree_fetch_build: no device-built tree (gg_build_local)");
+    CK(cudaSetDevice(c->device));
+    const GGBuiltDev &b = c->built;
+    const size_t nn = (size_t)b.nNodes;
+    if (iDim) CK(cudaMemcpyAsync(iDim, b.iDim, 4 * nn, cudaMemcpyDeviceToHost, c->st));
+    if (fSplit) CK(cudaMemcpyAsync(fSplit, b.fSplit, 8 * nn, cudaMemcpyDeviceToHost, c->st));
+    if (fBmax) CK(cudaMemcpyAsync(fBmax, b.fBmax, 8 * nn, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
     return GG_OK;
 }
 

@@ -172,6 +172,8 @@ struct GGBuiltDev {
     int nNodes, nPart, nLevels;
     const double *bnd, *r, *fMass, *fSoft, *fOpen2;
     const int *pLower, *pUpper, *iLower, *iUpper;
+    const int *iDim;                // split axis, -1 for a bucket (KDN.iDim)
+    const double *fSplit, *fBmax;   // split coordinate (KDN.fSplit), Bmax (pkdCalcCellStruct.Bmax)
     const double *x, *y, *z, *m, *h;
     const int *active; // null: all active
     const int *iorder;
@@ -190,3 +192,4 @@ cudaError_t gg_launch_permute(int n, const int *iorder, const double *vIn, doubl
                               const double *dtIn, double *dtOut, cudaStream_t st);
 cudaError_t gg_launch_state_init(int n, int *id, double *dt, double dt0, cudaStream_t st);
 cudaError_t gg_launch_bmax_about(int n, const PartS *parts, const double c[3], unsigned long long *out, cudaStream_t st);
+cudaError_t gg_launch_mom_reduce(int nn, const double *raw, double *mom, cudaStream_t st);

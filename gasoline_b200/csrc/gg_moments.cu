@@ -92,7 +92,25 @@ __global__ void __launch_bounds__(128) k_mom_up(int nn, const NodeW *nodes, int 
     }
 }
 
+// raw records -> the reference's reduced multipoles in FP64 (pkdCalcCell's definition), [nn][GG_NMOM]: for hosts that
+// want kdNodes[].mom back (gg_tree_fetch)
+__global__ void __launch_bounds__(128) k_mom_reduce(int nn, const double *raw, double *mom) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nn) return;
+    GGRawMom r;
+    load_raw(raw + (size_t)i * 32, r);
+    double q[31];
+    gg_raw_reduce(r, q);
+#pragma unroll
+    for (int k = 0; k < 31; ++k) mom[(size_t)i * GG_NMOM + k] = q[k];
+}
+
 } // namespace
+
+cudaError_t gg_launch_mom_reduce(int nn, const double *raw, double *mom, cudaStream_t st) {
+    if (nn > 0) k_mom_reduce<<<(nn + 127) / 128, 128, 0, st>>>(nn, raw, mom);
+    return cudaGetLastError();
+}
 
 cudaError_t gg_launch_device_moments(int nn, const NodeW *nodes, int nodeBase, int partBase, int iRootLocal,
                                      const double *x, const double *y, const double *z, const double *m, int *parent,

@@ -530,7 +530,7 @@ __global__ void __launch_bounds__(256) k_emit(int nn, const BNode *nodes, const 
                                               const double *csoft, const double *ccom, const unsigned long long *bmaxBits,
                                               double c23, double dTheta, double *bnd, double *r, double *fMass,
                                               double *fSoft, double *fOpen2, int *pLower, int *pUpper, int *iLower,
-                                              int *iUpper) {
+                                              int *iUpper, int *iDim, double *fSplit, double *fBmax) {
     const int t = blockIdx.x * 256 + threadIdx.x;
     if (t >= nn) return;
     const BNode nd = nodes[t];
@@ -549,6 +549,9 @@ __global__ void __launch_bounds__(256) k_emit(int nn, const BNode *nodes, const 
     pUpper[g] = nd.hi;
     iLower[g] = nd.left >= 0 ? pre[nd.left] : -1;
     iUpper[g] = nextB[t] >= 0 ? pre[nextB[t]] : -1;
+    iDim[g] = nd.left >= 0 ? nd.dim : -1; // KDN.iDim / fSplit (pkd.h:454-456): -1 / 0 for a bucket
+    fSplit[g] = nd.left >= 0 ? nd.split : 0.0;
+    fBmax[g] = bmax;
 }
 
 struct Buf {
@@ -661,22 +664,24 @@ int gg_builder_run(void **pBuilder, const gg_particles *pp, int nBucket, double 
     int *csize = (int *)(bmaxBits + nn), *arrive = csize + nn;
     BCK(B.num.need(sizeof(int) * 2 * (size_t)nn));
     int *pre = (int *)B.num.p, *nextB = pre + nn;
-    BCK(B.out.need(sizeof(double) * 13 * (size_t)nn));
-    BCK(B.outi.need(sizeof(int) * 4 * (size_t)nn));
+    BCK(B.out.need(sizeof(double) * 15 * (size_t)nn));
+    BCK(B.outi.need(sizeof(int) * 5 * (size_t)nn));
     double *obnd = (double *)B.out.p, *orr = obnd + 6 * (size_t)nn, *oM = orr + 3 * (size_t)nn, *oS = oM + nn, *oO = oS + nn;
-    int *oPL = (int *)B.outi.p, *oPU = oPL + nn, *oIL = oPU + nn, *oIU = oIL + nn;
+    int *oPL = (int *)B.outi.p, *oPU = oPL + nn, *oIL = oPU + nn, *oIU = oIL + nn, *oDim = oIU + nn;
+    double *oSplit = oO + nn, *oBmax = oSplit + nn;
     BCK(cudaMemsetAsync(bmaxBits, 0, sizeof(unsigned long long) * nn + sizeof(int) * 2 * (size_t)nn, st));
     const int gridN = (nn + 255) / 256;
     k_up<<<(nn + 127) / 128, 128, 0, st>>>(nn, nodes, x, y, z, m, h, cmass, csoft, ccom, csize, arrive);
     k_number<<<gridN, 256, 0, st>>>(nn, nodes, csize, pre, nextB);
     k_bmax<<<gridP, 256, 0, st>>>(n, cellOf, nodes, x, y, z, ccom, bmaxBits);
     k_emit<<<gridN, 256, 0, st>>>(nn, nodes, pre, nextB, cmass, csoft, ccom, bmaxBits, 2.0 / sqrt(3.0), dTheta, obnd, orr, oM,
-                                  oS, oO, oPL, oPU, oIL, oIU);
+                                  oS, oO, oPL, oPU, oIL, oIU, oDim, oSplit, oBmax);
     nl += 4;
     BCK(cudaGetLastError());
     out->nNodes = nn; out->nPart = n; out->nLevels = level + 1;
     out->bnd = obnd; out->r = orr; out->fMass = oM; out->fSoft = oS; out->fOpen2 = oO;
     out->pLower = oPL; out->pUpper = oPU; out->iLower = oIL; out->iUpper = oIU;
+    out->iDim = oDim; out->fSplit = oSplit; out->fBmax = oBmax;
     out->x = x; out->y = y; out->z = z; out->m = m; out->h = h; out->active = act; out->iorder = iord;
     if (pnLaunches) *pnLaunches = nl;
     return GG_OK;

@@ -222,6 +222,10 @@ void gg_tree_free(gg_built_tree *bt);
  */
 int gg_build_local(gg_context *ctx, int idSelf, const gg_particles *part, int nBucket, double dTheta, int *iOrder,
                    int *pnNodes, double root[GG_NROOT]);
+/* The construction by-products a host needs to fill the rest of its KDN records (pkd.h:454-469): split axis (-1 for a
+ * bucket), split coordinate, and Bmax of pkdCalcCellStruct, per cell in the numbering of gg_tree_fetch. */
+int gg_tree_fetch_build(gg_context *ctx, int *iDim, double *fSplit, double *fBmax);
+
 /*
  * Multi-rank hosts with device-built trees: the root cell of this rank's tree (what pstColCells gathers into kdTop,
  * pkd.c:4349, and pkdCalcRoot's expansion, pkd.c:4395) and this rank's pkdCalcCell sums about the centre of an interior

@@ -59,3 +59,46 @@ def test_reference_host_dropin_full_size_timing(gpu_lib):
     assert out["nActive"] == p.n and inter == 618322384.0
     f = p.m[0] * out["acc"]
     assert np.linalg.norm(f.sum(axis=0)) <= 2e-3 * np.linalg.norm(f, axis=1).sum()
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_reference_host_dropin_device_tree(name, gpu_lib, monkeypatch):
+    """GG_SHIM_DEVICE_TREE=1: the reference host's pkdBuildBinary is ALSO served by the GPU (gg_build_local; pStore
+    permuted and kdNodes filled by the shim).  The reference's own code then exports the tree it sees: every field the
+    gravity path reads must equal the PURE reference's tree bit for bit (moments to FP64 rounding), and pstGravity on it
+    must return the reference's sums."""
+    monkeypatch.setenv("GG_SHIM_DEVICE_TREE", "1")
+    p, active, theta, kw, z = load(name)
+    order = kw.get("iOrder", 4)
+    r = reflib.RefGravity(p, active=active, gpu_host=True)
+    r.build_tree(8, theta, 4)
+    t = r.tree()
+    assert t["nNodes"] == int(z["nNodes"]) and t["iRoot"] == int(z["iRoot"])
+    for k in ("bnd", "r", "fMass", "fSoft", "fOpen2", "pLower", "pUpper", "iLower", "iUpper"):
+        assert np.array_equal(t[k], z["tree_" + k]), f"{name}: kdNodes field {k} differs from the reference's tree"
+    assert np.array_equal(t["iOrder"], z["tree_iOrder"])
+    scale = np.abs(z["tree_mom"]).max(axis=0) + 1e-300
+    assert np.max(np.abs(t["mom"] - z["tree_mom"]) / scale) < 1e-9
+    assert np.allclose(t["root"], z["tree_root"], rtol=1e-9, atol=1e-12 * np.abs(z["tree_root"]).max())
+    out = r.gravity(kw["nReps"], kw["bPeriodic"], order, kw["bEwald"], order)
+    r.close()
+    assert (out["nActive"], out["dPartSum"], out["dCellSum"], out["dSoftSum"], out["dFlop"]) == tuple(z["sums"])
+    act = np.ones(p.n, bool) if active is None else t["active"].astype(bool)
+    d = np.linalg.norm(out["acc"] - z["acc"], axis=1)[act] / np.linalg.norm(z["acc"], axis=1)[act]
+    assert float(np.sqrt(np.mean(d * d))) <= RMS_TOL and float(d.max()) <= MAX_TOL
+    assert np.array_equal(out["fWeight"][act], z["fWeight"][act])
+
+
+def test_reference_host_dropin_device_tree_full_size_timing(gpu_lib, monkeypatch):
+    """The reference host's whole force step (pstBuildTree + pstGravity) at 1 M particles with both entry points on the GPU."""
+    monkeypatch.setenv("GG_SHIM_DEVICE_TREE", "1")
+    p = ics.plummer(1_000_000)
+    r = reflib.RefGravity(p, gpu_host=True)
+    tb = min(r.build_tree(8, 0.7, 4) for _ in range(3))
+    out = r.gravity(0, 0, 4, 0, 4)
+    out = r.gravity(0, 0, 4, 0, 4)
+    r.close()
+    inter = out["dPartSum"] + out["dCellSum"] + out["dSoftSum"]
+    print(f"reference host, 1 M Plummer, GG_SHIM_DEVICE_TREE=1: msrBuildTree sequence {tb * 1e3:.1f} ms (pkdBuildBinary on "
+          f"the GPU + pStore permutation + kdNodes fill + the host's pstColCells/pstCalcRoot), pstGravity {out['seconds'] * 1e3:.1f} ms")
+    assert inter == 618322384.0 and out["nActive"] == p.n
