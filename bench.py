@@ -394,7 +394,9 @@ def run_ours(a):
                                       "k_eval": eval_ms, "k_ewald": ms_ewald_max / a.steps,
                                       "other (task list, memsets, k_stats)": ms_step - tree_ms - ms_ewald_max / a.steps}}
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-               "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "ms_per_step": ms_step, "higher_is_better": True,
+               "scaling": "strong" if a.workload else "weak",  # default: 1 M particles per GPU; --workload fixes the total
+               "vs_baseline": None,
                "dtype": "f32 (FP64 opening tests, FP64 accumulation across lanes, FP64 Ewald)", "data": "synthetic",
                "config": config_of(spec, world), "clocks": clocks,
                "e2e": {"value": inter_all / (e2e_max / a.steps), "unit": UNIT, "h2d_bytes_per_step": int(h2d_all),
