@@ -866,6 +866,42 @@ int gg_state_fetch(gg_context *c, double *x, double *y, double *z, double *vx, d
     return GG_OK;
 }
 
+// New ACTIVE flags for the domain that is already loaded (same tree, same particles): what msrActiveRung changes between
+// two force evaluations on one tree (master.c:8403-8420).  Only the flags travel; the sink-bucket task list is rebuilt.
+int gg_set_active(gg_context *c, const int *active) {
+    if (!c || c->dom.empty()) return fail(GG_ERR_ARG, "gg_set_active: no local domain (gg_set_local / gg_build_local)");
+    CK(cudaSetDevice(c->device));
+    const Domain &L = c->dom[0];
+    const int np = L.nPart, nn = L.nNodes;
+    int rc;
+    const int *dActive = nullptr;
+    if (active) {
+        if ((rc = ensure(c, c->active, (size_t)(np + 1) * sizeof(int)))) return rc;
+        CK(cudaMemcpyAsync(c->active.p, active, sizeof(int) * np, cudaMemcpyDefault, c->st));
+        dActive = (const int *)c->active.p;
+        c->hActive.resize((size_t)np);
+        CK(cudaMemcpyAsync(c->hActive.data(), c->active.p, sizeof(int) * np, cudaMemcpyDeviceToHost, c->st));
+    } else c->hActive.clear();
+    int hCounts[2] = {0, 0};
+    c->nPartUpload = np;
+    if ((rc = build_task_list(c, nn, dActive, hCounts))) return rc;
+    CK(cudaStreamSynchronize(c->st));
+    c->nTasksLocal = hCounts[0];
+    c->nBucketsLocal = hCounts[1];
+    if (c->stateN > 0 && c->stateHasActive != (active != nullptr)) {
+        // the resident store keeps its own copy of the flags (kick / grav-step read them)
+        if (active) {
+            if ((rc = ensure(c, c->sact, sizeof(int) * (size_t)np))) return rc;
+        }
+        c->stateHasActive = active != nullptr;
+    }
+    if (c->stateN > 0 && active) {
+        CK(cudaMemcpyAsync(c->sact.p, c->active.p, sizeof(int) * np, cudaMemcpyDeviceToDevice, c->st));
+        CK(cudaStreamSynchronize(c->st));
+    }
+    return GG_OK;
+}
+
 // The root cell of the local (device-built) domain: what a multi-rank host hands to pstColCells / pstCalcRoot.
 int gg_domain_summary(gg_context *c, double bnd[6], double r[3], double *fMass, double *fSoft, double *fOpen2,
                       double mom[GG_NMOM], double root[GG_NROOT]) {

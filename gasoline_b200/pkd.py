@@ -93,6 +93,7 @@ def load_library(path: str | None = None):
     L.gg_cell_moments.argtypes = [C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_int, _dp, _dp]
     L.gg_tree_moments_m2m.argtypes = [C.POINTER(gg_tree), C.POINTER(gg_particles), _dp]
     L.gg_build_local.argtypes = [C.c_void_p, C.c_int, C.POINTER(gg_particles), C.c_int, C.c_double, _ip, _ip, _dp]
+    L.gg_set_active.argtypes = [C.c_void_p, _ip]
     L.gg_build_info.argtypes = [C.c_void_p, _ip, _ip, _dp]
     L.gg_domain_summary.argtypes = [C.c_void_p] + [_dp] * 7
     L.gg_domain_moments_about.argtypes = [C.c_void_p, _dp, _dp, _dp]
@@ -283,6 +284,15 @@ class PKD:
         nn, nl, ms = C.c_int(), C.c_int(), C.c_double()
         _check(self._L.gg_build_info(self._ctx, C.byref(nn), C.byref(nl), C.byref(ms)), "gg_build_info")
         return nn.value, nl.value, ms.value
+
+    def pkdSetActive(self, active):
+        """New ACTIVE flags (tree order; None = all) for the loaded domain, without re-uploading tree or particles
+        (gg_set_active) -- msrActiveRung between two force evaluations on one tree."""
+        if not getattr(self, "_uploaded", False):
+            raise GasolineB200Error("pkdSetActive: no domain loaded")
+        a = None if active is None else np.ascontiguousarray(active, dtype=np.int32)
+        _check(self._L.gg_set_active(self._ctx, _i(a) if a is not None else None), "gg_set_active")
+        self.active = a
 
     def pkdDomainSummary(self):
         """The root cell of the device-built local tree (gg_domain_summary): dict bnd, r, fMass, fSoft, fOpen2, mom,

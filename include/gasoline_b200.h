@@ -121,6 +121,13 @@ void gg_destroy(gg_context *ctx);
 int gg_set_local(gg_context *ctx, int idSelf, const gg_tree *tree, const gg_particles *part);
 
 /*
+ * New ACTIVE flags (tree order, host or device pointer; NULL = all active) for the domain that is already loaded -- what
+ * msrActiveRung changes between two force evaluations on the same tree (master.c:8403-8420).  Only the flags are
+ * transferred and the sink-bucket task list rebuilt; a resident store (gg_state_*) takes the flags over as well.
+ */
+int gg_set_active(gg_context *ctx, const int *active);
+
+/*
  * Multi-rank runs only.  The gathered top tree pkd->kdTop[1..nCell) (heap indexed, ROOT=1, pkd.h:77-86, filled by
  * pkdDistribCells pkd.c:4376): for each heap cell its pLower (-1 interior, else the rank owning the leaf), the
  * used flag (pUpper != 0), r, fMass, fSoft, fOpen2 and mom.  With one rank this call is not needed.

@@ -52,3 +52,35 @@ def test_zero_copy_leaves_inactive_untouched(gpu_lib):
         assert np.array_equal(u[act], staged[nm][act]), nm
         assert np.all(u[~act] == -7.0), nm
     pkd.close()
+
+
+def test_set_active_equals_fresh_upload(gpu_lib):
+    """gg_set_active: new ACTIVE flags on the loaded domain give exactly what a fresh gg_set_local with those flags gives
+    (sinks = active only, sources = all; inactive particles untouched), and NULL restores the all-active evaluation."""
+    from gasoline_b200 import ics
+    from gasoline_b200.pkd import PKD, GravityParams
+    p = ics.plummer(12000, seed=17)
+    g = GravityParams(nReps=0, bPeriodic=0, bEwald=0)
+    a = PKD()
+    a.pkdLoadParticles(p.x, p.y, p.z, p.m, p.h)
+    a.pkdBuildBinary(8, 0.7, 4)
+    full = a.pkdGravAll(g)
+    rng = np.random.default_rng(4)
+    act = (rng.random(p.n) < 0.25).astype(np.int32)  # tree order
+    a.pkdSetActive(act)
+    part = a.pkdGravAll(g)
+    counts = a.pkdBucketCounts()
+    b = PKD()
+    b.pkdSetTree(a.tree, a.x, a.y, a.z, a.fMass, a.fSoft, active=act)
+    ref = b.pkdGravAll(g)
+    assert np.array_equal(counts, b.pkdBucketCounts())
+    for k in ("nActive", "dPartSum", "dCellSum", "dSoftSum", "dFlop"):
+        assert part[k] == ref[k]
+    for k in ("acc", "pot", "dtGrav", "fWeight"):
+        assert np.array_equal(part[k], ref[k])
+    m = act.astype(bool)
+    assert np.all(part["acc"][~m] == 0)  # (active sinks see lists built for the ACTIVE bounding boxes: not `full`'s)
+    a.pkdSetActive(None)
+    again = a.pkdGravAll(g)
+    assert np.array_equal(again["acc"], full["acc"]) and again["nActive"] == p.n
+    a.close(); b.close()
