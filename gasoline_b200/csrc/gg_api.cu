@@ -84,7 +84,7 @@ struct gg_context {
     double msBuild = 0.0;
     // device-resident particle store (gg_state_*): positions / mass / softening / ACTIVE in tree order after every
     // gg_state_build, velocities SoA [3][n], persistent particle id, time step
-    DevBuf sx, sy, sz, sm, sh, sact, svel, sid, sdt, svel2, sid2, sdt2, sacc;
+    DevBuf sx, sy, sz, sm, sh, sact, svel, sid, sdt, svel2, sid2, sdt2, sacc, srhist;
     int stateN = 0;
     bool stateHasActive = false, stateDirty = true, stateForces = false;
 };
@@ -589,7 +589,7 @@ void gg_destroy(gg_context *c) {
                      &c->nextblk, &c->poolmask, &c->isb, &c->boffs, &c->bnode, &c->ghead, &c->gcnt, &c->bcnt, &c->btot,
                      &c->boff64, &c->lists, &c->letflag, &c->letfront, &c->letidx, &c->letout, &c->letmisc, &c->momraw,
                      &c->mparent, &c->dbgtask, &c->momout, &c->sx, &c->sy, &c->sz, &c->sm, &c->sh, &c->sact, &c->svel, &c->sid, &c->sdt,
-                     &c->svel2, &c->sid2, &c->sdt2, &c->sacc};
+                     &c->svel2, &c->sid2, &c->sdt2, &c->sacc, &c->srhist};
     for (DevBuf *b : all)
         if (b->p) cudaFree(b->p);
     if (c->pinned) cudaFreeHost(c->pinned);
@@ -732,7 +732,8 @@ int gg_state_load(gg_context *c, int n, const double *x, const double *y, const 
     for (DevBuf *b : d8)
         if ((rc = ensure(c, *b, nb))) return rc;
     if ((rc = ensure(c, c->svel, 3 * nb)) || (rc = ensure(c, c->svel2, 3 * nb))) return rc;
-    if ((rc = ensure(c, c->sid, sizeof(int) * (size_t)n)) || (rc = ensure(c, c->sid2, sizeof(int) * (size_t)n)) ||
+    // sid: (persistent id, rung) pairs
+    if ((rc = ensure(c, c->sid, sizeof(int) * 2 * (size_t)n)) || (rc = ensure(c, c->sid2, sizeof(int) * 2 * (size_t)n)) ||
         (rc = ensure(c, c->sact, sizeof(int) * (size_t)n)))
         return rc;
     const double *src[] = {x, y, z, fMass, fSoft};
@@ -859,10 +860,103 @@ int gg_state_fetch(gg_context *c, double *x, double *y, double *z, double *vx, d
     const double *v = (const double *)c->svel.p;
     struct { void *dst; const void *src; size_t bytes; } cp[] = {
         {x, c->sx.p, nb}, {y, c->sy.p, nb}, {z, c->sz.p, nb}, {vx, v, nb}, {vy, v + n, nb}, {vz, v + 2 * (size_t)n, nb},
-        {id, c->sid.p, sizeof(int) * (size_t)n}, {dt, c->sdt.p, nb}};
+        {dt, c->sdt.p, nb}};
     for (auto &e : cp)
         if (e.dst) CK(cudaMemcpyAsync(e.dst, e.src, e.bytes, cudaMemcpyDeviceToHost, c->st));
+    if (id) CK(cudaMemcpy2DAsync(id, sizeof(int), c->sid.p, 2 * sizeof(int), sizeof(int), (size_t)n, cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
+    return GG_OK;
+}
+
+int gg_state_fetch_rungs(gg_context *c, int *rung, int *active) {
+    if (!c || c->stateN < 1) return fail(GG_ERR_ARG, "gg_state_fetch_rungs: no resident particles (gg_state_load)");
+    CK(cudaSetDevice(c->device));
+    const int n = c->stateN;
+    if (rung)
+        CK(cudaMemcpy2DAsync(rung, sizeof(int), (const int *)c->sid.p + 1, 2 * sizeof(int), sizeof(int), (size_t)n,
+                             cudaMemcpyDeviceToHost, c->st));
+    if (active) {
+        if (c->stateHasActive) CK(cudaMemcpyAsync(active, c->sact.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->st));
+        else for (int i = 0; i < n; ++i) active[i] = 1;
+    }
+    CK(cudaStreamSynchronize(c->st));
+    return GG_OK;
+}
+
+int gg_state_set_rungs(gg_context *c, const int *rung) {
+    if (!c || c->stateN < 1 || !rung) return fail(GG_ERR_ARG, "gg_state_set_rungs: bad argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpy2DAsync((int *)c->sid.p + 1, 2 * sizeof(int), rung, sizeof(int), sizeof(int), (size_t)c->stateN,
+                         cudaMemcpyDefault, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return GG_OK;
+}
+
+int gg_state_init_dt(gg_context *c, double dDelta) {
+    if (!c || c->stateN < 1) return fail(GG_ERR_ARG, "gg_state_init_dt: no resident particles (gg_state_load)");
+    CK(cudaSetDevice(c->device));
+    CK(gg_launch_init_dt(c->stateN, (double *)c->sdt.p, c->stateHasActive ? (const int *)c->sact.p : nullptr, dDelta, c->st));
+    ++c->nLaunches;
+    return GG_OK;
+}
+
+int gg_state_accelstep(gg_context *c, double dEta, double dVelFac, double dAccFac, int bEpsAcc, int bSqrtPhi) {
+    (void)dVelFac; // the velocity enters only an assertion in the gravity-only build (pkd.c:4643)
+    if (!c || c->stateN < 1) return fail(GG_ERR_ARG, "gg_state_accelstep: no resident particles (gg_state_load)");
+    if (c->stateDirty || !c->stateForces)
+        return fail(GG_ERR_ARG, "gg_state_accelstep: no accelerations for the current particle order (gg_gravity first)");
+    CK(cudaSetDevice(c->device));
+    CK(gg_launch_accelstep(c->stateN, (double *)c->sdt.p, (const double *)c->acc.p, (const double *)c->pot.p,
+                           (const double *)c->sh.p, c->stateHasActive ? (const int *)c->sact.p : nullptr, dEta, dAccFac,
+                           bEpsAcc, bSqrtPhi, c->st));
+    ++c->nLaunches;
+    return GG_OK;
+}
+
+int gg_state_dt_to_rung(gg_context *c, int iRung, double dDelta, int iMaxRung, int bAll, int *pnMaxRung, int *piMaxRungIdeal,
+                        int *piMaxRungOut) {
+    if (!c || c->stateN < 1) return fail(GG_ERR_ARG, "gg_state_dt_to_rung: no resident particles (gg_state_load)");
+    if (iRung < 0 || iMaxRung < 1 || iMaxRung > 127 || iRung + 1 > 127)
+        return fail(GG_ERR_UNSUPPORTED, "gg_state_dt_to_rung: iRung=%d iMaxRung=%d (supported < 128)", iRung, iMaxRung);
+    CK(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = ensure(c, c->srhist, 130 * sizeof(int)))) return rc;
+    int *dh = (int *)c->srhist.p;
+    CK(cudaMemsetAsync(dh, 0, 130 * sizeof(int), c->st));
+    CK(gg_launch_dt_to_rung(c->stateN, (int *)c->sid.p, (const double *)c->sdt.p, iRung, dDelta, iMaxRung, bAll, dh, dh + 128, c->st));
+    ++c->nLaunches;
+    int h[130];
+    CK(cudaMemcpyAsync(h, dh, sizeof(h), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    int top = 0;
+    for (int r = 127; r > 0; --r)
+        if (h[r] > 0) { top = r; break; }
+    if (piMaxRungOut) *piMaxRungOut = top;
+    if (pnMaxRung) *pnMaxRung = h[top];
+    if (piMaxRungIdeal) *piMaxRungIdeal = h[128];
+    return GG_OK;
+}
+
+int gg_state_active_rung(gg_context *c, int iRung, int bGreater, int *pnActive) {
+    if (!c || c->stateN < 1) return fail(GG_ERR_ARG, "gg_state_active_rung: no resident particles (gg_state_load)");
+    CK(cudaSetDevice(c->device));
+    int rc;
+    const int n = c->stateN;
+    if ((rc = ensure(c, c->sact, sizeof(int) * (size_t)n))) return rc;
+    if ((rc = ensure(c, c->srhist, 130 * sizeof(int)))) return rc;
+    int *dCount = (int *)c->srhist.p + 129;
+    CK(cudaMemsetAsync(dCount, 0, sizeof(int), c->st));
+    CK(gg_launch_active_rung(n, (const int *)c->sid.p, (int *)c->sact.p, iRung, bGreater, dCount, c->st));
+    ++c->nLaunches;
+    c->stateHasActive = true;
+    int nAct = 0;
+    CK(cudaMemcpyAsync(&nAct, dCount, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    if (pnActive) *pnActive = nAct;
+    // the loaded domain (same order as the store unless it moved since its build) evaluates the new active set
+    if (!c->stateDirty && !c->dom.empty() && c->dom[0].nPart == n) {
+        if ((rc = gg_set_active(c, (const int *)c->sact.p))) return rc;
+    }
     return GG_OK;
 }
 

@@ -193,3 +193,9 @@ cudaError_t gg_launch_permute(int n, const int *iorder, const double *vIn, doubl
 cudaError_t gg_launch_state_init(int n, int *id, double *dt, double dt0, cudaStream_t st);
 cudaError_t gg_launch_bmax_about(int n, const PartS *parts, const double c[3], unsigned long long *out, cudaStream_t st);
 cudaError_t gg_launch_mom_reduce(int nn, const double *raw, double *mom, cudaStream_t st);
+cudaError_t gg_launch_init_dt(int n, double *dt, const int *active, double dDelta, cudaStream_t st);
+cudaError_t gg_launch_accelstep(int n, double *dt, const double *a, const double *pot, const double *fSoft, const int *active,
+                                double dEta, double dAccFac, int bEpsAcc, int bSqrtPhi, cudaStream_t st);
+cudaError_t gg_launch_dt_to_rung(int n, int *idr, const double *dt, int iRung, double dDelta, int iMaxRung, int bAll, int *hist,
+                                 int *ideal, cudaStream_t st);
+cudaError_t gg_launch_active_rung(int n, const int *idr, int *active, int iRung, int bGreater, int *count, cudaStream_t st);

@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(256) k_gravstep(int n, double *dt, const doubl
 }
 
 // the state's per-particle payload follows the tree build's permutation: out[i] = in[iorder[i]]
+// (id and rung travel interleaved: idr[2*i] = persistent id, idr[2*i+1] = rung)
 __global__ void __launch_bounds__(256) k_permute(int n, const int *iorder, const double *vIn, double *vOut, const int *idIn,
                                                  int *idOut, const double *dtIn, double *dtOut) {
     const int i = blockIdx.x * 256 + threadIdx.x;
@@ -69,15 +70,77 @@ __global__ void __launch_bounds__(256) k_permute(int n, const int *iorder, const
     const int s = iorder[i];
 #pragma unroll
     for (int j = 0; j < 3; ++j) vOut[(size_t)j * n + i] = vIn[(size_t)j * n + s];
-    idOut[i] = idIn[s];
+    reinterpret_cast<int2 *>(idOut)[i] = reinterpret_cast<const int2 *>(idIn)[s];
     dtOut[i] = dtIn[s];
 }
 
 __global__ void __launch_bounds__(256) k_state_init(int n, int *id, double *dt, double dt0) {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
-    id[i] = i;
+    reinterpret_cast<int2 *>(id)[i] = make_int2(i, 0);
     dt[i] = dt0;
+}
+
+// pkdInitDt (pkd.c:4818): ACTIVE particles dt = dDelta
+__global__ void __launch_bounds__(256) k_init_dt(int n, double *dt, const int *active, double dDelta) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n && (!active || active[i])) dt[i] = dDelta;
+}
+
+// pkdAccelStep (pkd.c:4625-4672, the -DNBODY build): ACTIVE particles, acc = sqrt(a.a) dAccFac;
+// bEpsAcc: dT = dEta sqrt(fSoft / acc); bSqrtPhi: dT = min(dT, dEta 3.5 sqrt(dAccFac |fPot|) / acc); dt = min(dt, dT)
+__global__ void __launch_bounds__(256) k_accelstep(int n, double *dt, const double *a, const double *pot, const double *fSoft,
+                                                   const int *active, double dEta, double dAccFac, int bEpsAcc,
+                                                   int bSqrtPhi) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n || (active && !active[i])) return;
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) acc = __dadd_rn(acc, __dmul_rn(a[3 * (size_t)i + j], a[3 * (size_t)i + j]));
+    acc = __dmul_rn(__dsqrt_rn(acc), dAccFac);
+    double dT = 1.7976931348623157e308;
+    if (bEpsAcc && acc > 0) dT = __dmul_rn(dEta, __dsqrt_rn(__ddiv_rn(fSoft[i], acc)));
+    if (bSqrtPhi && acc > 0) {
+        const double t = __ddiv_rn(__dmul_rn(__dmul_rn(dEta, 3.5), __dsqrt_rn(__dmul_rn(dAccFac, fabs(pot[i])))), acc);
+        if (t < dT) dT = t;
+    }
+    if (dT < dt[i]) dt[i] = dT;
+}
+
+// pkdDtToRung (pkd.c:4715-4810) with pkdOneParticleDtToRung (pkd.c:4689-4712).  hist[r] counts the particles left on
+// rung r (ALL particles: the reference's iMaxRungOut / nMaxRung scan them all), ideal = max(rung + 1) before clamping.
+__global__ void __launch_bounds__(256) k_dt_to_rung(int n, int *idr, const double *dt, int iRung, double dDelta, int iMaxRung,
+                                                    int bAll, int *hist, int *ideal) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    int r = idr[2 * (size_t)i + 1];
+    if (r >= iRung) {
+        if (bAll) {
+            const double d = dt[i];
+            int iSteps = (int)floor(__ddiv_rn(dDelta, d)), t = iRung;
+            if (fmod(dDelta, d) == 0.0) iSteps--;
+            if (iSteps < 0) iSteps = 0;
+            t += 32 - __clz(iSteps); // one rung per bit of iSteps
+            atomicMax(ideal, t + 1);
+            if (t >= iMaxRung) t = iMaxRung - 1;
+            r = t;
+        } else r = dDelta <= dt[i] ? iRung : iRung + 1;
+        idr[2 * (size_t)i + 1] = r;
+    }
+    atomicAdd(&hist[min(max(r, 0), 127)], 1);
+}
+
+// pkdActiveRung (pkd.c:4569-4590)
+__global__ void __launch_bounds__(256) k_active_rung(int n, const int *idr, int *active, int iRung, int bGreater, int *count) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    int a = 0;
+    if (i < n) {
+        const int r = idr[2 * (size_t)i + 1];
+        a = r == iRung || (bGreater && r > iRung);
+        active[i] = a;
+    }
+    const int c = __popc(__ballot_sync(0xffffffffu, a));
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
 }
 
 // max |r_p - rcm| over the particles (Bmax of pkdCalcCell, pkd.c:2018-2135, for one domain about a given centre):
@@ -126,5 +189,24 @@ cudaError_t gg_launch_permute(int n, const int *iorder, const double *vIn, doubl
 }
 cudaError_t gg_launch_state_init(int n, int *id, double *dt, double dt0, cudaStream_t st) {
     if (n > 0) k_state_init<<<(n + 255) / 256, 256, 0, st>>>(n, id, dt, dt0);
+    return cudaGetLastError();
+}
+
+cudaError_t gg_launch_init_dt(int n, double *dt, const int *active, double dDelta, cudaStream_t st) {
+    if (n > 0) k_init_dt<<<(n + 255) / 256, 256, 0, st>>>(n, dt, active, dDelta);
+    return cudaGetLastError();
+}
+cudaError_t gg_launch_accelstep(int n, double *dt, const double *a, const double *pot, const double *fSoft, const int *active,
+                                double dEta, double dAccFac, int bEpsAcc, int bSqrtPhi, cudaStream_t st) {
+    if (n > 0) k_accelstep<<<(n + 255) / 256, 256, 0, st>>>(n, dt, a, pot, fSoft, active, dEta, dAccFac, bEpsAcc, bSqrtPhi);
+    return cudaGetLastError();
+}
+cudaError_t gg_launch_dt_to_rung(int n, int *idr, const double *dt, int iRung, double dDelta, int iMaxRung, int bAll, int *hist,
+                                 int *ideal, cudaStream_t st) {
+    if (n > 0) k_dt_to_rung<<<(n + 255) / 256, 256, 0, st>>>(n, idr, dt, iRung, dDelta, iMaxRung, bAll, hist, ideal);
+    return cudaGetLastError();
+}
+cudaError_t gg_launch_active_rung(int n, const int *idr, int *active, int iRung, int bGreater, int *count, cudaStream_t st) {
+    if (n > 0) k_active_rung<<<(n + 255) / 256, 256, 0, st>>>(n, idr, active, iRung, bGreater, count);
     return cudaGetLastError();
 }

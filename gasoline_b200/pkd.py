@@ -104,6 +104,12 @@ def load_library(path: str | None = None):
     L.gg_state_drift.argtypes = [C.c_void_p, C.c_double, _dp, C.c_int, _dp]
     L.gg_state_gravstep.argtypes = [C.c_void_p, C.c_double, _dp]
     L.gg_state_fetch.argtypes = [C.c_void_p] + [_dp] * 6 + [_ip, _dp]
+    L.gg_state_init_dt.argtypes = [C.c_void_p, C.c_double]
+    L.gg_state_accelstep.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]
+    L.gg_state_dt_to_rung.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int, _ip, _ip, _ip]
+    L.gg_state_active_rung.argtypes = [C.c_void_p, C.c_int, C.c_int, _ip]
+    L.gg_state_set_rungs.argtypes = [C.c_void_p, _ip]
+    L.gg_state_fetch_rungs.argtypes = [C.c_void_p, _ip, _ip]
     L.gg_measure_fp32_peak.argtypes = [C.c_void_p, _dp, _dp]
     L.gg_flush_l2.argtypes = [C.c_void_p]
     _lib = L
@@ -367,6 +373,37 @@ class PKD:
         dmin = np.zeros(1)
         _check(self._L.gg_state_gravstep(self._ctx, float(dEta), _d(dmin)), "gg_state_gravstep")
         return float(dmin[0])
+
+    def pkdInitDt(self, dDelta: float):
+        """pkdInitDt (pkd.c:4818) on the resident store."""
+        _check(self._L.gg_state_init_dt(self._ctx, float(dDelta)), "gg_state_init_dt")
+
+    def pkdAccelStep(self, dEta: float, dVelFac: float = 1.0, dAccFac: float = 1.0, bEpsAcc: int = 1, bSqrtPhi: int = 0):
+        """pkdAccelStep (pkd.c:4625) on the resident store, with the last pkdGravAll's accelerations / potentials."""
+        _check(self._L.gg_state_accelstep(self._ctx, float(dEta), float(dVelFac), float(dAccFac), int(bEpsAcc),
+                                          int(bSqrtPhi)), "gg_state_accelstep")
+
+    def pkdDtToRung(self, iRung: int, dDelta: float, iMaxRung: int, bAll: int = 1):
+        """pkdDtToRung (pkd.c:4715) on the resident store: returns (iMaxRungOut, nMaxRung, iMaxRungIdeal)."""
+        o = np.zeros(3, np.int32)
+        _check(self._L.gg_state_dt_to_rung(self._ctx, int(iRung), float(dDelta), int(iMaxRung), int(bAll), _i(o[0:1]),
+                                           _i(o[1:2]), _i(o[2:3])), "gg_state_dt_to_rung")
+        return int(o[2]), int(o[0]), int(o[1])
+
+    def pkdActiveRung(self, iRung: int, bGreater: int = 1) -> int:
+        """pkdActiveRung (pkd.c:4569) on the resident store; the flags also become the sink set of the loaded domain."""
+        n = np.zeros(1, np.int32)
+        _check(self._L.gg_state_active_rung(self._ctx, int(iRung), int(bGreater), _i(n)), "gg_state_active_rung")
+        return int(n[0])
+
+    def pkdSetRungs(self, rung):
+        _check(self._L.gg_state_set_rungs(self._ctx, _i(np.ascontiguousarray(rung, dtype=np.int32))), "gg_state_set_rungs")
+
+    def pkdFetchRungs(self):
+        """(iRung, ACTIVE) of the resident store in its current order."""
+        r, a = np.zeros(self.nLocal, np.int32), np.zeros(self.nLocal, np.int32)
+        _check(self._L.gg_state_fetch_rungs(self._ctx, _i(r), _i(a)), "gg_state_fetch_rungs")
+        return r, a
 
     def pkdFetchResident(self):
         """Download the resident store (current order): dict with r [n][3], v [n][3], iOrder, dt."""

@@ -278,6 +278,26 @@ int gg_state_drift(gg_context *ctx, double dDelta, const double fCenter[3], int 
 int gg_state_gravstep(gg_context *ctx, double dEta, double *pdtMin);
 int gg_state_fetch(gg_context *ctx, double *x, double *y, double *z, double *vx, double *vy, double *vz, int *id,
                    double *dt);
+/*
+ * Time-step selection and rungs on the resident store (multistepping hosts, msrTopStepKDK master.c:8242):
+ *   gg_state_init_dt     = pkdInitDt (pkd.c:4818): ACTIVE particles dt = dDelta
+ *   gg_state_accelstep   = pkdAccelStep (pkd.c:4625, gravity-only build): dt = min(dt, dEta sqrt(fSoft/|a| dAccFac)) and, with
+ *                          bSqrtPhi, dEta 3.5 sqrt(dAccFac |fPot|)/(|a| dAccFac); a, fPot = the last gg_gravity's device results
+ *   gg_state_dt_to_rung  = pkdDtToRung (pkd.c:4715) with pkdOneParticleDtToRung (pkd.c:4689); returns the reference's
+ *                          three results (largest rung, how many particles sit on it, the ideal largest rung)
+ *   gg_state_active_rung = pkdActiveRung (pkd.c:4569): ACTIVE := rung == iRung || (bGreater && rung > iRung); the flags
+ *                          also become the active set of the loaded domain (like gg_set_active) when the store has not
+ *                          moved since its last build, otherwise the next gg_state_build carries them
+ * All bit-identical to the reference on the same inputs (tests/test_gpu_state.py, golden vectors from the compiled
+ * reference).  gg_state_set_rungs / gg_state_fetch_rungs move PARTICLE.iRung (and the ACTIVE flags) in the store's order.
+ */
+int gg_state_init_dt(gg_context *ctx, double dDelta);
+int gg_state_accelstep(gg_context *ctx, double dEta, double dVelFac, double dAccFac, int bEpsAcc, int bSqrtPhi);
+int gg_state_dt_to_rung(gg_context *ctx, int iRung, double dDelta, int iMaxRung, int bAll, int *pnMaxRung,
+                        int *piMaxRungIdeal, int *piMaxRungOut);
+int gg_state_active_rung(gg_context *ctx, int iRung, int bGreater, int *pnActive);
+int gg_state_set_rungs(gg_context *ctx, const int *rung);
+int gg_state_fetch_rungs(gg_context *ctx, int *rung, int *active);
 
 /* Every cell's reduced multipoles by the algorithm the DEVICE uses when gg_tree.mom is NULL (raw moments of the
  * buckets, children translated to the parent's centre and summed, then reduced as pkdCalcCell defines them), executed

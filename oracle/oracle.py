@@ -47,8 +47,35 @@ def lib():
         L.oracle_step_ops.restype = C.c_int
         L.oracle_step_ops.argtypes = [C.c_int, _dp, _dp, _dp, C.c_void_p, _dp, _dp, C.c_double, C.c_double, C.c_double,
                                       _dp, C.c_int, _dp, C.c_double, C.c_int]
+        L.oracle_rung_ops.restype = None
+        L.oracle_rung_ops.argtypes = RUNG_ARGTYPES
         _lib = L
     return _lib
+
+
+RUNG_ARGTYPES = [C.c_int, _dp, _dp, _dp, _dp, _dp, _ip, _dp, _ip, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int,
+                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip]
+INITDT, ACCELSTEP, GRAVSTEP_R, DTTORUNG, ACTIVERUNG = 1, 2, 4, 8, 16
+
+
+def rung_ops(fn, v, a, fPot, fSoft, dtGrav, active, dt, rung, dDelta=0.01, dEta=0.2, dVelFac=1.0, dAccFac=1.0, bEpsAcc=1,
+             bSqrtPhi=0, iRung=0, iMaxRung=16, bAll=1, iRungActive=0, bGreater=1, what=INITDT | ACCELSTEP | DTTORUNG):
+    """Common driver of oracle_rung_ops / ref_rung_ops (same C signature): returns updated copies (active, dt, rung)
+    and out = [iMaxRungOut, nMaxRung, iMaxRungIdeal, nActive]."""
+    c = lambda x, t: np.array(x, dtype=t, copy=True)
+    active, dt, rung = c(active, np.int32), c(dt, np.float64), c(rung, np.int32)
+    out = np.zeros(4, np.int32)
+    fn(dt.shape[0], np.ascontiguousarray(v, np.float64).reshape(-1, 3), np.ascontiguousarray(a, np.float64).reshape(-1, 3),
+       np.ascontiguousarray(fPot, np.float64), np.ascontiguousarray(fSoft, np.float64),
+       np.ascontiguousarray(dtGrav, np.float64), active, dt, rung, float(dDelta), float(dEta), float(dVelFac),
+       float(dAccFac), int(bEpsAcc), int(bSqrtPhi), int(iRung), int(iMaxRung), int(bAll), int(iRungActive),
+       int(bGreater), int(what), out)
+    return active, dt, rung, out
+
+
+def oracle_rung_ops(*args, **kw):
+    """pkdInitDt / pkdAccelStep / pkdGravStep / pkdDtToRung / pkdActiveRung restated (gravity_oracle.c)."""
+    return rung_ops(lib().oracle_rung_ops, *args, **kw)
 
 
 KICK, DRIFT, GRAVSTEP = 1, 2, 4

@@ -425,3 +425,51 @@ void ref_step_ops(int n, double *r3, double *v3, const double *a3, const int *ac
     }
     ref_destroy(r);
 }
+
+/*
+ * Time-step selection on the reference's own code: pkdInitDt (pkd.c:4818), pkdAccelStep
+ * (pkd.c:4625, -DNBODY: the gas branch is not compiled), pkdGravStep (pkd.c:4609), pkdDtToRung (pkd.c:4715) and
+ * pkdActiveRung (pkd.c:4569), in that order as selected by `what` (bits 0..4), on a throw-away one-rank PKD.
+ * dt, rung, active are updated in place; out[0] = pkdDtToRung's return (iMaxRungOut), out[1] = nMaxRung,
+ * out[2] = iMaxRungIdeal, out[3] = pkdActiveRung's return.
+ */
+void ref_rung_ops(int n, const double *v3, const double *a3, const double *fPot, const double *fSoft,
+                  const double *dtGrav, int *active, double *dt, int *rung, double dDelta, double dEta, double dVelFac,
+                  double dAccFac, int bEpsAcc, int bSqrtPhi, int iRung, int iMaxRung, int bAll, int iRungActive,
+                  int bGreater, int what, int *out) {
+    static const double open3[3] = {FLOAT_MAXVAL, FLOAT_MAXVAL, FLOAT_MAXVAL};
+    double *zero = calloc((size_t)n + 1, sizeof(double));
+    REF *r = ref_create(n, zero, zero, zero, zero, zero, NULL, open3);
+    int i, j, nMaxRung = 0, iMaxRungIdeal = 0;
+    free(zero);
+    out[0] = out[1] = out[2] = out[3] = 0;
+    for (i = 0; i < n; ++i) {
+        PARTICLE *p = &r->pkd->pStore[i];
+        p->iActive = TYPE_DARK | TYPE_TREEACTIVE | (active[i] ? TYPE_ACTIVE : 0);
+        for (j = 0; j < 3; ++j) {
+            p->v[j] = v3[3 * i + j];
+            p->a[j] = a3[3 * i + j];
+        }
+        p->fPot = fPot[i];
+        p->fSoft = fSoft[i];
+        p->dtGrav = dtGrav[i];
+        p->dt = dt[i];
+        p->iRung = rung[i];
+    }
+    if (what & 1) pkdInitDt(r->pkd, dDelta);
+    if (what & 2) pkdAccelStep(r->pkd, dEta, dVelFac, dAccFac, 1, bEpsAcc, bSqrtPhi, 0.0);
+    if (what & 4) pkdGravStep(r->pkd, dEta);
+    if (what & 8) {
+        out[0] = pkdDtToRung(r->pkd, iRung, dDelta, iMaxRung, bAll, 0, &nMaxRung, &iMaxRungIdeal);
+        out[1] = nMaxRung;
+        out[2] = iMaxRungIdeal;
+    }
+    if (what & 16) out[3] = pkdActiveRung(r->pkd, iRungActive, bGreater);
+    for (i = 0; i < n; ++i) {
+        PARTICLE *p = &r->pkd->pStore[i];
+        dt[i] = p->dt;
+        rung[i] = p->iRung;
+        active[i] = TYPEQueryACTIVE(p) ? 1 : 0;
+    }
+    ref_destroy(r);
+}

@@ -51,8 +51,17 @@ def lib(gpu_host: bool = False):
         L.ref_step_ops.restype = None
         L.ref_step_ops.argtypes = [C.c_int, _dp, _dp, _dp, C.c_void_p, _dp, _dp, C.c_double, C.c_double, C.c_double,
                                    _dp, C.c_int, _dp, C.c_double, C.c_int]
+        from oracle.oracle import RUNG_ARGTYPES
+        L.ref_rung_ops.restype = None
+        L.ref_rung_ops.argtypes = RUNG_ARGTYPES
         _libs[gpu_host] = L
     return _libs[gpu_host]
+
+
+def ref_rung_ops(*args, **kw):
+    """The reference's own pkdInitDt / pkdAccelStep / pkdGravStep / pkdDtToRung / pkdActiveRung (ref_api.c)."""
+    from oracle.oracle import rung_ops
+    return rung_ops(lib().ref_rung_ops, *args, **kw)
 
 
 def ref_step_ops(*args, **kw):

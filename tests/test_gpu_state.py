@@ -178,3 +178,47 @@ def test_gravstep_bit_exact_on_device_dtgrav(gpu_lib):
     assert np.array_equal(s["dt"], dt_ref)
     assert dmin == dt_ref.min() and np.all(s["dt"][act_tree == 0] == 0.03)
     pkd.close()
+
+
+def test_rungs_and_timestep_selection_bit_exact(gpu_lib):
+    """pkdActiveRung -> tree build -> gravity on the active set -> pkdInitDt, pkdAccelStep, pkdGravStep, pkdDtToRung,
+    pkdActiveRung, all on the resident store; against the oracle restatement (pinned to the compiled reference in the CPU
+    suite) fed with the very a / fPot / dtGrav the GPU produced: every dt, rung, flag and counter identical."""
+    from oracle.oracle import ACCELSTEP, ACTIVERUNG, DTTORUNG, GRAVSTEP_R, INITDT, oracle_rung_ops
+    p = ics.plummer(6000, seed=31)
+    rng = np.random.default_rng(8)
+    v0 = rng.normal(0, 0.3, size=(p.n, 3))
+    rung0 = rng.integers(0, 3, p.n).astype(np.int32)
+    dDelta, dEta = 0.02, 0.1
+    pkd = PKD()
+    pkd.pkdLoadResident(p.x, p.y, p.z, v0[:, 0], v0[:, 1], v0[:, 2], p.m, p.h, dt0=0.5)
+    pkd.pkdSetRungs(rung0)
+    nAct = pkd.pkdActiveRung(1, 1)  # before the build: the flags travel with the particles through the partition
+    assert nAct == int((rung0 >= 1).sum())
+    pkd.pkdBuildBinaryResident(8, 0.7)
+    out = pkd.pkdGravAll(GravityParams(nReps=0, bPeriodic=0, bEwald=0))
+    assert out["nActive"] == nAct
+    s0 = pkd.pkdFetchResident()
+    rung_t, act_t = pkd.pkdFetchRungs()
+    assert np.array_equal(rung_t, rung0[s0["iOrder"]]) and np.array_equal(act_t, (rung_t >= 1).astype(np.int32))
+    pkd.pkdInitDt(dDelta)
+    pkd.pkdAccelStep(dEta, bSqrtPhi=1)
+    pkd.pkdGravStep(dEta)
+    imax, nmax, ideal = pkd.pkdDtToRung(1, dDelta, 8)
+    nAct2 = pkd.pkdActiveRung(2, 1)
+    s = pkd.pkdFetchResident()
+    rung_g, act_g = pkd.pkdFetchRungs()
+    dtg = np.where(act_t != 0, out["dtGrav"], 1.0)
+    act_o, dt_o, rung_o, o = oracle_rung_ops(s0["v"], out["acc"], out["pot"], p.h[s0["iOrder"]], dtg, act_t,
+                                             np.full(p.n, 0.5), rung_t, dDelta=dDelta, dEta=dEta, bSqrtPhi=1, iRung=1,
+                                             iMaxRung=8, bAll=1, iRungActive=2, bGreater=1,
+                                             what=INITDT | ACCELSTEP | GRAVSTEP_R | DTTORUNG | ACTIVERUNG)
+    assert np.array_equal(s["dt"], dt_o)
+    assert np.array_equal(rung_g, rung_o) and np.array_equal(act_g, act_o)
+    assert (imax, nmax, ideal, nAct2) == tuple(int(x) for x in o)
+    assert len(np.unique(rung_g)) >= 4, "the case must spread the particles over several rungs"
+    # the new active set is what the loaded domain now evaluates (gg_set_active inside pkdActiveRung)
+    out2 = pkd.pkdGravAll(GravityParams(nReps=0, bPeriodic=0, bEwald=0))
+    assert out2["nActive"] == nAct2
+    assert np.all(out2["acc"][act_g == 0] == 0)
+    pkd.close()

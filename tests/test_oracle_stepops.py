@@ -40,3 +40,29 @@ def test_oracle_step_ops_vs_reference_random():
             o = oracle_step_ops(r, v, a, active, dtGrav, dt, what=what, **kw)
             f = reflib.ref_step_ops(r, v, a, active, dtGrav, dt, what=what, **kw)
             assert all(np.array_equal(x, y) for x, y in zip(o[:3], f[:3]))
+
+
+# ---- time-step selection and rungs (pkdInitDt, pkdAccelStep, pkdGravStep, pkdDtToRung, pkdActiveRung)
+import make_golden_rungops as _rg  # noqa: E402
+from oracle.oracle import oracle_rung_ops  # noqa: E402
+
+RGOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rungops.npz"))
+
+
+@pytest.mark.parametrize("name", list(_rg.CASES))
+def test_oracle_rung_ops_golden(name):
+    what, kw = _rg.CASES[name]
+    act, dt, rung, out = oracle_rung_ops(*_rg.inputs(), what=what, **kw)
+    assert np.array_equal(act, RGOLD[name + "_active"]) and np.array_equal(dt, RGOLD[name + "_dt"])
+    assert np.array_equal(rung, RGOLD[name + "_rung"]) and np.array_equal(out, RGOLD[name + "_out"])
+
+
+@pytest.mark.skipif(not (reflib.available() and os.path.exists("/root/reference/pkd.c")), reason="compiled reference not present")
+def test_oracle_rung_ops_vs_reference_random():
+    for seed in (5, 6):
+        args = _rg.inputs(seed=seed, n=1500)
+        for name, (what, kw) in _rg.CASES.items():
+            kw = dict(kw, dEta=0.05 * seed)
+            o = oracle_rung_ops(*args, what=what, **kw)
+            f = reflib.ref_rung_ops(*args, what=what, **kw)
+            assert all(np.array_equal(x, y) for x, y in zip(o, f)), name
