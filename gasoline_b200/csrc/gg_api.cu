@@ -87,6 +87,7 @@ struct gg_context {
     DevBuf sx, sy, sz, sm, sh, sact, svel, sid, sdt, svel2, sid2, sdt2, sacc, srhist;
     int stateN = 0;
     bool stateHasActive = false, stateDirty = true, stateForces = false;
+    bool sunMode = false; // run_gravity is evaluating the bDoSun dummy bucket: the particles' results stay as they are
 };
 
 namespace {
@@ -1391,7 +1392,7 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
 
     if ((rc = ensure(c, c->imgoff, im.off.size() * sizeof(double)))) return rc;
     CK(cudaMemcpyAsync(c->imgoff.p, im.off.data(), im.off.size() * sizeof(double), cudaMemcpyHostToDevice, c->st));
-    if ((rc = ensure(c, c->counts, (size_t)nn * 3 * sizeof(int)))) return rc;
+    if ((rc = ensure(c, c->counts, (size_t)(nn + 1) * 3 * sizeof(int), c->sunMode ? (size_t)nn * 3 * sizeof(int) : 0))) return rc;
     if ((rc = ensure(c, c->acc, (size_t)(n + 1) * 3 * sizeof(double)))) return rc;
     if ((rc = ensure(c, c->pot, (size_t)(n + 1) * sizeof(double)))) return rc;
     if ((rc = ensure(c, c->dtg, (size_t)(n + 1) * sizeof(double)))) return rc;
@@ -1406,11 +1407,19 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
     if ((rc = ensure(c, c->bnode, (size_t)(nn + 1) * sizeof(int)))) return rc;
 
     CK(cudaEventRecord(c->ev[0], c->st));
-    CK(cudaMemsetAsync(c->counts.p, 0xff, (size_t)nn * 3 * sizeof(int), c->st));
-    CK(cudaMemsetAsync(c->acc.p, 0, (size_t)n * 3 * sizeof(double), c->st));
-    CK(cudaMemsetAsync(c->pot.p, 0, (size_t)n * sizeof(double), c->st));
-    CK(cudaMemsetAsync(c->dtg.p, 0, (size_t)n * sizeof(double), c->st));
-    CK(cudaMemsetAsync(c->fweight.p, 0, (size_t)n * sizeof(double), c->st));
+    if (c->sunMode) { // only the dummy sink's slot (index n) and its bucket's counters: everything else holds results
+        CK(cudaMemsetAsync((int *)c->counts.p + 3 * (size_t)nn, 0xff, 3 * sizeof(int), c->st));
+        CK(cudaMemsetAsync((double *)c->acc.p + 3 * (size_t)n, 0, 3 * sizeof(double), c->st));
+        CK(cudaMemsetAsync((double *)c->pot.p + n, 0, sizeof(double), c->st));
+        CK(cudaMemsetAsync((double *)c->dtg.p + n, 0, sizeof(double), c->st));
+        CK(cudaMemsetAsync((double *)c->fweight.p + n, 0, sizeof(double), c->st));
+    } else {
+        CK(cudaMemsetAsync(c->counts.p, 0xff, (size_t)nn * 3 * sizeof(int), c->st));
+        CK(cudaMemsetAsync(c->acc.p, 0, (size_t)n * 3 * sizeof(double), c->st));
+        CK(cudaMemsetAsync(c->pot.p, 0, (size_t)n * sizeof(double), c->st));
+        CK(cudaMemsetAsync(c->dtg.p, 0, (size_t)n * sizeof(double), c->st));
+        CK(cudaMemsetAsync(c->fweight.p, 0, (size_t)n * sizeof(double), c->st));
+    }
     CK(cudaMemsetAsync(c->sums.p, 0, 16 * sizeof(unsigned long long), c->st));
     CK(cudaMemsetAsync(c->misc.p, 0, 16 * sizeof(int), c->st));
 
@@ -1522,6 +1531,8 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
     ta.maxBucket = c->maxBucket;
     ta.walkOnly = walkOnly ? 1 : 0;
     ta.mono64 = prm->bPeriodic ? 1 : 0;
+    ta.sunNode = c->sunMode ? nn : -1;
+    ta.sunBox = 1e-14; // dTinyBox, pkd.c:3004
     ta.acc = (double *)c->acc.p;
     ta.pot = (double *)c->pot.p;
     ta.dtg = (double *)c->dtg.p;
@@ -1642,6 +1653,55 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
     return GG_OK;
 }
 
+// The bDoSun pass of pkdGravAll (pkd.c:3003-3041): a dummy ACTIVE sink at the origin with softening dSunSoft, in a bucket
+// of its own whose cell box is +-1e-14, walks the tree (pkdBucketWalk) and is evaluated (pkdBucketInteract); its
+// acceleration is the indirect term of solar-system runs.  The dummy lives in the spare slot behind the particles and
+// the spare node behind the tree; the particles' results and counters are left as the main pass produced them, and --
+// like the reference -- the dummy's interactions are not counted in dPartSum / dCellSum / dFlop.
+int run_sun(gg_context *c, const gg_params *prm, gg_stats *stats) {
+    if (prm->bPeriodic || prm->nReps != 0)
+        return fail(GG_ERR_ARG, "gg_gravity: bDoSun needs open boundaries (the reference asserts it, pkd.c:3013-3014)");
+    if (c->dom.size() != 1 || c->nTop > 0)
+        return fail(GG_ERR_UNSUPPORTED, "gg_gravity: bDoSun with several domains is not supported");
+    int rc;
+    if ((rc = finish_mom(c))) return rc;
+    const Domain &L = c->dom[0];
+    const int n = L.nPart, nn = L.nNodes;
+    PartS ps;
+    ps.x = ps.y = ps.z = 0.0; ps.m = 0.f; ps.h = (float)prm->dSunSoft;
+    NodeW w;
+    w.rx = w.ry = w.rz = 0.0; w.fMass = 0.0; w.fOpen2 = 0.0; w.fSoft = prm->dSunSoft;
+    w.c0 = w.c1 = -1; w.pLower = n; w.nP = 1;
+    const double hs = prm->dSunSoft;
+    const int one = 1;
+    CK(cudaMemcpyAsync((PartS *)c->parts.p + n, &ps, sizeof(ps), cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync((NodeW *)c->nodes.p + nn, &w, sizeof(w), cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync((double *)c->hsoft.p + n, &hs, sizeof(hs), cudaMemcpyHostToDevice, c->st));
+    if (!c->hActive.empty()) CK(cudaMemcpyAsync((int *)c->active.p + n, &one, sizeof(one), cudaMemcpyHostToDevice, c->st));
+    CK(cudaStreamSynchronize(c->st)); // (the sources are stack variables)
+    Task t;
+    t.node = nn; t.pass = 0; t.ord = 0; t.pad = 0;
+    gg_params p2 = *prm;
+    p2.flags = GG_FLAG_NO_DOWNLOAD;
+    p2.bDoSun = 0;
+    gg_stats st2;
+    c->sunMode = true;
+    rc = run_gravity(c, &p2, &t, &st2);
+    c->sunMode = false;
+    if (rc) return rc;
+    double a3[3];
+    int c3[3];
+    CK(cudaMemcpyAsync(a3, (const double *)c->acc.p + 3 * (size_t)n, sizeof(a3), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(c3, (const int *)c->counts.p + 3 * (size_t)nn, sizeof(c3), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    if (stats) {
+        stats->aSun[0] = a3[0]; stats->aSun[1] = a3[1]; stats->aSun[2] = a3[2];
+        stats->nSunPart = c3[0]; stats->nSunCellSoft = c3[1]; stats->nSunCellNewt = c3[2];
+        stats->nKernelLaunches = c->nLaunches;
+    }
+    return GG_OK;
+}
+
 } // namespace
 
 extern "C" {
@@ -1675,6 +1735,9 @@ int gg_gravity(gg_context *c, const gg_params *prm, double *a, double *fPot, dou
     c->zc[0] = c->zc[1] = c->zc[2] = c->zc[3] = nullptr;
     if (rc) return rc;
     if (c->stateN > 0 && !(prm->flags & GG_FLAG_WALK_ONLY)) c->stateForces = true;
+    if (prm->bDoSun && !(prm->flags & GG_FLAG_WALK_ONLY)) {
+        if ((rc = run_sun(c, prm, stats))) return rc;
+    }
     if (!wantOut || zeroCopy) return GG_OK;
     const int n = c->dom[0].nPart;
     if (n == 0) return GG_OK;

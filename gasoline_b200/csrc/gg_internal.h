@@ -115,6 +115,8 @@ struct TreeKernelArgs {
     int maxBucket;           // largest particle count of any bucket (sizes the particle buffer)
     int walkOnly;
     int mono64;              // k_eval: cell monopoles in FP64 (periodic boxes, see eval_cells)
+    int sunNode;             // bDoSun pass (pkd.c:3003-3041): the dummy sink bucket's node, whose box is +-sunBox; else -1
+    double sunBox;
     // outputs (local particles, tree order)
     double *acc;             // [n][3]
     double *pot;

@@ -461,6 +461,12 @@ __global__ void __launch_bounds__(GG_WALK_WARPS * 32, GG_WALK_MIN_CTAS) k_walk(c
                     const int b = min(bb + (lane >> 3), nB - 1);
                     const int pl = __shfl_sync(FULL, myLower, b), np = __shfl_sync(FULL, myNP, b);
                     sink_box4(A, pl, np, lane, box, fSoftMax);
+                    if (A.sunNode >= 0 && __shfl_sync(FULL, myNode, b) == A.sunNode) {
+                        // the dummy sink of the bDoSun pass: the reference gives its cell a box of +-1e-14 about the
+                        // origin instead of the particle's own position (pkd.c:3017-3021)
+                        box[0] = box[1] = box[2] = -A.sunBox;
+                        box[3] = box[4] = box[5] = A.sunBox;
+                    }
                     if (bb + (lane >> 3) < nB) {
                         const int k = lane & 7;
                         const double v = k == 0 ? box[0] : k == 1 ? box[1] : k == 2 ? box[2] : k == 3 ? box[3]

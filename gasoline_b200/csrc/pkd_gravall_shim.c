@@ -30,7 +30,8 @@
  *
  * Scope of this file: one MDL rank per process image of the tree (mdlThreads == 1).  Multi-GPU runs hand each rank
  * the other domains' trees through gg_set_top / gg_set_remote (gasoline_b200/domain.py does it over NCCL).
- * bDoSun (pkd.c:3003-3041, solar-system indirect term) is not supported on the GPU path.
+ * bDoSun (pkd.c:3003-3041, the indirect term of solar-system runs) is passed through: gg_gravity evaluates the dummy
+ * sink at the origin after the particles and aSun comes back through gg_stats.
  */
 #include <pthread.h>
 #include <stdio.h>
@@ -233,8 +234,6 @@ void pkdGravAll(PKD pkd, int nReps, int bPeriodic, int iOrder, int bEwald, int i
     PASS pass;
     int j;
 
-    (void)dSunSoft;
-    mdlassert(pkd->mdl, !bDoSun); /* not supported on the GPU path */
     mdlassert(pkd->mdl, mdlThreads(pkd->mdl) == 1);
     mdlassert(pkd->mdl, pkd->idSelf >= 0 && pkd->idSelf < 64);
     s = &g_shim[pkd->idSelf];
@@ -273,13 +272,14 @@ void pkdGravAll(PKD pkd, int nReps, int bPeriodic, int iOrder, int bEwald, int i
     prm.nReps = nReps; prm.bPeriodic = bPeriodic; prm.iOrder = iOrder; prm.bEwald = bEwald; prm.iEwOrder = iEwOrder;
     prm.fEwCut = fEwCut; prm.fEwhCut = fEwhCut; prm.bComove = bComove; prm.dRhoFac = dRhoFac;
     for (j = 0; j < 3; ++j) prm.fPeriod[j] = pkd->fPeriod[j];
+    prm.bDoSun = bDoSun; prm.dSunSoft = dSunSoft;
     prm.accumulate = 0; /* this call's contribution, delivered zero-copy into the pinned arrays; merged below */
     if (gg_gravity(s->ctx, &prm, s->a, s->pot, s->dt, s->w, &st) != GG_OK) die("gg_gravity");
     parallel_for((size_t)n, write_back, &pass);
     pkdStopTimer(pkd, 2);
     *nActive = st.nActive;
     *pdPartSum = st.dPartSum; *pdCellSum = st.dCellSum; *pdSoftSum = st.dSoftSum; *pdFlop = st.dFlop;
-    if (aSun) aSun[0] = aSun[1] = aSun[2] = 0.0;
+    if (aSun) { aSun[0] = st.aSun[0]; aSun[1] = st.aSun[1]; aSun[2] = st.aSun[2]; } /* zero without bDoSun */
     memset(pcs, 0, sizeof(*pcs)); /* no software cache on this path */
     pkd->nPart = st.nMaxPart; pkd->nCellSoft = st.nMaxCellSoft; pkd->nCellNewt = st.nMaxCellNewt; /* diag only */
 }

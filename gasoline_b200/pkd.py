@@ -41,7 +41,8 @@ class gg_particles(C.Structure):
 class gg_params(C.Structure):
     _fields_ = [("nReps", C.c_int), ("bPeriodic", C.c_int), ("iOrder", C.c_int), ("bEwald", C.c_int),
                 ("iEwOrder", C.c_int), ("fEwCut", C.c_double), ("fEwhCut", C.c_double), ("bComove", C.c_int),
-                ("dRhoFac", C.c_double), ("fPeriod", C.c_double * 3), ("accumulate", C.c_int), ("flags", C.c_int)]
+                ("dRhoFac", C.c_double), ("fPeriod", C.c_double * 3), ("accumulate", C.c_int), ("flags", C.c_int),
+                ("bDoSun", C.c_int), ("dSunSoft", C.c_double)]
 
 
 class gg_stats(C.Structure):
@@ -49,7 +50,8 @@ class gg_stats(C.Structure):
                 ("dFlop", C.c_double), ("dFlopEwald", C.c_double), ("msTree", C.c_double), ("msEwald", C.c_double),
                 ("msTotal", C.c_double), ("nKernelLaunches", C.c_int), ("nMaxPart", C.c_int),
                 ("nMaxCellSoft", C.c_int), ("nMaxCellNewt", C.c_int), ("msWalk", C.c_double), ("msEval", C.c_double),
-                ("nListEntries", C.c_double)]
+                ("nListEntries", C.c_double), ("aSun", C.c_double * 3), ("nSunPart", C.c_int), ("nSunCellSoft", C.c_int),
+                ("nSunCellNewt", C.c_int)]
 
 
 _lib = None
@@ -484,10 +486,8 @@ class PKD:
 
     # -- the hot path ---------------------------------------------------------------------------------------
     def _params(self, g: GravityParams, accumulate: int, flags: int) -> gg_params:
-        if g.bDoSun:
-            raise GasolineB200Error("pkdGravAll: bDoSun (solar indirect term, pkd.c:3003) is not supported on the GPU path")
         return gg_params(g.nReps, g.bPeriodic, g.iOrder, g.bEwald, g.iEwOrder, g.fEwCut, g.fEwhCut, g.bComove,
-                         g.dRhoFac, (C.c_double * 3)(*self.fPeriod), accumulate, flags)
+                         g.dRhoFac, (C.c_double * 3)(*self.fPeriod), accumulate, flags, int(g.bDoSun), float(g.dSunSoft))
 
     def pkdGravAll(self, g: GravityParams, a=None, fPot=None, dtGrav=None, fWeight=None, walk_only=False,
                    download=True, accumulate=None):
@@ -507,7 +507,7 @@ class PKD:
         ptr = lambda v: v.ctypes.data_as(C.c_void_p) if v is not None else None
         _check(self._L.gg_gravity(self._ctx, C.byref(prm), ptr(a), ptr(fPot), ptr(dtGrav), ptr(fWeight), C.byref(st)),
                "gg_gravity")
-        self.stats = {k: getattr(st, k) for k, _ in gg_stats._fields_}
+        self.stats = {k: (np.array(st.aSun[:]) if k == "aSun" else getattr(st, k)) for k, _ in gg_stats._fields_}
         out = dict(self.stats)
         out.update(acc=a, pot=fPot, dtGrav=dtGrav, fWeight=fWeight)
         return out

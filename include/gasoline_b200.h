@@ -28,7 +28,7 @@ extern "C" {
 #define GG_OK 0
 #define GG_ERR_CUDA (-1)       /* a CUDA runtime call failed (message has file:line and the CUDA error) */
 #define GG_ERR_ARG (-2)        /* invalid argument / call order */
-#define GG_ERR_UNSUPPORTED (-3) /* e.g. bDoSun, iOrder outside 1..4, bucket larger than GG_MAX_BUCKET */
+#define GG_ERR_UNSUPPORTED (-3) /* e.g. iOrder outside 1..4, bucket larger than GG_MAX_BUCKET, bDoSun with several domains */
 #define GG_ERR_NOMEM (-4)
 
 #define GG_NMOM 31       /* Q6 O10 H15 in the order of struct pkdCalcCellStruct, pkd.h:441-451 */
@@ -82,6 +82,10 @@ typedef struct gg_params {
     double fPeriod[3]; /* pkd->fPeriod; >= DBL_MAX on an axis = not periodic (walk.c:326) */
     int accumulate;  /* 1: a, fPot += and dtGrav = max(old,new) like the reference; 0: overwrite */
     int flags;       /* GG_FLAG_* */
+    int bDoSun;      /* pkd.c:3003-3041: after the particles, a dummy sink at the origin (softening dSunSoft, cell box
+                        +-1e-14) walks the tree and is evaluated like a bucket; its acceleration comes back in
+                        gg_stats.aSun.  Open boundaries, one domain (the reference asserts nReps == 0, !bPeriodic) */
+    double dSunSoft;
 } gg_params;
 
 #define GG_FLAG_WALK_ONLY 1 /* build lists and count them, skip all force arithmetic (parity hook) */
@@ -101,6 +105,8 @@ typedef struct gg_stats {
     double msWalk;                       /* the walk kernel's share of msTree */
     double msEval;                       /* the list-evaluation kernel's share of msTree (the dominant kernel) */
     double nListEntries;                 /* entries of the per-bucket interaction lists k_eval streamed (4 B each) */
+    double aSun[3];                      /* bDoSun: the indirect acceleration at the origin (pkd.c:3037-3039), else 0 */
+    int nSunPart, nSunCellSoft, nSunCellNewt; /* bDoSun: the dummy bucket's list lengths (parity hook) */
 } gg_stats;
 
 const char *gg_last_error(void);

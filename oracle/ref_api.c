@@ -34,6 +34,7 @@ typedef struct {
 /* ---- per-bucket counts: --wrap=pkdBucketWalk -------------------------------------------------- */
 static int *g_counts = NULL; /* 3 ints per node, indexed by iBucket */
 static int g_nCounts = 0;
+static int *g_sunCounts = NULL; /* the lists of the bDoSun dummy bucket (pkd.c:3003-3041), iBucket == pkd->iFreeCell */
 void __real_pkdBucketWalk(PKD pkd, int iBucket, int nReps, int iOrder);
 /*
  * Multi-rank dump (gasoline_ref binary, pthread MDL ranks; env REF_DUMP=<prefix>): on a rank's first pkdBucketWalk
@@ -83,6 +84,11 @@ void __wrap_pkdBucketWalk(PKD pkd, int iBucket, int nReps, int iOrder) {
         rec[3] = pkd->nPart; rec[4] = pkd->nCellSoft; rec[5] = pkd->nCellNewt;
         fwrite(rec, sizeof(int), 6, g_dump[pkd->idSelf]);
         fflush(g_dump[pkd->idSelf]);
+    }
+    if (g_sunCounts && iBucket == pkd->iFreeCell) {
+        g_sunCounts[0] = pkd->nPart;
+        g_sunCounts[1] = pkd->nCellSoft;
+        g_sunCounts[2] = pkd->nCellNewt;
     }
     if (g_counts && iBucket < g_nCounts) {
         g_counts[3 * iBucket + 0] = pkd->nPart;
@@ -472,4 +478,30 @@ void ref_rung_ops(int n, const double *v3, const double *a3, const double *fPot,
         active[i] = TYPEQueryACTIVE(p) ? 1 : 0;
     }
     ref_destroy(r);
+}
+
+/*
+ * pstGravity with bDoSun = 1 (pkd.c:3003-3041: the indirect acceleration of solar-system runs -- a dummy sink at the
+ * origin with softening dSunSoft walks the tree and is evaluated like any bucket; open boundaries only): returns aSun
+ * and the dummy bucket's list counts.  The particles' own results are untouched by the dummy pass.
+ */
+void ref_gravity_sun(REF *r, int iOrder, double dSunSoft, double *aSun3, int *sunCounts3) {
+    struct inGravity in;
+    struct outGravity out;
+    int iDum, j;
+    memset(&in, 0, sizeof(in));
+    in.nReps = 0;
+    in.bPeriodic = 0;
+    in.iOrder = iOrder;
+    in.bEwald = 0;
+    in.iEwOrder = iOrder;
+    in.bDoSun = 1;
+    in.dSunSoft = dSunSoft;
+    in.dEwCut = 2.6;
+    in.dEwhCut = 2.8;
+    pkdInitAccel(r->pkd);
+    g_sunCounts = sunCounts3;
+    pstGravity(r->pst, &in, sizeof(in), &out, &iDum);
+    g_sunCounts = NULL;
+    for (j = 0; j < 3; ++j) aSun3[j] = out.aSun[j];
 }

@@ -1,0 +1,69 @@
+"""bDoSun (pkd.c:3003-3041): the indirect acceleration at the origin -- a dummy sink of softening dSunSoft in a cell of
++-1e-14 that walks the tree and is evaluated like any bucket -- against golden vectors produced by the compiled
+reference (tests/golden/make_golden_sun.py): the dummy bucket's interaction-list counts bit-exact, aSun within the
+north-star tolerance, and the particles' own results untouched by the extra pass."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from gasoline_b200.pkd import PKD, GasolineB200Error, GravityParams
+from oracle import reflib
+from parity import MAX_TOL
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+from make_golden_sun import NAMES, case  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sun.npz"))
+
+
+@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("build", ["host", "device"])
+def test_sun_indirect_term(name, build, gpu_lib):
+    p, theta, soft = case(name)
+    pkd = PKD()
+    pkd.pkdLoadParticles(p.x, p.y, p.z, p.m, p.h)
+    if build == "host":
+        pkd.pkdBuildBinary(8, theta, 4)
+    else:
+        pkd.pkdBuildBinaryDevice(8, theta)
+    plain = pkd.pkdGravAll(GravityParams(nReps=0, bPeriodic=0, bEwald=0))
+    counts_plain = pkd.pkdBucketCounts()
+    out = pkd.pkdGravAll(GravityParams(nReps=0, bPeriodic=0, bEwald=0, bDoSun=1, dSunSoft=soft))
+    assert (out["nSunPart"], out["nSunCellSoft"], out["nSunCellNewt"]) == tuple(GOLD[name + "_counts"])
+    ref = GOLD[name + "_aSun"]
+    err = np.linalg.norm(out["aSun"] - ref) / np.linalg.norm(ref)
+    print(f"sun {name} ({build} tree): aSun {out['aSun']}, relative error {err:.2e}")
+    assert err <= MAX_TOL
+    # the dummy pass is not counted and leaves the particles alone (pkd.c:3003-3041 runs after the bucket loop)
+    assert (out["nActive"], out["dPartSum"], out["dCellSum"], out["dSoftSum"], out["dFlop"]) == tuple(GOLD[name + "_sums"])
+    for k in ("acc", "pot", "dtGrav", "fWeight"):
+        assert np.array_equal(out[k], plain[k])
+    assert np.array_equal(pkd.pkdBucketCounts(), counts_plain)
+    assert np.all(plain["aSun"] == 0)
+    pkd.close()
+
+
+def test_sun_rejects_periodic(gpu_lib):
+    from gasoline_b200 import ics
+    p = ics.periodic_box(8)
+    pkd = PKD(fPeriod=p.period)
+    pkd.pkdLoadParticles(p.x, p.y, p.z, p.m, p.h)
+    pkd.pkdBuildBinary(8, 0.7, 4)
+    with pytest.raises(GasolineB200Error):  # the reference asserts nReps == 0 && !bPeriodic (pkd.c:3013-3014)
+        pkd.pkdGravAll(GravityParams(nReps=1, bPeriodic=1, bEwald=1, bDoSun=1, dSunSoft=0.01))
+    pkd.close()
+
+
+@pytest.mark.skipif(not reflib.gpu_host_available(), reason="oracle/_ref/libgasref_gpu.so not built")
+def test_sun_through_the_reference_host(gpu_lib):
+    """pstGravity with bDoSun = 1 on the reference host whose pkdGravAll is ours: aSun as the reference returns it."""
+    p, theta, soft = case("inside")
+    r = reflib.RefGravity(p, gpu_host=True)
+    r.build_tree(8, theta, 4)
+    a, _ = r.gravity_sun(soft)
+    r.close()
+    ref = GOLD["inside_aSun"]
+    assert np.linalg.norm(a - ref) / np.linalg.norm(ref) <= MAX_TOL
