@@ -1,7 +1,8 @@
-"""Print parity metrics of the CUDA path against the CPU oracle for a set of cases (development aid)."""
+"""Print parity metrics of the CUDA path against the CPU oracle for a set of cases (development aid; lives under tests/ because it uses the oracle)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, _ROOT)
+sys.path.insert(0, os.path.join(_ROOT, "tests"))
 import numpy as np
 from gasoline_b200 import ics, build
 from gasoline_b200.pkd import PKD, GravityParams

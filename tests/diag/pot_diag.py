@@ -1,6 +1,7 @@
-"""Potential-error diagnostic (development aid): signed error statistics of the CUDA path vs the oracle."""
+"""Potential-error diagnostic (development aid; lives under tests/ because it uses the oracle): signed error statistics of the CUDA path vs the oracle."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, _ROOT)
 import numpy as np
 from gasoline_b200 import ics
 from gasoline_b200.pkd import PKD, GravityParams
