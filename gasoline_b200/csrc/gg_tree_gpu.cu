@@ -164,7 +164,12 @@ __global__ void __launch_bounds__(256) k_flag(int n, const double *x, const doub
     if (i < n) {
         const int c = cellOf[i];
         if (c >= levelStart[level]) {
-            const BNode nd = nodes[c];
+            // only the range and the bounds are read: the cell's first particle writes dim / split / children below while
+            // the others are still here
+            BNode nd;
+            nd.lo = nodes[c].lo; nd.hi = nodes[c].hi;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) nd.b[k] = nodes[c].b[k];
             double split;
             int d = decide(nd, nBucket, &split);
             // a cell that still splits but holds <= GGB_WCAP particles leaves the level-synchronous path here: one warp
