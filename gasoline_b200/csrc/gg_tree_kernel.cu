@@ -663,15 +663,23 @@ __global__ void __launch_bounds__(256) k_scatter(const TreeKernelArgs A) {
         cur = A.bucketOff[b0 + lane] + (type <= 1 ? e[2] : 0) + (type == 0 ? e[1] : 0) +
               (src ? A.groupCnt[6 * g + 2 * type] : 0);
     }
-    int cnt = total - 32 * ((total - 1) / 32); // the head block is the partial one
+    const int cnt0 = total - 32 * ((total - 1) / 32); // the head block is the partial one
+    // the chain is a linked list (one dependent load per block): keep the NEXT block's entries and link in flight while
+    // the current block is distributed
+    unsigned it = 0, mk = 0;
+    if (lane < cnt0) {
+        it = A.pool[(size_t)blk * 32 + lane];
+        mk = src ? (unsigned)A.poolMask[(size_t)blk * 32 + lane] : all;
+    }
+    int nxt = A.nextBlk[blk];
     while (blk >= 0) {
-        unsigned it = 0, mk = 0;
-        if (lane < cnt) {
-            it = A.pool[(size_t)blk * 32 + lane];
-            mk = src ? (unsigned)A.poolMask[(size_t)blk * 32 + lane] : all;
+        unsigned itN = 0, mkN = 0;
+        int nxtN = -1;
+        if (nxt >= 0) {
+            itN = A.pool[(size_t)nxt * 32 + lane];
+            mkN = src ? (unsigned)A.poolMask[(size_t)nxt * 32 + lane] : all;
+            nxtN = A.nextBlk[nxt];
         }
-        blk = A.nextBlk[blk];
-        cnt = 32;
 #pragma unroll 2
         for (int b = 0; b < nB; ++b) {
             const bool has = (mk >> b) & 1u;
@@ -681,6 +689,7 @@ __global__ void __launch_bounds__(256) k_scatter(const TreeKernelArgs A) {
             if (has) A.lists[base + __popc(m & lt)] = it;
             if (lane == b) cur += __popc(m);
         }
+        blk = nxt; nxt = nxtN; it = itN; mk = mkN;
     }
 }
 
