@@ -20,6 +20,9 @@
 #ifndef GG_MIN_CTAS
 #define GG_MIN_CTAS 5        // resident CTAs per SM k_eval is compiled for (44 KB shared memory each; register cap 102)
 #endif
+#ifndef GG_MONO_MIN_CTAS
+#define GG_MONO_MIN_CTAS (GG_MIN_CTAS - 1) // k_eval<.,true> (periodic boxes, FP64 monopoles): 128 registers
+#endif
 #ifndef GG_CELL_UNROLL
 #define GG_CELL_UNROLL 1     // unroll factor of k_eval's (sink, cell) loop
 #endif

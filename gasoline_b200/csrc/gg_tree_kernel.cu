@@ -933,7 +933,7 @@ template <int ORDER, bool MONO64>
 #ifdef GG_EVAL_MAXREG
 __global__ void __launch_bounds__(GG_WARPS_PER_CTA * 32) __maxnreg__(MONO64 ? 128 : GG_EVAL_MAXREG) k_eval(const TreeKernelArgs A) {
 #else
-__global__ void __launch_bounds__(GG_WARPS_PER_CTA * 32, MONO64 ? GG_MIN_CTAS - 1 : GG_MIN_CTAS) k_eval(const TreeKernelArgs A) {
+__global__ void __launch_bounds__(GG_WARPS_PER_CTA * 32, MONO64 ? GG_MONO_MIN_CTAS : GG_MIN_CTAS) k_eval(const TreeKernelArgs A) {
 #endif
     typedef EvalSmemT<MONO64 ? 2 : 1> EvalSmem;
     extern __shared__ __align__(16) unsigned char eval_smem_raw[];
