@@ -154,7 +154,7 @@ Images make_images(const gg_params *prm) {
             }
         }
     }
-    im.bits = im.n <= 32 ? 5 : 7;
+    im.bits = im.n <= 32 ? 5 : (im.n <= 128 ? 7 : 9);
     return im;
 }
 
@@ -441,9 +441,9 @@ int upload_domain(gg_context *c, const gg_tree *t, const gg_particles *pp, int n
     double *dx = dmom + nMomD, *dy = dx + np, *dz = dy + np, *dm = dz + np, *dh = dm + np;
     int *di = (int *)c->rawi.p;
     const size_t keepN = (size_t)nodeBase, keepP = (size_t)partBase;
-    if ((rc = ensure(c, c->nodes, (keepN + nn + GG_MAX_IMAGES) * sizeof(NodeW), keepN * sizeof(NodeW)))) return rc;
-    if ((rc = ensure(c, c->momf, (keepN + nn + GG_MAX_IMAGES) * 128, keepN * 128))) return rc;
-    if ((rc = ensure(c, c->momq, (keepN + nn + GG_MAX_IMAGES) * 48, keepN * 48))) return rc;
+    if ((rc = ensure(c, c->nodes, (keepN + nn + GG_MAX_TOP) * sizeof(NodeW), keepN * sizeof(NodeW)))) return rc;
+    if ((rc = ensure(c, c->momf, (keepN + nn + GG_MAX_TOP) * 128, keepN * 128))) return rc;
+    if ((rc = ensure(c, c->momq, (keepN + nn + GG_MAX_TOP) * 48, keepN * 48))) return rc;
     if ((rc = ensure(c, c->parts, (keepP + np + 1) * sizeof(PartS), keepP * sizeof(PartS)))) return rc;
     if (local && (rc = ensure(c, c->hsoft, (size_t)(np + 1) * sizeof(double)))) return rc;
     // ---- what the walk needs, on the main stream (issued first: the copy engine serves it first)
@@ -1252,9 +1252,9 @@ int gg_set_remote_packed(gg_context *c, int id, const int hdr[3], const void *sr
     const size_t keepN = (size_t)c->nNodesAll, keepP = (size_t)c->nPartAll;
     int rc;
     if ((rc = finish_mom(c))) return rc;
-    if ((rc = ensure(c, c->nodes, (keepN + nn + GG_MAX_IMAGES) * sizeof(NodeW), keepN * sizeof(NodeW)))) return rc;
-    if ((rc = ensure(c, c->momf, (keepN + nn + GG_MAX_IMAGES) * 128, keepN * 128))) return rc;
-    if ((rc = ensure(c, c->momq, (keepN + nn + GG_MAX_IMAGES) * 48, keepN * 48))) return rc;
+    if ((rc = ensure(c, c->nodes, (keepN + nn + GG_MAX_TOP) * sizeof(NodeW), keepN * sizeof(NodeW)))) return rc;
+    if ((rc = ensure(c, c->momf, (keepN + nn + GG_MAX_TOP) * 128, keepN * 128))) return rc;
+    if ((rc = ensure(c, c->momq, (keepN + nn + GG_MAX_TOP) * 48, keepN * 48))) return rc;
     if ((rc = ensure(c, c->parts, (keepP + np + 1) * sizeof(PartS), keepP * sizeof(PartS)))) return rc;
     const char *i0 = (const char *)src;
     const char *i1 = i0 + (size_t)nn * sizeof(NodeW), *i2 = i1 + (size_t)nn * 128, *i3 = i2 + (size_t)nn * 48;
@@ -1284,7 +1284,7 @@ int gg_set_top(gg_context *c, int nCell, const int *pLower, const int *bUsed, co
                const double *fSoft, const double *fOpen2, const double *mom) {
     if (!c || nCell < 2 || !pLower || !bUsed || !r || !fMass || !fSoft || !fOpen2 || !mom)
         return fail(GG_ERR_ARG, "gg_set_top: bad argument");
-    if (nCell > GG_MAX_IMAGES) return fail(GG_ERR_UNSUPPORTED, "gg_set_top: nCell=%d > %d", nCell, GG_MAX_IMAGES);
+    if (nCell > GG_MAX_TOP) return fail(GG_ERR_UNSUPPORTED, "gg_set_top: nCell=%d > %d", nCell, GG_MAX_TOP);
     c->nTop = nCell;
     c->topLower.assign(pLower, pLower + nCell);
     c->topUsed.assign(bUsed, bUsed + nCell);
@@ -1358,7 +1358,7 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
     if (c->dom.empty()) return fail(GG_ERR_ARG, "gg_gravity: gg_set_local has not been called");
     if (prm->iOrder < 1 || prm->iOrder > 4 || prm->iEwOrder < 0 || prm->iEwOrder > 4)
         return fail(GG_ERR_UNSUPPORTED, "gg_gravity: iOrder=%d iEwOrder=%d (supported 1..4)", prm->iOrder, prm->iEwOrder);
-    if (prm->nReps < 0 || prm->nReps > 2) return fail(GG_ERR_UNSUPPORTED, "gg_gravity: nReps=%d (supported 0..2)", prm->nReps);
+    if (prm->nReps < 0 || prm->nReps > 3) return fail(GG_ERR_UNSUPPORTED, "gg_gravity: nReps=%d (supported 0..3)", prm->nReps);
     CK(cudaSetDevice(c->device));
     if (depth > 0) CK(cudaStreamSynchronize(c->st3)); // a re-run: the previous attempt's k_stats may still be in flight
     const Domain &L = c->dom[0];

@@ -43,7 +43,8 @@ typedef unsigned short gg_mask_t;
 #define GG_MAX_SINKS 8      // sinks evaluated per warp pass (accumulators live in registers)
 #define GG_STACK_CAP 512    // walk frontier entries per warp
 #define GG_STACK_DFS_MARGIN 128
-#define GG_MAX_IMAGES 128
+#define GG_MAX_IMAGES 343    // (2 nReps + 1)^3 images of the tree walk, nReps <= 3
+#define GG_MAX_TOP 128       // top-tree cells (2 x ranks, heap indexed) = spare node records behind the domains' nodes
 
 // The FP32 evaluation record of one cell from the reference's reduced multipoles q[GG_NMOM] (pkdCalcCell order): the
 // quadrupole made traceless like SETILIST (walk.c:41-48), and each order pre-multiplied by (2l-1)!! -- 3, 15, 105 -- so

@@ -424,7 +424,8 @@ __device__ __forceinline__ void sink_box4(const TreeKernelArgs &A, int pLower, i
 // the whole group that are monotone in floating point (so they can never disagree with the per-bucket result).
 __global__ void __launch_bounds__(GG_WALK_WARPS * 32, GG_WALK_MIN_CTAS) k_walk(const TreeKernelArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ double s_off[GG_MAX_IMAGES * 3];
+    // the image offsets live behind the warps' walk state, sized by the call's image count (27 in a periodic box)
+    double *s_off = reinterpret_cast<double *>(smem_raw + GG_WALK_WARPS * walk_smem_bytes());
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
     for (int i = threadIdx.x; i < A.nImages * 3; i += blockDim.x) s_off[i] = A.imgOff[i];
@@ -705,7 +706,7 @@ struct EvalSmemT {
         struct {                   // leaves (never in flight together with cells)
             int lstart[32], lpart[32]; // first staging slot and first particle of each leaf of the batch
             unsigned char owner[PCAP]; // staging slot -> leaf of the batch
-            unsigned char limg[32];
+            unsigned short limg[32];
         };
     };
 };
@@ -874,7 +875,7 @@ __device__ __forceinline__ void eval_leaves(const TreeKernelArgs &A, SM &W, cons
         const int nStaged = min(__shfl_sync(FULL, incl, r1 - 1) - base, PCAP);
         if (lane >= r0 && lane < r1) {
             const int s0 = incl - np - base;
-            W.lstart[lane] = s0; W.lpart[lane] = pl; W.limg[lane] = (unsigned char)ci;
+            W.lstart[lane] = s0; W.lpart[lane] = pl; W.limg[lane] = (unsigned short)ci;
             for (int j = 0; j < np; ++j) W.owner[s0 + j] = (unsigned char)lane;
         }
         __syncwarp();
@@ -1053,7 +1054,8 @@ __global__ void __launch_bounds__(GG_WARPS_PER_CTA * 32, MONO64 ? GG_MONO_MIN_CT
 
 } // namespace
 
-size_t gg_walk_kernel_smem() { return GG_WALK_WARPS * walk_smem_bytes(); }
+static size_t image_table_bytes(int nImages) { return ((size_t)nImages * 3 * sizeof(double) + 15) & ~(size_t)15; }
+size_t gg_walk_kernel_smem(int nImages) { return GG_WALK_WARPS * walk_smem_bytes() + image_table_bytes(nImages); }
 
 static int grid_for(const void *fn, int threads, size_t smem, int nSM, int warpsPerCta, int nTasks, cudaError_t *pe) {
     int perSM = 0;
@@ -1066,7 +1068,7 @@ static int grid_for(const void *fn, int threads, size_t smem, int nSM, int warps
 }
 
 cudaError_t gg_launch_walk_kernel(const TreeKernelArgs &a, int nSM, cudaStream_t st) {
-    const size_t smem = gg_walk_kernel_smem();
+    const size_t smem = gg_walk_kernel_smem(a.nImages);
     cudaError_t e = cudaFuncSetAttribute(k_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int nGroups = (a.nBuckets + GG_WALK_GB - 1) / GG_WALK_GB;
@@ -1084,8 +1086,8 @@ cudaError_t gg_launch_scatter_kernel(const TreeKernelArgs &a, int nSM, cudaStrea
     return cudaGetLastError();
 }
 
-size_t gg_eval_kernel_smem(int mono64) {
-    return GG_WARPS_PER_CTA * (mono64 ? sizeof(EvalSmemT<2>) : sizeof(EvalSmemT<1>)) + GG_MAX_IMAGES * 3 * sizeof(double);
+size_t gg_eval_kernel_smem(int mono64, int nImages) {
+    return GG_WARPS_PER_CTA * (mono64 ? sizeof(EvalSmemT<2>) : sizeof(EvalSmemT<1>)) + image_table_bytes(nImages);
 }
 
 cudaError_t gg_launch_eval_kernel(const TreeKernelArgs &a, int nSM, cudaStream_t st) {
@@ -1105,7 +1107,7 @@ cudaError_t gg_launch_eval_kernel(const TreeKernelArgs &a, int nSM, cudaStream_t
         default: fn = k_eval<4, false>; break;
         }
     }
-    const size_t smem = gg_eval_kernel_smem(a.mono64);
+    const size_t smem = gg_eval_kernel_smem(a.mono64, a.nImages);
     cudaError_t e = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int grid = grid_for((const void *)fn, GG_WARPS_PER_CTA * 32, smem, nSM, GG_WARPS_PER_CTA, a.nTasks, &e);

@@ -12,6 +12,10 @@ pytestmark = pytest.mark.gpu
 CASES = {
     "c1_periodic32_ewald": (lambda: ics.periodic_box(32), 0.7, GravityParams(nReps=1, bPeriodic=1, bEwald=1)),
     "periodic16_jitter": (lambda: ics.periodic_box(16, mode="jitter"), 0.7, GravityParams(nReps=1, bPeriodic=1)),
+    # nReplicas = 2 (125 images, 7 image bits) and 3 (343 images, 9 bits; Ewald's hole follows nReps, ewald.c:60-70)
+    "periodic10_nreps2_ewald": (lambda: ics.periodic_box(10), 0.7, GravityParams(nReps=2, bPeriodic=1, bEwald=1)),
+    "periodic8_nreps3_ewald": (lambda: ics.periodic_box(8), 0.7, GravityParams(nReps=3, bPeriodic=1, bEwald=1)),
+    "periodic8_nreps3_noewald": (lambda: ics.periodic_box(8, mode="jitter"), 0.6, GravityParams(nReps=3, bPeriodic=1, bEwald=0)),
     "plummer20k": (lambda: ics.plummer(20000), 0.7, GravityParams(nReps=0, bPeriodic=0, bEwald=0)),
     "plummer50k_theta05": (lambda: ics.plummer(50000), 0.5, GravityParams(nReps=0, bPeriodic=0, bEwald=0)),
 }

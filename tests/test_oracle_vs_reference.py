@@ -11,6 +11,8 @@ pytestmark = pytest.mark.skipif(not reflib.available(), reason="oracle/_ref/libg
 CASES = {
     "periodic16_ewald": (lambda: ics.periodic_box(16), 0.7, dict(nReps=1, bPeriodic=1, bEwald=1)),
     "periodic12_theta04": (lambda: ics.periodic_box(12, seed=9), 0.4, dict(nReps=1, bPeriodic=1, bEwald=1)),
+    "periodic8_nreps3_ewald": (lambda: ics.periodic_box(8), 0.7, dict(nReps=3, bPeriodic=1, bEwald=1)),
+    "periodic10_nreps2_noewald": (lambda: ics.periodic_box(10), 0.7, dict(nReps=2, bPeriodic=1, bEwald=0)),
     "plummer20k": (lambda: ics.plummer(20000), 0.7, dict(nReps=0, bPeriodic=0, bEwald=0)),
     "plummer8k_theta03": (lambda: ics.plummer(8000, seed=2), 0.3, dict(nReps=0, bPeriodic=0, bEwald=0)),
 }
