@@ -505,3 +505,29 @@ void ref_gravity_sun(REF *r, int iOrder, double dSunSoft, double *aSun3, int *su
     g_sunCounts = NULL;
     for (j = 0; j < 3; ++j) aSun3[j] = out.aSun[j];
 }
+
+/*
+ * pstGravity with bComove = 1 on open boundaries (pkd.c:2967-2991: acceleration and potential of the uniform negative
+ * background, a += dRhoFac r, fPot -= dRhoFac r^2 / 2 on ACTIVE particles, added per bucket right after its interactions).
+ */
+void ref_gravity_comove(REF *r, int iOrder, double dRhoFac, double *acc3, double *pot) {
+    struct inGravity in;
+    struct outGravity out;
+    int i, iDum;
+    memset(&in, 0, sizeof(in));
+    in.iOrder = iOrder;
+    in.iEwOrder = iOrder;
+    in.bComove = 1;
+    in.dRhoFac = dRhoFac;
+    in.dEwCut = 2.6;
+    in.dEwhCut = 2.8;
+    pkdInitAccel(r->pkd);
+    pstGravity(r->pst, &in, sizeof(in), &out, &iDum);
+    for (i = 0; i < r->n; ++i) {
+        PARTICLE *p = &r->pkd->pStore[i];
+        acc3[3 * (size_t)i + 0] = p->a[0];
+        acc3[3 * (size_t)i + 1] = p->a[1];
+        acc3[3 * (size_t)i + 2] = p->a[2];
+        pot[i] = p->fPot;
+    }
+}

@@ -52,6 +52,7 @@ def lib(gpu_host: bool = False):
         L.ref_step_ops.argtypes = [C.c_int, _dp, _dp, _dp, C.c_void_p, _dp, _dp, C.c_double, C.c_double, C.c_double,
                                    _dp, C.c_int, _dp, C.c_double, C.c_int]
         L.ref_gravity_sun.argtypes = [C.c_void_p, C.c_int, C.c_double, _dp, _ip]
+        L.ref_gravity_comove.argtypes = [C.c_void_p, C.c_int, C.c_double, _dp, _dp]
         from oracle.oracle import RUNG_ARGTYPES
         L.ref_rung_ops.restype = None
         L.ref_rung_ops.argtypes = RUNG_ARGTYPES
@@ -133,6 +134,12 @@ class RefGravity:
         return dict(acc=acc, pot=pot, dtGrav=dt, fWeight=w, counts=counts, nActive=int(stats[0]),
                     dPartSum=float(stats[1]), dCellSum=float(stats[2]), dSoftSum=float(stats[3]),
                     dFlop=float(stats[4]), seconds=float(stats[5]))
+
+    def gravity_comove(self, dRhoFac, iOrder=4):
+        """pstGravity with bComove=1 on open boundaries (pkd.c:2967-2991): (acc, pot) in tree order."""
+        acc, pot = np.zeros((self.n, 3)), np.zeros(self.n)
+        self._L.ref_gravity_comove(self.h, iOrder, float(dRhoFac), acc, pot)
+        return acc, pot
 
     def gravity_sun(self, dSunSoft, iOrder=4):
         """pstGravity with bDoSun=1 (pkd.c:3003-3041): (aSun[3], (nPart, nCellSoft, nCellNewt) of the dummy bucket)."""

@@ -1,4 +1,4 @@
-"""Golden vectors for bDoSun (pkd.c:3003-3041: the indirect acceleration at the origin, a dummy sink of softening dSunSoft)
+"""Golden vectors for bDoSun and bComove (pkd.c:3003-3041: the indirect acceleration at the origin, a dummy sink of softening dSunSoft)
 from the COMPILED REFERENCE.  Run where /root/reference exists:  python tests/golden/make_golden_sun.py"""
 import os
 import sys
@@ -37,6 +37,14 @@ if __name__ == "__main__":
         out[name + "_aSun"], out[name + "_counts"], out[name + "_sums"] = a, c3, np.array(
             [plain["nActive"], plain["dPartSum"], plain["dCellSum"], plain["dSoftSum"], plain["dFlop"]])
         print(name, a, c3)
+    # bComove (pkd.c:2967-2991) on the first case, partially active
+    p, theta, _ = case("inside")
+    active = (np.arange(p.n) % 3 != 0).astype(np.int32)
+    r = reflib.RefGravity(p, active=active)
+    r.build_tree(8, theta, 4)
+    out["comove_acc"], out["comove_pot"] = r.gravity_comove(0.37)
+    out["comove_active"] = r.tree()["active"]
+    r.close()
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "sun.npz")
     np.savez_compressed(path, **out)
     print("wrote", path)

@@ -67,3 +67,26 @@ def test_sun_through_the_reference_host(gpu_lib):
     r.close()
     ref = GOLD["inside_aSun"]
     assert np.linalg.norm(a - ref) / np.linalg.norm(ref) <= MAX_TOL
+
+
+def test_comove_background_term(gpu_lib):
+    """bComove && !bPeriodic (pkd.c:2967-2991): a += dRhoFac r, fPot -= dRhoFac r^2 / 2 on ACTIVE particles, against the
+    compiled reference's pstGravity (golden), partially active."""
+    from parity import RMS_TOL, acc_errors, pot_errors
+    p, theta, _ = case("inside")
+    active = (np.arange(p.n) % 3 != 0).astype(np.int32)
+    pkd = PKD()
+    pkd.pkdLoadParticles(p.x, p.y, p.z, p.m, p.h, active)
+    pkd.pkdBuildBinary(8, theta, 4)
+    assert np.array_equal(pkd.active, GOLD["comove_active"])
+    out = pkd.pkdGravAll(GravityParams(nReps=0, bPeriodic=0, bEwald=0, bComove=1, dRhoFac=0.37))
+    plain = pkd.pkdGravAll(GravityParams(nReps=0, bPeriodic=0, bEwald=0))
+    act = pkd.active != 0
+    rms, mx = acc_errors(out["acc"][act], GOLD["comove_acc"][act])
+    prms, pmx = pot_errors(out["pot"][act], GOLD["comove_pot"][act])
+    print(f"comove: acc rms {rms:.2e} max {mx:.2e}; pot rms {prms:.2e} max {pmx:.2e}")
+    assert rms <= RMS_TOL and mx <= MAX_TOL and prms <= RMS_TOL and pmx <= MAX_TOL
+    r = np.stack([pkd.x, pkd.y, pkd.z], axis=1)
+    assert np.allclose((out["acc"] - plain["acc"])[act], 0.37 * r[act], rtol=1e-12, atol=1e-13)
+    assert np.all(out["acc"][~act] == 0) and np.all(GOLD["comove_acc"][~act] == 0)
+    pkd.close()
