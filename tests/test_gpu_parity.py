@@ -16,6 +16,11 @@ CASES = {
     "periodic10_nreps2_ewald": (lambda: ics.periodic_box(10), 0.7, GravityParams(nReps=2, bPeriodic=1, bEwald=1)),
     "periodic8_nreps3_ewald": (lambda: ics.periodic_box(8), 0.7, GravityParams(nReps=3, bPeriodic=1, bEwald=1)),
     "periodic8_nreps3_noewald": (lambda: ics.periodic_box(8, mode="jitter"), 0.6, GravityParams(nReps=3, bPeriodic=1, bEwald=0)),
+    # lower multipole orders of the lists (QEVAL fallthrough, qeval.h:21-64) and of the Ewald root expansion (meval.h:21-81)
+    "plummer8k_order1": (lambda: ics.plummer(8000, seed=6), 0.7, GravityParams(nReps=0, bPeriodic=0, bEwald=0, iOrder=1)),
+    "plummer8k_order3": (lambda: ics.plummer(8000, seed=6), 0.7, GravityParams(nReps=0, bPeriodic=0, bEwald=0, iOrder=3)),
+    "periodic10_order2_ewald2": (lambda: ics.periodic_box(10), 0.7, GravityParams(nReps=1, bPeriodic=1, bEwald=1, iOrder=2, iEwOrder=2)),
+    "periodic10_order4_ewald3": (lambda: ics.periodic_box(10), 0.7, GravityParams(nReps=1, bPeriodic=1, bEwald=1, iOrder=4, iEwOrder=3)),
     "plummer20k": (lambda: ics.plummer(20000), 0.7, GravityParams(nReps=0, bPeriodic=0, bEwald=0)),
     "plummer50k_theta05": (lambda: ics.plummer(50000), 0.5, GravityParams(nReps=0, bPeriodic=0, bEwald=0)),
 }

@@ -13,6 +13,10 @@ CASES = {
     "periodic12_theta04": (lambda: ics.periodic_box(12, seed=9), 0.4, dict(nReps=1, bPeriodic=1, bEwald=1)),
     "periodic8_nreps3_ewald": (lambda: ics.periodic_box(8), 0.7, dict(nReps=3, bPeriodic=1, bEwald=1)),
     "periodic10_nreps2_noewald": (lambda: ics.periodic_box(10), 0.7, dict(nReps=2, bPeriodic=1, bEwald=0)),
+    "plummer8k_order1": (lambda: ics.plummer(8000, seed=6), 0.7, dict(nReps=0, bPeriodic=0, bEwald=0, iOrder=1)),
+    "plummer8k_order3": (lambda: ics.plummer(8000, seed=6), 0.7, dict(nReps=0, bPeriodic=0, bEwald=0, iOrder=3)),
+    "periodic10_order2_ewald2": (lambda: ics.periodic_box(10), 0.7, dict(nReps=1, bPeriodic=1, bEwald=1, iOrder=2, iEwOrder=2)),
+    "periodic10_order4_ewald3": (lambda: ics.periodic_box(10), 0.7, dict(nReps=1, bPeriodic=1, bEwald=1, iOrder=4, iEwOrder=3)),
     "plummer20k": (lambda: ics.plummer(20000), 0.7, dict(nReps=0, bPeriodic=0, bEwald=0)),
     "plummer8k_theta03": (lambda: ics.plummer(8000, seed=2), 0.3, dict(nReps=0, bPeriodic=0, bEwald=0)),
 }
@@ -23,9 +27,10 @@ def test_live_reference(name):
     mk, theta, kw = CASES[name]
     p = mk()
     r = reflib.RefGravity(p); r.build_tree(8, theta, 4); tr = r.tree()
-    rr = r.gravity(kw["nReps"], kw["bPeriodic"], 4, kw["bEwald"], 4); r.close()
+    io, ie = kw.get("iOrder", 4), kw.get("iEwOrder", 4)
+    rr = r.gravity(kw["nReps"], kw["bPeriodic"], io, kw["bEwald"], ie); r.close()
     o = oracle.OracleGravity(p); o.build_tree(8, theta, 4); to = o.tree()
-    ro = o.gravity(kw["nReps"], kw["bPeriodic"], 4, kw["bEwald"], 4); o.close()
+    ro = o.gravity(kw["nReps"], kw["bPeriodic"], io, kw["bEwald"], ie); o.close()
     for k in ("bnd", "r", "fMass", "fSoft", "fOpen2", "mom", "pLower", "pUpper", "iLower", "iUpper", "iOrder", "root"):
         assert np.array_equal(tr[k], to[k]), k
     assert np.array_equal(rr["counts"], ro["counts"])
