@@ -153,3 +153,37 @@ def test_ewald_table_matches_oracle(gpu_lib):
     assert got.shape == want.shape == (80, 5)
     assert np.allclose(got, want, rtol=1e-12, atol=1e-300)
     pkd.close()
+
+
+def test_edge_cases_no_active_one_active_coincident(gpu_lib):
+    """Ragged inputs: a call with no ACTIVE particle (a rung with nobody on it), with exactly one, and a particle set
+    with coincident particles (zero-extent buckets, zero-distance softened pairs) -- each against the oracle."""
+    p = ics.plummer(4000, seed=14)
+    g = GravityParams(nReps=0, bPeriodic=0, bEwald=0)
+    none = np.zeros(p.n, np.int32)
+    pkd, out, counts = run_gpu(p, 0.7, g, none)
+    assert out["nActive"] == 0 and out["dPartSum"] == 0 and out["dCellSum"] == 0 and out["dFlop"] == 0
+    assert np.all(out["acc"] == 0) and np.all(out["pot"] == 0) and np.all(counts == -1)
+    pkd.close()
+    one = none.copy()
+    one[1234] = 1
+    t, ref = run_oracle(p, 0.7, g, one)
+    pkd, out, counts = run_gpu(p, 0.7, g, one)
+    assert np.array_equal(counts, ref["counts"]) and out["nActive"] == 1 and out["dFlop"] == ref["dFlop"]
+    act = t["active"].astype(bool)
+    rms, mx = acc_errors(out["acc"][act], ref["acc"][act])
+    assert mx <= MAX_TOL and np.all(out["acc"][~act] == 0)
+    pkd.close()
+    x, y, z = p.x.copy(), p.y.copy(), p.z.copy()
+    idx = np.arange(0, p.n - 1, 5)
+    x[idx], y[idx], z[idx] = x[idx + 1], y[idx + 1], z[idx + 1]
+    q = ics.Particles(x, y, z, p.m, p.h, p.period, "coincident")
+    t, ref = run_oracle(q, 0.7, g)
+    pkd, out, counts = run_gpu(q, 0.7, g)
+    assert np.array_equal(counts, ref["counts"]) and out["dFlop"] == ref["dFlop"]
+    assert np.all(np.isfinite(out["acc"])) and np.all(np.isfinite(out["pot"]))
+    rms, mx = acc_errors(out["acc"], ref["acc"])
+    prms, pmx = pot_errors(out["pot"], ref["pot"])
+    print(f"coincident pairs: acc rms {rms:.3e} max {mx:.3e}; pot rms {prms:.3e} max {pmx:.3e}")
+    assert rms <= RMS_TOL and mx <= MAX_TOL and prms <= RMS_TOL and pmx <= MAX_TOL
+    pkd.close()
