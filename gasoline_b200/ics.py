@@ -12,6 +12,7 @@ Units G=1.  Everything is numpy on the host; this is input generation, not the t
 """
 from __future__ import annotations
 
+import os
 import struct
 from dataclasses import dataclass
 
@@ -113,3 +114,46 @@ def read_array_binary(path: str, ndim: int) -> np.ndarray:
         n = struct.unpack("=i", f.read(4))[0]
         a = np.fromfile(f, dtype=np.float64, count=n * ndim)
     return a.reshape(ndim, n).T.copy()
+
+
+def read_tipsy_native(path: str) -> Particles:
+    """Read the dark particles of a native Tipsy file (what pkdReadTipsy pkd.c:297 does: float32 on disk, widened to
+    double, pkd.c:686-695).  Gas / star records are skipped; open boundaries are assumed (the period is a run parameter)."""
+    with open(path, "rb") as f:
+        time, n, ndim, nsph, ndark, nstar = struct.unpack("=diiiii", f.read(28))
+        f.read(4)  # header padding to 32 bytes (pkd.c:262-263)
+        f.seek(48 * nsph, 1)  # gas records: 12 float32 (tipsydefs.h:9-15)
+        rec = np.fromfile(f, dtype=np.float32, count=9 * ndark).reshape(ndark, 9).astype(np.float64)
+    return Particles(rec[:, 1].copy(), rec[:, 2].copy(), rec[:, 3].copy(), rec[:, 0].copy(), rec[:, 7].copy(),
+                     (FLOAT_MAXVAL,) * 3, os.path.basename(path))
+
+
+def write_array_binary(path: str, a) -> None:
+    """The reference's binary array output, iBinaryOutput=2 (master.c:5527, outtype.c:1001-1012): int N, then all first
+    components, all second, ... as native doubles.  a: (N,) for a scalar (.pot, .dt) or (N, 3) for a vector (.accg)."""
+    a = np.asarray(a, dtype=np.float64)
+    a = a.reshape(a.shape[0], -1)
+    with open(path, "wb") as f:
+        f.write(struct.pack("=i", a.shape[0]))
+        np.ascontiguousarray(a.T).tofile(f)
+
+
+def write_array_ascii(path: str, a, interleaved: bool = True) -> None:
+    """The reference's ASCII array output, iBinaryOutput=0: "N\n", then one value per line in %.14g.  A vector written by
+    one node (msrOneNodeOutVector, master.c:5420: iDim = -3) comes particle by particle -- x, y, z of particle 0, then of
+    particle 1, ... (outtype.c:949-957); interleaved=False gives the per-component order of the parallel writer
+    (outtype.c:958-963: all first components, then all second, ...).  Scalars (.pot, .dt) are the same either way."""
+    a = np.asarray(a, dtype=np.float64)
+    a = a.reshape(a.shape[0], -1)
+    v = a.ravel() if interleaved else a.T.ravel()
+    with open(path, "w") as f:
+        f.write(f"{a.shape[0]}\n")
+        f.write("".join("%.14g\n" % x for x in v))
+
+
+def read_array_ascii(path: str, ndim: int, interleaved: bool = True) -> np.ndarray:
+    """Inverse of write_array_ascii: returns (N, ndim)."""
+    with open(path) as f:
+        n = int(f.readline())
+        v = np.array([float(x) for x in f.read().split()], dtype=np.float64)
+    return v.reshape(n, ndim).copy() if interleaved else v.reshape(ndim, n).T.copy()
