@@ -56,6 +56,8 @@ typedef struct {
     int *iDim, *order;
     PARTICLE *tmp; /* pStore permutation scratch, kept between builds (fresh pages cost more than the copy) */
     size_t capTmp;
+    const KDN *builtNodes; /* pkd->kdNodes as our pkdBuildBinary left it (NULL: the device holds no tree of this host) */
+    int builtN;
 } SHIM;
 
 static SHIM g_shim[64]; /* one per MDL rank living in this process (pthread-MDL ranks are threads) */
@@ -256,6 +258,7 @@ void pkdGravAll(PKD pkd, int nReps, int bPeriodic, int iOrder, int bEwald, int i
     t.pLower = s->pLower; t.pUpper = s->pUpper; t.iLower = s->iLower; t.iUpper = s->iUpper;
     pp.n = n; pp.x = s->x; pp.y = s->y; pp.z = s->z; pp.fMass = s->m; pp.fSoft = s->h; pp.active = s->active;
     if (gg_set_local(s->ctx, pkd->idSelf, &t, &pp) != GG_OK) die("gg_set_local");
+    s->builtNodes = NULL; /* the device now holds the host's arrays, not a tree it built itself (see pkdCalcRoot below) */
     if (bPeriodic && bEwald) {
         double root[GG_NROOT];
         const ILCN *R = &pkd->ilcnRoot;
@@ -347,6 +350,7 @@ void pkdBuildBinary(PKD pkd, int nBucket, int iOpenType, double dCrit, int iOrde
 
     if (!e || !atoi(e) || iOpenType != OPEN_JOSH || !bGravity || pkd->nLocal < 1 || nBucket > GG_MAX_BUCKET ||
         (bTreeActiveOnly && pkd->nTreeActive != pkd->nLocal) || mdlThreads(pkd->mdl) != 1) {
+        if (pkd->idSelf >= 0 && pkd->idSelf < 64) g_shim[pkd->idSelf].builtNodes = NULL;
         pkdBuildBinary_cpu(pkd, nBucket, iOpenType, dCrit, iOrder, bTreeActiveOnly, bGravity, pRoot);
         return;
     }
@@ -393,4 +397,32 @@ void pkdBuildBinary(PKD pkd, int nBucket, int iOpenType, double dCrit, int iOrde
     pkd->iRoot = 0;
     *pRoot = pkd->kdNodes[pkd->iRoot];
     mdlROcache(pkd->mdl, CID_CELL, pkd->kdNodes, sizeof(KDN), pkdNodes(pkd));
+    s->builtNodes = pkd->kdNodes;
+    s->builtN = nNodes;
+}
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * pkdCalcRoot (pkd.c:4395-4470): the complete l = 3, 4 moments of the rank's particles about its root centre, one host
+ * pass over pStore (~25 ms per million particles).  When the tree in pkd->kdNodes is the one our pkdBuildBinary just built
+ * -- same array, same size, and the device's root cell equal to the host's bit for bit -- they are read from the
+ * device's raw moment record of the root instead (gg_domain_summary; same sums in another order, ~1e-15 relative).
+ */
+void pkdCalcRoot_cpu(PKD pkd, struct ilCellNewt *pcc); /* the host's own, renamed by -DpkdCalcRoot=pkdCalcRoot_cpu */
+
+void pkdCalcRoot(PKD pkd, struct ilCellNewt *pcc) {
+    SHIM *s = (pkd->idSelf >= 0 && pkd->idSelf < 64) ? &g_shim[pkd->idSelf] : NULL;
+    if (s && s->ctx && s->builtNodes && s->builtNodes == pkd->kdNodes && s->builtN == pkd->nNodes) {
+        double root[GG_NROOT], r[3], fMass;
+        const KDN *c = &pkd->kdNodes[pkd->iRoot];
+        if (gg_domain_summary(s->ctx, NULL, r, &fMass, NULL, NULL, NULL, root) == GG_OK && r[0] == c->r[0] &&
+            r[1] == c->r[1] && r[2] == c->r[2] && fMass == c->fMass) {
+            pcc->xxx = root[10]; pcc->xyy = root[11]; pcc->xxy = root[12]; pcc->yyy = root[13]; pcc->xxz = root[14];
+            pcc->yyz = root[15]; pcc->xyz = root[16]; pcc->xzz = root[17]; pcc->yzz = root[18]; pcc->zzz = root[19];
+            pcc->xxxx = root[20]; pcc->xyyy = root[21]; pcc->xxxy = root[22]; pcc->yyyy = root[23]; pcc->xxxz = root[24];
+            pcc->yyyz = root[25]; pcc->xxyy = root[26]; pcc->xxyz = root[27]; pcc->xyyz = root[28]; pcc->xxzz = root[29];
+            pcc->xyzz = root[30]; pcc->xzzz = root[31]; pcc->yyzz = root[32]; pcc->yzzz = root[33]; pcc->zzzz = root[34];
+            return;
+        }
+    }
+    pkdCalcRoot_cpu(pkd, pcc);
 }
