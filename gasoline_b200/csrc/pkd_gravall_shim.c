@@ -156,6 +156,12 @@ static void flatten_particles(void *arg, size_t lo, size_t hi) {
     }
 }
 
+static void flatten_active(void *arg, size_t lo, size_t hi) {
+    PASS *a = (PASS *)arg;
+    size_t i;
+    for (i = lo; i < hi; ++i) a->s->active[i] = TYPEQueryACTIVE(&a->pkd->pStore[i]) ? 1 : 0;
+}
+
 /* a, fPot += ; dtGrav = max ; fWeight = : what pkdBucketInteract / pkdBucketEwald / pkdBucketWeight leave in pStore
  * (grav.c:100,192-195, ewald.c:166-170, pkd.c:2851-2861), ACTIVE particles only */
 static void write_back(void *arg, size_t lo, size_t hi) {
@@ -234,7 +240,7 @@ void pkdGravAll(PKD pkd, int nReps, int bPeriodic, int iOrder, int bEwald, int i
     gg_params prm;
     gg_stats st;
     PASS pass;
-    int j;
+    int j, bResident;
 
     mdlassert(pkd->mdl, mdlThreads(pkd->mdl) == 1);
     mdlassert(pkd->mdl, pkd->idSelf >= 0 && pkd->idSelf < 64);
@@ -250,15 +256,29 @@ void pkdGravAll(PKD pkd, int nReps, int bPeriodic, int iOrder, int bEwald, int i
 
     pass.pkd = pkd; pass.s = s;
     pass.bMom = getenv("GG_SHIM_HOST_MOMENTS") != NULL && atoi(getenv("GG_SHIM_HOST_MOMENTS")) != 0;
-    parallel_for((size_t)nNodes, flatten_nodes, &pass);
-    parallel_for((size_t)n, flatten_particles, &pass);
-    t.nNodes = nNodes; t.iRoot = pkd->iRoot;
-    t.bnd = s->bnd; t.r = s->r; t.fMass = s->fMass; t.fSoft = s->fSoft; t.fOpen2 = s->fOpen2;
-    t.mom = pass.bMom ? s->mom : NULL;
-    t.pLower = s->pLower; t.pUpper = s->pUpper; t.iLower = s->iLower; t.iUpper = s->iUpper;
-    pp.n = n; pp.x = s->x; pp.y = s->y; pp.z = s->z; pp.fMass = s->m; pp.fSoft = s->h; pp.active = s->active;
-    if (gg_set_local(s->ctx, pkd->idSelf, &t, &pp) != GG_OK) die("gg_set_local");
-    s->builtNodes = NULL; /* the device now holds the host's arrays, not a tree it built itself (see pkdCalcRoot below) */
+    bResident = 0;
+    if (s->builtNodes && s->builtNodes == pkd->kdNodes && s->builtN == nNodes && !pass.bMom) {
+        /* kdNodes is the tree our pkdBuildBinary built and the device still holds it (same array, same size, root cell
+         * equal bit for bit): nothing but the ACTIVE flags -- which msrActiveRung may have changed since -- goes up */
+        double r[3], fMass;
+        const KDN *c = &pkd->kdNodes[pkd->iRoot];
+        bResident = gg_domain_summary(s->ctx, NULL, r, &fMass, NULL, NULL, NULL, NULL) == GG_OK && r[0] == c->r[0] &&
+                    r[1] == c->r[1] && r[2] == c->r[2] && fMass == c->fMass;
+    }
+    if (bResident) {
+        parallel_for((size_t)n, flatten_active, &pass);
+        if (gg_set_active(s->ctx, s->active) != GG_OK) die("gg_set_active");
+    } else {
+        parallel_for((size_t)nNodes, flatten_nodes, &pass);
+        parallel_for((size_t)n, flatten_particles, &pass);
+        t.nNodes = nNodes; t.iRoot = pkd->iRoot;
+        t.bnd = s->bnd; t.r = s->r; t.fMass = s->fMass; t.fSoft = s->fSoft; t.fOpen2 = s->fOpen2;
+        t.mom = pass.bMom ? s->mom : NULL;
+        t.pLower = s->pLower; t.pUpper = s->pUpper; t.iLower = s->iLower; t.iUpper = s->iUpper;
+        pp.n = n; pp.x = s->x; pp.y = s->y; pp.z = s->z; pp.fMass = s->m; pp.fSoft = s->h; pp.active = s->active;
+        if (gg_set_local(s->ctx, pkd->idSelf, &t, &pp) != GG_OK) die("gg_set_local");
+        s->builtNodes = NULL; /* the device now holds the host's arrays, not a tree it built itself (see pkdCalcRoot below) */
+    }
     if (bPeriodic && bEwald) {
         double root[GG_NROOT];
         const ILCN *R = &pkd->ilcnRoot;
