@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libgasoline_b200.so")
-SOURCES = ["gg_api.cu", "gg_tree_kernel.cu", "gg_ewald.cu", "gg_moments.cu", "gg_tree_gpu.cu", "gg_state.cu", "gg_tree_build.cpp"]
+SOURCES = ["gg_api.cu", "gg_tree_kernel.cu", "gg_ewald.cu", "gg_moments.cu", "gg_tree_gpu.cu", "gg_state.cu", "gg_orb.cu", "gg_tree_build.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-pthread", "--use_fast_math=false"]
 

@@ -88,6 +88,11 @@ struct gg_context {
     int stateN = 0;
     bool stateHasActive = false, stateDirty = true, stateForces = false;
     bool sunMode = false; // run_gravity is evaluating the bDoSun dummy bucket: the particles' results stay as they are
+    // ORB domain decomposition services (gg_orb_*): the rank's particles for the decomposition and their PST cell
+    DevBuf ox, oy, oz, ow, ocell, okeys, ocnt, opart, osums;
+    int orbN = -1;          // -1: gg_orb_load not called
+    bool orbState = false;  // positions are the resident store's (sx, sy, sz)
+    bool orbWeights = false;
 };
 
 namespace {
@@ -590,7 +595,8 @@ void gg_destroy(gg_context *c) {
                      &c->nextblk, &c->poolmask, &c->isb, &c->boffs, &c->bnode, &c->ghead, &c->gcnt, &c->bcnt, &c->btot,
                      &c->boff64, &c->lists, &c->letflag, &c->letfront, &c->letidx, &c->letout, &c->letmisc, &c->momraw,
                      &c->mparent, &c->dbgtask, &c->momout, &c->sx, &c->sy, &c->sz, &c->sm, &c->sh, &c->sact, &c->svel, &c->sid, &c->sdt,
-                     &c->svel2, &c->sid2, &c->sdt2, &c->sacc, &c->srhist};
+                     &c->svel2, &c->sid2, &c->sdt2, &c->sacc, &c->srhist, &c->ox, &c->oy, &c->oz, &c->ow, &c->ocell,
+                     &c->okeys, &c->ocnt, &c->opart, &c->osums};
     for (DevBuf *b : all)
         if (b->p) cudaFree(b->p);
     if (c->pinned) cudaFreeHost(c->pinned);
@@ -716,6 +722,136 @@ int gg_build_local(gg_context *c, int idSelf, const gg_particles *pp, int nBucke
     CK(cudaSetDevice(c->device));
     c->stateN = 0; // a tree built from host particles replaces any resident store
     return build_and_load(c, idSelf, pp, nBucket, dTheta, iOrder, pnNodes, root);
+}
+
+
+// ---- ORB domain decomposition: the per-rank services of pstDomainDecomp on the device ----
+
+namespace {
+int orb_query(const char *who, gg_context *c, int nCells, const int *iCell, const int *iDim, const double *fSplit, OrbQuery &q) {
+    if (!c || c->orbN < 0) return fail(GG_ERR_ARG, "%s: no particles loaded (gg_orb_load)", who);
+    if (nCells < 1 || nCells > GG_ORB_MAX_SLOTS || !iCell) return fail(GG_ERR_ARG, "%s: nCells=%d (1..%d)", who, nCells, GG_ORB_MAX_SLOTS);
+    q.nSlots = nCells;
+    for (int s = 0; s < nCells; ++s) {
+        if (iCell[s] < 1 || iCell[s] >= GG_ORB_MAX_CELL) return fail(GG_ERR_ARG, "%s: PST cell %d outside 1..%d", who, iCell[s], GG_ORB_MAX_CELL - 1);
+        for (int t = 0; t < s; ++t)
+            if (iCell[t] == iCell[s]) return fail(GG_ERR_ARG, "%s: PST cell %d asked about twice", who, iCell[s]);
+        q.cell[s] = iCell[s];
+        q.dim[s] = iDim ? iDim[s] : 0;
+        q.split[s] = fSplit ? fSplit[s] : 0.0;
+        if (q.dim[s] < 0 || q.dim[s] > 2) return fail(GG_ERR_ARG, "%s: split axis %d", who, q.dim[s]);
+    }
+    return GG_OK;
+}
+const double *orb_pos(gg_context *c, int k) {
+    DevBuf *own[] = {&c->ox, &c->oy, &c->oz}, *st[] = {&c->sx, &c->sy, &c->sz};
+    return (const double *)(c->orbState ? st[k]->p : own[k]->p);
+}
+} // namespace
+
+int gg_orb_load(gg_context *c, int n, const double *x, const double *y, const double *z, const double *fWeight) {
+    if (!c || n < 0) return fail(GG_ERR_ARG, "gg_orb_load: bad argument (n=%d)", n);
+    CK(cudaSetDevice(c->device));
+    int rc;
+    const bool fromState = !x && !y && !z;
+    if (fromState) {
+        if (c->stateN < 1 || n != c->stateN) return fail(GG_ERR_ARG, "gg_orb_load: x == NULL means the resident store, which holds %d particles (n=%d)", c->stateN, n);
+    } else if (n > 0 && (!x || !y || !z)) return fail(GG_ERR_ARG, "gg_orb_load: x, y, z must all be given (or all NULL)");
+    const size_t nb = sizeof(double) * (size_t)(n > 0 ? n : 1);
+    if (!fromState) {
+        const double *src[] = {x, y, z};
+        DevBuf *dst[] = {&c->ox, &c->oy, &c->oz};
+        for (int k = 0; k < 3; ++k) {
+            if ((rc = ensure(c, *dst[k], nb))) return rc;
+            if (n > 0) CK(cudaMemcpyAsync(dst[k]->p, src[k], sizeof(double) * (size_t)n, cudaMemcpyDefault, c->st));
+        }
+    }
+    if (fWeight) {
+        if ((rc = ensure(c, c->ow, nb))) return rc;
+        if (n > 0) CK(cudaMemcpyAsync(c->ow.p, fWeight, sizeof(double) * (size_t)n, cudaMemcpyDefault, c->st));
+    }
+    if ((rc = ensure(c, c->ocell, sizeof(int) * (size_t)(n > 0 ? n : 1))) || (rc = ensure(c, c->okeys, sizeof(unsigned long long) * 6 * GG_ORB_MAX_SLOTS)) ||
+        (rc = ensure(c, c->ocnt, sizeof(int) * 2 * GG_ORB_MAX_SLOTS)) || (rc = ensure(c, c->osums, sizeof(double) * 2 * GG_ORB_MAX_SLOTS)) ||
+        (rc = ensure(c, c->opart, gg_orb_part_bytes(n))))
+        return rc;
+    CK(gg_launch_orb_init(n, (int *)c->ocell.p, c->st));
+    ++c->nLaunches;
+    CK(cudaStreamSynchronize(c->st));
+    c->orbN = n;
+    c->orbState = fromState;
+    c->orbWeights = fWeight != nullptr;
+    return GG_OK;
+}
+
+int gg_orb_bounds(gg_context *c, int nCells, const int *iCell, double *bnd, int *nIn) {
+    OrbQuery q;
+    int rc;
+    if ((rc = orb_query("gg_orb_bounds", c, nCells, iCell, nullptr, nullptr, q))) return rc;
+    if (!bnd || !nIn) return fail(GG_ERR_ARG, "gg_orb_bounds: bnd and nIn must be given");
+    CK(cudaSetDevice(c->device));
+    CK(gg_launch_orb_bounds(q, c->orbN, orb_pos(c, 0), orb_pos(c, 1), orb_pos(c, 2), (const int *)c->ocell.p,
+                            (unsigned long long *)c->okeys.p, (int *)c->ocnt.p, c->st));
+    ++c->nLaunches;
+    unsigned long long keys[6 * GG_ORB_MAX_SLOTS];
+    CK(cudaMemcpyAsync(keys, c->okeys.p, sizeof(unsigned long long) * 6 * nCells, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(nIn, c->ocnt.p, sizeof(int) * nCells, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    for (int i = 0; i < 6 * nCells; ++i) {
+        const unsigned long long k = keys[i];
+        const long long b = (k & 0x8000000000000000ull) ? (long long)(k & 0x7fffffffffffffffull) : (long long)~k;
+        memcpy(&bnd[i], &b, 8);
+    }
+    // a cell without particles of this rank: fMin = +FLOAT_MAXVAL, fMax = -FLOAT_MAXVAL like pkdCalcBound (pkd.c:1304-1330)
+    for (int s = 0; s < nCells; ++s)
+        if (nIn[s] == 0)
+            for (int k = 0; k < 6; ++k) bnd[6 * s + k] = k < 3 ? 1.7976931348623157e308 : -1.7976931348623157e308;
+    return GG_OK;
+}
+
+int gg_orb_weight(gg_context *c, int nCells, const int *iCell, const int *iDim, const double *fSplit, int *nLow, int *nHigh,
+                  double *fLow, double *fHigh) {
+    OrbQuery q;
+    int rc;
+    if (!iDim || !fSplit || !nLow || !nHigh || !fLow || !fHigh) return fail(GG_ERR_ARG, "gg_orb_weight: NULL argument");
+    if ((rc = orb_query("gg_orb_weight", c, nCells, iCell, iDim, fSplit, q))) return rc;
+    CK(cudaSetDevice(c->device));
+    const double *w = c->orbWeights ? (const double *)c->ow.p : nullptr;
+    CK(gg_launch_orb_weight(q, c->orbN, orb_pos(c, 0), orb_pos(c, 1), orb_pos(c, 2), w, (const int *)c->ocell.p, (int *)c->ocnt.p,
+                            (double *)c->opart.p, (double *)c->osums.p, c->st));
+    c->nLaunches += w ? 2 : 1;
+    int cnt[2 * GG_ORB_MAX_SLOTS];
+    double sums[2 * GG_ORB_MAX_SLOTS];
+    CK(cudaMemcpyAsync(cnt, c->ocnt.p, sizeof(int) * 2 * nCells, cudaMemcpyDeviceToHost, c->st));
+    if (w) CK(cudaMemcpyAsync(sums, c->osums.p, sizeof(double) * 2 * nCells, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    for (int s = 0; s < nCells; ++s) {
+        nLow[s] = cnt[2 * s]; nHigh[s] = cnt[2 * s + 1];
+        fLow[s] = w ? sums[2 * s] : (double)cnt[2 * s];       // fWeight = 1 for every particle (pkd.c:686: read sets it)
+        fHigh[s] = w ? sums[2 * s + 1] : (double)cnt[2 * s + 1];
+    }
+    return GG_OK;
+}
+
+int gg_orb_split(gg_context *c, int nCells, const int *iCell, const int *iDim, const double *fSplit) {
+    OrbQuery q;
+    int rc;
+    if (!iDim || !fSplit) return fail(GG_ERR_ARG, "gg_orb_split: NULL argument");
+    if ((rc = orb_query("gg_orb_split", c, nCells, iCell, iDim, fSplit, q))) return rc;
+    for (int s = 0; s < nCells; ++s)
+        if (2 * q.cell[s] + 1 >= GG_ORB_MAX_CELL) return fail(GG_ERR_ARG, "gg_orb_split: children of PST cell %d exceed %d", q.cell[s], GG_ORB_MAX_CELL - 1);
+    CK(cudaSetDevice(c->device));
+    CK(gg_launch_orb_split(q, c->orbN, orb_pos(c, 0), orb_pos(c, 1), orb_pos(c, 2), (int *)c->ocell.p, c->st));
+    ++c->nLaunches;
+    CK(cudaStreamSynchronize(c->st));
+    return GG_OK;
+}
+
+int gg_orb_fetch(gg_context *c, int *iCellOfParticle) {
+    if (!c || c->orbN < 0 || !iCellOfParticle) return fail(GG_ERR_ARG, "gg_orb_fetch: no particles loaded (gg_orb_load) or NULL argument");
+    CK(cudaSetDevice(c->device));
+    if (c->orbN > 0) CK(cudaMemcpyAsync(iCellOfParticle, c->ocell.p, sizeof(int) * (size_t)c->orbN, cudaMemcpyDefault, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return GG_OK;
 }
 
 // ---- device-resident particle store: pkd->pStore kept in HBM across force evaluations ----

@@ -205,3 +205,22 @@ cudaError_t gg_launch_accelstep(int n, double *dt, const double *a, const double
 cudaError_t gg_launch_dt_to_rung(int n, int *idr, const double *dt, int iRung, double dDelta, int iMaxRung, int bAll, int *hist,
                                  int *ideal, cudaStream_t st);
 cudaError_t gg_launch_active_rung(int n, const int *idr, int *active, int iRung, int bGreater, int *count, cudaStream_t st);
+
+// gg_orb.cu: the per-rank services of the ORB domain decomposition (pstCalcBound, pstWeight, the split's outcome) on
+// the particles of one rank, all cells of one level of the rank tree (PST) per launch
+#define GG_ORB_MAX_CELL 256  // PST heap indices (ROOT = 1): 2^(1 + ceil(log2 nThreads)) <= 256 for up to 128 ranks
+#define GG_ORB_MAX_SLOTS 64  // PST cells asked about in one call
+struct OrbQuery {
+    int nSlots;
+    int cell[GG_ORB_MAX_SLOTS]; // heap index of the PST cell
+    int dim[GG_ORB_MAX_SLOTS];  // split axis
+    double split[GG_ORB_MAX_SLOTS];
+};
+cudaError_t gg_launch_orb_init(int n, int *cellOf, cudaStream_t st);
+cudaError_t gg_launch_orb_bounds(const OrbQuery &q, int n, const double *x, const double *y, const double *z, const int *cellOf,
+                                 unsigned long long *out, int *cnt, cudaStream_t st);
+cudaError_t gg_launch_orb_weight(const OrbQuery &q, int n, const double *x, const double *y, const double *z, const double *w,
+                                 const int *cellOf, int *cnt, double *part, double *sums, cudaStream_t st);
+cudaError_t gg_launch_orb_split(const OrbQuery &q, int n, const double *x, const double *y, const double *z, int *cellOf,
+                                cudaStream_t st);
+size_t gg_orb_part_bytes(int n);

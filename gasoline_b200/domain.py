@@ -126,6 +126,149 @@ def orb_decompose(x, y, z, nThreads: int, weights=None) -> list:
     return out
 
 
+MAX_ITTR = 64  # pst.c:874
+
+
+def pst_domain_decomp(ranks: list, nThreads: int, split_work: bool = True, reduce=None):
+    """pstDomainDecomp (pst.c:1854-1935) with _pstRootSplit's root finder (pst.c:959-1034) for hosts that are not
+    Gasoline: first-call semantics (bDoRootFind = bDoSplitDimFind = 1, master.c:4176; stores with room, so the
+    inactive "wrap" split never moves the boundary).  The per-rank work -- bounds, trial weights, the final split --
+    is done on the device by every rank's PKD (pkdCalcBound, pkdWeight, pkdOrbSplit after pkdOrbLoad); this function
+    only runs the bisection and adds the ranks' answers, level by level of the rank tree with all cells of a level in
+    one request (the reference recurses cell by cell; the outcome per cell is the same).
+
+    ranks:  the PKD-like objects of the ranks THIS process drives (all of them in a single process; one under torchrun)
+    reduce: None, or f(kind, array) -> array combining the answers of the processes ("sum", "min", "max") --
+            DistributedExchange.orb_reduce wraps torch.distributed.all_reduce.
+    split_work: bSplitWork (default 1, master.c:964): compare fLow/nLower with fHigh/nUpper, else nLow/nLower, nHigh/nUpper.
+    Returns the interior PST cells as a list of dicts (iCell, iDim, fSplit, bnd, ittr) in level order; the particles'
+    destination ranks are leaf_rank(nThreads)[pkd.pkdOrbCells()]."""
+    def combine(kind, parts):
+        a = parts[0].copy()
+        for b in parts[1:]:
+            a = a + b if kind == "sum" else (np.minimum(a, b) if kind == "min" else np.maximum(a, b))
+        return reduce(kind, a) if reduce is not None else a
+
+    level = [pst_tree(nThreads)]
+    out = []
+    while True:
+        level = [n for n in level if not n.leaf]
+        if not level:
+            break
+        if len(level) > 64:
+            raise _pkd.GasolineB200Error("pst_domain_decomp: more than 64 PST cells on one level")
+        ic = np.array([n.iCell for n in level], np.int32)
+        got = [r.pkdCalcBound(ic) for r in ranks]
+        lo = combine("min", [g[0][:, :3] for g in got])
+        hi = combine("max", [g[0][:, 3:] for g in got])
+        k = len(level)
+        d = np.zeros(k, np.int32)
+        for j in range(k):  # the first axis of strictly largest extent (iSplitDim == -1, pst.c:1900-1910)
+            dimsize = -1.0
+            for a in range(3):
+                if hi[j, a] - lo[j, a] > dimsize:
+                    d[j], dimsize = a, hi[j, a] - lo[j, a]
+        fl, fu = lo[np.arange(k), d].copy(), hi[np.arange(k), d].copy()
+        fm = np.full(k, np.nan)
+        fmm = (fl + fu) / 2
+        ittr = np.zeros(k, np.int32)
+        nLower = np.array([len(n.lower.ranks) for n in level], np.float64)
+        nUpper = np.array([len(n.upper.ranks) for n in level], np.float64)
+        live = np.ones(k, bool)
+        while True:
+            live &= (fl < fmm) & (fmm < fu) & (ittr < MAX_ITTR)
+            if not live.any():
+                break
+            idx = np.nonzero(live)[0]
+            fm[idx] = fmm[idx]
+            got = [r.pkdWeight(ic[idx], d[idx], fm[idx]) for r in ranks]
+            nLow = combine("sum", [g[0].astype(np.int64) for g in got])
+            nHigh = combine("sum", [g[1].astype(np.int64) for g in got])
+            if split_work:
+                a = combine("sum", [g[2] for g in got]) / nLower[idx]
+                b = combine("sum", [g[3] for g in got]) / nUpper[idx]
+            else:
+                a, b = nLow / nLower[idx], nHigh / nUpper[idx]
+            for t, j in enumerate(idx):
+                if (nLow[t] == 1 and nHigh[t] == 1) or a[t] == b[t]:
+                    live[j] = False
+                    continue
+                if a[t] > b[t]:
+                    fu[j] = fm[j]
+                else:
+                    fl[j] = fm[j]
+                fmm[j] = (fl[j] + fu[j]) / 2
+                ittr[j] += 1
+        if np.isnan(fm).any():
+            raise _pkd.GasolineB200Error("pst_domain_decomp: a PST cell has no extent along its longest axis")
+        for r in ranks:
+            r.pkdOrbSplit(ic, d, fm)
+        for j, n in enumerate(level):
+            out.append(dict(iCell=n.iCell, iDim=int(d[j]), fSplit=float(fm[j]), bnd=np.concatenate([lo[j], hi[j]]),
+                            ittr=int(ittr[j])))
+        level = [c for n in level for c in (n.lower, n.upper)]
+    return out
+
+
+def leaf_rank(nThreads: int) -> np.ndarray:
+    """PST heap index -> rank for the leaves of the rank tree (-1 elsewhere)."""
+    m = np.full(top_cells(nThreads) * 2, -1, np.int32)
+
+    def walk(n):
+        if n.leaf:
+            m[n.iCell] = n.ranks[0]
+        else:
+            walk(n.lower)
+            walk(n.upper)
+
+    walk(pst_tree(nThreads))
+    return m
+
+
+def orb_reduce_dist(backend_device: str):
+    """The `reduce` of pst_domain_decomp over torch.distributed: every process contributes its ranks' combined answer;
+    the answers are all-gathered and combined in rank order on every process, so all processes see the same bits and
+    take the same branch of the bisection (what the reference gets from adding outWtLow and outWtHigh up the PST)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size()
+
+    def reduce(kind, a):
+        a = np.ascontiguousarray(a)
+        t = torch.from_numpy(a.reshape(-1).copy()).to(backend_device)
+        out = torch.empty(world * t.numel(), dtype=t.dtype, device=backend_device)
+        dist.all_gather_into_tensor(out, t)
+        g = out.cpu().numpy().reshape((world,) + a.shape)
+        r = g[0].copy()
+        for k in range(1, world):
+            r = r + g[k] if kind == "sum" else (np.minimum(r, g[k]) if kind == "min" else np.maximum(r, g[k]))
+        return r
+
+    return reduce
+
+
+def orb_exchange(cols: np.ndarray, dest, backend_device: str) -> np.ndarray:
+    """After the decomposition: rows of cols [n][k] (float64 particle records) travel to process dest[i] by ONE
+    all_to_all_single (the outcome of the reference's pkdColRejects / pkdSwapRejects rounds, pst.c:1275-1334).
+    Returns the rows this process now owns, grouped by sender in rank order, each sender's rows in their old order."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    dest = np.asarray(dest)
+    order = np.argsort(dest, kind="stable")
+    send_counts = np.bincount(dest, minlength=world).astype(np.int64)
+    k = cols.shape[1]
+    cnt_t = torch.from_numpy(send_counts).to(backend_device)
+    recv_t = torch.empty(world, dtype=torch.int64, device=backend_device)
+    dist.all_to_all_single(recv_t, cnt_t)
+    recv_counts = recv_t.cpu().numpy()
+    send = torch.from_numpy(np.ascontiguousarray(cols[order], dtype=np.float64).reshape(-1)).to(backend_device)
+    recv = torch.empty(int(recv_counts.sum()) * k, dtype=torch.float64, device=backend_device)
+    dist.all_to_all_single(recv, send, output_split_sizes=[int(c) * k for c in recv_counts],
+                           input_split_sizes=[int(c) * k for c in send_counts])
+    return recv.cpu().numpy().reshape(-1, k)
+
+
 # ---------------------------------------------------------------------------------------------- per-rank state
 class Domain:
     """One rank: its particles (tree order) and local tree on the host; the top tree once assemble() has run."""

@@ -112,6 +112,11 @@ def load_library(path: str | None = None):
     L.gg_state_active_rung.argtypes = [C.c_void_p, C.c_int, C.c_int, _ip]
     L.gg_state_set_rungs.argtypes = [C.c_void_p, _ip]
     L.gg_state_fetch_rungs.argtypes = [C.c_void_p, _ip, _ip]
+    L.gg_orb_load.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.gg_orb_bounds.argtypes = [C.c_void_p, C.c_int, _ip, _dp, _ip]
+    L.gg_orb_weight.argtypes = [C.c_void_p, C.c_int, _ip, _ip, _dp, _ip, _ip, _dp, _dp]
+    L.gg_orb_split.argtypes = [C.c_void_p, C.c_int, _ip, _ip, _dp]
+    L.gg_orb_fetch.argtypes = [C.c_void_p, C.c_void_p]
     L.gg_measure_fp32_peak.argtypes = [C.c_void_p, _dp, _dp]
     L.gg_flush_l2.argtypes = [C.c_void_p]
     _lib = L
@@ -353,6 +358,49 @@ class PKD:
         self.nNodesDevice = int(nn.value)
         self._uploaded = True
         return self.nNodesDevice
+
+    # -- ORB domain decomposition: the rank's services of pstDomainDecomp (driver: domain.pst_domain_decomp)
+    def pkdOrbLoad(self, x=None, y=None, z=None, fWeight=None):
+        """gg_orb_load: this rank's particles enter the decomposition in ROOT.  x is None: the resident store's positions
+        (pkdLoadResident).  fWeight None: 1 for every particle (what reading a file leaves, pkd.c:686)."""
+        if x is None:
+            n, ptr = self.nLocal, [None, None, None]
+            self._orb_keep = []
+        else:
+            cols = [np.ascontiguousarray(a, dtype=np.float64) for a in (x, y, z)]
+            n, ptr = int(cols[0].shape[0]), [a.ctypes.data for a in cols]
+            self._orb_keep = cols
+        w = None if fWeight is None else np.ascontiguousarray(fWeight, dtype=np.float64)
+        _check(self._L.gg_orb_load(self._ctx, n, ptr[0], ptr[1], ptr[2], None if w is None else w.ctypes.data), "gg_orb_load")
+        self._orb_n = n
+
+    def pkdCalcBound(self, iCell):
+        """pstCalcBound's leaf for the PST cells iCell: (bnd [k][6] = fMin, fMax; nIn [k]) of this rank's particles."""
+        ic = np.ascontiguousarray(iCell, dtype=np.int32)
+        bnd, nIn = np.zeros((len(ic), 6)), np.zeros(len(ic), np.int32)
+        _check(self._L.gg_orb_bounds(self._ctx, len(ic), _i(ic), _d(bnd), _i(nIn)), "gg_orb_bounds")
+        return bnd, nIn
+
+    def pkdWeight(self, iCell, iDim, fSplit):
+        """pstWeight's leaf (pkdWeight, pkd.c:945) for one trial split per PST cell: nLow, nHigh, fLow, fHigh."""
+        ic, idim = np.ascontiguousarray(iCell, dtype=np.int32), np.ascontiguousarray(iDim, dtype=np.int32)
+        fs = np.ascontiguousarray(fSplit, dtype=np.float64)
+        nLow, nHigh = np.zeros(len(ic), np.int32), np.zeros(len(ic), np.int32)
+        fLow, fHigh = np.zeros(len(ic)), np.zeros(len(ic))
+        _check(self._L.gg_orb_weight(self._ctx, len(ic), _i(ic), _i(idim), _d(fs), _i(nLow), _i(nHigh), _d(fLow), _d(fHigh)),
+               "gg_orb_weight")
+        return nLow, nHigh, fLow, fHigh
+
+    def pkdOrbSplit(self, iCell, iDim, fSplit):
+        ic, idim = np.ascontiguousarray(iCell, dtype=np.int32), np.ascontiguousarray(iDim, dtype=np.int32)
+        fs = np.ascontiguousarray(fSplit, dtype=np.float64)
+        _check(self._L.gg_orb_split(self._ctx, len(ic), _i(ic), _i(idim), _d(fs)), "gg_orb_split")
+
+    def pkdOrbCells(self) -> np.ndarray:
+        """The PST cell of every particle, in pkdOrbLoad order."""
+        out = np.zeros(max(self._orb_n, 1), np.int32)
+        _check(self._L.gg_orb_fetch(self._ctx, out.ctypes.data), "gg_orb_fetch")
+        return out[:self._orb_n]
 
     def pkdKick(self, dvFacOne: float, dvFacTwo: float, a=None):
         """pkdKick (pkd.c:3780) on the resident store; a: optional [n][3] accelerations in the store's order (default:

@@ -305,6 +305,31 @@ int gg_state_active_rung(gg_context *ctx, int iRung, int bGreater, int *pnActive
 int gg_state_set_rungs(gg_context *ctx, const int *rung);
 int gg_state_fetch_rungs(gg_context *ctx, int *rung, int *active);
 
+/*
+ * ORB domain decomposition: the PER-RANK services the reference's pstDomainDecomp (pst.c:1854) asks of
+ * every rank, on the device.  The host (Gasoline's PST, or gasoline_b200/domain.py: pst_domain_decomp for hosts that are
+ * not Gasoline) runs _pstRootSplit's bisection (pst.c:959-1034) and adds the ranks' answers; every particle carries
+ * the heap index of its cell of the rank tree (ROOT = 1, LOWER(i) = 2i, UPPER(i) = 2i+1, pkd.h:77-86), so all cells
+ * of one level are served by one launch.
+ *   gg_orb_load    the rank's particles for this decomposition (host or device pointers; x == y == z == NULL: the
+ *                  resident store of gg_state_load, n = its size); fWeight NULL: 1 for every particle, as after
+ *                  reading a file; every particle starts in ROOT.  n = 0 is allowed (a rank without particles)
+ *   gg_orb_bounds  = pstCalcBound (pst.c:1937) leaf / pkdCalcBound: bnd[k][6] = fMin[3], fMax[3] of the rank's particles
+ *                  in PST cell iCell[k] (+-FLOAT_MAXVAL when it has none), nIn[k] = how many
+ *   gg_orb_weight  = pstWeight (pst.c:1405) leaf / pkdWeight (pkd.c:945): for the trial split fSplit[k] of axis iDim[k] in
+ *                  cell iCell[k]: particles with r[d] < fSplit (nLow, fLow = their weight) and the others (nHigh,
+ *                  fHigh).  Counts are exact; weights are summed in a fixed order (reproducible run to run)
+ *   gg_orb_split   the split is final: particles of iCell[k] move to LOWER (r[d] < fSplit[k]) or UPPER
+ *   gg_orb_fetch   iCellOfParticle[n] (host or device pointer): the PST cell of every particle, in gg_orb_load order;
+ *                  after the last level these are the leaves = the ranks the particles go to
+ */
+int gg_orb_load(gg_context *ctx, int n, const double *x, const double *y, const double *z, const double *fWeight);
+int gg_orb_bounds(gg_context *ctx, int nCells, const int *iCell, double *bnd, int *nIn);
+int gg_orb_weight(gg_context *ctx, int nCells, const int *iCell, const int *iDim, const double *fSplit, int *nLow,
+                  int *nHigh, double *fLow, double *fHigh);
+int gg_orb_split(gg_context *ctx, int nCells, const int *iCell, const int *iDim, const double *fSplit);
+int gg_orb_fetch(gg_context *ctx, int *iCellOfParticle);
+
 /* Every cell's reduced multipoles by the algorithm the DEVICE uses when gg_tree.mom is NULL (raw moments of the
  * buckets, children translated to the parent's centre and summed, then reduced as pkdCalcCell defines them), executed
  * on the host: mom[nNodes][GG_NMOM].  A checking aid for hosts and tests; no GPU needed. */

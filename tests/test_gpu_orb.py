@@ -1,0 +1,130 @@
+"""GPU: the ORB domain decomposition services (gg_orb_*, csrc/gg_orb.cu) and the decomposition they drive
+(domain.pst_domain_decomp) against the oracle restatement of pstDomainDecomp/_pstRootSplit (oracle/orb_oracle.py, pinned
+to the compiled reference's domains in the CPU suite) and against the reference's own domains (golden fixtures).
+Bar: splits, counts and every particle's destination bit-exact."""
+import time
+
+import numpy as np
+import pytest
+
+from gasoline_b200 import domain, ics
+from gasoline_b200.pkd import PKD, GasolineB200Error
+from multirank_cases import NAMES, load
+from oracle import orb_oracle
+from orb_stub import HostOrbRank
+
+pytestmark = pytest.mark.gpu
+
+
+def _decompose(p, nThreads, nCtx=1, weights=None, split_work=True, resident=False):
+    owner = np.arange(p.n) % nCtx if nCtx > 1 else np.zeros(p.n, np.int64)
+    idx = [np.nonzero(owner == s)[0] for s in range(nCtx)]
+    pkds = [PKD(device=0, fPeriod=p.period) for _ in range(nCtx)]
+    for k, i in zip(pkds, idx):
+        w = None if weights is None else weights[i]
+        if resident:
+            zero = np.zeros(len(i))
+            k.pkdLoadResident(p.x[i], p.y[i], p.z[i], zero, zero, zero, p.m[i], p.h[i])
+            k.pkdOrbLoad(fWeight=w)
+        else:
+            k.pkdOrbLoad(p.x[i], p.y[i], p.z[i], fWeight=w)
+    nodes = domain.pst_domain_decomp(pkds, nThreads, split_work=split_work)
+    dest = np.zeros(p.n, np.int32)
+    lr = domain.leaf_rank(nThreads)
+    for i, k in zip(idx, pkds):
+        dest[i] = lr[k.pkdOrbCells()]
+        k.close()
+    return nodes, dest
+
+
+def test_services_equal_host_stand_in():
+    p = ics.plummer(30000, seed=9)
+    rng = np.random.default_rng(2)
+    w = rng.uniform(0.5, 4.0, p.n)
+    k = PKD(device=0, fPeriod=p.period)
+    k.pkdOrbLoad(p.x, p.y, p.z, fWeight=w)
+    h = HostOrbRank(p.x, p.y, p.z, w)
+    b, n = k.pkdCalcBound([1])
+    hb, hn = h.pkdCalcBound([1])
+    assert np.array_equal(b, hb) and np.array_equal(n, hn)
+    got, ref = k.pkdWeight([1], [1], [0.03]), h.pkdWeight([1], [1], [0.03])
+    assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])
+    assert np.allclose(got[2], ref[2], rtol=1e-13, atol=0) and np.allclose(got[3], ref[3], rtol=1e-13, atol=0)
+    again = k.pkdWeight([1], [1], [0.03])
+    assert np.array_equal(got[2], again[2]) and np.array_equal(got[3], again[3])  # fixed summation order
+    k.pkdOrbSplit([1], [1], [0.03]); h.pkdOrbSplit([1], [1], [0.03])
+    assert np.array_equal(k.pkdOrbCells(), h.pkdOrbCells())
+    # two cells of the next level in one request, plus a cell that holds nothing (heap index 7 does not exist yet)
+    cells, dims, splits = [2, 3, 7], [0, 2, 0], [-0.2, 0.4, 0.0]
+    b, n = k.pkdCalcBound(cells)
+    hb, hn = h.pkdCalcBound(cells)
+    assert np.array_equal(b, hb) and np.array_equal(n, hn) and n[2] == 0
+    got, ref = k.pkdWeight(cells, dims, splits), h.pkdWeight(cells, dims, splits)
+    assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])
+    assert np.allclose(got[2], ref[2], rtol=1e-13, atol=0) and np.allclose(got[3], ref[3], rtol=1e-13, atol=0)
+    k.pkdOrbSplit(cells[:2], dims[:2], splits[:2]); h.pkdOrbSplit(cells[:2], dims[:2], splits[:2])
+    assert np.array_equal(k.pkdOrbCells(), h.pkdOrbCells())
+    with pytest.raises(GasolineB200Error):
+        k.pkdWeight([2, 2], [0, 0], [0.0, 0.0])
+    k.close()
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_device_decomposition_reproduces_the_reference_domains(name):
+    p, theta, nThreads, z = load(name)
+    for sw in (True, False):
+        nodes, dest = _decompose(p, nThreads, nCtx=2, split_work=sw)
+        for r in range(nThreads):
+            assert np.array_equal(np.nonzero(dest == r)[0], np.sort(z[f"r{r}_iOrder"]))
+
+
+@pytest.mark.parametrize("nThreads,nCtx,resident", [(2, 1, False), (3, 2, False), (8, 3, False), (5, 1, True), (8, 1, True)])
+def test_device_decomposition_equals_oracle(nThreads, nCtx, resident):
+    p = ics.plummer(50000, seed=13)
+    doms, ref_nodes = orb_oracle.domain_decomp(p.x, p.y, p.z, nThreads)
+    nodes, dest = _decompose(p, nThreads, nCtx=nCtx, resident=resident)
+    for r in range(nThreads):
+        assert np.array_equal(np.nonzero(dest == r)[0], doms[r])
+    ref = {n[0]: n for n in ref_nodes}
+    for n in nodes:
+        assert n["iDim"] == ref[n["iCell"]][1] and n["fSplit"] == ref[n["iCell"]][2]
+        assert np.array_equal(n["bnd"], ref[n["iCell"]][3])
+
+
+def test_device_decomposition_weights_periodic_and_empty_rank():
+    p = ics.periodic_box(20)
+    w = np.ones(p.n); w[p.z > 0.1] = 5.0  # integer-valued work weights: all sums exact
+    doms, _ = orb_oracle.domain_decomp(p.x, p.y, p.z, 8, weights=w)
+    nodes, dest = _decompose(p, 8, nCtx=2, weights=w)
+    for r in range(8):
+        assert np.array_equal(np.nonzero(dest == r)[0], doms[r])
+    # a service rank without particles takes part (the reference's pkdCalcBound on an empty store)
+    a, b = PKD(device=0, fPeriod=p.period), PKD(device=0, fPeriod=p.period)
+    a.pkdOrbLoad(p.x, p.y, p.z); b.pkdOrbLoad(p.x[:0], p.y[:0], p.z[:0])
+    domain.pst_domain_decomp([a, b], 4)
+    doms4, _ = orb_oracle.domain_decomp(p.x, p.y, p.z, 4)
+    dest = domain.leaf_rank(4)[a.pkdOrbCells()]
+    for r in range(4):
+        assert np.array_equal(np.nonzero(dest == r)[0], doms4[r])
+    assert len(b.pkdOrbCells()) == 0
+    a.close(); b.close()
+
+
+def test_device_decomposition_full_size():
+    """1 M Plummer particles into 8 domains: equal to the oracle; time of the whole decomposition on the device."""
+    p = ics.plummer(1000000, seed=12345)
+    k = PKD(device=0, fPeriod=p.period)
+    k.pkdOrbLoad(p.x, p.y, p.z)
+    t0 = time.perf_counter()
+    nodes = domain.pst_domain_decomp([k], 8)
+    cells = k.pkdOrbCells()
+    ms = (time.perf_counter() - t0) * 1e3
+    dest = domain.leaf_rank(8)[cells]
+    k.close()
+    t0 = time.perf_counter()
+    doms, _ = orb_oracle.domain_decomp(p.x, p.y, p.z, 8)
+    ms_cpu = (time.perf_counter() - t0) * 1e3
+    for r in range(8):
+        assert np.array_equal(np.nonzero(dest == r)[0], doms[r])
+    print(f"ORB 1 M particles -> 8 domains: device {ms:.1f} ms ({sum(n['ittr'] for n in nodes)} bisection steps in "
+          f"3 levels), numpy restatement {ms_cpu:.0f} ms; domain sizes {np.bincount(dest).tolist()}")

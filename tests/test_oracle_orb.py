@@ -1,0 +1,118 @@
+"""CPU: the ORB domain decomposition.
+ * oracle/orb_oracle.py (restatement of pstDomainDecomp + _pstRootSplit) is PINNED against the domains the compiled
+   reference produced on 2, 3 and 4 pthread-MDL ranks (tests/golden/multirank_*.npz, r<k>_iOrder), particle for particle;
+ * the product's host-side driver (gasoline_b200/domain.py: pst_domain_decomp) gives the same splits and domains as the
+   oracle when served by a numpy stand-in for the device services (tests/orb_stub.py), with the particles spread over
+   1, 2 and 5 service ranks, and across two real processes (torch.distributed, gloo)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from gasoline_b200 import domain, ics
+from multirank_cases import NAMES, load
+from oracle import orb_oracle
+from orb_stub import HostOrbRank
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("split_work", [True, False])
+def test_orb_oracle_reproduces_the_reference_domains(name, split_work):
+    p, theta, nThreads, z = load(name)
+    doms, nodes = orb_oracle.domain_decomp(p.x, p.y, p.z, nThreads, split_work=split_work)
+    for r in range(nThreads):
+        assert np.array_equal(np.sort(z[f"r{r}_iOrder"]), doms[r]), f"rank {r}: domain differs from the reference's"
+    assert len(nodes) == nThreads - 1
+
+
+def _run_driver(p, nThreads, nService, weights=None, split_work=True):
+    rng = np.random.default_rng(7)
+    owner = rng.integers(0, nService, p.n)
+    idx = [np.nonzero(owner == s)[0] for s in range(nService)]
+    ranks = [HostOrbRank(p.x[i], p.y[i], p.z[i], None if weights is None else weights[i]) for i in idx]
+    nodes = domain.pst_domain_decomp(ranks, nThreads, split_work=split_work)
+    dest = np.zeros(p.n, np.int32)
+    lr = domain.leaf_rank(nThreads)
+    for i, r in zip(idx, ranks):
+        dest[i] = lr[r.pkdOrbCells()]
+    return nodes, dest
+
+
+@pytest.mark.parametrize("nThreads", [2, 3, 5, 8])
+@pytest.mark.parametrize("nService", [1, 2, 5])
+def test_driver_equals_oracle(nThreads, nService):
+    p = ics.plummer(6000, seed=11)
+    doms, ref_nodes = orb_oracle.domain_decomp(p.x, p.y, p.z, nThreads)
+    nodes, dest = _run_driver(p, nThreads, nService)
+    assert dest.min() >= 0
+    for r in range(nThreads):
+        assert np.array_equal(np.nonzero(dest == r)[0], doms[r])
+    ref = {n[0]: n for n in ref_nodes}
+    for n in nodes:
+        assert n["iDim"] == ref[n["iCell"]][1] and n["fSplit"] == ref[n["iCell"]][2]
+        assert np.array_equal(n["bnd"], ref[n["iCell"]][3])
+
+
+def test_driver_equals_oracle_on_reference_cases_and_count_mode():
+    for name in NAMES:
+        p, theta, nThreads, z = load(name)
+        for sw in (True, False):
+            nodes, dest = _run_driver(p, nThreads, 2, split_work=sw)
+            for r in range(nThreads):
+                assert np.array_equal(np.nonzero(dest == r)[0], np.sort(z[f"r{r}_iOrder"]))
+
+
+def test_driver_with_integer_weights_balances_work():
+    p = ics.plummer(8000, seed=3)
+    w = np.ones(p.n)
+    w[p.x > 0] = 3.0  # integer-valued: every sum is exact in any order
+    doms, _ = orb_oracle.domain_decomp(p.x, p.y, p.z, 4, weights=w)
+    nodes, dest = _run_driver(p, 4, 3, weights=w)
+    for r in range(4):
+        assert np.array_equal(np.nonzero(dest == r)[0], doms[r])
+    tot = [w[dest == r].sum() for r in range(4)]
+    assert max(tot) - min(tot) <= 8.0
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import numpy as np, torch, torch.distributed as dist
+from gasoline_b200 import domain, ics
+from orb_stub import HostOrbRank
+from oracle import orb_oracle
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+p = ics.plummer(5000, seed=21)
+mine = np.arange(p.n)[rank::world]            # any initial distribution: every other particle
+svc = HostOrbRank(p.x[mine], p.y[mine], p.z[mine])
+nodes = domain.pst_domain_decomp([svc], 4, reduce=domain.orb_reduce_dist("cpu"))
+dest = domain.leaf_rank(4)[svc.pkdOrbCells()]
+doms, ref_nodes = orb_oracle.domain_decomp(p.x, p.y, p.z, 4)
+for r in range(4):
+    assert np.array_equal(mine[dest == r], doms[r][np.isin(doms[r], mine)])
+assert [n["fSplit"] for n in nodes] == [n[2] for n in sorted(ref_nodes, key=lambda n: n[0])]
+# the particles travel to their ranks (2 processes drive ranks 0..1 here: destination modulo world)
+cols = np.stack([p.x[mine], p.y[mine], p.z[mine], mine.astype(np.float64)], axis=1)
+got = domain.orb_exchange(cols, dest % world, "cpu")
+want = np.sort(np.concatenate([doms[r] for r in range(4) if r % world == rank]))
+assert np.array_equal(np.sort(got[:, 3].astype(np.int64)), want)
+assert np.array_equal(got[:, 0], p.x[got[:, 3].astype(np.int64)])
+dist.destroy_process_group()
+open(os.path.join(os.environ["GG_TEST_OUT"], f"rank{{rank}}.ok"), "w").write("ok")
+"""
+
+
+def test_driver_across_processes_gloo_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29547", str(script)],
+                       capture_output=True, text=True, timeout=300, cwd=ROOT,
+                       env=dict(os.environ, GG_TEST_OUT=str(tmp_path)))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert (tmp_path / "rank0.ok").exists() and (tmp_path / "rank1.ok").exists()
