@@ -58,6 +58,9 @@ def parse_args():
     ap.add_argument("--workload", default=None, help="plummer:N:theta | periodic:n:theta (default: configs[1])")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--device-orb", action="store_true",
+                    help="N > 1: the from-particles leg takes its domains from the reference's ORB decomposition run on "
+                         "the devices (gg_orb_*) instead of the host-side median split")
     return ap.parse_args()
 
 
@@ -333,7 +336,17 @@ def run_ours(a):
         #      the host: particles H2D, tree build, root summaries + top tree (two small all-gathers), pruned LET
         #      exchange, force evaluation, results to the host
         from gasoline_b200 import domain
-        pkd4, exchange4 = domain.setup_rank(p, theta, rank, world, local, device_build=True)
+        orb_info = None
+        if a.device_orb:
+            orb_t = {}
+            barrier()
+            o0 = time.perf_counter()
+            domain.device_orb_share(p, rank, world, local, "cuda", timing=orb_t)
+            barrier()
+            orb_info = dict(orb_t, total_ms=(time.perf_counter() - o0) * 1e3,
+                            what="pstDomainDecomp on the devices: per-rank chunk H2D, bisection trials (gg_orb_weight + one "
+                                 "all-gather each), destinations, all-to-all of the particle indices (rank 0's clock)")
+        pkd4, exchange4 = domain.setup_rank(p, theta, rank, world, local, device_build=True, device_orb=a.device_orb)
         n4 = pkd4.nLocal
         o4 = (pinned_empty((n4, 3)), pinned_empty(n4), pinned_empty(n4), pinned_empty(n4))
         for it in range(min(a.warmup, 2) + a.steps):
@@ -353,6 +366,9 @@ def run_ours(a):
                           "phases_ms_rank0": {k: v * 1e3 for k, v in exchange4.driver.timing.items()},
                           "what": "per rank: host particles -> gg_build_local -> root summaries / top tree (all-gathers) -> "
                                   "pruned LET exchange (NCCL all-to-all) -> gg_gravity -> host arrays"}
+        if orb_info is not None:
+            from_particles["orb_device"] = orb_info
+            from_particles["particles_rank0"] = int(n4)
         pkd4.close()
 
     # ---- reduce over ranks: time = max, work = sum

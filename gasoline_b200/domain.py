@@ -741,15 +741,47 @@ class _DevView:
         self.t = torch.as_tensor(a, device=dev)
 
 
+def device_orb_share(p, rank: int, world: int, device: int, backend_device: str = "cuda", weights=None, timing=None):
+    """pstDomainDecomp across the processes of a torch.distributed job, per-rank work on the GPUs: this rank starts with
+    a contiguous chunk of `p`, as the reference's ranks start with a contiguous range of the file (pstReadTipsy splits
+    the file range down the rank tree, pst.c:676-725; the outcome does not depend on the initial distribution), answers the bisection's questions from its
+    device (gg_orb_*), and receives the particles of its domain by one all-to-all.  Returns their indices in `p`,
+    ascending."""
+    import time as _time
+    n = len(p.x)
+    lo = rank * (n // world) + min(rank, n % world)
+    hi = lo + n // world + (1 if rank < n % world else 0)
+    mine = np.arange(lo, hi)
+    t0 = _time.perf_counter()
+    svc = PKD(device=device, fPeriod=p.period)
+    svc.pkdOrbLoad(p.x[mine], p.y[mine], p.z[mine], fWeight=None if weights is None else np.asarray(weights)[mine])
+    t1 = _time.perf_counter()
+    nodes = pst_domain_decomp([svc], world, reduce=orb_reduce_dist(backend_device))
+    dest = leaf_rank(world)[svc.pkdOrbCells()]
+    svc.close()
+    t2 = _time.perf_counter()
+    got = orb_exchange(mine.astype(np.float64).reshape(-1, 1), dest, backend_device)
+    t3 = _time.perf_counter()
+    if timing is not None:
+        timing.update(load_ms=(t1 - t0) * 1e3, decomp_ms=(t2 - t1) * 1e3, exchange_ms=(t3 - t2) * 1e3,
+                      trials=int(sum(c["ittr"] for c in nodes)))
+    return np.sort(got[:, 0].astype(np.int64))
+
+
 def setup_rank(p, theta: float, rank: int, world: int, device: int | None, nBucket: int = 8, iOrder: int = 4,
-               weights=None, backend_device: str | None = None, device_build: bool = False):
+               weights=None, backend_device: str | None = None, device_build: bool = False, device_orb: bool = False):
     """What one torch.distributed rank does before its first force evaluation (bench.py --gpus N, tests): every rank
     holds the same particle set `p`, takes ITS share of the ORB decomposition (the host's job in a Gasoline run,
     pstDomainDecomp pst.c:1854), builds its local tree and creates its GPU context.  Returns (pkd, exchange) where
     exchange() runs the top-tree assembly + the tree exchange (steps 1-5 of this module) and returns the bytes this
-    rank received; with device=None no GPU context exists (host-only checks) and pkd is the host store."""
-    parts = orb_decompose(p.x, p.y, p.z, world, weights=weights)
-    idx = parts[rank]
+    rank received; with device=None no GPU context exists (host-only checks) and pkd is the host store.
+    device_orb: the share comes from the reference's decomposition run on the devices (device_orb_share) instead of
+    orb_decompose."""
+    if device_orb:
+        idx = device_orb_share(p, rank, world, device, backend_device or "cuda", weights=weights)
+    else:
+        parts = orb_decompose(p.x, p.y, p.z, world, weights=weights)
+        idx = parts[rank]
     d = Domain(rank, world, p.x[idx], p.y[idx], p.z[idx], p.m[idx], p.h[idx], p.period, theta, nBucket=nBucket,
                iOrder=iOrder, pinned=device is not None, device=device, device_build=device_build)
     d.global_index = idx[d.pkd.treeOrder if device_build else d.host.iOrderMap]  # tree position -> index in p

@@ -116,3 +116,44 @@ def test_driver_across_processes_gloo_world2(tmp_path):
                        env=dict(os.environ, GG_TEST_OUT=str(tmp_path)))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert (tmp_path / "rank0.ok").exists() and (tmp_path / "rank1.ok").exists()
+
+
+_WORKER_SHARE = r"""
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import numpy as np, torch.distributed as dist
+from gasoline_b200 import domain, ics
+from oracle import orb_oracle
+import orb_stub
+# CPU stand-in for the device services behind device_orb_share (test infrastructure): same interface as PKD
+class _Svc(orb_stub.HostOrbRank):
+    def __init__(self, device=None, fPeriod=None):
+        pass
+    def pkdOrbLoad(self, x, y, z, fWeight=None):
+        orb_stub.HostOrbRank.__init__(self, x, y, z, fWeight)
+    def close(self):
+        pass
+domain.PKD = _Svc
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+p = ics.plummer(3001, seed=8)
+t = {{}}
+idx = domain.device_orb_share(p, rank, world, None, "cpu", timing=t)
+doms, _ = orb_oracle.domain_decomp(p.x, p.y, p.z, world)
+assert np.array_equal(idx, doms[rank]) and t["trials"] > 0
+dist.destroy_process_group()
+open(os.path.join(os.environ["GG_TEST_OUT"], f"rank{{rank}}.ok"), "w").write("ok")
+"""
+
+
+def test_orb_share_across_processes_gloo_world2(tmp_path):
+    """device_orb_share's host logic (chunking, reduce, destinations, all-to-all) on two gloo processes, the device
+    services replaced by the numpy stand-in: every process ends up with exactly its domain of the oracle's decomposition."""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER_SHARE.format(root=ROOT))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29553", str(script)],
+                       capture_output=True, text=True, timeout=300, cwd=ROOT,
+                       env=dict(os.environ, GG_TEST_OUT=str(tmp_path)))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert (tmp_path / "rank0.ok").exists() and (tmp_path / "rank1.ok").exists()
