@@ -339,6 +339,7 @@ def run_ours(a):
         orb_info = None
         if a.device_orb:
             orb_t = {}
+            domain.device_orb_share(p, rank, world, local, "cuda")  # warm-up (context, NCCL channels)
             barrier()
             o0 = time.perf_counter()
             domain.device_orb_share(p, rank, world, local, "cuda", timing=orb_t)
