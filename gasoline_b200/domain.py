@@ -129,7 +129,11 @@ def orb_decompose(x, y, z, nThreads: int, weights=None) -> list:
 MAX_ITTR = 64  # pst.c:874
 
 
-def pst_domain_decomp(ranks: list, nThreads: int, split_work: bool = True, reduce=None):
+NEWSPLITDIMCUT = 0.707  # pst.c:1851
+
+
+def pst_domain_decomp(ranks: list, nThreads: int, split_work: bool = True, reduce=None, prev=None,
+                      bDoRootFind: bool = True, bDoSplitDimFind: bool = True):
     """pstDomainDecomp (pst.c:1854-1935) with _pstRootSplit's root finder (pst.c:959-1034) for hosts that are not
     Gasoline: first-call semantics (bDoRootFind = bDoSplitDimFind = 1, master.c:4176; stores with room, so the
     inactive "wrap" split never moves the boundary).  The per-rank work -- bounds, trial weights, the final split --
@@ -141,8 +145,13 @@ def pst_domain_decomp(ranks: list, nThreads: int, split_work: bool = True, reduc
     reduce: None, or f(kind, array) -> array combining the answers of the processes ("sum", "min", "max") --
             DistributedExchange.orb_reduce wraps torch.distributed.all_reduce.
     split_work: bSplitWork (default 1, master.c:964): compare fLow/nLower with fHigh/nUpper, else nLow/nLower, nHigh/nUpper.
+    prev: the list this function returned for the previous decomposition (pst->iSplitDim / pst->fSplit of every cell):
+            the split axis then only changes when another axis beats the old one's extent x NEWSPLITDIMCUT
+            (pst.c:1900-1910); bDoSplitDimFind = 0 keeps the axis, bDoRootFind = 0 keeps the old split while it lies
+            inside the cell's bounds (pst.c:963; the host sets both to 0 for small active sets, master.c:4210-4222).
     Returns the interior PST cells as a list of dicts (iCell, iDim, fSplit, bnd, ittr) in level order; the particles'
     destination ranks are leaf_rank(nThreads)[pkd.pkdOrbCells()]."""
+    old = {c["iCell"]: (c["iDim"], c["fSplit"]) for c in prev} if prev else {}
     def combine(kind, parts):
         a = parts[0].copy()
         for b in parts[1:]:
@@ -163,18 +172,24 @@ def pst_domain_decomp(ranks: list, nThreads: int, split_work: bool = True, reduc
         hi = combine("max", [g[0][:, 3:] for g in got])
         k = len(level)
         d = np.zeros(k, np.int32)
-        for j in range(k):  # the first axis of strictly largest extent (iSplitDim == -1, pst.c:1900-1910)
-            dimsize = -1.0
-            for a in range(3):
-                if hi[j, a] - lo[j, a] > dimsize:
-                    d[j], dimsize = a, hi[j, a] - lo[j, a]
-        fl, fu = lo[np.arange(k), d].copy(), hi[np.arange(k), d].copy()
         fm = np.full(k, np.nan)
+        for j in range(k):  # pst.c:1900-1910: first call (iSplitDim == -1) = the first axis of strictly largest extent
+            pd, pf = old.get(int(ic[j]), (-1, np.nan))
+            dj = pd
+            if bDoSplitDimFind or pd == -1:
+                dimsize = -1.0 if pd == -1 else (hi[j, pd] - lo[j, pd]) * NEWSPLITDIMCUT
+                for a in range(3):
+                    if hi[j, a] - lo[j, a] > dimsize:
+                        dj, dimsize = a, hi[j, a] - lo[j, a]
+            d[j], fm[j] = dj, pf
+        fl, fu = lo[np.arange(k), d].copy(), hi[np.arange(k), d].copy()
         fmm = (fl + fu) / 2
         ittr = np.zeros(k, np.int32)
         nLower = np.array([len(n.lower.ranks) for n in level], np.float64)
         nUpper = np.array([len(n.upper.ranks) for n in level], np.float64)
-        live = np.ones(k, bool)
+        # pst.c:963: the root finder runs when asked for, or when the previous split has left the cell's bounds
+        live = np.array([bool(bDoRootFind or not (fl[j] <= fm[j] <= fu[j])) for j in range(k)])
+        fm[live] = np.nan
         while True:
             live &= (fl < fmm) & (fmm < fu) & (ittr < MAX_ITTR)
             if not live.any():

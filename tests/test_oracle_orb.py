@@ -157,3 +157,43 @@ def test_orb_share_across_processes_gloo_world2(tmp_path):
                        env=dict(os.environ, GG_TEST_OUT=str(tmp_path)))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert (tmp_path / "rank0.ok").exists() and (tmp_path / "rank1.ok").exists()
+
+
+def test_repeated_decomposition_hysteresis_and_shortcuts():
+    """Later decompositions of a run (restated from pst.c:1900-1910, :963; not pinned by execution): the driver equals
+    the oracle; the split axis survives a small change of shape and flips on a large one; bDoRootFind = 0 keeps a split
+    that is still inside the bounds."""
+    p = ics.plummer(5000, seed=17)
+    doms0, nodes0 = orb_oracle.domain_decomp(p.x, p.y, p.z, 4)
+    prev = {n[0]: (n[1], n[2]) for n in nodes0}
+    # the particles move a little: same axes, new roots
+    rng = np.random.default_rng(5)
+    x, y, z = (c + rng.normal(0, 1e-3, p.n) for c in (p.x, p.y, p.z))
+    doms1, nodes1 = orb_oracle.domain_decomp(x, y, z, 4, prev=prev)
+    assert [n[1] for n in nodes1] == [n[1] for n in nodes0]
+    for nService in (1, 3):
+        owner = np.arange(p.n) % nService
+        idx = [np.nonzero(owner == s)[0] for s in range(nService)]
+        first = [HostOrbRank(p.x[i], p.y[i], p.z[i]) for i in idx]
+        got0 = domain.pst_domain_decomp(first, 4)
+        ranks = [HostOrbRank(x[i], y[i], z[i]) for i in idx]
+        got1 = domain.pst_domain_decomp(ranks, 4, prev=got0)
+        dest = np.zeros(p.n, np.int32)
+        for i, r in zip(idx, ranks):
+            dest[i] = domain.leaf_rank(4)[r.pkdOrbCells()]
+        for r in range(4):
+            assert np.array_equal(np.nonzero(dest == r)[0], doms1[r])
+        ref = {n[0]: n for n in nodes1}
+        assert all(c["iDim"] == ref[c["iCell"]][1] and c["fSplit"] == ref[c["iCell"]][2] for c in got1)
+        # bDoRootFind = bDoSplitDimFind = 0: the old axes and splits are kept (they are still inside the bounds)
+        ranks = [HostOrbRank(x[i], y[i], z[i]) for i in idx]
+        got2 = domain.pst_domain_decomp(ranks, 4, prev=got0, bDoRootFind=False, bDoSplitDimFind=False)
+        assert [(c["iDim"], c["fSplit"]) for c in got2] == [(c["iDim"], c["fSplit"]) for c in got0]
+        d2, n2 = orb_oracle.domain_decomp(x, y, z, 4, prev=prev, do_root_find=False, do_split_dim_find=False)
+        assert [(n[1], n[2]) for n in sorted(n2, key=lambda n: n[0])] == [(c["iDim"], c["fSplit"]) for c in got2]
+    # the axis loop as written (pst.c:1900-1910) starts from 0.707 x the previous axis's extent but visits all three axes,
+    # the previous one included, so it always ends on the first axis of strictly largest extent
+    for ext in ((1.0, 1.2, 0.5), (1.2, 1.0, 0.5), (0.8, 0.75, 1.0), (1.0, 1.0, 1.0)):
+        lo, hi = np.zeros(3), np.array(ext)
+        for pd in (-1, 0, 1, 2):
+            assert orb_oracle.split_dim(lo, hi, pd) == int(np.argmax(ext))
