@@ -197,3 +197,39 @@ def test_repeated_decomposition_hysteresis_and_shortcuts():
         lo, hi = np.zeros(3), np.array(ext)
         for pd in (-1, 0, 1, 2):
             assert orb_oracle.split_dim(lo, hi, pd) == int(np.argmax(ext))
+
+
+def _reference_domains_live(p, nThreads, tmp):
+    """Run the compiled reference binary on nThreads pthread-MDL ranks (nSteps = 0) and return each rank's particles."""
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_golden_multirank import parse_dump
+    from oracle import reflib
+    ics.write_tipsy_native(os.path.join(tmp, "ic.tipsy"), p)
+    open(os.path.join(tmp, "run.param"), "w").write(
+        f"achInFile = {tmp}/ic.tipsy\nachOutName = {tmp}/out\nbPeriodic = 0\ndTheta = 0.7\nnSteps = 0\nbVStep = 1\n"
+        "bDoDensity = 0\niBinaryOutput = 0\nbParaRead = 0\nbParaWrite = 0\nbOverwrite = 1\n")
+    env = dict(os.environ, MDL_NTHREADS=str(nThreads), REF_DUMP=os.path.join(tmp, "dump"))
+    try:  # (what the binary does after the force evaluation is of no interest; the dumps are complete by then)
+        subprocess.run([reflib.BIN_PATH, "run.param"], cwd=tmp, env=env, stdout=subprocess.DEVNULL,
+                       stderr=subprocess.DEVNULL, timeout=60)
+    except subprocess.TimeoutExpired:
+        pass
+    return [np.sort(parse_dump(os.path.join(tmp, f"dump.rank{r}"))["iOrder"]) for r in range(nThreads)]
+
+
+@pytest.mark.parametrize("n,nThreads,seed", [(4000, 5, 31), (5000, 7, 33), (3500, 8, 32), (2999, 6, 34)])
+def test_orb_oracle_vs_reference_binary_live(n, nThreads, seed, tmp_path):
+    """Build container only: rank counts beyond the committed fixtures (5-8 ranks: uneven nLower/nUpper on several
+    levels, domain sizes that do not divide) -- the restatement and the driver reproduce the domains of the reference
+    binary run live."""
+    from oracle import reflib
+    if not os.path.exists(reflib.BIN_PATH):
+        pytest.skip("oracle/_ref/gasoline_ref not built (needs /root/reference)")
+    p = ics.plummer(n, seed=seed)
+    ref = _reference_domains_live(p, nThreads, str(tmp_path))
+    doms, _ = orb_oracle.domain_decomp(p.x, p.y, p.z, nThreads)
+    nodes, dest = _run_driver(p, nThreads, 3)
+    for r in range(nThreads):
+        assert np.array_equal(ref[r], doms[r]), f"rank {r}"
+        assert np.array_equal(np.nonzero(dest == r)[0], ref[r])
