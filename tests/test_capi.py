@@ -118,3 +118,41 @@ def test_bottom_up_moments_match_particle_sums(lib, name):
         assert err.max() < 2e-13, (l, err.max())
     # single-particle / zero-extent cells: both are exactly zero
     assert np.all(out[bmax == 0] == 0)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_host_tree_builder_random_configurations(lib, seed):
+    """gg_tree_build (the product's host-side pkdBuildBinary) against the oracle's tree on the seeded random sweep
+    (tests/random_cases.py: 1..2500 particles, nBucket 1..33, duplicates, partial active sets, open and periodic);
+    the oracle is pinned to the compiled reference on the same sweep (tests/test_oracle_vs_reference.py).  Bit-exact,
+    single- and multi-threaded."""
+    from gasoline_b200 import pkd as pk
+    from oracle import oracle
+    from random_cases import random_case
+    p, active, nBucket, theta, kw = random_case(seed)
+    o = oracle.OracleGravity(p, active=active)
+    o.build_tree(nBucket, theta, 4)
+    t = o.tree()
+    o.close()
+    for nthreads in (1, 4):
+        cols = [np.array(a, dtype=np.float64) for a in (p.x, p.y, p.z, p.m, p.h)]
+        order = np.zeros(p.n, np.int32)
+        act = None if active is None else active.astype(np.int32).copy()
+        bt = C.c_void_p()
+        assert lib.gg_tree_build(p.n, *[pk._d(c) for c in cols], None if act is None else pk._i(act), pk._i(order), nBucket,
+                                 theta, 4, nthreads, C.byref(bt)) == 0
+        v = pk.gg_tree()
+        root = np.zeros(35)
+        assert lib.gg_tree_view(bt, C.byref(v), pk._d(root)) == 0
+        nn = v.nNodes
+        assert nn == t["nNodes"] and v.iRoot == t["iRoot"]
+        arr = lambda ptr, shape: np.ctypeslib.as_array(ptr, shape=shape)
+        for k, shape in (("bnd", (nn, 6)), ("r", (nn, 3)), ("fMass", (nn,)), ("fSoft", (nn,)), ("fOpen2", (nn,)), ("mom", (nn, 31)),
+                         ("pLower", (nn,)), ("pUpper", (nn,)), ("iLower", (nn,)), ("iUpper", (nn,))):
+            assert np.array_equal(arr(getattr(v, k), shape), t[k]), (k, p.n, nBucket, nthreads)
+        assert np.array_equal(order, t["iOrder"])
+        assert np.array_equal(root, t["root"])
+        assert np.array_equal(cols[0], t["x"]) and np.array_equal(cols[4], t["h"])  # particles permuted into tree order
+        if act is not None:
+            assert np.array_equal(act, t["active"])
+        lib.gg_tree_free(bt)
