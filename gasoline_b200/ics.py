@@ -107,6 +107,33 @@ def write_tipsy_native(path: str, p: Particles, time: float = 0.0) -> None:
         rec.tofile(f)
 
 
+def write_tipsy_standard(path: str, p: Particles, time: float = 0.0) -> None:
+    """Standard Tipsy (bStandard = 1): the same field sequence as the native file written through XDR, i.e. big-endian
+    -- header double time, ints nbodies ndim nsph ndark nstar and one pad int (xdrHeader, master.c:3563-3575: 32 bytes),
+    then per dark particle 9 big-endian float32 (pkdReadTipsy's xdr_float sequence, pkd.c:456-560; sizes pkdSeek
+    pkd.c:253-283)."""
+    N = p.n
+    with open(path, "wb") as f:
+        f.write(struct.pack(">diiiiii", time, N, 3, 0, N, 0, 0))
+        rec = np.zeros((N, 9), dtype=">f4")
+        rec[:, 0] = p.m
+        rec[:, 1] = p.x
+        rec[:, 2] = p.y
+        rec[:, 3] = p.z
+        rec[:, 7] = p.h
+        rec.tofile(f)
+
+
+def read_tipsy_standard(path: str) -> Particles:
+    """Dark particles of a standard (XDR, big-endian) Tipsy file; gas records (12 floats) are skipped."""
+    with open(path, "rb") as f:
+        time, n, ndim, nsph, ndark, nstar, _pad = struct.unpack(">diiiiii", f.read(32))
+        f.seek(48 * nsph, 1)
+        rec = np.fromfile(f, dtype=">f4", count=9 * ndark).reshape(ndark, 9).astype(np.float64)
+    return Particles(rec[:, 1].copy(), rec[:, 2].copy(), rec[:, 3].copy(), rec[:, 0].copy(), rec[:, 7].copy(),
+                     (FLOAT_MAXVAL,) * 3, os.path.basename(path))
+
+
 def read_array_binary(path: str, ndim: int) -> np.ndarray:
     """Reference binary array output (iBinaryOutput=2): int N, then N doubles per dimension
     (master.c:5527, outtype.c:1001-1012). Returns (N, ndim)."""

@@ -61,3 +61,28 @@ def test_array_files_match_the_reference_binary(tmp_path, mode):
     p_ref = np.zeros(p.n); p_ref[order] = ref["pot"]
     # (the oracle's 1/sqrt differs from the reference's table-based v_sqrt1 by ~2e-10; %.14g keeps 14 digits)
     assert np.allclose(acc, a_ref, rtol=1e-8, atol=2e-9) and np.allclose(pot, p_ref, rtol=1e-8, atol=0)
+
+
+def test_standard_tipsy_is_read_by_the_reference_like_the_native_file(tmp_path):
+    """bStandard = 1 (XDR, big-endian; xdrHeader master.c:3563, pkdReadTipsy pkd.c:456-560): the reference binary reads
+    our standard file and writes the same force files, byte for byte, as from our native file of the same particles;
+    our reader inverts our writer."""
+    p = ics.plummer(500, seed=8)
+    tmp = str(tmp_path)
+    f = os.path.join(tmp, "ic.std")
+    ics.write_tipsy_standard(f, p)
+    assert os.path.getsize(f) == 32 + 36 * p.n
+    q = ics.read_tipsy_standard(f)
+    for k in ("x", "y", "z", "m", "h"):
+        assert np.array_equal(getattr(q, k), getattr(p, k))
+    ics.write_tipsy_native(os.path.join(tmp, "ic.tipsy"), p)
+    for name, infile, std in (("nat", "ic.tipsy", 0), ("std", "ic.std", 1)):
+        open(os.path.join(tmp, f"{name}.param"), "w").write(
+            f"achInFile = {infile}\nachOutName = out_{name}\nbStandard = {std}\nbPeriodic = 0\nnReplicas = 0\nbEwald = 0\n"
+            "dTheta = 0.7\nnSteps = 0\nbVStep = 1\nbDoDensity = 0\niBinaryOutput = 0\nbParaRead = 0\nbParaWrite = 0\nbOverwrite = 1\n")
+        subprocess.run([reflib.BIN_PATH, f"{name}.param"], cwd=tmp, env=dict(os.environ, MDL_NTHREADS="1"),
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=300, check=True)
+    for ext in ("accg", "pot"):
+        assert filecmp.cmp(os.path.join(tmp, f"out_nat.{ext}"), os.path.join(tmp, f"out_std.{ext}"), shallow=False), ext
+    acc = ics.read_array_ascii(os.path.join(tmp, "out_std.accg"), 3)
+    assert acc.shape == (p.n, 3) and np.isfinite(acc).all() and np.abs(acc).max() > 0
