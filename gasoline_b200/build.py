@@ -12,8 +12,13 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libgasoline_b200.so")
 SOURCES = ["gg_api.cu", "gg_tree_kernel.cu", "gg_ewald.cu", "gg_moments.cu", "gg_tree_gpu.cu", "gg_state.cu", "gg_orb.cu", "gg_tree_build.cpp"]
+# Host code is compiled without FP contraction: the bit-exact tree build (gg_tree_build.cpp) and the top-tree arithmetic
+# must round every product and sum like the reference's x86-64 build, also on hosts whose compiler fuses by default
+# (aarch64).  Device code: the translation units whose results are claimed bit-identical to the reference get
+# -fmad=false on top of their explicit __d*_rn intrinsics; the force kernels (k_eval, k_ewald, moments) keep FMA.
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC,-O3,-pthread", "--use_fast_math=false"]
+              "-Xcompiler", "-fPIC,-O3,-pthread,-ffp-contract=off"]
+NO_FMAD = {"gg_tree_gpu.cu", "gg_state.cu", "gg_orb.cu"}
 
 
 def _nvcc() -> str:
@@ -39,8 +44,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     procs = []
     for src in SOURCES:
         obj = os.path.join(LIB_DIR, src.rsplit(".", 1)[0] + ".o")
-        cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + (["-Xptxas", "-v"] if verbose else []) + \
-              ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [_nvcc()] + NVCC_FLAGS + (["-fmad=false"] if src in NO_FMAD else []) + \
+              (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, p in procs:

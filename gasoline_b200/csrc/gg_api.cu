@@ -117,8 +117,10 @@ int ensure(gg_context *c, DevBuf &b, size_t bytes, size_t preserve = 0) {
     void *np = nullptr;
     CK(cudaMalloc(&np, cap));
     if (preserve && b.p) CK(cudaMemcpyAsync(np, b.p, preserve, cudaMemcpyDeviceToDevice, c->st));
-    if (b.p) {
+    if (b.p) { // work reading the old buffer may be in flight on any of the context's streams
         CK(cudaStreamSynchronize(c->st));
+        if (c->st2) CK(cudaStreamSynchronize(c->st2));
+        if (c->st3) CK(cudaStreamSynchronize(c->st3));
         CK(cudaFree(b.p));
     }
     b.p = np;
@@ -978,14 +980,20 @@ int gg_state_gravstep(gg_context *c, double dEta, double *pdtMin) {
     int rc;
     if ((rc = ensure(c, c->misc, 16 * sizeof(int)))) return rc;
     unsigned long long *dMin = (unsigned long long *)((int *)c->misc.p + 14);
+    int *dBad = (int *)c->misc.p + 13;
     CK(cudaMemsetAsync(dMin, 0xff, sizeof(unsigned long long), c->st));
+    CK(cudaMemsetAsync(dBad, 0, sizeof(int), c->st));
     CK(gg_launch_gravstep(c->stateN, (double *)c->sdt.p, (const double *)c->dtg.p,
-                          c->stateHasActive ? (const int *)c->sact.p : nullptr, dEta, dMin, c->st));
+                          c->stateHasActive ? (const int *)c->sact.p : nullptr, dEta, dMin, dBad, c->st));
     ++c->nLaunches;
     unsigned long long bits = 0;
+    int nBad = 0;
     CK(cudaMemcpyAsync(&bits, dMin, sizeof(bits), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(&nBad, dBad, sizeof(nBad), cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
     if (pdtMin) memcpy(pdtMin, &bits, sizeof(double));
+    if (nBad) // the reference asserts (pkd.c:4616)
+        return fail(GG_ERR_ARG, "gg_state_gravstep: %d active particle(s) have dtGrav <= 0 (no interaction was evaluated for them)", nBad);
     return GG_OK;
 }
 
@@ -1057,14 +1065,17 @@ int gg_state_dt_to_rung(gg_context *c, int iRung, double dDelta, int iMaxRung, i
         return fail(GG_ERR_UNSUPPORTED, "gg_state_dt_to_rung: iRung=%d iMaxRung=%d (supported < 128)", iRung, iMaxRung);
     CK(cudaSetDevice(c->device));
     int rc;
-    if ((rc = ensure(c, c->srhist, 130 * sizeof(int)))) return rc;
+    if ((rc = ensure(c, c->srhist, 132 * sizeof(int)))) return rc;
     int *dh = (int *)c->srhist.p;
-    CK(cudaMemsetAsync(dh, 0, 130 * sizeof(int), c->st));
-    CK(gg_launch_dt_to_rung(c->stateN, (int *)c->sid.p, (const double *)c->sdt.p, iRung, dDelta, iMaxRung, bAll, dh, dh + 128, c->st));
+    CK(cudaMemsetAsync(dh, 0, 132 * sizeof(int), c->st));
+    CK(gg_launch_dt_to_rung(c->stateN, (int *)c->sid.p, (const double *)c->sdt.p, iRung, dDelta, iMaxRung, bAll, dh, dh + 128,
+                            dh + 130, c->st));
     ++c->nLaunches;
-    int h[130];
+    int h[132];
     CK(cudaMemcpyAsync(h, dh, sizeof(h), cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
+    if (h[130]) // the reference asserts both (pkd.c:4694, 4749)
+        return fail(GG_ERR_ARG, "gg_state_dt_to_rung: %d particle(s) have dt <= 0 or dDelta/dt >= 2.1e9", h[130]);
     int top = 0;
     for (int r = 127; r > 0; --r)
         if (h[r] > 0) { top = r; break; }
@@ -1080,7 +1091,7 @@ int gg_state_active_rung(gg_context *c, int iRung, int bGreater, int *pnActive) 
     int rc;
     const int n = c->stateN;
     if ((rc = ensure(c, c->sact, sizeof(int) * (size_t)n))) return rc;
-    if ((rc = ensure(c, c->srhist, 130 * sizeof(int)))) return rc;
+    if ((rc = ensure(c, c->srhist, 132 * sizeof(int)))) return rc;
     int *dCount = (int *)c->srhist.p + 129;
     CK(cudaMemsetAsync(dCount, 0, sizeof(int), c->st));
     CK(gg_launch_active_rung(n, (const int *)c->sid.p, (int *)c->sact.p, iRung, bGreater, dCount, c->st));
@@ -1106,6 +1117,7 @@ int gg_set_active(gg_context *c, const int *active) {
     const int np = L.nPart, nn = L.nNodes;
     int rc;
     const int *dActive = nullptr;
+    c->stateForces = false; // a new sink set: the last evaluation's results do not cover the newly active particles
     if (active) {
         if ((rc = ensure(c, c->active, (size_t)(np + 1) * sizeof(int)))) return rc;
         CK(cudaMemcpyAsync(c->active.p, active, sizeof(int) * np, cudaMemcpyDefault, c->st));
@@ -1607,7 +1619,9 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
         ++c->nLaunches;
     }
     CK(cudaEventRecord(c->ev[3], c->st));
-    if (prm->bComove && !prm->bPeriodic && !(prm->flags & GG_FLAG_WALK_ONLY) && n > 0) {
+    // (not in the bDoSun / single-bucket passes: the reference adds the term once per bucket of the main loop,
+    //  pkd.c:2967-2991, before the Sun pass)
+    if (prm->bComove && !prm->bPeriodic && !(prm->flags & GG_FLAG_WALK_ONLY) && n > 0 && !singleTask) {
         k_comove<<<(n + 255) / 256, 256, 0, c->st>>>(n, (const PartS *)c->parts.p, dActive, prm->dRhoFac,
                                                      (double *)c->acc.p, (double *)c->pot.p);
         CK(cudaGetLastError());
@@ -1709,6 +1723,12 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
     sa.fWeight = (double *)c->fweight.p;
     sa.hfWeight = (!walkOnly && dActive) ? c->zc[3] : nullptr; // partially active: only active entries may be written
     sa.sums = (unsigned long long *)c->sums.p;
+    // every exit below must leave st3 idle: k_stats reads counts / writes fweight, sums and the caller's mapped fWeight
+    struct St3Guard {
+        cudaStream_t s;
+        bool armed;
+        ~St3Guard() { if (armed) cudaStreamSynchronize(s); }
+    } st3Guard{c->st3, true};
     CK(gg_launch_stats_kernel(sa, c->st3));
     if (!walkOnly && c->zc[3] && !dActive && n > 0) // one coalesced copy (per-bucket 8-byte stores over PCIe cost ~1 ms per 1 M particles)
         CK(cudaMemcpyAsync(c->zcHost[3], c->fweight.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->st3));
@@ -1757,6 +1777,7 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
     CK(cudaMemcpyAsync(hs, c->sums.p, sizeof(hs), cudaMemcpyDeviceToHost, c->st));
     CK(cudaMemcpyAsync(hm, c->misc.p, sizeof(hm), cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
+    st3Guard.armed = false; // c->st waited for evStats
     tr.mark("gravity: final sync");
     if (evalQueued) c->momPending = false; // k_eval waited for the moments and has finished
     if (hm[1]) return fail(GG_ERR_UNSUPPORTED, "gg_gravity: walk frontier overflowed %d entries (tree too deep)", GG_STACK_CAP);
@@ -1942,6 +1963,7 @@ int gg_bucket_walk(gg_context *c, const gg_params *prm, int iBucket, int n3[3]) 
     gg_params p = *prm;
     p.flags |= GG_FLAG_WALK_ONLY;
     Task t{iBucket, 0, 0, 0};
+    c->stateForces = false; // run_gravity clears the device result arrays: a following kick must not consume them
     int rc = run_gravity(c, &p, &t, nullptr);
     if (rc) return rc;
     CK(cudaMemcpyAsync(n3, (int *)c->counts.p + 3 * (size_t)iBucket, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->st));

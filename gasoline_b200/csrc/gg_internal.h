@@ -193,7 +193,7 @@ cudaError_t gg_launch_kick(int n, double *v, const double *a, const int *active,
 cudaError_t gg_launch_drift(int n, double *x, double *y, double *z, const double *v, double dDelta, const double c[3],
                             int bPeriodic, const double L[3], int *nOutside, cudaStream_t st);
 cudaError_t gg_launch_gravstep(int n, double *dt, const double *dtGrav, const int *active, double dEta,
-                               unsigned long long *dtMinBits, cudaStream_t st);
+                               unsigned long long *dtMinBits, int *nBad, cudaStream_t st);
 cudaError_t gg_launch_permute(int n, const int *iorder, const double *vIn, double *vOut, const int *idIn, int *idOut,
                               const double *dtIn, double *dtOut, cudaStream_t st);
 cudaError_t gg_launch_state_init(int n, int *id, double *dt, double dt0, cudaStream_t st);
@@ -203,7 +203,7 @@ cudaError_t gg_launch_init_dt(int n, double *dt, const int *active, double dDelt
 cudaError_t gg_launch_accelstep(int n, double *dt, const double *a, const double *pot, const double *fSoft, const int *active,
                                 double dEta, double dAccFac, int bEpsAcc, int bSqrtPhi, cudaStream_t st);
 cudaError_t gg_launch_dt_to_rung(int n, int *idr, const double *dt, int iRung, double dDelta, int iMaxRung, int bAll, int *hist,
-                                 int *ideal, cudaStream_t st);
+                                 int *ideal, int *nBad, cudaStream_t st);
 cudaError_t gg_launch_active_rung(int n, const int *idr, int *active, int iRung, int bGreater, int *count, cudaStream_t st);
 
 // gg_orb.cu: the per-rank services of the ORB domain decomposition (pstCalcBound, pstWeight, the split's outcome) on

@@ -44,12 +44,13 @@ __global__ void __launch_bounds__(256) k_drift(int n, double *x, double *y, doub
 
 // dt = min(dt, dEta/sqrt(dtGrav)) on ACTIVE particles; the smallest dt of all particles -> dtMinBits (ordered integer)
 __global__ void __launch_bounds__(256) k_gravstep(int n, double *dt, const double *dtGrav, const int *active, double dEta,
-                                                  unsigned long long *dtMinBits) {
+                                                  unsigned long long *dtMinBits, int *nBad) {
     const int i = blockIdx.x * 256 + threadIdx.x;
     double d = __longlong_as_double(0x7ff0000000000000ll);
     if (i < n) {
         d = dt[i];
         if (!active || active[i]) {
+            if (!(dtGrav[i] > 0.0)) atomicAdd(nBad, 1); // the reference asserts dtGrav > 0 (pkd.c:4616)
             const double g = __ddiv_rn(dEta, __dsqrt_rn(dtGrav[i]));
             if (g < d) { d = g; dt[i] = d; }
         }
@@ -110,13 +111,15 @@ __global__ void __launch_bounds__(256) k_accelstep(int n, double *dt, const doub
 // pkdDtToRung (pkd.c:4715-4810) with pkdOneParticleDtToRung (pkd.c:4689-4712).  hist[r] counts the particles left on
 // rung r (ALL particles: the reference's iMaxRungOut / nMaxRung scan them all), ideal = max(rung + 1) before clamping.
 __global__ void __launch_bounds__(256) k_dt_to_rung(int n, int *idr, const double *dt, int iRung, double dDelta, int iMaxRung,
-                                                    int bAll, int *hist, int *ideal) {
+                                                    int bAll, int *hist, int *ideal, int *nBad) {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
     int r = idr[2 * (size_t)i + 1];
     if (r >= iRung) {
         if (bAll) {
             const double d = dt[i];
+            // the reference asserts dt > 0 (pkd.c:4749) and dDelta/dt < 2.1e9 (pkd.c:4694: integer overflow)
+            if (!(d > 0.0) || !(__ddiv_rn(dDelta, d) < 2.1e9)) { atomicAdd(nBad, 1); return; }
             int iSteps = (int)floor(__ddiv_rn(dDelta, d)), t = iRung;
             if (fmod(dDelta, d) == 0.0) iSteps--;
             if (iSteps < 0) iSteps = 0;
@@ -178,8 +181,8 @@ cudaError_t gg_launch_drift(int n, double *x, double *y, double *z, const double
     return cudaGetLastError();
 }
 cudaError_t gg_launch_gravstep(int n, double *dt, const double *dtGrav, const int *active, double dEta,
-                               unsigned long long *dtMinBits, cudaStream_t st) {
-    if (n > 0) k_gravstep<<<(n + 255) / 256, 256, 0, st>>>(n, dt, dtGrav, active, dEta, dtMinBits);
+                               unsigned long long *dtMinBits, int *nBad, cudaStream_t st) {
+    if (n > 0) k_gravstep<<<(n + 255) / 256, 256, 0, st>>>(n, dt, dtGrav, active, dEta, dtMinBits, nBad);
     return cudaGetLastError();
 }
 cudaError_t gg_launch_permute(int n, const int *iorder, const double *vIn, double *vOut, const int *idIn, int *idOut,
@@ -202,8 +205,8 @@ cudaError_t gg_launch_accelstep(int n, double *dt, const double *a, const double
     return cudaGetLastError();
 }
 cudaError_t gg_launch_dt_to_rung(int n, int *idr, const double *dt, int iRung, double dDelta, int iMaxRung, int bAll, int *hist,
-                                 int *ideal, cudaStream_t st) {
-    if (n > 0) k_dt_to_rung<<<(n + 255) / 256, 256, 0, st>>>(n, idr, dt, iRung, dDelta, iMaxRung, bAll, hist, ideal);
+                                 int *ideal, int *nBad, cudaStream_t st) {
+    if (n > 0) k_dt_to_rung<<<(n + 255) / 256, 256, 0, st>>>(n, idr, dt, iRung, dDelta, iMaxRung, bAll, hist, ideal, nBad);
     return cudaGetLastError();
 }
 cudaError_t gg_launch_active_rung(int n, const int *idr, int *active, int iRung, int bGreater, int *count, cudaStream_t st) {

@@ -89,4 +89,10 @@ def test_comove_background_term(gpu_lib):
     r = np.stack([pkd.x, pkd.y, pkd.z], axis=1)
     assert np.allclose((out["acc"] - plain["acc"])[act], 0.37 * r[act], rtol=1e-12, atol=1e-13)
     assert np.all(out["acc"][~act] == 0) and np.all(GOLD["comove_acc"][~act] == 0)
+    # bDoSun on top of bComove: the reference adds the background term once per bucket of the main loop, before the Sun
+    # pass (pkd.c:2967-2991 vs 3003-3041) -- the dummy sink's pass must not apply it a second time
+    both = pkd.pkdGravAll(GravityParams(nReps=0, bPeriodic=0, bEwald=0, bComove=1, dRhoFac=0.37, bDoSun=1, dSunSoft=0.01))
+    assert np.array_equal(both["acc"], out["acc"]) and np.array_equal(both["pot"], out["pot"])
+    sun_only = pkd.pkdGravAll(GravityParams(nReps=0, bPeriodic=0, bEwald=0, bDoSun=1, dSunSoft=0.01))
+    assert np.array_equal(both["aSun"], sun_only["aSun"])
     pkd.close()
