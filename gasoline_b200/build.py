@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libgasoline_b200.so")
-SOURCES = ["gg_api.cu", "gg_tree_kernel.cu", "gg_ewald.cu", "gg_moments.cu", "gg_tree_gpu.cu", "gg_state.cu", "gg_orb.cu", "gg_tree_build.cpp"]
+SOURCES = ["gg_api.cu", "gg_tree_kernel.cu", "gg_ewald.cu", "gg_moments.cu", "gg_tree_gpu.cu", "gg_state.cu", "gg_orb.cu", "gg_comm.cu", "gg_tree_build.cpp"]
 # Host code is compiled without FP contraction: the bit-exact tree build (gg_tree_build.cpp) and the top-tree arithmetic
 # must round every product and sum like the reference's x86-64 build, also on hosts whose compiler fuses by default
 # (aarch64).  Device code: the translation units whose results are claimed bit-identical to the reference get
@@ -54,7 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {src}")
-    subprocess.check_call([_nvcc(), "-shared", "-o", LIB_PATH] + objs + ["-lcudart", "-lpthread"])
+    subprocess.check_call([_nvcc(), "-shared", "-o", LIB_PATH] + objs + ["-lcudart", "-lpthread", "-ldl"])
     return LIB_PATH
 
 

@@ -11,7 +11,7 @@
 #include <string>
 #include <thread>
 #include <vector>
-#include "gg_internal.h"
+#include "gg_context.h"
 #include "gg_m2m.h"
 
 void gg_ewald_table_host(const double *root, double L, double fhCut, int iOrder, std::vector<double> &ewt);
@@ -20,7 +20,9 @@ namespace {
 
 thread_local char g_err[512] = "";
 
-int fail(int code, const char *fmt, ...) {
+} // namespace
+
+int gg_fail(int code, const char *fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
@@ -28,72 +30,6 @@ int fail(int code, const char *fmt, ...) {
     fprintf(stderr, "gasoline_b200: %s\n", g_err);
     return code;
 }
-
-#define CK(call)                                                                                        \
-    do {                                                                                                \
-        cudaError_t e_ = (call);                                                                        \
-        if (e_ != cudaSuccess)                                                                          \
-            return fail(GG_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
-    } while (0)
-
-struct DevBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-};
-
-struct Domain {
-    int id, nNodes, nPart, iRoot, nodeBase, partBase;
-};
-
-} // namespace
-
-struct gg_context {
-    int device = 0, nSM = 0;
-    cudaStream_t st = nullptr;
-    cudaStream_t st2 = nullptr; // the local domain's moments travel here while the walk already runs on st
-    cudaEvent_t evMom = nullptr;
-    cudaStream_t st3 = nullptr; // k_stats (bookkeeping + fWeight) runs here, beside the list scatter / evaluation
-    cudaEvent_t evWalk = nullptr, evStats = nullptr, evPacked = nullptr;
-    double *zc[4] = {nullptr, nullptr, nullptr, nullptr}; // device aliases of the caller's mapped a, fPot, dtGrav, fWeight
-    double *zcHost[4] = {nullptr, nullptr, nullptr, nullptr};
-    bool momPending = false;    // st2 work (moment upload + k_pack_mom) not yet known to be complete
-    cudaEvent_t ev[8];
-    // layout
-    int idSelf = 0;
-    std::vector<Domain> dom; // dom[0] = local
-    int nNodesAll = 0, nPartAll = 0, maxBucket = 1;
-    bool haveRoot = false;
-    double root[GG_NROOT];
-    // top tree (host copy, packed at gravity time)
-    int nTop = 0;
-    std::vector<int> topLower, topUsed;
-    std::vector<double> topR, topMass, topSoft, topOpen2, topMom;
-    std::vector<int> hActive; // host copy of the local ACTIVE flags (empty = all active)
-    // device buffers
-    DevBuf nodes, momf, momq, parts, active, hsoft, tasks, ngroups, goffs, counts, acc, pot, dtg, fweight, nloop, sums,
-        misc, imgoff, ewt, raw, rawi, cubtmp, flush, pool, nextblk, poolmask, isb, boffs, bnode, ghead, gcnt, bcnt, btot, boff64, lists, letflag, letfront, letidx, letout, letmisc, momraw, mparent, dbgtask, momout;
-    void *pinned = nullptr;
-    size_t pinnedCap = 0;
-    int nTasks = 0;
-    int nTasksLocal = 0, nBucketsLocal = 0, nPartUpload = 0; // the task list gg_set_local built
-    int nLaunches = 0;
-    size_t capBlocks = 0; // list pool capacity (blocks of 32 references), kept at the high-water mark
-    void *builder = nullptr; // gg_tree_gpu.cu workspace (gg_build_local)
-    GGBuiltDev built{};      // the last device-built tree (all zero: none)
-    bool rootLazy = false;   // the Ewald root expansion is to be read from the device-formed moments when first needed
-    double msBuild = 0.0;
-    // device-resident particle store (gg_state_*): positions / mass / softening / ACTIVE in tree order after every
-    // gg_state_build, velocities SoA [3][n], persistent particle id, time step
-    DevBuf sx, sy, sz, sm, sh, sact, svel, sid, sdt, svel2, sid2, sdt2, sacc, srhist;
-    int stateN = 0;
-    bool stateHasActive = false, stateDirty = true, stateForces = false;
-    bool sunMode = false; // run_gravity is evaluating the bDoSun dummy bucket: the particles' results stay as they are
-    // ORB domain decomposition services (gg_orb_*): the rank's particles for the decomposition and their PST cell
-    DevBuf ox, oy, oz, ow, ocell, okeys, ocnt, opart, osums;
-    int orbN = -1;          // -1: gg_orb_load not called
-    bool orbState = false;  // positions are the resident store's (sx, sy, sz)
-    bool orbWeights = false;
-};
 
 namespace {
 
@@ -111,7 +47,9 @@ struct Trace {
     }
 };
 
-int ensure(gg_context *c, DevBuf &b, size_t bytes, size_t preserve = 0) {
+} // namespace
+
+int gg_ensure(gg_context *c, DevBuf &b, size_t bytes, size_t preserve) {
     if (bytes <= b.cap) return GG_OK;
     size_t cap = bytes + bytes / 4 + 256;
     void *np = nullptr;
@@ -127,6 +65,8 @@ int ensure(gg_context *c, DevBuf &b, size_t bytes, size_t preserve = 0) {
     b.cap = cap;
     return GG_OK;
 }
+
+namespace {
 
 int ensure_pinned(gg_context *c, size_t bytes) {
     if (bytes <= c->pinnedCap) return GG_OK;
@@ -165,14 +105,18 @@ Images make_images(const gg_params *prm) {
     return im;
 }
 
+} // namespace
+
 // Wait for the asynchronous half of the last gg_set_local (moments) before touching what it reads or writes.
-int finish_mom(gg_context *c) {
+int gg_finish_mom(gg_context *c) {
     if (c->momPending) {
         CK(cudaStreamSynchronize(c->st2));
         c->momPending = false;
     }
     return GG_OK;
 }
+
+namespace {
 
 // raw staging layout for one domain (doubles): r[3n] fMass[n] fSoft[n] fOpen2[n] mom[31n]; ints: pLower pUpper
 // iLower iUpper [n each]
@@ -301,40 +245,86 @@ __global__ void k_let_seed(unsigned *front, int *count, int nRemote, int iRoot) 
 
 __global__ void k_let_reset(int *count, int level) { count[(level + 1) & 1] = 0; }
 
-// per node of one remote: 1 if kept / the particles it contributes (opened buckets only)
-__global__ void k_let_counts(int n, const NodeW *nodes, const unsigned char *flag, int *keep, int *npart) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const unsigned char f = flag[i];
-    keep[i] = f & 1;
-    npart[i] = (f == 3 && nodes[i].c0 < 0) ? nodes[i].nP : 0;
+// per (remote, node): 1 if kept / the particles it contributes (opened buckets only).  All remotes in one launch; the
+// per-remote segments are nn + 1 long (one trailing zero), so ONE exclusive scan over the concatenation numbers every
+// remote's kept nodes and travelling particles, and segment r's base is the scan value at r * (nn + 1).
+__global__ void k_let_counts(int nn, int nRemote, const NodeW *nodes, const unsigned char *flag, int *keep, int *npart) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t seg = (size_t)nn + 1;
+    if (t >= seg * nRemote + 1) return;
+    const int r = (int)(t / seg), i = (int)(t - (size_t)r * seg);
+    int k = 0, np = 0;
+    if (r < nRemote && i < nn) {
+        const unsigned char f = flag[(size_t)r * nn + i];
+        k = f & 1;
+        if (f == 3) {
+            const int4 d = __ldg(reinterpret_cast<const int4 *>(&nodes[i]) + 3);
+            if (d.x < 0) np = d.w;
+        }
+    }
+    keep[t] = k;
+    npart[t] = np;
 }
 
-__global__ void k_let_pack(int n, const NodeW *nodes, const float4 *momf, const double *momq, const PartS *parts,
-                           const unsigned char *flag, const int *newIdx, const int *newPart, NodeW *oNodes, float4 *oMomf,
-                           double *oMomq, PartS *oParts) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || !(flag[i] & 1)) return;
-    const bool open = flag[i] == 3;
-    NodeW w = nodes[i];
-    const int o = newIdx[i];
-    if (open && w.c0 >= 0) {
-        w.c0 = newIdx[w.c0];
-        w.c1 = w.c1 >= 0 ? newIdx[w.c1] : -1;
-        w.pLower = 0;
-    } else if (open) { // opened bucket: its particles travel
-        const int p0 = newPart[i];
-        for (int j = 0; j < w.nP; ++j) oParts[p0 + j] = parts[w.pLower + j];
-        w.pLower = p0;
-    } else { // never opened over there: a childless cell (nP >= 4 keeps it clear of the "< 4 particles" rule)
-        w.c0 = w.c1 = -1;
-        w.pLower = 0;
+// the scan values at the segment boundaries -> a small array for one copy to the host
+__global__ void k_let_bounds(int nn, int nRemote, const int *newIdx, const int *newPart, int *out) {
+    const int r = threadIdx.x;
+    if (r > nRemote) return;
+    const size_t at = (size_t)r * ((size_t)nn + 1);
+    out[2 * r] = newIdx[at];
+    out[2 * r + 1] = newPart[at];
+}
+
+struct LetPackArgs {
+    int nn, nRemote;
+    const NodeW *nodes;
+    const float4 *momf;
+    const double *momq;
+    const PartS *parts;
+    const unsigned char *flag;
+    const int *newIdx, *newPart;
+    int baseIdx[16], basePart[16];
+    NodeW *oNodes[16];
+    float4 *oMomf[16];
+    double *oMomq[16];
+    PartS *oParts[16];
+};
+
+// 8 lanes per kept node: the 64 B walk record (re-linked), the 128 B moment record and the 48 B quadrupole move as 16 B
+// pieces; the particles of an opened bucket are copied by the same 8 lanes
+__global__ void __launch_bounds__(256) k_let_pack(const LetPackArgs A) {
+    const size_t t = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int piece = threadIdx.x & 7;
+    if (t >= (size_t)A.nn * A.nRemote) return;
+    const int r = (int)(t / A.nn), i = (int)(t - (size_t)r * A.nn);
+    const unsigned char f = A.flag[t];
+    if (!(f & 1)) return;
+    const size_t seg = (size_t)r * ((size_t)A.nn + 1);
+    const int *nIdx = A.newIdx + seg;
+    const int o = nIdx[i] - A.baseIdx[r];
+    const bool open = f == 3;
+    const NodeW *src = &A.nodes[i];
+    const int4 links = __ldg(reinterpret_cast<const int4 *>(src) + 3);
+    const int p0 = A.newPart[seg + i] - A.basePart[r];
+    if (piece < 3) reinterpret_cast<uint4 *>(&A.oNodes[r][o])[piece] = __ldg(reinterpret_cast<const uint4 *>(src) + piece);
+    else if (piece == 3) {
+        int4 w = links;
+        if (open && w.x >= 0) { // opened cell: children re-numbered
+            w.x = nIdx[links.x] - A.baseIdx[r];
+            w.y = links.y >= 0 ? nIdx[links.y] - A.baseIdx[r] : -1;
+            w.z = 0;
+        } else if (open) w.z = p0; // opened bucket: its particles travel
+        else { w.x = w.y = -1; w.z = 0; } // never opened over there: a childless cell (nP >= 4 keeps it clear of walk.c:81)
+        reinterpret_cast<int4 *>(&A.oNodes[r][o])[3] = w;
     }
-    oNodes[o] = w;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) oMomf[(size_t)o * 8 + k] = momf[(size_t)i * 8 + k];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) oMomq[(size_t)o * 6 + k] = momq[(size_t)i * 6 + k];
+    A.oMomf[r][(size_t)o * 8 + piece] = __ldg(&A.momf[(size_t)i * 8 + piece]);
+    if (piece < 3)
+        reinterpret_cast<uint4 *>(&A.oMomq[r][(size_t)o * 6])[piece] = __ldg(reinterpret_cast<const uint4 *>(&A.momq[(size_t)i * 6]) + piece);
+    if (open && links.x < 0) {
+        const uint4 *ps = reinterpret_cast<const uint4 *>(&A.parts[links.z]);
+        uint4 *pd = reinterpret_cast<uint4 *>(&A.oParts[r][p0]);
+        for (int k = piece; k < 2 * links.w; k += 8) pd[k] = __ldg(ps + k);
+    }
 }
 
 // number of 8-sink passes each local bucket needs (0 for cells and for buckets without an active sink)
@@ -404,19 +394,19 @@ __global__ void __launch_bounds__(256) k_fma_peak(int iters, float *out) {
 // after the caller's next synchronisation of c->st.
 int build_task_list(gg_context *c, int nn, const int *dActive, int *hCounts) {
     int rc;
-    if ((rc = ensure(c, c->ngroups, (size_t)(nn + 1) * sizeof(int)))) return rc;
-    if ((rc = ensure(c, c->goffs, (size_t)(nn + 1) * sizeof(int)))) return rc;
-    if ((rc = ensure(c, c->isb, (size_t)(nn + 1) * sizeof(int)))) return rc;
-    if ((rc = ensure(c, c->boffs, (size_t)(nn + 1) * sizeof(int)))) return rc;
-    if ((rc = ensure(c, c->bnode, (size_t)(nn + 1) * sizeof(int)))) return rc;
+    if ((rc = gg_ensure(c, c->ngroups, (size_t)(nn + 1) * sizeof(int)))) return rc;
+    if ((rc = gg_ensure(c, c->goffs, (size_t)(nn + 1) * sizeof(int)))) return rc;
+    if ((rc = gg_ensure(c, c->isb, (size_t)(nn + 1) * sizeof(int)))) return rc;
+    if ((rc = gg_ensure(c, c->boffs, (size_t)(nn + 1) * sizeof(int)))) return rc;
+    if ((rc = gg_ensure(c, c->bnode, (size_t)(nn + 1) * sizeof(int)))) return rc;
     // every bucket has >= 1 particle, a bucket of nP particles has <= ceil(nP/8) passes: nn + nPart/8 bounds the tasks
-    if ((rc = ensure(c, c->tasks, ((size_t)nn + (size_t)c->nPartUpload / GG_MAX_SINKS + 2) * sizeof(Task)))) return rc;
+    if ((rc = gg_ensure(c, c->tasks, ((size_t)nn + (size_t)c->nPartUpload / GG_MAX_SINKS + 2) * sizeof(Task)))) return rc;
     k_count_groups<<<(nn + 255) / 256, 256, 0, c->st>>>(nn, (const NodeW *)c->nodes.p, dActive, (int *)c->ngroups.p,
                                                         (int *)c->isb.p);
     CK(cudaGetLastError());
     size_t tmpBytes = 0;
     CK(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, (int *)c->ngroups.p, (int *)c->goffs.p, nn + 1, c->st));
-    if ((rc = ensure(c, c->cubtmp, tmpBytes))) return rc;
+    if ((rc = gg_ensure(c, c->cubtmp, tmpBytes))) return rc;
     CK(cudaMemsetAsync((int *)c->ngroups.p + nn, 0, sizeof(int), c->st));
     CK(cudaMemsetAsync((int *)c->isb.p + nn, 0, sizeof(int), c->st));
     CK(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmpBytes, (int *)c->ngroups.p, (int *)c->goffs.p, nn + 1, c->st));
@@ -439,20 +429,20 @@ int upload_domain(gg_context *c, const gg_tree *t, const gg_particles *pp, int n
     size_t nd = (size_t)nn * (3 + 3) + nMomD + (size_t)np * 5;
     int rc;
     Trace tr;
-    if ((rc = finish_mom(c))) return rc;
+    if ((rc = gg_finish_mom(c))) return rc;
     tr.mark("  upload: finish_mom");
-    if ((rc = ensure(c, c->raw, nd * sizeof(double)))) return rc;
-    if ((rc = ensure(c, c->rawi, (size_t)nn * 4 * sizeof(int)))) return rc;
+    if ((rc = gg_ensure(c, c->raw, nd * sizeof(double)))) return rc;
+    if ((rc = gg_ensure(c, c->rawi, (size_t)nn * 4 * sizeof(int)))) return rc;
     double *d = (double *)c->raw.p;
     double *dr = d, *dM = dr + 3 * (size_t)nn, *dS = dM + nn, *dO = dS + nn, *dmom = dO + nn;
     double *dx = dmom + nMomD, *dy = dx + np, *dz = dy + np, *dm = dz + np, *dh = dm + np;
     int *di = (int *)c->rawi.p;
     const size_t keepN = (size_t)nodeBase, keepP = (size_t)partBase;
-    if ((rc = ensure(c, c->nodes, (keepN + nn + GG_MAX_TOP) * sizeof(NodeW), keepN * sizeof(NodeW)))) return rc;
-    if ((rc = ensure(c, c->momf, (keepN + nn + GG_MAX_TOP) * 128, keepN * 128))) return rc;
-    if ((rc = ensure(c, c->momq, (keepN + nn + GG_MAX_TOP) * 48, keepN * 48))) return rc;
-    if ((rc = ensure(c, c->parts, (keepP + np + 1) * sizeof(PartS), keepP * sizeof(PartS)))) return rc;
-    if (local && (rc = ensure(c, c->hsoft, (size_t)(np + 1) * sizeof(double)))) return rc;
+    if ((rc = gg_ensure(c, c->nodes, (keepN + nn + GG_MAX_TOP) * sizeof(NodeW), keepN * sizeof(NodeW)))) return rc;
+    if ((rc = gg_ensure(c, c->momf, (keepN + nn + GG_MAX_TOP) * 128, keepN * 128))) return rc;
+    if ((rc = gg_ensure(c, c->momq, (keepN + nn + GG_MAX_TOP) * 48, keepN * 48))) return rc;
+    if ((rc = gg_ensure(c, c->parts, (keepP + np + 1) * sizeof(PartS), keepP * sizeof(PartS)))) return rc;
+    if (local && (rc = gg_ensure(c, c->hsoft, (size_t)(np + 1) * sizeof(double)))) return rc;
     // ---- what the walk needs, on the main stream (issued first: the copy engine serves it first)
     if (nn > 0) {
         CK(cudaMemcpyAsync(dr, t->r, sizeof(double) * 3 * nn, kind, c->st));
@@ -485,7 +475,7 @@ int upload_domain(gg_context *c, const gg_tree *t, const gg_particles *pp, int n
                 c->momPending = true;
             }
         }
-        if ((rc = ensure(c, c->misc, 16 * sizeof(int)))) return rc;
+        if ((rc = gg_ensure(c, c->misc, 16 * sizeof(int)))) return rc;
         CK(cudaMemsetAsync((int *)c->misc.p + 8, 0, 2 * sizeof(int), c->st));
         k_pack_nodes<<<(nn + 127) / 128, 128, 0, c->st>>>(nn, dr, dM, dS, dO, di, di + nn, di + 2 * (size_t)nn,
                                                           di + 3 * (size_t)nn, nodeBase, partBase, (NodeW *)c->nodes.p,
@@ -502,8 +492,8 @@ int upload_domain(gg_context *c, const gg_tree *t, const gg_particles *pp, int n
     if (devMom && nn > 0) {
         // moments from the packed walk records + the FP64 particle columns still in the staging buffer; for the local
         // domain on the second stream, beside the walk of the following gg_gravity (k_eval waits for evMom)
-        if ((rc = ensure(c, c->momraw, (size_t)nn * 32 * sizeof(double)))) return rc;
-        if ((rc = ensure(c, c->mparent, (size_t)nn * 2 * sizeof(int)))) return rc;
+        if ((rc = gg_ensure(c, c->momraw, (size_t)nn * 32 * sizeof(double)))) return rc;
+        if ((rc = gg_ensure(c, c->mparent, (size_t)nn * 2 * sizeof(int)))) return rc;
         if (local) {
             CK(cudaEventRecord(c->evPacked, c->st));
             CK(cudaStreamWaitEvent(c->st2, c->evPacked, 0));
@@ -523,7 +513,7 @@ int upload_domain(gg_context *c, const gg_tree *t, const gg_particles *pp, int n
     if (local) {
         const int *dActive = nullptr;
         if (pp->active) {
-            if ((rc = ensure(c, c->active, (size_t)(np + 1) * sizeof(int)))) return rc;
+            if ((rc = gg_ensure(c, c->active, (size_t)(np + 1) * sizeof(int)))) return rc;
             CK(cudaMemcpyAsync(c->active.p, pp->active, sizeof(int) * np, cudaMemcpyDefault, c->st));
             dActive = (const int *)c->active.p;
         }
@@ -536,9 +526,9 @@ int upload_domain(gg_context *c, const gg_tree *t, const gg_particles *pp, int n
     CK(cudaStreamSynchronize(c->st));
     tr.mark("  upload: sync");
     if (hChk[1])
-        return fail(GG_ERR_ARG, "gg_set_%s: %d bucket(s) span particles outside [0,%d)", local ? "local" : "remote", hChk[1], np);
+        return gg_fail(GG_ERR_ARG, "gg_set_%s: %d bucket(s) span particles outside [0,%d)", local ? "local" : "remote", hChk[1], np);
     if (hChk[0] > GG_MAX_BUCKET)
-        return fail(GG_ERR_UNSUPPORTED, "gg_set_%s: a bucket holds %d particles (limit GG_MAX_BUCKET=%d)",
+        return gg_fail(GG_ERR_UNSUPPORTED, "gg_set_%s: a bucket holds %d particles (limit GG_MAX_BUCKET=%d)",
                     local ? "local" : "remote", hChk[0], GG_MAX_BUCKET);
     if (local) {
         c->maxBucket = hChk[0] > 1 ? hChk[0] : 1;
@@ -556,19 +546,19 @@ const char *gg_last_error(void) { return g_err; }
 int gg_version(void) { return 100; }
 
 int gg_create(gg_context **pctx, int device) {
-    if (!pctx) return fail(GG_ERR_ARG, "gg_create: null out pointer");
+    if (!pctx) return gg_fail(GG_ERR_ARG, "gg_create: null out pointer");
     int nDev = 0;
     cudaError_t e = cudaGetDeviceCount(&nDev);
     if (e != cudaSuccess || nDev == 0)
-        return fail(GG_ERR_CUDA, "gg_create: no usable CUDA device (%s); this library has no CPU path",
+        return gg_fail(GG_ERR_CUDA, "gg_create: no usable CUDA device (%s); this library has no CPU path",
                     e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
     if (device < 0) CK(cudaGetDevice(&device));
-    if (device >= nDev) return fail(GG_ERR_ARG, "gg_create: device %d of %d", device, nDev);
+    if (device >= nDev) return gg_fail(GG_ERR_ARG, "gg_create: device %d of %d", device, nDev);
     CK(cudaSetDevice(device));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10)
-        return fail(GG_ERR_UNSUPPORTED, "gg_create: device %s is sm_%d%d; this build targets sm_100a only", prop.name,
+        return gg_fail(GG_ERR_UNSUPPORTED, "gg_create: device %s is sm_%d%d; this build targets sm_100a only", prop.name,
                     prop.major, prop.minor);
     gg_context *c = new gg_context();
     c->device = device;
@@ -581,6 +571,7 @@ int gg_create(gg_context **pctx, int device) {
     CK(cudaEventCreateWithFlags(&c->evStats, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->evPacked, cudaEventDisableTiming));
     for (auto &ev : c->ev) CK(cudaEventCreate(&ev));
+    for (auto &ev : c->evx) CK(cudaEventCreate(&ev));
     *pctx = c;
     return GG_OK;
 }
@@ -601,6 +592,11 @@ void gg_destroy(gg_context *c) {
                      &c->okeys, &c->ocnt, &c->opart, &c->osums};
     for (DevBuf *b : all)
         if (b->p) cudaFree(b->p);
+    gg_comm_release(c);
+    if (c->letrecv.p) cudaFree(c->letrecv.p);
+    if (c->commscratch.p) cudaFree(c->commscratch.p);
+    for (auto &ev : c->evx)
+        if (ev) cudaEventDestroy(ev);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->builder) gg_builder_free(c->builder);
     for (auto &ev : c->ev) cudaEventDestroy(ev);
@@ -615,7 +611,7 @@ void gg_destroy(gg_context *c) {
 }
 
 int gg_host_alloc(void **p, size_t bytes) {
-    if (!p) return fail(GG_ERR_ARG, "gg_host_alloc: null");
+    if (!p) return gg_fail(GG_ERR_ARG, "gg_host_alloc: null");
     CK(cudaMallocHost(p, bytes ? bytes : 1));
     return GG_OK;
 }
@@ -625,9 +621,9 @@ int gg_host_free(void *p) {
 }
 
 int gg_set_local(gg_context *c, int idSelf, const gg_tree *t, const gg_particles *pp) {
-    if (!c || !t || !pp) return fail(GG_ERR_ARG, "gg_set_local: null argument");
+    if (!c || !t || !pp) return gg_fail(GG_ERR_ARG, "gg_set_local: null argument");
     if (t->nNodes < 1 || pp->n < 0 || t->iRoot < 0 || t->iRoot >= t->nNodes)
-        return fail(GG_ERR_ARG, "gg_set_local: nNodes=%d n=%d iRoot=%d", t->nNodes, pp->n, t->iRoot);
+        return gg_fail(GG_ERR_ARG, "gg_set_local: nNodes=%d n=%d iRoot=%d", t->nNodes, pp->n, t->iRoot);
     CK(cudaSetDevice(c->device));
     Trace tr;
     c->dom.clear();
@@ -642,6 +638,8 @@ int gg_set_local(gg_context *c, int idSelf, const gg_tree *t, const gg_particles
     c->dom.push_back(Domain{idSelf, t->nNodes, pp->n, t->iRoot, 0, 0});
     c->nNodesAll = t->nNodes;
     c->nPartAll = pp->n;
+    c->haveRootBnd = t->bnd != nullptr;
+    if (t->bnd) memcpy(c->rootBnd, t->bnd + 6 * (size_t)t->iRoot, sizeof(c->rootBnd));
     if (pp->active) c->hActive.assign(pp->active, pp->active + pp->n); // (the device copy went up with the domain)
     else c->hActive.clear();
     return GG_OK;
@@ -651,7 +649,7 @@ int gg_set_local(gg_context *c, int idSelf, const gg_tree *t, const gg_particles
 // device-built tree: exactly the RAW moment record gg_moments.cu leaves for the root cell.
 static int fetch_root_lazy(gg_context *c) {
     if (!c->rootLazy) return GG_OK;
-    int rc = finish_mom(c);
+    int rc = gg_finish_mom(c);
     if (rc) return rc;
     const int iRoot = c->dom[0].iRoot;
     double raw[32];
@@ -673,13 +671,13 @@ static int fetch_root_lazy(gg_context *c) {
 static int build_and_load(gg_context *c, int idSelf, const gg_particles *pp, int nBucket, double dTheta, int *iOrder,
                           int *pnNodes, double *root) {
     int rc;
-    if ((rc = finish_mom(c))) return rc;
+    if ((rc = gg_finish_mom(c))) return rc;
     char msg[400];
     int nl = 0;
     GGBuiltDev b{};
     CK(cudaEventRecord(c->ev[6], c->st));
     rc = gg_builder_run(&c->builder, pp, nBucket, dTheta, c->st, &b, &nl, msg, sizeof(msg));
-    if (rc) return fail(rc, "%s", msg);
+    if (rc) return gg_fail(rc, "%s", msg);
     CK(cudaEventRecord(c->ev[7], c->st));
     c->nLaunches += nl;
     c->dom.clear();
@@ -696,6 +694,8 @@ static int build_and_load(gg_context *c, int idSelf, const gg_particles *pp, int
     c->nNodesAll = t.nNodes;
     c->nPartAll = dp.n;
     c->built = b;
+    CK(cudaMemcpyAsync(c->rootBnd, b.bnd, sizeof(c->rootBnd), cudaMemcpyDeviceToHost, c->st)); // (pre-order: root = cell 0)
+    c->haveRootBnd = true;
     if (b.active) {
         c->hActive.resize((size_t)dp.n);
         CK(cudaMemcpyAsync(c->hActive.data(), b.active, sizeof(int) * dp.n, cudaMemcpyDeviceToHost, c->st));
@@ -717,10 +717,10 @@ static int build_and_load(gg_context *c, int idSelf, const gg_particles *pp, int
 
 int gg_build_local(gg_context *c, int idSelf, const gg_particles *pp, int nBucket, double dTheta, int *iOrder,
                    int *pnNodes, double *root) {
-    if (!c || !pp) return fail(GG_ERR_ARG, "gg_build_local: null argument");
+    if (!c || !pp) return gg_fail(GG_ERR_ARG, "gg_build_local: null argument");
     if (pp->n < 1 || !pp->x || !pp->y || !pp->z || !pp->fMass || !pp->fSoft || nBucket < 1 || nBucket > GG_MAX_BUCKET ||
         !(dTheta > 0))
-        return fail(GG_ERR_ARG, "gg_build_local: n=%d nBucket=%d dTheta=%g", pp->n, nBucket, dTheta);
+        return gg_fail(GG_ERR_ARG, "gg_build_local: n=%d nBucket=%d dTheta=%g", pp->n, nBucket, dTheta);
     CK(cudaSetDevice(c->device));
     c->stateN = 0; // a tree built from host particles replaces any resident store
     return build_and_load(c, idSelf, pp, nBucket, dTheta, iOrder, pnNodes, root);
@@ -731,17 +731,17 @@ int gg_build_local(gg_context *c, int idSelf, const gg_particles *pp, int nBucke
 
 namespace {
 int orb_query(const char *who, gg_context *c, int nCells, const int *iCell, const int *iDim, const double *fSplit, OrbQuery &q) {
-    if (!c || c->orbN < 0) return fail(GG_ERR_ARG, "%s: no particles loaded (gg_orb_load)", who);
-    if (nCells < 1 || nCells > GG_ORB_MAX_SLOTS || !iCell) return fail(GG_ERR_ARG, "%s: nCells=%d (1..%d)", who, nCells, GG_ORB_MAX_SLOTS);
+    if (!c || c->orbN < 0) return gg_fail(GG_ERR_ARG, "%s: no particles loaded (gg_orb_load)", who);
+    if (nCells < 1 || nCells > GG_ORB_MAX_SLOTS || !iCell) return gg_fail(GG_ERR_ARG, "%s: nCells=%d (1..%d)", who, nCells, GG_ORB_MAX_SLOTS);
     q.nSlots = nCells;
     for (int s = 0; s < nCells; ++s) {
-        if (iCell[s] < 1 || iCell[s] >= GG_ORB_MAX_CELL) return fail(GG_ERR_ARG, "%s: PST cell %d outside 1..%d", who, iCell[s], GG_ORB_MAX_CELL - 1);
+        if (iCell[s] < 1 || iCell[s] >= GG_ORB_MAX_CELL) return gg_fail(GG_ERR_ARG, "%s: PST cell %d outside 1..%d", who, iCell[s], GG_ORB_MAX_CELL - 1);
         for (int t = 0; t < s; ++t)
-            if (iCell[t] == iCell[s]) return fail(GG_ERR_ARG, "%s: PST cell %d asked about twice", who, iCell[s]);
+            if (iCell[t] == iCell[s]) return gg_fail(GG_ERR_ARG, "%s: PST cell %d asked about twice", who, iCell[s]);
         q.cell[s] = iCell[s];
         q.dim[s] = iDim ? iDim[s] : 0;
         q.split[s] = fSplit ? fSplit[s] : 0.0;
-        if (q.dim[s] < 0 || q.dim[s] > 2) return fail(GG_ERR_ARG, "%s: split axis %d", who, q.dim[s]);
+        if (q.dim[s] < 0 || q.dim[s] > 2) return gg_fail(GG_ERR_ARG, "%s: split axis %d", who, q.dim[s]);
     }
     return GG_OK;
 }
@@ -752,29 +752,29 @@ const double *orb_pos(gg_context *c, int k) {
 } // namespace
 
 int gg_orb_load(gg_context *c, int n, const double *x, const double *y, const double *z, const double *fWeight) {
-    if (!c || n < 0) return fail(GG_ERR_ARG, "gg_orb_load: bad argument (n=%d)", n);
+    if (!c || n < 0) return gg_fail(GG_ERR_ARG, "gg_orb_load: bad argument (n=%d)", n);
     CK(cudaSetDevice(c->device));
     int rc;
     const bool fromState = !x && !y && !z;
     if (fromState) {
-        if (c->stateN < 1 || n != c->stateN) return fail(GG_ERR_ARG, "gg_orb_load: x == NULL means the resident store, which holds %d particles (n=%d)", c->stateN, n);
-    } else if (n > 0 && (!x || !y || !z)) return fail(GG_ERR_ARG, "gg_orb_load: x, y, z must all be given (or all NULL)");
+        if (c->stateN < 1 || n != c->stateN) return gg_fail(GG_ERR_ARG, "gg_orb_load: x == NULL means the resident store, which holds %d particles (n=%d)", c->stateN, n);
+    } else if (n > 0 && (!x || !y || !z)) return gg_fail(GG_ERR_ARG, "gg_orb_load: x, y, z must all be given (or all NULL)");
     const size_t nb = sizeof(double) * (size_t)(n > 0 ? n : 1);
     if (!fromState) {
         const double *src[] = {x, y, z};
         DevBuf *dst[] = {&c->ox, &c->oy, &c->oz};
         for (int k = 0; k < 3; ++k) {
-            if ((rc = ensure(c, *dst[k], nb))) return rc;
+            if ((rc = gg_ensure(c, *dst[k], nb))) return rc;
             if (n > 0) CK(cudaMemcpyAsync(dst[k]->p, src[k], sizeof(double) * (size_t)n, cudaMemcpyDefault, c->st));
         }
     }
     if (fWeight) {
-        if ((rc = ensure(c, c->ow, nb))) return rc;
+        if ((rc = gg_ensure(c, c->ow, nb))) return rc;
         if (n > 0) CK(cudaMemcpyAsync(c->ow.p, fWeight, sizeof(double) * (size_t)n, cudaMemcpyDefault, c->st));
     }
-    if ((rc = ensure(c, c->ocell, sizeof(int) * (size_t)(n > 0 ? n : 1))) || (rc = ensure(c, c->okeys, sizeof(unsigned long long) * 6 * GG_ORB_MAX_SLOTS)) ||
-        (rc = ensure(c, c->ocnt, sizeof(int) * 2 * GG_ORB_MAX_SLOTS)) || (rc = ensure(c, c->osums, sizeof(double) * 2 * GG_ORB_MAX_SLOTS)) ||
-        (rc = ensure(c, c->opart, gg_orb_part_bytes(n))))
+    if ((rc = gg_ensure(c, c->ocell, sizeof(int) * (size_t)(n > 0 ? n : 1))) || (rc = gg_ensure(c, c->okeys, sizeof(unsigned long long) * 6 * GG_ORB_MAX_SLOTS)) ||
+        (rc = gg_ensure(c, c->ocnt, sizeof(int) * 2 * GG_ORB_MAX_SLOTS)) || (rc = gg_ensure(c, c->osums, sizeof(double) * 2 * GG_ORB_MAX_SLOTS)) ||
+        (rc = gg_ensure(c, c->opart, gg_orb_part_bytes(n))))
         return rc;
     CK(gg_launch_orb_init(n, (int *)c->ocell.p, c->st));
     ++c->nLaunches;
@@ -789,7 +789,7 @@ int gg_orb_bounds(gg_context *c, int nCells, const int *iCell, double *bnd, int 
     OrbQuery q;
     int rc;
     if ((rc = orb_query("gg_orb_bounds", c, nCells, iCell, nullptr, nullptr, q))) return rc;
-    if (!bnd || !nIn) return fail(GG_ERR_ARG, "gg_orb_bounds: bnd and nIn must be given");
+    if (!bnd || !nIn) return gg_fail(GG_ERR_ARG, "gg_orb_bounds: bnd and nIn must be given");
     CK(cudaSetDevice(c->device));
     CK(gg_launch_orb_bounds(q, c->orbN, orb_pos(c, 0), orb_pos(c, 1), orb_pos(c, 2), (const int *)c->ocell.p,
                             (unsigned long long *)c->okeys.p, (int *)c->ocnt.p, c->st));
@@ -814,7 +814,7 @@ int gg_orb_weight(gg_context *c, int nCells, const int *iCell, const int *iDim, 
                   double *fLow, double *fHigh) {
     OrbQuery q;
     int rc;
-    if (!iDim || !fSplit || !nLow || !nHigh || !fLow || !fHigh) return fail(GG_ERR_ARG, "gg_orb_weight: NULL argument");
+    if (!iDim || !fSplit || !nLow || !nHigh || !fLow || !fHigh) return gg_fail(GG_ERR_ARG, "gg_orb_weight: NULL argument");
     if ((rc = orb_query("gg_orb_weight", c, nCells, iCell, iDim, fSplit, q))) return rc;
     CK(cudaSetDevice(c->device));
     const double *w = c->orbWeights ? (const double *)c->ow.p : nullptr;
@@ -837,10 +837,10 @@ int gg_orb_weight(gg_context *c, int nCells, const int *iCell, const int *iDim, 
 int gg_orb_split(gg_context *c, int nCells, const int *iCell, const int *iDim, const double *fSplit) {
     OrbQuery q;
     int rc;
-    if (!iDim || !fSplit) return fail(GG_ERR_ARG, "gg_orb_split: NULL argument");
+    if (!iDim || !fSplit) return gg_fail(GG_ERR_ARG, "gg_orb_split: NULL argument");
     if ((rc = orb_query("gg_orb_split", c, nCells, iCell, iDim, fSplit, q))) return rc;
     for (int s = 0; s < nCells; ++s)
-        if (2 * q.cell[s] + 1 >= GG_ORB_MAX_CELL) return fail(GG_ERR_ARG, "gg_orb_split: children of PST cell %d exceed %d", q.cell[s], GG_ORB_MAX_CELL - 1);
+        if (2 * q.cell[s] + 1 >= GG_ORB_MAX_CELL) return gg_fail(GG_ERR_ARG, "gg_orb_split: children of PST cell %d exceed %d", q.cell[s], GG_ORB_MAX_CELL - 1);
     CK(cudaSetDevice(c->device));
     CK(gg_launch_orb_split(q, c->orbN, orb_pos(c, 0), orb_pos(c, 1), orb_pos(c, 2), (int *)c->ocell.p, c->st));
     ++c->nLaunches;
@@ -849,7 +849,7 @@ int gg_orb_split(gg_context *c, int nCells, const int *iCell, const int *iDim, c
 }
 
 int gg_orb_fetch(gg_context *c, int *iCellOfParticle) {
-    if (!c || c->orbN < 0 || !iCellOfParticle) return fail(GG_ERR_ARG, "gg_orb_fetch: no particles loaded (gg_orb_load) or NULL argument");
+    if (!c || c->orbN < 0 || !iCellOfParticle) return gg_fail(GG_ERR_ARG, "gg_orb_fetch: no particles loaded (gg_orb_load) or NULL argument");
     CK(cudaSetDevice(c->device));
     if (c->orbN > 0) CK(cudaMemcpyAsync(iCellOfParticle, c->ocell.p, sizeof(int) * (size_t)c->orbN, cudaMemcpyDefault, c->st));
     CK(cudaStreamSynchronize(c->st));
@@ -862,18 +862,18 @@ int gg_state_load(gg_context *c, int n, const double *x, const double *y, const 
                   const double *vy, const double *vz, const double *fMass, const double *fSoft, const int *active,
                   double dt0) {
     if (!c || n < 1 || !x || !y || !z || !vx || !vy || !vz || !fMass || !fSoft)
-        return fail(GG_ERR_ARG, "gg_state_load: bad argument (n=%d)", n);
+        return gg_fail(GG_ERR_ARG, "gg_state_load: bad argument (n=%d)", n);
     CK(cudaSetDevice(c->device));
     int rc;
-    if ((rc = finish_mom(c))) return rc;
+    if ((rc = gg_finish_mom(c))) return rc;
     const size_t nb = sizeof(double) * (size_t)n;
     DevBuf *d8[] = {&c->sx, &c->sy, &c->sz, &c->sm, &c->sh, &c->sdt, &c->sdt2};
     for (DevBuf *b : d8)
-        if ((rc = ensure(c, *b, nb))) return rc;
-    if ((rc = ensure(c, c->svel, 3 * nb)) || (rc = ensure(c, c->svel2, 3 * nb))) return rc;
+        if ((rc = gg_ensure(c, *b, nb))) return rc;
+    if ((rc = gg_ensure(c, c->svel, 3 * nb)) || (rc = gg_ensure(c, c->svel2, 3 * nb))) return rc;
     // sid: (persistent id, rung) pairs
-    if ((rc = ensure(c, c->sid, sizeof(int) * 2 * (size_t)n)) || (rc = ensure(c, c->sid2, sizeof(int) * 2 * (size_t)n)) ||
-        (rc = ensure(c, c->sact, sizeof(int) * (size_t)n)))
+    if ((rc = gg_ensure(c, c->sid, sizeof(int) * 2 * (size_t)n)) || (rc = gg_ensure(c, c->sid2, sizeof(int) * 2 * (size_t)n)) ||
+        (rc = gg_ensure(c, c->sact, sizeof(int) * (size_t)n)))
         return rc;
     const double *src[] = {x, y, z, fMass, fSoft};
     DevBuf *dst[] = {&c->sx, &c->sy, &c->sz, &c->sm, &c->sh};
@@ -894,9 +894,9 @@ int gg_state_load(gg_context *c, int n, const double *x, const double *y, const 
 }
 
 int gg_state_build(gg_context *c, int idSelf, int nBucket, double dTheta, int *pnNodes) {
-    if (!c || c->stateN < 1) return fail(GG_ERR_ARG, "gg_state_build: no resident particles (gg_state_load)");
+    if (!c || c->stateN < 1) return gg_fail(GG_ERR_ARG, "gg_state_build: no resident particles (gg_state_load)");
     if (nBucket < 1 || nBucket > GG_MAX_BUCKET || !(dTheta > 0))
-        return fail(GG_ERR_ARG, "gg_state_build: nBucket=%d dTheta=%g", nBucket, dTheta);
+        return gg_fail(GG_ERR_ARG, "gg_state_build: nBucket=%d dTheta=%g", nBucket, dTheta);
     CK(cudaSetDevice(c->device));
     const int n = c->stateN;
     gg_particles pp{};
@@ -927,18 +927,18 @@ int gg_state_build(gg_context *c, int idSelf, int nBucket, double dTheta, int *p
 }
 
 int gg_state_kick(gg_context *c, double dvFacOne, double dvFacTwo, const double *a) {
-    if (!c || c->stateN < 1) return fail(GG_ERR_ARG, "gg_state_kick: no resident particles (gg_state_load)");
+    if (!c || c->stateN < 1) return gg_fail(GG_ERR_ARG, "gg_state_kick: no resident particles (gg_state_load)");
     CK(cudaSetDevice(c->device));
     const int n = c->stateN;
     const double *da = nullptr;
     if (a) { // the caller's accelerations, [n][3] in the store's current order
         int rc;
-        if ((rc = ensure(c, c->sacc, sizeof(double) * 3 * (size_t)n))) return rc;
+        if ((rc = gg_ensure(c, c->sacc, sizeof(double) * 3 * (size_t)n))) return rc;
         CK(cudaMemcpyAsync(c->sacc.p, a, sizeof(double) * 3 * (size_t)n, cudaMemcpyDefault, c->st));
         da = (const double *)c->sacc.p;
     } else {
         if (c->stateDirty || !c->stateForces)
-            return fail(GG_ERR_ARG, "gg_state_kick: no accelerations for the current particle order "
+            return gg_fail(GG_ERR_ARG, "gg_state_kick: no accelerations for the current particle order "
                                     "(sequence: gg_state_build, gg_gravity, gg_state_kick)");
         da = (const double *)c->acc.p;
     }
@@ -950,12 +950,12 @@ int gg_state_kick(gg_context *c, double dvFacOne, double dvFacTwo, const double 
 }
 
 int gg_state_drift(gg_context *c, double dDelta, const double fCenter[3], int bPeriodic, const double fPeriod[3]) {
-    if (!c || c->stateN < 1) return fail(GG_ERR_ARG, "gg_state_drift: no resident particles (gg_state_load)");
-    if (bPeriodic && (!fCenter || !fPeriod)) return fail(GG_ERR_ARG, "gg_state_drift: periodic drift needs fCenter, fPeriod");
+    if (!c || c->stateN < 1) return gg_fail(GG_ERR_ARG, "gg_state_drift: no resident particles (gg_state_load)");
+    if (bPeriodic && (!fCenter || !fPeriod)) return gg_fail(GG_ERR_ARG, "gg_state_drift: periodic drift needs fCenter, fPeriod");
     CK(cudaSetDevice(c->device));
     int rc;
-    if ((rc = finish_mom(c))) return rc; // the moment kernels of the last build read the positions
-    if ((rc = ensure(c, c->misc, 16 * sizeof(int)))) return rc;
+    if ((rc = gg_finish_mom(c))) return rc; // the moment kernels of the last build read the positions
+    if ((rc = gg_ensure(c, c->misc, 16 * sizeof(int)))) return rc;
     int *dOut = (int *)c->misc.p + 12;
     const double zero[3] = {0, 0, 0}, one[3] = {1, 1, 1};
     CK(cudaMemsetAsync(dOut, 0, sizeof(int), c->st));
@@ -967,18 +967,18 @@ int gg_state_drift(gg_context *c, double dDelta, const double fCenter[3], int bP
         int nOut = 0;
         CK(cudaMemcpyAsync(&nOut, dOut, sizeof(int), cudaMemcpyDeviceToHost, c->st));
         CK(cudaStreamSynchronize(c->st));
-        if (nOut) return fail(GG_ERR_ARG, "gg_state_drift: %d particle(s) left the periodic box by more than one period", nOut);
+        if (nOut) return gg_fail(GG_ERR_ARG, "gg_state_drift: %d particle(s) left the periodic box by more than one period", nOut);
     }
     return GG_OK;
 }
 
 int gg_state_gravstep(gg_context *c, double dEta, double *pdtMin) {
-    if (!c || c->stateN < 1) return fail(GG_ERR_ARG, "gg_state_gravstep: no resident particles (gg_state_load)");
+    if (!c || c->stateN < 1) return gg_fail(GG_ERR_ARG, "gg_state_gravstep: no resident particles (gg_state_load)");
     if (c->stateDirty || !c->stateForces)
-        return fail(GG_ERR_ARG, "gg_state_gravstep: no dtGrav for the current particle order (gg_gravity first)");
+        return gg_fail(GG_ERR_ARG, "gg_state_gravstep: no dtGrav for the current particle order (gg_gravity first)");
     CK(cudaSetDevice(c->device));
     int rc;
-    if ((rc = ensure(c, c->misc, 16 * sizeof(int)))) return rc;
+    if ((rc = gg_ensure(c, c->misc, 16 * sizeof(int)))) return rc;
     unsigned long long *dMin = (unsigned long long *)((int *)c->misc.p + 14);
     int *dBad = (int *)c->misc.p + 13;
     CK(cudaMemsetAsync(dMin, 0xff, sizeof(unsigned long long), c->st));
@@ -993,12 +993,12 @@ int gg_state_gravstep(gg_context *c, double dEta, double *pdtMin) {
     CK(cudaStreamSynchronize(c->st));
     if (pdtMin) memcpy(pdtMin, &bits, sizeof(double));
     if (nBad) // the reference asserts (pkd.c:4616)
-        return fail(GG_ERR_ARG, "gg_state_gravstep: %d active particle(s) have dtGrav <= 0 (no interaction was evaluated for them)", nBad);
+        return gg_fail(GG_ERR_ARG, "gg_state_gravstep: %d active particle(s) have dtGrav <= 0 (no interaction was evaluated for them)", nBad);
     return GG_OK;
 }
 
 int gg_state_fetch(gg_context *c, double *x, double *y, double *z, double *vx, double *vy, double *vz, int *id, double *dt) {
-    if (!c || c->stateN < 1) return fail(GG_ERR_ARG, "gg_state_fetch: no resident particles (gg_state_load)");
+    if (!c || c->stateN < 1) return gg_fail(GG_ERR_ARG, "gg_state_fetch: no resident particles (gg_state_load)");
     CK(cudaSetDevice(c->device));
     const int n = c->stateN;
     const size_t nb = sizeof(double) * (size_t)n;
@@ -1014,7 +1014,7 @@ int gg_state_fetch(gg_context *c, double *x, double *y, double *z, double *vx, d
 }
 
 int gg_state_fetch_rungs(gg_context *c, int *rung, int *active) {
-    if (!c || c->stateN < 1) return fail(GG_ERR_ARG, "gg_state_fetch_rungs: no resident particles (gg_state_load)");
+    if (!c || c->stateN < 1) return gg_fail(GG_ERR_ARG, "gg_state_fetch_rungs: no resident particles (gg_state_load)");
     CK(cudaSetDevice(c->device));
     const int n = c->stateN;
     if (rung)
@@ -1029,7 +1029,7 @@ int gg_state_fetch_rungs(gg_context *c, int *rung, int *active) {
 }
 
 int gg_state_set_rungs(gg_context *c, const int *rung) {
-    if (!c || c->stateN < 1 || !rung) return fail(GG_ERR_ARG, "gg_state_set_rungs: bad argument");
+    if (!c || c->stateN < 1 || !rung) return gg_fail(GG_ERR_ARG, "gg_state_set_rungs: bad argument");
     CK(cudaSetDevice(c->device));
     CK(cudaMemcpy2DAsync((int *)c->sid.p + 1, 2 * sizeof(int), rung, sizeof(int), sizeof(int), (size_t)c->stateN,
                          cudaMemcpyDefault, c->st));
@@ -1038,7 +1038,7 @@ int gg_state_set_rungs(gg_context *c, const int *rung) {
 }
 
 int gg_state_init_dt(gg_context *c, double dDelta) {
-    if (!c || c->stateN < 1) return fail(GG_ERR_ARG, "gg_state_init_dt: no resident particles (gg_state_load)");
+    if (!c || c->stateN < 1) return gg_fail(GG_ERR_ARG, "gg_state_init_dt: no resident particles (gg_state_load)");
     CK(cudaSetDevice(c->device));
     CK(gg_launch_init_dt(c->stateN, (double *)c->sdt.p, c->stateHasActive ? (const int *)c->sact.p : nullptr, dDelta, c->st));
     ++c->nLaunches;
@@ -1047,9 +1047,9 @@ int gg_state_init_dt(gg_context *c, double dDelta) {
 
 int gg_state_accelstep(gg_context *c, double dEta, double dVelFac, double dAccFac, int bEpsAcc, int bSqrtPhi) {
     (void)dVelFac; // the velocity enters only an assertion in the gravity-only build (pkd.c:4643)
-    if (!c || c->stateN < 1) return fail(GG_ERR_ARG, "gg_state_accelstep: no resident particles (gg_state_load)");
+    if (!c || c->stateN < 1) return gg_fail(GG_ERR_ARG, "gg_state_accelstep: no resident particles (gg_state_load)");
     if (c->stateDirty || !c->stateForces)
-        return fail(GG_ERR_ARG, "gg_state_accelstep: no accelerations for the current particle order (gg_gravity first)");
+        return gg_fail(GG_ERR_ARG, "gg_state_accelstep: no accelerations for the current particle order (gg_gravity first)");
     CK(cudaSetDevice(c->device));
     CK(gg_launch_accelstep(c->stateN, (double *)c->sdt.p, (const double *)c->acc.p, (const double *)c->pot.p,
                            (const double *)c->sh.p, c->stateHasActive ? (const int *)c->sact.p : nullptr, dEta, dAccFac,
@@ -1060,12 +1060,12 @@ int gg_state_accelstep(gg_context *c, double dEta, double dVelFac, double dAccFa
 
 int gg_state_dt_to_rung(gg_context *c, int iRung, double dDelta, int iMaxRung, int bAll, int *pnMaxRung, int *piMaxRungIdeal,
                         int *piMaxRungOut) {
-    if (!c || c->stateN < 1) return fail(GG_ERR_ARG, "gg_state_dt_to_rung: no resident particles (gg_state_load)");
+    if (!c || c->stateN < 1) return gg_fail(GG_ERR_ARG, "gg_state_dt_to_rung: no resident particles (gg_state_load)");
     if (iRung < 0 || iMaxRung < 1 || iMaxRung > 127 || iRung + 1 > 127)
-        return fail(GG_ERR_UNSUPPORTED, "gg_state_dt_to_rung: iRung=%d iMaxRung=%d (supported < 128)", iRung, iMaxRung);
+        return gg_fail(GG_ERR_UNSUPPORTED, "gg_state_dt_to_rung: iRung=%d iMaxRung=%d (supported < 128)", iRung, iMaxRung);
     CK(cudaSetDevice(c->device));
     int rc;
-    if ((rc = ensure(c, c->srhist, 132 * sizeof(int)))) return rc;
+    if ((rc = gg_ensure(c, c->srhist, 132 * sizeof(int)))) return rc;
     int *dh = (int *)c->srhist.p;
     CK(cudaMemsetAsync(dh, 0, 132 * sizeof(int), c->st));
     CK(gg_launch_dt_to_rung(c->stateN, (int *)c->sid.p, (const double *)c->sdt.p, iRung, dDelta, iMaxRung, bAll, dh, dh + 128,
@@ -1075,7 +1075,7 @@ int gg_state_dt_to_rung(gg_context *c, int iRung, double dDelta, int iMaxRung, i
     CK(cudaMemcpyAsync(h, dh, sizeof(h), cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
     if (h[130]) // the reference asserts both (pkd.c:4694, 4749)
-        return fail(GG_ERR_ARG, "gg_state_dt_to_rung: %d particle(s) have dt <= 0 or dDelta/dt >= 2.1e9", h[130]);
+        return gg_fail(GG_ERR_ARG, "gg_state_dt_to_rung: %d particle(s) have dt <= 0 or dDelta/dt >= 2.1e9", h[130]);
     int top = 0;
     for (int r = 127; r > 0; --r)
         if (h[r] > 0) { top = r; break; }
@@ -1086,12 +1086,12 @@ int gg_state_dt_to_rung(gg_context *c, int iRung, double dDelta, int iMaxRung, i
 }
 
 int gg_state_active_rung(gg_context *c, int iRung, int bGreater, int *pnActive) {
-    if (!c || c->stateN < 1) return fail(GG_ERR_ARG, "gg_state_active_rung: no resident particles (gg_state_load)");
+    if (!c || c->stateN < 1) return gg_fail(GG_ERR_ARG, "gg_state_active_rung: no resident particles (gg_state_load)");
     CK(cudaSetDevice(c->device));
     int rc;
     const int n = c->stateN;
-    if ((rc = ensure(c, c->sact, sizeof(int) * (size_t)n))) return rc;
-    if ((rc = ensure(c, c->srhist, 132 * sizeof(int)))) return rc;
+    if ((rc = gg_ensure(c, c->sact, sizeof(int) * (size_t)n))) return rc;
+    if ((rc = gg_ensure(c, c->srhist, 132 * sizeof(int)))) return rc;
     int *dCount = (int *)c->srhist.p + 129;
     CK(cudaMemsetAsync(dCount, 0, sizeof(int), c->st));
     CK(gg_launch_active_rung(n, (const int *)c->sid.p, (int *)c->sact.p, iRung, bGreater, dCount, c->st));
@@ -1111,7 +1111,7 @@ int gg_state_active_rung(gg_context *c, int iRung, int bGreater, int *pnActive) 
 // New ACTIVE flags for the domain that is already loaded (same tree, same particles): what msrActiveRung changes between
 // two force evaluations on one tree (master.c:8403-8420).  Only the flags travel; the sink-bucket task list is rebuilt.
 int gg_set_active(gg_context *c, const int *active) {
-    if (!c || c->dom.empty()) return fail(GG_ERR_ARG, "gg_set_active: no local domain (gg_set_local / gg_build_local)");
+    if (!c || c->dom.empty()) return gg_fail(GG_ERR_ARG, "gg_set_active: no local domain (gg_set_local / gg_build_local)");
     CK(cudaSetDevice(c->device));
     const Domain &L = c->dom[0];
     const int np = L.nPart, nn = L.nNodes;
@@ -1119,7 +1119,7 @@ int gg_set_active(gg_context *c, const int *active) {
     const int *dActive = nullptr;
     c->stateForces = false; // a new sink set: the last evaluation's results do not cover the newly active particles
     if (active) {
-        if ((rc = ensure(c, c->active, (size_t)(np + 1) * sizeof(int)))) return rc;
+        if ((rc = gg_ensure(c, c->active, (size_t)(np + 1) * sizeof(int)))) return rc;
         CK(cudaMemcpyAsync(c->active.p, active, sizeof(int) * np, cudaMemcpyDefault, c->st));
         dActive = (const int *)c->active.p;
         c->hActive.resize((size_t)np);
@@ -1134,7 +1134,7 @@ int gg_set_active(gg_context *c, const int *active) {
     if (c->stateN > 0 && c->stateHasActive != (active != nullptr)) {
         // the resident store keeps its own copy of the flags (kick / grav-step read them)
         if (active) {
-            if ((rc = ensure(c, c->sact, sizeof(int) * (size_t)np))) return rc;
+            if ((rc = gg_ensure(c, c->sact, sizeof(int) * (size_t)np))) return rc;
         }
         c->stateHasActive = active != nullptr;
     }
@@ -1149,7 +1149,7 @@ int gg_set_active(gg_context *c, const int *active) {
 int gg_domain_summary(gg_context *c, double bnd[6], double r[3], double *fMass, double *fSoft, double *fOpen2,
                       double mom[GG_NMOM], double root[GG_NROOT]) {
     if (!c || !c->built.nNodes || c->dom.empty())
-        return fail(GG_ERR_ARG, "gg_domain_summary: no device-built local tree (gg_build_local)");
+        return gg_fail(GG_ERR_ARG, "gg_domain_summary: no device-built local tree (gg_build_local)");
     CK(cudaSetDevice(c->device));
     int rc;
     c->rootLazy = true; // (re)read from the device records: gg_set_root_moments may have replaced c->root meanwhile
@@ -1184,11 +1184,11 @@ int gg_domain_summary(gg_context *c, double bnd[6], double r[3], double *fMass, 
 // rcm (exact binomial shift) and reducing it, Bmax by one pass over the particles.
 int gg_domain_moments_about(gg_context *c, const double rcm[3], double mom[GG_NMOM], double *pBmax) {
     if (!c || !rcm || !mom || !pBmax || c->dom.empty() || !c->momraw.p)
-        return fail(GG_ERR_ARG, "gg_domain_moments_about: needs a local domain with device-formed moments");
+        return gg_fail(GG_ERR_ARG, "gg_domain_moments_about: needs a local domain with device-formed moments");
     CK(cudaSetDevice(c->device));
     int rc;
-    if ((rc = finish_mom(c))) return rc;
-    if ((rc = ensure(c, c->misc, 16 * sizeof(int)))) return rc;
+    if ((rc = gg_finish_mom(c))) return rc;
+    if ((rc = gg_ensure(c, c->misc, 16 * sizeof(int)))) return rc;
     unsigned long long *dMax = (unsigned long long *)((int *)c->misc.p + 14);
     const Domain &L = c->dom[0];
     CK(cudaMemsetAsync(dMax, 0, sizeof(unsigned long long), c->st));
@@ -1212,7 +1212,7 @@ int gg_domain_moments_about(gg_context *c, const double rcm[3], double mom[GG_NM
 }
 
 int gg_build_info(gg_context *c, int *pnNodes, int *pnLevels, double *pmsBuild) {
-    if (!c || !c->built.nNodes) return fail(GG_ERR_ARG, "gg_build_info: no device-built tree");
+    if (!c || !c->built.nNodes) return gg_fail(GG_ERR_ARG, "gg_build_info: no device-built tree");
     if (pnNodes) *pnNodes = c->built.nNodes;
     if (pnLevels) *pnLevels = c->built.nLevels;
     if (pmsBuild) *pmsBuild = c->msBuild;
@@ -1222,10 +1222,10 @@ int gg_build_info(gg_context *c, int *pnNodes, int *pnLevels, double *pmsBuild) 
 int gg_tree_fetch(gg_context *c, double *bnd, double *r, double *fMass, double *fSoft, double *fOpen2, double *mom,
                   int *pLower, int *pUpper, int *iLower, int *iUpper, double *x, double *y, double *z, double *m,
                   double *h, int *active) {
-    if (!c || !c->built.nNodes) return fail(GG_ERR_ARG, "gg_tree_fetch: no device-built tree (gg_build_local)");
+    if (!c || !c->built.nNodes) return gg_fail(GG_ERR_ARG, "gg_tree_fetch: no device-built tree (gg_build_local)");
     CK(cudaSetDevice(c->device));
     int rc;
-    if ((rc = finish_mom(c))) return rc;
+    if ((rc = gg_finish_mom(c))) return rc;
     const GGBuiltDev &b = c->built;
     const size_t nn = (size_t)b.nNodes, np = (size_t)b.nPart;
     struct { void *dst; const void *src; size_t bytes; } cp[] = {
@@ -1238,7 +1238,7 @@ int gg_tree_fetch(gg_context *c, double *bnd, double *r, double *fMass, double *
     CK(cudaStreamSynchronize(c->st));
     if (mom) { // the reduced multipoles the device formed: raw records reduced by a kernel, then one copy
         int rc2;
-        if ((rc2 = ensure(c, c->momout, sizeof(double) * GG_NMOM * nn))) return rc2;
+        if ((rc2 = gg_ensure(c, c->momout, sizeof(double) * GG_NMOM * nn))) return rc2;
         CK(gg_launch_mom_reduce((int)nn, (const double *)c->momraw.p, (double *)c->momout.p, c->st));
         ++c->nLaunches;
         CK(cudaMemcpyAsync(mom, c->momout.p, sizeof(double) * GG_NMOM * nn, cudaMemcpyDeviceToHost, c->st));
@@ -1248,7 +1248,7 @@ int gg_tree_fetch(gg_context *c, double *bnd, double *r, double *fMass, double *
 }
 
 int gg_tree_fetch_build(gg_context *c, int *iDim, double *fSplit, double *fBmax) {
-    if (!c || !c->built.nNodes) return fail(GG_ERR_ARG, "gg_tree_fetch_build: no device-built tree (gg_build_local)");
+    if (!c || !c->built.nNodes) return gg_fail(GG_ERR_ARG, "gg_tree_fetch_build: no device-built tree (gg_build_local)");
     CK(cudaSetDevice(c->device));
     const GGBuiltDev &b = c->built;
     const size_t nn = (size_t)b.nNodes;
@@ -1260,9 +1260,9 @@ int gg_tree_fetch_build(gg_context *c, int *iDim, double *fSplit, double *fBmax)
 }
 
 int gg_set_remote(gg_context *c, int id, const gg_tree *t, const gg_particles *pp, int bDevice) {
-    if (!c || !t || !pp) return fail(GG_ERR_ARG, "gg_set_remote: null argument");
-    if (c->dom.empty()) return fail(GG_ERR_ARG, "gg_set_remote: call gg_set_local first");
-    if (id == c->idSelf) return fail(GG_ERR_ARG, "gg_set_remote: id %d is the local domain", id);
+    if (!c || !t || !pp) return gg_fail(GG_ERR_ARG, "gg_set_remote: null argument");
+    if (c->dom.empty()) return gg_fail(GG_ERR_ARG, "gg_set_remote: call gg_set_local first");
+    if (id == c->idSelf) return gg_fail(GG_ERR_ARG, "gg_set_remote: id %d is the local domain", id);
     CK(cudaSetDevice(c->device));
     // (bucket sizes and particle ranges are validated on the device while the records are packed)
     int rc = upload_domain(c, t, pp, c->nNodesAll, c->nPartAll, false, bDevice != 0);
@@ -1276,24 +1276,37 @@ int gg_set_remote(gg_context *c, int id, const gg_tree *t, const gg_particles *p
 int gg_let_export(gg_context *c, int nRemote, const double *bnd, const gg_params *prm, void **pDev, size_t *offsets,
                   int *hdr) {
     if (!c || !bnd || !prm || !pDev || !offsets || !hdr || c->dom.empty())
-        return fail(GG_ERR_ARG, "gg_let_export: bad argument / no local domain");
-    if (nRemote < 1 || nRemote > 15) return fail(GG_ERR_UNSUPPORTED, "gg_let_export: nRemote=%d (1..15)", nRemote);
+        return gg_fail(GG_ERR_ARG, "gg_let_export: bad argument / no local domain");
+    int rc = gg_let_export_impl(c, nRemote, bnd, prm, offsets, hdr);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(c->st));
+    *pDev = c->letout.p;
+    return GG_OK;
+}
+
+} // extern "C"
+
+// The export proper; the packing kernel is left in flight on c->st (the sizes are already known to the host).
+int gg_let_export_impl(gg_context *c, int nRemote, const double *bnd, const gg_params *prm, size_t *offsets, int *hdr) {
+    if (nRemote < 1 || nRemote > 15) return gg_fail(GG_ERR_UNSUPPORTED, "gg_let_export: nRemote=%d (1..15)", nRemote);
     CK(cudaSetDevice(c->device));
     int rc;
-    if ((rc = finish_mom(c))) return rc;
+    if ((rc = gg_finish_mom(c))) return rc;
     const Domain &L = c->dom[0];
     const int nn = L.nNodes;
-    if (nn >= (1 << 28)) return fail(GG_ERR_UNSUPPORTED, "gg_let_export: %d nodes", nn);
-    Trace tr;
+    if (nn >= (1 << 28)) return gg_fail(GG_ERR_UNSUPPORTED, "gg_let_export: %d nodes", nn);
     Images im = make_images(prm);
-    if (im.n > GG_MAX_IMAGES) return fail(GG_ERR_UNSUPPORTED, "gg_let_export: %d images", im.n);
-    if ((rc = ensure(c, c->imgoff, im.off.size() * sizeof(double)))) return rc;
-    if ((rc = ensure(c, c->letflag, (size_t)nRemote * nn))) return rc;
-    if ((rc = ensure(c, c->letfront, (size_t)2 * nRemote * nn * sizeof(unsigned)))) return rc;
-    if ((rc = ensure(c, c->letidx, (size_t)4 * (nn + 1) * sizeof(int)))) return rc;
-    if ((rc = ensure(c, c->letmisc, 64 * sizeof(double) * 2 + 64))) return rc;
+    if (im.n > GG_MAX_IMAGES) return gg_fail(GG_ERR_UNSUPPORTED, "gg_let_export: %d images", im.n);
+    const size_t seg = (size_t)nn + 1, nAll = seg * nRemote + 1;
+    if (nAll >= 0x7fffffffull) return gg_fail(GG_ERR_UNSUPPORTED, "gg_let_export: %d nodes x %d remotes", nn, nRemote);
+    if ((rc = gg_ensure(c, c->imgoff, im.off.size() * sizeof(double)))) return rc;
+    if ((rc = gg_ensure(c, c->letflag, (size_t)nRemote * nn))) return rc;
+    if ((rc = gg_ensure(c, c->letfront, (size_t)2 * nRemote * nn * sizeof(unsigned)))) return rc;
+    if ((rc = gg_ensure(c, c->letidx, 4 * nAll * sizeof(int)))) return rc;
+    if ((rc = gg_ensure(c, c->letmisc, 64 * sizeof(double) * 2 + 64 + 40 * sizeof(int)))) return rc;
     double *dBnd = (double *)c->letmisc.p;
     int *dCount = (int *)(dBnd + 6 * 16);
+    int *dBounds = dCount + 4;
     CK(cudaMemcpyAsync(c->imgoff.p, im.off.data(), im.off.size() * sizeof(double), cudaMemcpyHostToDevice, c->st));
     CK(cudaMemcpyAsync(dBnd, bnd, sizeof(double) * 6 * nRemote, cudaMemcpyHostToDevice, c->st));
     CK(cudaMemsetAsync(c->letflag.p, 0, (size_t)nRemote * nn, c->st));
@@ -1310,65 +1323,67 @@ int gg_let_export(gg_context *c, int nRemote, const double *bnd, const gg_params
         k_let_level<<<grid, 256, 0, c->st>>>(la, level);
         CK(cudaGetLastError());
         k_let_reset<<<1, 1, 0, c->st>>>(dCount, level + 1);
+        c->nLaunches += 2;
         if ((level & 7) == 7) {
             int cnt[2];
             CK(cudaMemcpyAsync(cnt, dCount, sizeof(cnt), cudaMemcpyDeviceToHost, c->st));
             CK(cudaStreamSynchronize(c->st));
             if (cnt[(level + 1) & 1] == 0) break;
         }
-        if (level > 4096) return fail(GG_ERR_UNSUPPORTED, "gg_let_export: tree deeper than 4096 levels");
+        if (level > 4096) return gg_fail(GG_ERR_UNSUPPORTED, "gg_let_export: tree deeper than 4096 levels");
     }
-    // ---- compaction per remote: new node numbers, new particle offsets, sizes
-    int *keep = (int *)c->letidx.p, *npart = keep + (nn + 1), *newIdx = npart + (nn + 1), *newPart = newIdx + (nn + 1);
+    // ---- compaction of all remotes at once: new node numbers, new particle offsets, sizes
+    int *keep = (int *)c->letidx.p, *npart = keep + nAll, *newIdx = npart + nAll, *newPart = newIdx + nAll;
     size_t tmpBytes = 0;
-    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, keep, newIdx, nn + 1, c->st));
-    if ((rc = ensure(c, c->cubtmp, tmpBytes))) return rc;
-    std::vector<int> nOut(nRemote), nOutP(nRemote);
-    // sizes first (one pass per remote), then one output buffer, then the packing pass
-    for (int pass = 0; pass < 2; ++pass) {
-        if (pass == 1) {
-            size_t off = 0;
-            for (int r = 0; r < nRemote; ++r) {
-                offsets[r] = off;
-                off += (size_t)nOut[r] * (sizeof(NodeW) + 128 + 48) + (size_t)nOutP[r] * sizeof(PartS);
-                off = (off + 255) & ~(size_t)255;
-            }
-            offsets[nRemote] = off;
-            if ((rc = ensure(c, c->letout, off + 256))) return rc;
-        }
-        for (int r = 0; r < nRemote; ++r) {
-            const unsigned char *fl = (const unsigned char *)c->letflag.p + (size_t)r * nn;
-            k_let_counts<<<(nn + 255) / 256, 256, 0, c->st>>>(nn, (const NodeW *)c->nodes.p, fl, keep, npart);
-            CK(cudaGetLastError());
-            CK(cudaMemsetAsync(keep + nn, 0, sizeof(int), c->st));
-            CK(cudaMemsetAsync(npart + nn, 0, sizeof(int), c->st));
-            CK(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmpBytes, keep, newIdx, nn + 1, c->st));
-            CK(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmpBytes, npart, newPart, nn + 1, c->st));
-            if (pass == 0) {
-                CK(cudaMemcpyAsync(&nOut[r], newIdx + nn, sizeof(int), cudaMemcpyDeviceToHost, c->st));
-                CK(cudaMemcpyAsync(&nOutP[r], newPart + nn, sizeof(int), cudaMemcpyDeviceToHost, c->st));
-                CK(cudaStreamSynchronize(c->st));
-            } else {
-                char *o = (char *)c->letout.p + offsets[r];
-                NodeW *oN = (NodeW *)o;
-                float4 *oF = (float4 *)(o + (size_t)nOut[r] * sizeof(NodeW));
-                double *oQ = (double *)((char *)oF + (size_t)nOut[r] * 128);
-                PartS *oP = (PartS *)((char *)oQ + (size_t)nOut[r] * 48);
-                k_let_pack<<<(nn + 127) / 128, 128, 0, c->st>>>(nn, (const NodeW *)c->nodes.p, (const float4 *)c->momf.p,
-                                                                (const double *)c->momq.p, (const PartS *)c->parts.p, fl,
-                                                                newIdx, newPart, oN, oF, oQ, oP);
-                CK(cudaGetLastError());
-                hdr[3 * r] = nOut[r]; hdr[3 * r + 1] = nOutP[r]; hdr[3 * r + 2] = 0; // pre-order: the root stays first
-            }
-        }
-    }
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, keep, newIdx, (int)nAll, c->st));
+    if ((rc = gg_ensure(c, c->cubtmp, tmpBytes))) return rc;
+    k_let_counts<<<(unsigned)((nAll + 255) / 256), 256, 0, c->st>>>(nn, nRemote, (const NodeW *)c->nodes.p,
+                                                                  (const unsigned char *)c->letflag.p, keep, npart);
+    CK(cudaGetLastError());
+    CK(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmpBytes, keep, newIdx, (int)nAll, c->st));
+    CK(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmpBytes, npart, newPart, (int)nAll, c->st));
+    k_let_bounds<<<1, 32, 0, c->st>>>(nn, nRemote, newIdx, newPart, dBounds);
+    CK(cudaGetLastError());
+    int hb[34];
+    CK(cudaMemcpyAsync(hb, dBounds, sizeof(int) * 2 * (nRemote + 1), cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
-    *pDev = c->letout.p;
+    c->nLaunches += 4;
+    LetPackArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    size_t off = 0;
+    for (int r = 0; r < nRemote; ++r) {
+        const int nOut = hb[2 * (r + 1)] - hb[2 * r], nOutP = hb[2 * (r + 1) + 1] - hb[2 * r + 1];
+        offsets[r] = off;
+        off += (size_t)nOut * (sizeof(NodeW) + 128 + 48) + (size_t)nOutP * sizeof(PartS);
+        off = (off + 255) & ~(size_t)255;
+        hdr[3 * r] = nOut; hdr[3 * r + 1] = nOutP; hdr[3 * r + 2] = 0; // pre-order: the root stays first
+        pa.baseIdx[r] = hb[2 * r]; pa.basePart[r] = hb[2 * r + 1];
+    }
+    offsets[nRemote] = off;
+    if ((rc = gg_ensure(c, c->letout, off + 256))) return rc;
+    for (int r = 0; r < nRemote; ++r) {
+        char *o = (char *)c->letout.p + offsets[r];
+        const size_t nOut = (size_t)hdr[3 * r];
+        pa.oNodes[r] = (NodeW *)o;
+        pa.oMomf[r] = (float4 *)(o + nOut * sizeof(NodeW));
+        pa.oMomq[r] = (double *)((char *)pa.oMomf[r] + nOut * 128);
+        pa.oParts[r] = (PartS *)((char *)pa.oMomq[r] + nOut * 48);
+    }
+    pa.nn = nn; pa.nRemote = nRemote;
+    pa.nodes = (const NodeW *)c->nodes.p; pa.momf = (const float4 *)c->momf.p; pa.momq = (const double *)c->momq.p;
+    pa.parts = (const PartS *)c->parts.p; pa.flag = (const unsigned char *)c->letflag.p;
+    pa.newIdx = newIdx; pa.newPart = newPart;
+    const size_t nThreads = (size_t)nn * nRemote * 8;
+    k_let_pack<<<(unsigned)((nThreads + 255) / 256), 256, 0, c->st>>>(pa);
+    CK(cudaGetLastError());
+    ++c->nLaunches;
     return GG_OK;
 }
 
+extern "C" {
+
 int gg_export_size(gg_context *c, size_t *bytes, int hdr[3]) {
-    if (!c || !bytes || !hdr || c->dom.empty()) return fail(GG_ERR_ARG, "gg_export_size: no local domain");
+    if (!c || !bytes || !hdr || c->dom.empty()) return gg_fail(GG_ERR_ARG, "gg_export_size: no local domain");
     const Domain &L = c->dom[0];
     hdr[0] = L.nNodes; hdr[1] = L.nPart; hdr[2] = L.iRoot;
     *bytes = (size_t)L.nNodes * (sizeof(NodeW) + 128 + 48) + (size_t)L.nPart * sizeof(PartS);
@@ -1376,9 +1391,9 @@ int gg_export_size(gg_context *c, size_t *bytes, int hdr[3]) {
 }
 
 int gg_export_local(gg_context *c, void *dst) {
-    if (!c || !dst || c->dom.empty()) return fail(GG_ERR_ARG, "gg_export_local: no local domain");
+    if (!c || !dst || c->dom.empty()) return gg_fail(GG_ERR_ARG, "gg_export_local: no local domain");
     CK(cudaSetDevice(c->device));
-    { int rc0 = finish_mom(c); if (rc0) return rc0; }
+    { int rc0 = gg_finish_mom(c); if (rc0) return rc0; }
     const Domain &L = c->dom[0];
     char *o = (char *)dst;
     const size_t nn = (size_t)L.nNodes, np = (size_t)L.nPart;
@@ -1391,27 +1406,35 @@ int gg_export_local(gg_context *c, void *dst) {
 }
 
 int gg_set_remote_packed(gg_context *c, int id, const int hdr[3], const void *src) {
-    if (!c || !hdr || !src) return fail(GG_ERR_ARG, "gg_set_remote_packed: null argument");
-    if (c->dom.empty()) return fail(GG_ERR_ARG, "gg_set_remote_packed: call gg_set_local first");
-    if (id == c->idSelf) return fail(GG_ERR_ARG, "gg_set_remote_packed: id %d is the local domain", id);
+    if (!c || !hdr || !src) return gg_fail(GG_ERR_ARG, "gg_set_remote_packed: null argument");
+    int rc = gg_ingest_packed(c, id, hdr, src);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(c->st)); // the source buffer belongs to the caller (next all-gather may overwrite it)
+    return GG_OK;
+}
+
+} // extern "C"
+
+int gg_ingest_packed(gg_context *c, int id, const int hdr[3], const void *src) {
+    if (c->dom.empty()) return gg_fail(GG_ERR_ARG, "gg_set_remote_packed: call gg_set_local first");
+    if (id == c->idSelf) return gg_fail(GG_ERR_ARG, "gg_set_remote_packed: id %d is the local domain", id);
     const int nn = hdr[0], np = hdr[1], iRoot = hdr[2];
-    if (nn < 1 || np < 0 || iRoot < 0 || iRoot >= nn) return fail(GG_ERR_ARG, "gg_set_remote_packed: nNodes=%d n=%d iRoot=%d", nn, np, iRoot);
+    if (nn < 1 || np < 0 || iRoot < 0 || iRoot >= nn) return gg_fail(GG_ERR_ARG, "gg_set_remote_packed: nNodes=%d n=%d iRoot=%d", nn, np, iRoot);
     CK(cudaSetDevice(c->device));
     const size_t keepN = (size_t)c->nNodesAll, keepP = (size_t)c->nPartAll;
     int rc;
-    if ((rc = finish_mom(c))) return rc;
-    if ((rc = ensure(c, c->nodes, (keepN + nn + GG_MAX_TOP) * sizeof(NodeW), keepN * sizeof(NodeW)))) return rc;
-    if ((rc = ensure(c, c->momf, (keepN + nn + GG_MAX_TOP) * 128, keepN * 128))) return rc;
-    if ((rc = ensure(c, c->momq, (keepN + nn + GG_MAX_TOP) * 48, keepN * 48))) return rc;
-    if ((rc = ensure(c, c->parts, (keepP + np + 1) * sizeof(PartS), keepP * sizeof(PartS)))) return rc;
+    if ((rc = gg_finish_mom(c))) return rc;
+    if ((rc = gg_ensure(c, c->nodes, (keepN + nn + GG_MAX_TOP) * sizeof(NodeW), keepN * sizeof(NodeW)))) return rc;
+    if ((rc = gg_ensure(c, c->momf, (keepN + nn + GG_MAX_TOP) * 128, keepN * 128))) return rc;
+    if ((rc = gg_ensure(c, c->momq, (keepN + nn + GG_MAX_TOP) * 48, keepN * 48))) return rc;
+    if ((rc = gg_ensure(c, c->parts, (keepP + np + 1) * sizeof(PartS), keepP * sizeof(PartS)))) return rc;
     const char *i0 = (const char *)src;
     const char *i1 = i0 + (size_t)nn * sizeof(NodeW), *i2 = i1 + (size_t)nn * 128, *i3 = i2 + (size_t)nn * 48;
     k_rebase_nodes<<<(nn + 255) / 256, 256, 0, c->st>>>(nn, (const NodeW *)i0, (int)keepN, (int)keepP, (NodeW *)c->nodes.p);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync((char *)c->momf.p + keepN * 128, i1, (size_t)nn * 128, cudaMemcpyDeviceToDevice, c->st));
     CK(cudaMemcpyAsync((char *)c->momq.p + keepN * 48, i2, (size_t)nn * 48, cudaMemcpyDeviceToDevice, c->st));
-    CK(cudaMemcpyAsync((PartS *)c->parts.p + keepP, i3, (size_t)np * sizeof(PartS), cudaMemcpyDeviceToDevice, c->st));
-    CK(cudaStreamSynchronize(c->st)); // the source buffer belongs to the caller (next all-gather may overwrite it)
+    if (np > 0) CK(cudaMemcpyAsync((PartS *)c->parts.p + keepP, i3, (size_t)np * sizeof(PartS), cudaMemcpyDeviceToDevice, c->st));
     c->dom.push_back(Domain{id, nn, np, iRoot, (int)keepN, (int)keepP});
     c->nNodesAll += nn;
     c->nPartAll += np;
@@ -1419,8 +1442,10 @@ int gg_set_remote_packed(gg_context *c, int id, const int hdr[3], const void *sr
     return GG_OK;
 }
 
+extern "C" {
+
 int gg_clear_remote(gg_context *c) {
-    if (!c || c->dom.empty()) return fail(GG_ERR_ARG, "gg_clear_remote: no local domain");
+    if (!c || c->dom.empty()) return gg_fail(GG_ERR_ARG, "gg_clear_remote: no local domain");
     c->dom.resize(1);
     c->nNodesAll = c->dom[0].nNodes;
     c->nPartAll = c->dom[0].nPart;
@@ -1431,8 +1456,8 @@ int gg_clear_remote(gg_context *c) {
 int gg_set_top(gg_context *c, int nCell, const int *pLower, const int *bUsed, const double *r, const double *fMass,
                const double *fSoft, const double *fOpen2, const double *mom) {
     if (!c || nCell < 2 || !pLower || !bUsed || !r || !fMass || !fSoft || !fOpen2 || !mom)
-        return fail(GG_ERR_ARG, "gg_set_top: bad argument");
-    if (nCell > GG_MAX_TOP) return fail(GG_ERR_UNSUPPORTED, "gg_set_top: nCell=%d > %d", nCell, GG_MAX_TOP);
+        return gg_fail(GG_ERR_ARG, "gg_set_top: bad argument");
+    if (nCell > GG_MAX_TOP) return gg_fail(GG_ERR_UNSUPPORTED, "gg_set_top: nCell=%d > %d", nCell, GG_MAX_TOP);
     c->nTop = nCell;
     c->topLower.assign(pLower, pLower + nCell);
     c->topUsed.assign(bUsed, bUsed + nCell);
@@ -1445,7 +1470,7 @@ int gg_set_top(gg_context *c, int nCell, const int *pLower, const int *bUsed, co
 }
 
 int gg_set_root_moments(gg_context *c, const double root[GG_NROOT]) {
-    if (!c || !root) return fail(GG_ERR_ARG, "gg_set_root_moments: null");
+    if (!c || !root) return gg_fail(GG_ERR_ARG, "gg_set_root_moments: null");
     memcpy(c->root, root, sizeof(c->root));
     c->haveRoot = true;
     c->rootLazy = false;
@@ -1477,11 +1502,11 @@ int pack_top(gg_context *c, int *pRoot) {
         NodeW &o = w[i];
         o.rx = c->topR[3 * i]; o.ry = c->topR[3 * i + 1]; o.rz = c->topR[3 * i + 2];
         o.fOpen2 = c->topOpen2[i]; o.fSoft = c->topSoft[i]; o.fMass = c->topMass[i];
-        if (2 * i + 1 >= n) return fail(GG_ERR_ARG, "gg_set_top: interior cell %d has no children in the heap", i);
+        if (2 * i + 1 >= n) return gg_fail(GG_ERR_ARG, "gg_set_top: interior cell %d has no children in the heap", i);
         o.c0 = map_top(c, 2 * i, topBase);
         o.c1 = map_top(c, 2 * i + 1, topBase);
         if (o.c0 < -1 || o.c1 < -1)
-            return fail(GG_ERR_ARG, "gg_set_top: a top leaf names a rank whose domain was not loaded");
+            return gg_fail(GG_ERR_ARG, "gg_set_top: a top leaf names a rank whose domain was not loaded");
         o.pLower = 0;
         o.nP = 1 << 30; // exempt from the "< 4 particles" rule: the top walk has no such test (walk.c:363-371)
         const double *q = &c->topMom[(size_t)GG_NMOM * i];
@@ -1490,23 +1515,23 @@ int pack_top(gg_context *c, int *pRoot) {
     }
     int rc;
     const size_t keep = (size_t)topBase;
-    if ((rc = ensure(c, c->nodes, (keep + n) * sizeof(NodeW), keep * sizeof(NodeW)))) return rc;
-    if ((rc = ensure(c, c->momf, (keep + n) * 128, keep * 128))) return rc;
-    if ((rc = ensure(c, c->momq, (keep + n) * 48, keep * 48))) return rc;
+    if ((rc = gg_ensure(c, c->nodes, (keep + n) * sizeof(NodeW), keep * sizeof(NodeW)))) return rc;
+    if ((rc = gg_ensure(c, c->momf, (keep + n) * 128, keep * 128))) return rc;
+    if ((rc = gg_ensure(c, c->momq, (keep + n) * 48, keep * 48))) return rc;
     CK(cudaMemcpyAsync((NodeW *)c->nodes.p + topBase, w.data(), sizeof(NodeW) * n, cudaMemcpyHostToDevice, c->st));
     CK(cudaMemcpyAsync((char *)c->momf.p + keep * 128, mf.data(), 128 * (size_t)n, cudaMemcpyHostToDevice, c->st));
     CK(cudaMemcpyAsync((char *)c->momq.p + keep * 48, mq.data(), 48 * (size_t)n, cudaMemcpyHostToDevice, c->st));
     CK(cudaStreamSynchronize(c->st));
     *pRoot = map_top(c, 1, topBase);
-    if (*pRoot < 0) return fail(GG_ERR_ARG, "gg_set_top: root of the top tree cannot be resolved");
+    if (*pRoot < 0) return gg_fail(GG_ERR_ARG, "gg_set_top: root of the top tree cannot be resolved");
     return GG_OK;
 }
 
 int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_stats *stats, int depth = 0) {
-    if (c->dom.empty()) return fail(GG_ERR_ARG, "gg_gravity: gg_set_local has not been called");
+    if (c->dom.empty()) return gg_fail(GG_ERR_ARG, "gg_gravity: gg_set_local has not been called");
     if (prm->iOrder < 1 || prm->iOrder > 4 || prm->iEwOrder < 0 || prm->iEwOrder > 4)
-        return fail(GG_ERR_UNSUPPORTED, "gg_gravity: iOrder=%d iEwOrder=%d (supported 1..4)", prm->iOrder, prm->iEwOrder);
-    if (prm->nReps < 0 || prm->nReps > 3) return fail(GG_ERR_UNSUPPORTED, "gg_gravity: nReps=%d (supported 0..3)", prm->nReps);
+        return gg_fail(GG_ERR_UNSUPPORTED, "gg_gravity: iOrder=%d iEwOrder=%d (supported 1..4)", prm->iOrder, prm->iEwOrder);
+    if (prm->nReps < 0 || prm->nReps > 3) return gg_fail(GG_ERR_UNSUPPORTED, "gg_gravity: nReps=%d (supported 0..3)", prm->nReps);
     CK(cudaSetDevice(c->device));
     if (depth > 0) CK(cudaStreamSynchronize(c->st3)); // a re-run: the previous attempt's k_stats may still be in flight
     const Domain &L = c->dom[0];
@@ -1516,43 +1541,43 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
         int rcr = fetch_root_lazy(c);
         if (rcr) return rcr;
     }
-    if (doEwald && !c->haveRoot) return fail(GG_ERR_ARG, "gg_gravity: Ewald needs gg_set_root_moments");
+    if (doEwald && !c->haveRoot) return gg_fail(GG_ERR_ARG, "gg_gravity: Ewald needs gg_set_root_moments");
     Trace tr;
     Images im = make_images(prm);
-    if (im.n > GG_MAX_IMAGES) return fail(GG_ERR_UNSUPPORTED, "gg_gravity: %d images", im.n);
+    if (im.n > GG_MAX_IMAGES) return gg_fail(GG_ERR_UNSUPPORTED, "gg_gravity: %d images", im.n);
     int rootNode = L.iRoot;
     int nNodesAll = c->nNodesAll;
     int rc;
     if (c->nTop > 0 || c->dom.size() > 1) { // several domains: buffers may be re-allocated below -- no overlap
-        if ((rc = finish_mom(c))) return rc;
+        if ((rc = gg_finish_mom(c))) return rc;
     }
     if (c->nTop > 0) {
         if ((rc = pack_top(c, &rootNode))) return rc;
         nNodesAll += c->nTop;
     } else if (c->dom.size() > 1)
-        return fail(GG_ERR_ARG, "gg_gravity: remote domains are loaded but gg_set_top was not called");
+        return gg_fail(GG_ERR_ARG, "gg_gravity: remote domains are loaded but gg_set_top was not called");
     const unsigned cap = (1u << (32 - im.bits)) - 2u;
     if ((unsigned)nNodesAll > cap || (unsigned)c->nPartAll > cap)
-        return fail(GG_ERR_UNSUPPORTED, "gg_gravity: %d nodes / %d particles exceed the %u addressable with %d images",
+        return gg_fail(GG_ERR_UNSUPPORTED, "gg_gravity: %d nodes / %d particles exceed the %u addressable with %d images",
                     nNodesAll, c->nPartAll, cap, im.n);
     c->nLaunches = 0;
     const int *dActive = c->hActive.empty() ? nullptr : (const int *)c->active.p;
 
-    if ((rc = ensure(c, c->imgoff, im.off.size() * sizeof(double)))) return rc;
+    if ((rc = gg_ensure(c, c->imgoff, im.off.size() * sizeof(double)))) return rc;
     CK(cudaMemcpyAsync(c->imgoff.p, im.off.data(), im.off.size() * sizeof(double), cudaMemcpyHostToDevice, c->st));
-    if ((rc = ensure(c, c->counts, (size_t)(nn + 1) * 3 * sizeof(int), c->sunMode ? (size_t)nn * 3 * sizeof(int) : 0))) return rc;
-    if ((rc = ensure(c, c->acc, (size_t)(n + 1) * 3 * sizeof(double)))) return rc;
-    if ((rc = ensure(c, c->pot, (size_t)(n + 1) * sizeof(double)))) return rc;
-    if ((rc = ensure(c, c->dtg, (size_t)(n + 1) * sizeof(double)))) return rc;
-    if ((rc = ensure(c, c->fweight, (size_t)(n + 1) * sizeof(double)))) return rc;
-    if ((rc = ensure(c, c->nloop, (size_t)(n + 1) * sizeof(int)))) return rc;
-    if ((rc = ensure(c, c->sums, 16 * sizeof(unsigned long long)))) return rc;
-    if ((rc = ensure(c, c->misc, 16 * sizeof(int)))) return rc;
-    if ((rc = ensure(c, c->ngroups, (size_t)(nn + 1) * sizeof(int)))) return rc;
-    if ((rc = ensure(c, c->goffs, (size_t)(nn + 1) * sizeof(int)))) return rc;
-    if ((rc = ensure(c, c->isb, (size_t)(nn + 1) * sizeof(int)))) return rc;
-    if ((rc = ensure(c, c->boffs, (size_t)(nn + 1) * sizeof(int)))) return rc;
-    if ((rc = ensure(c, c->bnode, (size_t)(nn + 1) * sizeof(int)))) return rc;
+    if ((rc = gg_ensure(c, c->counts, (size_t)(nn + 1) * 3 * sizeof(int), c->sunMode ? (size_t)nn * 3 * sizeof(int) : 0))) return rc;
+    if ((rc = gg_ensure(c, c->acc, (size_t)(n + 1) * 3 * sizeof(double)))) return rc;
+    if ((rc = gg_ensure(c, c->pot, (size_t)(n + 1) * sizeof(double)))) return rc;
+    if ((rc = gg_ensure(c, c->dtg, (size_t)(n + 1) * sizeof(double)))) return rc;
+    if ((rc = gg_ensure(c, c->fweight, (size_t)(n + 1) * sizeof(double)))) return rc;
+    if ((rc = gg_ensure(c, c->nloop, (size_t)(n + 1) * sizeof(int)))) return rc;
+    if ((rc = gg_ensure(c, c->sums, 16 * sizeof(unsigned long long)))) return rc;
+    if ((rc = gg_ensure(c, c->misc, 16 * sizeof(int)))) return rc;
+    if ((rc = gg_ensure(c, c->ngroups, (size_t)(nn + 1) * sizeof(int)))) return rc;
+    if ((rc = gg_ensure(c, c->goffs, (size_t)(nn + 1) * sizeof(int)))) return rc;
+    if ((rc = gg_ensure(c, c->isb, (size_t)(nn + 1) * sizeof(int)))) return rc;
+    if ((rc = gg_ensure(c, c->boffs, (size_t)(nn + 1) * sizeof(int)))) return rc;
+    if ((rc = gg_ensure(c, c->bnode, (size_t)(nn + 1) * sizeof(int)))) return rc;
 
     CK(cudaEventRecord(c->ev[0], c->st));
     if (c->sunMode) { // only the dummy sink's slot (index n) and its bucket's counters: everything else holds results
@@ -1580,7 +1605,7 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
         const double Lbox = prm->fPeriod[0];
         gg_ewald_table_host(c->root, Lbox, prm->fEwhCut, prm->iEwOrder, ewt);
         nEwh = (int)(ewt.size() / 5);
-        if ((rc = ensure(c, c->ewt, (ewt.size() + 8) * sizeof(double)))) return rc;
+        if ((rc = gg_ensure(c, c->ewt, (ewt.size() + 8) * sizeof(double)))) return rc;
         CK(cudaMemcpyAsync(c->ewt.p, ewt.data(), ewt.size() * sizeof(double), cudaMemcpyHostToDevice, c->st));
         EwaldKernelArgs ea;
         memset(&ea, 0, sizeof(ea));
@@ -1631,7 +1656,7 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
     int nTasks = 0, nBuckets = 0;
     if (singleTask) {
         // (its own small buffer: the task list of gg_set_local stays intact for the next gg_gravity)
-        if ((rc = ensure(c, c->dbgtask, sizeof(Task) + sizeof(int)))) return rc;
+        if ((rc = gg_ensure(c, c->dbgtask, sizeof(Task) + sizeof(int)))) return rc;
         CK(cudaMemcpyAsync(c->dbgtask.p, singleTask, sizeof(Task), cudaMemcpyHostToDevice, c->st));
         CK(cudaMemcpyAsync((char *)c->dbgtask.p + sizeof(Task), &singleTask->node, sizeof(int), cudaMemcpyHostToDevice, c->st));
         nTasks = nBuckets = 1;
@@ -1640,11 +1665,11 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
         nBuckets = c->nBucketsLocal;
     }
     const int nWalkGroups = (nBuckets + GG_WALK_GB - 1) / GG_WALK_GB;
-    if ((rc = ensure(c, c->ghead, (size_t)(nWalkGroups + 1) * 6 * sizeof(int)))) return rc;
-    if ((rc = ensure(c, c->gcnt, (size_t)(nWalkGroups + 1) * 6 * sizeof(int)))) return rc;
-    if ((rc = ensure(c, c->bcnt, (size_t)(nBuckets + 1) * 3 * sizeof(int)))) return rc;
-    if ((rc = ensure(c, c->btot, (size_t)(nBuckets + 1) * sizeof(long long)))) return rc;
-    if ((rc = ensure(c, c->boff64, (size_t)(nBuckets + 1) * sizeof(long long)))) return rc;
+    if ((rc = gg_ensure(c, c->ghead, (size_t)(nWalkGroups + 1) * 6 * sizeof(int)))) return rc;
+    if ((rc = gg_ensure(c, c->gcnt, (size_t)(nWalkGroups + 1) * 6 * sizeof(int)))) return rc;
+    if ((rc = gg_ensure(c, c->bcnt, (size_t)(nBuckets + 1) * 3 * sizeof(int)))) return rc;
+    if ((rc = gg_ensure(c, c->btot, (size_t)(nBuckets + 1) * sizeof(long long)))) return rc;
+    if ((rc = gg_ensure(c, c->boff64, (size_t)(nBuckets + 1) * sizeof(long long)))) return rc;
     c->nTasks = nTasks;
 
     // ---- walk (lists -> HBM pool) + list evaluation
@@ -1692,10 +1717,10 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
     if (nTasks > 0) {
         if (!walkOnly) {
             if (c->capBlocks > 0x7fffffffu / 32u)
-                return fail(GG_ERR_NOMEM, "gg_gravity: interaction lists need %zu blocks (> 2^31 references)", c->capBlocks);
-            if ((rc = ensure(c, c->pool, c->capBlocks * 32 * sizeof(unsigned)))) return rc;
-            if ((rc = ensure(c, c->nextblk, c->capBlocks * sizeof(int)))) return rc;
-            if ((rc = ensure(c, c->poolmask, c->capBlocks * 32 * sizeof(gg_mask_t)))) return rc;
+                return gg_fail(GG_ERR_NOMEM, "gg_gravity: interaction lists need %zu blocks (> 2^31 references)", c->capBlocks);
+            if ((rc = gg_ensure(c, c->pool, c->capBlocks * 32 * sizeof(unsigned)))) return rc;
+            if ((rc = gg_ensure(c, c->nextblk, c->capBlocks * sizeof(int)))) return rc;
+            if ((rc = gg_ensure(c, c->poolmask, c->capBlocks * 32 * sizeof(gg_mask_t)))) return rc;
         }
         ta.pool = (unsigned *)c->pool.p;
         ta.nextBlk = (int *)c->nextblk.p;
@@ -1741,7 +1766,7 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
         size_t tmpBytes = 0;
         CK(cudaMemsetAsync((long long *)c->btot.p + nBuckets, 0, sizeof(long long), c->st));
         CK(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, (long long *)c->btot.p, (long long *)c->boff64.p, nBuckets + 1, c->st));
-        if ((rc = ensure(c, c->cubtmp, tmpBytes))) return rc;
+        if ((rc = gg_ensure(c, c->cubtmp, tmpBytes))) return rc;
         CK(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmpBytes, (long long *)c->btot.p, (long long *)c->boff64.p, nBuckets + 1, c->st));
         long long nEntries = 0;
         int hm3[4];
@@ -1749,15 +1774,15 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
         CK(cudaMemcpyAsync(hm3, c->misc.p, sizeof(hm3), cudaMemcpyDeviceToHost, c->st));
         CK(cudaStreamSynchronize(c->st));
         tr.mark("gravity: walk sync");
-        if (hm3[1]) return fail(GG_ERR_UNSUPPORTED, "gg_gravity: walk frontier overflowed %d entries (tree too deep)", GG_STACK_CAP);
+        if (hm3[1]) return gg_fail(GG_ERR_UNSUPPORTED, "gg_gravity: walk frontier overflowed %d entries (tree too deep)", GG_STACK_CAP);
         if ((size_t)hm3[3] > c->capBlocks) {
             // the chain pool was too small: the walk kept counting, so hm3[3] is what it needs -- grow and run again
-            if (depth >= 2) return fail(GG_ERR_NOMEM, "gg_gravity: list pool overflow persists (%d blocks)", hm3[3]);
+            if (depth >= 2) return gg_fail(GG_ERR_NOMEM, "gg_gravity: list pool overflow persists (%d blocks)", hm3[3]);
             c->capBlocks = (size_t)hm3[3] + (size_t)hm3[3] / 8 + 1024;
             return run_gravity(c, prm, singleTask, stats, depth + 1);
         }
         nListEntries = nEntries;
-        if ((rc = ensure(c, c->lists, ((size_t)nEntries + 32) * sizeof(unsigned)))) return rc;
+        if ((rc = gg_ensure(c, c->lists, ((size_t)nEntries + 32) * sizeof(unsigned)))) return rc;
         ta.lists = (unsigned *)c->lists.p;
         CK(gg_launch_scatter_kernel(ta, c->nSM, c->st));
         if (c->momPending) CK(cudaStreamWaitEvent(c->st, c->evMom, 0)); // the moments arrive on the second stream
@@ -1780,10 +1805,10 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
     st3Guard.armed = false; // c->st waited for evStats
     tr.mark("gravity: final sync");
     if (evalQueued) c->momPending = false; // k_eval waited for the moments and has finished
-    if (hm[1]) return fail(GG_ERR_UNSUPPORTED, "gg_gravity: walk frontier overflowed %d entries (tree too deep)", GG_STACK_CAP);
+    if (hm[1]) return gg_fail(GG_ERR_UNSUPPORTED, "gg_gravity: walk frontier overflowed %d entries (tree too deep)", GG_STACK_CAP);
     if (!walkOnly && (size_t)hm[3] > c->capBlocks) {
         // the list pool was too small: the walk kept counting, so hm[3] is what it needs -- grow and run again
-        if (depth >= 2) return fail(GG_ERR_NOMEM, "gg_gravity: list pool overflow persists (%d blocks)", hm[3]);
+        if (depth >= 2) return gg_fail(GG_ERR_NOMEM, "gg_gravity: list pool overflow persists (%d blocks)", hm[3]);
         c->capBlocks = (size_t)hm[3] + (size_t)hm[3] / 8 + 1024;
         return run_gravity(c, prm, singleTask, stats, depth + 1);
     }
@@ -1817,11 +1842,11 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
 // like the reference -- the dummy's interactions are not counted in dPartSum / dCellSum / dFlop.
 int run_sun(gg_context *c, const gg_params *prm, gg_stats *stats) {
     if (prm->bPeriodic || prm->nReps != 0)
-        return fail(GG_ERR_ARG, "gg_gravity: bDoSun needs open boundaries (the reference asserts it, pkd.c:3013-3014)");
+        return gg_fail(GG_ERR_ARG, "gg_gravity: bDoSun needs open boundaries (the reference asserts it, pkd.c:3013-3014)");
     if (c->dom.size() != 1 || c->nTop > 0)
-        return fail(GG_ERR_UNSUPPORTED, "gg_gravity: bDoSun with several domains is not supported");
+        return gg_fail(GG_ERR_UNSUPPORTED, "gg_gravity: bDoSun with several domains is not supported");
     int rc;
-    if ((rc = finish_mom(c))) return rc;
+    if ((rc = gg_finish_mom(c))) return rc;
     const Domain &L = c->dom[0];
     const int n = L.nPart, nn = L.nNodes;
     PartS ps;
@@ -1865,9 +1890,9 @@ extern "C" {
 
 int gg_gravity(gg_context *c, const gg_params *prm, double *a, double *fPot, double *dtGrav, double *fWeight,
                gg_stats *stats) {
-    if (!c || !prm) return fail(GG_ERR_ARG, "gg_gravity: null argument");
+    if (!c || !prm) return gg_fail(GG_ERR_ARG, "gg_gravity: null argument");
     const bool wantOut = !(prm->flags & (GG_FLAG_NO_DOWNLOAD | GG_FLAG_WALK_ONLY));
-    if (wantOut && (!a || !fPot || !dtGrav || !fWeight)) return fail(GG_ERR_ARG, "gg_gravity: null output array");
+    if (wantOut && (!a || !fPot || !dtGrav || !fWeight)) return gg_fail(GG_ERR_ARG, "gg_gravity: null output array");
     // Zero-copy delivery: in overwrite mode, output arrays that are mapped pinned host memory (gg_host_alloc,
     // cudaHostAlloc, cudaHostRegister) are written by the kernels themselves as each sink bucket finishes, so the
     // device->host transfer overlaps the evaluation instead of following it.  Only ACTIVE particles are written
@@ -1887,7 +1912,7 @@ int gg_gravity(gg_context *c, const gg_params *prm, double *a, double *fPot, dou
         if (zeroCopy) for (int k = 0; k < 4; ++k) { c->zc[k] = dp[k]; c->zcHost[k] = hp[k]; }
     }
     if (c->stateN > 0 && c->stateDirty)
-        return fail(GG_ERR_ARG, "gg_gravity: the resident particles moved since the last tree build (gg_state_build first)");
+        return gg_fail(GG_ERR_ARG, "gg_gravity: the resident particles moved since the last tree build (gg_state_build first)");
     int rc = run_gravity(c, prm, nullptr, stats);
     c->zc[0] = c->zc[1] = c->zc[2] = c->zc[3] = nullptr;
     if (rc) return rc;
@@ -1950,7 +1975,7 @@ int gg_gravity(gg_context *c, const gg_params *prm, double *a, double *fPot, dou
 }
 
 int gg_bucket_counts(gg_context *c, int *counts3) {
-    if (!c || !counts3 || c->dom.empty()) return fail(GG_ERR_ARG, "gg_bucket_counts: bad argument");
+    if (!c || !counts3 || c->dom.empty()) return gg_fail(GG_ERR_ARG, "gg_bucket_counts: bad argument");
     CK(cudaSetDevice(c->device));
     CK(cudaMemcpyAsync(counts3, c->counts.p, sizeof(int) * 3 * (size_t)c->dom[0].nNodes, cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
@@ -1958,8 +1983,8 @@ int gg_bucket_counts(gg_context *c, int *counts3) {
 }
 
 int gg_bucket_walk(gg_context *c, const gg_params *prm, int iBucket, int n3[3]) {
-    if (!c || !prm || !n3 || c->dom.empty()) return fail(GG_ERR_ARG, "gg_bucket_walk: bad argument");
-    if (iBucket < 0 || iBucket >= c->dom[0].nNodes) return fail(GG_ERR_ARG, "gg_bucket_walk: iBucket=%d", iBucket);
+    if (!c || !prm || !n3 || c->dom.empty()) return gg_fail(GG_ERR_ARG, "gg_bucket_walk: bad argument");
+    if (iBucket < 0 || iBucket >= c->dom[0].nNodes) return gg_fail(GG_ERR_ARG, "gg_bucket_walk: iBucket=%d", iBucket);
     gg_params p = *prm;
     p.flags |= GG_FLAG_WALK_ONLY;
     Task t{iBucket, 0, 0, 0};
@@ -1972,12 +1997,12 @@ int gg_bucket_walk(gg_context *c, const gg_params *prm, int iBucket, int n3[3]) 
 }
 
 int gg_ewald_table(gg_context *c, const gg_params *prm, double *ewt5, int nMax, int *pnEwh) {
-    if (!c || !prm || !pnEwh) return fail(GG_ERR_ARG, "gg_ewald_table: bad argument");
+    if (!c || !prm || !pnEwh) return gg_fail(GG_ERR_ARG, "gg_ewald_table: bad argument");
     if (c->rootLazy) {
         int rcr = fetch_root_lazy(c);
         if (rcr) return rcr;
     }
-    if (!c->haveRoot) return fail(GG_ERR_ARG, "gg_ewald_table: gg_set_root_moments has not been called");
+    if (!c->haveRoot) return gg_fail(GG_ERR_ARG, "gg_ewald_table: gg_set_root_moments has not been called");
     std::vector<double> ewt;
     gg_ewald_table_host(c->root, prm->fPeriod[0], prm->fEwhCut, prm->iEwOrder, ewt);
     *pnEwh = (int)(ewt.size() / 5);
@@ -1986,10 +2011,10 @@ int gg_ewald_table(gg_context *c, const gg_params *prm, double *ewt5, int nMax, 
 }
 
 int gg_measure_fp32_peak(gg_context *c, double *pTflops, double *pMs) {
-    if (!c || !pTflops) return fail(GG_ERR_ARG, "gg_measure_fp32_peak: null");
+    if (!c || !pTflops) return gg_fail(GG_ERR_ARG, "gg_measure_fp32_peak: null");
     CK(cudaSetDevice(c->device));
     int rc;
-    if ((rc = ensure(c, c->misc, 16 * sizeof(int)))) return rc;
+    if ((rc = gg_ensure(c, c->misc, 16 * sizeof(int)))) return rc;
     const int iters = 4096, blocks = c->nSM * 8, threads = 256;
     double best = 0.0, bestMs = 0.0;
     for (int rep = 0; rep < 4; ++rep) { // first repetition warms the clocks up
@@ -2009,18 +2034,18 @@ int gg_measure_fp32_peak(gg_context *c, double *pTflops, double *pMs) {
 }
 
 int gg_flush_l2(gg_context *c) {
-    if (!c) return fail(GG_ERR_ARG, "gg_flush_l2: null");
+    if (!c) return gg_fail(GG_ERR_ARG, "gg_flush_l2: null");
     CK(cudaSetDevice(c->device));
     const size_t bytes = (size_t)384 << 20; // 3x the 126 MB L2
     int rc;
-    if ((rc = ensure(c, c->flush, bytes))) return rc;
+    if ((rc = gg_ensure(c, c->flush, bytes))) return rc;
     CK(cudaMemsetAsync(c->flush.p, 0x5a, bytes, c->st));
     CK(cudaStreamSynchronize(c->st));
     return GG_OK;
 }
 
 int gg_device_results(gg_context *c, void **a, void **fPot, void **dtGrav, void **fWeight) {
-    if (!c) return fail(GG_ERR_ARG, "gg_device_results: null");
+    if (!c) return gg_fail(GG_ERR_ARG, "gg_device_results: null");
     if (a) *a = c->acc.p;
     if (fPot) *fPot = c->pot.p;
     if (dtGrav) *dtGrav = c->dtg.p;

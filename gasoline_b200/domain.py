@@ -367,11 +367,12 @@ class Domain:
         ints = np.concatenate([[t.nNodes, t.iRoot, h.nLocal, 0], t.pLower, t.pUpper, t.iLower, t.iUpper]).astype(np.int32)
         return np.ascontiguousarray(dbl, dtype=np.float64), ints
 
-    def attach(self):
-        """Hand kdTop + ilcnRoot to the GPU context (gg_set_local via upload, gg_set_top, gg_set_root_moments)."""
+    def attach(self, upload: bool = True):
+        """Hand kdTop + ilcnRoot to the GPU context (gg_set_local via upload, gg_set_top, gg_set_root_moments).
+        upload=False: the local domain is already resident (only the top tree / Ewald root go up)."""
         if self.pkd is None:
             raise _pkd.GasolineB200Error("Domain.attach: created without a device")
-        if not self.device_build:  # (a device-built domain is already loaded)
+        if upload and not self.device_build:  # (a device-built domain is already loaded)
             self.pkd.upload()
         k = self.kdTop
         self.pkd.pkdDistribCells(k["pLower"], k["bUsed"], k["r"], k["fMass"], k["fSoft"], k["fOpen2"], k["mom"])
@@ -745,6 +746,83 @@ class DistributedExchange:
         return nrecv
 
 
+class LibExchange:
+    """One Domain per rank with every collective BELOW the C ABI (csrc/gg_comm.cu): the small all-gathers of the top-tree
+    assembly go through gg_comm_allgather, the tree exchange is gg_exchange (LET export -> NCCL send/receive or
+    in-process peer copies -> ingest).  The rank's PKD must have a communicator (commInitNccl / commInitLocal)."""
+
+    def __init__(self, domain: Domain):
+        self.d = domain
+        self.timing = {}
+        self.let_bytes = (0, 0)
+        self.stats = None
+        self._summaries = None
+
+    def top_tree(self):
+        pk = self.d.pkd
+        summaries = pk.commAllgather(self.d.summary())
+        anc = pk.commAllgather(self.d.ancestor_moments(summaries))
+        self.d.assemble(summaries, anc)
+        self._summaries = summaries
+        return summaries, anc
+
+    def exchange(self, g, top: bool = True, upload: bool = True):
+        """upload: gg_set_local of the host's tree + particles (a new step of a host-driven run); top: assemble the top
+        tree again (after a tree build).  Then gg_set_top / gg_set_root_moments and the collective gg_exchange."""
+        import time
+        tm = {}
+        t0 = time.perf_counter()
+
+        def lap(name):
+            nonlocal t0
+            t1 = time.perf_counter()
+            tm[name] = t1 - t0
+            t0 = t1
+
+        d = self.d
+        if top or d.kdTop is None:
+            self.top_tree()
+            lap("top_tree")
+        d.attach(upload=upload)
+        lap("attach_local" if upload else "set_top")
+        st = d.pkd.pkdExchange(g, self._summaries[:, 0:6])
+        lap("gg_exchange")
+        tm.update(let_export=st["msExport"] * 1e-3, transfer=st["msTransfer"] * 1e-3, ingest=st["msIngest"] * 1e-3)
+        self.timing, self.stats = tm, st
+        self.let_bytes = (int(st["bytesSent"]), int(st["bytesReceived"]))
+        return int(st["bytesReceived"])
+
+
+def run_threads(domains: list, g, rounds: int = 1):
+    """All ranks inside this process as THREADS with an in-process group (gg_group): every rank runs the same collective
+    sequence a multi-process job runs -- top-tree all-gathers and gg_exchange below the ABI.  Returns the LibExchange
+    drivers.  (ctypes releases the GIL inside the library, so the group's barriers make progress.)"""
+    import threading
+    grp = _pkd.Group(len(domains))
+    drivers = [LibExchange(d) for d in domains]
+    errs = []
+
+    def work(k):
+        try:
+            d = domains[k]
+            d.pkd.commInitLocal(grp, d.idSelf)
+            for _ in range(rounds):
+                drivers[k].exchange(g)
+        except Exception as e:  # surfaced below; a failing rank would otherwise leave the others in a barrier
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(len(domains))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=300)
+    if errs:
+        raise errs[0]
+    if any(t.is_alive() for t in th):
+        raise _pkd.GasolineB200Error("run_threads: a rank did not return (collective mismatch)")
+    return drivers
+
+
 class _DevView:
     """A torch uint8 view of a raw device allocation owned by the library (no copy, no ownership)."""
 
@@ -784,15 +862,21 @@ def device_orb_share(p, rank: int, world: int, device: int, backend_device: str 
 
 
 def setup_rank(p, theta: float, rank: int, world: int, device: int | None, nBucket: int = 8, iOrder: int = 4,
-               weights=None, backend_device: str | None = None, device_build: bool = False, device_orb: bool = False):
+               weights=None, backend_device: str | None = None, device_build: bool = False, device_orb: bool = False,
+               comm: str = "lib", idx=None):
     """What one torch.distributed rank does before its first force evaluation (bench.py --gpus N, tests): every rank
     holds the same particle set `p`, takes ITS share of the ORB decomposition (the host's job in a Gasoline run,
     pstDomainDecomp pst.c:1854), builds its local tree and creates its GPU context.  Returns (pkd, exchange) where
     exchange() runs the top-tree assembly + the tree exchange (steps 1-5 of this module) and returns the bytes this
     rank received; with device=None no GPU context exists (host-only checks) and pkd is the host store.
     device_orb: the share comes from the reference's decomposition run on the devices (device_orb_share) instead of
-    orb_decompose."""
-    if device_orb:
+    orb_decompose.  idx: this rank's particle indices when the caller has already decomposed.
+    comm: "lib" (default on GPUs) -- the rank's context gets an NCCL communicator of its own (gg_comm_init; the id
+    travels by torch.distributed's object broadcast, the host's control plane) and every data-plane collective runs
+    below the C ABI (LibExchange); "torch" -- the bring-up path through torch.distributed tensors."""
+    if idx is not None:
+        idx = np.asarray(idx)  # the caller already knows this rank's share
+    elif device_orb:
         idx = device_orb_share(p, rank, world, device, backend_device or "cuda", weights=weights)
     else:
         parts = orb_decompose(p.x, p.y, p.z, world, weights=weights)
@@ -800,15 +884,28 @@ def setup_rank(p, theta: float, rank: int, world: int, device: int | None, nBuck
     d = Domain(rank, world, p.x[idx], p.y[idx], p.z[idx], p.m[idx], p.h[idx], p.period, theta, nBucket=nBucket,
                iOrder=iOrder, pinned=device is not None, device=device, device_build=device_build)
     d.global_index = idx[d.pkd.treeOrder if device_build else d.host.iOrderMap]  # tree position -> index in p
-    ex = DistributedExchange(d, backend_device or ("cpu" if device is None else "cuda"))
     attach = device is not None
+    lib = attach and (backend_device or "cuda") != "cpu" and comm != "torch"
+    if lib:
+        # the library's own NCCL communicator: the id is created on rank 0 and handed round by the host's control plane
+        import torch
+        import torch.distributed as dist
+        ident = [_pkd.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ident, src=0)
+        d.pkd.commInitNccl(ident[0], rank, world)
+        ex = LibExchange(d)
+    else:
+        ex = DistributedExchange(d, backend_device or ("cpu" if device is None else "cuda"))
 
-    def exchange(top: bool = True, let=None, rebuild: bool = False):
+    def exchange(top: bool = True, let=None, rebuild: bool = False, upload: bool = True):
         """let = GravityParams: send pruned locally-essential trees (gg_let_export) instead of whole domains.
-        rebuild (device_build only): build the local tree again from the rank's particles first (a new step)."""
+        rebuild (device_build only): build the local tree again from the rank's particles first (a new step).
+        upload=False (library exchange only): the local domain is already resident on the device."""
         if rebuild:
             d.rebuild()
             top = True
+        if lib:
+            return ex.exchange(let, top=top, upload=upload)
         if attach and ex.dev != "cpu":
             return ex.exchange_let(let, top=top) if let is not None else ex.exchange_packed(top=top)
         return ex.exchange(attach=attach)

@@ -54,6 +54,13 @@ class gg_stats(C.Structure):
                 ("nSunCellNewt", C.c_int)]
 
 
+class gg_exchange_stats(C.Structure):
+    _fields_ = [("msExport", C.c_double), ("msTransfer", C.c_double), ("msIngest", C.c_double), ("msTotal", C.c_double),
+                ("bytesSent", C.c_double), ("bytesReceived", C.c_double), ("bytesWholeDomain", C.c_double),
+                ("nKernelLaunches", C.c_int)]
+
+
+GG_UNIQUE_ID_BYTES = 128
 _lib = None
 
 
@@ -117,6 +124,16 @@ def load_library(path: str | None = None):
     L.gg_orb_weight.argtypes = [C.c_void_p, C.c_int, _ip, _ip, _dp, _ip, _ip, _dp, _dp]
     L.gg_orb_split.argtypes = [C.c_void_p, C.c_int, _ip, _ip, _dp]
     L.gg_orb_fetch.argtypes = [C.c_void_p, C.c_void_p]
+    L.gg_comm_unique_id.argtypes = [C.c_void_p]
+    L.gg_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    L.gg_group_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    L.gg_group_destroy.argtypes = [C.c_void_p]
+    L.gg_group_destroy.restype = None
+    L.gg_comm_init_local.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.gg_comm_free.argtypes = [C.c_void_p]
+    L.gg_comm_info.argtypes = [C.c_void_p, _ip, _ip, _ip, _ip]
+    L.gg_comm_allgather.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.gg_exchange.argtypes = [C.c_void_p, C.POINTER(gg_params), _dp, C.POINTER(gg_exchange_stats)]
     L.gg_measure_fp32_peak.argtypes = [C.c_void_p, _dp, _dp]
     L.gg_flush_l2.argtypes = [C.c_void_p]
     _lib = L
@@ -147,6 +164,31 @@ def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
     _check(L.gg_host_alloc(C.byref(p), n), "gg_host_alloc")
     buf = (C.c_char * n).from_address(p.value)
     return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+
+
+def comm_unique_id() -> bytes:
+    """gg_comm_unique_id (ncclGetUniqueId): created on ONE rank, handed to every rank's commInitNccl by the host."""
+    buf = C.create_string_buffer(GG_UNIQUE_ID_BYTES)
+    _check(load_library().gg_comm_unique_id(buf), "gg_comm_unique_id")
+    return buf.raw
+
+
+class Group:
+    """gg_group: the meeting point of ranks that live in one process (threads)."""
+
+    def __init__(self, n: int):
+        self._L = load_library()
+        self.handle = C.c_void_p()
+        self.n = int(n)
+        _check(self._L.gg_group_create(C.byref(self.handle), self.n), "gg_group_create")
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self._L.gg_group_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:
+            pass
 
 
 @dataclass
@@ -531,6 +573,43 @@ class PKD:
         """pkdDistribRoot (pkd.c:4472): the Ewald root expansion for every rank."""
         self.ilcnRoot = np.array(ilcnRoot, dtype=np.float64, copy=True)
         _check(self._L.gg_set_root_moments(self._ctx, _d(self.ilcnRoot)), "gg_set_root_moments")
+
+    # -- multi-rank exchange below the ABI (csrc/gg_comm.cu) ---------------------------------------------------
+    def commInitNccl(self, unique_id: bytes, rank: int, nRanks: int):
+        """gg_comm_init: this rank's NCCL communicator (collective over all ranks; id from comm_unique_id() on one rank)."""
+        buf = C.create_string_buffer(bytes(unique_id), GG_UNIQUE_ID_BYTES)
+        _check(self._L.gg_comm_init(self._ctx, buf, int(rank), int(nRanks)), "gg_comm_init")
+        self.commRank, self.commSize = int(rank), int(nRanks)
+
+    def commInitLocal(self, group: "Group", rank: int):
+        """gg_comm_init_local: ranks that are threads of this process (several may share one GPU)."""
+        _check(self._L.gg_comm_init_local(self._ctx, group.handle, int(rank)), "gg_comm_init_local")
+        self._group = group  # keep it alive
+        self.commRank, self.commSize = int(rank), group.n
+
+    def commInfo(self):
+        o = np.zeros(4, np.int32)
+        _check(self._L.gg_comm_info(self._ctx, _i(o[0:1]), _i(o[1:2]), _i(o[2:3]), _i(o[3:4])), "gg_comm_info")
+        return dict(rank=int(o[0]), nRanks=int(o[1]), transport="group" if o[2] else "nccl", nccl_version=int(o[3]))
+
+    def commAllgather(self, a: np.ndarray) -> np.ndarray:
+        """gg_comm_allgather of a small host array: returns [nRanks] + a.shape."""
+        a = np.ascontiguousarray(a)
+        out = np.zeros((self.commSize,) + a.shape, dtype=a.dtype)
+        _check(self._L.gg_comm_allgather(self._ctx, a.ctypes.data_as(C.c_void_p), a.nbytes, out.ctypes.data_as(C.c_void_p)),
+               "gg_comm_allgather")
+        return out
+
+    def pkdExchange(self, g: "GravityParams", bndAll=None, want_stats: bool = True):
+        """gg_exchange: the collective that replaces pkdRemoteWalk's pulls (walk.c:181-304) -- pruned locally-essential trees
+        of every other rank become this rank's remote domains.  bndAll [nRanks][6]: the ranks' root bounds (None: gathered
+        by the library).  Returns the phase timings / byte counts."""
+        prm = self._params(g, 0, 0)
+        b = None if bndAll is None else np.ascontiguousarray(bndAll, dtype=np.float64)
+        st = gg_exchange_stats()
+        _check(self._L.gg_exchange(self._ctx, C.byref(prm), _d(b) if b is not None else None,
+                                   C.byref(st) if want_stats else None), "gg_exchange")
+        return {k: getattr(st, k) for k, _ in gg_exchange_stats._fields_}
 
     # -- the hot path ---------------------------------------------------------------------------------------
     def _params(self, g: GravityParams, accumulate: int, flags: int) -> gg_params:

@@ -174,6 +174,50 @@ int gg_export_size(gg_context *ctx, size_t *bytes, int hdr[3]);
 int gg_export_local(gg_context *ctx, void *dst);
 int gg_set_remote_packed(gg_context *ctx, int id, const int hdr[3], const void *src);
 
+/*
+ * The exchange BELOW the ABI (multi-rank hosts: one context = one rank = one GPU).  In the reference every rank's
+ * pkdGravAll pulls remote cells and particles on demand through the MDL software cache (pkdRemoteWalk, walk.c:181-304:
+ * mdlAquire(CID_CELL / CID_PARTICLE, ..., id)); here every rank pushes, once per force evaluation, the locally
+ * essential part of its tree to every other rank and the library moves the bytes itself:
+ *   gg_comm_unique_id + gg_comm_init   an NCCL communicator over the ranks' GPUs (NVLink / NVSwitch).  One rank creates
+ *                                      the 128-byte id, the host distributes it by its own means (an MDL service,
+ *                                      MPI_Bcast, the pthread MDL's shared memory) and every rank calls gg_comm_init --
+ *                                      collectively, like ncclCommInitRank.  Ranks may be processes or threads.
+ *   gg_group_create + gg_comm_init_local   the same for ranks that are threads of ONE process (pthread MDL): pointers
+ *                                      are published in the group and the pieces move by peer-to-peer copies; several
+ *                                      ranks may then share one GPU (how the one-GPU test box runs multi-rank hosts).
+ *   gg_exchange                        COLLECTIVE, after gg_set_local / gg_build_local and before gg_gravity: forgets the
+ *                                      remote domains of the previous step, prunes the local tree against every other
+ *                                      rank's root bounds (gg_let_export's rule, all periodic images of prm), sends each
+ *                                      rank its piece (sizes by an all-gather, trees by grouped send/receive on the
+ *                                      context's stream) and ingests what arrives as remote domain r = rank r.
+ *                                      bndAll[nRanks][6] = every rank's root bounds (fMin[3], fMax[3]) as the host's top
+ *                                      tree knows them (pkd->kdTop leaves), or NULL: the library gathers them itself.
+ *                                      The top tree itself (gg_set_top) and the Ewald root (gg_set_root_moments) are the
+ *                                      host's (pkdDistribCells / pkdDistribRoot) and may be set before or after.
+ *   gg_comm_allgather                  small host buffers (<= 8 KB per rank) over the same transport -- what a host
+ *                                      without an MDL of its own uses to assemble the top tree.
+ * Rank r must be the context whose local domain has idSelf == r.
+ */
+#define GG_UNIQUE_ID_BYTES 128
+typedef struct gg_group gg_group;
+typedef struct gg_exchange_stats {
+    double msExport, msTransfer, msIngest, msTotal; /* device time of the phases (CUDA events on the context's stream) */
+    double bytesSent, bytesReceived;                /* pruned trees this rank sent / received */
+    double bytesWholeDomain;                        /* what sending the whole local domain to ONE rank would have moved */
+    int nKernelLaunches;
+} gg_exchange_stats;
+int gg_comm_unique_id(void *id /* GG_UNIQUE_ID_BYTES */);
+int gg_comm_init(gg_context *ctx, const void *id, int rank, int nRanks);
+int gg_group_create(gg_group **pg, int nRanks);
+void gg_group_destroy(gg_group *g);
+int gg_comm_init_local(gg_context *ctx, gg_group *g, int rank);
+int gg_comm_free(gg_context *ctx);
+/* transport: 0 NCCL, 1 in-process group; ncclVersion as ncclGetVersion reports it (0 for the group transport) */
+int gg_comm_info(gg_context *ctx, int *pRank, int *pnRanks, int *pTransport, int *pNcclVersion);
+int gg_comm_allgather(gg_context *ctx, const void *mine, size_t bytes, void *all);
+int gg_exchange(gg_context *ctx, const gg_params *prm, const double *bndAll, gg_exchange_stats *stats);
+
 /* pkd->ilcnRoot (pkdCalcRoot/pkdDistribRoot, pkd.c:4395-4493): complete l<=4 moments of the whole box for Ewald. */
 int gg_set_root_moments(gg_context *ctx, const double root[GG_NROOT]);
 
