@@ -545,6 +545,15 @@ extern "C" {
 const char *gg_last_error(void) { return g_err; }
 int gg_version(void) { return 100; }
 
+int gg_device_count(int *pn) {
+    if (!pn) return gg_fail(GG_ERR_ARG, "gg_device_count: null");
+    int nDev = 0;
+    cudaError_t e = cudaGetDeviceCount(&nDev);
+    if (e != cudaSuccess) return gg_fail(GG_ERR_CUDA, "gg_device_count: %s", cudaGetErrorString(e));
+    *pn = nDev;
+    return GG_OK;
+}
+
 int gg_create(gg_context **pctx, int device) {
     if (!pctx) return gg_fail(GG_ERR_ARG, "gg_create: null out pointer");
     int nDev = 0;
@@ -1515,9 +1524,9 @@ int pack_top(gg_context *c, int *pRoot) {
     }
     int rc;
     const size_t keep = (size_t)topBase;
-    if ((rc = gg_ensure(c, c->nodes, (keep + n) * sizeof(NodeW), keep * sizeof(NodeW)))) return rc;
-    if ((rc = gg_ensure(c, c->momf, (keep + n) * 128, keep * 128))) return rc;
-    if ((rc = gg_ensure(c, c->momq, (keep + n) * 48, keep * 48))) return rc;
+    if ((rc = gg_ensure(c, c->nodes, (keep + n + 1) * sizeof(NodeW), keep * sizeof(NodeW)))) return rc;
+    if ((rc = gg_ensure(c, c->momf, (keep + n + 1) * 128, keep * 128))) return rc;
+    if ((rc = gg_ensure(c, c->momq, (keep + n + 1) * 48, keep * 48))) return rc;
     CK(cudaMemcpyAsync((NodeW *)c->nodes.p + topBase, w.data(), sizeof(NodeW) * n, cudaMemcpyHostToDevice, c->st));
     CK(cudaMemcpyAsync((char *)c->momf.p + keep * 128, mf.data(), 128 * (size_t)n, cudaMemcpyHostToDevice, c->st));
     CK(cudaMemcpyAsync((char *)c->momq.p + keep * 48, mq.data(), 48 * (size_t)n, cudaMemcpyHostToDevice, c->st));
@@ -1565,11 +1574,17 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
 
     if ((rc = gg_ensure(c, c->imgoff, im.off.size() * sizeof(double)))) return rc;
     CK(cudaMemcpyAsync(c->imgoff.p, im.off.data(), im.off.size() * sizeof(double), cudaMemcpyHostToDevice, c->st));
-    if ((rc = gg_ensure(c, c->counts, (size_t)(nn + 1) * 3 * sizeof(int), c->sunMode ? (size_t)nn * 3 * sizeof(int) : 0))) return rc;
-    if ((rc = gg_ensure(c, c->acc, (size_t)(n + 1) * 3 * sizeof(double)))) return rc;
-    if ((rc = gg_ensure(c, c->pot, (size_t)(n + 1) * sizeof(double)))) return rc;
-    if ((rc = gg_ensure(c, c->dtg, (size_t)(n + 1) * sizeof(double)))) return rc;
-    if ((rc = gg_ensure(c, c->fweight, (size_t)(n + 1) * sizeof(double)))) return rc;
+    // bDoSun pass: the dummy sink lives in the spare slots BEHIND everything that is loaded -- particle sunP, node sunN
+    // (behind the remote domains and the top cells when there are any) -- and the per-particle / per-node result
+    // arrays, indexed by the same numbers, grow to cover them while keeping the main pass's results
+    const int sunP = c->nPartAll, sunN = nNodesAll;
+    const size_t nRes = c->sunMode ? (size_t)sunP + 1 : (size_t)n + 1, nCnt = c->sunMode ? (size_t)sunN + 1 : (size_t)nn + 1;
+    const bool keepRes = c->sunMode;
+    if ((rc = gg_ensure(c, c->counts, nCnt * 3 * sizeof(int), keepRes ? (size_t)nn * 3 * sizeof(int) : 0))) return rc;
+    if ((rc = gg_ensure(c, c->acc, nRes * 3 * sizeof(double), keepRes ? (size_t)n * 3 * sizeof(double) : 0))) return rc;
+    if ((rc = gg_ensure(c, c->pot, nRes * sizeof(double), keepRes ? (size_t)n * sizeof(double) : 0))) return rc;
+    if ((rc = gg_ensure(c, c->dtg, nRes * sizeof(double), keepRes ? (size_t)n * sizeof(double) : 0))) return rc;
+    if ((rc = gg_ensure(c, c->fweight, nRes * sizeof(double), keepRes ? (size_t)n * sizeof(double) : 0))) return rc;
     if ((rc = gg_ensure(c, c->nloop, (size_t)(n + 1) * sizeof(int)))) return rc;
     if ((rc = gg_ensure(c, c->sums, 16 * sizeof(unsigned long long)))) return rc;
     if ((rc = gg_ensure(c, c->misc, 16 * sizeof(int)))) return rc;
@@ -1580,12 +1595,12 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
     if ((rc = gg_ensure(c, c->bnode, (size_t)(nn + 1) * sizeof(int)))) return rc;
 
     CK(cudaEventRecord(c->ev[0], c->st));
-    if (c->sunMode) { // only the dummy sink's slot (index n) and its bucket's counters: everything else holds results
-        CK(cudaMemsetAsync((int *)c->counts.p + 3 * (size_t)nn, 0xff, 3 * sizeof(int), c->st));
-        CK(cudaMemsetAsync((double *)c->acc.p + 3 * (size_t)n, 0, 3 * sizeof(double), c->st));
-        CK(cudaMemsetAsync((double *)c->pot.p + n, 0, sizeof(double), c->st));
-        CK(cudaMemsetAsync((double *)c->dtg.p + n, 0, sizeof(double), c->st));
-        CK(cudaMemsetAsync((double *)c->fweight.p + n, 0, sizeof(double), c->st));
+    if (c->sunMode) { // only the dummy sink's slot and its bucket's counters: everything else holds results
+        CK(cudaMemsetAsync((int *)c->counts.p + 3 * (size_t)sunN, 0xff, 3 * sizeof(int), c->st));
+        CK(cudaMemsetAsync((double *)c->acc.p + 3 * (size_t)sunP, 0, 3 * sizeof(double), c->st));
+        CK(cudaMemsetAsync((double *)c->pot.p + sunP, 0, sizeof(double), c->st));
+        CK(cudaMemsetAsync((double *)c->dtg.p + sunP, 0, sizeof(double), c->st));
+        CK(cudaMemsetAsync((double *)c->fweight.p + sunP, 0, sizeof(double), c->st));
     } else {
         CK(cudaMemsetAsync(c->counts.p, 0xff, (size_t)nn * 3 * sizeof(int), c->st));
         CK(cudaMemsetAsync(c->acc.p, 0, (size_t)n * 3 * sizeof(double), c->st));
@@ -1706,7 +1721,7 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
     ta.maxBucket = c->maxBucket;
     ta.walkOnly = walkOnly ? 1 : 0;
     ta.mono64 = prm->bPeriodic ? 1 : 0;
-    ta.sunNode = c->sunMode ? nn : -1;
+    ta.sunNode = c->sunMode ? sunN : -1;
     ta.sunBox = 1e-14; // dTinyBox, pkd.c:3004
     ta.acc = (double *)c->acc.p;
     ta.pot = (double *)c->pot.p;
@@ -1843,26 +1858,32 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
 int run_sun(gg_context *c, const gg_params *prm, gg_stats *stats) {
     if (prm->bPeriodic || prm->nReps != 0)
         return gg_fail(GG_ERR_ARG, "gg_gravity: bDoSun needs open boundaries (the reference asserts it, pkd.c:3013-3014)");
-    if (c->dom.size() != 1 || c->nTop > 0)
-        return gg_fail(GG_ERR_UNSUPPORTED, "gg_gravity: bDoSun with several domains is not supported");
     int rc;
     if ((rc = gg_finish_mom(c))) return rc;
-    const Domain &L = c->dom[0];
-    const int n = L.nPart, nn = L.nNodes;
+    // Several domains (pst.c:3258-3277 hands bDoSun to the ONE rank whose domain holds the origin; that rank's dummy sink
+    // then walks top tree, local and remote trees like any bucket): the spare slots are the ones behind everything loaded.
+    const int sunP = c->nPartAll, sunN = c->nNodesAll + c->nTop;
+    if ((rc = gg_ensure(c, c->parts, ((size_t)sunP + 1) * sizeof(PartS), (size_t)sunP * sizeof(PartS)))) return rc;
+    if ((rc = gg_ensure(c, c->nodes, ((size_t)sunN + 1) * sizeof(NodeW), (size_t)sunN * sizeof(NodeW)))) return rc;
+    if ((rc = gg_ensure(c, c->momf, ((size_t)sunN + 1) * 128, (size_t)sunN * 128))) return rc;
+    if ((rc = gg_ensure(c, c->momq, ((size_t)sunN + 1) * 48, (size_t)sunN * 48))) return rc;
+    const int nLoc = c->dom[0].nPart;
+    if ((rc = gg_ensure(c, c->hsoft, ((size_t)sunP + 1) * sizeof(double), ((size_t)nLoc + 1) * sizeof(double)))) return rc;
+    if (!c->hActive.empty() && (rc = gg_ensure(c, c->active, ((size_t)sunP + 1) * sizeof(int), ((size_t)nLoc + 1) * sizeof(int)))) return rc;
     PartS ps;
     ps.x = ps.y = ps.z = 0.0; ps.m = 0.f; ps.h = (float)prm->dSunSoft;
     NodeW w;
     w.rx = w.ry = w.rz = 0.0; w.fMass = 0.0; w.fOpen2 = 0.0; w.fSoft = prm->dSunSoft;
-    w.c0 = w.c1 = -1; w.pLower = n; w.nP = 1;
+    w.c0 = w.c1 = -1; w.pLower = sunP; w.nP = 1;
     const double hs = prm->dSunSoft;
     const int one = 1;
-    CK(cudaMemcpyAsync((PartS *)c->parts.p + n, &ps, sizeof(ps), cudaMemcpyHostToDevice, c->st));
-    CK(cudaMemcpyAsync((NodeW *)c->nodes.p + nn, &w, sizeof(w), cudaMemcpyHostToDevice, c->st));
-    CK(cudaMemcpyAsync((double *)c->hsoft.p + n, &hs, sizeof(hs), cudaMemcpyHostToDevice, c->st));
-    if (!c->hActive.empty()) CK(cudaMemcpyAsync((int *)c->active.p + n, &one, sizeof(one), cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync((PartS *)c->parts.p + sunP, &ps, sizeof(ps), cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync((NodeW *)c->nodes.p + sunN, &w, sizeof(w), cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync((double *)c->hsoft.p + sunP, &hs, sizeof(hs), cudaMemcpyHostToDevice, c->st));
+    if (!c->hActive.empty()) CK(cudaMemcpyAsync((int *)c->active.p + sunP, &one, sizeof(one), cudaMemcpyHostToDevice, c->st));
     CK(cudaStreamSynchronize(c->st)); // (the sources are stack variables)
     Task t;
-    t.node = nn; t.pass = 0; t.ord = 0; t.pad = 0;
+    t.node = sunN; t.pass = 0; t.ord = 0; t.pad = 0;
     gg_params p2 = *prm;
     p2.flags = GG_FLAG_NO_DOWNLOAD;
     p2.bDoSun = 0;
@@ -1873,8 +1894,8 @@ int run_sun(gg_context *c, const gg_params *prm, gg_stats *stats) {
     if (rc) return rc;
     double a3[3];
     int c3[3];
-    CK(cudaMemcpyAsync(a3, (const double *)c->acc.p + 3 * (size_t)n, sizeof(a3), cudaMemcpyDeviceToHost, c->st));
-    CK(cudaMemcpyAsync(c3, (const int *)c->counts.p + 3 * (size_t)nn, sizeof(c3), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(a3, (const double *)c->acc.p + 3 * (size_t)sunP, sizeof(a3), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(c3, (const int *)c->counts.p + 3 * (size_t)sunN, sizeof(c3), cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
     if (stats) {
         stats->aSun[0] = a3[0]; stats->aSun[1] = a3[1]; stats->aSun[2] = a3[2];

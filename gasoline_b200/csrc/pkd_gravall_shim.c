@@ -28,8 +28,14 @@
  * ~30 ms instead of ~1.2 s for 1 M particles.  Without the variable, or for what the device build does not cover
  * (iOpenType other than OPEN_JOSH, a tree over part of the particles, bGravity = 0), the host's own build runs.
  *
- * Scope of this file: one MDL rank per process image of the tree (mdlThreads == 1).  Multi-GPU runs hand each rank
- * the other domains' trees through gg_set_top / gg_set_remote (gasoline_b200/domain.py does it over NCCL).
+ * Several MDL ranks (mdlThreads > 1; pst.c:3248-3303 fans pstGravity out, every leaf calls this function at the same
+ * time): rank r drives GPU r (GG_SHIM_DEVICE overrides; r modulo the device count otherwise).  On its first call every
+ * rank joins the library's communicator -- the 128-byte NCCL id (or, with GG_SHIM_COMM=local / fewer GPUs than ranks,
+ * the address of an in-process group for thread ranks) travels from rank 0 through the host's own MDL: a read-only
+ * cache on CID_PARTICLE, the slot pkdGravAll itself opens at this point (pkd.c:2896-2899), read with mdlAquire.  Per
+ * call: pkd->kdTop (pkdDistribCells, pkd.c:4376; walked as a heap from ROOT like walk.c:342-435 walks it) goes down
+ * through gg_set_top, the ranks' root bounds (the kdTop leaves) to gg_exchange, which replaces pkdRemoteWalk's pulls
+ * (walk.c:181-304) by one push of pruned trees over NCCL / NVLink; then gg_gravity as with one rank.
  * bDoSun (pkd.c:3003-3041, the indirect term of solar-system runs) is passed through: gg_gravity evaluates the dummy
  * sink at the origin after the particles and aSun comes back through gg_stats.
  */
@@ -54,6 +60,7 @@ typedef struct {
     /* pkdBuildBinary on the device: construction by-products per cell, permutation per particle */
     double *fSplit, *fBmax;
     int *iDim, *order;
+    int bJoined; /* this rank has joined the library's communicator (multi-rank runs) */
     PARTICLE *tmp; /* pStore permutation scratch, kept between builds (fresh pages cost more than the copy) */
     size_t capTmp;
     const KDN *builtNodes; /* pkd->kdNodes as our pkdBuildBinary left it (NULL: the device holds no tree of this host) */
@@ -61,6 +68,10 @@ typedef struct {
 } SHIM;
 
 static SHIM g_shim[64]; /* one per MDL rank living in this process (pthread-MDL ranks are threads) */
+
+/* Debug / parity seam for hosts and tests: the library context rank idSelf of this process drives (NULL before its first
+ * force evaluation) -- e.g. for gg_bucket_counts after a pstGravity. */
+gg_context *pkdGravAllContext(int idSelf) { return (idSelf >= 0 && idSelf < 64) ? g_shim[idSelf].ctx : NULL; }
 
 /* ---- a minimal parallel-for over [0, n): the flatten / write-back passes are bandwidth-bound strided copies ---- */
 typedef struct {
@@ -230,6 +241,103 @@ static void reserve(SHIM *s, size_t nNodes, size_t nPart) {
     }
 }
 
+static void die(const char *what);
+
+/* Which GPU this rank drives: GG_SHIM_DEVICE, else rank modulo the number of devices. */
+static int shim_device(PKD pkd) {
+    const char *e = getenv("GG_SHIM_DEVICE");
+    int nDev = 0;
+    if (e && *e) return atoi(e);
+    if (mdlThreads(pkd->mdl) == 1) return -1; /* the current device, as before */
+    if (gg_device_count(&nDev) != GG_OK || nDev < 1) die("gg_device_count");
+    return pkd->idSelf % nDev;
+}
+
+/* First multi-rank call: every rank joins the communicator.  COLLECTIVE over the MDL ranks. */
+typedef struct {
+    char id[GG_UNIQUE_ID_BYTES]; /* NCCL unique id ... */
+    gg_group *grp;               /* ... or the in-process group (thread ranks) */
+    int bLocal;
+} COMMSEED;
+
+static void shim_join(PKD pkd, SHIM *s) {
+    static COMMSEED seed; /* rank 0's copy is the one the others read */
+    COMMSEED mine, *p0;
+    const int nT = mdlThreads(pkd->mdl);
+    memset(&mine, 0, sizeof(mine));
+    if (pkd->idSelf == 0) {
+        const char *e = getenv("GG_SHIM_COMM");
+        int nDev = 0;
+        if (gg_device_count(&nDev) != GG_OK) die("gg_device_count");
+        seed.bLocal = e ? strcmp(e, "local") == 0 : nDev < nT;
+        if (seed.bLocal) {
+            if (gg_group_create(&seed.grp, nT) != GG_OK) die("gg_group_create");
+        } else if (gg_comm_unique_id(seed.id) != GG_OK) die("gg_comm_unique_id");
+    }
+    /* rank 0's seed through the host's MDL (works for every MDL flavour: the cache open is the barrier) */
+    mdlROcache(pkd->mdl, CID_PARTICLE, &seed, sizeof(COMMSEED), 1);
+    p0 = (COMMSEED *)mdlAquire(pkd->mdl, CID_PARTICLE, 0, 0);
+    mine = *p0;
+    mdlRelease(pkd->mdl, CID_PARTICLE, p0);
+    mdlFinishCache(pkd->mdl, CID_PARTICLE);
+    if (mine.bLocal) {
+        if (gg_comm_init_local(s->ctx, mine.grp, pkd->idSelf) != GG_OK) die("gg_comm_init_local");
+    } else if (gg_comm_init(s->ctx, mine.id, pkd->idSelf, nT) != GG_OK) die("gg_comm_init");
+    s->bJoined = 1;
+}
+
+/* pkd->kdTop -> gg_set_top, and the ranks' root bounds for gg_exchange.  kdTop is a heap (ROOT = 1, LOWER(i) = 2i,
+ * UPPER(i) = 2i + 1, pkd.h:77-86) in malloc'ed memory of which only the used cells were written (pkd.c:4385-4391), so it
+ * is walked from ROOT: pLower >= 0 is a leaf = that rank's root cell, else an interior cell with both children. */
+static void shim_top(PKD pkd, SHIM *s, double *bndAll) {
+    const int nT = mdlThreads(pkd->mdl);
+    int nCell = 2, i, j, top, stack[128];
+    static const int kMax = 128;
+    int pLower[128], bUsed[128];
+    double r[3 * 128], fMass[128], fSoft[128], fOpen2[128], *mom;
+    while (nCell < 2 * nT) nCell *= 2; /* master.c:4293: 2^(1 + ceil(log2 nThreads)) */
+    mdlassert(pkd->mdl, nCell <= kMax);
+    mom = (double *)calloc((size_t)GG_NMOM * nCell, sizeof(double));
+    mdlassert(pkd->mdl, mom != NULL);
+    memset(bUsed, 0, sizeof(bUsed));
+    memset(pLower, 0xff, sizeof(pLower));
+    memset(r, 0, sizeof(r)); memset(fMass, 0, sizeof(fMass)); memset(fSoft, 0, sizeof(fSoft)); memset(fOpen2, 0, sizeof(fOpen2));
+    top = 0;
+    stack[top++] = ROOT;
+    while (top > 0) {
+        const KDN *c;
+        const struct pkdCalcCellStruct *q;
+        double *mo;
+        i = stack[--top];
+        mdlassert(pkd->mdl, i < nCell);
+        c = &pkd->kdTop[i];
+        q = &c->mom;
+        bUsed[i] = 1;
+        pLower[i] = c->pLower;
+        for (j = 0; j < 3; ++j) r[3 * i + j] = c->r[j];
+        fMass[i] = c->fMass; fSoft[i] = c->fSoft; fOpen2[i] = c->fOpen2;
+        mo = &mom[(size_t)GG_NMOM * i];
+        mo[0] = q->Qxx; mo[1] = q->Qyy; mo[2] = q->Qzz; mo[3] = q->Qxy; mo[4] = q->Qxz; mo[5] = q->Qyz;
+        mo[6] = q->Oxxx; mo[7] = q->Oxyy; mo[8] = q->Oxxy; mo[9] = q->Oyyy; mo[10] = q->Oxxz; mo[11] = q->Oyyz;
+        mo[12] = q->Oxyz; mo[13] = q->Oxzz; mo[14] = q->Oyzz; mo[15] = q->Ozzz;
+        mo[16] = q->Hxxxx; mo[17] = q->Hxyyy; mo[18] = q->Hxxxy; mo[19] = q->Hyyyy; mo[20] = q->Hxxxz;
+        mo[21] = q->Hyyyz; mo[22] = q->Hxxyy; mo[23] = q->Hxxyz; mo[24] = q->Hxyyz; mo[25] = q->Hxxzz;
+        mo[26] = q->Hxyzz; mo[27] = q->Hxzzz; mo[28] = q->Hyyzz; mo[29] = q->Hyzzz; mo[30] = q->Hzzzz;
+        if (c->pLower >= 0) { /* a rank's root cell */
+            mdlassert(pkd->mdl, c->pLower < nT);
+            for (j = 0; j < 3; ++j) {
+                bndAll[6 * c->pLower + j] = c->bnd.fMin[j];
+                bndAll[6 * c->pLower + 3 + j] = c->bnd.fMax[j];
+            }
+        } else {
+            stack[top++] = UPPER(i);
+            stack[top++] = LOWER(i);
+        }
+    }
+    if (gg_set_top(s->ctx, nCell, pLower, bUsed, r, fMass, fSoft, fOpen2, mom) != GG_OK) die("gg_set_top");
+    free(mom);
+}
+
 void pkdGravAll(PKD pkd, int nReps, int bPeriodic, int iOrder, int bEwald, int iEwOrder, double fEwCut,
                 double fEwhCut, int bComove, double dRhoFac, int bDoSun, double dSunSoft, double *aSun, int *nActive,
                 double *pdPartSum, double *pdCellSum, double *pdSoftSum, CASTAT *pcs, double *pdFlop) {
@@ -242,10 +350,10 @@ void pkdGravAll(PKD pkd, int nReps, int bPeriodic, int iOrder, int bEwald, int i
     PASS pass;
     int j, bResident;
 
-    mdlassert(pkd->mdl, mdlThreads(pkd->mdl) == 1);
     mdlassert(pkd->mdl, pkd->idSelf >= 0 && pkd->idSelf < 64);
     s = &g_shim[pkd->idSelf];
-    if (!s->ctx && gg_create(&s->ctx, -1) != GG_OK) die("gg_create");
+    if (!s->ctx && gg_create(&s->ctx, shim_device(pkd)) != GG_OK) die("gg_create");
+    if (mdlThreads(pkd->mdl) > 1 && !s->bJoined) shim_join(pkd, s);
     reserve(s, (size_t)nNodes, (size_t)n);
 
     /* the timers the caller reads back (pst.c:3316-3324) */
@@ -296,6 +404,12 @@ void pkdGravAll(PKD pkd, int nReps, int bPeriodic, int iOrder, int bEwald, int i
     prm.fEwCut = fEwCut; prm.fEwhCut = fEwhCut; prm.bComove = bComove; prm.dRhoFac = dRhoFac;
     for (j = 0; j < 3; ++j) prm.fPeriod[j] = pkd->fPeriod[j];
     prm.bDoSun = bDoSun; prm.dSunSoft = dSunSoft;
+    if (mdlThreads(pkd->mdl) > 1) {
+        /* the host's top tree and, in place of pkdRemoteWalk's pulls, one collective push of pruned trees */
+        double bndAll[6 * 64];
+        shim_top(pkd, s, bndAll);
+        if (gg_exchange(s->ctx, &prm, bndAll, NULL) != GG_OK) die("gg_exchange");
+    }
     prm.accumulate = 0; /* this call's contribution, delivered zero-copy into the pinned arrays; merged below */
     if (gg_gravity(s->ctx, &prm, s->a, s->pot, s->dt, s->w, &st) != GG_OK) die("gg_gravity");
     parallel_for((size_t)n, write_back, &pass);
@@ -369,7 +483,7 @@ void pkdBuildBinary(PKD pkd, int nBucket, int iOpenType, double dCrit, int iOrde
     double t0 = 0.0;
 
     if (!e || !atoi(e) || iOpenType != OPEN_JOSH || !bGravity || pkd->nLocal < 1 || nBucket > GG_MAX_BUCKET ||
-        (bTreeActiveOnly && pkd->nTreeActive != pkd->nLocal) || mdlThreads(pkd->mdl) != 1) {
+        (bTreeActiveOnly && pkd->nTreeActive != pkd->nLocal)) {
         if (pkd->idSelf >= 0 && pkd->idSelf < 64) g_shim[pkd->idSelf].builtNodes = NULL;
         pkdBuildBinary_cpu(pkd, nBucket, iOpenType, dCrit, iOrder, bTreeActiveOnly, bGravity, pRoot);
         return;
@@ -384,7 +498,7 @@ void pkdBuildBinary(PKD pkd, int nBucket, int iOpenType, double dCrit, int iOrde
     n = pkd->nLocal;
     mdlassert(pkd->mdl, pkd->idSelf >= 0 && pkd->idSelf < 64);
     s = &g_shim[pkd->idSelf];
-    if (!s->ctx && gg_create(&s->ctx, -1) != GG_OK) die("gg_create");
+    if (!s->ctx && gg_create(&s->ctx, shim_device(pkd)) != GG_OK) die("gg_create");
     reserve(s, 0, (size_t)n);
     pass.pkd = pkd; pass.s = s; pass.bMom = 1; pass.iOrder = iOrder; pass.tmp = NULL;
     parallel_for((size_t)n, flatten_particles, &pass);

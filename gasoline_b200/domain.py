@@ -311,6 +311,8 @@ class Domain:
             self.rebuild()
         else:
             _build(host, nBucket, theta, iOrder)
+            # this rank's OWN pkdCalcRoot expansion: attach() later replaces host.ilcnRoot by the distributed one
+            self.localRoot = np.array(host.ilcnRoot, dtype=np.float64, copy=True)
         self.kdTop = None
         self.ilcnRoot = None
 
@@ -327,7 +329,7 @@ class Domain:
                                    s["root"]]).astype(np.float64)
         t, r = self.host.tree, self.host.tree.iRoot
         return np.concatenate([t.bnd[r], t.r[r], [t.fMass[r], t.fSoft[r], t.fOpen2[r]], t.mom[r],
-                               self.host.ilcnRoot]).astype(np.float64)
+                               self.localRoot]).astype(np.float64)
 
     # -- steps 2 + 3 (local part)
     def ancestor_moments(self, summaries: np.ndarray) -> np.ndarray:

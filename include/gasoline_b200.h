@@ -112,6 +112,8 @@ typedef struct gg_stats {
 const char *gg_last_error(void);
 int gg_version(void);
 
+/* Number of CUDA devices this process sees (a multi-rank host maps rank r to device r modulo this). */
+int gg_device_count(int *pn);
 /* device < 0: use the current device.  Fails (GG_ERR_CUDA) when no CUDA device is usable. */
 int gg_create(gg_context **pctx, int device);
 void gg_destroy(gg_context *ctx);

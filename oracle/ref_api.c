@@ -22,6 +22,10 @@
 #include "grav.h"
 #include "ewald.h"
 #include "opentype.h"
+#ifdef REF_GPU_HOST
+#include "gasoline_b200.h"
+gg_context *pkdGravAllContext(int idSelf); /* gasoline_b200/csrc/pkd_gravall_shim.c */
+#endif
 
 typedef struct {
     MDL mdl;
@@ -106,6 +110,25 @@ void __wrap_pkdGravAll(PKD pkd, int nReps, int bPeriodic, int iOrder, int bEwald
                        int *nActive, double *pdPartSum, double *pdCellSum, double *pdSoftSum, CASTAT *pcs, double *pdFlop) {
     __real_pkdGravAll(pkd, nReps, bPeriodic, iOrder, bEwald, iEwOrder, fEwCut, fEwhCut, bComove, dRhoFac, bDoSun,
                       dSunSoft, aSun, nActive, pdPartSum, pdCellSum, pdSoftSum, pcs, pdFlop);
+#ifdef REF_GPU_HOST
+    /* the drop-in host: pkdGravAll is the product's shim, which never calls pkdBucketWalk -- the per-bucket records of
+     * the dump come from the library's counters (gg_bucket_counts), in the same record format */
+    if (getenv("REF_DUMP") && pkd->idSelf < REF_MAX_RANKS && !g_dump[pkd->idSelf]) {
+        gg_context *ctx = pkdGravAllContext(pkd->idSelf);
+        int *cnt = malloc((size_t)pkd->nNodes * 3 * sizeof(int)), i;
+        assert(ctx && cnt);
+        dump_header(pkd);
+        if (gg_bucket_counts(ctx, cnt) != 0) abort();
+        for (i = 0; i < pkd->nNodes; ++i) {
+            int rec[6];
+            if (pkd->kdNodes[i].iLower != -1 || cnt[3 * i] < 0) continue;
+            rec[0] = i; rec[1] = pkd->kdNodes[i].pLower; rec[2] = pkd->kdNodes[i].pUpper;
+            rec[3] = cnt[3 * i]; rec[4] = cnt[3 * i + 1]; rec[5] = cnt[3 * i + 2];
+            fwrite(rec, sizeof(int), 6, g_dump[pkd->idSelf]);
+        }
+        free(cnt);
+    }
+#endif
     if (getenv("REF_DUMP") && pkd->idSelf < REF_MAX_RANKS && g_dump[pkd->idSelf]) {
         FILE *f = g_dump[pkd->idSelf];
         int rec[6] = {-1, 0, 0, 0, 0, 0}, i;

@@ -96,3 +96,37 @@ def test_comove_background_term(gpu_lib):
     sun_only = pkd.pkdGravAll(GravityParams(nReps=0, bPeriodic=0, bEwald=0, bDoSun=1, dSunSoft=0.01))
     assert np.array_equal(both["aSun"], sun_only["aSun"])
     pkd.close()
+
+
+def test_sun_with_remote_domains(gpu_lib):
+    """bDoSun on a rank that also holds remote domains (pst.c:3258-3277 hands it to the one rank whose domain contains the
+    origin; that rank's dummy sink walks the top tree, its own tree and the remote trees).  With an opening angle so small
+    that every cell is opened the result does not depend on how the particles are split into trees: the dummy's list is
+    all N particles and aSun equals the one-domain value to rounding; at theta = 0.7 it agrees within the tree error."""
+    from gasoline_b200 import domain, ics
+    p = ics.plummer(4000, seed=21)
+    soft = 0.01
+    one = PKD()
+    one.pkdLoadParticles(p.x, p.y, p.z, p.m, p.h)
+    for theta, tol in ((0.02, 1e-9), (0.7, 2e-3)):
+        one.pkdBuildBinary(8, theta, 4)
+        ref = one.pkdGravAll(GravityParams(nReps=0, bPeriodic=0, bEwald=0, bDoSun=1, dSunSoft=soft))
+        parts = domain.orb_decompose(p.x, p.y, p.z, 3)
+        doms = [domain.Domain(r, 3, p.x[ix], p.y[ix], p.z[ix], p.m[ix], p.h[ix], p.period, theta, device=0)
+                for r, ix in enumerate(parts)]
+        g = GravityParams(nReps=0, bPeriodic=0, bEwald=0)
+        domain.run_in_process(doms, let=g)
+        for r, d in enumerate(doms):
+            plain = d.pkd.pkdGravAll(g)
+            out = d.pkd.pkdGravAll(GravityParams(nReps=0, bPeriodic=0, bEwald=0, bDoSun=1, dSunSoft=soft))
+            err = np.linalg.norm(out["aSun"] - ref["aSun"]) / np.linalg.norm(ref["aSun"])
+            print(f"sun with remote domains, theta {theta}, rank {r}: aSun rel diff to the one-domain run {err:.2e}, "
+                  f"lists {out['nSunPart']}/{out['nSunCellSoft']}/{out['nSunCellNewt']}")
+            assert err <= tol
+            if theta < 0.1:
+                assert out["nSunPart"] == p.n and out["nSunCellNewt"] == 0
+            for k in ("acc", "pot", "dtGrav", "fWeight"):  # the particles' own results are untouched by the extra pass
+                assert np.array_equal(out[k], plain[k])
+        for d in doms:
+            d.pkd.close()
+    one.close()
