@@ -581,6 +581,7 @@ int gg_create(gg_context **pctx, int device) {
     CK(cudaEventCreateWithFlags(&c->evPacked, cudaEventDisableTiming));
     for (auto &ev : c->ev) CK(cudaEventCreate(&ev));
     for (auto &ev : c->evx) CK(cudaEventCreate(&ev));
+    for (auto &ev : c->evt) CK(cudaEventCreate(&ev));
     *pctx = c;
     return GG_OK;
 }
@@ -605,6 +606,8 @@ void gg_destroy(gg_context *c) {
     if (c->letrecv.p) cudaFree(c->letrecv.p);
     if (c->commscratch.p) cudaFree(c->commscratch.p);
     for (auto &ev : c->evx)
+        if (ev) cudaEventDestroy(ev);
+    for (auto &ev : c->evt)
         if (ev) cudaEventDestroy(ev);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->builder) gg_builder_free(c->builder);
@@ -2051,6 +2054,24 @@ int gg_measure_fp32_peak(gg_context *c, double *pTflops, double *pMs) {
     }
     *pTflops = best;
     if (pMs) *pMs = bestMs;
+    return GG_OK;
+}
+
+int gg_timer_start(gg_context *c) {
+    if (!c) return gg_fail(GG_ERR_ARG, "gg_timer_start: null");
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventRecord(c->evt[0], c->st));
+    return GG_OK;
+}
+
+int gg_timer_stop(gg_context *c, double *pMs) {
+    if (!c || !pMs) return gg_fail(GG_ERR_ARG, "gg_timer_stop: null");
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventRecord(c->evt[1], c->st));
+    CK(cudaEventSynchronize(c->evt[1]));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, c->evt[0], c->evt[1]));
+    *pMs = ms;
     return GG_OK;
 }
 

@@ -67,6 +67,7 @@ struct gg_context {
     bool haveRootBnd = false;
     DevBuf letrecv, commscratch;
     cudaEvent_t evx[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t evt[2] = {nullptr, nullptr}; // gg_timer_start / gg_timer_stop
 };
 
 // error reporting: formats into the calling thread's message buffer (gg_last_error), prints it, returns code

@@ -136,6 +136,8 @@ def load_library(path: str | None = None):
     L.gg_exchange.argtypes = [C.c_void_p, C.POINTER(gg_params), _dp, C.POINTER(gg_exchange_stats)]
     L.gg_measure_fp32_peak.argtypes = [C.c_void_p, _dp, _dp]
     L.gg_flush_l2.argtypes = [C.c_void_p]
+    L.gg_timer_start.argtypes = [C.c_void_p]
+    L.gg_timer_stop.argtypes = [C.c_void_p, _dp]
     _lib = L
     return L
 
@@ -665,6 +667,16 @@ class PKD:
 
     def flush_l2(self):
         _check(self._L.gg_flush_l2(self._ctx), "gg_flush_l2")
+
+    def timer_start(self):
+        """CUDA event on the library's stream (gg_timer_start)."""
+        _check(self._L.gg_timer_start(self._ctx), "gg_timer_start")
+
+    def timer_stop(self) -> float:
+        """Milliseconds of device time since timer_start, host-induced gaps included (gg_timer_stop)."""
+        ms = C.c_double()
+        _check(self._L.gg_timer_stop(self._ctx, C.byref(ms)), "gg_timer_stop")
+        return ms.value
 
     def pkdBucketCounts(self) -> np.ndarray:
         """(nPart, nCellSoft, nCellNewt) per tree node after pkdGravAll -- what pkdBucketWalk leaves in

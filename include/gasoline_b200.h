@@ -249,6 +249,10 @@ int gg_device_results(gg_context *ctx, void **a, void **fPot, void **dtGrav, voi
  * load (dependent-FFMA microbenchmark on all SMs, TFLOP/s; kernel duration in ms) -- the denominator of the FP32
  * roofline -- and an L2 flush (writes 384 MB) to put between timed iterations. */
 int gg_measure_fp32_peak(gg_context *ctx, double *pTflops, double *pMs);
+/* CUDA events on the stream the library launches on: the device time of everything queued between the two calls (several
+ * ABI calls, e.g. gg_set_top + gg_exchange + gg_gravity), host-induced gaps included. */
+int gg_timer_start(gg_context *ctx);
+int gg_timer_stop(gg_context *ctx, double *pMs);
 int gg_flush_l2(gg_context *ctx);
 
 /* Pinned host memory for the arrays handed to gg_set_local / gg_gravity. */

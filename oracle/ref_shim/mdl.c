@@ -159,13 +159,21 @@ void mdlHandler(MDL mdl) {
         mdl->bReq = 0;
         pthread_cond_broadcast(&s->cv);
         pthread_mutex_unlock(&s->mux);
-        if (sid == SRV_STOP) {
+        if (sid == SRV_STOP) { /* msrFinish waits for a reply to the stop request too (master.c:3472-3473) */
             free(in);
+            r = mdl->pmdl[from];
+            pthread_mutex_lock(&s->mux);
+            while (r->pbReply[mdl->idSelf]) pthread_cond_wait(&s->cv, &s->mux);
+            r->ppszReply[mdl->idSelf] = NULL;
+            r->pnReplyOut[mdl->idSelf] = 0;
+            r->pbReply[mdl->idSelf] = 1;
+            pthread_cond_broadcast(&s->cv);
+            pthread_mutex_unlock(&s->mux);
             break;
         }
         assert(sid < mdl->nMaxServices && mdl->psrv[sid].fcnService);
         assert(nIn <= mdl->psrv[sid].nInBytes);
-        out = malloc(mdl->psrv[sid].nOutBytes > 0 ? mdl->psrv[sid].nOutBytes : 1);
+        out = calloc(mdl->psrv[sid].nOutBytes > 0 ? mdl->psrv[sid].nOutBytes : 1, 1); /* (services that fill nothing reply zeros) */
         (*mdl->psrv[sid].fcnService)(mdl->psrv[sid].p1, in, nIn, out, &nOut);
         assert(nOut <= mdl->psrv[sid].nOutBytes);
         free(in);
@@ -181,14 +189,20 @@ void mdlHandler(MDL mdl) {
 }
 
 /*
- * Bilateral transfer (pkd.c:1497,1522): outgoing bytes sit at the TOP of vBuf, incoming bytes land at
- * the bottom; each side accepts at most its free space nBufBytes-nOutBytes.
+ * Bilateral transfer (pkd.c:1497,1522): outgoing bytes sit at the TOP of vBuf, incoming bytes land at the bottom.
+ * A real MDL moves the two directions piece by piece, so the space an outgoing piece vacates takes incoming data: the
+ * exchange is complete whenever each side's WHOLE buffer can hold what the other sends (pkdSwapAll, pkd.c:1504-1527,
+ * relies on it: its buffer is full of outgoing particles and it asserts completeness).  Otherwise each side accepts
+ * what fits its free space and the caller comes back for the rest (pkdSwapRejects).  Both directions go through a
+ * temporary copy, so neither side writes its buffer before the partner has read it.
  */
 int mdlSwap(MDL mdl, int id, size_t nBufBytes, void *vBuf, size_t nOutBytes, size_t *pnSndBytes,
             size_t *pnRcvBytes) {
     struct mdlShared *s = mdl->shared;
     MDL o = mdl->pmdl[id];
-    size_t nIn, nSnd, nRoomOther, nOtherOut, nOtherDone0;
+    size_t nIn, nSnd, nOtherOut, nOtherBuf, nOtherDone0;
+    char *tmp;
+    int bFull;
     TRACE("[%d] swap with %d buf %zu out %zu\n", mdl->idSelf, id, nBufBytes, nOutBytes);
     pthread_mutex_lock(&s->mux);
     mdl->pSwapBuf = vBuf;
@@ -201,17 +215,30 @@ int mdlSwap(MDL mdl, int id, size_t nBufBytes, void *vBuf, size_t nOutBytes, siz
     while (!(o->iSwapState >= 1 && o->idSwapWith == mdl->idSelf)) pthread_cond_wait(&s->cv, &s->mux);
     nOtherDone0 = o->nSwapTaken; /* reused as a monotonic "swaps completed" counter */
     pthread_mutex_unlock(&s->mux);
-    /* both published: pull what fits from the partner's outgoing region (its top) into my bottom */
     nOtherOut = o->nSwapOut;
-    nIn = nOtherOut;
-    if (nIn > nBufBytes - nOutBytes) nIn = nBufBytes - nOutBytes;
-    memcpy(vBuf, o->pSwapBuf + (o->nSwapBuf - o->nSwapOut), nIn);
-    nRoomOther = o->nSwapBuf - o->nSwapOut;
-    nSnd = nOutBytes < nRoomOther ? nOutBytes : nRoomOther;
+    nOtherBuf = o->nSwapBuf;
+    bFull = nOtherOut <= nBufBytes && nOutBytes <= nOtherBuf; /* both sides evaluate the same condition */
+    if (bFull) {
+        nIn = nOtherOut;
+        nSnd = nOutBytes;
+    } else {
+        nIn = nOtherOut < nBufBytes - nOutBytes ? nOtherOut : nBufBytes - nOutBytes;
+        nSnd = nOutBytes < nOtherBuf - nOtherOut ? nOutBytes : nOtherBuf - nOtherOut;
+    }
+    /* pull the FIRST nIn bytes of the partner's outgoing region (its top) into a temporary */
+    tmp = malloc(nIn ? nIn : 1);
+    assert(tmp != NULL);
+    memcpy(tmp, o->pSwapBuf + (nOtherBuf - nOtherOut), nIn);
     pthread_mutex_lock(&s->mux);
-    mdl->iSwapState = 2; /* copied */
+    mdl->iSwapState = 2; /* copied: the partner may now overwrite its buffer */
     pthread_cond_broadcast(&s->cv);
     while (!(o->iSwapState == 2 || o->nSwapTaken != nOtherDone0)) pthread_cond_wait(&s->cv, &s->mux);
+    pthread_mutex_unlock(&s->mux);
+    /* the partner has read what it takes from us -- the FIRST nSnd bytes of our outgoing region, so what it did not
+     * take is already at the very top, where pkdSwapRejects expects the remaining rejects; incoming bytes go to the bottom */
+    memcpy(vBuf, tmp, nIn);
+    free(tmp);
+    pthread_mutex_lock(&s->mux);
     mdl->iSwapState = 0;
     mdl->idSwapWith = -1;
     mdl->nSwapTaken += 1;
