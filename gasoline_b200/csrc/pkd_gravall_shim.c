@@ -365,7 +365,8 @@ void pkdGravAll(PKD pkd, int nReps, int bPeriodic, int iOrder, int bEwald, int i
     pass.pkd = pkd; pass.s = s;
     pass.bMom = getenv("GG_SHIM_HOST_MOMENTS") != NULL && atoi(getenv("GG_SHIM_HOST_MOMENTS")) != 0;
     bResident = 0;
-    if (s->builtNodes && s->builtNodes == pkd->kdNodes && s->builtN == nNodes && !pass.bMom) {
+    if (s->builtNodes && s->builtNodes == pkd->kdNodes && s->builtN == nNodes && !pass.bMom &&
+        !(getenv("GG_SHIM_FORCE_UPLOAD") && atoi(getenv("GG_SHIM_FORCE_UPLOAD")))) { /* (measurement aid: always flatten) */
         /* kdNodes is the tree our pkdBuildBinary built and the device still holds it (same array, same size, root cell
          * equal bit for bit): nothing but the ACTIVE flags -- which msrActiveRung may have changed since -- goes up */
         double r[3], fMass;
