@@ -1643,6 +1643,10 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
         ea.trQ3[1] = 0.5 * (R[12] + R[13] + R[18]); // Qy = xxy + yyy + yzz
         ea.trQ3[2] = 0.5 * (R[14] + R[15] + R[19]); // Qz = xxz + yyz + zzz
         ea.trQ2 = 0.5 * (R[4] + R[5] + R[9]);
+        for (int k = 0; k < 10; ++k) ea.O32[k] = (float)R[10 + k];
+        for (int k = 0; k < 15; ++k) ea.H32[k] = (float)R[20 + k];
+        for (int k = 0; k < 7; ++k) ea.trQ4f[k] = (float)ea.trQ4[k];
+        for (int k = 0; k < 3; ++k) ea.trQ3f[k] = (float)ea.trQ3[k];
         ea.ewt = (const double *)c->ewt.p;
         ea.nEwh = nEwh;
         ea.nReps = prm->nReps;
@@ -1683,9 +1687,9 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
         nBuckets = c->nBucketsLocal;
     }
     const int nWalkGroups = (nBuckets + GG_WALK_GB - 1) / GG_WALK_GB;
-    if ((rc = gg_ensure(c, c->ghead, (size_t)(nWalkGroups + 1) * 6 * sizeof(int)))) return rc;
-    if ((rc = gg_ensure(c, c->gcnt, (size_t)(nWalkGroups + 1) * 6 * sizeof(int)))) return rc;
-    if ((rc = gg_ensure(c, c->bcnt, (size_t)(nBuckets + 1) * 3 * sizeof(int)))) return rc;
+    if ((rc = gg_ensure(c, c->ghead, (size_t)(nWalkGroups + 1) * 2 * GG_NLIST * sizeof(int)))) return rc;
+    if ((rc = gg_ensure(c, c->gcnt, (size_t)(nWalkGroups + 1) * 2 * GG_NLIST * sizeof(int)))) return rc;
+    if ((rc = gg_ensure(c, c->bcnt, (size_t)(nBuckets + 1) * GG_NLIST * sizeof(int)))) return rc;
     if ((rc = gg_ensure(c, c->btot, (size_t)(nBuckets + 1) * sizeof(long long)))) return rc;
     if ((rc = gg_ensure(c, c->boff64, (size_t)(nBuckets + 1) * sizeof(long long)))) return rc;
     c->nTasks = nTasks;
@@ -1724,6 +1728,7 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
     ta.maxBucket = c->maxBucket;
     ta.walkOnly = walkOnly ? 1 : 0;
     ta.mono64 = prm->bPeriodic ? 1 : 0;
+    ta.bigFrac = prm->bPeriodic ? GG_BIG_FRAC : 0.0;
     ta.sunNode = c->sunMode ? sunN : -1;
     ta.sunBox = 1e-14; // dTinyBox, pkd.c:3004
     ta.acc = (double *)c->acc.p;

@@ -21,7 +21,7 @@
 #define GG_MIN_CTAS 5        // resident CTAs per SM k_eval is compiled for (44 KB shared memory each; register cap 102)
 #endif
 #ifndef GG_MONO_MIN_CTAS
-#define GG_MONO_MIN_CTAS (GG_MIN_CTAS - 1) // k_eval<.,true> (periodic boxes, FP64 monopoles): 128 registers
+#define GG_MONO_MIN_CTAS GG_MIN_CTAS       // k_eval<.,true> (periodic boxes): the FP64 monopoles are confined to the big-cell loop
 #endif
 #ifndef GG_CELL_UNROLL
 #define GG_CELL_UNROLL 1     // unroll factor of k_eval's (sink, cell) loop
@@ -41,6 +41,10 @@ typedef unsigned char gg_mask_t;  // bucket mask of a frontier item / of a maske
 typedef unsigned short gg_mask_t;
 #endif
 #define GG_MAX_SINKS 8      // sinks evaluated per warp pass (accumulators live in registers)
+#define GG_NLIST 4          // list types: 0 leaves (opened buckets), 1 softened cells, 2 Newtonian cells, 3 big Newtonian cells
+#ifndef GG_BIG_FRAC
+#define GG_BIG_FRAC (1.0 / 64.0) // periodic boxes: cells holding >= this share of the whole mass get FP64 monopoles (eval_cells)
+#endif
 #define GG_STACK_CAP 512    // walk frontier entries per warp
 #define GG_STACK_DFS_MARGIN 128
 #define GG_MAX_IMAGES 343    // (2 nReps + 1)^3 images of the tree walk, nReps <= 3
@@ -105,10 +109,10 @@ struct TreeKernelArgs {
     int capBlocks;
     int *poolCursor;         // blocks handed out (may exceed capBlocks: the host then grows the pool and reruns)
     gg_mask_t *poolMask;     // [capBlocks][32] masked chains: which buckets of the walk group the entry belongs to
-    int *groupHead;          // [nWalkGroups][3 list types][2]: chain shared by every bucket of the group, masked chain
-    int *groupCnt;           // [nWalkGroups][3][2] entries in each chain
+    int *groupHead;          // [nWalkGroups][GG_NLIST list types][2]: chain shared by every bucket of the group, masked chain
+    int *groupCnt;           // [nWalkGroups][GG_NLIST][2] entries in each chain
     // per-bucket contiguous lists (k_scatter output, k_eval input), indexed by bucket ordinal
-    int *bucketCnt;          // [nBuckets][3] entries of the bucket's leaf / softened-cell / Newtonian-cell list
+    int *bucketCnt;          // [nBuckets][GG_NLIST] entries of the bucket's leaf / softened-cell / Newtonian / big Newtonian list
     long long *bucketTot;    // [nBuckets + 1] k_walk: entries of the bucket over the three lists
     const long long *bucketOff; // [nBuckets + 1] exclusive scan of bucketTot: where the bucket's lists start
     unsigned *lists;         // [bucketOff[nBuckets]]: per bucket its Newtonian cells, softened cells, leaves
@@ -118,7 +122,8 @@ struct TreeKernelArgs {
     int iOrder;
     int maxBucket;           // largest particle count of any bucket (sizes the particle buffer)
     int walkOnly;
-    int mono64;              // k_eval: cell monopoles in FP64 (periodic boxes, see eval_cells)
+    int mono64;              // k_eval: the big-cell list exists and its monopoles are evaluated in FP64 (periodic boxes)
+    double bigFrac;          // k_walk: a Newtonian cell is "big" when fMass >= bigFrac x the root cell's mass; <= 0: never
     int sunNode;             // bDoSun pass (pkd.c:3003-3041): the dummy sink bucket's node, whose box is +-sunBox; else -1
     double sunBox;
     // outputs (local particles, tree order)
@@ -140,6 +145,9 @@ struct EwaldKernelArgs {
     double trQ4[7];          // Qxx,Qxy,Qxz,Qyy,Qyz,Qzz, Qtr of the hexadecapole traces (meval.h:36-42)
     double trQ3[3];          // Qx,Qy,Qz (meval.h:55-57)
     double trQ2;             // 0.5*(xx+yy+zz) (meval.h:68)
+    // FP32 copies of the l = 3, 4 moments and their traces: those two orders of MEVAL are evaluated on the FP32 pipe
+    // (their terms are <~ 1e-2 of the monopole term; 1e-7 of them is far below the tolerance), see gg_ewald.cu
+    float O32[10], H32[15], trQ4f[7], trQ3f[3];
     const double *ewt;       // [nEwh][5]
     int nEwh;
     int nReps, nEwReps, iOrder;

@@ -295,7 +295,7 @@ struct WalkSmem {
     double box[GG_WALK_GB][6];  // sink boxes (active particles) of the group's buckets
     double gbox[6];             // ... and the box around all of them
     double fSoftMax[GG_WALK_GB];
-    int head[3][2], fill[3][2], cnt[3][2]; // chain state per list type (0 leaves, 1 soft, 2 Newtonian) x (shared, masked)
+    int head[GG_NLIST][2], fill[GG_NLIST][2], cnt[GG_NLIST][2]; // chain state per list type (0 leaves, 1 soft, 2 Newtonian, 3 big Newtonian) x (shared, masked)
     int own[GG_WALK_GB];        // particles of the bucket itself met in the home image (walk.c:93)
     int bnode[GG_WALK_GB];
 };
@@ -434,6 +434,8 @@ __global__ void __launch_bounds__(GG_WALK_WARPS * 32, GG_WALK_MIN_CTAS) k_walk(c
     const unsigned imgMask = (1u << A.imgBits) - 1u;
     Slab slab{0, GG_SLAB_BLOCKS};
     const int nGroups = (A.nBuckets + GG_WALK_GB - 1) / GG_WALK_GB;
+    // "big" = at least bigFrac of everything there is (the mass of the walk's root cell); bigFrac <= 0: no such class
+    const double bigMass = A.bigFrac > 0.0 ? __dmul_rn(A.bigFrac, __ldg(&A.nodes[A.rootNode].fMass)) : 1.7976931348623157e308;
 
     for (;;) {
         int g = 0;
@@ -500,10 +502,10 @@ __global__ void __launch_bounds__(GG_WALK_WARPS * 32, GG_WALK_MIN_CTAS) k_walk(c
                 if (lane < 6) W.gbox[lane] = v;
             }
         }
-        if (lane < 6) {
+        if (lane < 2 * GG_NLIST) {
             (&W.head[0][0])[lane] = -1; (&W.fill[0][0])[lane] = 0; (&W.cnt[0][0])[lane] = 0;
         }
-        int myP = 0, myS = 0, myN = 0, myL = 0, sharedP = 0, unused = 0; // lane b: masked entries of bucket b
+        int myP = 0, myS = 0, myN = 0, myB = 0, myL = 0, sharedP = 0, unused = 0; // lane b: masked entries of bucket b
         int nStack = A.nImages;
         for (int i = lane; i < A.nImages; i += 32) {
             W.stack[i] = ((unsigned)A.rootNode << A.imgBits) | (unsigned)i;
@@ -534,14 +536,14 @@ __global__ void __launch_bounds__(GG_WALK_WARPS * 32, GG_WALK_MIN_CTAS) k_walk(c
             }
             __syncwarp();
             // ---- decide, per bucket of the item's mask: open / Newtonian cell / softened cell
-            unsigned mOpen = 0, mSoft = 0, mNewt = 0, amb = 0;
+            unsigned mOpen = 0, mSoft = 0, mNewt = 0, mBig = 0, amb = 0;
             int img = 0, np = 0, c0 = -1, c1 = -1, nPnode = 0;
-            double x = 0.0, y = 0.0, z = 0.0, fOpen2 = 0.0, fSoftC = 0.0;
+            double x = 0.0, y = 0.0, z = 0.0, fOpen2 = 0.0, fSoftC = 0.0, fMassC = 0.0;
             if (node >= 0) {
                 img = (int)(item & imgMask);
                 const NodeW nd = load_node_smem(&W.nstage[lane * NSTRIDE]);
                 x = nd.rx + s_off[3 * img]; y = nd.ry + s_off[3 * img + 1]; z = nd.rz + s_off[3 * img + 2];
-                fOpen2 = nd.fOpen2; fSoftC = nd.fSoft; c0 = nd.c0; c1 = nd.c1; nPnode = nd.nP;
+                fOpen2 = nd.fOpen2; fSoftC = nd.fSoft; fMassC = nd.fMass; c0 = nd.c0; c1 = nd.c1; nPnode = nd.nP;
                 if (nd.nP < 4) mOpen = mask; // walk.c:81 (pUpper - pLower < 3)
                 else if (near_dist2(W.gbox, x, y, z) <= fOpen2) { // else: no bucket inside the group box opens it
                     if (far_dist2(W.gbox, x, y, z) <= fOpen2) mOpen = mask; // every bucket inside the group box does
@@ -594,6 +596,9 @@ __global__ void __launch_bounds__(GG_WALK_WARPS * 32, GG_WALK_MIN_CTAS) k_walk(c
                             if (!(twoh2 < fOpen2) && intersect_np(W.box[b], twoh2, x, y, z)) mSoft |= 1u << b;
                         }
                     mNewt = mAcc & ~mSoft;
+                    // periodic boxes: the few massive far cells go to a list of their own, whose monopoles k_eval
+                    // evaluates in FP64 (see eval_cells); same cell = same class for every bucket of the group
+                    if (fMassC >= bigMass) { mBig = mNewt; mNewt = 0; }
                 }
                 if (mOpen && c0 < 0) { // an opened bucket: all its particles are sources (walk.c:93-114)
                     np = nPnode;
@@ -618,6 +623,7 @@ __global__ void __launch_bounds__(GG_WALK_WARPS * 32, GG_WALK_MIN_CTAS) k_walk(c
             }
             nStack += 2 * __popc(mPush);
             distribute(A, W, 2, mNewt, all, nB, item, 0, lane, lt, slab, myN, unused, unused);
+            distribute(A, W, 3, mBig, all, nB, item, 0, lane, lt, slab, myB, unused, unused);
             distribute(A, W, 1, mSoft, all, nB, item, 0, lane, lt, slab, myS, unused, unused);
             distribute(A, W, 0, np > 0 ? mOpen : 0u, all, nB, item, np, lane, lt, slab, myP, sharedP, myL);
             __syncwarp();
@@ -627,14 +633,14 @@ __global__ void __launch_bounds__(GG_WALK_WARPS * 32, GG_WALK_MIN_CTAS) k_walk(c
             int *c = &A.counts[3 * W.bnode[lane]];
             c[0] = sharedP + myP - W.own[lane];
             c[1] = W.cnt[1][0] + myS;
-            c[2] = W.cnt[2][0] + myN;
-            int *e = &A.bucketCnt[3 * (b0 + lane)]; // list ENTRIES (a leaf entry stands for all particles of a bucket)
-            e[0] = W.cnt[0][0] + myL; e[1] = c[1]; e[2] = c[2];
-            A.bucketTot[b0 + lane] = (long long)e[0] + e[1] + e[2];
+            c[2] = W.cnt[2][0] + myN + W.cnt[3][0] + myB; // pkd->nCellNewt: ordinary + big
+            int *e = &A.bucketCnt[GG_NLIST * (b0 + lane)]; // list ENTRIES (a leaf entry stands for all particles of a bucket)
+            e[0] = W.cnt[0][0] + myL; e[1] = c[1]; e[2] = W.cnt[2][0] + myN; e[3] = W.cnt[3][0] + myB;
+            A.bucketTot[b0 + lane] = (long long)e[0] + e[1] + e[2] + e[3];
         }
-        if (lane < 6) {
-            A.groupHead[6 * g + lane] = (&W.head[0][0])[lane];
-            A.groupCnt[6 * g + lane] = (&W.cnt[0][0])[lane];
+        if (lane < 2 * GG_NLIST) {
+            A.groupHead[2 * GG_NLIST * g + lane] = (&W.head[0][0])[lane];
+            A.groupCnt[2 * GG_NLIST * g + lane] = (&W.cnt[0][0])[lane];
         }
         __syncwarp();
     }
@@ -643,26 +649,26 @@ __global__ void __launch_bounds__(GG_WALK_WARPS * 32, GG_WALK_MIN_CTAS) k_walk(c
 // ------------------------------------------------------------------------------------------------ k_scatter
 // One warp per (walk group, list type, chain): copy the chain into the contiguous per-bucket lists k_eval streams
 // through (shared entries to every bucket of the group, masked entries to the buckets of their mask).  Bucket b's
-// lists start at bucketOff[b]: Newtonian cells, then softened cells, then leaves; within a type the group's shared
-// entries come first, so all six warps of a group know where to write without talking to each other.
+// lists start at bucketOff[b]: big Newtonian cells, Newtonian cells, softened cells, leaves; within a type the group's
+// shared entries come first, so all eight warps of a group know where to write without talking to each other.
 __global__ void __launch_bounds__(256) k_scatter(const TreeKernelArgs A) {
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const int nGroups = (A.nBuckets + GG_WALK_GB - 1) / GG_WALK_GB;
     const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int g = w / 6, sub = w - 6 * g, type = sub >> 1, src = sub & 1;
+    const int g = w / (2 * GG_NLIST), sub = w - 2 * GG_NLIST * g, type = sub >> 1, src = sub & 1;
     if (g >= nGroups) return;
-    int blk = A.groupHead[6 * g + 2 * type + src];
+    int blk = A.groupHead[2 * GG_NLIST * g + 2 * type + src];
     if (blk < 0) return;
-    const int total = A.groupCnt[6 * g + 2 * type + src];
+    const int total = A.groupCnt[2 * GG_NLIST * g + 2 * type + src];
     const int b0 = g * GG_WALK_GB, nB = min(GG_WALK_GB, A.nBuckets - b0);
     const unsigned all = (1u << nB) - 1u;
     // lane b < nB: write cursor of bucket b
     long long cur = 0;
     if (lane < nB) {
-        const int *e = &A.bucketCnt[3 * (b0 + lane)];
-        cur = A.bucketOff[b0 + lane] + (type <= 1 ? e[2] : 0) + (type == 0 ? e[1] : 0) +
-              (src ? A.groupCnt[6 * g + 2 * type] : 0);
+        const int *e = &A.bucketCnt[GG_NLIST * (b0 + lane)];
+        cur = A.bucketOff[b0 + lane] + (type <= 2 ? e[3] : 0) + (type <= 1 ? e[2] : 0) + (type == 0 ? e[1] : 0) +
+              (src ? A.groupCnt[2 * GG_NLIST * g + 2 * type] : 0);
     }
     const int cnt0 = total - 32 * ((total - 1) / 32); // the head block is the partial one
     // the chain is a linked list (one dependent load per block): keep the NEXT block's entries and link in flight while
@@ -700,9 +706,10 @@ template <int NRAW>
 struct EvalSmemT {
     float4 stage[2][32 * CSTRIDE]; // double-buffered staged block; [0] also the sink hand-out / final reduction scratch
     union {
-        // cells: FP64 (x, y, z, M) of the block in flight, converted to sink-centred FP32 on arrival.  NRAW = 2 (MONO64):
-        // double-buffered like `stage`, and the conversion leaves the FP64 sink-centred position behind for the hot loop
-        double raw[NRAW][32 * 4];
+        // cells: FP64 (x, y, z, M) of the block in flight, converted to sink-centred FP32 on arrival.  The MONO64 loop
+        // (big cells of periodic boxes) works on blocks of <= 16 cells and uses the two halves as a double buffer like
+        // `stage`: its conversion leaves the FP64 sink-centred position behind for the hot loop
+        double raw[32 * 4];
         struct {                   // leaves (never in flight together with cells)
             int lstart[32], lpart[32]; // first staging slot and first particle of each leaf of the batch
             unsigned char owner[PCAP]; // staging slot -> leaf of the batch
@@ -745,8 +752,8 @@ __device__ __forceinline__ void gather_cells(const TreeKernelArgs &A, SM &W, int
     if (lane < cnt) {
         cn = (int)(it >> A.imgBits);
         const char *src = reinterpret_cast<const char *>(&A.nodes[cn]);
-        cp_async_cg16(&W.raw[rbuf][4 * lane], src);
-        cp_async_cg16(&W.raw[rbuf][4 * lane + 2], src + 16);
+        cp_async_cg16(&W.raw[rbuf + 4 * lane], src);
+        cp_async_cg16(&W.raw[rbuf + 4 * lane + 2], src + 16);
     }
     if (ORDER >= 2) {
         constexpr int LPR = ORDER == 2 ? 2 : (ORDER == 3 ? 4 : 8); // float4 pieces of the record in use
@@ -789,31 +796,32 @@ __device__ __forceinline__ void eval_cells(const TreeKernelArgs &A, SM &W, const
     if (n <= 0) return;
     // block size = the largest multiple of G that fits the 32 staging slots: the G sub-groups then make the same number
     // of trips through a full block (with 32 cells and G = 6 two sub-groups would run a 6th trip alone: 11 % idle)
-    const int BS = GG_EVAL_BSG ? 32 - (32 % E.G) : 32;
+    const int BSMAX = MONO64 ? 16 : 32; // (MONO64: half blocks, the FP64 staging is double-buffered in the same 1 KB)
+    const int BS = GG_EVAL_BSG ? BSMAX - (BSMAX % E.G) : BSMAX;
     const int nBlk = (n + BS - 1) / BS;
     unsigned itCur = lane < min(BS, n) ? L[lane] : 0u;
     gather_cells<ORDER>(A, W, 0, 0, itCur, min(BS, n), lane);
     unsigned itNext = (lane < BS && BS + lane < n) ? L[BS + lane] : 0u;
 #pragma unroll 1
     for (int i = 0; i < nBlk; ++i) {
-        const int buf = i & 1, rbuf = MONO64 ? buf : 0, cnt = min(BS, n - BS * i);
+        const int buf = i & 1, rbuf = MONO64 ? 64 * buf : 0, cnt = min(BS, n - BS * i);
         cp_async_wait_all();
         __syncwarp();
         if (lane < cnt) { // FP64 subtraction of the sink-bucket centre, then FP32
             const int ci = (int)(itCur & E.imgMask);
-            const double2 p01 = *reinterpret_cast<const double2 *>(&W.raw[rbuf][4 * lane]);
-            const double2 p23 = *reinterpret_cast<const double2 *>(&W.raw[rbuf][4 * lane + 2]);
+            const double2 p01 = *reinterpret_cast<const double2 *>(&W.raw[rbuf + 4 * lane]);
+            const double2 p23 = *reinterpret_cast<const double2 *>(&W.raw[rbuf + 4 * lane + 2]);
             const double rx = (p01.x + s_off[3 * ci]) - E.cenx, ry = (p01.y + s_off[3 * ci + 1]) - E.ceny,
                          rz = (p23.x + s_off[3 * ci + 2]) - E.cenz;
             W.stage[buf][lane * CSTRIDE] = make_float4((float)rx, (float)ry, (float)rz, (float)p23.y);
             if (MONO64) {
-                *reinterpret_cast<double2 *>(&W.raw[rbuf][4 * lane]) = make_double2(rx, ry);
-                W.raw[rbuf][4 * lane + 2] = rz;
+                *reinterpret_cast<double2 *>(&W.raw[rbuf + 4 * lane]) = make_double2(rx, ry);
+                W.raw[rbuf + 4 * lane + 2] = rz;
             }
         }
         __syncwarp();
         if (i + 1 < nBlk) {
-            gather_cells<ORDER>(A, W, buf ^ 1, MONO64 ? buf ^ 1 : 0, itNext, min(BS, n - BS * (i + 1)), lane);
+            gather_cells<ORDER>(A, W, buf ^ 1, MONO64 ? 64 * (buf ^ 1) : 0, itNext, min(BS, n - BS * (i + 1)), lane);
             itCur = itNext;
             const int k = BS * (i + 2) + lane;
             itNext = (lane < BS && k < n) ? L[k] : 0u;
@@ -830,8 +838,8 @@ __device__ __forceinline__ void eval_cells(const TreeKernelArgs &A, SM &W, const
                 cell_on_sink<ORDER, MONO64>(c, pc.w, K.sx - pc.x, K.sy - pc.y, K.sz - pc.z, K.ms, K.ax, K.ay, K.az, K.ap,
                                             K.dtm, &g0);
                 if (MONO64) {
-                    const double2 q01 = *reinterpret_cast<const double2 *>(&W.raw[rbuf][4 * j]);
-                    const double2 q23 = *reinterpret_cast<const double2 *>(&W.raw[rbuf][4 * j + 2]);
+                    const double2 q01 = *reinterpret_cast<const double2 *>(&W.raw[rbuf + 4 * j]);
+                    const double2 q23 = *reinterpret_cast<const double2 *>(&W.raw[rbuf + 4 * j + 2]);
                     const double ddx = K.sxd - q01.x, ddy = K.syd - q01.y, ddz = K.szd - q23.x;
                     const double d2 = ddx * ddx + ddy * ddy + ddz * ddz;
                     const double y = (double)g0;
@@ -981,7 +989,7 @@ __global__ void __launch_bounds__(GG_WARPS_PER_CTA * 32, MONO64 ? GG_MONO_MIN_CT
                     const PartS p = load_part(&A.parts[pi]);
                     W.stage[0][rank] = make_float4((float)(p.x - E.cenx), (float)(p.y - E.ceny), (float)(p.z - E.cenz), p.m);
                     W.stage[0][GG_MAX_SINKS + rank] = make_float4(p.h, __int_as_float(pi), 0.f, 0.f);
-                    if (MONO64) { W.raw[0][4 * rank] = p.x - E.cenx; W.raw[0][4 * rank + 1] = p.y - E.ceny; W.raw[0][4 * rank + 2] = p.z - E.cenz; }
+                    if (MONO64) { W.raw[4 * rank] = p.x - E.cenx; W.raw[4 * rank + 1] = p.y - E.ceny; W.raw[4 * rank + 2] = p.z - E.cenz; }
                 }
                 seen += __popc(m);
             }
@@ -993,15 +1001,20 @@ __global__ void __launch_bounds__(GG_WARPS_PER_CTA * 32, MONO64 ? GG_MONO_MIN_CT
             K.sx = sk.x; K.sy = sk.y; K.sz = sk.z; K.ms = sk.w; K.hs = sk2.x;
             K.sidx = __float_as_int(sk2.y);
             K.sxd = K.syd = K.szd = 0.0;
-            if (MONO64) { K.sxd = W.raw[0][4 * sI]; K.syd = W.raw[0][4 * sI + 1]; K.szd = W.raw[0][4 * sI + 2]; }
+            if (MONO64) { K.sxd = W.raw[4 * sI]; K.syd = W.raw[4 * sI + 1]; K.szd = W.raw[4 * sI + 2]; }
         }
         K.ax = K.ay = K.az = K.ap = K.dtm = 0.f;
         K.dax = K.day = K.daz = K.dap = 0.0;
         __syncwarp();
-        const int nLeaf = A.bucketCnt[3 * task.ord], nSoft = A.bucketCnt[3 * task.ord + 1], nNewt = A.bucketCnt[3 * task.ord + 2];
+        const int4 nL = __ldg(reinterpret_cast<const int4 *>(&A.bucketCnt[GG_NLIST * task.ord]));
+        const int nLeaf = nL.x, nSoft = nL.y, nNewt = nL.z, nBig = nL.w;
         const unsigned *L = A.lists + A.bucketOff[task.ord];
 
-        eval_cells<ORDER, MONO64>(A, W, s_off, E, K, L, nNewt, lane);
+        if (MONO64) { // the massive far cells of a periodic box: monopoles in FP64
+            eval_cells<ORDER, true>(A, W, s_off, E, K, L, nBig, lane);
+            L += nBig;
+        }
+        eval_cells<ORDER, false>(A, W, s_off, E, K, L, nNewt, lane);
         L += nNewt;
         for (int i = 0; i < nSoft; i += 32) {
             const int cnt = min(32, nSoft - i);
@@ -1082,7 +1095,7 @@ cudaError_t gg_launch_scatter_kernel(const TreeKernelArgs &a, int nSM, cudaStrea
     (void)nSM;
     const int nGroups = (a.nBuckets + GG_WALK_GB - 1) / GG_WALK_GB;
     if (nGroups <= 0) return cudaSuccess;
-    k_scatter<<<(6 * nGroups + 7) / 8, 256, 0, st>>>(a);
+    k_scatter<<<(2 * GG_NLIST * nGroups + 7) / 8, 256, 0, st>>>(a);
     return cudaGetLastError();
 }
 
