@@ -1728,7 +1728,16 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
     ta.maxBucket = c->maxBucket;
     ta.walkOnly = walkOnly ? 1 : 0;
     ta.mono64 = prm->bPeriodic ? 1 : 0;
-    ta.bigFrac = prm->bPeriodic ? GG_BIG_FRAC : 0.0;
+    ta.bigMass = DBL_MAX;
+    if (prm->bPeriodic && !walkOnly) { // the mass of the cell every image's walk starts from = everything there is
+        double rootMass = 0.0;
+        if (doEwald && c->haveRoot) rootMass = c->root[0]; // pkdCalcRoot / pkdDistribRoot: m of the whole box (pkd.c:4395-4493)
+        else { // periodic without Ewald: read the root cell (one small synchronous copy)
+            CK(cudaMemcpyAsync(&rootMass, &((const NodeW *)c->nodes.p)[rootNode].fMass, sizeof(double), cudaMemcpyDeviceToHost, c->st));
+            CK(cudaStreamSynchronize(c->st));
+        }
+        ta.bigMass = GG_BIG_FRAC * rootMass;
+    }
     ta.sunNode = c->sunMode ? sunN : -1;
     ta.sunBox = 1e-14; // dTinyBox, pkd.c:3004
     ta.acc = (double *)c->acc.p;

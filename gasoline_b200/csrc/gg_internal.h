@@ -123,7 +123,8 @@ struct TreeKernelArgs {
     int maxBucket;           // largest particle count of any bucket (sizes the particle buffer)
     int walkOnly;
     int mono64;              // k_eval: the big-cell list exists and its monopoles are evaluated in FP64 (periodic boxes)
-    double bigFrac;          // k_walk: a Newtonian cell is "big" when fMass >= bigFrac x the root cell's mass; <= 0: never
+    double bigMass;          // k_walk: a Newtonian cell is "big" when fMass >= bigMass (GG_BIG_FRAC x the mass of the walk's root
+                             // cell in periodic boxes, DBL_MAX otherwise: never)
     int sunNode;             // bDoSun pass (pkd.c:3003-3041): the dummy sink bucket's node, whose box is +-sunBox; else -1
     double sunBox;
     // outputs (local particles, tree order)

@@ -434,8 +434,7 @@ __global__ void __launch_bounds__(GG_WALK_WARPS * 32, GG_WALK_MIN_CTAS) k_walk(c
     const unsigned imgMask = (1u << A.imgBits) - 1u;
     Slab slab{0, GG_SLAB_BLOCKS};
     const int nGroups = (A.nBuckets + GG_WALK_GB - 1) / GG_WALK_GB;
-    // "big" = at least bigFrac of everything there is (the mass of the walk's root cell); bigFrac <= 0: no such class
-    const double bigMass = A.bigFrac > 0.0 ? __dmul_rn(A.bigFrac, __ldg(&A.nodes[A.rootNode].fMass)) : 1.7976931348623157e308;
+    const bool haveBig = A.bigMass < 1.0e308; // periodic boxes only (open boundaries: the class is empty, nothing is spent on it)
 
     for (;;) {
         int g = 0;
@@ -538,12 +537,13 @@ __global__ void __launch_bounds__(GG_WALK_WARPS * 32, GG_WALK_MIN_CTAS) k_walk(c
             // ---- decide, per bucket of the item's mask: open / Newtonian cell / softened cell
             unsigned mOpen = 0, mSoft = 0, mNewt = 0, mBig = 0, amb = 0;
             int img = 0, np = 0, c0 = -1, c1 = -1, nPnode = 0;
-            double x = 0.0, y = 0.0, z = 0.0, fOpen2 = 0.0, fSoftC = 0.0, fMassC = 0.0;
+            double x = 0.0, y = 0.0, z = 0.0, fOpen2 = 0.0, fSoftC = 0.0;
+            bool isBig = false;
             if (node >= 0) {
                 img = (int)(item & imgMask);
                 const NodeW nd = load_node_smem(&W.nstage[lane * NSTRIDE]);
                 x = nd.rx + s_off[3 * img]; y = nd.ry + s_off[3 * img + 1]; z = nd.rz + s_off[3 * img + 2];
-                fOpen2 = nd.fOpen2; fSoftC = nd.fSoft; fMassC = nd.fMass; c0 = nd.c0; c1 = nd.c1; nPnode = nd.nP;
+                fOpen2 = nd.fOpen2; fSoftC = nd.fSoft; isBig = nd.fMass >= A.bigMass; c0 = nd.c0; c1 = nd.c1; nPnode = nd.nP;
                 if (nd.nP < 4) mOpen = mask; // walk.c:81 (pUpper - pLower < 3)
                 else if (near_dist2(W.gbox, x, y, z) <= fOpen2) { // else: no bucket inside the group box opens it
                     if (far_dist2(W.gbox, x, y, z) <= fOpen2) mOpen = mask; // every bucket inside the group box does
@@ -598,7 +598,7 @@ __global__ void __launch_bounds__(GG_WALK_WARPS * 32, GG_WALK_MIN_CTAS) k_walk(c
                     mNewt = mAcc & ~mSoft;
                     // periodic boxes: the few massive far cells go to a list of their own, whose monopoles k_eval
                     // evaluates in FP64 (see eval_cells); same cell = same class for every bucket of the group
-                    if (fMassC >= bigMass) { mBig = mNewt; mNewt = 0; }
+                    if (isBig) { mBig = mNewt; mNewt = 0; }
                 }
                 if (mOpen && c0 < 0) { // an opened bucket: all its particles are sources (walk.c:93-114)
                     np = nPnode;
@@ -623,7 +623,7 @@ __global__ void __launch_bounds__(GG_WALK_WARPS * 32, GG_WALK_MIN_CTAS) k_walk(c
             }
             nStack += 2 * __popc(mPush);
             distribute(A, W, 2, mNewt, all, nB, item, 0, lane, lt, slab, myN, unused, unused);
-            distribute(A, W, 3, mBig, all, nB, item, 0, lane, lt, slab, myB, unused, unused);
+            if (haveBig) distribute(A, W, 3, mBig, all, nB, item, 0, lane, lt, slab, myB, unused, unused);
             distribute(A, W, 1, mSoft, all, nB, item, 0, lane, lt, slab, myS, unused, unused);
             distribute(A, W, 0, np > 0 ? mOpen : 0u, all, nB, item, np, lane, lt, slab, myP, sharedP, myL);
             __syncwarp();
@@ -797,7 +797,7 @@ __device__ __forceinline__ void eval_cells(const TreeKernelArgs &A, SM &W, const
     // block size = the largest multiple of G that fits the 32 staging slots: the G sub-groups then make the same number
     // of trips through a full block (with 32 cells and G = 6 two sub-groups would run a 6th trip alone: 11 % idle)
     const int BSMAX = MONO64 ? 16 : 32; // (MONO64: half blocks, the FP64 staging is double-buffered in the same 1 KB)
-    const int BS = GG_EVAL_BSG ? BSMAX - (BSMAX % E.G) : BSMAX;
+    const int BS = (GG_EVAL_BSG && E.G <= BSMAX) ? BSMAX - (BSMAX % E.G) : BSMAX; // (G = 32 sub-groups of one sink: whole blocks)
     const int nBlk = (n + BS - 1) / BS;
     unsigned itCur = lane < min(BS, n) ? L[lane] : 0u;
     gather_cells<ORDER>(A, W, 0, 0, itCur, min(BS, n), lane);

@@ -48,12 +48,14 @@ void __real_pkdBucketWalk(PKD pkd, int iBucket, int nReps, int iOrder);
  */
 #define REF_MAX_RANKS 64
 static FILE *g_dump[REF_MAX_RANKS];
+static int g_dumpStep[REF_MAX_RANKS]; /* REF_DUMP_ALL: one dump per force evaluation, <prefix>.s<k>.rank<id> */
 static void dump_header(PKD pkd) {
     const char *prefix = getenv("REF_DUMP");
     char name[512];
     FILE *f;
     int i, k, hdr[6], nTop;
-    snprintf(name, sizeof(name), "%s.rank%d", prefix, pkd->idSelf);
+    if (getenv("REF_DUMP_ALL")) snprintf(name, sizeof(name), "%s.s%d.rank%d", prefix, g_dumpStep[pkd->idSelf], pkd->idSelf);
+    else snprintf(name, sizeof(name), "%s.rank%d", prefix, pkd->idSelf);
     f = fopen(name, "wb");
     assert(f);
     g_dump[pkd->idSelf] = f;
@@ -141,6 +143,15 @@ void __wrap_pkdGravAll(PKD pkd, int nReps, int bPeriodic, int iOrder, int bEwald
             double v[6];
             v[0] = p->a[0]; v[1] = p->a[1]; v[2] = p->a[2]; v[3] = p->fPot; v[4] = p->dtGrav; v[5] = p->fWeight;
             fwrite(v, sizeof(double), 6, f);
+        }
+        if (getenv("REF_DUMP_ALL")) { /* the positions this evaluation (and the decomposition before it) saw */
+            for (i = 0; i < pkd->nLocal; ++i) {
+                const PARTICLE *p = &pkd->pStore[i];
+                double v[3];
+                v[0] = p->r[0]; v[1] = p->r[1]; v[2] = p->r[2];
+                fwrite(v, sizeof(double), 3, f);
+            }
+            ++g_dumpStep[pkd->idSelf];
         }
         fclose(f);
         g_dump[pkd->idSelf] = NULL;

@@ -48,8 +48,11 @@ def parse_dump(path):
             break
         recs.append(r.copy())
     sums = np.frombuffer(b, np.float64, 4, off).copy(); off += 32
-    res = np.frombuffer(b, np.float64, 6 * nLocal, off).reshape(nLocal, 6).copy()
-    return dict(nThreads=nThreads, idSelf=idSelf, nNodes=nNodes, iRoot=iRoot, iOrder=iOrder, top_i=top_i, top_d=top_d,
+    res = np.frombuffer(b, np.float64, 6 * nLocal, off).reshape(nLocal, 6).copy(); off += 48 * nLocal
+    pos = None
+    if len(b) >= off + 24 * nLocal:  # REF_DUMP_ALL: the particles' positions at this force evaluation
+        pos = np.frombuffer(b, np.float64, 3 * nLocal, off).reshape(nLocal, 3).copy()
+    return dict(pos=pos, nThreads=nThreads, idSelf=idSelf, nNodes=nNodes, iRoot=iRoot, iOrder=iOrder, top_i=top_i, top_d=top_d,
                 root=root, buckets=np.array(recs, np.int32), sums=sums, res=res)
 
 

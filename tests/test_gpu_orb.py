@@ -128,3 +128,33 @@ def test_device_decomposition_full_size():
         assert np.array_equal(np.nonzero(dest == r)[0], doms[r])
     print(f"ORB 1 M particles -> 8 domains: device {ms:.1f} ms ({sum(n['ittr'] for n in nodes)} bisection steps in "
           f"3 levels), numpy restatement {ms_cpu:.0f} ms; domain sizes {np.bincount(dest).tolist()}")
+
+
+def test_later_decompositions_on_the_device_match_the_stepping_reference():
+    """Second, third, ... decomposition of a run (tests/golden/orbsteps_*.npz: a TIME-STEPPING multi-rank run of the reference
+    binary): the device services under domain.pst_domain_decomp with `prev` = the previous cells' axis and split and the
+    work weights the previous force evaluation left -- every particle on the reference's rank."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden_orbsteps import CASES
+    for name in sorted(CASES):
+        if name.endswith("_overflow"):
+            continue  # the store-overflow branch (pst.c:1049-1270) is not reproduced; see tests/test_oracle_orb.py
+        z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+        nThreads, nSteps = int(z["nThreads"]), int(z["nSteps"])
+        prev = None
+        for k in range(nSteps + 1):
+            pos, want = z[f"s{k}_pos"], z[f"s{k}_rank"]
+            w = None if k == 0 else z[f"s{k - 1}_fWeight"]
+            idx = [np.nonzero(np.arange(len(pos)) % 2 == s)[0] for s in range(2)]
+            pkds = [PKD(device=0) for _ in idx]
+            for q, i in zip(pkds, idx):
+                q.pkdOrbLoad(pos[i, 0], pos[i, 1], pos[i, 2], fWeight=None if w is None else w[i])
+            cells = domain.pst_domain_decomp(pkds, nThreads, prev=prev)
+            dest = np.zeros(len(pos), np.int32)
+            for i, q in zip(idx, pkds):
+                dest[i] = domain.leaf_rank(nThreads)[q.pkdOrbCells()]
+                q.close()
+            assert np.array_equal(dest, want), f"{name}: decomposition {k} differs from the reference's"
+            prev = cells

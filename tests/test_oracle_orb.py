@@ -233,3 +233,50 @@ def test_orb_oracle_vs_reference_binary_live(n, nThreads, seed, tmp_path):
     for r in range(nThreads):
         assert np.array_equal(ref[r], doms[r]), f"rank {r}"
         assert np.array_equal(np.nonzero(dest == r)[0], ref[r])
+
+
+# ---- later decompositions of a run, PINNED: a time-stepping multi-rank run of the reference binary (make_golden_orbsteps.py)
+import sys as _sys  # noqa: E402
+
+_sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+from make_golden_orbsteps import CASES as ORBSTEP_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(ORBSTEP_CASES))
+def test_later_decompositions_match_the_stepping_reference(name):
+    """Step 0 = the first decomposition (unit weights, no previous split).  Steps >= 1 = what pstDomainDecomp does on every
+    later call of a single-rung run: bounds of the moved particles, split axis by the NEWSPLITDIMCUT hysteresis against the
+    previous axis (pst.c:1900-1910), bisection from the new bounds with the work weights pkdGravAll left in fWeight
+    (bSplitWork, master.c:964).  Oracle and device-service driver (host stub of the services) against the reference's
+    particle-to-rank assignment, particle for particle."""
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    nThreads, nSteps = int(z["nThreads"]), int(z["nSteps"])
+    prev_o, prev_d = None, None
+    for k in range(nSteps + 1):
+        pos, want = z[f"s{k}_pos"], z[f"s{k}_rank"]
+        w = None if k == 0 else z[f"s{k - 1}_fWeight"]
+        doms, nodes = orb_oracle.domain_decomp(pos[:, 0], pos[:, 1], pos[:, 2], nThreads, weights=w, prev=prev_o)
+        got = np.full(len(pos), -1, np.int32)
+        for r, ix in enumerate(doms):
+            got[ix] = r
+        nbad = int(np.count_nonzero(got != want))
+        if name.endswith("_overflow") and k == nSteps:
+            # the witness: a rank's store (N / nThreads x 1.1 = 550 particles) cannot take the 552 the work-weighted split
+            # sends it, the reference enters the store-overflow branch of _pstRootSplit (pst.c:1049-1270), which is NOT
+            # restated (DESIGN.md: stores with room) -- the outcome must differ, and only then
+            assert nbad > 0 and max(len(d) for d in doms) > int(len(pos) / nThreads * 1.1)
+            return
+        assert nbad == 0, f"{name} decomposition {k}: {nbad} particles on another rank than in the reference run"
+        prev_o = {n[0]: (n[1], n[2]) for n in nodes}
+        # the driver above the per-rank services (what bench.py / a non-Gasoline host runs), services on 2 host stubs
+        owner = np.arange(len(pos)) % 2
+        idx = [np.nonzero(owner == s)[0] for s in range(2)]
+        ranks = [HostOrbRank(pos[i, 0], pos[i, 1], pos[i, 2], None if w is None else w[i]) for i in idx]
+        cells = domain.pst_domain_decomp(ranks, nThreads, prev=prev_d)
+        dest = np.zeros(len(pos), np.int32)
+        for i, r in zip(idx, ranks):
+            dest[i] = domain.leaf_rank(nThreads)[r.pkdOrbCells()]
+        assert np.array_equal(dest, want), f"{name} decomposition {k}: the driver's domains differ from the reference's"
+        prev_d = cells
+    if nSteps >= 1:  # the work weights really moved the boundaries
+        assert not np.array_equal(np.bincount(z["s0_rank"]), np.bincount(z["s1_rank"]))
