@@ -1539,6 +1539,49 @@ int pack_top(gg_context *c, int *pRoot) {
     return GG_OK;
 }
 
+// pkdEwaldInit (ewald.c:182-248) + the constants of pkdBucketEwald (ewald.c:30-44) for the device kernel: the k-space
+// table goes to c->ewt, everything else travels as kernel arguments.  parts / acc / pot / nLoop = the local domain's.
+int make_ewald_args(gg_context *c, const gg_params *prm, EwaldKernelArgs &ea) {
+    std::vector<double> ewt;
+    const double Lbox = prm->fPeriod[0];
+    gg_ewald_table_host(c->root, Lbox, prm->fEwhCut, prm->iEwOrder, ewt);
+    int rc;
+    if ((rc = gg_ensure(c, c->ewt, (ewt.size() + 8) * sizeof(double)))) return rc;
+    // (pageable source of a few KB: the runtime stages it before the call returns, so the local vector may go)
+    CK(cudaMemcpyAsync(c->ewt.p, ewt.data(), ewt.size() * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    memset(&ea, 0, sizeof(ea));
+    ea.parts = (const PartS *)c->parts.p;
+    memcpy(ea.root, c->root, sizeof(ea.root));
+    const double *R = c->root;
+    ea.trQ4[0] = R[20] + R[26] + R[29]; // Qxx = xxxx + xxyy + xxzz   (meval.h:36-41)
+    ea.trQ4[1] = R[22] + R[21] + R[30]; // Qxy = xxxy + xyyy + xyzz
+    ea.trQ4[2] = R[24] + R[28] + R[31]; // Qxz = xxxz + xyyz + xzzz
+    ea.trQ4[3] = R[26] + R[23] + R[32]; // Qyy = xxyy + yyyy + yyzz
+    ea.trQ4[4] = R[27] + R[25] + R[33]; // Qyz = xxyz + yyyz + yzzz
+    ea.trQ4[5] = R[29] + R[32] + R[34]; // Qzz = xxzz + yyzz + zzzz
+    ea.trQ4[6] = (1.0 / 8.0) * (ea.trQ4[0] + ea.trQ4[3] + ea.trQ4[5]);
+    ea.trQ3[0] = 0.5 * (R[10] + R[11] + R[17]); // Qx = xxx + xyy + xzz   (meval.h:55-57)
+    ea.trQ3[1] = 0.5 * (R[12] + R[13] + R[18]); // Qy = xxy + yyy + yzz
+    ea.trQ3[2] = 0.5 * (R[14] + R[15] + R[19]); // Qz = xxz + yyz + zzz
+    ea.trQ2 = 0.5 * (R[4] + R[5] + R[9]);
+    ea.ewt = (const double *)c->ewt.p;
+    ea.nEwh = (int)(ewt.size() / 5);
+    ea.nReps = prm->nReps;
+    ea.nEwReps = (int)ceil(prm->fEwCut);
+    if (prm->nReps > ea.nEwReps) ea.nEwReps = prm->nReps;
+    ea.iOrder = prm->iEwOrder;
+    ea.L = Lbox;
+    ea.fEwCut2 = prm->fEwCut * prm->fEwCut * Lbox * Lbox;
+    ea.alpha = 2.0 / Lbox;
+    ea.alpha2 = ea.alpha * ea.alpha;
+    ea.k1 = M_PI / (ea.alpha2 * Lbox * Lbox * Lbox);
+    ea.ka = 2.0 * ea.alpha / sqrt(M_PI);
+    ea.acc = (double *)c->acc.p;
+    ea.pot = (double *)c->pot.p;
+    ea.nLoop = (int *)c->nloop.p;
+    return GG_OK;
+}
+
 int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_stats *stats, int depth = 0) {
     if (c->dom.empty()) return gg_fail(GG_ERR_ARG, "gg_gravity: gg_set_local has not been called");
     if (prm->iOrder < 1 || prm->iOrder > 4 || prm->iEwOrder < 0 || prm->iEwOrder > 4)
@@ -1619,49 +1662,11 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
     CK(cudaEventRecord(c->ev[7], c->st));
     int nEwh = 0;
     if (doEwald && !singleTask) {
-        std::vector<double> ewt;
-        const double Lbox = prm->fPeriod[0];
-        gg_ewald_table_host(c->root, Lbox, prm->fEwhCut, prm->iEwOrder, ewt);
-        nEwh = (int)(ewt.size() / 5);
-        if ((rc = gg_ensure(c, c->ewt, (ewt.size() + 8) * sizeof(double)))) return rc;
-        CK(cudaMemcpyAsync(c->ewt.p, ewt.data(), ewt.size() * sizeof(double), cudaMemcpyHostToDevice, c->st));
         EwaldKernelArgs ea;
-        memset(&ea, 0, sizeof(ea));
-        ea.parts = (const PartS *)c->parts.p;
+        if ((rc = make_ewald_args(c, prm, ea))) return rc;
+        nEwh = ea.nEwh;
         ea.active = dActive;
         ea.n = n;
-        memcpy(ea.root, c->root, sizeof(ea.root));
-        const double *R = c->root;
-        ea.trQ4[0] = R[20] + R[26] + R[29]; // Qxx = xxxx + xxyy + xxzz   (meval.h:36-41)
-        ea.trQ4[1] = R[22] + R[21] + R[30]; // Qxy = xxxy + xyyy + xyzz
-        ea.trQ4[2] = R[24] + R[28] + R[31]; // Qxz = xxxz + xyyz + xzzz
-        ea.trQ4[3] = R[26] + R[23] + R[32]; // Qyy = xxyy + yyyy + yyzz
-        ea.trQ4[4] = R[27] + R[25] + R[33]; // Qyz = xxyz + yyyz + yzzz
-        ea.trQ4[5] = R[29] + R[32] + R[34]; // Qzz = xxzz + yyzz + zzzz
-        ea.trQ4[6] = (1.0 / 8.0) * (ea.trQ4[0] + ea.trQ4[3] + ea.trQ4[5]);
-        ea.trQ3[0] = 0.5 * (R[10] + R[11] + R[17]); // Qx = xxx + xyy + xzz   (meval.h:55-57)
-        ea.trQ3[1] = 0.5 * (R[12] + R[13] + R[18]); // Qy = xxy + yyy + yzz
-        ea.trQ3[2] = 0.5 * (R[14] + R[15] + R[19]); // Qz = xxz + yyz + zzz
-        ea.trQ2 = 0.5 * (R[4] + R[5] + R[9]);
-        for (int k = 0; k < 10; ++k) ea.O32[k] = (float)R[10 + k];
-        for (int k = 0; k < 15; ++k) ea.H32[k] = (float)R[20 + k];
-        for (int k = 0; k < 7; ++k) ea.trQ4f[k] = (float)ea.trQ4[k];
-        for (int k = 0; k < 3; ++k) ea.trQ3f[k] = (float)ea.trQ3[k];
-        ea.ewt = (const double *)c->ewt.p;
-        ea.nEwh = nEwh;
-        ea.nReps = prm->nReps;
-        ea.nEwReps = (int)ceil(prm->fEwCut);
-        if (prm->nReps > ea.nEwReps) ea.nEwReps = prm->nReps;
-        ea.iOrder = prm->iEwOrder;
-        ea.L = Lbox;
-        ea.fEwCut2 = prm->fEwCut * prm->fEwCut * Lbox * Lbox;
-        ea.alpha = 2.0 / Lbox;
-        ea.alpha2 = ea.alpha * ea.alpha;
-        ea.k1 = M_PI / (ea.alpha2 * Lbox * Lbox * Lbox);
-        ea.ka = 2.0 * ea.alpha / sqrt(M_PI);
-        ea.acc = (double *)c->acc.p;
-        ea.pot = (double *)c->pot.p;
-        ea.nLoop = (int *)c->nloop.p;
         CK(gg_launch_ewald_kernel(ea, c->st));
         ++c->nLaunches;
     }
@@ -2031,6 +2036,87 @@ int gg_bucket_walk(gg_context *c, const gg_params *prm, int iBucket, int n3[3]) 
     if (rc) return rc;
     CK(cudaMemcpyAsync(n3, (int *)c->counts.p + 3 * (size_t)iBucket, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
+    return GG_OK;
+}
+
+// The two inner seams of the reference's bucket loop as entry points (parity / debugging hooks).
+static int bucket_range(gg_context *c, const char *who, int iBucket, int *pLo, int *pN) {
+    if (c->dom.empty()) return gg_fail(GG_ERR_ARG, "%s: no local domain", who);
+    if (iBucket < 0 || iBucket >= c->dom[0].nNodes) return gg_fail(GG_ERR_ARG, "%s: iBucket=%d", who, iBucket);
+    NodeW w;
+    CK(cudaMemcpyAsync(&w, (const NodeW *)c->nodes.p + iBucket, sizeof(w), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    if (w.c0 >= 0) return gg_fail(GG_ERR_ARG, "%s: node %d is a cell, not a bucket", who, iBucket);
+    *pLo = w.pLower; *pN = w.nP;
+    return GG_OK;
+}
+
+int gg_bucket_interact(gg_context *c, const gg_params *prm, int iBucket, int nMax, double *a, double *fPot, double *dtGrav,
+                       int n3[3]) {
+    if (!c || !prm || !a || !fPot || !dtGrav) return gg_fail(GG_ERR_ARG, "gg_bucket_interact: null argument");
+    CK(cudaSetDevice(c->device));
+    int lo = 0, np = 0, rc;
+    if ((rc = bucket_range(c, "gg_bucket_interact", iBucket, &lo, &np))) return rc;
+    if (np > nMax) return gg_fail(GG_ERR_ARG, "gg_bucket_interact: the bucket holds %d particles, room for %d", np, nMax);
+    gg_params p = *prm;
+    p.flags = GG_FLAG_NO_DOWNLOAD; p.bDoSun = 0;
+    Task t{iBucket, 0, 0, 0};
+    c->stateForces = false; // run_gravity clears the device result arrays
+    const int nPass = (np + GG_MAX_SINKS - 1) / GG_MAX_SINKS;
+    for (int pass = 0; pass < nPass; ++pass) { // a pass evaluates <= 8 active sinks of the bucket; results accumulate
+        t.pass = pass;
+        const bool keep = c->sunMode;
+        if (pass > 0) c->sunMode = true; // (re-uses the "leave the other particles' results alone" mode of the bDoSun pass)
+        rc = run_gravity(c, &p, &t, nullptr);
+        c->sunMode = keep;
+        if (rc) return rc;
+    }
+    CK(cudaMemcpyAsync(a, (const double *)c->acc.p + 3 * (size_t)lo, sizeof(double) * 3 * np, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(fPot, (const double *)c->pot.p + lo, sizeof(double) * np, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(dtGrav, (const double *)c->dtg.p + lo, sizeof(double) * np, cudaMemcpyDeviceToHost, c->st));
+    if (n3) CK(cudaMemcpyAsync(n3, (const int *)c->counts.p + 3 * (size_t)iBucket, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return GG_OK;
+}
+
+int gg_bucket_ewald(gg_context *c, const gg_params *prm, int iBucket, int nMax, double *a, double *fPot, int *pnFlop) {
+    if (!c || !prm || !a || !fPot) return gg_fail(GG_ERR_ARG, "gg_bucket_ewald: null argument");
+    CK(cudaSetDevice(c->device));
+    int lo = 0, np = 0, rc;
+    if ((rc = bucket_range(c, "gg_bucket_ewald", iBucket, &lo, &np))) return rc;
+    if (np > nMax) return gg_fail(GG_ERR_ARG, "gg_bucket_ewald: the bucket holds %d particles, room for %d", np, nMax);
+    if (c->rootLazy && (rc = fetch_root_lazy(c))) return rc;
+    if (!c->haveRoot) return gg_fail(GG_ERR_ARG, "gg_bucket_ewald: gg_set_root_moments has not been called");
+    const int n = c->dom[0].nPart;
+    if ((rc = gg_ensure(c, c->acc, (size_t)(n + 1) * 3 * sizeof(double))) || (rc = gg_ensure(c, c->pot, (size_t)(n + 1) * sizeof(double))) ||
+        (rc = gg_ensure(c, c->nloop, (size_t)(n + 1) * sizeof(int))))
+        return rc;
+    EwaldKernelArgs ea;
+    if ((rc = make_ewald_args(c, prm, ea))) return rc;
+    c->stateForces = false;
+    // the kernel on the bucket's slice of the particle arrays (the correction is per particle: no neighbours involved)
+    ea.parts = (const PartS *)c->parts.p + lo;
+    ea.active = c->hActive.empty() ? nullptr : (const int *)c->active.p + lo;
+    ea.n = np;
+    ea.acc = (double *)c->acc.p + 3 * (size_t)lo;
+    ea.pot = (double *)c->pot.p + lo;
+    ea.nLoop = (int *)c->nloop.p + lo;
+    CK(cudaMemsetAsync(ea.acc, 0, sizeof(double) * 3 * np, c->st));
+    CK(cudaMemsetAsync(ea.pot, 0, sizeof(double) * np, c->st));
+    CK(cudaMemsetAsync(ea.nLoop, 0, sizeof(int) * np, c->st));
+    CK(gg_launch_ewald_kernel(ea, c->st));
+    std::vector<int> nl((size_t)np);
+    CK(cudaMemcpyAsync(a, ea.acc, sizeof(double) * 3 * np, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(fPot, ea.pot, sizeof(double) * np, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(nl.data(), ea.nLoop, sizeof(int) * np, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    if (pnFlop) { // ewald.c:175-176: nLoop real-space terms and nEwhLoop k-space rows per active particle
+        static const int mflop[5] = {10, 10, 48, 151, 343};
+        long long f = 0;
+        for (int j = 0; j < np; ++j)
+            if (c->hActive.empty() || c->hActive[(size_t)lo + j]) f += (long long)nl[j] * (104 + mflop[prm->iEwOrder]) + (long long)ea.nEwh * 58;
+        *pnFlop = (int)f;
+    }
     return GG_OK;
 }
 

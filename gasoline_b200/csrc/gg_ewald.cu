@@ -38,58 +38,36 @@ __host__ __device__ inline void contract3(const double *O, T dx, T dy, T dz, T &
     oz = O[4] * hxx + O[6] * xy + O[7] * xz + O[5] * hyy + O[8] * yz + O[9] * hzz;
 }
 
-// MEVAL (meval.h:21-81) with the trace terms precomputed; accumulates into ax,ay,az,fPot.  Orders <= 2 (monopole, the
-// quadrupole and its trace, which is monopole-sized in a cube) in FP64; orders 3 and 4 -- ~110 of the ~180 multiply-adds of
-// a term, on moments whose contribution is <~ 1e-2 of the monopole's -- in FP32 with FP32 running sums (f32[0..3] = ax, ay,
-// az, -pot), folded into the FP64 results once per particle.  The kernel is FP64-pipe bound; this halves that pipe's work.
+// MEVAL (meval.h:21-81) with the trace terms precomputed; accumulates into ax,ay,az,fPot.
 __device__ __forceinline__ void meval(int iOrder, const EwaldKernelArgs &A, const double *g, double dx, double dy,
-                                      double dz, double &ax, double &ay, double &az, double &fPot, float *f32) {
+                                      double dz, double &ax, double &ay, double &az, double &fPot) {
     const double *R = A.root;
     double ta = 0.0;
+    if (iOrder >= 4) {
+        double hx, hy, hz;
+        contract4(&R[20], dx, dy, dz, hx, hy, hz);
+        double qr = 0.25 * (hx * dx + hy * dy + hz * dz);
+        const double *T = A.trQ4;
+        double Qhx = 0.5 * (T[0] * dx + T[1] * dy + T[2] * dz);
+        double Qhy = 0.5 * (T[1] * dx + T[3] * dy + T[4] * dz);
+        double Qhz = 0.5 * (T[2] * dx + T[4] * dy + T[5] * dz);
+        double Qh = 0.5 * (Qhx * dx + Qhy * dy + Qhz * dz);
+        fPot -= g[4] * qr - g[3] * Qh + g[2] * T[6];
+        ta += g[5] * qr - g[4] * Qh + g[3] * T[6];
+        ax += g[4] * hx - g[3] * Qhx;
+        ay += g[4] * hy - g[3] * Qhy;
+        az += g[4] * hz - g[3] * Qhz;
+    }
     if (iOrder >= 3) {
-        const float x = (float)dx, y = (float)dy, z = (float)dz;
-        const float g2 = (float)g[2], g3 = (float)g[3], g4 = (float)g[4];
-        const float hxx = 0.5f * x * x, hyy = 0.5f * y * y, hzz = 0.5f * z * z, xy = x * y, xz = x * z, yz = y * z;
-        float taf = 0.f, fx = f32[0], fy = f32[1], fz = f32[2], fp = f32[3];
-        if (iOrder >= 4) {
-            const float g5 = (float)g[5];
-            const float *H = A.H32, *T = A.trQ4f;
-            const float cxxx = (1.f / 3.f) * hxx * x, cyyy = (1.f / 3.f) * hyy * y, czzz = (1.f / 3.f) * hzz * z;
-            const float cxxy = hxx * y, cxxz = hxx * z, cxyy = hyy * x, cyyz = hyy * z, cxzz = hzz * x, cyzz = hzz * y, cxyz = xy * z;
-            const float hx = H[0] * cxxx + H[2] * cxxy + H[4] * cxxz + H[6] * cxyy + H[7] * cxyz + H[9] * cxzz + H[1] * cyyy +
-                             H[8] * cyyz + H[10] * cyzz + H[11] * czzz;
-            const float hy = H[2] * cxxx + H[6] * cxxy + H[7] * cxxz + H[1] * cxyy + H[8] * cxyz + H[10] * cxzz + H[3] * cyyy +
-                             H[5] * cyyz + H[12] * cyzz + H[13] * czzz;
-            const float hz = H[4] * cxxx + H[7] * cxxy + H[9] * cxxz + H[8] * cxyy + H[10] * cxyz + H[11] * cxzz + H[5] * cyyy +
-                             H[12] * cyyz + H[13] * cyzz + H[14] * czzz;
-            const float qr = 0.25f * (hx * x + hy * y + hz * z);
-            const float Qhx = 0.5f * (T[0] * x + T[1] * y + T[2] * z);
-            const float Qhy = 0.5f * (T[1] * x + T[3] * y + T[4] * z);
-            const float Qhz = 0.5f * (T[2] * x + T[4] * y + T[5] * z);
-            const float Qh = 0.5f * (Qhx * x + Qhy * y + Qhz * z);
-            fp += g4 * qr - g3 * Qh + g2 * T[6];
-            taf += g5 * qr - g4 * Qh + g3 * T[6];
-            fx += g4 * hx - g3 * Qhx;
-            fy += g4 * hy - g3 * Qhy;
-            fz += g4 * hz - g3 * Qhz;
-        }
-        {
-            const float *O = A.O32, *T = A.trQ3f;
-            const float ox = O[0] * hxx + O[2] * xy + O[4] * xz + O[1] * hyy + O[6] * yz + O[7] * hzz;
-            const float oy = O[2] * hxx + O[1] * xy + O[6] * xz + O[3] * hyy + O[5] * yz + O[8] * hzz;
-            const float oz = O[4] * hxx + O[6] * xy + O[7] * xz + O[5] * hyy + O[8] * yz + O[9] * hzz;
-            const float qr = (1.f / 3.f) * (ox * x + oy * y + oz * z);
-            const float Qtr = T[0] * x + T[1] * y + T[2] * z;
-            fp += g3 * qr - g2 * Qtr;
-            taf += g4 * qr - g3 * Qtr;
-            fx += g3 * ox - g2 * T[0];
-            fy += g3 * oy - g2 * T[1];
-            fz += g3 * oz - g2 * T[2];
-        }
-        f32[0] = fx - x * taf;
-        f32[1] = fy - y * taf;
-        f32[2] = fz - z * taf;
-        f32[3] = fp;
+        double ox, oy, oz;
+        contract3(&R[10], dx, dy, dz, ox, oy, oz);
+        double qr = (1.0 / 3.0) * (ox * dx + oy * dy + oz * dz);
+        double Qtr = A.trQ3[0] * dx + A.trQ3[1] * dy + A.trQ3[2] * dz;
+        fPot -= g[3] * qr - g[2] * Qtr;
+        ta += g[4] * qr - g[3] * Qtr;
+        ax += g[3] * ox - g[2] * A.trQ3[0];
+        ay += g[3] * oy - g[2] * A.trQ3[1];
+        az += g[3] * oz - g[2] * A.trQ3[2];
     }
     if (iOrder >= 2) {
         double qx = R[7] * dz + R[6] * dy + R[4] * dx;
@@ -124,7 +102,6 @@ __global__ void __launch_bounds__(128, GG_EWALD_MIN_CTAS) k_ewald(const EwaldKer
     const double dx = A.parts[i].x - A.root[1], dy = A.parts[i].y - A.root[2], dz = A.parts[i].z - A.root[3];
     const int nE = A.nEwReps, nR = A.nReps;
     int nLoop = 0;
-    float f32[4] = {0.f, 0.f, 0.f, 0.f}; // the l = 3, 4 part of the real-space sum: ax, ay, az, -pot
     for (int ix = -nE; ix <= nE; ++ix) {
         const bool holex = (ix >= -nR && ix <= nR);
         const double dxo = dx + ix * L;
@@ -161,7 +138,7 @@ __global__ void __launch_bounds__(128, GG_EWALD_MIN_CTAS) k_ewald(const EwaldKer
                     g[4] = 7 * g[3] * dir2 + alphan * a; alphan *= 2 * A.alpha2;
                     g[5] = 9 * g[4] * dir2 + alphan * a;
                 }
-                meval(A.iOrder, A, g, dxo, dyo, dzo, ax, ay, az, fPot, f32);
+                meval(A.iOrder, A, g, dxo, dyo, dzo, ax, ay, az, fPot);
                 ++nLoop;
             }
         }
@@ -176,10 +153,10 @@ __global__ void __launch_bounds__(128, GG_EWALD_MIN_CTAS) k_ewald(const EwaldKer
         ay += e[1] * t;
         az += e[2] * t;
     }
-    A.pot[i] += fPot - (double)f32[3];
-    A.acc[3 * (size_t)i] += ax + (double)f32[0];
-    A.acc[3 * (size_t)i + 1] += ay + (double)f32[1];
-    A.acc[3 * (size_t)i + 2] += az + (double)f32[2];
+    A.pot[i] += fPot;
+    A.acc[3 * (size_t)i] += ax;
+    A.acc[3 * (size_t)i + 1] += ay;
+    A.acc[3 * (size_t)i + 2] += az;
     A.nLoop[i] = nLoop;
 }
 

@@ -43,7 +43,9 @@ typedef unsigned short gg_mask_t;
 #define GG_MAX_SINKS 8      // sinks evaluated per warp pass (accumulators live in registers)
 #define GG_NLIST 4          // list types: 0 leaves (opened buckets), 1 softened cells, 2 Newtonian cells, 3 big Newtonian cells
 #ifndef GG_BIG_FRAC
-#define GG_BIG_FRAC (1.0 / 64.0) // periodic boxes: cells holding >= this share of the whole mass get FP64 monopoles (eval_cells)
+#define GG_BIG_FRAC (1.0 / 512.0) // periodic boxes: cells holding >= this share of the whole mass get FP64 monopoles (eval_cells).
+                                  // Measured on the 256^3 box, theta 0.5 (profiles/r02_big_frac.md): 1/64 -> k_eval 104.5 ms but
+                                  // potential rms error 5e-6; 1/512 -> 108.1 ms, 1.5e-6; all cells -> 122 ms, 3e-7
 #endif
 #define GG_STACK_CAP 512    // walk frontier entries per warp
 #define GG_STACK_DFS_MARGIN 128
@@ -146,9 +148,6 @@ struct EwaldKernelArgs {
     double trQ4[7];          // Qxx,Qxy,Qxz,Qyy,Qyz,Qzz, Qtr of the hexadecapole traces (meval.h:36-42)
     double trQ3[3];          // Qx,Qy,Qz (meval.h:55-57)
     double trQ2;             // 0.5*(xx+yy+zz) (meval.h:68)
-    // FP32 copies of the l = 3, 4 moments and their traces: those two orders of MEVAL are evaluated on the FP32 pipe
-    // (their terms are <~ 1e-2 of the monopole term; 1e-7 of them is far below the tolerance), see gg_ewald.cu
-    float O32[10], H32[15], trQ4f[7], trQ3f[3];
     const double *ewt;       // [nEwh][5]
     int nEwh;
     int nReps, nEwReps, iOrder;

@@ -92,6 +92,8 @@ def load_library(path: str | None = None):
     L.gg_bucket_counts.argtypes = [C.c_void_p, C.c_void_p]
     L.gg_bucket_walk.argtypes = [C.c_void_p, C.POINTER(gg_params), C.c_int, _ip]
     L.gg_ewald_table.argtypes = [C.c_void_p, C.POINTER(gg_params), C.c_void_p, C.c_int, _ip]
+    L.gg_bucket_interact.argtypes = [C.c_void_p, C.POINTER(gg_params), C.c_int, C.c_int, _dp, _dp, _dp, _ip]
+    L.gg_bucket_ewald.argtypes = [C.c_void_p, C.POINTER(gg_params), C.c_int, C.c_int, _dp, _dp, _ip]
     L.gg_device_results.argtypes = [C.c_void_p] + [C.POINTER(C.c_void_p)] * 4
     L.gg_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
     L.gg_host_free.argtypes = [C.c_void_p]
@@ -694,6 +696,26 @@ class PKD:
         n3 = np.zeros(3, dtype=np.int32)
         _check(self._L.gg_bucket_walk(self._ctx, C.byref(prm), int(iBucket), _i(n3)), "gg_bucket_walk")
         return tuple(int(v) for v in n3)
+
+    def pkdBucketInteract(self, iBucket: int, g: GravityParams, nMax: int = 64):
+        """pkdBucketWalk + pkdBucketInteract (walk.h:32, grav.h:100) for one bucket: (acc [nP][3], pot, dtGrav, (nPart,
+        nCellSoft, nCellNewt)) of the bucket's particles."""
+        if not getattr(self, "_uploaded", False):
+            self.upload()
+        prm = self._params(g, 0, 0)
+        a, p, d, n3 = np.zeros((nMax, 3)), np.zeros(nMax), np.zeros(nMax), np.zeros(3, np.int32)
+        _check(self._L.gg_bucket_interact(self._ctx, C.byref(prm), int(iBucket), nMax, _d(a), _d(p), _d(d), _i(n3)),
+               "gg_bucket_interact")
+        return a, p, d, tuple(int(v) for v in n3)
+
+    def pkdBucketEwald(self, iBucket: int, g: GravityParams, nMax: int = 64):
+        """pkdBucketEwald (ewald.h:8) for one bucket: (acc [nP][3], pot, flops as the reference returns them)."""
+        if not getattr(self, "_uploaded", False):
+            self.upload()
+        prm = self._params(g, 0, 0)
+        a, p, nf = np.zeros((nMax, 3)), np.zeros(nMax), np.zeros(1, np.int32)
+        _check(self._L.gg_bucket_ewald(self._ctx, C.byref(prm), int(iBucket), nMax, _d(a), _d(p), _i(nf)), "gg_bucket_ewald")
+        return a, p, int(nf[0])
 
     def pkdEwaldInit(self, fhCut: float = 2.8, iOrder: int = 4) -> np.ndarray:
         """pkdEwaldInit (ewald.c:182): rows (hx,hy,hz,hCfac,hSfac) of the k-space table."""

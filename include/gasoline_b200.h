@@ -239,6 +239,17 @@ int gg_bucket_counts(gg_context *ctx, int *counts3);
  * image) pairs for cells and (particle index, image) pairs for particles.  Returns counts in n3. */
 int gg_bucket_walk(gg_context *ctx, const gg_params *prm, int iBucket, int n3[3]);
 
+/* The two inner seams of pkdGravAll's bucket loop (pkd.c:2952-2964), for ONE bucket of the loaded local domain:
+ *   gg_bucket_interact = pkdBucketWalk + pkdBucketInteract (walk.h:32, grav.h:100): the bucket's lists are built and
+ *       evaluated; a[3 j], fPot[j], dtGrav[j] receive the results of the bucket's particle j (pLower + j; inactive
+ *       particles get zeros), n3 (may be NULL) the list lengths;
+ *   gg_bucket_ewald    = pkdBucketEwald (ewald.h:8) on the bucket's particles with the root moments of
+ *       gg_set_root_moments: a, fPot of the correction alone, *pnFlop (may be NULL) its return value (ewald.c:175-176).
+ * Parity / debugging hooks: every call launches whole kernels for a handful of particles. */
+int gg_bucket_interact(gg_context *ctx, const gg_params *prm, int iBucket, int nMax, double *a, double *fPot,
+                       double *dtGrav, int n3[3]);
+int gg_bucket_ewald(gg_context *ctx, const gg_params *prm, int iBucket, int nMax, double *a, double *fPot, int *pnFlop);
+
 /* pkdEwaldInit (ewald.c:182): the k-space table the device uses, 5 doubles per row (hx,hy,hz,hCfac,hSfac). */
 int gg_ewald_table(gg_context *ctx, const gg_params *prm, double *ewt5, int nMax, int *pnEwh);
 

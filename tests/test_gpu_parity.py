@@ -187,3 +187,31 @@ def test_edge_cases_no_active_one_active_coincident(gpu_lib):
     print(f"coincident pairs: acc rms {rms:.3e} max {mx:.3e}; pot rms {prms:.3e} max {pmx:.3e}")
     assert rms <= RMS_TOL and mx <= MAX_TOL and prms <= RMS_TOL and pmx <= MAX_TOL
     pkd.close()
+
+
+def test_per_bucket_seams_add_up_to_pkdGravAll(gpu_lib):
+    """gg_bucket_interact (pkdBucketWalk + pkdBucketInteract, walk.h:32 / grav.h:100) and gg_bucket_ewald (pkdBucketEwald,
+    ewald.h:8) for single buckets: tree part + Ewald part = what pkdGravAll leaves for the bucket's particles."""
+    from gasoline_b200 import ics
+    from gasoline_b200.pkd import PKD, GravityParams
+    p = ics.periodic_box(12)
+    g = GravityParams(nReps=1, bPeriodic=1, bEwald=1)
+    pkd = PKD(fPeriod=p.period)
+    pkd.pkdLoadParticles(p.x, p.y, p.z, p.m, p.h)
+    pkd.pkdBuildBinary(8, 0.7, 4)
+    full = pkd.pkdGravAll(g)
+    counts = pkd.pkdBucketCounts()
+    t = pkd.tree
+    bk = np.where(t.iLower == -1)[0]
+    for b in bk[:: max(1, len(bk) // 7)]:
+        lo, n = int(t.pLower[b]), int(t.pUpper[b] - t.pLower[b] + 1)
+        a, ph, dt, n3 = pkd.pkdBucketInteract(int(b), g)
+        ae, pe, nflop = pkd.pkdBucketEwald(int(b), g)
+        assert n3 == tuple(counts[b])
+        tot = a[:n] + ae[:n]
+        rel = np.linalg.norm(tot - full["acc"][lo:lo + n], axis=1) / np.linalg.norm(full["acc"][lo:lo + n], axis=1)
+        assert rel.max() < 1e-12, rel.max()
+        assert np.allclose(ph[:n] + pe[:n], full["pot"][lo:lo + n], rtol=1e-12, atol=1e-14)
+        assert np.array_equal(dt[:n], full["dtGrav"][lo:lo + n])
+        assert nflop > 0
+    pkd.close()
