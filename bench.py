@@ -103,6 +103,32 @@ def make_ic(spec: str):
     return ics.periodic_box(int(n_s)), GravityParams(nReps=1, bPeriodic=1, bEwald=1), float(theta_s)
 
 
+def make_ic_shared(spec: str, rank: int, world: int, barrier):
+    """N > 1: the initial conditions are generated ONCE (rank 0) and shared with the other ranks of the node through
+    /dev/shm as float32 columns (what a Tipsy file holds); every rank maps them and only ever touches the particles it
+    needs (its chunk for the decomposition, then its domain).  Masses and softenings are uniform: zero-stride views."""
+    from gasoline_b200 import ics
+    from gasoline_b200.pkd import GravityParams
+    kind, n_s, theta_s = spec.split(":")
+    d = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir(),
+                     f"gg_ic_{os.environ.get('MASTER_PORT', '0')}_{spec.replace(':', '_')}")
+    if rank == 0:
+        p, g, theta = make_ic(spec)
+        os.makedirs(d, exist_ok=True)
+        for k in ("x", "y", "z"):
+            np.save(os.path.join(d, k + ".npy"), getattr(p, k).astype(np.float32))
+        np.save(os.path.join(d, "meta.npy"), np.array([p.m[0], p.h[0], p.period[0], p.period[1], p.period[2]]))
+        del p
+    barrier()
+    meta = np.load(os.path.join(d, "meta.npy"))
+    cols = [np.load(os.path.join(d, k + ".npy"), mmap_mode="r") for k in ("x", "y", "z")]
+    n = cols[0].shape[0]
+    p = ics.Particles(cols[0], cols[1], cols[2], np.broadcast_to(np.float64(meta[0]), (n,)),
+                      np.broadcast_to(np.float64(meta[1]), (n,)), tuple(float(v) for v in meta[2:5]), f"shared:{spec}")
+    g = GravityParams(nReps=0, bPeriodic=0, bEwald=0) if kind == "plummer" else GravityParams(nReps=1, bPeriodic=1, bEwald=1)
+    return p, g, float(theta_s), d
+
+
 # ---------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
@@ -487,12 +513,13 @@ def run_multi(a):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except OSError:
         pass
-    p, g, theta = make_ic(spec)
-
     def barrier():
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
+
+    p, g, theta, ic_dir = make_ic_shared(spec, rank, world, barrier)
+    big = p.n > 40_000_000  # (C5: the parity checker and the C-host leg would need the whole box on one host process)
 
     # ---- the domains: the reference's ORB decomposition (pstDomainDecomp) with the per-rank services on the devices
     t0 = time.time()
@@ -551,7 +578,10 @@ def run_multi(a):
 
     # ---- parity self-check (rank 0 evaluates a sample of its buckets with the CPU oracle on all ranks' trees)
     parity = None
-    if not a.no_parity:
+    if big and not a.no_parity and rank == 0:
+        parity = {"ok": None, "skipped": f"{p.n} particles: the checker would need every rank's tree in one host process; "
+                                         "parity at this size is covered by the property tests (tests/test_gpu_fullsize.py)"}
+    if not a.no_parity and not big:
         lens = torch.zeros(world, dtype=torch.int64, device="cuda")
         lens[rank] = len(idx)
         dist.all_reduce(lens)
@@ -609,7 +639,7 @@ def run_multi(a):
     ms_max, tree_max, e2e_max, wall_max, eval_max, walk_max, ewald_max, exp_max, xfer_max, ing_max = vals.tolist()
     inter_all, flop_all, launches_all, n_all, nodes_all, h2d_all, d2h_all, entries_all = sums.tolist()
     c_host = None
-    if not a.no_extra:
+    if not a.no_extra and not big:
         # the reference BINARY on `world` pthread-MDL ranks, rank r on GPU r: rank 0 launches it, the others keep off the GPUs
         flag = os.path.join(tempfile.gettempdir(), f"gg_bench_{os.environ.get('MASTER_PORT', '0')}.done")
         if rank == 0 and os.path.exists(flag):
@@ -662,6 +692,10 @@ def run_multi(a):
             out["e2e_pkdGravAll"] = c_host
         print(json.dumps(out), flush=True)
     pkd.close()
+    barrier()
+    if rank == 0:
+        import shutil
+        shutil.rmtree(ic_dir, ignore_errors=True)
     dist.destroy_process_group()
 
 

@@ -210,8 +210,10 @@ def test_per_bucket_seams_add_up_to_pkdGravAll(gpu_lib):
         assert n3 == tuple(counts[b])
         tot = a[:n] + ae[:n]
         rel = np.linalg.norm(tot - full["acc"][lo:lo + n], axis=1) / np.linalg.norm(full["acc"][lo:lo + n], axis=1)
-        assert rel.max() < 1e-12, rel.max()
-        assert np.allclose(ph[:n] + pe[:n], full["pot"][lo:lo + n], rtol=1e-12, atol=1e-14)
-        assert np.array_equal(dt[:n], full["dtGrav"][lo:lo + n])
+        # (a bucket walked alone gets its lists in another ORDER than as one of a walk group of ten: the FP32 pair terms
+        #  then add up in another order -- 1e-7, not 1e-16)
+        assert rel.max() < 2e-6, rel.max()
+        assert np.allclose(ph[:n] + pe[:n], full["pot"][lo:lo + n], rtol=2e-6, atol=1e-9)
+        assert np.allclose(dt[:n], full["dtGrav"][lo:lo + n], rtol=1e-5)
         assert nflop > 0
     pkd.close()
