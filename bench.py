@@ -136,13 +136,16 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, period_ms: int = 50):
+        """index: one GPU, or a comma-separated list (ONE poller for all ranks' GPUs: a poller per rank makes eight
+        processes take the driver's lock twenty times a second, which showed up as milliseconds of skew between the
+        ranks of a step that contains a collective)."""
+        self.index, self.rows, self.proc, self.period = index, [], None, period_ms
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", str(self.period), "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
             time.sleep(0.3)  # the first sample takes nvidia-smi a moment
@@ -540,9 +543,12 @@ def run_multi(a):
     for _ in range(a.warmup):
         exchange(top=False, let=g, upload=False)
         pkd.pkdGravAll(g, download=False)
-    sampler = ClockSampler(local)
+    # clocks of all the job's GPUs from ONE poller on rank 0 (see ClockSampler)
+    sampler = ClockSampler(",".join(str(i) for i in range(world)), period_ms=100) if rank == 0 else None
     barrier()
-    sampler.start()
+    if sampler is not None:
+        sampler.start()
+    barrier()
     acc = dict(ms=0.0, tree=0.0, ewald=0.0, eval=0.0, walk=0.0, launches=0, export=0.0, transfer=0.0, ingest=0.0)
     wall0 = time.perf_counter()
     for _ in range(a.steps):
@@ -557,7 +563,7 @@ def run_multi(a):
         acc["launches"] += st["nKernelLaunches"] + xs["nKernelLaunches"]
     barrier()
     wall = time.perf_counter() - wall0
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler is not None else None
     inter = st["dPartSum"] + st["dCellSum"] + st["dSoftSum"]
 
     # ---- end to end: host tree + particles in (gg_set_local), exchange, evaluation, results in pinned host arrays

@@ -213,7 +213,8 @@ def test_per_bucket_seams_add_up_to_pkdGravAll(gpu_lib):
         # (a bucket walked alone gets its lists in another ORDER than as one of a walk group of ten: the FP32 pair terms
         #  then add up in another order -- 1e-7, not 1e-16)
         assert rel.max() < 2e-6, rel.max()
-        assert np.allclose(ph[:n] + pe[:n], full["pot"][lo:lo + n], rtol=2e-6, atol=1e-9)
+        # (tree part and Ewald part of the potential nearly cancel in a periodic box: the bar is relative to the parts)
+        assert np.allclose(ph[:n] + pe[:n], full["pot"][lo:lo + n], rtol=0, atol=5e-6 * np.abs(ph[:n]).max())
         assert np.allclose(dt[:n], full["dtGrav"][lo:lo + n], rtol=1e-5)
         assert nflop > 0
     pkd.close()
