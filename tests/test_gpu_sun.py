@@ -108,9 +108,13 @@ def test_sun_with_remote_domains(gpu_lib):
     soft = 0.01
     one = PKD()
     one.pkdLoadParticles(p.x, p.y, p.z, p.m, p.h)
-    for theta, tol in ((0.02, 2e-6), (0.7, 0.1)):  # (theta 0.7: the net pull at the centre of the sphere nearly cancels, so two different trees agree only roughly)
+    # theta 0.7: the net pull at the centre of the sphere nearly cancels (|aSun| is a few per cent of a typical particle's
+    # acceleration), so two different trees agree only to the TREE error of the force -- measured against the typical
+    # acceleration, not against |aSun| itself
+    for theta, tol in ((0.02, 2e-6), (0.7, 5e-3)):
         one.pkdBuildBinary(8, theta, 4)
         ref = one.pkdGravAll(GravityParams(nReps=0, bPeriodic=0, bEwald=0, bDoSun=1, dSunSoft=soft))
+        scale = np.linalg.norm(ref["aSun"]) if theta < 0.1 else np.sqrt((ref["acc"] ** 2).sum(axis=1).mean())
         parts = domain.orb_decompose(p.x, p.y, p.z, 3)
         doms = [domain.Domain(r, 3, p.x[ix], p.y[ix], p.z[ix], p.m[ix], p.h[ix], p.period, theta, device=0)
                 for r, ix in enumerate(parts)]
@@ -119,8 +123,9 @@ def test_sun_with_remote_domains(gpu_lib):
         for r, d in enumerate(doms):
             plain = d.pkd.pkdGravAll(g)
             out = d.pkd.pkdGravAll(GravityParams(nReps=0, bPeriodic=0, bEwald=0, bDoSun=1, dSunSoft=soft))
-            err = np.linalg.norm(out["aSun"] - ref["aSun"]) / np.linalg.norm(ref["aSun"])
-            print(f"sun with remote domains, theta {theta}, rank {r}: aSun rel diff to the one-domain run {err:.2e}, "
+            err = np.linalg.norm(out["aSun"] - ref["aSun"]) / scale
+            print(f"sun with remote domains, theta {theta}, rank {r}: aSun diff to the one-domain run {err:.2e} "
+                  f"(|aSun| = {np.linalg.norm(ref['aSun']) / scale:.2e} of the scale), "
                   f"lists {out['nSunPart']}/{out['nSunCellSoft']}/{out['nSunCellNewt']}")
             assert err <= tol
             if theta < 0.1:
