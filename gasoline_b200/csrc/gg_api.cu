@@ -59,6 +59,7 @@ int gg_ensure(gg_context *c, DevBuf &b, size_t bytes, size_t preserve) {
         CK(cudaStreamSynchronize(c->st));
         if (c->st2) CK(cudaStreamSynchronize(c->st2));
         if (c->st3) CK(cudaStreamSynchronize(c->st3));
+        if (c->st4) CK(cudaStreamSynchronize(c->st4));
         CK(cudaFree(b.p));
     }
     b.p = np;
@@ -420,6 +421,30 @@ int build_task_list(gg_context *c, int nn, const int *dActive, int *hCounts) {
     return GG_OK;
 }
 
+int make_ewald_args(gg_context *c, const gg_params *prm, EwaldKernelArgs &ea, cudaStream_t st);
+
+// the parameters the Ewald correction depends on (ewald.c:15-178, 182-248)
+bool same_ewald_params(const gg_params &a, const gg_params &b) {
+    return a.bPeriodic == b.bPeriodic && a.bEwald == b.bEwald && a.iEwOrder == b.iEwOrder && a.nReps == b.nReps &&
+           a.fEwCut == b.fEwCut && a.fEwhCut == b.fEwhCut && a.fPeriod[0] == b.fPeriod[0] && a.fPeriod[1] == b.fPeriod[1] &&
+           a.fPeriod[2] == b.fPeriod[2];
+}
+
+// Before anything else touches acc / pot / nloop or the particle records: order the side stream's early Ewald (if any)
+// before the main stream, and forget its results.
+int drop_early_ewald(gg_context *c) {
+    if (c->ewPending) {
+        CK(cudaStreamWaitEvent(c->st, c->evEw[2], 0));
+        c->ewPending = false;
+    }
+    c->ewValid = false;
+    return GG_OK;
+}
+
+#ifndef GG_EARLY_SLICE
+#define GG_EARLY_SLICE (1 << 20) // particles per slice of the early-Ewald upload (40 MB: ~0.7 ms of PCIe 5, ~1.7 ms of k_ewald)
+#endif
+
 int upload_domain(gg_context *c, const gg_tree *t, const gg_particles *pp, int nodeBase, int partBase, bool local,
                   bool onDevice) {
     const int nn = t->nNodes, np = pp->n;
@@ -443,6 +468,63 @@ int upload_domain(gg_context *c, const gg_tree *t, const gg_particles *pp, int n
     if ((rc = gg_ensure(c, c->momq, (keepN + nn + GG_MAX_TOP) * 48, keepN * 48))) return rc;
     if ((rc = gg_ensure(c, c->parts, (keepP + np + 1) * sizeof(PartS), keepP * sizeof(PartS)))) return rc;
     if (local && (rc = gg_ensure(c, c->hsoft, (size_t)(np + 1) * sizeof(double)))) return rc;
+    // ---- announced periodic + Ewald evaluation (gg_announce): the particles go up FIRST, slice by slice, and every slice's
+    //      Ewald correction starts on the side stream as soon as the slice is packed -- the FP64 kernel then runs beside
+    //      the copies of the remaining particles and of the tree instead of after them
+    const bool early = local && !onDevice && c->annValid && c->ann.bPeriodic && c->ann.bEwald && c->ann.iEwOrder > 0 &&
+                       c->ann.iEwOrder <= 4 && c->ann.nReps >= 0 && c->ann.nReps <= 3 && c->haveRoot && np > 0 && partBase == 0 &&
+                       !(c->ann.flags & GG_FLAG_WALK_ONLY);
+    if (local && (rc = drop_early_ewald(c))) return rc;
+    if (early) {
+        if ((rc = gg_ensure(c, c->acc, (size_t)(np + 1) * 3 * sizeof(double)))) return rc;
+        if ((rc = gg_ensure(c, c->pot, (size_t)(np + 1) * sizeof(double)))) return rc;
+        if ((rc = gg_ensure(c, c->nloop, (size_t)(np + 1) * sizeof(int)))) return rc;
+        const int *dActive = nullptr;
+        if (pp->active) {
+            if ((rc = gg_ensure(c, c->active, (size_t)(np + 1) * sizeof(int)))) return rc;
+            CK(cudaMemcpyAsync(c->active.p, pp->active, sizeof(int) * np, cudaMemcpyDefault, c->st));
+            dActive = (const int *)c->active.p;
+        }
+        EwaldKernelArgs ea;
+        CK(cudaEventRecord(c->evPacked, c->st)); // (everything queued on the main stream so far, incl. the ACTIVE flags)
+        CK(cudaStreamWaitEvent(c->st4, c->evPacked, 0));
+        if ((rc = make_ewald_args(c, &c->ann, ea, c->st4))) return rc;
+        ea.active = dActive;
+        CK(cudaMemsetAsync(c->acc.p, 0, (size_t)np * 3 * sizeof(double), c->st4));
+        CK(cudaMemsetAsync(c->pot.p, 0, (size_t)np * sizeof(double), c->st4));
+        CK(cudaEventRecord(c->evEw[0], c->st4));
+        const int nSlice = (np + GG_EARLY_SLICE - 1) / GG_EARLY_SLICE;
+        while ((int)c->evSlice.size() < nSlice) {
+            cudaEvent_t ev;
+            CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            c->evSlice.push_back(ev);
+        }
+        for (int k = 0; k < nSlice; ++k) {
+            const int lo = k * GG_EARLY_SLICE, hi = lo + GG_EARLY_SLICE < np ? lo + GG_EARLY_SLICE : np, m = hi - lo;
+            CK(cudaMemcpyAsync(dx + lo, pp->x + lo, sizeof(double) * m, kind, c->st));
+            CK(cudaMemcpyAsync(dy + lo, pp->y + lo, sizeof(double) * m, kind, c->st));
+            CK(cudaMemcpyAsync(dz + lo, pp->z + lo, sizeof(double) * m, kind, c->st));
+            CK(cudaMemcpyAsync(dm + lo, pp->fMass + lo, sizeof(double) * m, kind, c->st));
+            CK(cudaMemcpyAsync(dh + lo, pp->fSoft + lo, sizeof(double) * m, kind, c->st));
+            k_pack_parts<<<(m + 255) / 256, 256, 0, c->st>>>(m, dx + lo, dy + lo, dz + lo, dm + lo, dh + lo, partBase + lo,
+                                                             (PartS *)c->parts.p, (double *)c->hsoft.p + lo);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(c->evSlice[k], c->st));
+            CK(cudaStreamWaitEvent(c->st4, c->evSlice[k], 0));
+            ea.first = lo;
+            ea.n = hi;
+            CK(gg_launch_ewald_kernel(ea, c->st4));
+            c->nLaunches += 2;
+        }
+        CK(cudaEventRecord(c->evEw[1], c->st4));
+        CK(cudaEventRecord(c->evEw[2], c->st4));
+        c->ewPending = true;
+        c->ewValid = true;
+        c->ewPrm = c->ann;
+        memcpy(c->ewRoot, c->root, sizeof(c->ewRoot));
+        c->ewNEwh = ea.nEwh;
+        c->ewN = np;
+    }
     // ---- what the walk needs, on the main stream (issued first: the copy engine serves it first)
     if (nn > 0) {
         CK(cudaMemcpyAsync(dr, t->r, sizeof(double) * 3 * nn, kind, c->st));
@@ -454,7 +536,7 @@ int upload_domain(gg_context *c, const gg_tree *t, const gg_particles *pp, int n
         CK(cudaMemcpyAsync(di + 2 * (size_t)nn, t->iLower, sizeof(int) * nn, kind, c->st));
         CK(cudaMemcpyAsync(di + 3 * (size_t)nn, t->iUpper, sizeof(int) * nn, kind, c->st));
     }
-    if (np > 0) {
+    if (np > 0 && !early) {
         CK(cudaMemcpyAsync(dx, pp->x, sizeof(double) * np, kind, c->st));
         CK(cudaMemcpyAsync(dy, pp->y, sizeof(double) * np, kind, c->st));
         CK(cudaMemcpyAsync(dz, pp->z, sizeof(double) * np, kind, c->st));
@@ -483,7 +565,7 @@ int upload_domain(gg_context *c, const gg_tree *t, const gg_particles *pp, int n
         CK(cudaGetLastError());
         ++c->nLaunches;
     }
-    if (np > 0) {
+    if (np > 0 && !early) {
         k_pack_parts<<<(np + 255) / 256, 256, 0, c->st>>>(np, dx, dy, dz, dm, dh, partBase, (PartS *)c->parts.p,
                                                           local ? (double *)c->hsoft.p : nullptr);
         CK(cudaGetLastError());
@@ -514,7 +596,7 @@ int upload_domain(gg_context *c, const gg_tree *t, const gg_particles *pp, int n
         const int *dActive = nullptr;
         if (pp->active) {
             if ((rc = gg_ensure(c, c->active, (size_t)(np + 1) * sizeof(int)))) return rc;
-            CK(cudaMemcpyAsync(c->active.p, pp->active, sizeof(int) * np, cudaMemcpyDefault, c->st));
+            if (!early) CK(cudaMemcpyAsync(c->active.p, pp->active, sizeof(int) * np, cudaMemcpyDefault, c->st));
             dActive = (const int *)c->active.p;
         }
         c->nPartUpload = np;
@@ -579,6 +661,10 @@ int gg_create(gg_context **pctx, int device) {
     CK(cudaEventCreateWithFlags(&c->evWalk, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->evStats, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->evPacked, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&c->st4, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&c->evEw[0]));
+    CK(cudaEventCreate(&c->evEw[1]));
+    CK(cudaEventCreateWithFlags(&c->evEw[2], cudaEventDisableTiming));
     for (auto &ev : c->ev) CK(cudaEventCreate(&ev));
     for (auto &ev : c->evx) CK(cudaEventCreate(&ev));
     for (auto &ev : c->evt) CK(cudaEventCreate(&ev));
@@ -592,6 +678,7 @@ void gg_destroy(gg_context *c) {
     cudaStreamSynchronize(c->st);
     cudaStreamSynchronize(c->st2);
     if (c->st3) cudaStreamSynchronize(c->st3);
+    if (c->st4) cudaStreamSynchronize(c->st4);
     DevBuf *all[] = {&c->nodes, &c->momf, &c->momq, &c->parts, &c->active, &c->hsoft, &c->tasks, &c->ngroups,
                      &c->goffs, &c->counts, &c->acc, &c->pot, &c->dtg, &c->fweight, &c->nloop, &c->sums, &c->misc,
                      &c->imgoff, &c->ewt, &c->raw, &c->rawi, &c->cubtmp, &c->flush, &c->pool,
@@ -615,6 +702,10 @@ void gg_destroy(gg_context *c) {
     cudaStreamDestroy(c->st);
     cudaStreamDestroy(c->st2);
     if (c->st3) cudaStreamDestroy(c->st3);
+    if (c->st4) cudaStreamDestroy(c->st4);
+    for (auto &ev : c->evSlice) cudaEventDestroy(ev);
+    for (auto &ev : c->evEw)
+        if (ev) cudaEventDestroy(ev);
     if (c->evWalk) cudaEventDestroy(c->evWalk);
     if (c->evStats) cudaEventDestroy(c->evStats);
     if (c->evPacked) cudaEventDestroy(c->evPacked);
@@ -684,6 +775,7 @@ static int build_and_load(gg_context *c, int idSelf, const gg_particles *pp, int
                           int *pnNodes, double *root) {
     int rc;
     if ((rc = gg_finish_mom(c))) return rc;
+    if ((rc = drop_early_ewald(c))) return rc;
     char msg[400];
     int nl = 0;
     GGBuiltDev b{};
@@ -1130,6 +1222,7 @@ int gg_set_active(gg_context *c, const int *active) {
     int rc;
     const int *dActive = nullptr;
     c->stateForces = false; // a new sink set: the last evaluation's results do not cover the newly active particles
+    if ((rc = drop_early_ewald(c))) return rc; // (an early Ewald correction was computed for the previous sink set)
     if (active) {
         if ((rc = gg_ensure(c, c->active, (size_t)(np + 1) * sizeof(int)))) return rc;
         CK(cudaMemcpyAsync(c->active.p, active, sizeof(int) * np, cudaMemcpyDefault, c->st));
@@ -1481,6 +1574,13 @@ int gg_set_top(gg_context *c, int nCell, const int *pLower, const int *bUsed, co
     return GG_OK;
 }
 
+int gg_announce(gg_context *c, const gg_params *prm) {
+    if (!c) return gg_fail(GG_ERR_ARG, "gg_announce: null context");
+    c->annValid = prm != nullptr;
+    if (prm) c->ann = *prm;
+    return GG_OK;
+}
+
 int gg_set_root_moments(gg_context *c, const double root[GG_NROOT]) {
     if (!c || !root) return gg_fail(GG_ERR_ARG, "gg_set_root_moments: null");
     memcpy(c->root, root, sizeof(c->root));
@@ -1541,14 +1641,14 @@ int pack_top(gg_context *c, int *pRoot) {
 
 // pkdEwaldInit (ewald.c:182-248) + the constants of pkdBucketEwald (ewald.c:30-44) for the device kernel: the k-space
 // table goes to c->ewt, everything else travels as kernel arguments.  parts / acc / pot / nLoop = the local domain's.
-int make_ewald_args(gg_context *c, const gg_params *prm, EwaldKernelArgs &ea) {
+int make_ewald_args(gg_context *c, const gg_params *prm, EwaldKernelArgs &ea, cudaStream_t st) {
     std::vector<double> ewt;
     const double Lbox = prm->fPeriod[0];
     gg_ewald_table_host(c->root, Lbox, prm->fEwhCut, prm->iEwOrder, ewt);
     int rc;
     if ((rc = gg_ensure(c, c->ewt, (ewt.size() + 8) * sizeof(double)))) return rc;
     // (pageable source of a few KB: the runtime stages it before the call returns, so the local vector may go)
-    CK(cudaMemcpyAsync(c->ewt.p, ewt.data(), ewt.size() * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(c->ewt.p, ewt.data(), ewt.size() * sizeof(double), cudaMemcpyHostToDevice, st));
     memset(&ea, 0, sizeof(ea));
     ea.parts = (const PartS *)c->parts.p;
     memcpy(ea.root, c->root, sizeof(ea.root));
@@ -1640,6 +1740,15 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
     if ((rc = gg_ensure(c, c->boffs, (size_t)(nn + 1) * sizeof(int)))) return rc;
     if ((rc = gg_ensure(c, c->bnode, (size_t)(nn + 1) * sizeof(int)))) return rc;
 
+    // the Ewald correction gg_set_local launched early (gg_announce): same parameters, same root expansion, same sink set,
+    // first evaluation of this upload -> acc / pot / nloop already hold it (or will, on the side stream)
+    const bool usePre = doEwald && !singleTask && !c->sunMode && depth == 0 && c->ewValid && c->ewN == n &&
+                        same_ewald_params(c->ewPrm, *prm) && memcmp(c->ewRoot, c->root, sizeof(c->ewRoot)) == 0;
+    if (c->ewPending) { // either way the side stream's work is ordered before what follows on the main stream
+        CK(cudaStreamWaitEvent(c->st, c->evEw[2], 0));
+        c->ewPending = false;
+    }
+    c->ewValid = false; // consumed (or stale): a second evaluation of the same upload computes the correction itself
     CK(cudaEventRecord(c->ev[0], c->st));
     if (c->sunMode) { // only the dummy sink's slot and its bucket's counters: everything else holds results
         CK(cudaMemsetAsync((int *)c->counts.p + 3 * (size_t)sunN, 0xff, 3 * sizeof(int), c->st));
@@ -1649,8 +1758,10 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
         CK(cudaMemsetAsync((double *)c->fweight.p + sunP, 0, sizeof(double), c->st));
     } else {
         CK(cudaMemsetAsync(c->counts.p, 0xff, (size_t)nn * 3 * sizeof(int), c->st));
-        CK(cudaMemsetAsync(c->acc.p, 0, (size_t)n * 3 * sizeof(double), c->st));
-        CK(cudaMemsetAsync(c->pot.p, 0, (size_t)n * sizeof(double), c->st));
+        if (!usePre) {
+            CK(cudaMemsetAsync(c->acc.p, 0, (size_t)n * 3 * sizeof(double), c->st));
+            CK(cudaMemsetAsync(c->pot.p, 0, (size_t)n * sizeof(double), c->st));
+        }
         CK(cudaMemsetAsync(c->dtg.p, 0, (size_t)n * sizeof(double), c->st));
         CK(cudaMemsetAsync(c->fweight.p, 0, (size_t)n * sizeof(double), c->st));
     }
@@ -1661,9 +1772,10 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
     //      with them already in acc/pot the list evaluation's store is the final one (zero-copy delivery below)
     CK(cudaEventRecord(c->ev[7], c->st));
     int nEwh = 0;
-    if (doEwald && !singleTask) {
+    if (usePre) nEwh = c->ewNEwh;
+    else if (doEwald && !singleTask) {
         EwaldKernelArgs ea;
-        if ((rc = make_ewald_args(c, prm, ea))) return rc;
+        if ((rc = make_ewald_args(c, prm, ea, c->st))) return rc;
         nEwh = ea.nEwh;
         ea.active = dActive;
         ea.n = n;
@@ -1865,7 +1977,9 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
         CK(cudaEventElapsedTime(&ms, c->ev[1], c->ev[5])); stats->msWalk = ms;
         if (evalTimed) { CK(cudaEventElapsedTime(&ms, c->ev[6], c->ev[2])); stats->msEval = ms; }
         stats->nListEntries = (double)nListEntries;
-        CK(cudaEventElapsedTime(&ms, c->ev[7], c->ev[3])); stats->msEwald = ms;
+        if (usePre) CK(cudaEventElapsedTime(&ms, c->evEw[0], c->evEw[1])); // (on the side stream, beside the upload)
+        else CK(cudaEventElapsedTime(&ms, c->ev[7], c->ev[3]));
+        stats->msEwald = ms;
         CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[4])); stats->msTotal = ms;
         stats->nKernelLaunches = c->nLaunches;
     }
@@ -2092,7 +2206,7 @@ int gg_bucket_ewald(gg_context *c, const gg_params *prm, int iBucket, int nMax, 
         (rc = gg_ensure(c, c->nloop, (size_t)(n + 1) * sizeof(int))))
         return rc;
     EwaldKernelArgs ea;
-    if ((rc = make_ewald_args(c, prm, ea))) return rc;
+    if ((rc = make_ewald_args(c, prm, ea, c->st))) return rc;
     c->stateForces = false;
     // the kernel on the bucket's slice of the particle arrays (the correction is per particle: no neighbours involved)
     ea.parts = (const PartS *)c->parts.p + lo;

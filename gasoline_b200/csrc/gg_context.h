@@ -68,6 +68,17 @@ struct gg_context {
     DevBuf letrecv, commscratch;
     cudaEvent_t evx[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t evt[2] = {nullptr, nullptr}; // gg_timer_start / gg_timer_stop
+    // gg_announce: parameters of the next gg_gravity; the Ewald correction launched early by gg_set_local (side stream st4)
+    bool annValid = false;
+    gg_params ann;
+    cudaStream_t st4 = nullptr;
+    std::vector<cudaEvent_t> evSlice; // "slice k of the particles is packed"
+    cudaEvent_t evEw[3] = {nullptr, nullptr, nullptr}; // early Ewald: start, end (timed), done (ordering)
+    bool ewPending = false; // st4 work in flight or finished but not yet ordered before c->st
+    bool ewValid = false;   // acc / pot / nloop hold the Ewald correction of the loaded domain for ewPrm / ewRoot
+    gg_params ewPrm;
+    double ewRoot[GG_NROOT];
+    int ewNEwh = 0, ewN = 0;
 };
 
 // error reporting: formats into the calling thread's message buffer (gg_last_error), prints it, returns code

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(128, GG_EWALD_MIN_CTAS) k_ewald(const EwaldKer
     extern __shared__ double s_ewt[];
     for (int i = threadIdx.x; i < A.nEwh * 5; i += blockDim.x) s_ewt[i] = A.ewt[i];
     __syncthreads();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = A.first + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= A.n) return;
     if (A.active && !A.active[i]) return;
     const double L = A.L;
@@ -218,13 +218,13 @@ __global__ void __launch_bounds__(256) k_stats(const StatsKernelArgs A) {
 } // namespace
 
 cudaError_t gg_launch_ewald_kernel(const EwaldKernelArgs &a, cudaStream_t st) {
-    if (a.n <= 0) return cudaSuccess;
+    if (a.n <= a.first) return cudaSuccess;
     size_t smem = (size_t)a.nEwh * 5 * sizeof(double);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_ewald, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    k_ewald<<<(a.n + 127) / 128, 128, smem, st>>>(a);
+    k_ewald<<<(a.n - a.first + 127) / 128, 128, smem, st>>>(a);
     return cudaGetLastError();
 }
 

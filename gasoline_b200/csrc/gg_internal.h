@@ -29,6 +29,9 @@
 #ifndef GG_EVAL_BSG
 #define GG_EVAL_BSG 1       // k_eval stages blocks of the largest multiple of G cells (<= 32) instead of always 32
 #endif
+#ifndef GG_GATHER_PPL
+#define GG_GATHER_PPL 1     // consecutive 16 B pieces of a 128 B moment record one lane copies in k_eval's gather (1: 8 lanes per record)
+#endif
 #define GG_WALK_WARPS 8      // k_walk
 #define GG_WALK_MIN_CTAS 4   // 32 warps per SM (register cap 64)
 #define GG_SLAB_BLOCKS 32    // list blocks a warp takes from the pool per atomic
@@ -143,7 +146,7 @@ struct TreeKernelArgs {
 struct EwaldKernelArgs {
     const PartS *parts;      // local particles
     const int *active;
-    int n;
+    int first, n;            // particles [first, n)
     double root[GG_NROOT];
     double trQ4[7];          // Qxx,Qxy,Qxz,Qyy,Qyz,Qzz, Qtr of the hexadecapole traces (meval.h:36-42)
     double trQ3[3];          // Qx,Qy,Qz (meval.h:55-57)

@@ -702,14 +702,19 @@ __global__ void __launch_bounds__(256) k_scatter(const TreeKernelArgs A) {
 
 // ------------------------------------------------------------------------------------------------ k_eval
 #define PCAP (32 * CSTRIDE / PSTRIDE) // particles staged at once (96)
+#ifndef MONO_BS
+#define MONO_BS 31
+#endif
 template <int NRAW>
 struct EvalSmemT {
     float4 stage[2][32 * CSTRIDE]; // double-buffered staged block; [0] also the sink hand-out / final reduction scratch
     union {
         // cells: FP64 (x, y, z, M) of the block in flight, converted to sink-centred FP32 on arrival.  The MONO64 loop
-        // (big cells of periodic boxes) works on blocks of <= 16 cells and uses the two halves as a double buffer like
-        // `stage`: its conversion leaves the FP64 sink-centred position behind for the hot loop
-        double raw[32 * 4];
+        // (big cells of periodic boxes; NRAW = 2) double-buffers it like `stage`: its conversion leaves the FP64
+        // sink-centred position behind for the hot loop.  Its blocks hold <= MONO_BS = 31 cells: with 32 the CTA would be
+        // 42 bytes over the 45 670 B that let five of them share an SM (profiles/r02_k_eval_c4.md: half blocks of 16 cost
+        // 130 staging instructions per 2.9 trips of the hot loop)
+        double raw[NRAW == 2 ? 2 * MONO_BS * 4 : 32 * 4];
         struct {                   // leaves (never in flight together with cells)
             int lstart[32], lpart[32]; // first staging slot and first particle of each leaf of the batch
             unsigned char owner[PCAP]; // staging slot -> leaf of the batch
@@ -756,9 +761,11 @@ __device__ __forceinline__ void gather_cells(const TreeKernelArgs &A, SM &W, int
         cp_async_cg16(&W.raw[rbuf + 4 * lane + 2], src + 16);
     }
     if (ORDER >= 2) {
-        constexpr int LPR = ORDER == 2 ? 2 : (ORDER == 3 ? 4 : 8); // float4 pieces of the record in use
-        const int piece = lane & (LPR - 1), sub = lane / LPR;
-        // one shuffle, one 64-bit multiply-add and the copy per record: the lane's piece offset is folded into both
+        constexpr int NP = ORDER == 2 ? 2 : (ORDER == 3 ? 4 : 8); // float4 pieces of the record in use
+        constexpr int PPL = GG_GATHER_PPL < NP ? GG_GATHER_PPL : NP; // consecutive pieces one lane copies
+        constexpr int LPR = NP / PPL;                                // lanes per record
+        const int piece = (lane & (LPR - 1)) * PPL, sub = lane / LPR;
+        // one shuffle, one 64-bit multiply-add and the copies per record: the lane's piece offset is folded into both
         // bases once, and the shared-memory address of trip i is the base plus a compile-time constant
         const unsigned sdst = (unsigned)__cvta_generic_to_shared(&W.stage[buf][sub * CSTRIDE + 1 + piece]);
         const char *gsrc = reinterpret_cast<const char *>(A.momf) + piece * 16;
@@ -772,9 +779,12 @@ __device__ __forceinline__ void gather_cells(const TreeKernelArgs &A, SM &W, int
             // one bucket's walk) list the same cells again and again; measured on the 128^3 box: k_eval 6.84 -> 5.85 ms
             // (the wait for this gather was 18 % of all stall samples), Plummer unchanged.  The 32 B node halves stay
             // .cg: through L1 they cost 5 % on both workloads.
-            if (rec < cnt)
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sdst + i * (32 / LPR) * CSTRIDE * 16), "l"(src)
-                             : "memory");
+            if (rec < cnt) {
+#pragma unroll
+                for (int pc = 0; pc < PPL; ++pc)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sdst + i * (32 / LPR) * CSTRIDE * 16 + pc * 16),
+                                 "l"(src + pc * 16) : "memory");
+            }
         }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -796,7 +806,7 @@ __device__ __forceinline__ void eval_cells(const TreeKernelArgs &A, SM &W, const
     if (n <= 0) return;
     // block size = the largest multiple of G that fits the 32 staging slots: the G sub-groups then make the same number
     // of trips through a full block (with 32 cells and G = 6 two sub-groups would run a 6th trip alone: 11 % idle)
-    const int BSMAX = MONO64 ? 16 : 32; // (MONO64: half blocks, the FP64 staging is double-buffered in the same 1 KB)
+    const int BSMAX = MONO64 ? MONO_BS : 32; // (MONO64: the FP64 staging is double-buffered, see EvalSmemT)
     const int BS = (GG_EVAL_BSG && E.G <= BSMAX) ? BSMAX - (BSMAX % E.G) : BSMAX; // (G = 32 sub-groups of one sink: whole blocks)
     const int nBlk = (n + BS - 1) / BS;
     unsigned itCur = lane < min(BS, n) ? L[lane] : 0u;
@@ -804,7 +814,7 @@ __device__ __forceinline__ void eval_cells(const TreeKernelArgs &A, SM &W, const
     unsigned itNext = (lane < BS && BS + lane < n) ? L[BS + lane] : 0u;
 #pragma unroll 1
     for (int i = 0; i < nBlk; ++i) {
-        const int buf = i & 1, rbuf = MONO64 ? 64 * buf : 0, cnt = min(BS, n - BS * i);
+        const int buf = i & 1, rbuf = MONO64 ? 4 * MONO_BS * buf : 0, cnt = min(BS, n - BS * i);
         cp_async_wait_all();
         __syncwarp();
         if (lane < cnt) { // FP64 subtraction of the sink-bucket centre, then FP32
@@ -821,7 +831,7 @@ __device__ __forceinline__ void eval_cells(const TreeKernelArgs &A, SM &W, const
         }
         __syncwarp();
         if (i + 1 < nBlk) {
-            gather_cells<ORDER>(A, W, buf ^ 1, MONO64 ? 64 * (buf ^ 1) : 0, itNext, min(BS, n - BS * (i + 1)), lane);
+            gather_cells<ORDER>(A, W, buf ^ 1, MONO64 ? 4 * MONO_BS * (buf ^ 1) : 0, itNext, min(BS, n - BS * (i + 1)), lane);
             itCur = itNext;
             const int k = BS * (i + 2) + lane;
             itNext = (lane < BS && k < n) ? L[k] : 0u;

@@ -369,16 +369,17 @@ class Domain:
         ints = np.concatenate([[t.nNodes, t.iRoot, h.nLocal, 0], t.pLower, t.pUpper, t.iLower, t.iUpper]).astype(np.int32)
         return np.ascontiguousarray(dbl, dtype=np.float64), ints
 
-    def attach(self, upload: bool = True):
+    def attach(self, upload: bool = True, announce=None):
         """Hand kdTop + ilcnRoot to the GPU context (gg_set_local via upload, gg_set_top, gg_set_root_moments).
-        upload=False: the local domain is already resident (only the top tree / Ewald root go up)."""
+        upload=False: the local domain is already resident (only the top tree / Ewald root go up).  announce: the
+        parameters of the force evaluation that follows (PKD.upload)."""
         if self.pkd is None:
             raise _pkd.GasolineB200Error("Domain.attach: created without a device")
+        self.pkd.pkdDistribRoot(self.ilcnRoot)  # (first: an announced Ewald correction starts during the upload)
         if upload and not self.device_build:  # (a device-built domain is already loaded)
-            self.pkd.upload()
+            self.pkd.upload(announce=announce)
         k = self.kdTop
         self.pkd.pkdDistribCells(k["pLower"], k["bUsed"], k["r"], k["fMass"], k["fSoft"], k["fOpen2"], k["mom"])
-        self.pkd.pkdDistribRoot(self.ilcnRoot)
 
     def set_remote_raw(self, id_: int, dbl, ints, dbl_ptr: int | None = None, int_ptr: int | None = None):
         """A remote domain from export_raw() data.  With dbl_ptr/int_ptr (device addresses of the same layout, e.g.
@@ -785,7 +786,7 @@ class LibExchange:
         if top or d.kdTop is None:
             self.top_tree()
             lap("top_tree")
-        d.attach(upload=upload)
+        d.attach(upload=upload, announce=g)
         lap("attach_local" if upload else "set_top")
         st = d.pkd.pkdExchange(g, self._summaries[:, 0:6])
         lap("gg_exchange")

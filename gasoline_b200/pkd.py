@@ -87,6 +87,7 @@ def load_library(path: str | None = None):
     L.gg_set_remote_packed.argtypes = [C.c_void_p, C.c_int, _ip, C.c_void_p]
     L.gg_set_top.argtypes = [C.c_void_p, C.c_int, _ip, _ip, _dp, _dp, _dp, _dp, _dp]
     L.gg_set_root_moments.argtypes = [C.c_void_p, _dp]
+    L.gg_announce.argtypes = [C.c_void_p, C.c_void_p]
     L.gg_gravity.argtypes = [C.c_void_p, C.POINTER(gg_params), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                              C.POINTER(gg_stats)]
     L.gg_bucket_counts.argtypes = [C.c_void_p, C.c_void_p]
@@ -519,16 +520,25 @@ class PKD:
         self.iOrderMap = np.arange(self.nLocal, dtype=np.int32) if iOrderMap is None else np.asarray(iOrderMap, np.int32)
         self._uploaded = False
 
-    def upload(self):
-        """Ingest pStore + kdNodes into HBM (gg_set_local); also pkd->ilcnRoot when present."""
+    def upload(self, announce: "GravityParams | None" = None):
+        """Ingest pStore + kdNodes into HBM (gg_set_local); also pkd->ilcnRoot when present.  announce = the parameters
+        of the pkdGravAll that follows (gg_announce): with Ewald on, the correction then starts while the domain is
+        still being copied (the root expansion goes up first for that)."""
         if self.tree is None:
             raise GasolineB200Error("upload: build or set a tree first")
         tv = self.tree.view(with_mom=not self.device_moments)
         pv = gg_particles(self.nLocal, _d(self.x), _d(self.y), _d(self.z), _d(self.fMass), _d(self.fSoft),
                           _i(self.active) if self.active is not None else None)
-        _check(self._L.gg_set_local(self._ctx, self.idSelf, C.byref(tv), C.byref(pv)), "gg_set_local")
         if self.ilcnRoot is not None:
             _check(self._L.gg_set_root_moments(self._ctx, _d(self.ilcnRoot)), "gg_set_root_moments")
+        if announce is not None:
+            prm = self._params(announce, 0, 0)
+            _check(self._L.gg_announce(self._ctx, C.byref(prm)), "gg_announce")
+        try:
+            _check(self._L.gg_set_local(self._ctx, self.idSelf, C.byref(tv), C.byref(pv)), "gg_set_local")
+        finally:
+            if announce is not None:
+                _check(self._L.gg_announce(self._ctx, None), "gg_announce")
         self._uploaded = True
 
     def pkdSetRemote(self, id_: int, tree: Tree, x, y, z, fMass, fSoft):

@@ -224,6 +224,19 @@ int gg_exchange(gg_context *ctx, const gg_params *prm, const double *bndAll, gg_
 int gg_set_root_moments(gg_context *ctx, const double root[GG_NROOT]);
 
 /*
+ * Optional: announce the parameters of the NEXT gg_gravity before the domain goes up.  pkdGravAll (pkd.c:2868) receives
+ * tree, particles and parameters in one call; a host that splits it into gg_set_local + gg_gravity can say here what is
+ * coming.  With bPeriodic && bEwald (and the root expansion already set by gg_set_root_moments) the following
+ * gg_set_local then uploads the particles FIRST, in slices, and launches the Ewald correction of each slice on a side
+ * stream as soon as it has landed (pkdBucketEwald needs only the particles and pkd->ilcnRoot, ewald.c:15): the FP64
+ * kernel runs while the copy engine is still busy with the rest of the particles and the tree.  gg_gravity with the
+ * same Ewald parameters picks the finished correction up instead of launching it; any other sequence (different
+ * parameters, gg_set_active, new root moments in between, a re-run) falls back to the ordinary order.  Results are
+ * identical either way (same kernel, same inputs).  prm == NULL withdraws the announcement.
+ */
+int gg_announce(gg_context *ctx, const gg_params *prm);
+
+/*
  * One force evaluation = pkdGravAll (pkd.c:2868).  Output arrays are indexed like the local particles (tree
  * order): a[3*i..], fPot[i], dtGrav[i] (running max of 1/dt^2, grav.c:100), fWeight[i] (flops of the particle's
  * bucket, written for active particles only, pkd.c:2851).  Inactive particles are left untouched.
