@@ -1908,8 +1908,8 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
         CK(cudaMemcpyAsync(c->zcHost[3], c->fweight.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->st3));
     CK(cudaEventRecord(c->evStats, c->st3));
     if (nTasks > 0) ++c->nLaunches;
-    bool evalTimed = false, evalQueued = false;
-    long long nListEntries = 0;
+    bool evalTimed = false, evalQueued = false, fastLists = false;
+    long long nListEntries = 0, capListEntries = 0;
     if (nTasks > 0 && !walkOnly) {
         // per-bucket list offsets = exclusive scan of the entry counts the walk left; the total sizes the list array
         size_t tmpBytes = 0;
@@ -1917,21 +1917,33 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
         CK(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, (long long *)c->btot.p, (long long *)c->boff64.p, nBuckets + 1, c->st));
         if ((rc = gg_ensure(c, c->cubtmp, tmpBytes))) return rc;
         CK(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmpBytes, (long long *)c->btot.p, (long long *)c->boff64.p, nBuckets + 1, c->st));
-        long long nEntries = 0;
-        int hm3[4];
-        CK(cudaMemcpyAsync(&nEntries, (long long *)c->boff64.p + nBuckets, sizeof(long long), cudaMemcpyDeviceToHost, c->st));
-        CK(cudaMemcpyAsync(hm3, c->misc.p, sizeof(hm3), cudaMemcpyDeviceToHost, c->st));
-        CK(cudaStreamSynchronize(c->st));
-        tr.mark("gravity: walk sync");
-        if (hm3[1]) return gg_fail(GG_ERR_UNSUPPORTED, "gg_gravity: walk frontier overflowed %d entries (tree too deep)", GG_STACK_CAP);
-        if ((size_t)hm3[3] > c->capBlocks) {
-            // the chain pool was too small: the walk kept counting, so hm3[3] is what it needs -- grow and run again
-            if (depth >= 2) return gg_fail(GG_ERR_NOMEM, "gg_gravity: list pool overflow persists (%d blocks)", hm3[3]);
-            c->capBlocks = (size_t)hm3[3] + (size_t)hm3[3] / 8 + 1024;
-            return run_gravity(c, prm, singleTask, stats, depth + 1);
+        // Once the list array has a size from an earlier evaluation, scatter and evaluation are queued straight behind the
+        // walk: a one-thread kernel checks on the device that the walk's output fits (k_guard), the host looks at the same
+        // numbers after the evaluation and re-runs with larger buffers if not.  The first evaluation of a context (no size
+        // known) and every re-run read the sizes back between the walk and the scatter (GG_SYNC_WALK=1 forces that).
+        static const bool syncWalk = getenv("GG_SYNC_WALK") != nullptr && atoi(getenv("GG_SYNC_WALK")) != 0;
+        fastLists = depth == 0 && !syncWalk && c->lists.cap >= 64 * sizeof(unsigned);
+        if (fastLists) {
+            capListEntries = (long long)(c->lists.cap / sizeof(unsigned)) - 32;
+            ta.okFlag = (const int *)c->misc.p + 4;
+            CK(gg_launch_guard_kernel(ta, capListEntries, (int *)c->misc.p + 4, c->st));
+        } else {
+            long long nEntries = 0;
+            int hm3[4];
+            CK(cudaMemcpyAsync(&nEntries, (long long *)c->boff64.p + nBuckets, sizeof(long long), cudaMemcpyDeviceToHost, c->st));
+            CK(cudaMemcpyAsync(hm3, c->misc.p, sizeof(hm3), cudaMemcpyDeviceToHost, c->st));
+            CK(cudaStreamSynchronize(c->st));
+            tr.mark("gravity: walk sync");
+            if (hm3[1]) return gg_fail(GG_ERR_UNSUPPORTED, "gg_gravity: walk frontier overflowed %d entries (tree too deep)", GG_STACK_CAP);
+            if ((size_t)hm3[3] > c->capBlocks) {
+                // the chain pool was too small: the walk kept counting, so hm3[3] is what it needs -- grow and run again
+                if (depth >= 2) return gg_fail(GG_ERR_NOMEM, "gg_gravity: list pool overflow persists (%d blocks)", hm3[3]);
+                c->capBlocks = (size_t)hm3[3] + (size_t)hm3[3] / 8 + 1024;
+                return run_gravity(c, prm, singleTask, stats, depth + 1);
+            }
+            nListEntries = nEntries;
+            if ((rc = gg_ensure(c, c->lists, ((size_t)nEntries + 32) * sizeof(unsigned)))) return rc;
         }
-        nListEntries = nEntries;
-        if ((rc = gg_ensure(c, c->lists, ((size_t)nEntries + 32) * sizeof(unsigned)))) return rc;
         ta.lists = (unsigned *)c->lists.p;
         CK(gg_launch_scatter_kernel(ta, c->nSM, c->st));
         if (c->momPending) CK(cudaStreamWaitEvent(c->st, c->evMom, 0)); // the moments arrive on the second stream
@@ -1948,8 +1960,10 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
 
     unsigned long long hs[16];
     int hm[16];
+    long long nEntriesFast = 0;
     CK(cudaMemcpyAsync(hs, c->sums.p, sizeof(hs), cudaMemcpyDeviceToHost, c->st));
     CK(cudaMemcpyAsync(hm, c->misc.p, sizeof(hm), cudaMemcpyDeviceToHost, c->st));
+    if (fastLists) CK(cudaMemcpyAsync(&nEntriesFast, (long long *)c->boff64.p + nBuckets, sizeof(long long), cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
     st3Guard.armed = false; // c->st waited for evStats
     tr.mark("gravity: final sync");
@@ -1960,6 +1974,13 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
         if (depth >= 2) return gg_fail(GG_ERR_NOMEM, "gg_gravity: list pool overflow persists (%d blocks)", hm[3]);
         c->capBlocks = (size_t)hm[3] + (size_t)hm[3] / 8 + 1024;
         return run_gravity(c, prm, singleTask, stats, depth + 1);
+    }
+    if (fastLists) {
+        nListEntries = nEntriesFast;
+        if (nEntriesFast > capListEntries) { // k_guard held scatter and evaluation back: the list array was too small
+            if ((rc = gg_ensure(c, c->lists, ((size_t)nEntriesFast + (size_t)nEntriesFast / 8 + 32) * sizeof(unsigned)))) return rc;
+            return run_gravity(c, prm, singleTask, stats, depth + 1);
+        }
     }
     if (stats) {
         memset(stats, 0, sizeof(*stats));

@@ -138,6 +138,8 @@ struct TreeKernelArgs {
     double *dtg;
     int *counts;             // [nLocalNodes][3]
     int *errFlag;
+    const int *okFlag;       // non-null: k_scatter / k_eval run only if *okFlag != 0 (k_guard: the walk's output fits the
+                             // buffers they were launched with -- no host round trip between the walk and the evaluation)
     // zero-copy result delivery: the caller's a / fPot / dtGrav arrays when they are mapped pinned host memory (device
     // aliases, else null) -- k_eval stores every finished sink there as well, so the download overlaps the evaluation
     double *hacc, *hpot, *hdtg;
@@ -173,6 +175,7 @@ struct StatsKernelArgs {
 };
 
 cudaError_t gg_launch_walk_kernel(const TreeKernelArgs &a, int nSM, cudaStream_t st);
+cudaError_t gg_launch_guard_kernel(const TreeKernelArgs &a, long long capListEntries, int *okFlag, cudaStream_t st);
 cudaError_t gg_launch_scatter_kernel(const TreeKernelArgs &a, int nSM, cudaStream_t st);
 cudaError_t gg_launch_eval_kernel(const TreeKernelArgs &a, int nSM, cudaStream_t st);
 cudaError_t gg_launch_ewald_kernel(const EwaldKernelArgs &a, cudaStream_t st);

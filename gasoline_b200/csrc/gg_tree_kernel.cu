@@ -651,7 +651,16 @@ __global__ void __launch_bounds__(GG_WALK_WARPS * 32, GG_WALK_MIN_CTAS) k_walk(c
 // through (shared entries to every bucket of the group, masked entries to the buckets of their mask).  Bucket b's
 // lists start at bucketOff[b]: big Newtonian cells, Newtonian cells, softened cells, leaves; within a type the group's
 // shared entries come first, so all eight warps of a group know where to write without talking to each other.
+// One thread: do the walk's results fit what k_scatter / k_eval were launched with?  (frontier overflow flag, blocks taken
+// from the chain pool, total list entries.)  The host reads the same numbers after the evaluation and, if not, grows the
+// buffers and runs the evaluation again -- the common case costs no synchronisation between the walk and the evaluation.
+__global__ void k_guard(const int *errFlag, const int *poolCursor, int capBlocks, const long long *bucketOff, int nBuckets,
+                        long long capListEntries, int *okFlag) {
+    *okFlag = (*errFlag == 0 && *poolCursor <= capBlocks && bucketOff[nBuckets] <= capListEntries) ? 1 : 0;
+}
+
 __global__ void __launch_bounds__(256) k_scatter(const TreeKernelArgs A) {
+    if (A.okFlag && !*A.okFlag) return;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const int nGroups = (A.nBuckets + GG_WALK_GB - 1) / GG_WALK_GB;
@@ -960,6 +969,7 @@ __global__ void __launch_bounds__(GG_WARPS_PER_CTA * 32, MONO64 ? GG_MONO_MIN_CT
     double *s_off = reinterpret_cast<double *>(s_w + GG_WARPS_PER_CTA);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
+    if (A.okFlag && !*A.okFlag) return;
     for (int i = threadIdx.x; i < A.nImages * 3; i += blockDim.x) s_off[i] = A.imgOff[i];
     __syncthreads();
     EvalSmem &W = s_w[warp];
@@ -1098,6 +1108,11 @@ cudaError_t gg_launch_walk_kernel(const TreeKernelArgs &a, int nSM, cudaStream_t
     const int grid = grid_for((const void *)k_walk, GG_WALK_WARPS * 32, smem, nSM, GG_WALK_WARPS, nGroups, &e);
     if (e != cudaSuccess) return e;
     k_walk<<<grid, GG_WALK_WARPS * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t gg_launch_guard_kernel(const TreeKernelArgs &a, long long capListEntries, int *okFlag, cudaStream_t st) {
+    k_guard<<<1, 1, 0, st>>>(a.errFlag, a.poolCursor, a.capBlocks, a.bucketOff, a.nBuckets, capListEntries, okFlag);
     return cudaGetLastError();
 }
 

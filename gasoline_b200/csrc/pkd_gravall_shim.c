@@ -11,7 +11,8 @@
  *   1. flattens pkd->kdNodes[0..nNodes) and pkd->pStore[0..nLocal) into the SoA views gg_set_local takes (pinned
  *      staging buffers kept between calls, grown by high-water mark; the reference frees and rebuilds kdNodes before
  *      every gravity call, pkd.c:2636-2642, so nothing can be assumed resident).  The AoS records are 536 B / 184 B
- *      wide, so this pass is memory-bound host work: it runs on GG_SHIM_THREADS threads (default min(8, cores)).
+ *      wide, so this pass is memory-bound host work: it runs on GG_SHIM_THREADS threads per rank (default: the cores
+ *      divided among the ranks of the process, at most 16).
  *      The cells' multipole moments are NOT copied unless GG_SHIM_HOST_MOMENTS=1: the device forms them from the
  *      particles (gg_tree.mom = NULL; same definition, FP64, forces identical to rounding of the FP32 records);
  *   2. hands over pkd->ilcnRoot (pkdDistribRoot, pkd.c:4472) when Ewald is on;
@@ -86,15 +87,21 @@ static void *job_main(void *p) {
     return NULL;
 }
 
+static int g_shimRanks = 1; /* ranks of the host inside this process (pthread MDL): they share the cores */
+
 static int shim_threads(void) {
-    static int nT = 0;
-    if (!nT) {
+    static int nAll = 0;
+    int nT;
+    if (!nAll) {
         const char *e = getenv("GG_SHIM_THREADS");
         long nc = sysconf(_SC_NPROCESSORS_ONLN);
-        nT = e ? atoi(e) : (int)(nc < 8 ? nc : 8);
-        if (nT < 1) nT = 1;
-        if (nT > 64) nT = 64;
+        nAll = e ? -atoi(e) : (int)nc; /* negative: set by hand, per rank */
+        if (!nAll) nAll = 1;
     }
+    nT = nAll < 0 ? -nAll : nAll / (g_shimRanks > 0 ? g_shimRanks : 1);
+    if (nAll > 0 && nT > 16) nT = 16;
+    if (nT < 1) nT = 1;
+    if (nT > 64) nT = 64;
     return nT;
 }
 
@@ -352,6 +359,7 @@ void pkdGravAll(PKD pkd, int nReps, int bPeriodic, int iOrder, int bEwald, int i
 
     mdlassert(pkd->mdl, pkd->idSelf >= 0 && pkd->idSelf < 64);
     s = &g_shim[pkd->idSelf];
+    g_shimRanks = mdlThreads(pkd->mdl); /* (every rank writes the same value) */
     if (!s->ctx && gg_create(&s->ctx, shim_device(pkd)) != GG_OK) die("gg_create");
     if (mdlThreads(pkd->mdl) > 1 && !s->bJoined) shim_join(pkd, s);
     reserve(s, (size_t)nNodes, (size_t)n);
@@ -374,20 +382,6 @@ void pkdGravAll(PKD pkd, int nReps, int bPeriodic, int iOrder, int bEwald, int i
         bResident = gg_domain_summary(s->ctx, NULL, r, &fMass, NULL, NULL, NULL, NULL) == GG_OK && r[0] == c->r[0] &&
                     r[1] == c->r[1] && r[2] == c->r[2] && fMass == c->fMass;
     }
-    if (bResident) {
-        parallel_for((size_t)n, flatten_active, &pass);
-        if (gg_set_active(s->ctx, s->active) != GG_OK) die("gg_set_active");
-    } else {
-        parallel_for((size_t)nNodes, flatten_nodes, &pass);
-        parallel_for((size_t)n, flatten_particles, &pass);
-        t.nNodes = nNodes; t.iRoot = pkd->iRoot;
-        t.bnd = s->bnd; t.r = s->r; t.fMass = s->fMass; t.fSoft = s->fSoft; t.fOpen2 = s->fOpen2;
-        t.mom = pass.bMom ? s->mom : NULL;
-        t.pLower = s->pLower; t.pUpper = s->pUpper; t.iLower = s->iLower; t.iUpper = s->iUpper;
-        pp.n = n; pp.x = s->x; pp.y = s->y; pp.z = s->z; pp.fMass = s->m; pp.fSoft = s->h; pp.active = s->active;
-        if (gg_set_local(s->ctx, pkd->idSelf, &t, &pp) != GG_OK) die("gg_set_local");
-        s->builtNodes = NULL; /* the device now holds the host's arrays, not a tree it built itself (see pkdCalcRoot below) */
-    }
     if (bPeriodic && bEwald) {
         double root[GG_NROOT];
         const ILCN *R = &pkd->ilcnRoot;
@@ -405,6 +399,23 @@ void pkdGravAll(PKD pkd, int nReps, int bPeriodic, int iOrder, int bEwald, int i
     prm.fEwCut = fEwCut; prm.fEwhCut = fEwhCut; prm.bComove = bComove; prm.dRhoFac = dRhoFac;
     for (j = 0; j < 3; ++j) prm.fPeriod[j] = pkd->fPeriod[j];
     prm.bDoSun = bDoSun; prm.dSunSoft = dSunSoft;
+    /* what evaluation follows: with Ewald on, gg_set_local then sends the particles first and starts the correction of
+     * every slice beside the remaining copies (pkdBucketEwald needs only pStore and ilcnRoot, ewald.c:15) */
+    if (gg_announce(s->ctx, &prm) != GG_OK) die("gg_announce");
+    if (bResident) {
+        parallel_for((size_t)n, flatten_active, &pass);
+        if (gg_set_active(s->ctx, s->active) != GG_OK) die("gg_set_active");
+    } else {
+        parallel_for((size_t)nNodes, flatten_nodes, &pass);
+        parallel_for((size_t)n, flatten_particles, &pass);
+        t.nNodes = nNodes; t.iRoot = pkd->iRoot;
+        t.bnd = s->bnd; t.r = s->r; t.fMass = s->fMass; t.fSoft = s->fSoft; t.fOpen2 = s->fOpen2;
+        t.mom = pass.bMom ? s->mom : NULL;
+        t.pLower = s->pLower; t.pUpper = s->pUpper; t.iLower = s->iLower; t.iUpper = s->iUpper;
+        pp.n = n; pp.x = s->x; pp.y = s->y; pp.z = s->z; pp.fMass = s->m; pp.fSoft = s->h; pp.active = s->active;
+        if (gg_set_local(s->ctx, pkd->idSelf, &t, &pp) != GG_OK) die("gg_set_local");
+        s->builtNodes = NULL; /* the device now holds the host's arrays, not a tree it built itself (see pkdCalcRoot below) */
+    }
     if (mdlThreads(pkd->mdl) > 1) {
         /* the host's top tree and, in place of pkdRemoteWalk's pulls, one collective push of pruned trees */
         double bndAll[6 * 64];
@@ -499,6 +510,7 @@ void pkdBuildBinary(PKD pkd, int nBucket, int iOpenType, double dCrit, int iOrde
     n = pkd->nLocal;
     mdlassert(pkd->mdl, pkd->idSelf >= 0 && pkd->idSelf < 64);
     s = &g_shim[pkd->idSelf];
+    g_shimRanks = mdlThreads(pkd->mdl); /* (every rank writes the same value) */
     if (!s->ctx && gg_create(&s->ctx, shim_device(pkd)) != GG_OK) die("gg_create");
     reserve(s, 0, (size_t)n);
     pass.pkd = pkd; pass.s = s; pass.bMom = 1; pass.iOrder = iOrder; pass.tmp = NULL;
