@@ -49,6 +49,8 @@ def _f32(a):
 def periodic_box(n: int, seed: int = 12345, mode: str = "zeldovich", rms_disp: float = 1.0,
                  jitter: float = 0.3) -> Particles:
     """n^3 particles in the unit box centred on the origin (master.c:1728 fCenter=0)."""
+    if n >= 384 and mode == "zeldovich":
+        return _periodic_box_large(n, seed, rms_disp)
     rng = np.random.default_rng(seed)
     g = (np.arange(n) + 0.5) / n - 0.5
     X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
@@ -76,6 +78,42 @@ def periodic_box(n: int, seed: int = 12345, mode: str = "zeldovich", rms_disp: f
     N = n ** 3
     return Particles(pos[0], pos[1], pos[2], _f32(np.full(N, 1.0 / N)), _f32(np.full(N, 1.0 / (20.0 * n))),
                      (1.0, 1.0, 1.0), f"periodic_{mode}_{n}^3_seed{seed}")
+
+
+def _periodic_box_large(n: int, seed: int, rms_disp: float) -> Particles:
+    """The same Zel'dovich realisation recipe for boxes of 384^3 and more (BASELINE.json configs[4]: 512^3): threaded
+    FFTs (scipy.fft, all cores), one displacement component in memory at a time, broadcasting instead of meshgrids.
+    (Not bit-identical to the small-box path -- another FFT library -- so the boxes the fixtures use keep theirs.)"""
+    import os
+    import scipy.fft as sfft
+    rng = np.random.default_rng(seed)
+    workers = os.cpu_count() or 1
+    k1 = (np.fft.fftfreq(n, d=1.0 / n) * 2 * np.pi)
+    k3 = (np.fft.rfftfreq(n, d=1.0 / n) * 2 * np.pi)
+    kx, ky, kz = k1[:, None, None], k1[None, :, None], k3[None, None, :]
+    k2 = kx * kx + ky * ky + kz * kz
+    k2[0, 0, 0] = 1.0
+    knyq = np.pi * n
+    dk = rng.normal(size=k2.shape) + 1j * rng.normal(size=k2.shape)
+    dk *= np.where(k2 <= knyq * knyq, k2 ** -1.5, 0.0)  # sqrt(P) / k^2, P ~ k^-2
+    dk[0, 0, 0] = 0.0
+    del k2
+    disp = [sfft.irfftn(1j * kk * dk, s=(n, n, n), axes=(0, 1, 2), workers=workers) for kk in (kx, ky, kz)]
+    del dk
+    norm = rms_disp / n / np.sqrt(sum(float(np.mean(d * d)) for d in disp) / 3.0 + 1e-300)
+    g = (np.arange(n) + 0.5) / n - 0.5
+    pos = []
+    for ax, d in enumerate(disp):
+        d *= norm
+        d += g.reshape([n if a == ax else 1 for a in range(3)])
+        d -= np.floor(d + 0.5)  # wrap into [-0.5, 0.5)
+        q = _f32(d.ravel())
+        q[q >= 0.5] -= 1.0
+        pos.append(q)
+        disp[ax] = None
+    N = n ** 3
+    return Particles(pos[0], pos[1], pos[2], _f32(np.full(N, 1.0 / N)), _f32(np.full(N, 1.0 / (20.0 * n))),
+                     (1.0, 1.0, 1.0), f"periodic_zeldovich_{n}^3_seed{seed}")
 
 
 def plummer(N: int, seed: int = 12345, eps: float = 0.005, rmax: float = 20.0) -> Particles:
