@@ -441,6 +441,12 @@ int drop_early_ewald(gg_context *c) {
     return GG_OK;
 }
 
+// Preconditions of an early Ewald correction for parameters p on the loaded / arriving local domain.
+bool early_ewald_ok(const gg_context *c, const gg_params &p) {
+    return p.bPeriodic && p.bEwald && p.iEwOrder > 0 && p.iEwOrder <= 4 && p.nReps >= 0 && p.nReps <= 3 && c->haveRoot &&
+           !(p.flags & GG_FLAG_WALK_ONLY);
+}
+
 #ifndef GG_EARLY_SLICE
 #define GG_EARLY_SLICE (1 << 20) // particles per slice of the early-Ewald upload (40 MB: ~0.7 ms of PCIe 5, ~1.7 ms of k_ewald)
 #endif
@@ -471,9 +477,7 @@ int upload_domain(gg_context *c, const gg_tree *t, const gg_particles *pp, int n
     // ---- announced periodic + Ewald evaluation (gg_announce): the particles go up FIRST, slice by slice, and every slice's
     //      Ewald correction starts on the side stream as soon as the slice is packed -- the FP64 kernel then runs beside
     //      the copies of the remaining particles and of the tree instead of after them
-    const bool early = local && !onDevice && c->annValid && c->ann.bPeriodic && c->ann.bEwald && c->ann.iEwOrder > 0 &&
-                       c->ann.iEwOrder <= 4 && c->ann.nReps >= 0 && c->ann.nReps <= 3 && c->haveRoot && np > 0 && partBase == 0 &&
-                       !(c->ann.flags & GG_FLAG_WALK_ONLY);
+    const bool early = local && !onDevice && c->annValid && early_ewald_ok(c, c->ann) && np > 0 && partBase == 0;
     if (local && (rc = drop_early_ewald(c))) return rc;
     if (early) {
         if ((rc = gg_ensure(c, c->acc, (size_t)(np + 1) * 3 * sizeof(double)))) return rc;
@@ -621,6 +625,42 @@ int upload_domain(gg_context *c, const gg_tree *t, const gg_particles *pp, int n
 }
 
 } // namespace
+
+// The Ewald correction of the RESIDENT local domain, started on the side stream (gg_exchange calls this first: the FP64
+// kernel then runs beside the pruning kernels, the size all-gather's host round trips, the NCCL transfer and the ingest).
+// gg_gravity picks it up like the one gg_set_local starts for an announced upload.
+int gg_early_ewald(gg_context *c, const gg_params *prm) {
+    if (c->dom.empty() || c->ewValid || c->sunMode || !early_ewald_ok(c, *prm)) return GG_OK;
+    if (c->rootLazy) return GG_OK; // (the root expansion would have to be fetched first: ordinary order)
+    const int np = c->dom[0].nPart;
+    if (np <= 0) return GG_OK;
+    int rc;
+    if ((rc = drop_early_ewald(c))) return rc;
+    if ((rc = gg_ensure(c, c->acc, (size_t)(np + 1) * 3 * sizeof(double)))) return rc;
+    if ((rc = gg_ensure(c, c->pot, (size_t)(np + 1) * sizeof(double)))) return rc;
+    if ((rc = gg_ensure(c, c->nloop, (size_t)(np + 1) * sizeof(int)))) return rc;
+    EwaldKernelArgs ea;
+    CK(cudaEventRecord(c->evPacked, c->st)); // (whatever still reads or writes the result arrays on the main stream)
+    CK(cudaStreamWaitEvent(c->st4, c->evPacked, 0));
+    if ((rc = make_ewald_args(c, prm, ea, c->st4))) return rc;
+    ea.active = c->hActive.empty() ? nullptr : (const int *)c->active.p;
+    ea.first = 0;
+    ea.n = np;
+    CK(cudaMemsetAsync(c->acc.p, 0, (size_t)np * 3 * sizeof(double), c->st4));
+    CK(cudaMemsetAsync(c->pot.p, 0, (size_t)np * sizeof(double), c->st4));
+    CK(cudaEventRecord(c->evEw[0], c->st4));
+    CK(gg_launch_ewald_kernel(ea, c->st4));
+    ++c->nLaunches;
+    CK(cudaEventRecord(c->evEw[1], c->st4));
+    CK(cudaEventRecord(c->evEw[2], c->st4));
+    c->ewPending = true;
+    c->ewValid = true;
+    c->ewPrm = *prm;
+    memcpy(c->ewRoot, c->root, sizeof(c->ewRoot));
+    c->ewNEwh = ea.nEwh;
+    c->ewN = np;
+    return GG_OK;
+}
 
 extern "C" {
 

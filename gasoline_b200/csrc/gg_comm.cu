@@ -275,6 +275,7 @@ int gg_exchange(gg_context *c, const gg_params *prm, const double *bndAll, gg_ex
     if (m->n == 1) return GG_OK;
     int rc;
     const int n = m->n, me = m->rank;
+    if ((rc = gg_early_ewald(c, prm))) return rc; // (beside the exchange; gg_gravity picks it up)
     CK(cudaEventRecord(c->evx[0], c->st));
     // ---- the other domains' root bounds: given by the host (it has them in its top tree) or gathered here
     double bnd[GG_MAX_RANKS][6];

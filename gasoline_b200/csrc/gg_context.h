@@ -102,3 +102,5 @@ int gg_let_export_impl(gg_context *c, int nRemote, const double *bnd, const gg_p
 // ingest one remote domain from device records at src (stream-ordered on c->st; no host synchronisation)
 int gg_ingest_packed(gg_context *c, int id, const int hdr[3], const void *src);
 void gg_comm_release(gg_context *c);
+// start the Ewald correction of the resident local domain on the side stream (no-op unless prm asks for one; gg_api.cu)
+int gg_early_ewald(gg_context *c, const gg_params *prm);

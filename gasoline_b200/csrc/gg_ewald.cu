@@ -87,6 +87,9 @@ __device__ __forceinline__ void meval(int iOrder, const EwaldKernelArgs &A, cons
     az -= dz * ta;
 }
 
+#ifndef GG_EWALD_RSQRT
+#define GG_EWALD_RSQRT 1
+#endif
 #ifndef GG_EWALD_MIN_CTAS
 #define GG_EWALD_MIN_CTAS 5 // 96 registers, 20 warps per SM: 4.21 -> 3.70 ms on the 128^3 box (3 CTAs: 3.79, 6: 4.05)
 #endif
@@ -124,7 +127,13 @@ __global__ void __launch_bounds__(128, GG_EWALD_MIN_CTAS) k_ewald(const EwaldKer
                     g[4] = alphan * (r2 / 11 - 1.0 / 9.0); alphan *= 2 * A.alpha2;
                     g[5] = alphan * (r2 / 13 - 1.0 / 11.0);
                 } else { // ewald.c:118-136
+#if GG_EWALD_RSQRT
+                    // 1/r from the FP64 reciprocal square root (MUFU.RSQ64H + Newton, <= 1 ulp) and r = r2 / r: spares the
+                    // IEEE square root AND the division (together ~45 of the term's ~300 FP64-pipe instructions)
+                    const double dir = rsqrt(r2), r = r2 * dir, dir2 = dir * dir;
+#else
                     double r = sqrt(r2), dir = 1.0 / r, dir2 = dir * dir;
+#endif
                     // erfc(x) = exp(-x^2) erfcx(x): the exponential is needed anyway (ewald.c:121), and the scaled function
                     // is the cheaper one; -erf(x) = erfc(x) - 1 (x > 0.1 here: the series branch took the small radii)
                     const double ex = exp(-r2 * A.alpha2);
