@@ -182,6 +182,17 @@ __global__ void k_pack_parts(int n, const double *x, const double *y, const doub
     if (hsoft) hsoft[i] = h[i];
 }
 
+// gg_gravity_chunked: task index and first particle of each of nChunk + 1 boundaries -- boundary k starts at task
+// k nTasks / nChunk, moved forward to the first pass of a bucket (the passes of one bucket stay in one chunk).
+__global__ void k_chunk_bounds(const Task *tasks, int nTasks, const NodeW *nodes, int nChunk, int nPart, int *out) {
+    const int k = threadIdx.x;
+    if (k > nChunk) return;
+    int t = (int)((long long)k * nTasks / nChunk);
+    while (t < nTasks && tasks[t].pass != 0) ++t;
+    out[2 * k] = t;
+    out[2 * k + 1] = k == 0 ? 0 : (t < nTasks ? nodes[tasks[t].node].pLower : nPart);
+}
+
 // A remote domain arriving in device record layout: copy the walk records with links / particle indices rebased
 // from the owner's numbering (base 0) to this rank's global numbering.
 __global__ void k_rebase_nodes(int n, const NodeW *src, int nodeBase, int partBase, NodeW *dst) {
@@ -785,6 +796,171 @@ int gg_set_local(gg_context *c, int idSelf, const gg_tree *t, const gg_particles
     if (t->bnd) memcpy(c->rootBnd, t->bnd + 6 * (size_t)t->iRoot, sizeof(c->rootBnd));
     if (pp->active) c->hActive.assign(pp->active, pp->active + pp->n); // (the device copy went up with the domain)
     else c->hActive.clear();
+    return GG_OK;
+}
+
+// ---- gg_set_local in slices (see the header).  The staging layout and every kernel are upload_domain's.
+int gg_local_begin(gg_context *c, int idSelf, int nNodes, int iRoot, int nPart, const double *rootBnd, int bActive) {
+    if (!c) return gg_fail(GG_ERR_ARG, "gg_local_begin: null context");
+    if (nNodes < 1 || nPart < 0 || iRoot < 0 || iRoot >= nNodes)
+        return gg_fail(GG_ERR_ARG, "gg_local_begin: nNodes=%d n=%d iRoot=%d", nNodes, nPart, iRoot);
+    CK(cudaSetDevice(c->device));
+    c->dom.clear();
+    c->nTop = 0;
+    c->idSelf = idSelf;
+    c->built = GGBuiltDev{};
+    c->rootLazy = false;
+    c->stateN = 0;
+    gg_context::Sliced &S = c->sl;
+    S = gg_context::Sliced{};
+    int rc;
+    if ((rc = gg_finish_mom(c))) return rc;
+    if ((rc = drop_early_ewald(c))) return rc;
+    const size_t nn = (size_t)nNodes, np = (size_t)nPart;
+    if ((rc = gg_ensure(c, c->raw, (nn * 6 + np * 5) * sizeof(double)))) return rc;
+    if ((rc = gg_ensure(c, c->rawi, nn * 4 * sizeof(int)))) return rc;
+    if ((rc = gg_ensure(c, c->nodes, (nn + GG_MAX_TOP) * sizeof(NodeW)))) return rc;
+    if ((rc = gg_ensure(c, c->momf, (nn + GG_MAX_TOP) * 128))) return rc;
+    if ((rc = gg_ensure(c, c->momq, (nn + GG_MAX_TOP) * 48))) return rc;
+    if ((rc = gg_ensure(c, c->parts, (np + 1) * sizeof(PartS)))) return rc;
+    if ((rc = gg_ensure(c, c->hsoft, (np + 1) * sizeof(double)))) return rc;
+    if ((rc = gg_ensure(c, c->misc, 16 * sizeof(int)))) return rc;
+    if (bActive && (rc = gg_ensure(c, c->active, (np + 1) * sizeof(int)))) return rc;
+    double *d = (double *)c->raw.p;
+    S.dr = d; S.dM = S.dr + 3 * nn; S.dS = S.dM + nn; S.dO = S.dS + nn;
+    S.dx = S.dO + nn; S.dy = S.dx + np; S.dz = S.dy + np; S.dm = S.dz + np; S.dh = S.dm + np;
+    S.di = (int *)c->rawi.p;
+    S.nn = nNodes; S.np = nPart; S.iRoot = iRoot; S.idSelf = idSelf; S.active = bActive != 0;
+    c->haveRootBnd = rootBnd != nullptr;
+    if (rootBnd) memcpy(c->rootBnd, rootBnd, sizeof(c->rootBnd));
+    if (bActive) c->hActive.assign(np, 0);
+    else c->hActive.clear();
+    CK(cudaMemsetAsync((int *)c->misc.p + 8, 0, 2 * sizeof(int), c->st));
+    S.early = c->annValid && early_ewald_ok(c, c->ann) && nPart > 0;
+    if (S.early) {
+        if ((rc = gg_ensure(c, c->acc, (np + 1) * 3 * sizeof(double)))) return rc;
+        if ((rc = gg_ensure(c, c->pot, (np + 1) * sizeof(double)))) return rc;
+        if ((rc = gg_ensure(c, c->nloop, (np + 1) * sizeof(int)))) return rc;
+        CK(cudaEventRecord(c->evPacked, c->st));
+        CK(cudaStreamWaitEvent(c->st4, c->evPacked, 0));
+        if ((rc = make_ewald_args(c, &c->ann, S.ea, c->st4))) return rc;
+        S.ea.active = bActive ? (const int *)c->active.p : nullptr;
+        CK(cudaMemsetAsync(c->acc.p, 0, np * 3 * sizeof(double), c->st4));
+        CK(cudaMemsetAsync(c->pot.p, 0, np * sizeof(double), c->st4));
+        CK(cudaEventRecord(c->evEw[0], c->st4));
+    }
+    S.open = true;
+    return GG_OK;
+}
+
+int gg_local_particles(gg_context *c, int first, int count, const double *x, const double *y, const double *z,
+                       const double *fMass, const double *fSoft, const int *active) {
+    if (!c || !c->sl.open) return gg_fail(GG_ERR_ARG, "gg_local_particles: no gg_local_begin");
+    gg_context::Sliced &S = c->sl;
+    if (count <= 0) return GG_OK;
+    if (first < 0 || first + count > S.np || !x || !y || !z || !fMass || !fSoft || (S.active && !active))
+        return gg_fail(GG_ERR_ARG, "gg_local_particles: slice [%d, %d) of %d particles / null array", first, first + count, S.np);
+    CK(cudaSetDevice(c->device));
+    const size_t lo = (size_t)first, nb = sizeof(double) * (size_t)count;
+    if (S.active) {
+        CK(cudaMemcpyAsync((int *)c->active.p + lo, active, sizeof(int) * (size_t)count, cudaMemcpyHostToDevice, c->st));
+        memcpy(c->hActive.data() + lo, active, sizeof(int) * (size_t)count);
+    }
+    CK(cudaMemcpyAsync(S.dx + lo, x, nb, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(S.dy + lo, y, nb, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(S.dz + lo, z, nb, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(S.dm + lo, fMass, nb, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(S.dh + lo, fSoft, nb, cudaMemcpyHostToDevice, c->st));
+    k_pack_parts<<<(count + 255) / 256, 256, 0, c->st>>>(count, S.dx + lo, S.dy + lo, S.dz + lo, S.dm + lo, S.dh + lo, first,
+                                                         (PartS *)c->parts.p, (double *)c->hsoft.p + lo);
+    CK(cudaGetLastError());
+    ++c->nLaunches;
+    if (S.early) {
+        const size_t k = (size_t)S.nEv++;
+        if (k >= c->evSlice.size()) {
+            cudaEvent_t ev;
+            CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            c->evSlice.push_back(ev);
+        }
+        CK(cudaEventRecord(c->evSlice[k], c->st));
+        CK(cudaStreamWaitEvent(c->st4, c->evSlice[k], 0));
+        S.ea.first = first;
+        S.ea.n = first + count;
+        CK(gg_launch_ewald_kernel(S.ea, c->st4));
+        ++c->nLaunches;
+    }
+    S.gotP += count;
+    return GG_OK;
+}
+
+int gg_local_nodes(gg_context *c, int first, int count, const double *r, const double *fMass, const double *fSoft,
+                   const double *fOpen2, const int *pLower, const int *pUpper, const int *iLower, const int *iUpper) {
+    if (!c || !c->sl.open) return gg_fail(GG_ERR_ARG, "gg_local_nodes: no gg_local_begin");
+    gg_context::Sliced &S = c->sl;
+    if (count <= 0) return GG_OK;
+    if (first < 0 || first + count > S.nn || !r || !fMass || !fSoft || !fOpen2 || !pLower || !pUpper || !iLower || !iUpper)
+        return gg_fail(GG_ERR_ARG, "gg_local_nodes: slice [%d, %d) of %d nodes / null array", first, first + count, S.nn);
+    CK(cudaSetDevice(c->device));
+    const size_t lo = (size_t)first, nn = (size_t)S.nn, nd = sizeof(double) * (size_t)count, ni = sizeof(int) * (size_t)count;
+    CK(cudaMemcpyAsync(S.dr + 3 * lo, r, 3 * nd, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(S.dM + lo, fMass, nd, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(S.dS + lo, fSoft, nd, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(S.dO + lo, fOpen2, nd, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(S.di + lo, pLower, ni, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(S.di + nn + lo, pUpper, ni, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(S.di + 2 * nn + lo, iLower, ni, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(S.di + 3 * nn + lo, iUpper, ni, cudaMemcpyHostToDevice, c->st));
+    S.gotN += count;
+    return GG_OK;
+}
+
+int gg_local_end(gg_context *c) {
+    if (!c || !c->sl.open) return gg_fail(GG_ERR_ARG, "gg_local_end: no gg_local_begin");
+    gg_context::Sliced &S = c->sl;
+    S.open = false;
+    if (S.gotP != S.np || S.gotN != S.nn)
+        return gg_fail(GG_ERR_ARG, "gg_local_end: %d of %d particles and %d of %d nodes arrived", S.gotP, S.np, S.gotN, S.nn);
+    CK(cudaSetDevice(c->device));
+    const int nn = S.nn, np = S.np;
+    int rc;
+    if (S.early) {
+        CK(cudaEventRecord(c->evEw[1], c->st4));
+        CK(cudaEventRecord(c->evEw[2], c->st4));
+        c->ewPending = true;
+        c->ewValid = true;
+        c->ewPrm = c->ann;
+        memcpy(c->ewRoot, c->root, sizeof(c->ewRoot));
+        c->ewNEwh = S.ea.nEwh;
+        c->ewN = np;
+    }
+    // links between cells cross slices (a cell reads its first child's iUpper): the node records are packed once all are here
+    k_pack_nodes<<<(nn + 127) / 128, 128, 0, c->st>>>(nn, S.dr, S.dM, S.dS, S.dO, S.di, S.di + nn, S.di + 2 * (size_t)nn,
+                                                      S.di + 3 * (size_t)nn, 0, 0, (NodeW *)c->nodes.p, np, (int *)c->misc.p + 8);
+    CK(cudaGetLastError());
+    ++c->nLaunches;
+    if ((rc = gg_ensure(c, c->momraw, (size_t)nn * 32 * sizeof(double)))) return rc;
+    if ((rc = gg_ensure(c, c->mparent, (size_t)nn * 2 * sizeof(int)))) return rc;
+    CK(cudaEventRecord(c->evPacked, c->st));
+    CK(cudaStreamWaitEvent(c->st2, c->evPacked, 0));
+    CK(gg_launch_device_moments(nn, (const NodeW *)c->nodes.p, 0, 0, S.iRoot, S.dx, S.dy, S.dz, S.dm, (int *)c->mparent.p,
+                                (int *)c->mparent.p + nn, (double *)c->momraw.p, (float4 *)c->momf.p, (double *)c->momq.p, c->st2));
+    c->nLaunches += 2;
+    CK(cudaEventRecord(c->evMom, c->st2));
+    c->momPending = true;
+    int hChk[2] = {0, 0}, hCounts[2] = {0, 0};
+    c->nPartUpload = np;
+    if ((rc = build_task_list(c, nn, S.active ? (const int *)c->active.p : nullptr, hCounts))) return rc;
+    CK(cudaMemcpyAsync(hChk, (int *)c->misc.p + 8, sizeof(hChk), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    if (hChk[1]) return gg_fail(GG_ERR_ARG, "gg_local_end: %d bucket(s) span particles outside [0,%d)", hChk[1], np);
+    if (hChk[0] > GG_MAX_BUCKET)
+        return gg_fail(GG_ERR_UNSUPPORTED, "gg_local_end: a bucket holds %d particles (limit GG_MAX_BUCKET=%d)", hChk[0], GG_MAX_BUCKET);
+    c->maxBucket = hChk[0] > 1 ? hChk[0] : 1;
+    c->nTasksLocal = hCounts[0];
+    c->nBucketsLocal = hCounts[1];
+    c->dom.push_back(Domain{S.idSelf, nn, np, S.iRoot, 0, 0});
+    c->nNodesAll = nn;
+    c->nPartAll = np;
     return GG_OK;
 }
 
@@ -1950,6 +2126,9 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
     if (nTasks > 0) ++c->nLaunches;
     bool evalTimed = false, evalQueued = false, fastLists = false;
     long long nListEntries = 0, capListEntries = 0;
+    int nCh = 1, hBounds[2 * 66];
+    ta.taskBegin = 0;
+    ta.taskEnd = nTasks;
     if (nTasks > 0 && !walkOnly) {
         // per-bucket list offsets = exclusive scan of the entry counts the walk left; the total sizes the list array
         size_t tmpBytes = 0;
@@ -1962,7 +2141,16 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
         // numbers after the evaluation and re-runs with larger buffers if not.  The first evaluation of a context (no size
         // known) and every re-run read the sizes back between the walk and the scatter (GG_SYNC_WALK=1 forces that).
         static const bool syncWalk = getenv("GG_SYNC_WALK") != nullptr && atoi(getenv("GG_SYNC_WALK")) != 0;
-        fastLists = depth == 0 && !syncWalk && c->lists.cap >= 64 * sizeof(unsigned);
+        // gg_gravity_chunked: the evaluation in nCh launches; the callbacks may only see final results, so this order reads
+        // the walk's sizes back first (a failed k_guard would leave a chunk unwritten)
+        if (c->chunkFn && c->nChunk > 1 && c->zc[0] && !singleTask && !c->sunMode && nTasks >= 64 * c->nChunk && c->nChunk <= 64) {
+            nCh = c->nChunk;
+            if ((rc = gg_ensure(c, c->chunkb, 2 * 66 * sizeof(int)))) return rc;
+            k_chunk_bounds<<<1, 96, 0, c->st>>>(ta.tasks, nTasks, (const NodeW *)c->nodes.p, nCh, n, (int *)c->chunkb.p);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(hBounds, c->chunkb.p, sizeof(int) * 2 * (nCh + 1), cudaMemcpyDeviceToHost, c->st));
+        }
+        fastLists = depth == 0 && !syncWalk && nCh == 1 && c->lists.cap >= 64 * sizeof(unsigned);
         if (fastLists) {
             capListEntries = (long long)(c->lists.cap / sizeof(unsigned)) - 32;
             ta.okFlag = (const int *)c->misc.p + 4;
@@ -1988,7 +2176,26 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
         CK(gg_launch_scatter_kernel(ta, c->nSM, c->st));
         if (c->momPending) CK(cudaStreamWaitEvent(c->st, c->evMom, 0)); // the moments arrive on the second stream
         CK(cudaEventRecord(c->ev[6], c->st));
-        CK(gg_launch_eval_kernel(ta, c->nSM, c->st));
+        if (nCh == 1) CK(gg_launch_eval_kernel(ta, c->nSM, c->st));
+        else {
+            while ((int)c->evChunk.size() < nCh) {
+                cudaEvent_t ev;
+                CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming | cudaEventBlockingSync));
+                c->evChunk.push_back(ev);
+            }
+            for (int k = 0; k < nCh; ++k) {
+                if (k > 0) CK(cudaMemsetAsync(ta.taskCounter + 2, 0, sizeof(int), c->st)); // (every launch counts from its own begin)
+                ta.taskBegin = hBounds[2 * k];
+                ta.taskEnd = hBounds[2 * k + 2];
+                if (ta.taskEnd > ta.taskBegin) {
+                    CK(gg_launch_eval_kernel(ta, c->nSM, c->st));
+                    ++c->nLaunches;
+                }
+                CK(cudaEventRecord(c->evChunk[k], c->st));
+            }
+            ta.taskBegin = 0;
+            ta.taskEnd = nTasks;
+        }
         evalQueued = true;
         evalTimed = true;
         c->nLaunches += 4;
@@ -1997,6 +2204,15 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
 
     CK(cudaStreamWaitEvent(c->st, c->evStats, 0));
     CK(cudaEventRecord(c->ev[4], c->st));
+    if (nCh > 1) { // hand the finished ranges to the caller while the later ones are still being evaluated
+        CK(cudaEventSynchronize(c->evStats)); // (fWeight is delivered by k_stats's stream)
+        for (int k = 0; k < nCh; ++k) {
+            CK(cudaEventSynchronize(c->evChunk[k]));
+            const int p0 = hBounds[2 * k + 1], p1 = k + 1 < nCh ? hBounds[2 * k + 3] : n;
+            if (p1 > p0) c->chunkFn(c->chunkUser, p0, p1 - p0);
+        }
+        c->chunkFn = nullptr; // delivered: gg_gravity_chunked does not call again
+    }
 
     unsigned long long hs[16];
     int hm[16];
@@ -2105,6 +2321,22 @@ int run_sun(gg_context *c, const gg_params *prm, gg_stats *stats) {
 } // namespace
 
 extern "C" {
+
+int gg_gravity_chunked(gg_context *c, const gg_params *prm, double *a, double *fPot, double *dtGrav, double *fWeight,
+                       gg_stats *stats, int nChunks, gg_chunk_fn onChunk, void *user) {
+    if (!c || !prm) return gg_fail(GG_ERR_ARG, "gg_gravity_chunked: null argument");
+    c->nChunk = nChunks > 64 ? 64 : nChunks;
+    c->chunkFn = onChunk;
+    c->chunkUser = user;
+    const int rc = gg_gravity(c, prm, a, fPot, dtGrav, fWeight, stats);
+    const bool pending = c->chunkFn != nullptr; // not delivered in pieces: one call for everything
+    c->chunkFn = nullptr;
+    c->nChunk = 1;
+    if (rc == GG_OK && pending && onChunk && !c->dom.empty() && c->dom[0].nPart > 0 &&
+        !(prm->flags & (GG_FLAG_NO_DOWNLOAD | GG_FLAG_WALK_ONLY)))
+        onChunk(user, 0, c->dom[0].nPart);
+    return rc;
+}
 
 int gg_gravity(gg_context *c, const gg_params *prm, double *a, double *fPot, double *dtGrav, double *fWeight,
                gg_stats *stats) {

@@ -79,6 +79,21 @@ struct gg_context {
     gg_params ewPrm;
     double ewRoot[GG_NROOT];
     int ewNEwh = 0, ewN = 0;
+    // gg_gravity_chunked: the list evaluation in nChunk launches over consecutive task ranges, the caller told as each lands
+    int nChunk = 1;
+    void (*chunkFn)(void *, int, int) = nullptr;
+    void *chunkUser = nullptr;
+    std::vector<cudaEvent_t> evChunk;
+    DevBuf chunkb;
+    // gg_local_begin .. gg_local_end: the local domain arriving in slices
+    struct Sliced {
+        bool open = false, early = false, active = false;
+        int nn = 0, np = 0, iRoot = 0, idSelf = 0, gotP = 0, gotN = 0, nEv = 0;
+        double *dr = nullptr, *dM = nullptr, *dS = nullptr, *dO = nullptr, *dx = nullptr, *dy = nullptr, *dz = nullptr,
+               *dm = nullptr, *dh = nullptr;
+        int *di = nullptr;
+        EwaldKernelArgs ea;
+    } sl;
 };
 
 // error reporting: formats into the calling thread's message buffer (gg_last_error), prints it, returns code

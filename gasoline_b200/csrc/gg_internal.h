@@ -138,6 +138,7 @@ struct TreeKernelArgs {
     double *dtg;
     int *counts;             // [nLocalNodes][3]
     int *errFlag;
+    int taskBegin, taskEnd;  // k_eval: this launch evaluates tasks [taskBegin, taskEnd) (the whole list unless gg_gravity_chunked)
     const int *okFlag;       // non-null: k_scatter / k_eval run only if *okFlag != 0 (k_guard: the walk's output fits the
                              // buffers they were launched with -- no host round trip between the walk and the evaluation)
     // zero-copy result delivery: the caller's a / fPot / dtGrav arrays when they are mapped pinned host memory (device

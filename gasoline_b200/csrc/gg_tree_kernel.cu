@@ -978,9 +978,9 @@ __global__ void __launch_bounds__(GG_WARPS_PER_CTA * 32, MONO64 ? GG_MONO_MIN_CT
 
     for (;;) {
         int t = 0;
-        if (lane == 0) t = atomicAdd(A.taskCounter + 2, 1);
+        if (lane == 0) t = A.taskBegin + atomicAdd(A.taskCounter + 2, 1);
         t = __shfl_sync(FULL, t, 0);
-        if (t >= A.nTasks) break;
+        if (t >= A.taskEnd) break;
         const Task task = A.tasks[t];
         const NodeW bk = load_node(&A.nodes[task.node]);
         double box[6], fSoftMax;
@@ -1148,7 +1148,7 @@ cudaError_t gg_launch_eval_kernel(const TreeKernelArgs &a, int nSM, cudaStream_t
     const size_t smem = gg_eval_kernel_smem(a.mono64, a.nImages);
     cudaError_t e = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const int grid = grid_for((const void *)fn, GG_WARPS_PER_CTA * 32, smem, nSM, GG_WARPS_PER_CTA, a.nTasks, &e);
+    const int grid = grid_for((const void *)fn, GG_WARPS_PER_CTA * 32, smem, nSM, GG_WARPS_PER_CTA, a.taskEnd - a.taskBegin, &e);
     if (e != cudaSuccess) return e;
     fn<<<grid, GG_WARPS_PER_CTA * 32, smem, st>>>(a);
     return cudaGetLastError();

@@ -127,6 +127,22 @@ static void parallel_for(size_t n, void (*fn)(void *, size_t, size_t), void *arg
         if (th[t]) pthread_join(th[t], NULL);
 }
 
+/* the same over [lo, hi) */
+typedef struct {
+    void (*fn)(void *, size_t, size_t);
+    void *arg;
+    size_t base;
+} SHIFT;
+static void shifted(void *arg, size_t lo, size_t hi) {
+    SHIFT *h = (SHIFT *)arg;
+    h->fn(h->arg, h->base + lo, h->base + hi);
+}
+static void parallel_range(size_t lo, size_t hi, void (*fn)(void *, size_t, size_t), void *arg) {
+    SHIFT h;
+    h.fn = fn; h.arg = arg; h.base = lo;
+    if (hi > lo) parallel_for(hi - lo, shifted, &h);
+}
+
 typedef struct {
     PKD pkd;
     SHIM *s;
@@ -194,6 +210,10 @@ static void write_back(void *arg, size_t lo, size_t hi) {
         if (s->dt[i] > p->dtGrav) p->dtGrav = s->dt[i];
         p->fWeight = s->w[i];
     }
+}
+
+static void write_back_chunk(void *arg, int first, int count) {
+    parallel_range((size_t)first, (size_t)first + (size_t)count, write_back, arg);
 }
 
 /* GG_SHIM_TRACE=1: phase timings of the two entry points on stderr */
@@ -405,6 +425,29 @@ void pkdGravAll(PKD pkd, int nReps, int bPeriodic, int iOrder, int bEwald, int i
     if (bResident) {
         parallel_for((size_t)n, flatten_active, &pass);
         if (gg_set_active(s->ctx, s->active) != GG_OK) die("gg_set_active");
+    } else if (!pass.bMom && !(getenv("GG_SHIM_SLICED") && !atoi(getenv("GG_SHIM_SLICED")))) {
+        /* flatten and hand over in slices: while these threads flatten slice k + 1 the copy engine moves slice k, and the
+         * Ewald correction of the slices that have landed already runs (GG_SHIM_SLICED=0: everything in one piece) */
+        const size_t SLP = (size_t)1 << 19, SLN = (size_t)1 << 18;
+        const KDN *root = &pkd->kdNodes[pkd->iRoot];
+        double rb[6];
+        size_t lo;
+        for (j = 0; j < 3; ++j) { rb[j] = root->bnd.fMin[j]; rb[3 + j] = root->bnd.fMax[j]; }
+        if (gg_local_begin(s->ctx, pkd->idSelf, nNodes, pkd->iRoot, n, rb, 1) != GG_OK) die("gg_local_begin");
+        for (lo = 0; lo < (size_t)n; lo += SLP) {
+            const size_t hi = lo + SLP < (size_t)n ? lo + SLP : (size_t)n;
+            parallel_range(lo, hi, flatten_particles, &pass);
+            if (gg_local_particles(s->ctx, (int)lo, (int)(hi - lo), s->x + lo, s->y + lo, s->z + lo, s->m + lo, s->h + lo,
+                                   s->active + lo) != GG_OK) die("gg_local_particles");
+        }
+        for (lo = 0; lo < (size_t)nNodes; lo += SLN) {
+            const size_t hi = lo + SLN < (size_t)nNodes ? lo + SLN : (size_t)nNodes;
+            parallel_range(lo, hi, flatten_nodes, &pass);
+            if (gg_local_nodes(s->ctx, (int)lo, (int)(hi - lo), s->r + 3 * lo, s->fMass + lo, s->fSoft + lo, s->fOpen2 + lo,
+                               s->pLower + lo, s->pUpper + lo, s->iLower + lo, s->iUpper + lo) != GG_OK) die("gg_local_nodes");
+        }
+        if (gg_local_end(s->ctx) != GG_OK) die("gg_local_end");
+        s->builtNodes = NULL;
     } else {
         parallel_for((size_t)nNodes, flatten_nodes, &pass);
         parallel_for((size_t)n, flatten_particles, &pass);
@@ -422,9 +465,15 @@ void pkdGravAll(PKD pkd, int nReps, int bPeriodic, int iOrder, int bEwald, int i
         shim_top(pkd, s, bndAll);
         if (gg_exchange(s->ctx, &prm, bndAll, NULL) != GG_OK) die("gg_exchange");
     }
-    prm.accumulate = 0; /* this call's contribution, delivered zero-copy into the pinned arrays; merged below */
-    if (gg_gravity(s->ctx, &prm, s->a, s->pot, s->dt, s->w, &st) != GG_OK) die("gg_gravity");
-    parallel_for((size_t)n, write_back, &pass);
+    prm.accumulate = 0; /* this call's contribution, delivered zero-copy into the pinned arrays; merged by write_back */
+    {
+        /* the evaluation in GG_SHIM_CHUNKS pieces (default 8): the += pass over the 184-byte PARTICLE records of a finished
+         * range runs on the host's cores while the GPU evaluates the next range */
+        const char *e = getenv("GG_SHIM_CHUNKS");
+        const int nChunks = e ? atoi(e) : 8;
+        if (gg_gravity_chunked(s->ctx, &prm, s->a, s->pot, s->dt, s->w, &st, nChunks < 1 ? 1 : nChunks, write_back_chunk, &pass) != GG_OK)
+            die("gg_gravity");
+    }
     pkdStopTimer(pkd, 2);
     *nActive = st.nActive;
     *pdPartSum = st.dPartSum; *pdCellSum = st.dCellSum; *pdSoftSum = st.dSoftSum; *pdFlop = st.dFlop;

@@ -88,6 +88,10 @@ def load_library(path: str | None = None):
     L.gg_set_top.argtypes = [C.c_void_p, C.c_int, _ip, _ip, _dp, _dp, _dp, _dp, _dp]
     L.gg_set_root_moments.argtypes = [C.c_void_p, _dp]
     L.gg_announce.argtypes = [C.c_void_p, C.c_void_p]
+    L.gg_local_begin.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_int]
+    L.gg_local_particles.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6
+    L.gg_local_nodes.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 8
+    L.gg_local_end.argtypes = [C.c_void_p]
     L.gg_gravity.argtypes = [C.c_void_p, C.POINTER(gg_params), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                              C.POINTER(gg_stats)]
     L.gg_bucket_counts.argtypes = [C.c_void_p, C.c_void_p]
@@ -520,6 +524,39 @@ class PKD:
         self.iOrderMap = np.arange(self.nLocal, dtype=np.int32) if iOrderMap is None else np.asarray(iOrderMap, np.int32)
         self._uploaded = False
 
+    def upload_sliced(self, nSlices: int = 4, announce: "GravityParams | None" = None):
+        """The same ingest in slices (gg_local_begin / gg_local_particles / gg_local_nodes / gg_local_end): what a host
+        that has to flatten AoS records first does (the pkdGravAll shim).  Moments are formed on the device."""
+        if self.tree is None:
+            raise GasolineB200Error("upload_sliced: build or set a tree first")
+        t, n, nn = self.tree, self.nLocal, self.tree.nNodes
+        if self.ilcnRoot is not None:
+            _check(self._L.gg_set_root_moments(self._ctx, _d(self.ilcnRoot)), "gg_set_root_moments")
+        if announce is not None:
+            prm = self._params(announce, 0, 0)
+            _check(self._L.gg_announce(self._ctx, C.byref(prm)), "gg_announce")
+        try:
+            bnd = np.ascontiguousarray(t.bnd.reshape(-1, 6)[t.iRoot]) if t.bnd is not None and t.bnd.size else None
+            _check(self._L.gg_local_begin(self._ctx, self.idSelf, nn, t.iRoot, n, _d(bnd) if bnd is not None else None,
+                                          1 if self.active is not None else 0), "gg_local_begin")
+            off = lambda a, lo, k=1: C.c_void_p(int(a.ctypes.data) + int(a.itemsize) * int(lo) * k)
+            cuts = np.linspace(0, n, nSlices + 1).astype(int)
+            for lo, hi in reversed(list(zip(cuts[:-1], cuts[1:]))):  # (any order)
+                _check(self._L.gg_local_particles(self._ctx, int(lo), int(hi - lo), off(self.x, lo), off(self.y, lo),
+                                                  off(self.z, lo), off(self.fMass, lo), off(self.fSoft, lo),
+                                                  off(self.active, lo) if self.active is not None else None),
+                       "gg_local_particles")
+            cuts = np.linspace(0, nn, nSlices + 1).astype(int)
+            for lo, hi in zip(cuts[:-1], cuts[1:]):
+                _check(self._L.gg_local_nodes(self._ctx, int(lo), int(hi - lo), off(t.r, lo, 3), off(t.fMass, lo),
+                                              off(t.fSoft, lo), off(t.fOpen2, lo), off(t.pLower, lo), off(t.pUpper, lo),
+                                              off(t.iLower, lo), off(t.iUpper, lo)), "gg_local_nodes")
+            _check(self._L.gg_local_end(self._ctx), "gg_local_end")
+        finally:
+            if announce is not None:
+                _check(self._L.gg_announce(self._ctx, None), "gg_announce")
+        self._uploaded = True
+
     def upload(self, announce: "GravityParams | None" = None):
         """Ingest pStore + kdNodes into HBM (gg_set_local); also pkd->ilcnRoot when present.  announce = the parameters
         of the pkdGravAll that follows (gg_announce): with Ewald on, the correction then starts while the domain is
@@ -651,6 +688,31 @@ class PKD:
         self.stats = {k: (np.array(st.aSun[:]) if k == "aSun" else getattr(st, k)) for k, _ in gg_stats._fields_}
         out = dict(self.stats)
         out.update(acc=a, pot=fPot, dtGrav=dtGrav, fWeight=fWeight)
+        return out
+
+    def pkdGravAllChunked(self, g: GravityParams, a, fPot, dtGrav, fWeight, nChunks: int, on_chunk=None):
+        """gg_gravity_chunked: pkdGravAll in overwrite mode into mapped pinned arrays, the list evaluation in nChunks
+        launches; on_chunk(first, count) is called as each particle range becomes final.  Returns the stats dict plus
+        `chunks` = [(first, count), ...] in call order."""
+        if not getattr(self, "_uploaded", False) and not getattr(self, "_resident", False):
+            self.upload()
+        prm = self._params(g, 0, 0)
+        st = gg_stats()
+        seen = []
+
+        def cb(user, first, count):
+            seen.append((int(first), int(count)))
+            if on_chunk is not None:
+                on_chunk(int(first), int(count))
+
+        fn = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int)(cb)
+        ptr = lambda v: v.ctypes.data_as(C.c_void_p)
+        self._L.gg_gravity_chunked.argtypes = [C.c_void_p, C.POINTER(gg_params)] + [C.c_void_p] * 4 + \
+                                             [C.POINTER(gg_stats), C.c_int, C.c_void_p, C.c_void_p]
+        _check(self._L.gg_gravity_chunked(self._ctx, C.byref(prm), ptr(a), ptr(fPot), ptr(dtGrav), ptr(fWeight), C.byref(st),
+                                          int(nChunks), C.cast(fn, C.c_void_p), None), "gg_gravity_chunked")
+        out = {k: (np.array(st.aSun[:]) if k == "aSun" else getattr(st, k)) for k, _ in gg_stats._fields_}
+        out.update(acc=a, pot=fPot, dtGrav=dtGrav, fWeight=fWeight, chunks=seen)
         return out
 
     def upload_bytes(self) -> int:

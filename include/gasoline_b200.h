@@ -220,6 +220,22 @@ int gg_comm_info(gg_context *ctx, int *pRank, int *pnRanks, int *pTransport, int
 int gg_comm_allgather(gg_context *ctx, const void *mine, size_t bytes, void *all);
 int gg_exchange(gg_context *ctx, const gg_params *prm, const double *bndAll, gg_exchange_stats *stats);
 
+/*
+ * gg_set_local in SLICES, for hosts whose tree and particles are not SoA arrays to begin with (pkd->kdNodes is an array of
+ * 536-byte KDN, pkd->pStore of 184-byte PARTICLE: the shim has to flatten them): while the host flattens slice k + 1 the
+ * copy engine already moves slice k, and with an announced Ewald evaluation (gg_announce) the correction of slice k runs
+ * on the side stream.  Pointers are to the slice's first element (pinned host memory, valid until gg_local_end returns);
+ * slices may arrive in any order but must cover [0, nPart) and [0, nNodes) exactly once.  The cells' moments are formed on
+ * the device (as with gg_tree.mom == NULL).  rootBnd = (fMin[3], fMax[3]) of the root cell or NULL (see gg_exchange);
+ * active == NULL in every slice = all particles are sinks.  Same result as gg_set_local, to the bit.
+ */
+int gg_local_begin(gg_context *ctx, int idSelf, int nNodes, int iRoot, int nPart, const double *rootBnd, int bActive);
+int gg_local_particles(gg_context *ctx, int first, int count, const double *x, const double *y, const double *z,
+                       const double *fMass, const double *fSoft, const int *active);
+int gg_local_nodes(gg_context *ctx, int first, int count, const double *r, const double *fMass, const double *fSoft,
+                   const double *fOpen2, const int *pLower, const int *pUpper, const int *iLower, const int *iUpper);
+int gg_local_end(gg_context *ctx);
+
 /* pkd->ilcnRoot (pkdCalcRoot/pkdDistribRoot, pkd.c:4395-4493): complete l<=4 moments of the whole box for Ewald. */
 int gg_set_root_moments(gg_context *ctx, const double root[GG_NROOT]);
 
@@ -243,6 +259,20 @@ int gg_announce(gg_context *ctx, const gg_params *prm);
  */
 int gg_gravity(gg_context *ctx, const gg_params *prm, double *a, double *fPot, double *dtGrav, double *fWeight,
                gg_stats *stats);
+
+/*
+ * gg_gravity with the results handed over in pieces.  The list evaluation runs as nChunks launches over consecutive ranges
+ * of sink buckets (tree order); as soon as a range has finished -- while the GPU evaluates the next one -- onChunk(user,
+ * first, count) is called on the calling thread: a[3 i], fPot[i], dtGrav[i], fWeight[i] of the ACTIVE particles
+ * first <= i < first + count are final.  The ranges are disjoint and cover [0, nLocal) in ascending order.  For hosts that
+ * must fold the results into records of their own (pkdGravAll's in-place += on pStore, grav.c:192-195): that memory-bound
+ * pass then runs beside the evaluation instead of after it.  Needs overwrite mode (prm->accumulate == 0) and output arrays
+ * in mapped pinned memory (gg_host_alloc); otherwise, and for small task lists, it is gg_gravity followed by ONE callback
+ * for [0, nLocal).  Results are those of gg_gravity, bit for bit (same kernels, same lists).
+ */
+typedef void (*gg_chunk_fn)(void *user, int first, int count);
+int gg_gravity_chunked(gg_context *ctx, const gg_params *prm, double *a, double *fPot, double *dtGrav, double *fWeight,
+                       gg_stats *stats, int nChunks, gg_chunk_fn onChunk, void *user);
 
 /* After gg_gravity: per-node (nPart, nCellSoft, nCellNewt) of the local tree, -1 where the node is not a bucket
  * with an active sink -- the counters pkdBucketWalk leaves in pkd->nPart/nCellSoft/nCellNewt (walk.c:175-177). */

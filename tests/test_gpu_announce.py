@@ -85,3 +85,46 @@ def test_announced_upload_in_slices(gpu_lib):
     print(f"128^3: Ewald {ref['msEwald']:.2f} ms in the ordinary order, {out['msEwald']:.2f} ms beside the upload; "
           f"device total {ref['msTotal']:.2f} -> {out['msTotal']:.2f} ms")
     k.close()
+
+
+@pytest.mark.parametrize("case", ["plummer", "periodic_ewald", "periodic_ewald_active"])
+def test_sliced_upload_equals_gg_set_local(case, gpu_lib):
+    """gg_local_begin / _particles / _nodes / _end (slices in any order; early Ewald per slice when announced) load the very
+    domain gg_set_local loads: every result bit for bit."""
+    if case == "plummer":
+        p, g, active = ics.plummer(30000, seed=5), GravityParams(nReps=0, bPeriodic=0, bEwald=0), None
+    else:
+        p, g = ics.periodic_box(24, seed=4), GravityParams(nReps=1, bPeriodic=1, bEwald=1)
+        active = (np.random.default_rng(8).random(p.n) < 0.6).astype(np.int32) if case.endswith("active") else None
+    k = _pkd(p, active)
+    k.device_moments = True
+    k.upload()
+    ref = k.pkdGravAll(g)
+    counts = k.pkdBucketCounts()
+    for nSlices, ann in ((1, None), (5, None), (3, g)):
+        k.upload_sliced(nSlices, announce=ann)
+        out = k.pkdGravAll(g)
+        for nm in KEYS:
+            assert np.array_equal(out[nm], ref[nm]), (nm, nSlices)
+        assert np.array_equal(k.pkdBucketCounts(), counts)
+        for nm in ("nActive", "dPartSum", "dCellSum", "dSoftSum", "dFlop"):
+            assert out[nm] == ref[nm], nm
+    k.close()
+
+
+def test_sliced_upload_argument_checks(gpu_lib):
+    import ctypes as C
+    from gasoline_b200.pkd import GasolineB200Error
+    p = ics.plummer(2000, seed=1)
+    k = _pkd(p)
+    L, ctx = k._L, k._ctx
+    assert L.gg_local_end(ctx) != 0  # nothing begun
+    assert L.gg_local_begin(ctx, 0, k.tree.nNodes, k.tree.iRoot, k.nLocal, None, 0) == 0
+    assert L.gg_local_particles(ctx, 10, k.nLocal, *([C.c_void_p(k.x.ctypes.data)] * 5), None) != 0  # runs past the end
+    assert L.gg_local_end(ctx) != 0  # incomplete
+    with pytest.raises(GasolineB200Error):
+        k._uploaded = True
+        k.pkdGravAll(GravityParams(nReps=0, bPeriodic=0, bEwald=0))  # no domain loaded after the failed sequence
+    k.upload()
+    assert k.pkdGravAll(GravityParams(nReps=0, bPeriodic=0, bEwald=0))["nActive"] == p.n
+    k.close()

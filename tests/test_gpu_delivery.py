@@ -84,3 +84,43 @@ def test_set_active_equals_fresh_upload(gpu_lib):
     again = a.pkdGravAll(g)
     assert np.array_equal(again["acc"], full["acc"]) and again["nActive"] == p.n
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("name,frac", [("plummer20k", 1.0), ("periodic16_ewald", 1.0), ("plummer20k", 0.5)])
+def test_chunked_evaluation_hands_over_final_ranges(name, frac, gpu_lib):
+    """gg_gravity_chunked: the list evaluation in several launches; every callback's particle range is final at the time
+    of the call (copied there and compared with the one-launch result), the ranges are disjoint, ascending and cover all
+    particles; the totals are gg_gravity's."""
+    mk, g = CASES[name]
+    p = mk()
+    active = None if frac == 1.0 else (np.random.default_rng(2).random(p.n) < frac).astype(np.int32)
+    pkd = PKD(fPeriod=p.period, pinned=True)
+    pkd.pkdLoadParticles(p.x, p.y, p.z, p.m, p.h, active)
+    pkd.pkdBuildBinary(8, 0.7, 4)
+    n = pkd.nLocal
+    ref = pkd.pkdGravAll(g)
+    act = np.ones(n, bool) if pkd.active is None else pkd.active.astype(bool)
+    pin = [pinned_empty((n, 3)), pinned_empty(n), pinned_empty(n), pinned_empty(n)]
+    for v in pin:
+        v[...] = np.nan
+    snap = {}
+
+    def on_chunk(first, count):
+        snap[first] = [v[first:first + count].copy() for v in pin]
+
+    out = pkd.pkdGravAllChunked(g, *pin, nChunks=6, on_chunk=on_chunk)
+    ch = out["chunks"]
+    assert len(ch) > 1 and ch[0][0] == 0 and sum(c for _, c in ch) == n
+    assert all(ch[i][0] + ch[i][1] == ch[i + 1][0] for i in range(len(ch) - 1))
+    for first, count in ch:
+        a = act[first:first + count]
+        for nm, v in zip(("acc", "pot", "dtGrav", "fWeight"), snap[first]):
+            assert np.array_equal(v[a], ref[nm][first:first + count][a]), (nm, first)
+    for nm in ("nActive", "dPartSum", "dCellSum", "dSoftSum", "dFlop"):
+        assert out[nm] == ref[nm], nm
+    # too few tasks / no callback: one call for everything, same numbers
+    small = pkd.pkdGravAllChunked(g, *pin, nChunks=64)
+    assert small["chunks"] == [(0, n)]
+    for nm, v in zip(("acc", "pot", "dtGrav", "fWeight"), pin):
+        assert np.array_equal(v[act], ref[nm][act]), nm
+    pkd.close()
