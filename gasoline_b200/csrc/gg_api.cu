@@ -737,7 +737,7 @@ void gg_destroy(gg_context *c) {
                      &c->boff64, &c->lists, &c->letflag, &c->letfront, &c->letidx, &c->letout, &c->letmisc, &c->momraw,
                      &c->mparent, &c->dbgtask, &c->momout, &c->sx, &c->sy, &c->sz, &c->sm, &c->sh, &c->sact, &c->svel, &c->sid, &c->sdt,
                      &c->svel2, &c->sid2, &c->sdt2, &c->sacc, &c->srhist, &c->ox, &c->oy, &c->oz, &c->ow, &c->ocell,
-                     &c->okeys, &c->ocnt, &c->opart, &c->osums};
+                     &c->okeys, &c->ocnt, &c->opart, &c->osums, &c->obis};
     for (DevBuf *b : all)
         if (b->p) cudaFree(b->p);
     gg_comm_release(c);
@@ -1150,6 +1150,40 @@ int gg_orb_weight(gg_context *c, int nCells, const int *iCell, const int *iDim, 
         nLow[s] = cnt[2 * s]; nHigh[s] = cnt[2 * s + 1];
         fLow[s] = w ? sums[2 * s] : (double)cnt[2 * s];       // fWeight = 1 for every particle (pkd.c:686: read sets it)
         fHigh[s] = w ? sums[2 * s + 1] : (double)cnt[2 * s + 1];
+    }
+    return GG_OK;
+}
+
+int gg_orb_bisect(gg_context *c, int nCells, const int *iCell, const int *iDim, const double *fLow, const double *fUp,
+                  const int *bLive, const double *nLower, const double *nUpper, int bSplitWork, double *fSplit,
+                  int *bHasSplit, int *ittr) {
+    if (!iDim || !fLow || !fUp || !bLive || !nLower || !nUpper || !fSplit || !bHasSplit || !ittr)
+        return gg_fail(GG_ERR_ARG, "gg_orb_bisect: NULL argument");
+    OrbBisect h;
+    memset(&h, 0, sizeof(h));
+    int rc;
+    if ((rc = orb_query("gg_orb_bisect", c, nCells, iCell, iDim, nullptr, h.q))) return rc;
+    for (int s = 0; s < nCells; ++s) {
+        if (!(nLower[s] > 0.0) || !(nUpper[s] > 0.0)) return gg_fail(GG_ERR_ARG, "gg_orb_bisect: cell %d has no ranks on one side", iCell[s]);
+        h.fl[s] = fLow[s]; h.fu[s] = fUp[s];
+        h.fmm[s] = (fLow[s] + fUp[s]) / 2;
+        h.nLower[s] = nLower[s]; h.nUpper[s] = nUpper[s];
+        h.live[s] = bLive[s] ? 1 : 0;
+    }
+    h.splitWork = bSplitWork ? 1 : 0;
+    h.maxIttr = 64; // MAX_ITTR, pst.c:874
+    CK(cudaSetDevice(c->device));
+    if ((rc = gg_ensure(c, c->obis, sizeof(OrbBisect)))) return rc;
+    const double *w = c->orbWeights ? (const double *)c->ow.p : nullptr;
+    CK(gg_launch_orb_bisect((OrbBisect *)c->obis.p, h, c->orbN, orb_pos(c, 0), orb_pos(c, 1), orb_pos(c, 2), w,
+                            (const int *)c->ocell.p, (int *)c->ocnt.p, (double *)c->opart.p, (double *)c->osums.p, c->st));
+    c->nLaunches += 1 + (h.maxIttr + 1) * (w ? 3 : 2);
+    CK(cudaMemcpyAsync(&h, c->obis.p, sizeof(OrbBisect), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    for (int s = 0; s < nCells; ++s) {
+        fSplit[s] = h.q.split[s];
+        bHasSplit[s] = h.hasSplit[s];
+        ittr[s] = h.ittr[s];
     }
     return GG_OK;
 }

@@ -57,7 +57,7 @@ struct gg_context {
     bool stateHasActive = false, stateDirty = true, stateForces = false;
     bool sunMode = false; // run_gravity is evaluating the bDoSun dummy bucket: the particles' results stay as they are
     // ORB domain decomposition services (gg_orb_*): the rank's particles for the decomposition and their PST cell
-    DevBuf ox, oy, oz, ow, ocell, okeys, ocnt, opart, osums;
+    DevBuf ox, oy, oz, ow, ocell, okeys, ocnt, opart, osums, obis;
     int orbN = -1;          // -1: gg_orb_load not called
     bool orbState = false;  // positions are the resident store's (sx, sy, sz)
     bool orbWeights = false;

@@ -231,6 +231,18 @@ struct OrbQuery {
     int dim[GG_ORB_MAX_SLOTS];  // split axis
     double split[GG_ORB_MAX_SLOTS];
 };
+// The root finder of one level of the rank tree with its state on the device (gg_orb_bisect): _pstRootSplit's bisection
+// (pst.c:959-1034) for all cells of the level at once, no host round trip per trial.
+struct OrbBisect {
+    OrbQuery q;                       // the level's cells; q.split = the trial split (fm) of every cell
+    double fl[GG_ORB_MAX_SLOTS], fu[GG_ORB_MAX_SLOTS], fmm[GG_ORB_MAX_SLOTS]; // bracket and its midpoint
+    double nLower[GG_ORB_MAX_SLOTS], nUpper[GG_ORB_MAX_SLOTS];                // ranks below / above the split
+    int ittr[GG_ORB_MAX_SLOTS], live[GG_ORB_MAX_SLOTS];
+    int nLive, splitWork, maxIttr, hasSplit[GG_ORB_MAX_SLOTS];
+};
+// queue the whole bisection on st: B (device) initialised from the host copy h; cnt/part/sums as for gg_launch_orb_weight
+cudaError_t gg_launch_orb_bisect(OrbBisect *B, const OrbBisect &h, int n, const double *x, const double *y, const double *z,
+                                 const double *w, const int *cellOf, int *cnt, double *part, double *sums, cudaStream_t st);
 cudaError_t gg_launch_orb_init(int n, int *cellOf, cudaStream_t st);
 cudaError_t gg_launch_orb_bounds(const OrbQuery &q, int n, const double *x, const double *y, const double *z, const int *cellOf,
                                  unsigned long long *out, int *cnt, cudaStream_t st);

@@ -13,6 +13,10 @@
 // bit by anyone -- with fWeight = 1 (every first decomposition of a run) all sums are exact integers.
 #include "gg_internal.h"
 
+#ifndef GG_ORB_PPT
+#define GG_ORB_PPT 1 // particles per thread in the weighing kernels (4 measured slower: 3.4 -> 4.3 ms per 8-domain decomposition of 1 M)
+#endif
+
 namespace {
 
 __device__ __forceinline__ unsigned long long enc(double v) {
@@ -86,37 +90,51 @@ __global__ void __launch_bounds__(256) k_orb_weight(const OrbQuery Q, int n, con
         for (int k = 0; k < 8; ++k) sW[k][t >> 1][t & 1] = 0.0;
     }
     __syncthreads();
-    const int i = blockIdx.x * 256 + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int mine = -1;
-    bool low = false;
-    double wi = 0.0;
-    if (i < n) {
-        mine = slotOf[cellOf[i]];
-        if (mine >= 0) {
-            const int d = Q.dim[mine];
-            const double c = d == 0 ? x[i] : (d == 1 ? y[i] : z[i]);
-            low = c < Q.split[mine];
-            if (w) wi = w[i];
+    // GG_ORB_PPT particles per thread, a CTA's particles contiguous; the same geometry as k_orb_weight_d, so that the
+    // host-driven and the device-driven bisection add the weights in the same order
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int base = blockIdx.x * (256 * GG_ORB_PPT) + threadIdx.x;
+    int mineA[GG_ORB_PPT];
+    double cA[GG_ORB_PPT], wA[GG_ORB_PPT];
+#pragma unroll
+    for (int u = 0; u < GG_ORB_PPT; ++u) {
+        const int i = base + u * 256;
+        mineA[u] = i < n ? slotOf[cellOf[i]] : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < GG_ORB_PPT; ++u) {
+        const int i = base + u * 256;
+        cA[u] = 0.0; wA[u] = 0.0;
+        if (mineA[u] >= 0) {
+            const int d = Q.dim[mineA[u]];
+            cA[u] = d == 0 ? x[i] : (d == 1 ? y[i] : z[i]);
+            if (w) wA[u] = w[i];
         }
     }
-    unsigned todo = __ballot_sync(0xffffffffu, mine >= 0);
-    while (todo) {
-        const int s = __shfl_sync(0xffffffffu, mine, __ffs(todo) - 1);
-        const bool in = mine == s;
-        const unsigned m = __ballot_sync(0xffffffffu, in), ml = __ballot_sync(0xffffffffu, in && low);
-        todo &= ~m;
-        if (lane == 0) {
-            atomicAdd(&sCnt[s][0], __popc(ml));
-            atomicAdd(&sCnt[s][1], __popc(m & ~ml));
-        }
-        if (w) {
-            double a = in && low ? wi : 0.0, b = in && !low ? wi : 0.0;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                a = __dadd_rn(a, __shfl_xor_sync(0xffffffffu, a, o));
-                b = __dadd_rn(b, __shfl_xor_sync(0xffffffffu, b, o));
+    for (int u = 0; u < GG_ORB_PPT; ++u) {
+        const int mine = mineA[u];
+        const bool low = mine >= 0 && cA[u] < Q.split[mine];
+        const double wi = wA[u];
+        unsigned todo = __ballot_sync(0xffffffffu, mine >= 0);
+        while (todo) {
+            const int s = __shfl_sync(0xffffffffu, mine, __ffs(todo) - 1);
+            const bool in = mine == s;
+            const unsigned m = __ballot_sync(0xffffffffu, in), ml = __ballot_sync(0xffffffffu, in && low);
+            todo &= ~m;
+            if (lane == 0) {
+                atomicAdd(&sCnt[s][0], __popc(ml));
+                atomicAdd(&sCnt[s][1], __popc(m & ~ml));
             }
-            if (lane == 0) { sW[warp][s][0] = a; sW[warp][s][1] = b; }
+            if (w) {
+                double a = in && low ? wi : 0.0, b = in && !low ? wi : 0.0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    a = __dadd_rn(a, __shfl_xor_sync(0xffffffffu, a, o));
+                    b = __dadd_rn(b, __shfl_xor_sync(0xffffffffu, b, o));
+                }
+                if (lane == 0) { sW[warp][s][0] = __dadd_rn(sW[warp][s][0], a); sW[warp][s][1] = __dadd_rn(sW[warp][s][1], b); }
+            }
         }
     }
     __syncthreads();
@@ -161,9 +179,164 @@ __global__ void __launch_bounds__(256) k_orb_split(const OrbQuery Q, int n, cons
     cellOf[i] = 2 * c + (v < Q.split[s] ? 0 : 1); // LOWER / UPPER (pkd.h:78-79)
 }
 
+// ---- the bisection with its state on the device ---------------------------------------------------------------------
+// k_orb_weight with the query read from the device state: cells that are no longer bisected have no slot
+__global__ void __launch_bounds__(256) k_orb_weight_d(const OrbBisect *B, int n, const double *x, const double *y, const double *z,
+                                                      const double *w, const int *cellOf, int *cnt, double *part) {
+    if (B->nLive == 0) return;
+    __shared__ signed char slotOf[GG_ORB_MAX_CELL];
+    __shared__ int sCnt[GG_ORB_MAX_SLOTS][2], sDim[GG_ORB_MAX_SLOTS];
+    __shared__ double sSplit[GG_ORB_MAX_SLOTS];
+    __shared__ double sW[8][GG_ORB_MAX_SLOTS][2];
+    const int nSlots = B->q.nSlots;
+    for (int i = threadIdx.x; i < GG_ORB_MAX_CELL; i += blockDim.x) slotOf[i] = -1;
+    __syncthreads();
+    for (int s = threadIdx.x; s < nSlots; s += blockDim.x) {
+        if (B->live[s]) slotOf[B->q.cell[s]] = (signed char)s;
+        sDim[s] = B->q.dim[s];
+        sSplit[s] = B->q.split[s];
+    }
+    for (int t = threadIdx.x; t < 2 * nSlots; t += 256) {
+        sCnt[t >> 1][t & 1] = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sW[k][t >> 1][t & 1] = 0.0;
+    }
+    __syncthreads();
+    // GG_ORB_PPT particles per thread, a CTA's particles contiguous (the weights' summation order is a function of the
+    // launch geometry only): the cell ids of all of them are loaded first, then the coordinates -- four loads in flight
+    // per thread instead of one (the one-particle kernel is latency-bound: profiles/r01_k_orb_weight.md)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int base = blockIdx.x * (256 * GG_ORB_PPT) + threadIdx.x;
+    int mineA[GG_ORB_PPT];
+    double cA[GG_ORB_PPT], wA[GG_ORB_PPT];
+#pragma unroll
+    for (int u = 0; u < GG_ORB_PPT; ++u) {
+        const int i = base + u * 256;
+        mineA[u] = i < n ? slotOf[cellOf[i]] : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < GG_ORB_PPT; ++u) {
+        const int i = base + u * 256;
+        cA[u] = 0.0; wA[u] = 0.0;
+        if (mineA[u] >= 0) {
+            const int d = sDim[mineA[u]];
+            cA[u] = d == 0 ? x[i] : (d == 1 ? y[i] : z[i]);
+            if (w) wA[u] = w[i];
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < GG_ORB_PPT; ++u) {
+        const int mine = mineA[u];
+        const bool low = mine >= 0 && cA[u] < sSplit[mine];
+        const double wi = wA[u];
+        unsigned todo = __ballot_sync(0xffffffffu, mine >= 0);
+        while (todo) {
+            const int s = __shfl_sync(0xffffffffu, mine, __ffs(todo) - 1);
+            const bool in = mine == s;
+            const unsigned m = __ballot_sync(0xffffffffu, in), ml = __ballot_sync(0xffffffffu, in && low);
+            todo &= ~m;
+            if (lane == 0) {
+                atomicAdd(&sCnt[s][0], __popc(ml));
+                atomicAdd(&sCnt[s][1], __popc(m & ~ml));
+            }
+            if (w) {
+                double a = in && low ? wi : 0.0, b = in && !low ? wi : 0.0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    a = __dadd_rn(a, __shfl_xor_sync(0xffffffffu, a, o));
+                    b = __dadd_rn(b, __shfl_xor_sync(0xffffffffu, b, o));
+                }
+                if (lane == 0) { sW[warp][s][0] = __dadd_rn(sW[warp][s][0], a); sW[warp][s][1] = __dadd_rn(sW[warp][s][1], b); }
+            }
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < 2 * nSlots; t += 256) {
+        const int s = t >> 1, side = t & 1;
+        if (sCnt[s][side]) atomicAdd(&cnt[2 * s + side], sCnt[s][side]);
+        if (w) {
+            double a = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a = __dadd_rn(a, sW[k][s][side]);
+            part[((size_t)blockIdx.x * GG_ORB_MAX_SLOTS + s) * 2 + side] = a;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_orb_weight_sum_d(const OrbBisect *B, int nBlocks, const double *part, double *sums) {
+    const int s = blockIdx.x >> 1, side = blockIdx.x & 1;
+    if (B->nLive == 0 || s >= B->q.nSlots || !B->live[s]) return;
+    __shared__ double sh[256];
+    double a = 0.0;
+    for (int b = threadIdx.x; b < nBlocks; b += 256) a = __dadd_rn(a, part[((size_t)b * GG_ORB_MAX_SLOTS + s) * 2 + side]);
+    sh[threadIdx.x] = a;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] = __dadd_rn(sh[threadIdx.x], sh[threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) sums[2 * s + side] = sh[0];
+}
+
+// One step of the root finder for every cell of the level (one thread per cell): digest the answer to the last trial
+// (pst.c:1001-1030: stop on a one-one split or equal loads, else move the bracket's upper or lower end to the trial),
+// then set up the next one (pst.c:984-999: while the midpoint lies strictly inside the bracket and ittr < MAX_ITTR).
+__global__ void __launch_bounds__(GG_ORB_MAX_SLOTS) k_orb_decide(OrbBisect *B, int *cnt, double *sums, int first, int useW) {
+    __shared__ int nLive;
+    const int s = threadIdx.x;
+    if (s == 0) nLive = 0;
+    __syncthreads();
+    if (!first && B->nLive == 0) return;
+    if (s < B->q.nSlots) {
+        int live = B->live[s];
+        double fl = B->fl[s], fu = B->fu[s], fmm = B->fmm[s];
+        if (!first && live) {
+            const int nLow = cnt[2 * s], nHigh = cnt[2 * s + 1];
+            const double wl = useW ? sums[2 * s] : (double)nLow, wh = useW ? sums[2 * s + 1] : (double)nHigh;
+            const double a = B->splitWork ? __ddiv_rn(wl, B->nLower[s]) : __ddiv_rn((double)nLow, B->nLower[s]);
+            const double b = B->splitWork ? __ddiv_rn(wh, B->nUpper[s]) : __ddiv_rn((double)nHigh, B->nUpper[s]);
+            if ((nLow == 1 && nHigh == 1) || a == b) live = 0;
+            else {
+                if (a > b) fu = B->q.split[s];
+                else fl = B->q.split[s];
+                fmm = __dmul_rn(__dadd_rn(fl, fu), 0.5);
+                B->ittr[s] += 1;
+            }
+        }
+        if (live) live = (fl < fmm) && (fmm < fu) && (B->ittr[s] < B->maxIttr);
+        if (live) {
+            B->q.split[s] = fmm;
+            B->hasSplit[s] = 1;
+            atomicAdd(&nLive, 1);
+        }
+        B->live[s] = live; B->fl[s] = fl; B->fu[s] = fu; B->fmm[s] = fmm;
+        cnt[2 * s] = cnt[2 * s + 1] = 0;
+        if (useW) sums[2 * s] = sums[2 * s + 1] = 0.0;
+    }
+    __syncthreads();
+    if (s == 0) B->nLive = nLive;
+}
+
 inline int blocks_for(int n) { return (n + 255) / 256; }
 
 } // namespace
+
+cudaError_t gg_launch_orb_bisect(OrbBisect *B, const OrbBisect &h, int n, const double *x, const double *y, const double *z,
+                                 const double *w, const int *cellOf, int *cnt, double *part, double *sums, cudaStream_t st) {
+    cudaError_t e = cudaMemcpyAsync(B, &h, sizeof(OrbBisect), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    k_orb_decide<<<1, GG_ORB_MAX_SLOTS, 0, st>>>(B, cnt, sums, 1, w != nullptr);
+    // MAX_ITTR trials at most; once no cell is live the remaining launches return at their first instruction
+    for (int t = 0; t <= h.maxIttr; ++t) {
+        if (n > 0) {
+            const int nb = (n + 256 * GG_ORB_PPT - 1) / (256 * GG_ORB_PPT);
+            k_orb_weight_d<<<nb, 256, 0, st>>>(B, n, x, y, z, w, cellOf, cnt, part);
+            if (w) k_orb_weight_sum_d<<<2 * h.q.nSlots, 256, 0, st>>>(B, nb, part, sums);
+        }
+        k_orb_decide<<<1, GG_ORB_MAX_SLOTS, 0, st>>>(B, cnt, sums, 0, w != nullptr);
+    }
+    return cudaGetLastError();
+}
 
 cudaError_t gg_launch_orb_init(int n, int *cellOf, cudaStream_t st) {
     if (n > 0) k_orb_init<<<blocks_for(n), 256, 0, st>>>(n, cellOf);
@@ -194,8 +367,9 @@ cudaError_t gg_launch_orb_weight(const OrbQuery &q, int n, const double *x, cons
         if (e != cudaSuccess) return e;
     }
     if (n > 0) {
-        k_orb_weight<<<blocks_for(n), 256, 0, st>>>(q, n, x, y, z, w, cellOf, cnt, part);
-        if (w) k_orb_weight_sum<<<2 * q.nSlots, 256, 0, st>>>(q.nSlots, blocks_for(n), part, sums);
+        const int nb = (n + 256 * GG_ORB_PPT - 1) / (256 * GG_ORB_PPT);
+        k_orb_weight<<<nb, 256, 0, st>>>(q, n, x, y, z, w, cellOf, cnt, part);
+        if (w) k_orb_weight_sum<<<2 * q.nSlots, 256, 0, st>>>(q.nSlots, nb, part, sums);
     }
     return cudaGetLastError();
 }

@@ -133,7 +133,7 @@ NEWSPLITDIMCUT = 0.707  # pst.c:1851
 
 
 def pst_domain_decomp(ranks: list, nThreads: int, split_work: bool = True, reduce=None, prev=None,
-                      bDoRootFind: bool = True, bDoSplitDimFind: bool = True):
+                      bDoRootFind: bool = True, bDoSplitDimFind: bool = True, device_bisect: bool | None = None):
     """pstDomainDecomp (pst.c:1854-1935) with _pstRootSplit's root finder (pst.c:959-1034) for hosts that are not
     Gasoline: first-call semantics (bDoRootFind = bDoSplitDimFind = 1, master.c:4176; stores with room, so the
     inactive "wrap" split never moves the boundary).  The per-rank work -- bounds, trial weights, the final split --
@@ -149,8 +149,12 @@ def pst_domain_decomp(ranks: list, nThreads: int, split_work: bool = True, reduc
             the split axis then only changes when another axis beats the old one's extent x NEWSPLITDIMCUT
             (pst.c:1900-1910); bDoSplitDimFind = 0 keeps the axis, bDoRootFind = 0 keeps the old split while it lies
             inside the cell's bounds (pst.c:963; the host sets both to 0 for small active sets, master.c:4210-4222).
+    device_bisect: run each level's root finder on the device (gg_orb_bisect: no host round trip per trial).  Default:
+            whenever ONE context holds all particles (len(ranks) == 1, no reduce) and offers it.  Same splits, bit for bit.
     Returns the interior PST cells as a list of dicts (iCell, iDim, fSplit, bnd, ittr) in level order; the particles'
     destination ranks are leaf_rank(nThreads)[pkd.pkdOrbCells()]."""
+    can = len(ranks) == 1 and reduce is None and hasattr(ranks[0], "pkdOrbBisect")
+    device_bisect = can if device_bisect is None else (device_bisect and can)
     old = {c["iCell"]: (c["iDim"], c["fSplit"]) for c in prev} if prev else {}
     def combine(kind, parts):
         a = parts[0].copy()
@@ -190,6 +194,11 @@ def pst_domain_decomp(ranks: list, nThreads: int, split_work: bool = True, reduc
         # pst.c:963: the root finder runs when asked for, or when the previous split has left the cell's bounds
         live = np.array([bool(bDoRootFind or not (fl[j] <= fm[j] <= fu[j])) for j in range(k)])
         fm[live] = np.nan
+        if device_bisect:
+            fs, has, it = ranks[0].pkdOrbBisect(ic, d, fl, fu, live, nLower, nUpper, split_work)
+            fm[has] = fs[has]
+            ittr[:] = it
+            live[:] = False
         while True:
             live &= (fl < fmm) & (fmm < fu) & (ittr < MAX_ITTR)
             if not live.any():

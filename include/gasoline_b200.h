@@ -433,6 +433,20 @@ int gg_orb_weight(gg_context *ctx, int nCells, const int *iCell, const int *iDim
                   int *nHigh, double *fLow, double *fHigh);
 int gg_orb_split(gg_context *ctx, int nCells, const int *iCell, const int *iDim, const double *fSplit);
 int gg_orb_fetch(gg_context *ctx, int *iCellOfParticle);
+/*
+ * _pstRootSplit's root finder (pst.c:959-1034) for ALL cells of one level of the rank tree with its state on the device:
+ * what a host that owns all particles of the decomposition in one context (one GPU, or the first levels of a larger
+ * run) does instead of up to 64 gg_orb_weight round trips.  Per cell k: split axis iDim[k], bracket [fLow[k], fUp[k]]
+ * (the cell's bounds along that axis), bLive[k] = the bisection runs for this cell (bDoRootFind, or the previous split
+ * has left the bounds), nLower[k] / nUpper[k] = ranks below / above the split, bSplitWork (master.c:964).  Every trial
+ * is one weighing launch (the cells still bisected) and a one-block decide kernel; the launches are queued without a
+ * host synchronisation and return at their first instruction once no cell is live.  Out: fSplit[k] (where bHasSplit[k];
+ * a cell that never got a trial keeps the split the host had for it), ittr[k] as the reference counts them.  Branches,
+ * midpoints and stopping rules are the reference's, so the splits are those of the host-driven loop bit for bit.
+ */
+int gg_orb_bisect(gg_context *ctx, int nCells, const int *iCell, const int *iDim, const double *fLow, const double *fUp,
+                  const int *bLive, const double *nLower, const double *nUpper, int bSplitWork, double *fSplit,
+                  int *bHasSplit, int *ittr);
 
 /* Every cell's reduced multipoles by the algorithm the DEVICE uses when gg_tree.mom is NULL (raw moments of the
  * buckets, children translated to the parent's centre and summed, then reduced as pkdCalcCell defines them), executed

@@ -158,3 +158,70 @@ def test_later_decompositions_on_the_device_match_the_stepping_reference():
                 q.close()
             assert np.array_equal(dest, want), f"{name}: decomposition {k} differs from the reference's"
             prev = cells
+
+
+def test_bisection_on_the_device_equals_the_host_driven_loop():
+    """gg_orb_bisect (the root finder's state on the device, no host round trip per trial) against the host-driven loop over
+    gg_orb_weight: same split axis, split, trial count for every PST cell and the same cell for every particle -- counts
+    mode, integer and non-integer work weights (the weight sums are order-fixed in both), 2-13 ranks, and the later
+    decompositions of a stepping run (prev axis / split kept or re-found)."""
+    import os
+    import sys
+
+    def both(load, nThreads, **kw):
+        res = []
+        for dev in (False, True):
+            k = PKD(device=0)
+            load(k)
+            nodes = domain.pst_domain_decomp([k], nThreads, device_bisect=dev, **kw)
+            res.append((nodes, k.pkdOrbCells().copy()))
+            k.close()
+        (na, ca), (nb, cb) = res
+        assert len(na) == len(nb)
+        for u, v in zip(na, nb):
+            assert (u["iCell"], u["iDim"], u["ittr"]) == (v["iCell"], v["iDim"], v["ittr"]) and u["fSplit"] == v["fSplit"], (u, v)
+        assert np.array_equal(ca, cb)
+        return nb
+
+    p = ics.plummer(30000, seed=3)
+    rng = np.random.default_rng(4)
+    for nThreads in (2, 3, 5, 8, 13):
+        both(lambda k: k.pkdOrbLoad(p.x, p.y, p.z), nThreads)
+        both(lambda k: k.pkdOrbLoad(p.x, p.y, p.z), nThreads, split_work=False)
+    w_int = rng.integers(1, 9, p.n).astype(np.float64)
+    w_real = rng.uniform(0.5, 40.0, p.n)
+    for w in (w_int, w_real):
+        both(lambda k: k.pkdOrbLoad(p.x, p.y, p.z, fWeight=w), 8)
+    q = ics.periodic_box(24)
+    prev = both(lambda k: k.pkdOrbLoad(q.x, q.y, q.z), 6)
+    x2 = q.x + rng.normal(0, 0.01, q.n)
+    for flags in (dict(), dict(bDoRootFind=False), dict(bDoRootFind=False, bDoSplitDimFind=False)):
+        both(lambda k: k.pkdOrbLoad(x2, q.y, q.z, fWeight=rng.uniform(1, 3, q.n) if False else None), 6, prev=prev, **flags)
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden_orbsteps import CASES
+    name = sorted(n for n in CASES if not n.endswith("_overflow"))[0]
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    nThreads, prev = int(z["nThreads"]), None
+    for s in range(int(z["nSteps"]) + 1):
+        pos, want = z[f"s{s}_pos"], z[f"s{s}_rank"]
+        w = None if s == 0 else z[f"s{s - 1}_fWeight"]
+        k = PKD(device=0)
+        k.pkdOrbLoad(pos[:, 0], pos[:, 1], pos[:, 2], fWeight=w)
+        prev = domain.pst_domain_decomp([k], nThreads, prev=prev, device_bisect=True)
+        assert np.array_equal(domain.leaf_rank(nThreads)[k.pkdOrbCells()], want), f"{name}: decomposition {s}"
+        k.close()
+
+
+def test_bisection_on_the_device_timing():
+    p = ics.plummer(1000000, seed=12345)
+    k = PKD(device=0, fPeriod=p.period)
+    out = {}
+    for dev in (False, True, True):
+        k.pkdOrbLoad(p.x, p.y, p.z)
+        t0 = time.perf_counter()
+        nodes = domain.pst_domain_decomp([k], 8, device_bisect=dev)
+        out[dev] = ((time.perf_counter() - t0) * 1e3, sum(n["ittr"] for n in nodes))
+    k.close()
+    print(f"ORB 1 M particles -> 8 domains, {out[True][1]} trials: host-driven loop {out[False][0]:.2f} ms, bisection on the "
+          f"device {out[True][0]:.2f} ms")
+    assert out[True][1] == out[False][1]
