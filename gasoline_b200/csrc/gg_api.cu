@@ -705,14 +705,18 @@ int gg_create(gg_context **pctx, int device) {
     gg_context *c = new gg_context();
     c->device = device;
     c->nSM = prop.multiProcessorCount;
-    CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    // the main stream outranks the side streams: kernels of the exchange / walk / evaluation get an SM slot as soon as one
+    // frees up, an early Ewald correction (st4) only fills what they leave
+    int prLeast = 0, prGreatest = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prLeast, &prGreatest));
+    CK(cudaStreamCreateWithPriority(&c->st, cudaStreamNonBlocking, prGreatest));
     CK(cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->evMom, cudaEventDisableTiming));
     CK(cudaStreamCreateWithFlags(&c->st3, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->evWalk, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->evStats, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->evPacked, cudaEventDisableTiming));
-    CK(cudaStreamCreateWithFlags(&c->st4, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithPriority(&c->st4, cudaStreamNonBlocking, prLeast));
     CK(cudaEventCreate(&c->evEw[0]));
     CK(cudaEventCreate(&c->evEw[1]));
     CK(cudaEventCreateWithFlags(&c->evEw[2], cudaEventDisableTiming));

@@ -322,7 +322,20 @@ struct Slab {
 // Append <= 32 entries (one per lane with `has`) to chain (type, d); d = 1 also records the entry's bucket mask.
 // The head block of a chain is the one being filled; older blocks are full.  Blocks come from the warp's slab; a
 // new slab costs one atomic.  Warp-collective.
-__device__ __forceinline__ void append(const TreeKernelArgs &A, WalkSmem &W, int type, int d, bool has, unsigned entry,
+#ifndef GG_WALK_NOINLINE
+#define GG_WALK_NOINLINE 0 // 1: append is a real function, 2: distribute is (k_walk's loop body is ~100 KB of code when both are inlined)
+#endif
+#if GG_WALK_NOINLINE == 1
+#define GG_APPEND_INLINE __noinline__
+#else
+#define GG_APPEND_INLINE __forceinline__
+#endif
+#if GG_WALK_NOINLINE == 2
+#define GG_DISTRIBUTE_INLINE __noinline__
+#else
+#define GG_DISTRIBUTE_INLINE __forceinline__
+#endif
+__device__ GG_APPEND_INLINE void append(const TreeKernelArgs &A, WalkSmem &W, int type, int d, bool has, unsigned entry,
                                        unsigned mask, int lane, unsigned lt, Slab &slab) {
     const unsigned m = __ballot_sync(FULL, has);
     if (!m) return;
@@ -363,7 +376,7 @@ __device__ __forceinline__ void append(const TreeKernelArgs &A, WalkSmem &W, int
 // One list type of one step: lanes with dm == all go to the group's shared chain, the others to its masked chain.
 // myCnt (lane b counts for bucket b of the group) gets the per-bucket number of masked entries -- of particles for
 // leaves (np > 0).
-__device__ __forceinline__ void distribute(const TreeKernelArgs &A, WalkSmem &W, int type, unsigned dm, unsigned all,
+__device__ GG_DISTRIBUTE_INLINE void distribute(const TreeKernelArgs &A, WalkSmem &W, int type, unsigned dm, unsigned all,
                                            int nB, unsigned entry, int np, int lane, unsigned lt, Slab &slab,
                                            int &myCnt, int &sharedP, int &myLeaves) {
     const unsigned mAny = __ballot_sync(FULL, dm != 0);
