@@ -87,6 +87,11 @@ __device__ __forceinline__ void meval(int iOrder, const EwaldKernelArgs &A, cons
     az -= dz * ta;
 }
 
+#ifndef GG_EWALD_EXPFAC
+#define GG_EWALD_EXPFAC 0 // 1: exp(-alpha^2 r^2) as a product of per-axis factors (21 exponentials per particle instead of ~90).
+                          // Measured: no change (128^3 3.453 vs 3.450 ms, 256^3 27.01 vs 27.00 ms) -- the kernel waits on its
+                          // dependent FP64 chains (erfcx, the gam[] recursion, MEVAL), not on the instruction count.  Off.
+#endif
 #ifndef GG_EWALD_RSQRT
 #define GG_EWALD_RSQRT 1
 #endif
@@ -105,12 +110,31 @@ __global__ void __launch_bounds__(128, GG_EWALD_MIN_CTAS) k_ewald(const EwaldKer
     const double dx = A.parts[i].x - A.root[1], dy = A.parts[i].y - A.root[2], dz = A.parts[i].z - A.root[3];
     const int nE = A.nEwReps, nR = A.nReps;
     int nLoop = 0;
+#if GG_EWALD_EXPFAC
+    // exp(-alpha^2 r^2) = exp(-alpha^2 dx'^2) exp(-alpha^2 dy'^2) exp(-alpha^2 dz'^2) with dx' = dx + ix L: 3 (2 nE + 1)
+    // exponentials per particle instead of one per accepted image (~90 of the 343), two multiplications per image
+    constexpr int EW_TAB = 9; // nE <= 4
+    const bool expFac = nE <= (EW_TAB - 1) / 2;
+    double eyT[EW_TAB], ezT[EW_TAB];
+    if (expFac)
+        for (int k = -nE; k <= nE; ++k) {
+            const double ty = dy + k * L, tz = dz + k * L;
+            eyT[k + nE] = exp(-(ty * ty) * A.alpha2);
+            ezT[k + nE] = exp(-(tz * tz) * A.alpha2);
+        }
+#endif
     for (int ix = -nE; ix <= nE; ++ix) {
         const bool holex = (ix >= -nR && ix <= nR);
         const double dxo = dx + ix * L;
+#if GG_EWALD_EXPFAC
+        const double exX = expFac ? exp(-(dxo * dxo) * A.alpha2) : 0.0;
+#endif
         for (int iy = -nE; iy <= nE; ++iy) {
             const bool holexy = holex && (iy >= -nR && iy <= nR);
             const double dyo = dy + iy * L;
+#if GG_EWALD_EXPFAC
+            const double exXY = expFac ? exX * eyT[iy + nE] : 0.0;
+#endif
             for (int iz = -nE; iz <= nE; ++iz) {
                 const bool hole = holexy && (iz >= -nR && iz <= nR);
                 const double dzo = dz + iz * L;
@@ -136,7 +160,11 @@ __global__ void __launch_bounds__(128, GG_EWALD_MIN_CTAS) k_ewald(const EwaldKer
 #endif
                     // erfc(x) = exp(-x^2) erfcx(x): the exponential is needed anyway (ewald.c:121), and the scaled function
                     // is the cheaper one; -erf(x) = erfc(x) - 1 (x > 0.1 here: the series branch took the small radii)
+#if GG_EWALD_EXPFAC
+                    const double ex = expFac ? exXY * ezT[iz + nE] : exp(-r2 * A.alpha2);
+#else
                     const double ex = exp(-r2 * A.alpha2);
+#endif
                     double a = ex * A.ka * dir2;
                     const double ec = ex * erfcx(A.alpha * r);
                     g[0] = (hole ? ec - 1.0 : ec) * dir;
