@@ -54,7 +54,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {src}")
-    subprocess.check_call([_nvcc(), "-shared", "-o", LIB_PATH] + objs + ["-lcudart", "-lpthread", "-ldl"])
+    subprocess.check_call([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs +
+                          ["-lcudart", "-lpthread", "-ldl"])
     return LIB_PATH
 
 

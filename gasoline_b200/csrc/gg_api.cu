@@ -991,8 +991,20 @@ static int fetch_root_lazy(gg_context *c) {
 }
 
 // Build the tree of the particles pp (host or device pointers) on the device and load it as the local domain.
-static int build_and_load(gg_context *c, int idSelf, const gg_particles *pp, int nBucket, double dTheta, int *iOrder,
-                          int *pnNodes, double *root) {
+// pkdCalcOpen's criteria on the device: OPEN_JOSH, and the three that take Bmax itself (a zero factor in k_emit).
+// OPEN_ABSPAR needs the radial moments B2..B6 summed particle by particle in the reference's order and its root finder
+// (pkd.c:2182-2224): the host builder has them (gg_tree_build_open), the device builder does not.
+static int open_factor(const char *who, int iOpenType, double *c23) {
+    if (iOpenType == GG_OPEN_JOSH) *c23 = 2.0 / sqrt(3.0);
+    else if (iOpenType == GG_OPEN_RELPAR || iOpenType == GG_OPEN_ABSTOT || iOpenType == GG_OPEN_RELTOT) *c23 = 0.0;
+    else if (iOpenType == GG_OPEN_ABSPAR)
+        return gg_fail(GG_ERR_UNSUPPORTED, "%s: OPEN_ABSPAR is built on the host (gg_tree_build_open), not on the device", who);
+    else return gg_fail(GG_ERR_ARG, "%s: iOpenType=%d", who, iOpenType);
+    return GG_OK;
+}
+
+static int build_and_load(gg_context *c, int idSelf, const gg_particles *pp, int nBucket, double dTheta, double c23,
+                          int *iOrder, int *pnNodes, double *root) {
     int rc;
     if ((rc = gg_finish_mom(c))) return rc;
     if ((rc = drop_early_ewald(c))) return rc;
@@ -1000,7 +1012,7 @@ static int build_and_load(gg_context *c, int idSelf, const gg_particles *pp, int
     int nl = 0;
     GGBuiltDev b{};
     CK(cudaEventRecord(c->ev[6], c->st));
-    rc = gg_builder_run(&c->builder, pp, nBucket, dTheta, c->st, &b, &nl, msg, sizeof(msg));
+    rc = gg_builder_run(&c->builder, pp, nBucket, dTheta, c23, c->st, &b, &nl, msg, sizeof(msg));
     if (rc) return gg_fail(rc, "%s", msg);
     CK(cudaEventRecord(c->ev[7], c->st));
     c->nLaunches += nl;
@@ -1041,13 +1053,21 @@ static int build_and_load(gg_context *c, int idSelf, const gg_particles *pp, int
 
 int gg_build_local(gg_context *c, int idSelf, const gg_particles *pp, int nBucket, double dTheta, int *iOrder,
                    int *pnNodes, double *root) {
+    return gg_build_local_open(c, idSelf, pp, nBucket, GG_OPEN_JOSH, dTheta, iOrder, pnNodes, root);
+}
+
+int gg_build_local_open(gg_context *c, int idSelf, const gg_particles *pp, int nBucket, int iOpenType, double dTheta,
+                        int *iOrder, int *pnNodes, double *root) {
     if (!c || !pp) return gg_fail(GG_ERR_ARG, "gg_build_local: null argument");
+    double c23;
+    int rco = open_factor("gg_build_local", iOpenType, &c23);
+    if (rco) return rco;
     if (pp->n < 1 || !pp->x || !pp->y || !pp->z || !pp->fMass || !pp->fSoft || nBucket < 1 || nBucket > GG_MAX_BUCKET ||
         !(dTheta > 0))
         return gg_fail(GG_ERR_ARG, "gg_build_local: n=%d nBucket=%d dTheta=%g", pp->n, nBucket, dTheta);
     CK(cudaSetDevice(c->device));
     c->stateN = 0; // a tree built from host particles replaces any resident store
-    return build_and_load(c, idSelf, pp, nBucket, dTheta, iOrder, pnNodes, root);
+    return build_and_load(c, idSelf, pp, nBucket, dTheta, c23, iOrder, pnNodes, root);
 }
 
 
@@ -1252,7 +1272,14 @@ int gg_state_load(gg_context *c, int n, const double *x, const double *y, const 
 }
 
 int gg_state_build(gg_context *c, int idSelf, int nBucket, double dTheta, int *pnNodes) {
+    return gg_state_build_open(c, idSelf, nBucket, GG_OPEN_JOSH, dTheta, pnNodes);
+}
+
+int gg_state_build_open(gg_context *c, int idSelf, int nBucket, int iOpenType, double dTheta, int *pnNodes) {
     if (!c || c->stateN < 1) return gg_fail(GG_ERR_ARG, "gg_state_build: no resident particles (gg_state_load)");
+    double c23;
+    int rco = open_factor("gg_state_build", iOpenType, &c23);
+    if (rco) return rco;
     if (nBucket < 1 || nBucket > GG_MAX_BUCKET || !(dTheta > 0))
         return gg_fail(GG_ERR_ARG, "gg_state_build: nBucket=%d dTheta=%g", nBucket, dTheta);
     CK(cudaSetDevice(c->device));
@@ -1262,7 +1289,7 @@ int gg_state_build(gg_context *c, int idSelf, int nBucket, double dTheta, int *p
     pp.x = (const double *)c->sx.p; pp.y = (const double *)c->sy.p; pp.z = (const double *)c->sz.p;
     pp.fMass = (const double *)c->sm.p; pp.fSoft = (const double *)c->sh.p;
     pp.active = c->stateHasActive ? (const int *)c->sact.p : nullptr;
-    int rc = build_and_load(c, idSelf, &pp, nBucket, dTheta, nullptr, pnNodes, nullptr);
+    int rc = build_and_load(c, idSelf, &pp, nBucket, dTheta, c23, nullptr, pnNodes, nullptr);
     if (rc) return rc;
     // the store follows the tree order: velocities, ids and time steps by the build's permutation, the rest as built
     const GGBuiltDev &b = c->built;

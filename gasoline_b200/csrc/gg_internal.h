@@ -199,7 +199,7 @@ struct GGBuiltDev {
     const int *active; // null: all active
     const int *iorder;
 };
-int gg_builder_run(void **pBuilder, const gg_particles *pp, int nBucket, double dTheta, cudaStream_t st, GGBuiltDev *out,
+int gg_builder_run(void **pBuilder, const gg_particles *pp, int nBucket, double dTheta, double c23, cudaStream_t st, GGBuiltDev *out,
                    int *pnLaunches, char *err, size_t errLen);
 void gg_builder_free(void *builder);
 

@@ -9,7 +9,8 @@
 //   * cells are numbered in depth-first pre-order (cell, lower subtree, upper subtree), as pkd->iFreeCell++ does;
 //   * mass, centre of mass and mass-weighted softening come from the children (buckets: from the particles);
 //     reduced multipoles to hexadecapole and Bmax are summed particle by particle about the cell's centre
-//     (pkdCalcCell, pkd.c:2018-2135); fOpen2 = max(Bmax, 2/sqrt(3) Bmax/theta)^2 (OPEN_JOSH, pkd.c:2253-2260);
+//     (pkdCalcCell, pkd.c:2018-2135); fOpen2 = max(Bmax, 2/sqrt(3) Bmax/theta)^2 (OPEN_JOSH, pkd.c:2253-2260), or one of
+//     the other opening criteria of pkdCalcOpen (pkd.c:2228-2264) through gg_tree_build_open;
 //   * links are threaded: iLower = first child, iUpper = next cell (pkdThreadTree, pkd.c:2590-2620);
 //   * the Ewald root expansion holds COMPLETE l=3,4 moments about the root centre (pkdCalcRoot, pkd.c:4395).
 // Unlike the reference's single recursion this builder partitions the top levels serially, hands the subtrees to
@@ -35,7 +36,7 @@ struct Cell { // one tree cell during construction; child links are indices into
 
 struct gg_built_tree_impl {
     int nNodes = 0, iRoot = -1;
-    std::vector<double> bnd, r, fMass, fSoft, fOpen2, mom;
+    std::vector<double> bnd, r, fMass, fSoft, fOpen2, mom, bmom; // bmom: Bmax, B2..B6 per cell (pkd.h:441-451)
     std::vector<int> pLower, pUpper, iLower, iUpper;
     double root[GG_NROOT];
 };
@@ -105,13 +106,17 @@ void build_shape(P *p, int lo, int hi, int nBucket, std::vector<Cell> &cells) {
     }
 }
 
-void cell_moments(const P *p, int lo, int hi, const double *rc, int iOrder, double *q, double *bmax) {
-    double B = 0.0;
+// bnum (may be null): Bmax and the radial moments B2..B6 = sum m d^k the opening criteria are made of (pkd.c:2080-2087)
+void cell_moments(const P *p, int lo, int hi, const double *rc, int iOrder, double *q, double *bmax, double *bnum = nullptr) {
+    double B = 0.0, b2 = 0.0, b3 = 0.0, b4 = 0.0, b5 = 0.0, b6 = 0.0;
     for (int k = 0; k < GG_NMOM; ++k) q[k] = 0.0;
     for (int j = lo; j <= hi; ++j) {
         const double m = p[j].m, dx = p[j].r[0] - rc[0], dy = p[j].r[1] - rc[1], dz = p[j].r[2] - rc[2];
         const double d2 = dx * dx + dy * dy + dz * dz, d1 = std::sqrt(d2);
         if (d1 > B) B = d1;
+        if (bnum) {
+            b2 += m * d2; b3 += m * d2 * d1; b4 += m * d2 * d2; b5 += m * d2 * d2 * d1; b6 += m * d2 * d2 * d2;
+        }
         if (iOrder >= 4) {
             q[16] += m * (dx * dx * dx * dx - 6.0 / 7.0 * d2 * (dx * dx - 0.1 * d2));
             q[17] += m * (dx * dy * dy * dy - 3.0 / 7.0 * d2 * dx * dy);
@@ -145,6 +150,60 @@ void cell_moments(const P *p, int lo, int hi, const double *rc, int iOrder, doub
         q[3] += m * dx * dy; q[4] += m * dx * dz; q[5] += m * dy * dz;
     }
     *bmax = B;
+    if (bnum) { bnum[0] = B; bnum[1] = b2; bnum[2] = b3; bnum[3] = b4; bnum[4] = b5; bnum[5] = b6; }
+}
+
+// The error estimate of a cell's expansion truncated after `order`, seen from distance r (fcnAbsMono .. fcnAbsHex,
+// pkd.c:2137-2179): ((l + 2) B_{l+1} - (l + 1) B_{l+2} / r) / (r^l (r - Bmax))^2 ... with the reference's grouping.
+inline double abs_error(const double *b, int order, double r) {
+    double t;
+    switch (order) {
+    case 1: t = r * (r - b[0]); t *= t; return (3.0 * b[1] - 2.0 * b[2] / r) / t;
+    case 2: t = r * (r - b[0]); t *= r * t; return (4.0 * b[2] - 3.0 * b[3] / r) / t;
+    case 3: t = r * r * (r - b[0]); t *= t; return (5.0 * b[3] - 4.0 * b[4] / r) / t;
+    default: t = r * r * (r - b[0]); t *= r * t; return (6.0 * b[4] - 5.0 * b[5] / r) / t;
+    }
+}
+
+// OPEN_ABSPAR: the distance at which that estimate falls to dErrBnd, by the reference's hunt + bisection
+// (dRootBracket, pkd.c:2182-2224): start just outside Bmax, double until the estimate is below the bound, halve the
+// bracket until the estimate is within 1e-6 dErrBnd below it (or 33 halvings).  A cell without extent (one particle,
+// coincident particles) has Bmax = B_k = 0: the estimate is 0/0 there and the reference's hunt never ends -- reported
+// through *bad instead of repeated.
+double open_abs_partial(const double *b, double dErrBnd, int order, bool *bad) {
+    const double crit = 1e-6 * dErrBnd;
+    double lower = (1.0 + 1e-6) * b[0];
+    const double e0 = abs_error(b, order, lower);
+    if (e0 < dErrBnd) return lower;
+    if (!(e0 == e0) || !(lower > 0.0)) { *bad = true; return lower; }
+    double upper = 2 * lower, mid;
+    for (;;) {
+        const double dif = dErrBnd - abs_error(b, order, upper);
+        if (dif > crit) break;
+        if (!(dif == dif) || upper > 1.0e300) { *bad = true; return upper; }
+        upper = 2 * upper;
+    }
+    for (int iter = 0;;) {
+        mid = 0.5 * (lower + upper);
+        const double dif = dErrBnd - abs_error(b, order, mid);
+        if (dif < 0) lower = mid;
+        else {
+            upper = mid;
+            if (dif < crit) break;
+        }
+        if (++iter > 32) break;
+    }
+    return mid;
+}
+
+// pkdCalcOpen (pkd.c:2228-2264)
+inline double open_radius(const double *b, int iOpenType, double dCrit, int order, bool *bad) {
+    if (iOpenType == GG_OPEN_ABSPAR) return open_abs_partial(b, dCrit, order, bad);
+    if (iOpenType == GG_OPEN_JOSH) {
+        const double dOpen = 2 / std::sqrt(3.0) * b[0] / dCrit;
+        return dOpen < b[0] ? b[0] : dOpen;
+    }
+    return b[0]; // OPEN_RELPAR, OPEN_ABSTOT, OPEN_RELTOT: "the minimal, i.e., Bmax"
 }
 
 } // namespace
@@ -154,7 +213,15 @@ struct gg_built_tree : gg_built_tree_impl {};
 extern "C" int gg_tree_build(int n, double *x, double *y, double *z, double *fMass, double *fSoft, int *active,
                              int *iOrderOut, int nBucket, double dTheta, int iOrderMom, int nThreads,
                              gg_built_tree **out) {
-    if (n <= 0 || !x || !y || !z || !fMass || !fSoft || !out || nBucket < 1 || !(dTheta > 0)) return GG_ERR_ARG;
+    return gg_tree_build_open(n, x, y, z, fMass, fSoft, active, iOrderOut, nBucket, GG_OPEN_JOSH, dTheta, iOrderMom,
+                              nThreads, out);
+}
+
+extern "C" int gg_tree_build_open(int n, double *x, double *y, double *z, double *fMass, double *fSoft, int *active,
+                                  int *iOrderOut, int nBucket, int iOpenType, double dCrit, int iOrderMom, int nThreads,
+                                  gg_built_tree **out) {
+    if (n <= 0 || !x || !y || !z || !fMass || !fSoft || !out || nBucket < 1 || !(dCrit > 0)) return GG_ERR_ARG;
+    if (iOpenType < GG_OPEN_JOSH || iOpenType > GG_OPEN_RELTOT || iOrderMom < 1 || iOrderMom > 4) return GG_ERR_ARG;
     if (nThreads <= 0) nThreads = (int)std::max(1u, std::thread::hardware_concurrency());
     std::vector<P> ps((size_t)n);
     for (int i = 0; i < n; ++i) {
@@ -215,7 +282,7 @@ extern "C" int gg_tree_build(int n, double *x, double *y, double *z, double *fMa
     bt->nNodes = nn;
     bt->iRoot = 0;
     bt->bnd.resize((size_t)nn * 6); bt->r.resize((size_t)nn * 3); bt->fMass.resize(nn); bt->fSoft.resize(nn);
-    bt->fOpen2.resize(nn); bt->mom.resize((size_t)nn * GG_NMOM);
+    bt->fOpen2.resize(nn); bt->mom.resize((size_t)nn * GG_NMOM); bt->bmom.resize((size_t)nn * 6);
     bt->pLower.resize(nn); bt->pUpper.resize(nn); bt->iLower.resize(nn); bt->iUpper.resize(nn);
     std::vector<int> left(nn, -1), right(nn, -1);
     std::vector<int> topIndex(top.size(), -1), subBase(pending.size(), -1);
@@ -285,6 +352,7 @@ extern "C" int gg_tree_build(int n, double *x, double *y, double *z, double *fMa
         bt->fMass[g] = M;
         bt->fSoft[g] = S;
     }
+    std::atomic<bool> badOpen{false};
     {
         std::atomic<int> nextCell{0};
         auto work = [&]() {
@@ -292,11 +360,12 @@ extern "C" int gg_tree_build(int n, double *x, double *y, double *z, double *fMa
                 int g0 = nextCell.fetch_add(256);
                 if (g0 >= nn) break;
                 for (int g = g0; g < std::min(nn, g0 + 256); ++g) {
-                    double bmax;
+                    double bmax, *b = &bt->bmom[6 * (size_t)g];
+                    bool bad = false;
                     cell_moments(p, bt->pLower[g], bt->pUpper[g], &bt->r[3 * (size_t)g], iOrderMom,
-                                 &bt->mom[(size_t)GG_NMOM * g], &bmax);
-                    double dOpen = 2 / std::sqrt(3.0) * bmax / dTheta;
-                    if (dOpen < bmax) dOpen = bmax;
+                                 &bt->mom[(size_t)GG_NMOM * g], &bmax, b);
+                    const double dOpen = open_radius(b, iOpenType, dCrit, iOrderMom, &bad);
+                    if (bad) badOpen = true;
                     bt->fOpen2[g] = dOpen * dOpen;
                 }
             }
@@ -305,6 +374,10 @@ extern "C" int gg_tree_build(int n, double *x, double *y, double *z, double *fMa
         for (int t = 1; t < nThreads; ++t) th.emplace_back(work);
         work();
         for (auto &t : th) t.join();
+    }
+    if (badOpen) { // OPEN_ABSPAR on a tree with a zero-extent cell: the reference does not return from it either
+        delete bt;
+        return GG_ERR_UNSUPPORTED;
     }
     // ---- threading: next[g] = sibling if g is a lower child, else the parent's next
     {
@@ -360,6 +433,12 @@ extern "C" int gg_tree_view(const gg_built_tree *bt, gg_tree *v, double root[GG_
     v->pLower = bt->pLower.data(); v->pUpper = bt->pUpper.data(); v->iLower = bt->iLower.data();
     v->iUpper = bt->iUpper.data();
     if (root) std::memcpy(root, bt->root, sizeof(bt->root));
+    return GG_OK;
+}
+
+extern "C" int gg_tree_bnumbers(const gg_built_tree *bt, double *bmom) {
+    if (!bt || !bmom) return GG_ERR_ARG;
+    std::memcpy(bmom, bt->bmom.data(), bt->bmom.size() * sizeof(double));
     return GG_OK;
 }
 

@@ -547,7 +547,9 @@ __global__ void __launch_bounds__(256) k_emit(int nn, const BNode *nodes, const 
     fMass[g] = cmass[t];
     fSoft[g] = csoft[t];
     const double bmax = __longlong_as_double((long long)bmaxBits[t]);
-    double dOpen = __ddiv_rn(__dmul_rn(c23, bmax), dTheta); // OPEN_JOSH, pkd.c:2253-2260
+    // OPEN_JOSH, pkd.c:2253-2260: c23 = 2/sqrt(3); the criteria that take "the minimal, i.e., Bmax" (pkd.c:2261-2264:
+    // OPEN_RELPAR, OPEN_ABSTOT, OPEN_RELTOT) arrive as c23 = 0
+    double dOpen = __ddiv_rn(__dmul_rn(c23, bmax), dTheta);
     if (dOpen < bmax) dOpen = bmax;
     fOpen2[g] = __dmul_rn(dOpen, dOpen);
     pLower[g] = nd.lo;
@@ -592,7 +594,7 @@ struct Builder {
         }                                                                                                     \
     } while (0)
 
-int gg_builder_run(void **pBuilder, const gg_particles *pp, int nBucket, double dTheta, cudaStream_t st, GGBuiltDev *out,
+int gg_builder_run(void **pBuilder, const gg_particles *pp, int nBucket, double dTheta, double c23, cudaStream_t st, GGBuiltDev *out,
                    int *pnLaunches, char *err, size_t errLen) {
     if (!*pBuilder) *pBuilder = new Builder();
     Builder &B = *(Builder *)*pBuilder;
@@ -679,7 +681,7 @@ int gg_builder_run(void **pBuilder, const gg_particles *pp, int nBucket, double 
     k_up<<<(nn + 127) / 128, 128, 0, st>>>(nn, nodes, x, y, z, m, h, cmass, csoft, ccom, csize, arrive);
     k_number<<<gridN, 256, 0, st>>>(nn, nodes, csize, pre, nextB);
     k_bmax<<<gridP, 256, 0, st>>>(n, cellOf, nodes, x, y, z, ccom, bmaxBits);
-    k_emit<<<gridN, 256, 0, st>>>(nn, nodes, pre, nextB, cmass, csoft, ccom, bmaxBits, 2.0 / sqrt(3.0), dTheta, obnd, orr, oM,
+    k_emit<<<gridN, 256, 0, st>>>(nn, nodes, pre, nextB, cmass, csoft, ccom, bmaxBits, c23, dTheta, obnd, orr, oM,
                                   oS, oO, oPL, oPU, oIL, oIU, oDim, oSplit, oBmax);
     nl += 4;
     BCK(cudaGetLastError());

@@ -27,7 +27,7 @@
  * same numbering, the same order of pStore, r / fMass / fSoft / fOpen2 / bnd bit for bit), pStore is permuted and
  * kdNodes filled from it, so that pstBuildTree and everything downstream see the tree they would have built -- in
  * ~30 ms instead of ~1.2 s for 1 M particles.  Without the variable, or for what the device build does not cover
- * (iOpenType other than OPEN_JOSH, a tree over part of the particles, bGravity = 0), the host's own build runs.
+ * (iOpenType = OPEN_ABSPAR, a tree over part of the particles, bGravity = 0), the host's own build runs.
  *
  * Several MDL ranks (mdlThreads > 1; pst.c:3248-3303 fans pstGravity out, every leaf calls this function at the same
  * time): rank r drives GPU r (GG_SHIM_DEVICE overrides; r modulo the device count otherwise).  On its first call every
@@ -530,7 +530,7 @@ static void fill_nodes(void *arg, size_t lo, size_t hi) {
             q->Hyyyz = mo[21]; q->Hxxyy = mo[22]; q->Hxxyz = mo[23]; q->Hxyyz = mo[24]; q->Hxxzz = mo[25];
             q->Hxyzz = mo[26]; q->Hxzzz = mo[27]; q->Hyyzz = mo[28]; q->Hyzzz = mo[29]; q->Hzzzz = mo[30];
         }
-        q->Bmax = s->fBmax[i]; /* B2..B6 (other opening criteria, pkd.c:2228-2252) are not formed: OPEN_JOSH only */
+        q->Bmax = s->fBmax[i]; /* B2..B6 (read by OPEN_ABSPAR only, pkd.c:2137-2179; that criterion is built by the host) stay 0 */
     }
 }
 
@@ -543,7 +543,10 @@ void pkdBuildBinary(PKD pkd, int nBucket, int iOpenType, double dCrit, int iOrde
     int n, nNodes = 0;
     double t0 = 0.0;
 
-    if (!e || !atoi(e) || iOpenType != OPEN_JOSH || !bGravity || pkd->nLocal < 1 || nBucket > GG_MAX_BUCKET ||
+    /* OPEN_ABSPAR (dRootBracket on B2..B6, pkd.c:2182-2252) stays with the host's build; OPEN_JOSH and the three criteria
+     * whose radius is Bmax (pkd.c:2261-2264) are built on the device */
+    if (!e || !atoi(e) || iOpenType == OPEN_ABSPAR || iOpenType < OPEN_JOSH || iOpenType > OPEN_RELTOT || !bGravity ||
+        pkd->nLocal < 1 || nBucket > GG_MAX_BUCKET ||
         (bTreeActiveOnly && pkd->nTreeActive != pkd->nLocal)) {
         if (pkd->idSelf >= 0 && pkd->idSelf < 64) g_shim[pkd->idSelf].builtNodes = NULL;
         pkdBuildBinary_cpu(pkd, nBucket, iOpenType, dCrit, iOrder, bTreeActiveOnly, bGravity, pRoot);
@@ -566,7 +569,8 @@ void pkdBuildBinary(PKD pkd, int nBucket, int iOpenType, double dCrit, int iOrde
     parallel_for((size_t)n, flatten_particles, &pass);
     lap(&t0, "build: flatten particles");
     pp.n = n; pp.x = s->x; pp.y = s->y; pp.z = s->z; pp.fMass = s->m; pp.fSoft = s->h; pp.active = NULL;
-    if (gg_build_local(s->ctx, pkd->idSelf, &pp, nBucket, dCrit, s->order, &nNodes, NULL) != GG_OK) die("gg_build_local");
+    if (gg_build_local_open(s->ctx, pkd->idSelf, &pp, nBucket, iOpenType, dCrit, s->order, &nNodes, NULL) != GG_OK)
+        die("gg_build_local_open");
     lap(&t0, "build: gg_build_local");
     reserve(s, (size_t)nNodes, (size_t)n);
     if (gg_tree_fetch(s->ctx, s->bnd, s->r, s->fMass, s->fSoft, s->fOpen2, s->mom, s->pLower, s->pUpper, s->iLower,

@@ -19,6 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgasoline_b200.so")
 GG_NMOM, GG_NROOT = 31, 35
 GG_FLAG_WALK_ONLY, GG_FLAG_NO_DOWNLOAD = 1, 2
+OPEN_JOSH, OPEN_ABSPAR, OPEN_RELPAR, OPEN_ABSTOT, OPEN_RELTOT = 1, 2, 3, 4, 5  # opentype.h:5-9 = GG_OPEN_*
 
 
 class GasolineB200Error(RuntimeError):
@@ -104,11 +105,16 @@ def load_library(path: str | None = None):
     L.gg_host_free.argtypes = [C.c_void_p]
     L.gg_tree_build.argtypes = [C.c_int, _dp, _dp, _dp, _dp, _dp, _ip, _ip, C.c_int, C.c_double, C.c_int, C.c_int,
                                 C.POINTER(C.c_void_p)]
+    L.gg_tree_build_open.argtypes = [C.c_int, _dp, _dp, _dp, _dp, _dp, _ip, _ip, C.c_int, C.c_int, C.c_double, C.c_int,
+                                     C.c_int, C.POINTER(C.c_void_p)]
+    L.gg_tree_bnumbers.argtypes = [C.c_void_p, _dp]
     L.gg_tree_view.argtypes = [C.c_void_p, C.POINTER(gg_tree), _dp]
     L.gg_tree_free.argtypes = [C.c_void_p]
     L.gg_cell_moments.argtypes = [C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_int, _dp, _dp]
     L.gg_tree_moments_m2m.argtypes = [C.POINTER(gg_tree), C.POINTER(gg_particles), _dp]
     L.gg_build_local.argtypes = [C.c_void_p, C.c_int, C.POINTER(gg_particles), C.c_int, C.c_double, _ip, _ip, _dp]
+    L.gg_build_local_open.argtypes = [C.c_void_p, C.c_int, C.POINTER(gg_particles), C.c_int, C.c_int, C.c_double, _ip, _ip,
+                                      _dp]
     L.gg_set_active.argtypes = [C.c_void_p, _ip]
     L.gg_orb_bisect.argtypes = [C.c_void_p, C.c_int, _ip, _ip, _dp, _dp, _ip, _dp, _dp, C.c_int, _dp, _ip, _ip]
     L.gg_build_info.argtypes = [C.c_void_p, _ip, _ip, _dp]
@@ -117,6 +123,7 @@ def load_library(path: str | None = None):
     L.gg_tree_fetch.argtypes = [C.c_void_p] + [_dp] * 6 + [_ip] * 4 + [_dp] * 5 + [_ip]
     L.gg_state_load.argtypes = [C.c_void_p, C.c_int] + [_dp] * 8 + [_ip, C.c_double]
     L.gg_state_build.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, _ip]
+    L.gg_state_build_open.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, _ip]
     L.gg_state_kick.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p]
     L.gg_state_drift.argtypes = [C.c_void_p, C.c_double, _dp, C.c_int, _dp]
     L.gg_state_gravstep.argtypes = [C.c_void_p, C.c_double, _dp]
@@ -293,16 +300,19 @@ class PKD:
         out[...] = a
         return out
 
-    def pkdBuildBinary(self, nBucket: int = 8, dCrit: float = 0.7, iOrder: int = 4, nThreads: int = 0):
-        """pkdBuildBinary (pkd.c:2627) + pkdCalcRoot (pkd.c:4395): spatial-bisection tree, OPEN_JOSH opening radius
-        with theta=dCrit; permutes pStore into tree order.  Host-side C++ (csrc/gg_tree_build.cpp)."""
+    def pkdBuildBinary(self, nBucket: int = 8, dCrit: float = 0.7, iOrder: int = 4, nThreads: int = 0,
+                       iOpenType: int = OPEN_JOSH):
+        """pkdBuildBinary (pkd.c:2627) + pkdCalcRoot (pkd.c:4395): spatial-bisection tree, opening radius by pkdCalcOpen
+        (pkd.c:2228-2264; iOpenType as in opentype.h:5-9, default OPEN_JOSH with theta=dCrit); permutes pStore into tree
+        order.  Host-side C++ (csrc/gg_tree_build.cpp)."""
         if self.nLocal == 0:
             raise GasolineB200Error("pkdBuildBinary: no particles")
         bt = C.c_void_p()
         order = np.zeros(self.nLocal, dtype=np.int32)
         act = _i(self.active) if self.active is not None else None
-        _check(self._L.gg_tree_build(self.nLocal, _d(self.x), _d(self.y), _d(self.z), _d(self.fMass), _d(self.fSoft),
-                                     act, _i(order), nBucket, dCrit, iOrder, nThreads, C.byref(bt)), "gg_tree_build")
+        _check(self._L.gg_tree_build_open(self.nLocal, _d(self.x), _d(self.y), _d(self.z), _d(self.fMass), _d(self.fSoft),
+                                          act, _i(order), nBucket, int(iOpenType), dCrit, iOrder, nThreads, C.byref(bt)),
+               "gg_tree_build_open")
         try:
             v = gg_tree()
             root = np.zeros(GG_NROOT)
@@ -321,11 +331,14 @@ class PKD:
         self._uploaded = False
         return self.tree
 
-    def pkdBuildBinaryDevice(self, nBucket: int = 8, dCrit: float = 0.7, want_root: bool = False):
+    def pkdBuildBinaryDevice(self, nBucket: int = 8, dCrit: float = 0.7, want_root: bool = False,
+                             iOpenType: int = OPEN_JOSH):
         """pkdBuildBinary (pkd.c:2627) ON THE DEVICE (gg_build_local, csrc/gg_tree_gpu.cu): the particles go up in their
         current order, the tree -- bit-identical to pkdBuildBinary's -- is built and left loaded on the GPU, moments
         formed there; pkdGravAll follows without any tree transfer.  Results come back in tree order; iOrderMap maps
-        tree position -> original index.  self.tree stays None (pkdFetchTree downloads it when a host wants it)."""
+        tree position -> original index.  self.tree stays None (pkdFetchTree downloads it when a host wants it).
+        iOpenType: OPEN_JOSH, or one of the criteria whose radius is Bmax (OPEN_RELPAR / ABSTOT / RELTOT, pkd.c:2261-2264);
+        OPEN_ABSPAR is the host builder's (pkdBuildBinary)."""
         if self.nLocal == 0:
             raise GasolineB200Error("pkdBuildBinaryDevice: no particles")
         pv = gg_particles(self.nLocal, _d(self.x), _d(self.y), _d(self.z), _d(self.fMass), _d(self.fSoft),
@@ -334,8 +347,9 @@ class PKD:
             self._devOrder = pinned_empty((self.nLocal,), np.int32) if self.pinned else np.zeros(self.nLocal, np.int32)
         nn = C.c_int()
         root = np.zeros(GG_NROOT) if want_root else None
-        _check(self._L.gg_build_local(self._ctx, self.idSelf, C.byref(pv), int(nBucket), float(dCrit),
-                                      _i(self._devOrder), C.byref(nn), _d(root) if want_root else None), "gg_build_local")
+        _check(self._L.gg_build_local_open(self._ctx, self.idSelf, C.byref(pv), int(nBucket), int(iOpenType), float(dCrit),
+                                           _i(self._devOrder), C.byref(nn), _d(root) if want_root else None),
+               "gg_build_local_open")
         self.nNodesDevice = int(nn.value)
         self.treeOrder = self._devOrder  # tree position -> index into the arrays given to pkdLoadParticles
         self.tree = None
@@ -403,10 +417,11 @@ class PKD:
         self._uploaded = False
         self._resident = True
 
-    def pkdBuildBinaryResident(self, nBucket: int = 8, dCrit: float = 0.7):
+    def pkdBuildBinaryResident(self, nBucket: int = 8, dCrit: float = 0.7, iOpenType: int = OPEN_JOSH):
         """pkdBuildBinary on the resident store (gg_state_build): the store is permuted into tree order on the device."""
         nn = C.c_int()
-        _check(self._L.gg_state_build(self._ctx, self.idSelf, int(nBucket), float(dCrit), C.byref(nn)), "gg_state_build")
+        _check(self._L.gg_state_build_open(self._ctx, self.idSelf, int(nBucket), int(iOpenType), float(dCrit), C.byref(nn)),
+               "gg_state_build_open")
         self.nNodesDevice = int(nn.value)
         self._uploaded = True
         return self.nNodesDevice

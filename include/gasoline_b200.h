@@ -33,6 +33,12 @@ extern "C" {
 
 #define GG_NMOM 31       /* Q6 O10 H15 in the order of struct pkdCalcCellStruct, pkd.h:441-451 */
 #define GG_NROOT 35      /* struct ilCellNewt, pkd.h:481-494: m,x,y,z,xx,yy,xy,xz,yz,zz, 10 octopole, 15 hexadecapole */
+/* opening criteria of pkdCalcOpen (pkd.c:2228-2264), numbered as in opentype.h:5-9 */
+#define GG_OPEN_JOSH 1
+#define GG_OPEN_ABSPAR 2
+#define GG_OPEN_RELPAR 3
+#define GG_OPEN_ABSTOT 4
+#define GG_OPEN_RELTOT 5
 #define GG_MAX_BUCKET 64 /* most particles one bucket may hold (reference default nBucket=8, master.c:480) */
 
 typedef struct gg_context gg_context;
@@ -322,7 +328,16 @@ int gg_host_free(void *p);
 typedef struct gg_built_tree gg_built_tree;
 int gg_tree_build(int n, double *x, double *y, double *z, double *fMass, double *fSoft, int *active, int *iOrder,
                   int nBucket, double dTheta, int iOrder_mom, int nThreads, gg_built_tree **out);
+/* ... with any of pkdCalcOpen's opening criteria (pkd.c:2228-2264; numbering of opentype.h:5-9).  dCrit is theta for
+ * GG_OPEN_JOSH and the absolute error bound for GG_OPEN_ABSPAR (the distance at which the truncation-error estimate of
+ * the order-iOrder_mom expansion falls to it, dRootBracket pkd.c:2182-2224); the other three criteria take the reference's
+ * "minimal" radius Bmax.  GG_OPEN_ABSPAR returns GG_ERR_UNSUPPORTED when a cell has no extent (a one-particle bucket):
+ * the reference's root finder does not terminate on such a cell. */
+int gg_tree_build_open(int n, double *x, double *y, double *z, double *fMass, double *fSoft, int *active, int *iOrder,
+                       int nBucket, int iOpenType, double dCrit, int iOrder_mom, int nThreads, gg_built_tree **out);
 int gg_tree_view(const gg_built_tree *bt, gg_tree *view, double root[GG_NROOT]);
+/* Bmax, B2..B6 of every cell (struct pkdCalcCellStruct, pkd.h:441-451; pkd.c:2080-2087): bmom[nNodes][6]. */
+int gg_tree_bnumbers(const gg_built_tree *bt, double *bmom);
 void gg_tree_free(gg_built_tree *bt);
 
 
@@ -339,6 +354,11 @@ void gg_tree_free(gg_built_tree *bt);
  */
 int gg_build_local(gg_context *ctx, int idSelf, const gg_particles *part, int nBucket, double dTheta, int *iOrder,
                    int *pnNodes, double root[GG_NROOT]);
+/* ... with pkdCalcOpen's criterion named (GG_OPEN_*, below): GG_OPEN_JOSH (dCrit = theta) and the three criteria whose
+ * opening radius is Bmax (GG_OPEN_RELPAR, GG_OPEN_ABSTOT, GG_OPEN_RELTOT; pkd.c:2261-2264) are built on the device;
+ * GG_OPEN_ABSPAR returns GG_ERR_UNSUPPORTED (gg_tree_build_open on the host has it). */
+int gg_build_local_open(gg_context *ctx, int idSelf, const gg_particles *part, int nBucket, int iOpenType, double dCrit,
+                        int *iOrder, int *pnNodes, double root[GG_NROOT]);
 /* The construction by-products a host needs to fill the rest of its KDN records (pkd.h:454-469): split axis (-1 for a
  * bucket), split coordinate, and Bmax of pkdCalcCellStruct, per cell in the numbering of gg_tree_fetch. */
 int gg_tree_fetch_build(gg_context *ctx, int *iDim, double *fSplit, double *fBmax);
@@ -383,6 +403,7 @@ int gg_state_load(gg_context *ctx, int n, const double *x, const double *y, cons
                   const double *vy, const double *vz, const double *fMass, const double *fSoft, const int *active,
                   double dt0);
 int gg_state_build(gg_context *ctx, int idSelf, int nBucket, double dTheta, int *pnNodes);
+int gg_state_build_open(gg_context *ctx, int idSelf, int nBucket, int iOpenType, double dCrit, int *pnNodes);
 int gg_state_kick(gg_context *ctx, double dvFacOne, double dvFacTwo, const double *a);
 int gg_state_drift(gg_context *ctx, double dDelta, const double fCenter[3], int bPeriodic, const double fPeriod[3]);
 int gg_state_gravstep(gg_context *ctx, double dEta, double *pdtMin);

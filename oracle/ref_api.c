@@ -203,8 +203,16 @@ void ref_destroy(REF *r) {
     free(r);
 }
 
-/* msrBuildTree (master.c:4249) for one rank; iOpenType = OPEN_JOSH, dCrit = theta (master.c:1897-1934). */
+/* msrBuildTree (master.c:4249) for one rank with any opening criterion of opentype.h:5-9 (dCrit = theta for OPEN_JOSH,
+ * the error bound for OPEN_ABSPAR; master.c:1897-1934). */
+double ref_build_tree_open(REF *r, int nBucket, int iOpenType, double dCrit, int iOrder);
+
+/* ... iOpenType = OPEN_JOSH, dCrit = theta: the default of a run that sets dTheta. */
 double ref_build_tree(REF *r, int nBucket, double dTheta, int iOrder) {
+    return ref_build_tree_open(r, nBucket, OPEN_JOSH, dTheta, iOrder);
+}
+
+double ref_build_tree_open(REF *r, int nBucket, int iOpenType, double dCrit, int iOrder) {
     struct inBuildTree in;
     struct outBuildTree out;
     struct inColCells inc;
@@ -215,9 +223,9 @@ double ref_build_tree(REF *r, int nBucket, double dTheta, int iOrder) {
 
     pkdActiveTypeOrder(r->pkd, TYPE_ACTIVE | TYPE_TREEACTIVE); /* msrActiveTypeOrder, master.c:4263 */
     in.nBucket = nBucket;
-    in.iOpenType = OPEN_JOSH;
+    in.iOpenType = iOpenType;
     in.iOrder = iOrder;
-    in.dCrit = dTheta;
+    in.dCrit = dCrit;
     in.bActiveOnly = 0;
     in.bTreeActiveOnly = 0;
     in.bBinary = 1;

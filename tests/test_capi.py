@@ -3,6 +3,7 @@ GPU (no CPU fallback), and its host-side tree builder reproduces the reference's
 import ctypes as C
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -156,3 +157,59 @@ def test_host_tree_builder_random_configurations(lib, seed):
         if act is not None:
             assert np.array_equal(act, t["active"])
         lib.gg_tree_free(bt)
+
+
+# ---- the opening criteria of pkdCalcOpen other than OPEN_JOSH (pkd.c:2228-2264), pinned to the compiled reference
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import make_golden_opentypes as _ot  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(_ot.CASES))
+def test_host_tree_builder_other_opening_criteria(lib, name):
+    """gg_tree_build_open against tests/golden/opentypes.npz (the reference's pstBuildTree with iOpenType = OPEN_ABSPAR at
+    orders 1-4 -- dRootBracket's hunt and bisection, pkd.c:2182-2224 -- and OPEN_RELPAR / ABSTOT / RELTOT): fOpen2 and the
+    radial moments Bmax, B2..B6 of every cell bit-exact, tree and multipoles as before."""
+    from gasoline_b200 import pkd as pk
+    gen, args, nBucket, iOpenType, dCrit, iOrder, kw = _ot.CASES[name]
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "opentypes.npz"))
+    p, _ = _ot.particles(name)
+    for nthreads in (1, 4):
+        cols = [np.array(a, dtype=np.float64) for a in (p.x, p.y, p.z, p.m, p.h)]
+        order = np.zeros(p.n, np.int32)
+        bt = C.c_void_p()
+        assert lib.gg_tree_build_open(p.n, *[pk._d(c) for c in cols], None, pk._i(order), nBucket, iOpenType, dCrit, iOrder,
+                                      nthreads, C.byref(bt)) == 0
+        v = pk.gg_tree()
+        assert lib.gg_tree_view(bt, C.byref(v), None) == 0
+        nn = v.nNodes
+        assert nn == len(z[f"{name}_tree_fOpen2"])
+        arr = lambda ptr, shape: np.ctypeslib.as_array(ptr, shape=shape)
+        assert np.array_equal(arr(v.fOpen2, (nn,)), z[f"{name}_tree_fOpen2"])
+        bm = np.zeros((nn, 6))
+        assert lib.gg_tree_bnumbers(bt, pk._d(bm)) == 0
+        nb = {1: 3, 2: 4, 3: 5, 4: 6}[iOrder]  # pkdCalcCell initialises B5 / B6 only from octopole / hexadecapole order on
+        assert np.array_equal(bm[:, :nb], z[f"{name}_tree_bmom"][:, :nb])
+        nm = {1: 6, 2: 6, 3: 16, 4: 31}[iOrder]
+        assert np.array_equal(arr(v.mom, (nn, 31))[:, :nm], z[f"{name}_tree_mom"][:, :nm])
+        assert np.array_equal(arr(v.r, (nn, 3)), z[f"{name}_tree_r"])
+        for k in ("pLower", "pUpper", "iLower", "iUpper"):
+            assert np.array_equal(arr(getattr(v, k), (nn,)), z[f"{name}_tree_{k}"]), k
+        assert np.array_equal(order, z[f"{name}_tree_iOrder"])
+        lib.gg_tree_free(bt)
+    if iOpenType == _ot.OPEN_ABSPAR:  # the criterion really differs from theta's
+        josh = (2 / np.sqrt(3.0) * z[f"{name}_tree_bmom"][:, 0] / 0.7) ** 2
+        assert not np.allclose(josh, z[f"{name}_tree_fOpen2"], rtol=1e-3)
+    else:
+        assert np.array_equal(z[f"{name}_tree_fOpen2"], z[f"{name}_tree_bmom"][:, 0] ** 2)
+
+
+def test_abspar_on_a_cell_without_extent_is_an_error_not_a_hang(lib):
+    """A one-particle bucket has Bmax = B_k = 0; the reference's dRootBracket (pkd.c:2182-2224) evaluates 0/0 there and
+    never leaves its hunt loop (observed with oracle/_ref).  The builder reports GG_ERR_UNSUPPORTED instead."""
+    from gasoline_b200 import ics, pkd as pk
+    p = ics.plummer(500, seed=3)
+    cols = [np.array(a, dtype=np.float64) for a in (p.x, p.y, p.z, p.m, p.h)]
+    bt = C.c_void_p()
+    rc = lib.gg_tree_build_open(p.n, *[pk._d(c) for c in cols], None, None, 8, _ot.OPEN_ABSPAR, 1e-3, 4, 2, C.byref(bt))
+    assert rc == -3 and not bt.value
+    assert lib.gg_tree_build_open(p.n, *[pk._d(c) for c in cols], None, None, 8, 6, 0.7, 4, 2, C.byref(bt)) == -2

@@ -131,3 +131,58 @@ def test_device_tree_rebuild_reuses_context(gpu_lib):
         assert np.array_equal(od["acc"], oh["acc"])
         host.close()
     dev.close()
+
+
+# ---- pkdCalcOpen's other opening criteria (pkd.c:2228-2264), against fixtures from the compiled reference
+import os  # noqa: E402
+import sys  # noqa: E402
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import make_golden_opentypes as _ot  # noqa: E402
+from parity import MAX_TOL, RMS_TOL  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(_ot.CASES))
+def test_other_opening_criteria_match_the_reference(name, gpu_lib):
+    """Trees with iOpenType = OPEN_ABSPAR (host builder: dRootBracket at orders 1-4) and OPEN_RELPAR / ABSTOT / RELTOT (host AND
+    device builder) through the CUDA force path, against tests/golden/opentypes.npz: per-bucket list counts and sums
+    bit-exact, forces within the tolerance."""
+    gen, args, nBucket, iOpenType, dCrit, iOrder, kw = _ot.CASES[name]
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "opentypes.npz"))
+    p, _ = _ot.particles(name)
+    g = GravityParams(nReps=kw["nReps"], bPeriodic=kw["bPeriodic"], bEwald=kw["bEwald"], iOrder=iOrder, iEwOrder=iOrder)
+    builds = ["host"] if iOpenType == _ot.OPEN_ABSPAR else ["host", "device"]
+    for how in builds:
+        pkd = PKD(fPeriod=p.period)
+        pkd.pkdLoadParticles(p.x, p.y, p.z, p.m, p.h, None)
+        if how == "host":
+            t = pkd.pkdBuildBinary(nBucket, dCrit, iOrder, iOpenType=iOpenType)
+            assert np.array_equal(t.fOpen2, z[f"{name}_tree_fOpen2"])
+            order = pkd.iOrderMap
+        else:
+            pkd.pkdBuildBinaryDevice(nBucket, dCrit, iOpenType=iOpenType)
+            t, _p = pkd.pkdFetchTree()
+            assert np.array_equal(t.fOpen2, z[f"{name}_tree_fOpen2"])
+            order = pkd.treeOrder
+        assert np.array_equal(order, z[f"{name}_tree_iOrder"])
+        out = pkd.pkdGravAll(g)
+        assert np.array_equal(pkd.pkdBucketCounts(), z[f"{name}_counts"])
+        assert (out["nActive"], out["dPartSum"], out["dCellSum"], out["dSoftSum"], out["dFlop"]) == tuple(z[f"{name}_sums"])
+        ref_a, ref_p = z[f"{name}_acc"], z[f"{name}_pot"]
+        d = np.linalg.norm(out["acc"] - ref_a, axis=1) / np.maximum(np.linalg.norm(ref_a, axis=1),
+                                                                    np.sqrt(np.mean(np.sum(ref_a * ref_a, axis=1))))
+        dp = np.abs(out["pot"] - ref_p) / np.maximum(np.abs(ref_p), np.sqrt(np.mean(ref_p ** 2)))
+        print(f"{name} [{how}]: acc rms {np.sqrt(np.mean(d * d)):.2e} max {d.max():.2e}; pot max {dp.max():.2e}")
+        assert np.sqrt(np.mean(d * d)) <= RMS_TOL and d.max() <= MAX_TOL
+        assert np.sqrt(np.mean(dp * dp)) <= RMS_TOL and dp.max() <= MAX_TOL
+        pkd.close()
+
+
+def test_abspar_is_not_built_on_the_device(gpu_lib):
+    from gasoline_b200.pkd import GasolineB200Error
+    p = ics.plummer(400, seed=3)
+    pkd = PKD(fPeriod=p.period)
+    pkd.pkdLoadParticles(p.x, p.y, p.z, p.m, p.h, None)
+    with pytest.raises(GasolineB200Error, match="OPEN_ABSPAR"):
+        pkd.pkdBuildBinaryDevice(16, 1e-3, iOpenType=_ot.OPEN_ABSPAR)
+    pkd.close()
