@@ -102,7 +102,7 @@ Images make_images(const gg_params *prm) {
             }
         }
     }
-    im.bits = im.n <= 32 ? 5 : (im.n <= 128 ? 7 : 9);
+    im.bits = im.n <= 32 ? 5 : (im.n <= 128 ? 7 : (im.n <= 512 ? 9 : (im.n <= 1024 ? 10 : 11)));
     return im;
 }
 
@@ -1967,7 +1967,7 @@ int run_gravity(gg_context *c, const gg_params *prm, const Task *singleTask, gg_
     if (c->dom.empty()) return gg_fail(GG_ERR_ARG, "gg_gravity: gg_set_local has not been called");
     if (prm->iOrder < 1 || prm->iOrder > 4 || prm->iEwOrder < 0 || prm->iEwOrder > 4)
         return gg_fail(GG_ERR_UNSUPPORTED, "gg_gravity: iOrder=%d iEwOrder=%d (supported 1..4)", prm->iOrder, prm->iEwOrder);
-    if (prm->nReps < 0 || prm->nReps > 3) return gg_fail(GG_ERR_UNSUPPORTED, "gg_gravity: nReps=%d (supported 0..3)", prm->nReps);
+    if (prm->nReps < 0 || prm->nReps > 5) return gg_fail(GG_ERR_UNSUPPORTED, "gg_gravity: nReps=%d (supported 0..5)", prm->nReps);
     CK(cudaSetDevice(c->device));
     if (depth > 0) CK(cudaStreamSynchronize(c->st3)); // a re-run: the previous attempt's k_stats may still be in flight
     const Domain &L = c->dom[0];

@@ -52,7 +52,8 @@ typedef unsigned short gg_mask_t;
 #endif
 #define GG_STACK_CAP 512    // walk frontier entries per warp
 #define GG_STACK_DFS_MARGIN 128
-#define GG_MAX_IMAGES 343    // (2 nReps + 1)^3 images of the tree walk, nReps <= 3
+#define GG_MAX_IMAGES 1331   // (2 nReps + 1)^3 images of the tree walk, nReps <= 5 (11 image bits in a list reference)
+#define GG_SEED_IMAGES 343   // image roots put on a warp's walk frontier at once (all of them up to nReps = 3)
 #define GG_MAX_TOP 128       // top-tree cells (2 x ranks, heap indexed) = spare node records behind the domains' nodes
 
 // The FP32 evaluation record of one cell from the reference's reduced multipoles q[GG_NMOM] (pkdCalcCell order): the

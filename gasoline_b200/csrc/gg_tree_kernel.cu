@@ -298,6 +298,7 @@ struct WalkSmem {
     int head[GG_NLIST][2], fill[GG_NLIST][2], cnt[GG_NLIST][2]; // chain state per list type (0 leaves, 1 soft, 2 Newtonian, 3 big Newtonian) x (shared, masked)
     int own[GG_WALK_GB];        // particles of the bucket itself met in the home image (walk.c:93)
     int bnode[GG_WALK_GB];
+    int seedNext;               // first image whose root has not been put on the frontier yet
 };
 
 __host__ __device__ inline size_t walk_smem_bytes() { return (sizeof(WalkSmem) + 15) & ~(size_t)15; }
@@ -518,14 +519,26 @@ __global__ void __launch_bounds__(GG_WALK_WARPS * 32, GG_WALK_MIN_CTAS) k_walk(c
             (&W.head[0][0])[lane] = -1; (&W.fill[0][0])[lane] = 0; (&W.cnt[0][0])[lane] = 0;
         }
         int myP = 0, myS = 0, myN = 0, myB = 0, myL = 0, sharedP = 0, unused = 0; // lane b: masked entries of bucket b
-        int nStack = A.nImages;
-        for (int i = lane; i < A.nImages; i += 32) {
-            W.stack[i] = ((unsigned)A.rootNode << A.imgBits) | (unsigned)i;
-            W.smask[i] = (gg_mask_t)all;
-        }
+        // the frontier starts with the root under every image offset (walk.c:325-337); more images than GG_SEED_IMAGES
+        // (nReplicas > 3) are seeded in batches, the next one when the frontier has run empty
+        // (the batch cursor lives in shared memory: k_walk has no register to spare for it)
+        int nStack = 0;
+        if (lane == 0) W.seedNext = 0;
         __syncwarp();
-
-        while (nStack > 0) {
+        for (;;) {
+            if (nStack == 0) {
+                const int nextImg = W.seedNext;
+                if (nextImg >= A.nImages) break;
+                const int nSeed = min(GG_SEED_IMAGES, A.nImages - nextImg);
+                for (int i = lane; i < nSeed; i += 32) {
+                    W.stack[i] = ((unsigned)A.rootNode << A.imgBits) | (unsigned)(nextImg + i);
+                    W.smask[i] = (gg_mask_t)all;
+                }
+                nStack = nSeed;
+                __syncwarp();
+                if (lane == 0) W.seedNext = nextImg + nSeed;
+                __syncwarp();
+            }
             int k = min(32, nStack);
             if (nStack > GG_STACK_CAP - GG_STACK_DFS_MARGIN) k = 1; // near the cap: depth-first, growth <= 1 per step
             unsigned item = 0xffffffffu, mask = 0;

@@ -16,6 +16,9 @@ CASES = {
     "periodic10_nreps2_ewald": (lambda: ics.periodic_box(10), 0.7, GravityParams(nReps=2, bPeriodic=1, bEwald=1)),
     "periodic8_nreps3_ewald": (lambda: ics.periodic_box(8), 0.7, GravityParams(nReps=3, bPeriodic=1, bEwald=1)),
     "periodic8_nreps3_noewald": (lambda: ics.periodic_box(8, mode="jitter"), 0.6, GravityParams(nReps=3, bPeriodic=1, bEwald=0)),
+    # nReplicas 4 (729 images, 10 bits) and 5 (1331 images, 11 bits): the walk seeds its frontier in batches of 343 roots
+    "periodic6_nreps4_ewald": (lambda: ics.periodic_box(6, mode="jitter"), 0.7, GravityParams(nReps=4, bPeriodic=1, bEwald=1)),
+    "periodic5_nreps5_noewald": (lambda: ics.periodic_box(5, seed=3), 0.6, GravityParams(nReps=5, bPeriodic=1, bEwald=0)),
     # lower multipole orders of the lists (QEVAL fallthrough, qeval.h:21-64) and of the Ewald root expansion (meval.h:21-81)
     "plummer8k_order1": (lambda: ics.plummer(8000, seed=6), 0.7, GravityParams(nReps=0, bPeriodic=0, bEwald=0, iOrder=1)),
     "plummer8k_order3": (lambda: ics.plummer(8000, seed=6), 0.7, GravityParams(nReps=0, bPeriodic=0, bEwald=0, iOrder=3)),

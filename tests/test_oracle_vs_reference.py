@@ -14,6 +14,9 @@ CASES = {
     "periodic12_theta04": (lambda: ics.periodic_box(12, seed=9), 0.4, dict(nReps=1, bPeriodic=1, bEwald=1)),
     "periodic8_nreps3_ewald": (lambda: ics.periodic_box(8), 0.7, dict(nReps=3, bPeriodic=1, bEwald=1)),
     "periodic10_nreps2_noewald": (lambda: ics.periodic_box(10), 0.7, dict(nReps=2, bPeriodic=1, bEwald=0)),
+    # nReplicas 4 and 5: 729 / 1331 images of the walk; Ewald's image loop and hole follow nReps (ewald.c:54-70)
+    "periodic6_nreps4_ewald": (lambda: ics.periodic_box(6, mode="jitter"), 0.7, dict(nReps=4, bPeriodic=1, bEwald=1)),
+    "periodic5_nreps5_noewald": (lambda: ics.periodic_box(5, seed=3), 0.6, dict(nReps=5, bPeriodic=1, bEwald=0)),
     "plummer8k_order1": (lambda: ics.plummer(8000, seed=6), 0.7, dict(nReps=0, bPeriodic=0, bEwald=0, iOrder=1)),
     "plummer8k_order3": (lambda: ics.plummer(8000, seed=6), 0.7, dict(nReps=0, bPeriodic=0, bEwald=0, iOrder=3)),
     "periodic10_order2_ewald2": (lambda: ics.periodic_box(10), 0.7, dict(nReps=1, bPeriodic=1, bEwald=1, iOrder=2, iEwOrder=2)),
