@@ -32,14 +32,24 @@ struct gg_group {
     const char *sendBase[GG_MAX_RANKS];
     size_t sendOff[GG_MAX_RANKS][GG_MAX_RANKS], sendBytes[GG_MAX_RANKS][GG_MAX_RANKS];
     int dev[GG_MAX_RANKS];
-    void barrier() {
+    // false: a rank of the group gave up (fail()) -- the collective is void and nobody waits for the missing rank
+    bool barrier() {
         std::unique_lock<std::mutex> lk(m);
+        if (failed) return false;
         const unsigned long g = gen;
         if (++arrived == n) {
             arrived = 0;
             ++gen;
             cv.notify_all();
-        } else cv.wait(lk, [&] { return gen != g; });
+        } else cv.wait(lk, [&] { return gen != g || failed; });
+        return !failed;
+    }
+    // a rank that leaves a collective early (an error between two barriers) releases the ranks waiting for it; the group
+    // stays failed: its ranks are out of step and a new group has to be made
+    void fail() {
+        std::lock_guard<std::mutex> lk(m);
+        failed = true;
+        cv.notify_all();
     }
 };
 
@@ -124,9 +134,9 @@ int allgather_host(gg_context *c, const void *mine, size_t bytes, void *all) {
         gg_group *g = m->grp;
         if (bytes > GG_SMALL_BYTES) return gg_fail(GG_ERR_ARG, "gg_comm_allgather: %zu bytes per rank (limit %d)", bytes, GG_SMALL_BYTES);
         memcpy(g->small[m->rank], mine, bytes);
-        g->barrier();
+        if (!g->barrier()) return gg_fail(GG_ERR_ARG, "gg_comm: a rank of the in-process group failed");
         for (int r = 0; r < m->n; ++r) memcpy((char *)all + (size_t)r * bytes, g->small[r], bytes);
-        g->barrier(); // nobody overwrites its slot before everyone has read it
+        if (!g->barrier()) return gg_fail(GG_ERR_ARG, "gg_comm: a rank of the in-process group failed"); // (nobody overwrites its slot before everyone has read it)
         return GG_OK;
     }
     int rc;
@@ -152,7 +162,7 @@ int alltoallv_device(gg_context *c, const char *sendBase, const size_t *sendOff,
         g->sendBase[m->rank] = sendBase;
         g->dev[m->rank] = c->device;
         for (int p = 0; p < m->n; ++p) { g->sendOff[m->rank][p] = sendOff[p]; g->sendBytes[m->rank][p] = sendBytes[p]; }
-        g->barrier();
+        if (!g->barrier()) return gg_fail(GG_ERR_ARG, "gg_exchange: a rank of the in-process group failed");
         cudaError_t e = cudaSuccess;
         for (int p = 0; p < m->n && e == cudaSuccess; ++p) {
             if (p == m->rank || recvBytes[p] == 0) continue;
@@ -161,8 +171,11 @@ int alltoallv_device(gg_context *c, const char *sendBase, const size_t *sendOff,
             else e = cudaMemcpyPeerAsync(recvBase + recvOff[p], c->device, src, g->dev[p], recvBytes[p], c->st);
         }
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->st);
-        g->barrier(); // every rank has pulled its pieces: the send buffers may be reused
-        if (e != cudaSuccess) return gg_fail(GG_ERR_CUDA, "gg_exchange: peer copy failed: %s", cudaGetErrorString(e));
+        if (e != cudaSuccess) {
+            g->fail();
+            return gg_fail(GG_ERR_CUDA, "gg_exchange: peer copy failed: %s", cudaGetErrorString(e));
+        }
+        if (!g->barrier()) return gg_fail(GG_ERR_ARG, "gg_exchange: a rank of the in-process group failed"); // (every rank has pulled its pieces: the send buffers may be reused)
         return GG_OK;
     }
     NCK(g_nccl.GroupStart());
@@ -260,7 +273,16 @@ int gg_comm_allgather(gg_context *c, const void *mine, size_t bytes, void *all) 
     return allgather_host(c, mine, bytes, all);
 }
 
+static int exchange_impl(gg_context *c, const gg_params *prm, const double *bndAll, gg_exchange_stats *stats);
+
 int gg_exchange(gg_context *c, const gg_params *prm, const double *bndAll, gg_exchange_stats *stats) {
+    const int rc = exchange_impl(c, prm, bndAll, stats);
+    // in-process group: the other ranks are (or will be) waiting in this collective's barriers -- let them go
+    if (rc != GG_OK && c && c->comm && c->comm->grp && c->comm->n > 1) c->comm->grp->fail();
+    return rc;
+}
+
+static int exchange_impl(gg_context *c, const gg_params *prm, const double *bndAll, gg_exchange_stats *stats) {
     if (!c || !prm) return gg_fail(GG_ERR_ARG, "gg_exchange: null argument");
     if (!c->comm) return gg_fail(GG_ERR_ARG, "gg_exchange: no communicator (gg_comm_init / gg_comm_init_local)");
     if (c->dom.empty()) return gg_fail(GG_ERR_ARG, "gg_exchange: no local domain (gg_set_local / gg_build_local)");

@@ -436,6 +436,7 @@ __device__ __forceinline__ void sink_box4(const TreeKernelArgs &A, int pLower, i
 // carries the set of buckets that have opened all of its ancestors; the reference's per-bucket opening test
 // (walk.c:81-127) is evaluated for exactly those buckets, short-cut by two conservative tests against the box of
 // the whole group that are monotone in floating point (so they can never disagree with the per-bucket result).
+template <bool SEED_BATCHES>
 __global__ void __launch_bounds__(GG_WALK_WARPS * 32, GG_WALK_MIN_CTAS) k_walk(const TreeKernelArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // the image offsets live behind the warps' walk state, sized by the call's image count (27 in a periodic box)
@@ -519,26 +520,37 @@ __global__ void __launch_bounds__(GG_WALK_WARPS * 32, GG_WALK_MIN_CTAS) k_walk(c
             (&W.head[0][0])[lane] = -1; (&W.fill[0][0])[lane] = 0; (&W.cnt[0][0])[lane] = 0;
         }
         int myP = 0, myS = 0, myN = 0, myB = 0, myL = 0, sharedP = 0, unused = 0; // lane b: masked entries of bucket b
-        // the frontier starts with the root under every image offset (walk.c:325-337); more images than GG_SEED_IMAGES
-        // (nReplicas > 3) are seeded in batches, the next one when the frontier has run empty
-        // (the batch cursor lives in shared memory: k_walk has no register to spare for it)
+        // the frontier starts with the root under every image offset (walk.c:325-337).  More images than GG_SEED_IMAGES
+        // (nReplicas > 3; SEED_BATCHES) are seeded in batches, the next one when the frontier has run empty; the batch
+        // cursor lives in shared memory (k_walk has no register to spare for it).
         int nStack = 0;
-        if (lane == 0) W.seedNext = 0;
-        __syncwarp();
-        for (;;) {
-            if (nStack == 0) {
-                const int nextImg = W.seedNext;
-                if (nextImg >= A.nImages) break;
-                const int nSeed = min(GG_SEED_IMAGES, A.nImages - nextImg);
-                for (int i = lane; i < nSeed; i += 32) {
-                    W.stack[i] = ((unsigned)A.rootNode << A.imgBits) | (unsigned)(nextImg + i);
-                    W.smask[i] = (gg_mask_t)all;
-                }
-                nStack = nSeed;
-                __syncwarp();
-                if (lane == 0) W.seedNext = nextImg + nSeed;
-                __syncwarp();
+        if (SEED_BATCHES) {
+            if (lane == 0) W.seedNext = 0;
+        } else {
+            nStack = A.nImages;
+            for (int i = lane; i < A.nImages; i += 32) {
+                W.stack[i] = ((unsigned)A.rootNode << A.imgBits) | (unsigned)i;
+                W.smask[i] = (gg_mask_t)all;
             }
+        }
+        __syncwarp();
+
+        for (;;) {
+            if (SEED_BATCHES) {
+                if (nStack == 0) {
+                    const int nextImg = W.seedNext;
+                    if (nextImg >= A.nImages) break;
+                    const int nSeed = min(GG_SEED_IMAGES, A.nImages - nextImg);
+                    for (int i = lane; i < nSeed; i += 32) {
+                        W.stack[i] = ((unsigned)A.rootNode << A.imgBits) | (unsigned)(nextImg + i);
+                        W.smask[i] = (gg_mask_t)all;
+                    }
+                    nStack = nSeed;
+                    __syncwarp();
+                    if (lane == 0) W.seedNext = nextImg + nSeed;
+                    __syncwarp();
+                }
+            } else if (nStack <= 0) break;
             int k = min(32, nStack);
             if (nStack > GG_STACK_CAP - GG_STACK_DFS_MARGIN) k = 1; // near the cap: depth-first, growth <= 1 per step
             unsigned item = 0xffffffffu, mask = 0;
@@ -1128,12 +1140,14 @@ static int grid_for(const void *fn, int threads, size_t smem, int nSM, int warps
 
 cudaError_t gg_launch_walk_kernel(const TreeKernelArgs &a, int nSM, cudaStream_t st) {
     const size_t smem = gg_walk_kernel_smem(a.nImages);
-    cudaError_t e = cudaFuncSetAttribute(k_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // more image roots than a frontier takes at once (nReplicas > 3): the instantiation that seeds them in batches
+    void (*fn)(const TreeKernelArgs) = a.nImages > GG_SEED_IMAGES ? k_walk<true> : k_walk<false>;
+    cudaError_t e = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int nGroups = (a.nBuckets + GG_WALK_GB - 1) / GG_WALK_GB;
-    const int grid = grid_for((const void *)k_walk, GG_WALK_WARPS * 32, smem, nSM, GG_WALK_WARPS, nGroups, &e);
+    const int grid = grid_for((const void *)fn, GG_WALK_WARPS * 32, smem, nSM, GG_WALK_WARPS, nGroups, &e);
     if (e != cudaSuccess) return e;
-    k_walk<<<grid, GG_WALK_WARPS * 32, smem, st>>>(a);
+    fn<<<grid, GG_WALK_WARPS * 32, smem, st>>>(a);
     return cudaGetLastError();
 }
 
