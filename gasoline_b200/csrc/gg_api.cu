@@ -741,7 +741,7 @@ void gg_destroy(gg_context *c) {
                      &c->boff64, &c->lists, &c->letflag, &c->letfront, &c->letidx, &c->letout, &c->letmisc, &c->momraw,
                      &c->mparent, &c->dbgtask, &c->momout, &c->sx, &c->sy, &c->sz, &c->sm, &c->sh, &c->sact, &c->svel, &c->sid, &c->sdt,
                      &c->svel2, &c->sid2, &c->sdt2, &c->sacc, &c->srhist, &c->ox, &c->oy, &c->oz, &c->ow, &c->ocell,
-                     &c->okeys, &c->ocnt, &c->opart, &c->osums, &c->obis};
+                     &c->okeys, &c->ocnt, &c->opart, &c->osums, &c->obis, &c->oans};
     for (DevBuf *b : all)
         if (b->p) cudaFree(b->p);
     gg_comm_release(c);
@@ -1202,6 +1202,73 @@ int gg_orb_bisect(gg_context *c, int nCells, const int *iCell, const int *iDim, 
     CK(gg_launch_orb_bisect((OrbBisect *)c->obis.p, h, c->orbN, orb_pos(c, 0), orb_pos(c, 1), orb_pos(c, 2), w,
                             (const int *)c->ocell.p, (int *)c->ocnt.p, (double *)c->opart.p, (double *)c->osums.p, c->st));
     c->nLaunches += 1 + (h.maxIttr + 1) * (w ? 3 : 2);
+    CK(cudaMemcpyAsync(&h, c->obis.p, sizeof(OrbBisect), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    for (int s = 0; s < nCells; ++s) {
+        fSplit[s] = h.q.split[s];
+        bHasSplit[s] = h.hasSplit[s];
+        ittr[s] = h.ittr[s];
+    }
+    return GG_OK;
+}
+
+// COLLECTIVE over the context's communicator: the same root finder when every rank holds PART of the particles.  Per trial
+// each rank weighs its own particles, the ranks' answer records are all-gathered between the devices (in-stream with NCCL:
+// no host round trip per trial either), and every rank's k_orb_decide adds them in rank order -- same bits, same branch,
+// same split on all ranks (pst.c:1004-1030 adds the lower and upper sub-trees' answers the same way).  Every rank passes
+// the same arguments; fSplit / bHasSplit / ittr come back identical everywhere.
+static int orb_bisect_all(gg_context *c, int nCells, const int *iCell, const int *iDim, const double *fLow, const double *fUp,
+                          const int *bLive, const double *nLower, const double *nUpper, int bSplitWork, double *fSplit,
+                          int *bHasSplit, int *ittr);
+
+int gg_orb_bisect_all(gg_context *c, int nCells, const int *iCell, const int *iDim, const double *fLow, const double *fUp,
+                      const int *bLive, const double *nLower, const double *nUpper, int bSplitWork, double *fSplit,
+                      int *bHasSplit, int *ittr) {
+    const int rc = orb_bisect_all(c, nCells, iCell, iDim, fLow, fUp, bLive, nLower, nUpper, bSplitWork, fSplit, bHasSplit, ittr);
+    if (rc != GG_OK) gg_comm_abort(c);
+    return rc;
+}
+
+static int orb_bisect_all(gg_context *c, int nCells, const int *iCell, const int *iDim, const double *fLow, const double *fUp,
+                          const int *bLive, const double *nLower, const double *nUpper, int bSplitWork, double *fSplit,
+                          int *bHasSplit, int *ittr) {
+    if (!c) return gg_fail(GG_ERR_ARG, "gg_orb_bisect_all: null context");
+    const int nRanks = gg_comm_ranks(c);
+    if (nRanks <= 1)
+        return gg_orb_bisect(c, nCells, iCell, iDim, fLow, fUp, bLive, nLower, nUpper, bSplitWork, fSplit, bHasSplit, ittr);
+    if (!iDim || !fLow || !fUp || !bLive || !nLower || !nUpper || !fSplit || !bHasSplit || !ittr)
+        return gg_fail(GG_ERR_ARG, "gg_orb_bisect_all: NULL argument");
+    OrbBisect h;
+    memset(&h, 0, sizeof(h));
+    int rc;
+    if ((rc = orb_query("gg_orb_bisect_all", c, nCells, iCell, iDim, nullptr, h.q))) return rc;
+    for (int s = 0; s < nCells; ++s) {
+        if (!(nLower[s] > 0.0) || !(nUpper[s] > 0.0)) return gg_fail(GG_ERR_ARG, "gg_orb_bisect_all: cell %d has no ranks on one side", iCell[s]);
+        h.fl[s] = fLow[s]; h.fu[s] = fUp[s];
+        h.fmm[s] = (fLow[s] + fUp[s]) / 2;
+        h.nLower[s] = nLower[s]; h.nUpper[s] = nUpper[s];
+        h.live[s] = bLive[s] ? 1 : 0;
+    }
+    h.splitWork = bSplitWork ? 1 : 0;
+    h.maxIttr = 64; // MAX_ITTR, pst.c:874
+    CK(cudaSetDevice(c->device));
+    if ((rc = gg_ensure(c, c->obis, sizeof(OrbBisect)))) return rc;
+    // record 0: this rank's answer (the weighing kernels' sums / cnt point into it); records 1..nRanks: everybody's
+    if ((rc = gg_ensure(c, c->oans, (size_t)GG_ORB_REC_BYTES * (nRanks + 1)))) return rc;
+    unsigned char *mine = (unsigned char *)c->oans.p, *all = mine + GG_ORB_REC_BYTES;
+    double *sums = (double *)mine;
+    int *cnt = (int *)(mine + GG_ORB_REC_CNT);
+    CK(cudaMemsetAsync(mine, 0, (size_t)GG_ORB_REC_BYTES * (nRanks + 1), c->st));
+    const double *w = c->orbWeights ? (const double *)c->ow.p : nullptr;
+    OrbBisect *B = (OrbBisect *)c->obis.p;
+    CK(gg_launch_orb_bisect_begin(B, h, cnt, sums, w != nullptr, c->st));
+    for (int t = 0; t <= h.maxIttr; ++t) { // (every rank queues the same number of collectives)
+        CK(gg_launch_orb_trial(B, h.q.nSlots, c->orbN, orb_pos(c, 0), orb_pos(c, 1), orb_pos(c, 2), w, (const int *)c->ocell.p,
+                               cnt, (double *)c->opart.p, sums, c->st));
+        if ((rc = gg_comm_allgather_dev(c, mine, all, GG_ORB_REC_BYTES))) return rc;
+        CK(gg_launch_orb_decide(B, cnt, sums, w != nullptr, nRanks, all, c->st));
+    }
+    c->nLaunches += 1 + (h.maxIttr + 1) * (w ? 4 : 3);
     CK(cudaMemcpyAsync(&h, c->obis.p, sizeof(OrbBisect), cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
     for (int s = 0; s < nCells; ++s) {

@@ -125,6 +125,39 @@ void gg_comm_release(gg_context *c) {
     c->comm = nullptr;
 }
 
+int gg_comm_ranks(const gg_context *c) { return c && c->comm ? c->comm->n : 1; }
+
+void gg_comm_abort(gg_context *c) {
+    if (c && c->comm && c->comm->grp && c->comm->n > 1) c->comm->grp->fail();
+}
+
+int gg_comm_allgather_dev(gg_context *c, const void *sendDev, void *recvDev, size_t bytes) {
+    GGComm *m = c->comm;
+    if (!m) return gg_fail(GG_ERR_ARG, "gg_comm_allgather_dev: no communicator");
+    if (m->grp) {
+        gg_group *g = m->grp;
+        cudaError_t e = cudaStreamSynchronize(c->st); // this rank's record must be complete before a peer reads it
+        g->sendBase[m->rank] = (const char *)sendDev;
+        g->dev[m->rank] = c->device;
+        if (e != cudaSuccess) g->fail();
+        if (!g->barrier()) return gg_fail(GG_ERR_CUDA, "gg_comm_allgather_dev: a rank of the in-process group failed");
+        for (int r = 0; r < m->n && e == cudaSuccess; ++r) {
+            char *dst = (char *)recvDev + (size_t)r * bytes;
+            if (g->dev[r] == c->device) e = cudaMemcpyAsync(dst, g->sendBase[r], bytes, cudaMemcpyDeviceToDevice, c->st);
+            else e = cudaMemcpyPeerAsync(dst, c->device, g->sendBase[r], g->dev[r], bytes, c->st);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->st);
+        if (e != cudaSuccess) g->fail();
+        if (!g->barrier()) // (every rank has read the records: they may be overwritten)
+            return gg_fail(GG_ERR_CUDA, "gg_comm_allgather_dev: a rank of the in-process group failed (%s)", cudaGetErrorString(e));
+        return GG_OK;
+    }
+    if (!g_nccl.AllGather) return gg_fail(GG_ERR_UNSUPPORTED, "gg_comm_allgather_dev: NCCL is not loaded");
+    ncclResult_t r_ = g_nccl.AllGather(sendDev, recvDev, bytes, ncclChar, m->nccl, c->st);
+    if (r_ != ncclSuccess) return gg_fail(GG_ERR_CUDA, "gg_comm_allgather_dev: NCCL: %s", g_nccl.GetErrorString(r_));
+    return GG_OK;
+}
+
 namespace {
 
 // every rank contributes `bytes` of host memory; all[r * bytes ..] receives rank r's
@@ -278,7 +311,7 @@ static int exchange_impl(gg_context *c, const gg_params *prm, const double *bndA
 int gg_exchange(gg_context *c, const gg_params *prm, const double *bndAll, gg_exchange_stats *stats) {
     const int rc = exchange_impl(c, prm, bndAll, stats);
     // in-process group: the other ranks are (or will be) waiting in this collective's barriers -- let them go
-    if (rc != GG_OK && c && c->comm && c->comm->grp && c->comm->n > 1) c->comm->grp->fail();
+    if (rc != GG_OK) gg_comm_abort(c);
     return rc;
 }
 

@@ -57,7 +57,7 @@ struct gg_context {
     bool stateHasActive = false, stateDirty = true, stateForces = false;
     bool sunMode = false; // run_gravity is evaluating the bDoSun dummy bucket: the particles' results stay as they are
     // ORB domain decomposition services (gg_orb_*): the rank's particles for the decomposition and their PST cell
-    DevBuf ox, oy, oz, ow, ocell, okeys, ocnt, opart, osums, obis;
+    DevBuf ox, oy, oz, ow, ocell, okeys, ocnt, opart, osums, obis, oans;
     int orbN = -1;          // -1: gg_orb_load not called
     bool orbState = false;  // positions are the resident store's (sx, sy, sz)
     bool orbWeights = false;
@@ -117,5 +117,11 @@ int gg_let_export_impl(gg_context *c, int nRemote, const double *bnd, const gg_p
 // ingest one remote domain from device records at src (stream-ordered on c->st; no host synchronisation)
 int gg_ingest_packed(gg_context *c, int id, const int hdr[3], const void *src);
 void gg_comm_release(gg_context *c);
+// ranks of the context's communicator (1 without one), and a small all-gather between DEVICE buffers: rank r's `bytes` at
+// sendDev land at recvDev + r * bytes on every rank -- stream-ordered on c->st with NCCL (no host synchronisation), through
+// the meeting point with the in-process group
+int gg_comm_ranks(const gg_context *c);
+void gg_comm_abort(gg_context *c); // a rank leaves a collective early (error): in-process peers stop waiting for it
+int gg_comm_allgather_dev(gg_context *c, const void *sendDev, void *recvDev, size_t bytes);
 // start the Ewald correction of the resident local domain on the side stream (no-op unless prm asks for one; gg_api.cu)
 int gg_early_ewald(gg_context *c, const gg_params *prm);

@@ -244,6 +244,15 @@ struct OrbBisect {
 // queue the whole bisection on st: B (device) initialised from the host copy h; cnt/part/sums as for gg_launch_orb_weight
 cudaError_t gg_launch_orb_bisect(OrbBisect *B, const OrbBisect &h, int n, const double *x, const double *y, const double *z,
                                  const double *w, const int *cellOf, int *cnt, double *part, double *sums, cudaStream_t st);
+// ... in pieces, for gg_orb_bisect_all (a collective between a trial's weighing and its decision).  One rank's answer to a
+// trial is a record of GG_ORB_REC_BYTES: sums[MAX_SLOTS][2] doubles, then cnt[MAX_SLOTS][2] ints at GG_ORB_REC_CNT.
+#define GG_ORB_REC_CNT (2 * GG_ORB_MAX_SLOTS * 8)
+#define GG_ORB_REC_BYTES (GG_ORB_REC_CNT + 2 * GG_ORB_MAX_SLOTS * 4)
+cudaError_t gg_launch_orb_bisect_begin(OrbBisect *B, const OrbBisect &h, int *cnt, double *sums, int useW, cudaStream_t st);
+cudaError_t gg_launch_orb_trial(OrbBisect *B, int nSlots, int n, const double *x, const double *y, const double *z,
+                                const double *w, const int *cellOf, int *cnt, double *part, double *sums, cudaStream_t st);
+cudaError_t gg_launch_orb_decide(OrbBisect *B, int *cnt, double *sums, int useW, int nRanks, const unsigned char *all,
+                                 cudaStream_t st);
 cudaError_t gg_launch_orb_init(int n, int *cellOf, cudaStream_t st);
 cudaError_t gg_launch_orb_bounds(const OrbQuery &q, int n, const double *x, const double *y, const double *z, const int *cellOf,
                                  unsigned long long *out, int *cnt, cudaStream_t st);

@@ -281,7 +281,11 @@ __global__ void __launch_bounds__(256) k_orb_weight_sum_d(const OrbBisect *B, in
 // One step of the root finder for every cell of the level (one thread per cell): digest the answer to the last trial
 // (pst.c:1001-1030: stop on a one-one split or equal loads, else move the bracket's upper or lower end to the trial),
 // then set up the next one (pst.c:984-999: while the midpoint lies strictly inside the bracket and ittr < MAX_ITTR).
-__global__ void __launch_bounds__(GG_ORB_MAX_SLOTS) k_orb_decide(OrbBisect *B, int *cnt, double *sums, int first, int useW) {
+// Several ranks (gg_orb_bisect_all): `all` holds every rank's answer record (GG_ORB_REC_BYTES each: sums, then counts) as
+// gathered for this trial; the records are added in rank order, so every rank takes the same branch with the same bits --
+// what the reference gets from adding outWtLow and outWtHigh up the rank tree (pst.c:1004-1010).
+__global__ void __launch_bounds__(GG_ORB_MAX_SLOTS) k_orb_decide(OrbBisect *B, int *cnt, double *sums, int first, int useW,
+                                                                 int nRanks, const unsigned char *all) {
     __shared__ int nLive;
     const int s = threadIdx.x;
     if (s == 0) nLive = 0;
@@ -291,8 +295,23 @@ __global__ void __launch_bounds__(GG_ORB_MAX_SLOTS) k_orb_decide(OrbBisect *B, i
         int live = B->live[s];
         double fl = B->fl[s], fu = B->fu[s], fmm = B->fmm[s];
         if (!first && live) {
-            const int nLow = cnt[2 * s], nHigh = cnt[2 * s + 1];
-            const double wl = useW ? sums[2 * s] : (double)nLow, wh = useW ? sums[2 * s + 1] : (double)nHigh;
+            int nLow = cnt[2 * s], nHigh = cnt[2 * s + 1];
+            double wl = useW ? sums[2 * s] : 0.0, wh = useW ? sums[2 * s + 1] : 0.0;
+            if (nRanks > 1) {
+                nLow = nHigh = 0;
+                wl = wh = 0.0;
+                for (int r = 0; r < nRanks; ++r) {
+                    const unsigned char *rec = all + (size_t)r * GG_ORB_REC_BYTES;
+                    const double *rs = reinterpret_cast<const double *>(rec);
+                    const int *rc = reinterpret_cast<const int *>(rec + GG_ORB_REC_CNT);
+                    nLow += rc[2 * s]; nHigh += rc[2 * s + 1];
+                    if (useW) {
+                        wl = r ? __dadd_rn(wl, rs[2 * s]) : rs[2 * s];
+                        wh = r ? __dadd_rn(wh, rs[2 * s + 1]) : rs[2 * s + 1];
+                    }
+                }
+            }
+            if (!useW) { wl = (double)nLow; wh = (double)nHigh; }
             const double a = B->splitWork ? __ddiv_rn(wl, B->nLower[s]) : __ddiv_rn((double)nLow, B->nLower[s]);
             const double b = B->splitWork ? __ddiv_rn(wh, B->nUpper[s]) : __ddiv_rn((double)nHigh, B->nUpper[s]);
             if ((nLow == 1 && nHigh == 1) || a == b) live = 0;
@@ -323,18 +342,38 @@ inline int blocks_for(int n) { return (n + 255) / 256; }
 
 cudaError_t gg_launch_orb_bisect(OrbBisect *B, const OrbBisect &h, int n, const double *x, const double *y, const double *z,
                                  const double *w, const int *cellOf, int *cnt, double *part, double *sums, cudaStream_t st) {
-    cudaError_t e = cudaMemcpyAsync(B, &h, sizeof(OrbBisect), cudaMemcpyHostToDevice, st);
+    cudaError_t e = gg_launch_orb_bisect_begin(B, h, cnt, sums, w != nullptr, st);
     if (e != cudaSuccess) return e;
-    k_orb_decide<<<1, GG_ORB_MAX_SLOTS, 0, st>>>(B, cnt, sums, 1, w != nullptr);
     // MAX_ITTR trials at most; once no cell is live the remaining launches return at their first instruction
     for (int t = 0; t <= h.maxIttr; ++t) {
-        if (n > 0) {
-            const int nb = (n + 256 * GG_ORB_PPT - 1) / (256 * GG_ORB_PPT);
-            k_orb_weight_d<<<nb, 256, 0, st>>>(B, n, x, y, z, w, cellOf, cnt, part);
-            if (w) k_orb_weight_sum_d<<<2 * h.q.nSlots, 256, 0, st>>>(B, nb, part, sums);
-        }
-        k_orb_decide<<<1, GG_ORB_MAX_SLOTS, 0, st>>>(B, cnt, sums, 0, w != nullptr);
+        if ((e = gg_launch_orb_trial(B, h.q.nSlots, n, x, y, z, w, cellOf, cnt, part, sums, st)) != cudaSuccess) return e;
+        if ((e = gg_launch_orb_decide(B, cnt, sums, w != nullptr, 1, nullptr, st)) != cudaSuccess) return e;
     }
+    return cudaGetLastError();
+}
+
+// The pieces of the bisection, for a caller that puts a collective between a trial's weighing and its decision:
+// state to the device + the first trial's set-up; this rank's answer to the current trial; the decision.
+cudaError_t gg_launch_orb_bisect_begin(OrbBisect *B, const OrbBisect &h, int *cnt, double *sums, int useW, cudaStream_t st) {
+    cudaError_t e = cudaMemcpyAsync(B, &h, sizeof(OrbBisect), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    k_orb_decide<<<1, GG_ORB_MAX_SLOTS, 0, st>>>(B, cnt, sums, 1, useW, 1, nullptr);
+    return cudaGetLastError();
+}
+
+cudaError_t gg_launch_orb_trial(OrbBisect *B, int nSlots, int n, const double *x, const double *y, const double *z,
+                                const double *w, const int *cellOf, int *cnt, double *part, double *sums, cudaStream_t st) {
+    if (n > 0) {
+        const int nb = (n + 256 * GG_ORB_PPT - 1) / (256 * GG_ORB_PPT);
+        k_orb_weight_d<<<nb, 256, 0, st>>>(B, n, x, y, z, w, cellOf, cnt, part);
+        if (w) k_orb_weight_sum_d<<<2 * nSlots, 256, 0, st>>>(B, nb, part, sums);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t gg_launch_orb_decide(OrbBisect *B, int *cnt, double *sums, int useW, int nRanks, const unsigned char *all,
+                                 cudaStream_t st) {
+    k_orb_decide<<<1, GG_ORB_MAX_SLOTS, 0, st>>>(B, cnt, sums, 0, useW, nRanks, all);
     return cudaGetLastError();
 }
 

@@ -133,7 +133,8 @@ NEWSPLITDIMCUT = 0.707  # pst.c:1851
 
 
 def pst_domain_decomp(ranks: list, nThreads: int, split_work: bool = True, reduce=None, prev=None,
-                      bDoRootFind: bool = True, bDoSplitDimFind: bool = True, device_bisect: bool | None = None):
+                      bDoRootFind: bool = True, bDoSplitDimFind: bool = True, device_bisect: bool | None = None,
+                      collective_bisect: bool = False):
     """pstDomainDecomp (pst.c:1854-1935) with _pstRootSplit's root finder (pst.c:959-1034) for hosts that are not
     Gasoline: first-call semantics (bDoRootFind = bDoSplitDimFind = 1, master.c:4176; stores with room, so the
     inactive "wrap" split never moves the boundary).  The per-rank work -- bounds, trial weights, the final split --
@@ -151,10 +152,19 @@ def pst_domain_decomp(ranks: list, nThreads: int, split_work: bool = True, reduc
             inside the cell's bounds (pst.c:963; the host sets both to 0 for small active sets, master.c:4210-4222).
     device_bisect: run each level's root finder on the device (gg_orb_bisect: no host round trip per trial).  Default:
             whenever ONE context holds all particles (len(ranks) == 1, no reduce) and offers it.  Same splits, bit for bit.
+    collective_bisect: this process drives ONE rank whose context has a library communicator (commInitNccl /
+            commInitLocal) over all ranks of the decomposition: each level's root finder is gg_orb_bisect_all -- the ranks'
+            answers to a trial travel device to device (in-stream over NCCL), added in rank order like `reduce` does.
+            `reduce` still combines the bounds (orb_reduce_lib keeps that below the C ABI too).
     Returns the interior PST cells as a list of dicts (iCell, iDim, fSplit, bnd, ittr) in level order; the particles'
     destination ranks are leaf_rank(nThreads)[pkd.pkdOrbCells()]."""
     can = len(ranks) == 1 and reduce is None and hasattr(ranks[0], "pkdOrbBisect")
     device_bisect = can if device_bisect is None else (device_bisect and can)
+    if collective_bisect:
+        if len(ranks) != 1 or reduce is None or getattr(ranks[0], "commSize", 0) != nThreads:
+            raise _pkd.GasolineB200Error("pst_domain_decomp: collective_bisect needs one rank per caller, a reduce for the "
+                                         "bounds and a communicator over all nThreads ranks")
+        device_bisect = True
     old = {c["iCell"]: (c["iDim"], c["fSplit"]) for c in prev} if prev else {}
     def combine(kind, parts):
         a = parts[0].copy()
@@ -195,7 +205,8 @@ def pst_domain_decomp(ranks: list, nThreads: int, split_work: bool = True, reduc
         live = np.array([bool(bDoRootFind or not (fl[j] <= fm[j] <= fu[j])) for j in range(k)])
         fm[live] = np.nan
         if device_bisect:
-            fs, has, it = ranks[0].pkdOrbBisect(ic, d, fl, fu, live, nLower, nUpper, split_work)
+            fs, has, it = ranks[0].pkdOrbBisect(ic, d, fl, fu, live, nLower, nUpper, split_work,
+                                                **(dict(collective=True) if collective_bisect else {}))
             fm[has] = fs[has]
             ittr[:] = it
             live[:] = False
@@ -265,6 +276,20 @@ def orb_reduce_dist(backend_device: str):
         g = out.cpu().numpy().reshape((world,) + a.shape)
         r = g[0].copy()
         for k in range(1, world):
+            r = r + g[k] if kind == "sum" else (np.minimum(r, g[k]) if kind == "min" else np.maximum(r, g[k]))
+        return r
+
+    return reduce
+
+
+def orb_reduce_lib(pkd):
+    """The `reduce` of pst_domain_decomp over the library's own communicator (gg_comm_allgather of the small host arrays,
+    NCCL or in-process group), combined in rank order on every rank -- no torch.distributed on the decomposition's path."""
+    def reduce(kind, a):
+        a = np.ascontiguousarray(a)
+        g = pkd.commAllgather(a)
+        r = g[0].copy()
+        for k in range(1, g.shape[0]):
             r = r + g[k] if kind == "sum" else (np.minimum(r, g[k]) if kind == "min" else np.maximum(r, g[k]))
         return r
 
@@ -846,12 +871,15 @@ class _DevView:
         self.t = torch.as_tensor(a, device=dev)
 
 
-def device_orb_share(p, rank: int, world: int, device: int, backend_device: str = "cuda", weights=None, timing=None):
+def device_orb_share(p, rank: int, world: int, device: int, backend_device: str = "cuda", weights=None, timing=None,
+                     collective: bool = False):
     """pstDomainDecomp across the processes of a torch.distributed job, per-rank work on the GPUs: this rank starts with
     a contiguous chunk of `p`, as the reference's ranks start with a contiguous range of the file (pstReadTipsy splits
     the file range down the rank tree, pst.c:676-725; the outcome does not depend on the initial distribution), answers the bisection's questions from its
     device (gg_orb_*), and receives the particles of its domain by one all-to-all.  Returns their indices in `p`,
-    ascending."""
+    ascending.
+    collective: the service context gets a library communicator (NCCL; the id travels by torch.distributed's object
+    broadcast) and every level's bisection is ONE gg_orb_bisect_all -- the trial answers never visit the host."""
     import time as _time
     n = len(p.x)
     lo = rank * (n // world) + min(rank, n % world)
@@ -860,8 +888,16 @@ def device_orb_share(p, rank: int, world: int, device: int, backend_device: str 
     t0 = _time.perf_counter()
     svc = PKD(device=device, fPeriod=p.period)
     svc.pkdOrbLoad(p.x[mine], p.y[mine], p.z[mine], fWeight=None if weights is None else np.asarray(weights)[mine])
+    if collective and world > 1:
+        import torch.distributed as dist
+        ident = [_pkd.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ident, src=0)
+        svc.commInitNccl(ident[0], rank, world)
     t1 = _time.perf_counter()
-    nodes = pst_domain_decomp([svc], world, reduce=orb_reduce_dist(backend_device))
+    if collective and world > 1:
+        nodes = pst_domain_decomp([svc], world, reduce=orb_reduce_lib(svc), collective_bisect=True)
+    else:
+        nodes = pst_domain_decomp([svc], world, reduce=orb_reduce_dist(backend_device))
     dest = leaf_rank(world)[svc.pkdOrbCells()]
     svc.close()
     t2 = _time.perf_counter()

@@ -117,6 +117,7 @@ def load_library(path: str | None = None):
                                       _dp]
     L.gg_set_active.argtypes = [C.c_void_p, _ip]
     L.gg_orb_bisect.argtypes = [C.c_void_p, C.c_int, _ip, _ip, _dp, _dp, _ip, _dp, _dp, C.c_int, _dp, _ip, _ip]
+    L.gg_orb_bisect_all.argtypes = L.gg_orb_bisect.argtypes
     L.gg_build_info.argtypes = [C.c_void_p, _ip, _ip, _dp]
     L.gg_domain_summary.argtypes = [C.c_void_p] + [_dp] * 7
     L.gg_domain_moments_about.argtypes = [C.c_void_p, _dp, _dp, _dp]
@@ -458,16 +459,19 @@ class PKD:
                "gg_orb_weight")
         return nLow, nHigh, fLow, fHigh
 
-    def pkdOrbBisect(self, iCell, iDim, fLow, fUp, live, nLower, nUpper, split_work: bool = True):
+    def pkdOrbBisect(self, iCell, iDim, fLow, fUp, live, nLower, nUpper, split_work: bool = True, collective: bool = False):
         """_pstRootSplit's root finder for all cells of a level with its state on the device (gg_orb_bisect): returns
-        (fSplit, hasSplit, ittr).  Only for a context that holds ALL particles of the decomposition."""
+        (fSplit, hasSplit, ittr).  collective=False: for a context that holds ALL particles of the decomposition.
+        collective=True (gg_orb_bisect_all): every rank of this context's communicator calls it with the same arguments and
+        holds part of the particles; the ranks' answers to a trial are all-gathered between the devices."""
         ic, idim = np.ascontiguousarray(iCell, dtype=np.int32), np.ascontiguousarray(iDim, dtype=np.int32)
         a = [np.ascontiguousarray(v, dtype=np.float64) for v in (fLow, fUp, nLower, nUpper)]
         lv = np.ascontiguousarray(live, dtype=np.int32)
         k = len(ic)
         fs, has, ittr = np.zeros(k), np.zeros(k, np.int32), np.zeros(k, np.int32)
-        _check(self._L.gg_orb_bisect(self._ctx, k, _i(ic), _i(idim), _d(a[0]), _d(a[1]), _i(lv), _d(a[2]), _d(a[3]),
-                                     1 if split_work else 0, _d(fs), _i(has), _i(ittr)), "gg_orb_bisect")
+        fn = self._L.gg_orb_bisect_all if collective else self._L.gg_orb_bisect
+        _check(fn(self._ctx, k, _i(ic), _i(idim), _d(a[0]), _d(a[1]), _i(lv), _d(a[2]), _d(a[3]),
+                  1 if split_work else 0, _d(fs), _i(has), _i(ittr)), "gg_orb_bisect_all" if collective else "gg_orb_bisect")
         return fs, has.astype(bool), ittr
 
     def pkdOrbSplit(self, iCell, iDim, fSplit):

@@ -468,6 +468,13 @@ int gg_orb_fetch(gg_context *ctx, int *iCellOfParticle);
 int gg_orb_bisect(gg_context *ctx, int nCells, const int *iCell, const int *iDim, const double *fLow, const double *fUp,
                   const int *bLive, const double *nLower, const double *nUpper, int bSplitWork, double *fSplit,
                   int *bHasSplit, int *ittr);
+/* COLLECTIVE form for ranks that each hold part of the particles (a communicator from gg_comm_init / gg_comm_init_local):
+ * per trial every rank weighs its own particles, the ranks' answers are all-gathered between the devices (in-stream with
+ * NCCL: no host round trip per trial) and added in rank order on every rank -- the same bits, branch and split everywhere,
+ * as pst.c:1004-1030 adds the answers of the lower and upper sub-trees.  Every rank passes the same arguments. */
+int gg_orb_bisect_all(gg_context *ctx, int nCells, const int *iCell, const int *iDim, const double *fLow, const double *fUp,
+                  const int *bLive, const double *nLower, const double *nUpper, int bSplitWork, double *fSplit,
+                  int *bHasSplit, int *ittr);
 
 /* Every cell's reduced multipoles by the algorithm the DEVICE uses when gg_tree.mom is NULL (raw moments of the
  * buckets, children translated to the parent's centre and summed, then reduced as pkdCalcCell defines them), executed

@@ -225,3 +225,77 @@ def test_bisection_on_the_device_timing():
     print(f"ORB 1 M particles -> 8 domains, {out[True][1]} trials: host-driven loop {out[False][0]:.2f} ms, bisection on the "
           f"device {out[True][0]:.2f} ms")
     assert out[True][1] == out[False][1]
+
+
+def _collective_decomp(p, nThreads, shares, weights=None, **kw):
+    """Every rank a thread with its own context and share of the particles (in-process group): pst_domain_decomp with the
+    bounds through gg_comm_allgather and each level's root finder as ONE gg_orb_bisect_all."""
+    import threading
+    from gasoline_b200 import pkd as _pkd
+    grp = _pkd.Group(nThreads)
+    res, errs = [None] * nThreads, []
+
+    def work(r):
+        try:
+            k = PKD(device=0, fPeriod=p.period)
+            i = shares[r]
+            k.pkdOrbLoad(p.x[i], p.y[i], p.z[i], fWeight=None if weights is None else weights[i])
+            k.commInitLocal(grp, r)
+            nodes = domain.pst_domain_decomp([k], nThreads, reduce=domain.orb_reduce_lib(k), collective_bisect=True, **kw)
+            res[r] = (nodes, k.pkdOrbCells().copy())
+            k.close()
+        except Exception as e:  # noqa: BLE001 -- surfaced below
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(nThreads)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=300)
+    if errs:
+        raise errs[0]
+    assert not any(t.is_alive() for t in th), "a rank did not return from the collective decomposition"
+    return res
+
+
+def test_collective_bisection_equals_the_host_driven_loop():
+    """gg_orb_bisect_all (ranks = threads with an in-process group here; NCCL in a multi-process job) against the host-driven
+    loop over the SAME shares (one thread, the ranks' answers added in rank order on the host): every PST cell's axis, split
+    and trial count and every particle's cell identical -- counts, integer and real work weights, an empty rank, uneven
+    shares, and a later decomposition that starts from the previous axes."""
+    p = ics.plummer(40000, seed=5)
+    rng = np.random.default_rng(8)
+    w_real = rng.uniform(0.5, 40.0, p.n)
+    for nThreads, weights, kw in ((2, None, {}), (3, None, dict(split_work=False)), (4, w_real, {}), (5, w_real, {}),
+                                  (3, rng.integers(1, 9, p.n).astype(np.float64), {})):
+        cuts = np.sort(rng.choice(np.arange(1, p.n), nThreads - 1, replace=False))
+        if nThreads == 5:
+            cuts[1] = cuts[0]  # rank 1 starts with no particles at all
+        shares = np.split(np.arange(p.n), cuts)
+        pkds = [PKD(device=0, fPeriod=p.period) for _ in range(nThreads)]
+        for k, i in zip(pkds, shares):
+            k.pkdOrbLoad(p.x[i], p.y[i], p.z[i], fWeight=None if weights is None else weights[i])
+        ref_nodes = domain.pst_domain_decomp(pkds, nThreads, **kw)
+        ref_cells = [k.pkdOrbCells().copy() for k in pkds]
+        for k in pkds:
+            k.close()
+        got = _collective_decomp(p, nThreads, shares, weights, **kw)
+        for r in range(nThreads):
+            nodes, cells = got[r]
+            assert len(nodes) == len(ref_nodes)
+            for u, v in zip(ref_nodes, nodes):
+                assert (u["iCell"], u["iDim"], u["ittr"]) == (v["iCell"], v["iDim"], v["ittr"]) and u["fSplit"] == v["fSplit"], (r, u, v)
+            assert np.array_equal(cells, ref_cells[r]), f"rank {r} of {nThreads}"
+        if nThreads == 4:  # a later decomposition: previous axes / splits, particles moved
+            q = ics.Particles(p.x + rng.normal(0, 0.02, p.n), p.y, p.z, p.m, p.h, p.period, "moved")
+            pk2 = [PKD(device=0, fPeriod=p.period) for _ in range(nThreads)]
+            for k, i in zip(pk2, shares):
+                k.pkdOrbLoad(q.x[i], q.y[i], q.z[i], fWeight=weights[i])
+            ref2 = domain.pst_domain_decomp(pk2, nThreads, prev=ref_nodes, bDoRootFind=False)
+            ref2_cells = [k.pkdOrbCells().copy() for k in pk2]
+            for k in pk2:
+                k.close()
+            got2 = _collective_decomp(q, nThreads, shares, weights, prev=ref_nodes, bDoRootFind=False)
+            for r in range(nThreads):
+                assert [(u["iDim"], u["fSplit"], u["ittr"]) for u in got2[r][0]] == [(u["iDim"], u["fSplit"], u["ittr"]) for u in ref2]
+                assert np.array_equal(got2[r][1], ref2_cells[r])
