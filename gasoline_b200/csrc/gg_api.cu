@@ -1262,13 +1262,24 @@ static int orb_bisect_all(gg_context *c, int nCells, const int *iCell, const int
     const double *w = c->orbWeights ? (const double *)c->ow.p : nullptr;
     OrbBisect *B = (OrbBisect *)c->obis.p;
     CK(gg_launch_orb_bisect_begin(B, h, cnt, sums, w != nullptr, c->st));
-    for (int t = 0; t <= h.maxIttr; ++t) { // (every rank queues the same number of collectives)
-        CK(gg_launch_orb_trial(B, h.q.nSlots, c->orbN, orb_pos(c, 0), orb_pos(c, 1), orb_pos(c, 2), w, (const int *)c->ocell.p,
-                               cnt, (double *)c->opart.p, sums, c->st));
-        if ((rc = gg_comm_allgather_dev(c, mine, all, GG_ORB_REC_BYTES))) return rc;
-        CK(gg_launch_orb_decide(B, cnt, sums, w != nullptr, nRanks, all, c->st));
+    // Trials are queued GG_ORB_CHUNK at a time without a host synchronisation; between chunks the number of cells still
+    // bisected is read back (the state is identical on every rank, so all ranks stop after the same chunk and have queued
+    // the same collectives).  A trial past the last live cell costs a collective for nothing: the typical 20-50 trials of a
+    // level end after 2-4 chunks instead of MAX_ITTR + 1 rounds.
+    int rounds = 0;
+    for (int t0 = 0; t0 <= h.maxIttr; t0 += GG_ORB_CHUNK) {
+        for (int t = t0; t < t0 + GG_ORB_CHUNK && t <= h.maxIttr; ++t, ++rounds) {
+            CK(gg_launch_orb_trial(B, h.q.nSlots, c->orbN, orb_pos(c, 0), orb_pos(c, 1), orb_pos(c, 2), w,
+                                   (const int *)c->ocell.p, cnt, (double *)c->opart.p, sums, c->st));
+            if ((rc = gg_comm_allgather_dev(c, mine, all, GG_ORB_REC_BYTES))) return rc;
+            CK(gg_launch_orb_decide(B, cnt, sums, w != nullptr, nRanks, all, c->st));
+        }
+        int nLive = 0;
+        CK(cudaMemcpyAsync(&nLive, &B->nLive, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        if (nLive == 0) break;
     }
-    c->nLaunches += 1 + (h.maxIttr + 1) * (w ? 4 : 3);
+    c->nLaunches += 1 + rounds * (w ? 4 : 3);
     CK(cudaMemcpyAsync(&h, c->obis.p, sizeof(OrbBisect), cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
     for (int s = 0; s < nCells; ++s) {

@@ -246,6 +246,7 @@ cudaError_t gg_launch_orb_bisect(OrbBisect *B, const OrbBisect &h, int n, const 
                                  const double *w, const int *cellOf, int *cnt, double *part, double *sums, cudaStream_t st);
 // ... in pieces, for gg_orb_bisect_all (a collective between a trial's weighing and its decision).  One rank's answer to a
 // trial is a record of GG_ORB_REC_BYTES: sums[MAX_SLOTS][2] doubles, then cnt[MAX_SLOTS][2] ints at GG_ORB_REC_CNT.
+#define GG_ORB_CHUNK 16 // trials queued between two looks at the number of live cells (gg_orb_bisect_all)
 #define GG_ORB_REC_CNT (2 * GG_ORB_MAX_SLOTS * 8)
 #define GG_ORB_REC_BYTES (GG_ORB_REC_CNT + 2 * GG_ORB_MAX_SLOTS * 4)
 cudaError_t gg_launch_orb_bisect_begin(OrbBisect *B, const OrbBisect &h, int *cnt, double *sums, int useW, cudaStream_t st);

@@ -893,14 +893,15 @@ def device_orb_share(p, rank: int, world: int, device: int, backend_device: str 
         ident = [_pkd.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ident, src=0)
         svc.commInitNccl(ident[0], rank, world)
+        svc.commAllgather(np.zeros(1))  # NCCL sets its channels up at the first collective: not part of a decomposition
     t1 = _time.perf_counter()
     if collective and world > 1:
         nodes = pst_domain_decomp([svc], world, reduce=orb_reduce_lib(svc), collective_bisect=True)
     else:
         nodes = pst_domain_decomp([svc], world, reduce=orb_reduce_dist(backend_device))
     dest = leaf_rank(world)[svc.pkdOrbCells()]
-    svc.close()
     t2 = _time.perf_counter()
+    svc.close()  # (with a library communicator this tears NCCL down: not part of a decomposition)
     got = orb_exchange(mine.astype(np.float64).reshape(-1, 1), dest, backend_device)
     t3 = _time.perf_counter()
     if timing is not None:
