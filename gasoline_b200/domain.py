@@ -134,7 +134,7 @@ NEWSPLITDIMCUT = 0.707  # pst.c:1851
 
 def pst_domain_decomp(ranks: list, nThreads: int, split_work: bool = True, reduce=None, prev=None,
                       bDoRootFind: bool = True, bDoSplitDimFind: bool = True, device_bisect: bool | None = None,
-                      collective_bisect: bool = False):
+                      collective_bisect: bool = False, stores=None):
     """pstDomainDecomp (pst.c:1854-1935) with _pstRootSplit's root finder (pst.c:959-1034) for hosts that are not
     Gasoline: first-call semantics (bDoRootFind = bDoSplitDimFind = 1, master.c:4176; stores with room, so the
     inactive "wrap" split never moves the boundary).  The per-rank work -- bounds, trial weights, the final split --
@@ -156,8 +156,14 @@ def pst_domain_decomp(ranks: list, nThreads: int, split_work: bool = True, reduc
             commInitLocal) over all ranks of the decomposition: each level's root finder is gg_orb_bisect_all -- the ranks'
             answers to a trial travel device to device (in-stream over NCCL), added in rank order like `reduce` does.
             `reduce` still combines the bounds (orb_reduce_lib keeps that below the C ABI too).
-    Returns the interior PST cells as a list of dicts (iCell, iDim, fSplit, bnd, ittr) in level order; the particles'
-    destination ranks are leaf_rank(nThreads)[pkd.pkdOrbCells()]."""
+    stores: pkd->nStore of every rank (rank_stores) for hosts whose ranks keep the reference's fixed particle stores: the
+            "reverse" split of pst.c:1049-1270 then runs for every cell -- a second boundary fSplitInactive, bisected into the
+            cell when one side's particles would not fit its ranks' stores, and the lower ranks receive the WRAPPED interval
+            between the two boundaries (pkdColRejects -> pkdLowerPartWrap, pkd.c:1165-1211, 1463-1485).  The counts come from
+            pkdWeight; a boundary that really moved needs the ranks' pkdOrbSplitWrap (the host stand-in of the services has it;
+            the device services keep stores sized by need and refuse).  None (default): stores with room.
+    Returns the interior PST cells as a list of dicts (iCell, iDim, fSplit, bnd, ittr[, fSplitInactive, fixed]) in level
+    order; the particles' destination ranks are leaf_rank(nThreads)[pkd.pkdOrbCells()]."""
     can = len(ranks) == 1 and reduce is None and hasattr(ranks[0], "pkdOrbBisect")
     device_bisect = can if device_bisect is None else (device_bisect and can)
     if collective_bisect:
@@ -166,6 +172,7 @@ def pst_domain_decomp(ranks: list, nThreads: int, split_work: bool = True, reduc
                                          "bounds and a communicator over all nThreads ranks")
         device_bisect = True
     old = {c["iCell"]: (c["iDim"], c["fSplit"]) for c in prev} if prev else {}
+    oldInactive = {c["iCell"]: c["fSplitInactive"] for c in prev if "fSplitInactive" in c} if prev else {}
     def combine(kind, parts):
         a = parts[0].copy()
         for b in parts[1:]:
@@ -236,12 +243,134 @@ def pst_domain_decomp(ranks: list, nThreads: int, split_work: bool = True, reduc
                 ittr[j] += 1
         if np.isnan(fm).any():
             raise _pkd.GasolineB200Error("pst_domain_decomp: a PST cell has no extent along its longest axis")
-        for r in ranks:
-            r.pkdOrbSplit(ic, d, fm)
+        extra = [{} for _ in level]
+        if stores is None:
+            for r in ranks:
+                r.pkdOrbSplit(ic, d, fm)
+        else:
+            bmin, bmax = lo[np.arange(k), d], hi[np.arange(k), d]
+
+            def n_low(cells, f):  # particles of the cells with r[d] < f, over all ranks
+                sel = np.asarray(cells, np.int64)
+                got = [r.pkdWeight(ic[sel], d[sel], np.asarray(f, np.float64)) for r in ranks]
+                return combine("sum", [g[0].astype(np.int64) for g in got])
+
+            nIn = combine("sum", [np.asarray(r.pkdCalcBound(ic)[1], np.int64) for r in ranks])
+            nLowSplit = n_low(np.arange(k), fm)
+            fI = np.zeros(k)
+            for j, n in enumerate(level):
+                def count(f, j=j):  # pkdWeightWrap over the ranks: (nLowTot, nHighTot) of the wrapped interval
+                    if f > fm[j]:
+                        nl = int(nLowSplit[j]) + int(nIn[j]) - int(n_low([j], [f])[0])
+                    else:
+                        nl = int(nLowSplit[j]) - int(n_low([j], [f])[0])
+                    return nl, int(nIn[j]) - nl
+                keep = oldInactive.get(int(ic[j])) if not bDoSplitDimFind else None
+                fI[j], fixed = _reverse_split(count, float(fm[j]), float(bmin[j]), float(bmax[j]),
+                                              int(sum(stores[q] for q in n.lower.ranks)), int(sum(stores[q] for q in n.upper.ranks)),
+                                              len(n.lower.ranks), len(n.upper.ranks), keep)
+                extra[j] = dict(fSplitInactive=float(fI[j]), fixed=bool(fixed))
+            plain = (fI > bmax) | (fI <= bmin)  # the wrapped interval is r[d] < fSplit for every particle of the cell
+            if plain.all():
+                for r in ranks:
+                    r.pkdOrbSplit(ic, d, fm)
+            else:
+                for r in ranks:
+                    if not hasattr(r, "pkdOrbSplitWrap"):
+                        raise _pkd.GasolineB200Error(
+                            "pst_domain_decomp: the split of PST cell %d sends a side more particles than its ranks' stores hold "
+                            "(pst.c:1049-1270); the device services keep stores sized by need and have no wrap split -- "
+                            "call without `stores`" % int(ic[np.nonzero(~plain)[0][0]]))
+                    r.pkdOrbSplitWrap(ic, d, fm, fI)
         for j, n in enumerate(level):
             out.append(dict(iCell=n.iCell, iDim=int(d[j]), fSplit=float(fm[j]), bnd=np.concatenate([lo[j], hi[j]]),
-                            ittr=int(ittr[j])))
+                            ittr=int(ittr[j]), **extra[j]))
         level = [c for n in level for c in (n.lower, n.upper)]
+    return out
+
+
+NUM_SAFETY = 4  # pst.c:882 (no STARFORM): minimum margin per rank when a store fills up
+
+
+def _reverse_split(count, fSplit: float, bmin: float, bmax: float, nLowerStore: int, nUpperStore: int, nLower: int, nUpper: int,
+                   prev_inactive=None):
+    """pst.c:1049-1270 for one PST cell: the second boundary fSplitInactive.  count(f) -> (nLowTot, nHighTot) of the wrapped
+    interval between f and fSplit (pstWeightWrap).  Starts just outside the bounds (or from the previous decomposition's
+    value when bDoSplitDimFind = 0, pst.c:1060); when a side holds more than its ranks' stores less a safety margin, the
+    boundary is bisected (midpoints wrap around the cell's extent) until the side fits to within 5 % of the free space.
+    Returns (fSplitInactive, moved into the cell?)."""
+    ext = bmax - bmin
+    nLeaves = nLower + nUpper
+    fl, fu = fSplit + 1e-6 * ext, fSplit - 1e-6 * ext
+
+    def mid(fl, fu):
+        if fu > fl:
+            return 0.5 * (fl + fu)
+        fmm = 0.5 * (fl + fu + ext)
+        return 0.5 * (fl + fu - ext) if fmm > bmax else fmm
+
+    if prev_inactive is not None:
+        fm = prev_inactive
+    else:
+        fm = mid(fl, fu)
+        fm = bmin - 1e-6 * ext if abs(fm - bmin) < abs(fm - bmax) else bmax + 1e-6 * ext
+    nLowTot, nHighTot = count(fm)
+    safety, sloppy = NUM_SAFETY, 2
+    nSafeTot = nLowerStore + nUpperStore - (nLowTot + nHighTot)
+    if nSafeTot <= sloppy * safety * nLeaves:
+        sloppy = 1  # no slop to play with
+    if int(nSafeTot / nLeaves) < safety:
+        safety = int(nSafeTot / nLeaves)
+    margin = max(int(0.05 * nSafeTot / nLeaves), safety)  # only accurate to 5 % of the available space
+    lowSide = nLowTot > nLowerStore - safety * nLower
+    if not lowSide and not nHighTot > nUpperStore - safety * nUpper:
+        return fm, False
+    fm = min(max(fm, bmin), bmax)
+    if lowSide:
+        fl = fm
+    else:
+        fu = fm
+    fmm = mid(fl, fu)
+    for _ in range(1, MAX_ITTR):
+        fm = fmm
+        nLowTot, nHighTot = count(fm)
+        nSide, store, nRanks = (nLowTot, nLowerStore, nLower) if lowSide else (nHighTot, nUpperStore, nUpper)
+        over, under = nSide > store - margin * nRanks, nSide < store - sloppy * margin * nRanks
+        if lowSide:
+            if over or not under:
+                fl = fm
+            else:
+                fu = fm
+        else:
+            if over or not under:
+                fu = fm
+            else:
+                fl = fm
+        if not over and not under:
+            break
+        if fu == fl:
+            break
+        fmm = mid(fl, fu)
+    if (nLowTot if lowSide else nHighTot) > (nLowerStore if lowSide else nUpperStore):
+        raise _pkd.GasolineB200Error("pst_domain_decomp: the particles do not fit the ranks' stores (pst.c:1194 / 1253)")
+    return fm, True
+
+
+def rank_stores(nThreads: int, nTotal: int, fExtraStore: float = 0.1) -> np.ndarray:
+    """pkd->nStore of every rank of a run that read nTotal particles: the file is split down the rank tree (pstReadTipsy,
+    pst.c:676-725: the lower ranks get nLower * (n / nLeaves) particles) and a rank's store holds its share plus
+    ceil(share * dExtraStore) (dExtraStore defaults to 0.1, master.c:883)."""
+    out = np.zeros(nThreads, np.int64)
+
+    def walk(node, n):
+        if node.leaf:
+            out[node.ranks[0]] = n + int(np.ceil(n * fExtraStore))
+            return
+        nl = len(node.lower.ranks) * (n // len(node.ranks))
+        walk(node.lower, nl)
+        walk(node.upper, n - nl)
+
+    walk(pst_tree(nThreads), nTotal)
     return out
 
 

@@ -25,14 +25,19 @@ from oracle import reflib  # noqa: E402
 
 # name -> (generator, args, theta, nThreads, nSteps, dDelta, dExtraStore)
 # dExtraStore = 1: every rank's store has room for what the work-weighted splits send it, so the store-overflow branch of
-# _pstRootSplit (pst.c:1049-1270) never moves a boundary.  The last case keeps the default 0.1: its third decomposition
-# overflows rank 1's store (552 > 550 particles) and the reference falls into that branch -- kept as the witness of what
-# the restatement does NOT cover (tests/test_oracle_orb.py marks it).
+# _pstRootSplit (pst.c:1049-1270) never moves a boundary.  The *_overflow cases run with small stores (the first with the
+# default dExtraStore = 0.1): some of their decompositions send a side more particles than its ranks' stores hold and the
+# reference bisects its second boundary (fSplitInactive) into the cell -- on 2, 3, 5 and 6 ranks, open and periodic, up to
+# four cells of one decomposition.  The restatements reproduce them when given the ranks' stores (rank_stores).
 CASES = {
     "orbsteps_plummer2000_r4": ("plummer", dict(N=2000, seed=5), 0.7, 4, 3, 0.02, 1.0),
     "orbsteps_plummer1500_r3": ("plummer", dict(N=1500, seed=8), 0.7, 3, 2, 0.05, 1.0),
     "orbsteps_periodic10_r2": ("periodic_box", dict(n=10), 0.7, 2, 2, 0.01, 1.0),
     "orbsteps_plummer1500_r3_overflow": ("plummer", dict(N=1500, seed=8), 0.7, 3, 2, 0.05, 0.1),
+    "orbsteps_plummer3000_r5_overflow": ("plummer", dict(N=3000, seed=11), 0.7, 5, 3, 0.05, 0.05),
+    "orbsteps_periodic12_r3_overflow": ("periodic_box", dict(n=12), 0.7, 3, 2, 0.01, 0.01),
+    "orbsteps_plummer1800_r2_overflow": ("plummer", dict(N=1800, seed=2), 0.7, 2, 3, 0.05, 0.02),
+    "orbsteps_plummer2500_r6_overflow": ("plummer", dict(N=2500, seed=9), 0.7, 6, 2, 0.05, 0.06),
 }
 
 
@@ -59,7 +64,10 @@ def run_case(gen, args, theta, nThreads, nSteps, dDelta, dExtraStore):
 
 def main():
     assert os.path.exists(reflib.BIN_PATH), "build oracle/_ref first (make -C oracle ref)"
+    only = sys.argv[1:]  # (names: regenerate just those)
     for name, (gen, args, theta, nThreads, nSteps, dDelta, dExtraStore) in CASES.items():
+        if only and name not in only:
+            continue
         p, steps = run_case(gen, args, theta, nThreads, nSteps, dDelta, dExtraStore)
         assert len(steps) == nSteps + 1, (name, len(steps))
         out = dict(nThreads=nThreads, theta=theta, nSteps=nSteps, dDelta=dDelta, dExtraStore=dExtraStore)

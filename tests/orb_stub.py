@@ -37,5 +37,17 @@ class HostOrbRank:
             m = self.cell == iCell[j]
             self.cell[m] = 2 * iCell[j] + (self.pos[m, iDim[j]] >= fSplit[j])
 
+    def pkdOrbSplitWrap(self, iCell, iDim, fSplit, fSplitInactive):
+        """The outcome of pkdColRejects with a second boundary (pkd.c:1463-1485): the lower child takes the wrapped interval
+        between fSplitInactive and fSplit (pkdLowerPartWrap, pkd.c:1165-1211)."""
+        for j in range(len(iCell)):
+            m = self.cell == iCell[j]
+            c = self.pos[m, iDim[j]]
+            if fSplitInactive[j] > fSplit[j]:
+                low = (c < fSplit[j]) | (c >= fSplitInactive[j])
+            else:
+                low = (c < fSplit[j]) & (c >= fSplitInactive[j])
+            self.cell[m] = 2 * iCell[j] + (~low)
+
     def pkdOrbCells(self):
         return self.cell

@@ -247,36 +247,79 @@ def test_later_decompositions_match_the_stepping_reference(name):
     """Step 0 = the first decomposition (unit weights, no previous split).  Steps >= 1 = what pstDomainDecomp does on every
     later call of a single-rung run: bounds of the moved particles, split axis by the NEWSPLITDIMCUT hysteresis against the
     previous axis (pst.c:1900-1910), bisection from the new bounds with the work weights pkdGravAll left in fWeight
-    (bSplitWork, master.c:964).  Oracle and device-service driver (host stub of the services) against the reference's
-    particle-to-rank assignment, particle for particle."""
+    (bSplitWork, master.c:964).  The *_overflow runs have small particle stores: where a split sends a side more than its
+    ranks' stores hold the reference bisects a second boundary into the cell and the lower ranks receive the wrapped
+    interval between the two (pst.c:1049-1270) -- reproduced when the restatements are given the ranks' stores.  Oracle and
+    device-service driver (host stub of the services) against the reference's particle-to-rank assignment, particle for
+    particle."""
     z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
     nThreads, nSteps = int(z["nThreads"]), int(z["nSteps"])
+    overflow = name.endswith("_overflow")
+    stores = orb_oracle.rank_stores(nThreads, len(z["s0_pos"]), float(z["dExtraStore"])) if overflow else None
+    if overflow:
+        assert np.array_equal(stores, domain.rank_stores(nThreads, len(z["s0_pos"]), float(z["dExtraStore"])))
     prev_o, prev_d = None, None
+    nFixed = nDiffer = 0
     for k in range(nSteps + 1):
         pos, want = z[f"s{k}_pos"], z[f"s{k}_rank"]
         w = None if k == 0 else z[f"s{k - 1}_fWeight"]
-        doms, nodes = orb_oracle.domain_decomp(pos[:, 0], pos[:, 1], pos[:, 2], nThreads, weights=w, prev=prev_o)
+        doms, nodes = orb_oracle.domain_decomp(pos[:, 0], pos[:, 1], pos[:, 2], nThreads, weights=w, prev=prev_o, stores=stores)
         got = np.full(len(pos), -1, np.int32)
         for r, ix in enumerate(doms):
             got[ix] = r
         nbad = int(np.count_nonzero(got != want))
-        if name.endswith("_overflow") and k == nSteps:
-            # the witness: a rank's store (N / nThreads x 1.1 = 550 particles) cannot take the 552 the work-weighted split
-            # sends it, the reference enters the store-overflow branch of _pstRootSplit (pst.c:1049-1270), which is NOT
-            # restated (DESIGN.md: stores with room) -- the outcome must differ, and only then
-            assert nbad > 0 and max(len(d) for d in doms) > int(len(pos) / nThreads * 1.1)
-            return
         assert nbad == 0, f"{name} decomposition {k}: {nbad} particles on another rank than in the reference run"
-        prev_o = {n[0]: (n[1], n[2]) for n in nodes}
+        if overflow:
+            assert np.all(np.bincount(want, minlength=nThreads) <= stores)
+            nFixed += sum(1 for n in nodes if n[5])
+            if any(n[5] for n in nodes):
+                # without the stores the plain split (r[d] < fSplit) decomposes differently: some rank gets more than it holds
+                plain, _ = orb_oracle.domain_decomp(pos[:, 0], pos[:, 1], pos[:, 2], nThreads, weights=w,
+                                                    prev={c: v[:2] for c, v in prev_o.items()} if prev_o else None)
+                assert any(not np.array_equal(a, b) for a, b in zip(plain, doms))
+                nDiffer += 1
+        prev_o = {n[0]: tuple(n[i] for i in ((1, 2, 4) if overflow else (1, 2))) for n in nodes}
         # the driver above the per-rank services (what bench.py / a non-Gasoline host runs), services on 2 host stubs
         owner = np.arange(len(pos)) % 2
         idx = [np.nonzero(owner == s)[0] for s in range(2)]
         ranks = [HostOrbRank(pos[i, 0], pos[i, 1], pos[i, 2], None if w is None else w[i]) for i in idx]
-        cells = domain.pst_domain_decomp(ranks, nThreads, prev=prev_d)
+        cells = domain.pst_domain_decomp(ranks, nThreads, prev=prev_d, stores=stores)
         dest = np.zeros(len(pos), np.int32)
         for i, r in zip(idx, ranks):
             dest[i] = domain.leaf_rank(nThreads)[r.pkdOrbCells()]
         assert np.array_equal(dest, want), f"{name} decomposition {k}: the driver's domains differ from the reference's"
+        if overflow:
+            by = {n[0]: n for n in nodes}
+            for c in cells:
+                assert c["fSplitInactive"] == by[c["iCell"]][4] and c["fixed"] == by[c["iCell"]][5]
         prev_d = cells
+    if overflow:
+        assert nFixed >= 1 and nDiffer >= 1, "the fixture no longer enters the store-overflow branch"
     if nSteps >= 1:  # the work weights really moved the boundaries
         assert not np.array_equal(np.bincount(z["s0_rank"]), np.bincount(z["s1_rank"]))
+
+
+def test_a_store_overflow_is_refused_by_ranks_without_a_wrap_split():
+    """The device services (PKD.pkdOrb*) keep stores sized by need and have no pkdOrbSplitWrap: pst_domain_decomp with
+    `stores` runs the reverse split's counting on them and, when a boundary really moves into a cell, says so instead of
+    decomposing differently from the reference.  (Here: the host stand-in with the method hidden.)"""
+    from gasoline_b200.pkd import GasolineB200Error
+    name = "orbsteps_plummer1800_r2_overflow"
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    nThreads = int(z["nThreads"])
+    stores = domain.rank_stores(nThreads, len(z["s0_pos"]), float(z["dExtraStore"]))
+
+    class NoWrap(HostOrbRank):
+        def __getattribute__(self, a):
+            if a == "pkdOrbSplitWrap":
+                raise AttributeError(a)
+            return super().__getattribute__(a)
+
+    pos, w = z["s1_pos"], z["s0_fWeight"]
+    with pytest.raises(GasolineB200Error, match="stores"):
+        domain.pst_domain_decomp([NoWrap(pos[:, 0], pos[:, 1], pos[:, 2], w)], nThreads, stores=stores)
+    # the first decomposition of the run fits: same call, no complaint, the reference's domains
+    pos0 = z["s0_pos"]
+    r0 = NoWrap(pos0[:, 0], pos0[:, 1], pos0[:, 2])
+    domain.pst_domain_decomp([r0], nThreads, stores=stores)
+    assert np.array_equal(domain.leaf_rank(nThreads)[r0.pkdOrbCells()], z["s0_rank"])
