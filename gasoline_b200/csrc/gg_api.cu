@@ -1304,6 +1304,25 @@ int gg_orb_split(gg_context *c, int nCells, const int *iCell, const int *iDim, c
     return GG_OK;
 }
 
+int gg_orb_split_wrap(gg_context *c, int nCells, const int *iCell, const int *iDim, const double *fSplit,
+                      const double *fSplitInactive) {
+    OrbQuery q;
+    OrbWrap w;
+    int rc;
+    if (!iDim || !fSplit || !fSplitInactive) return gg_fail(GG_ERR_ARG, "gg_orb_split_wrap: NULL argument");
+    if ((rc = orb_query("gg_orb_split_wrap", c, nCells, iCell, iDim, fSplit, q))) return rc;
+    memset(&w, 0, sizeof(w));
+    for (int s = 0; s < nCells; ++s) {
+        if (2 * q.cell[s] + 1 >= GG_ORB_MAX_CELL) return gg_fail(GG_ERR_ARG, "gg_orb_split_wrap: children of PST cell %d exceed %d", q.cell[s], GG_ORB_MAX_CELL - 1);
+        w.inactive[s] = fSplitInactive[s];
+    }
+    CK(cudaSetDevice(c->device));
+    CK(gg_launch_orb_split_wrap(q, w, c->orbN, orb_pos(c, 0), orb_pos(c, 1), orb_pos(c, 2), (int *)c->ocell.p, c->st));
+    ++c->nLaunches;
+    CK(cudaStreamSynchronize(c->st));
+    return GG_OK;
+}
+
 int gg_orb_fetch(gg_context *c, int *iCellOfParticle) {
     if (!c || c->orbN < 0 || !iCellOfParticle) return gg_fail(GG_ERR_ARG, "gg_orb_fetch: no particles loaded (gg_orb_load) or NULL argument");
     CK(cudaSetDevice(c->device));

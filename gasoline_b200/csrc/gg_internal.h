@@ -232,6 +232,9 @@ struct OrbQuery {
     int dim[GG_ORB_MAX_SLOTS];  // split axis
     double split[GG_ORB_MAX_SLOTS];
 };
+struct OrbWrap {
+    double inactive[GG_ORB_MAX_SLOTS]; // fSplitInactive of every cell of the query (gg_orb_split_wrap)
+};
 // The root finder of one level of the rank tree with its state on the device (gg_orb_bisect): _pstRootSplit's bisection
 // (pst.c:959-1034) for all cells of the level at once, no host round trip per trial.
 struct OrbBisect {
@@ -261,4 +264,6 @@ cudaError_t gg_launch_orb_weight(const OrbQuery &q, int n, const double *x, cons
                                  const int *cellOf, int *cnt, double *part, double *sums, cudaStream_t st);
 cudaError_t gg_launch_orb_split(const OrbQuery &q, int n, const double *x, const double *y, const double *z, int *cellOf,
                                 cudaStream_t st);
+cudaError_t gg_launch_orb_split_wrap(const OrbQuery &q, const OrbWrap &w, int n, const double *x, const double *y, const double *z,
+                                     int *cellOf, cudaStream_t st);
 size_t gg_orb_part_bytes(int n);

@@ -179,6 +179,23 @@ __global__ void __launch_bounds__(256) k_orb_split(const OrbQuery Q, int n, cons
     cellOf[i] = 2 * c + (v < Q.split[s] ? 0 : 1); // LOWER / UPPER (pkd.h:78-79)
 }
 
+// The split with a second boundary (the store-overflow outcome of pkdColRejects, pkd.c:1463-1485): the lower child takes
+// the WRAPPED interval between fSplitInactive and fSplit (pkdLowerPartWrap, pkd.c:1165-1211), the upper child the rest.
+__global__ void __launch_bounds__(256) k_orb_split_wrap(const OrbQuery Q, const OrbWrap W, int n, const double *x, const double *y,
+                                                        const double *z, int *cellOf) {
+    __shared__ signed char slotOf[GG_ORB_MAX_CELL];
+    load_slots(Q, slotOf);
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const int c = cellOf[i], s = slotOf[c];
+    if (s < 0) return;
+    const int d = Q.dim[s];
+    const double v = d == 0 ? x[i] : (d == 1 ? y[i] : z[i]);
+    const double fS = Q.split[s], fI = W.inactive[s];
+    const bool low = fI > fS ? (v < fS || v >= fI) : (v < fS && v >= fI);
+    cellOf[i] = 2 * c + (low ? 0 : 1);
+}
+
 // ---- the bisection with its state on the device ---------------------------------------------------------------------
 // k_orb_weight with the query read from the device state: cells that are no longer bisected have no slot
 __global__ void __launch_bounds__(256) k_orb_weight_d(const OrbBisect *B, int n, const double *x, const double *y, const double *z,
@@ -416,6 +433,12 @@ cudaError_t gg_launch_orb_weight(const OrbQuery &q, int n, const double *x, cons
 cudaError_t gg_launch_orb_split(const OrbQuery &q, int n, const double *x, const double *y, const double *z, int *cellOf,
                                 cudaStream_t st) {
     if (n > 0) k_orb_split<<<blocks_for(n), 256, 0, st>>>(q, n, x, y, z, cellOf);
+    return cudaGetLastError();
+}
+
+cudaError_t gg_launch_orb_split_wrap(const OrbQuery &q, const OrbWrap &w, int n, const double *x, const double *y, const double *z,
+                                     int *cellOf, cudaStream_t st) {
+    if (n > 0) k_orb_split_wrap<<<blocks_for(n), 256, 0, st>>>(q, w, n, x, y, z, cellOf);
     return cudaGetLastError();
 }
 

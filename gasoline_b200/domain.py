@@ -160,8 +160,8 @@ def pst_domain_decomp(ranks: list, nThreads: int, split_work: bool = True, reduc
             "reverse" split of pst.c:1049-1270 then runs for every cell -- a second boundary fSplitInactive, bisected into the
             cell when one side's particles would not fit its ranks' stores, and the lower ranks receive the WRAPPED interval
             between the two boundaries (pkdColRejects -> pkdLowerPartWrap, pkd.c:1165-1211, 1463-1485).  The counts come from
-            pkdWeight; a boundary that really moved needs the ranks' pkdOrbSplitWrap (the host stand-in of the services has it;
-            the device services keep stores sized by need and refuse).  None (default): stores with room.
+            pkdWeight; a boundary that really moved is applied by the ranks' pkdOrbSplitWrap (gg_orb_split_wrap).  None
+            (default): stores with room -- what a run with device-resident stores sized by need wants.
     Returns the interior PST cells as a list of dicts (iCell, iDim, fSplit, bnd, ittr[, fSplitInactive, fixed]) in level
     order; the particles' destination ranks are leaf_rank(nThreads)[pkd.pkdOrbCells()]."""
     can = len(ranks) == 1 and reduce is None and hasattr(ranks[0], "pkdOrbBisect")
@@ -279,8 +279,7 @@ def pst_domain_decomp(ranks: list, nThreads: int, split_work: bool = True, reduc
                     if not hasattr(r, "pkdOrbSplitWrap"):
                         raise _pkd.GasolineB200Error(
                             "pst_domain_decomp: the split of PST cell %d sends a side more particles than its ranks' stores hold "
-                            "(pst.c:1049-1270); the device services keep stores sized by need and have no wrap split -- "
-                            "call without `stores`" % int(ic[np.nonzero(~plain)[0][0]]))
+                            "(pst.c:1049-1270) and the ranks' services have no pkdOrbSplitWrap" % int(ic[np.nonzero(~plain)[0][0]]))
                     r.pkdOrbSplitWrap(ic, d, fm, fI)
         for j, n in enumerate(level):
             out.append(dict(iCell=n.iCell, iDim=int(d[j]), fSplit=float(fm[j]), bnd=np.concatenate([lo[j], hi[j]]),

@@ -118,6 +118,7 @@ def load_library(path: str | None = None):
     L.gg_set_active.argtypes = [C.c_void_p, _ip]
     L.gg_orb_bisect.argtypes = [C.c_void_p, C.c_int, _ip, _ip, _dp, _dp, _ip, _dp, _dp, C.c_int, _dp, _ip, _ip]
     L.gg_orb_bisect_all.argtypes = L.gg_orb_bisect.argtypes
+    L.gg_orb_split_wrap.argtypes = [C.c_void_p, C.c_int, _ip, _ip, _dp, _dp]
     L.gg_build_info.argtypes = [C.c_void_p, _ip, _ip, _dp]
     L.gg_domain_summary.argtypes = [C.c_void_p] + [_dp] * 7
     L.gg_domain_moments_about.argtypes = [C.c_void_p, _dp, _dp, _dp]
@@ -478,6 +479,13 @@ class PKD:
         ic, idim = np.ascontiguousarray(iCell, dtype=np.int32), np.ascontiguousarray(iDim, dtype=np.int32)
         fs = np.ascontiguousarray(fSplit, dtype=np.float64)
         _check(self._L.gg_orb_split(self._ctx, len(ic), _i(ic), _i(idim), _d(fs)), "gg_orb_split")
+
+    def pkdOrbSplitWrap(self, iCell, iDim, fSplit, fSplitInactive):
+        """gg_orb_split_wrap: the outcome of pkdColRejects with a second boundary (pkd.c:1463-1485) -- the lower child takes
+        the wrapped interval between fSplitInactive and fSplit (the store-overflow split, pst.c:1049-1270)."""
+        ic, idim = np.ascontiguousarray(iCell, dtype=np.int32), np.ascontiguousarray(iDim, dtype=np.int32)
+        fs, fi = np.ascontiguousarray(fSplit, dtype=np.float64), np.ascontiguousarray(fSplitInactive, dtype=np.float64)
+        _check(self._L.gg_orb_split_wrap(self._ctx, len(ic), _i(ic), _i(idim), _d(fs), _d(fi)), "gg_orb_split_wrap")
 
     def pkdOrbCells(self) -> np.ndarray:
         """The PST cell of every particle, in pkdOrbLoad order."""

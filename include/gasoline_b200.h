@@ -453,6 +453,12 @@ int gg_orb_bounds(gg_context *ctx, int nCells, const int *iCell, double *bnd, in
 int gg_orb_weight(gg_context *ctx, int nCells, const int *iCell, const int *iDim, const double *fSplit, int *nLow,
                   int *nHigh, double *fLow, double *fHigh);
 int gg_orb_split(gg_context *ctx, int nCells, const int *iCell, const int *iDim, const double *fSplit);
+/* The split with a second boundary per cell -- what pkdColRejects leaves when a side's particles do not fit its ranks'
+ * stores (pst.c:1049-1270, pkd.c:1463-1485): the lower child takes the WRAPPED interval between fSplitInactive and fSplit
+ * (pkdLowerPartWrap, pkd.c:1165-1211: r < fSplit or r >= fSplitInactive when fSplitInactive > fSplit, else
+ * fSplitInactive <= r < fSplit), the upper child the rest. */
+int gg_orb_split_wrap(gg_context *ctx, int nCells, const int *iCell, const int *iDim, const double *fSplit,
+                      const double *fSplitInactive);
 int gg_orb_fetch(gg_context *ctx, int *iCellOfParticle);
 /*
  * _pstRootSplit's root finder (pst.c:959-1034) for ALL cells of one level of the rank tree with its state on the device:

@@ -300,9 +300,9 @@ def test_later_decompositions_match_the_stepping_reference(name):
 
 
 def test_a_store_overflow_is_refused_by_ranks_without_a_wrap_split():
-    """The device services (PKD.pkdOrb*) keep stores sized by need and have no pkdOrbSplitWrap: pst_domain_decomp with
-    `stores` runs the reverse split's counting on them and, when a boundary really moves into a cell, says so instead of
-    decomposing differently from the reference.  (Here: the host stand-in with the method hidden.)"""
+    """Ranks whose services have no pkdOrbSplitWrap (a host's own): pst_domain_decomp with `stores` runs the reverse split's
+    counting on them and, when a boundary really moves into a cell, says so instead of decomposing differently from the
+    reference.  (Here: the host stand-in with the method hidden; the device services have gg_orb_split_wrap.)"""
     from gasoline_b200.pkd import GasolineB200Error
     name = "orbsteps_plummer1800_r2_overflow"
     z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
