@@ -136,8 +136,9 @@ def pst_domain_decomp(ranks: list, nThreads: int, split_work: bool = True, reduc
                       bDoRootFind: bool = True, bDoSplitDimFind: bool = True, device_bisect: bool | None = None,
                       collective_bisect: bool = False, stores=None):
     """pstDomainDecomp (pst.c:1854-1935) with _pstRootSplit's root finder (pst.c:959-1034) for hosts that are not
-    Gasoline: first-call semantics (bDoRootFind = bDoSplitDimFind = 1, master.c:4176; stores with room, so the
-    inactive "wrap" split never moves the boundary).  The per-rank work -- bounds, trial weights, the final split --
+    Gasoline: the first call of a run (bDoRootFind = bDoSplitDimFind = 1, master.c:4176) and, with `prev`, the later ones;
+    with `stores` also the second boundary of ranks with fixed particle stores (pst.c:1049-1270).  The per-rank work --
+    bounds, trial weights, the final split --
     is done on the device by every rank's PKD (pkdCalcBound, pkdWeight, pkdOrbSplit after pkdOrbLoad); this function
     only runs the bisection and adds the ranks' answers, level by level of the rank tree with all cells of a level in
     one request (the reference recurses cell by cell; the outcome per cell is the same).
