@@ -32,6 +32,9 @@ def lib():
         L.orc_destroy.argtypes = [C.c_void_p]
         L.orc_build_tree.restype = C.c_double
         L.orc_build_tree.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int]
+        L.orc_build_tree_open.restype = C.c_double
+        L.orc_build_tree_open.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int]
+        L.orc_export_bnumbers.argtypes = [C.c_void_p, _dp]
         L.orc_num_nodes.argtypes = [C.c_void_p]
         L.orc_root.argtypes = [C.c_void_p]
         L.orc_export_nodes.argtypes = [C.c_void_p] + [_dp] * 7 + [_ip] * 5
@@ -137,9 +140,16 @@ class OracleGravity:
             lib().orc_destroy(self.h)
             self.h = None
 
-    def build_tree(self, nBucket=8, theta=0.7, iOrder=4):
-        self.t_build = lib().orc_build_tree(self.h, nBucket, theta, iOrder)
+    def build_tree(self, nBucket=8, theta=0.7, iOrder=4, iOpenType=1):
+        """iOpenType as in opentype.h:5-9 (1 = OPEN_JOSH with dCrit = theta; 2 = OPEN_ABSPAR with dCrit = the error bound)."""
+        self.t_build = lib().orc_build_tree_open(self.h, nBucket, iOpenType, theta, iOrder)
         return self.t_build
+
+    def bnumbers(self):
+        """B2..B6 of every cell of the tree built last (pkdCalcCell, pkd.c:2083-2087): [nNodes][5]."""
+        out = np.zeros((lib().orc_num_nodes(self.h), 5))
+        lib().orc_export_bnumbers(self.h, out)
+        return out
 
     def tree(self):
         L = lib()

@@ -73,3 +73,33 @@ def test_oracle_import_tree_roundtrip():
     b = o2.gravity(1, 1)
     o2.close()
     assert np.array_equal(a["counts"], b["counts"]) and np.array_equal(a["acc"], b["acc"])
+
+
+# ---- the opening criteria of pkdCalcOpen other than OPEN_JOSH (pkd.c:2228-2264)
+import make_golden_opentypes as _ot  # noqa: E402  (tests/golden is on sys.path through golden_cases)
+
+
+@pytest.mark.parametrize("name", sorted(_ot.CASES))
+def test_oracle_opening_criteria_match_reference_fixture(name):
+    """The oracle's tree with iOpenType = OPEN_ABSPAR (dRootBracket at orders 1-4) / OPEN_RELPAR / ABSTOT / RELTOT and the
+    forces that tree gives, against tests/golden/opentypes.npz (the compiled reference): fOpen2 and B2..B6 of every cell,
+    per-bucket list counts and the sums bit-exact."""
+    import os
+    from oracle import oracle
+    gen, args, nBucket, iOpenType, dCrit, iOrder, kw = _ot.CASES[name]
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "opentypes.npz"))
+    p, _ = _ot.particles(name)
+    o = oracle.OracleGravity(p)
+    o.build_tree(nBucket, dCrit, iOrder, iOpenType=iOpenType)
+    t = o.tree()
+    assert np.array_equal(t["fOpen2"], z[f"{name}_tree_fOpen2"])
+    nb = {1: 2, 2: 3, 3: 4, 4: 5}[iOrder]  # (the reference initialises B5 / B6 only from octopole / hexadecapole order on)
+    assert np.array_equal(o.bnumbers()[:, :nb], z[f"{name}_tree_bmom"][:, 1:1 + nb])
+    assert np.array_equal(t["bmax"], z[f"{name}_tree_bmom"][:, 0])
+    assert np.array_equal(t["iOrder"], z[f"{name}_tree_iOrder"])
+    res = o.gravity(kw["nReps"], kw["bPeriodic"], iOrder, kw["bEwald"], iOrder)
+    o.close()
+    assert np.array_equal(res["counts"], z[f"{name}_counts"])
+    assert (res["nActive"], res["dPartSum"], res["dCellSum"], res["dSoftSum"], res["dFlop"]) == tuple(z[f"{name}_sums"])
+    d = np.linalg.norm(res["acc"] - z[f"{name}_acc"], axis=1)
+    assert d.max() <= 1e-9 * np.linalg.norm(z[f"{name}_acc"], axis=1).max()
