@@ -536,7 +536,8 @@ def run_multi(a):
         # device to device over NCCL); GG_ORB_COLLECTIVE=0: the trial answers through torch.distributed and the host
         orb_coll = os.environ.get("GG_ORB_COLLECTIVE", "1") != "0"
         idx = domain.device_orb_share(p, rank, world, local, "cuda", timing=orb, collective=orb_coll)
-        orb["bisection"] = "gg_orb_bisect_all (in-stream NCCL all-gather per trial)" if orb_coll else "host loop, torch.distributed all-gathers per trial"
+        orb["bisection"] = ("gg_orb_bisect_all (in-stream NCCL all-gather per trial)" if orb.get("collective")
+                            else "host loop, torch.distributed all-gathers per trial")
     orb["seconds"] = time.time() - t0
     pkd, exchange = domain.setup_rank(p, theta, rank, world, local, idx=idx)
     t_tree = time.time() - t0 - orb["seconds"]

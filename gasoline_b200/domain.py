@@ -1017,14 +1017,30 @@ def device_orb_share(p, rank: int, world: int, device: int, backend_device: str 
     t0 = _time.perf_counter()
     svc = PKD(device=device, fPeriod=p.period)
     svc.pkdOrbLoad(p.x[mine], p.y[mine], p.z[mine], fWeight=None if weights is None else np.asarray(weights)[mine])
-    if collective and world > 1:
+    collective = bool(collective and world > 1)
+    if collective:
+        import torch
         import torch.distributed as dist
-        ident = [_pkd.comm_unique_id() if rank == 0 else None]
+        ok = 1
+        try:
+            ident = [_pkd.comm_unique_id() if rank == 0 else None]
+        except _pkd.GasolineB200Error:  # (no NCCL to load: every rank then takes the host path together)
+            ident, ok = [None], 0
         dist.broadcast_object_list(ident, src=0)
-        svc.commInitNccl(ident[0], rank, world)
-        svc.commAllgather(np.zeros(1))  # NCCL sets its channels up at the first collective: not part of a decomposition
+        try:
+            if ident[0] is None:
+                ok = 0
+            else:
+                svc.commInitNccl(ident[0], rank, world)
+        except _pkd.GasolineB200Error:
+            ok = 0
+        agreed = torch.tensor([ok], device=backend_device)
+        dist.all_reduce(agreed, op=dist.ReduceOp.MIN)  # all ranks take the same path
+        collective = bool(agreed.item())
+        if collective:
+            svc.commAllgather(np.zeros(1))  # NCCL sets its channels up at the first collective: not part of a decomposition
     t1 = _time.perf_counter()
-    if collective and world > 1:
+    if collective:
         nodes = pst_domain_decomp([svc], world, reduce=orb_reduce_lib(svc), collective_bisect=True)
     else:
         nodes = pst_domain_decomp([svc], world, reduce=orb_reduce_dist(backend_device))
@@ -1035,7 +1051,7 @@ def device_orb_share(p, rank: int, world: int, device: int, backend_device: str 
     t3 = _time.perf_counter()
     if timing is not None:
         timing.update(load_ms=(t1 - t0) * 1e3, decomp_ms=(t2 - t1) * 1e3, exchange_ms=(t3 - t2) * 1e3,
-                      trials=int(sum(c["ittr"] for c in nodes)))
+                      trials=int(sum(c["ittr"] for c in nodes)), collective=collective)
     return np.sort(got[:, 0].astype(np.int64))
 
 

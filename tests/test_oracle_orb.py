@@ -133,6 +133,9 @@ class _Svc(orb_stub.HostOrbRank):
         orb_stub.HostOrbRank.__init__(self, x, y, z, fWeight)
     def close(self):
         pass
+    def commInitNccl(self, ident, rank, world):  # no GPU here: the library communicator cannot be made on rank 1
+        if rank == 1:
+            raise domain._pkd.GasolineB200Error("gg_comm_init failed (test stand-in)")
 domain.PKD = _Svc
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
@@ -140,7 +143,11 @@ p = ics.plummer(3001, seed=8)
 t = {{}}
 idx = domain.device_orb_share(p, rank, world, None, "cpu", timing=t)
 doms, _ = orb_oracle.domain_decomp(p.x, p.y, p.z, world)
-assert np.array_equal(idx, doms[rank]) and t["trials"] > 0
+assert np.array_equal(idx, doms[rank]) and t["trials"] > 0 and t["collective"] is False
+# collective asked for, but one rank cannot join the library communicator: ALL ranks agree on the host path
+t2 = {{}}
+idx2 = domain.device_orb_share(p, rank, world, None, "cpu", timing=t2, collective=True)
+assert np.array_equal(idx2, doms[rank]) and t2["collective"] is False and t2["trials"] == t["trials"]
 dist.destroy_process_group()
 open(os.path.join(os.environ["GG_TEST_OUT"], f"rank{{rank}}.ok"), "w").write("ok")
 """
